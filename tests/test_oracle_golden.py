@@ -1,0 +1,138 @@
+"""Pins the CPU oracle against the reference's own golden outputs.
+
+Fixtures under tests/golden/ were transcribed from /root/reference by tests/golden/make_golden.py.
+
+NOTE on the eigenvalue goldens: all fixtures are reproduced to the printed 6 digits by the
+*power-iteration* estimator with exactly 20 iterations started from deal.II's initial guess
+(v_i = i mod 11 minus mean, constrained DoFs zeroed) in deal.II's default DoF numbering.  The
+reference HEAD sets eig_cg_n_iterations = 40 (include/precondition.templates.h:109) and defaults to
+lanczos for symmetric preconditioners (:113-114); the committed .output files predate both
+settings (every fixture has min ev = max ev / 1.2, the power-iteration signature).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import dasm_oracle as o
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+EST = json.load(open(os.path.join(GOLD, "chebyshev_fdm_estimates.json")))
+
+
+def level_problem(nref, k=3, dtype=np.float64):
+    nc = 2 ** nref
+    mesh = o.StructuredMesh(2, (nc, nc), (False, False), dirichlet=True)
+    cd, nd, order, bnd = o.dealii_numbering_2d(nref, k)
+    mesh.cell_order = order
+    b = o.Basis1D(k)
+    G = o.merged_coefficients(mesh.jacobians(b), b, 2)
+    op = o.LaplaceOperator(2, k, cd, nd, bnd, G, dtype=dtype)
+    return mesh, cd, nd, bnd, op
+
+
+@pytest.mark.parametrize("name,n_overlap,wt", [
+    ("dummy_mg_chebyshev_fdm_1_post", 1, "post"),
+    ("dummy_mg_chebyshev_fdm_1_pre", 1, "pre"),
+    ("dummy_mg_chebyshev_fdm_1_symm", 1, "symm"),
+    ("dummy_mg_chebyshev_fdm_1_none", 1, "none"),
+    ("dummy_mg_chebyshev_fdm_3", 3, "post"),
+])
+def test_fdm_eigenvalue_estimates(name, n_overlap, wt):
+    gold = EST[name]
+    assert len(gold) == 4
+    for nref in range(4):  # levels with 1 / 4 / 16 / 64 cells, 16 / 49 / 169 / 625 DoFs
+        mesh, cd, nd, bnd, op = level_problem(nref)
+        assert nd == (3 * 2 ** nref + 1) ** 2
+        P = o.FDMPreconditioner(mesh, 3, cd, nd, bnd, n_overlap, wt)
+        ch = o.Chebyshev(op, P, degree=1, ev_algorithm="power iteration", eig_cg_n_iterations=20)
+        mn, mx = ch.estimate_eigenvalues()
+        assert mx == pytest.approx(gold[nref]["max"], rel=5e-6), (name, nref)
+        assert mn == pytest.approx(gold[nref]["min"], rel=5e-6), (name, nref)
+
+
+def test_fdm_full_overlap_equals_exact_asm_golden():
+    # dummy_mg_chebyshev_asm.output (matrix-based exact ASM) == dummy_mg_chebyshev_fdm_3.output
+    a, f = EST["dummy_mg_chebyshev_asm"], EST["dummy_mg_chebyshev_fdm_3"]
+    for x, y in zip(a, f):
+        assert x["max"] == pytest.approx(y["max"], rel=1e-5)
+
+
+def test_jacobi_eigenvalue_estimate():
+    gold = EST["dummy_chebyshev_diagonal"][0]
+    mesh, cd, nd, bnd, op = level_problem(3)
+    ch = o.Chebyshev(op, o.JacobiPreconditioner(op), degree=3, ev_algorithm="power iteration", eig_cg_n_iterations=20)
+    mn, mx = ch.estimate_eigenvalues()
+    assert mx == pytest.approx(gold["max"], rel=5e-6)
+    assert mn == pytest.approx(gold["min"], rel=5e-6)
+
+
+def test_fdm_block_equals_restricted_matrix_inverse():
+    """fdm_01.cc:148-177: the FDM patch inverse equals gauss_jordan(R A R^T) on Cartesian meshes."""
+    for n_overlap in (1, 2, 3):
+        mesh, cd, nd, bnd, op = level_problem(2)
+        P = o.FDMPreconditioner(mesh, 3, cd, nd, bnd, n_overlap, "none")
+        A = op.dense()
+        for c in (0, 5, 10, 15):
+            sel = P.mask[c] > 0
+            ii = P.idx[c][sel]
+            Ainv = np.linalg.inv(A[np.ix_(ii, ii)])
+            m = P.m
+            B = np.zeros((len(ii), len(ii)))
+            for j in range(len(ii)):
+                e = np.zeros((mesh.C, m * m))
+                e[c, np.nonzero(sel)[0][j]] = 1.0
+                B[:, j] = P.apply_inverse(e)[c][sel]
+            assert np.allclose(B, Ainv, rtol=1e-9, atol=1e-11)
+
+
+def test_indices_overlap_01():
+    """indices_overlap_01.output: 2-D Q2, 3 refinements, patch DoF lists n_overlap = 0..3."""
+    lines = open(os.path.join(GOLD, "indices_overlap_01.output.txt")).read().split("\n")
+    k, nref = 2, 3
+    cd, nd, order, bnd = o.dealii_numbering_2d(nref, k)
+    nc = 2 ** nref
+    mesh = o.StructuredMesh(2, (nc, nc), (False, False))
+    row = 0
+    for c in order:  # the reference prints cells in active-cell (Morton) order
+        for n_overlap in range(0, k + 2):
+            gold = [int(t) for t in lines[row].split()]
+            row += 1
+            if n_overlap == 0:
+                mine = [int(cd[c].reshape(3, 3)[1, 1])]
+            elif n_overlap > k:
+                continue
+            else:
+                idx = o.patch_dof_indices(mesh, k, cd, n_overlap)[c]
+                mine = [int(i) for i in idx if i != int(o.INVALID)]
+            assert mine == gold, (c, n_overlap)
+        row += 1  # blank line
+
+
+def test_subdivided_hyper_cube_balanced():
+    rows = json.load(open(os.path.join(GOLD, "subdivided_hyper_cube_balanced_01.json")))
+    assert len(rows) >= 40
+    for s, nref, s0, s1, s2, ncells in rows:
+        r, sub = o.decompose_for_subdivided_hyper_cube_balanced(3, s)
+        assert (r, sub) == (nref, [s0, s1, s2])
+        assert float("%.2e" % (np.prod(sub) * 8 ** r)) == pytest.approx(ncells, rel=1e-9)
+
+
+def test_tridiagonal_round_trip():
+    """tridiagonal_01.cc: Thomas solve of tridiag(-1,2,-1), n = 10."""
+    n = 10
+    a = -np.ones(n)
+    b = 2 * np.ones(n)
+    c = -np.ones(n)
+    x = np.arange(1, n + 1, dtype=float)
+    T = np.diag(b) + np.diag(a[1:], -1) + np.diag(c[:-1], 1)
+    assert np.allclose(o.thomas_solve(a, b, c, T @ x), x)
+
+
+def test_compressed_indices_round_trip():
+    for dim, k in ((2, 3), (3, 2), (3, 4)):
+        mesh = o.StructuredMesh(dim, (3,) * dim, (True,) + (False,) * (dim - 1))
+        cd, nd, con, comp = o.number_dofs_first_touch(mesh, k)
+        assert np.array_equal(o.expand_compressed(comp, k, dim), cd)
+        assert sorted(set(cd.reshape(-1).tolist())) == list(range(nd))
