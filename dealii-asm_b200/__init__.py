@@ -1,0 +1,399 @@
+"""Python host-side mirror of the reference's operator / preconditioner interface over libdasm's C ABI.
+
+Class and factory names follow the reference (file:line into the reference tree):
+  LaplaceOperatorMatrixFree      include/operator.h:266-1628
+  ASPoissonPreconditioner        include/matrix_free.h:63-1568
+  PreconditionChebyshev          deal.II class configured in include/precondition.templates.h:89-158
+  create_fdm_preconditioner      include/precondition.templates.h:162-247
+  create_system_preconditioner   include/precondition.templates.h:251-818 (types Chebyshev and FDM)
+The parameter dictionaries use the reference's JSON vocabulary ("n overlap", "weighting type",
+"weight sequence", "degree", "optimize", "smoothing range", "ev algorithm", "polynomial type", ...).
+
+All compute happens in libdasm.so (CUDA, sm_100a).  There is no CPU fallback: importing works
+without a GPU (so symbols can be checked), creating a Context does not.
+PyTorch is used only for device memory (tensors whose data_ptr is handed to the C ABI).
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libdasm.so")
+
+F64, F32 = 0, 1
+WEIGHT = {"none": 0, "pre": 1, "post": 2, "ras": 3, "symm": 4}
+WSEQ = {"global": 0, "local": 1, "dg": 2, "DG": 2, "compressed": 3}
+MAP = {"cartesian": 0, "sine": 1, "kershaw": 2}
+HOOK_NONE, HOOK_ZERO_DST, HOOK_RESIDUAL, HOOK_CHEB_UPDATE, HOOK_SCALE = 0, 1, 2, 3, 4
+
+
+class DasmError(RuntimeError):
+    pass
+
+
+class Hook(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int), ("f1", ctypes.c_double), ("f2", ctypes.c_double),
+                ("v0", ctypes.c_void_p), ("v1", ctypes.c_void_p)]
+
+
+_lib = None
+
+
+def lib():
+    """loads libdasm.so (fails loudly if it was not built: run __graft_entry__.build())."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise DasmError("libdasm.so not built (%s); run `python -c 'import __graft_entry__ as g; g.build()'`" % LIB_PATH)
+        try:
+            import torch  # noqa: F401  (loads the CUDA runtime / NCCL the library links against)
+        except Exception:
+            pass
+        _lib = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
+        _lib.dasm_last_error.restype = ctypes.c_char_p
+        _lib.dasm_version.restype = ctypes.c_char_p
+        _lib.dasm_ctx_stream.restype = ctypes.c_void_p
+        for name in ("dasm_ctx_launch_count", "dasm_mesh_n_cells", "dasm_mesh_n_global_cells", "dasm_op_n_dofs",
+                     "dasm_op_n_ghost", "dasm_op_vec_size", "dasm_op_n_global_dofs", "dasm_op_constrained_dofs",
+                     "dasm_fdm_n_instances", "dasm_fdm_memory_consumption"):
+            getattr(_lib, name).restype = ctypes.c_longlong
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise DasmError(lib().dasm_last_error().decode())
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def decompose_balanced(s):
+    nr = ctypes.c_int()
+    sub = (ctypes.c_int * 3)()
+    _check(lib().dasm_decompose_balanced(int(s), ctypes.byref(nr), sub))
+    return nr.value, list(sub)
+
+
+class Context:
+    def __init__(self, device=0):
+        self.h = ctypes.c_void_p()
+        _check(lib().dasm_ctx_create(int(device), ctypes.byref(self.h)))
+        self.device = device
+
+    def sync(self):
+        _check(lib().dasm_ctx_sync(self.h))
+
+    def launch_count(self):
+        return lib().dasm_ctx_launch_count(self.h)
+
+    def stream_ptr(self):
+        return lib().dasm_ctx_stream(self.h)
+
+    def comm_init(self, n_ranks, rank, id_bytes):
+        buf = (ctypes.c_char * 128).from_buffer_copy(id_bytes)
+        _check(lib().dasm_ctx_comm_init(self.h, int(n_ranks), int(rank), buf))
+
+    @staticmethod
+    def nccl_unique_id():
+        buf = (ctypes.c_char * 128)()
+        _check(lib().dasm_nccl_unique_id(buf))
+        return bytes(buf)
+
+
+class Mesh:
+    """structured hex mesh (hyper-rectangle, optionally sine-deformed or Kershaw)."""
+
+    def __init__(self, ctx, n_cells, periodic=(0, 0, 0), dirichlet=True, length=(1., 1., 1.), map_kind="cartesian",
+                 map_params=(0., 0., 0., 0.), partition=(1, 1, 1), rank=0):
+        self.ctx = ctx
+        self.h = ctypes.c_void_p()
+        self.n_cells_dir = tuple(int(c) for c in n_cells)
+        self.periodic = tuple(int(p) for p in periodic)
+        self.dirichlet = bool(dirichlet)
+        self.length = tuple(float(x) for x in length)
+        self.map_kind = map_kind
+        self.map_params = tuple(map_params)
+        nc = (ctypes.c_int * 3)(*self.n_cells_dir)
+        per = (ctypes.c_int * 3)(*self.periodic)
+        ln = (ctypes.c_double * 3)(*self.length)
+        mp = (ctypes.c_double * 4)(*[float(x) for x in map_params])
+        pt = (ctypes.c_int * 3)(*[int(x) for x in partition])
+        _check(lib().dasm_mesh_create_structured(ctx.h, nc, per, int(bool(dirichlet)), ln, MAP[map_kind], mp, pt, int(rank),
+                                                 ctypes.byref(self.h)))
+
+    @classmethod
+    def hyper_cube_balanced(cls, ctx, n_subdivisions, periodic=True, **kw):
+        """GridGenerator::subdivided_hyper_cube_balanced + refine_global, matrix_free_loop_08.likwid.cc:160-174."""
+        nr, sub = decompose_balanced(n_subdivisions)
+        n_cells = [s * 2 ** nr for s in sub]
+        return cls(ctx, n_cells, periodic=(int(periodic),) * 3, length=[float(s) for s in sub], **kw)
+
+    @property
+    def n_cells(self):
+        return lib().dasm_mesh_n_cells(self.h)
+
+    def cell_coordinates(self):
+        out = np.zeros((self.n_cells, 3), dtype=np.int32)
+        lib().dasm_mesh_cell_coordinates(self.h, out.ctypes.data_as(ctypes.c_void_p))
+        return out
+
+    def __del__(self):
+        try:
+            lib().dasm_mesh_destroy(self.h)
+        except Exception:
+            pass
+
+
+class LaplaceOperatorMatrixFree:
+    """include/operator.h:266-1628."""
+
+    def __init__(self, mesh, degree, number="double", mapping_type="", compress_indices=True):
+        import torch
+        self.mesh = mesh
+        self.ctx = mesh.ctx
+        self.degree = degree
+        self.number = number
+        self.ntype = F64 if number == "double" else F32
+        self.torch_dtype = torch.float64 if number == "double" else torch.float32
+        self.h = ctypes.c_void_p()
+        _check(lib().dasm_op_create(mesh.h, int(degree), self.ntype, mapping_type.encode(), int(compress_indices),
+                                    ctypes.byref(self.h)))
+
+    # -- sizes
+    def n_dofs(self):
+        return lib().dasm_op_n_dofs(self.h)
+
+    def vec_size(self):
+        return lib().dasm_op_vec_size(self.h)
+
+    def m(self):
+        return lib().dasm_op_n_global_dofs(self.h)
+
+    def uses_compressed_indices(self):
+        return bool(lib().dasm_op_uses_compressed_indices(self.h))
+
+    @staticmethod
+    def is_matrix_free():
+        return True
+
+    def is_symmetric(self):
+        return True
+
+    def el(self, i, j):
+        raise NotImplementedError("ExcNotImplemented")  # operator.h:1457-1463
+
+    def Tvmult(self, dst, src):
+        raise NotImplementedError("ExcNotImplemented")  # operator.h:1432-1438
+
+    def initialize_dof_vector(self):
+        import torch
+        return torch.zeros(self.vec_size(), dtype=self.torch_dtype, device="cuda:%d" % self.ctx.device)
+
+    def to_device(self, host_owned):
+        import torch
+        v = torch.zeros(self.vec_size(), dtype=self.torch_dtype)
+        v[: self.n_dofs()] = torch.as_tensor(np.asarray(host_owned)).to(self.torch_dtype)
+        out = v.to("cuda:%d" % self.ctx.device)
+        torch.cuda.synchronize()
+        return out
+
+    def to_host(self, dev):
+        self.ctx.sync()
+        return dev[: self.n_dofs()].double().cpu().numpy()
+
+    # -- operator
+    def vmult(self, dst, src, pre=None, post=None):
+        if pre is None and post is None:
+            _check(lib().dasm_op_vmult(self.h, _ptr(dst), _ptr(src)))
+        else:
+            _check(lib().dasm_op_vmult_hooks(self.h, _ptr(dst), _ptr(src), ctypes.byref(pre) if pre else None,
+                                             ctypes.byref(post) if post else None))
+
+    def compute_inverse_diagonal(self, diag):
+        _check(lib().dasm_op_inverse_diagonal(self.h, _ptr(diag)))
+
+    def compressed_indices(self, plain=False):
+        out = np.zeros((self.mesh.n_cells, 27), dtype=np.uint32)
+        lib().dasm_op_compressed_indices(self.h, int(plain), out.ctypes.data_as(ctypes.c_void_p))
+        return out
+
+    def constrained_dofs(self):
+        n = lib().dasm_op_constrained_dofs(self.h, None)
+        out = np.zeros(n, dtype=np.uint32)
+        if n:
+            lib().dasm_op_constrained_dofs(self.h, out.ctypes.data_as(ctypes.c_void_p))
+        return out
+
+    def merged_coefficients(self, cell):
+        n3 = (self.degree + 1) ** 3
+        out = np.zeros(6 * n3)
+        _check(lib().dasm_op_merged_coefficients(self.h, ctypes.c_longlong(cell), out.ctypes.data_as(ctypes.c_void_p)))
+        return out.reshape(6, n3)
+
+    def __del__(self):
+        try:
+            lib().dasm_op_destroy(self.h)
+        except Exception:
+            pass
+
+
+class ASPoissonPreconditioner:
+    """include/matrix_free.h:63-1568 (element-centred FDM additive Schwarz)."""
+
+    def __init__(self, op, n_overlap=1, sub_mesh_approximation=3, weight_type="post", weight_local_global="global",
+                 overlap_pre_post=True, element_centric=True):
+        self.op = op
+        self.h = ctypes.c_void_p()
+        if weight_type not in WEIGHT:
+            raise DasmError("Weighting type <%s> is not known!" % weight_type)  # precondition.templates.h:24-28
+        if weight_local_global not in WSEQ:
+            raise DasmError("weight sequence <%s> is not known!" % weight_local_global)
+        _check(lib().dasm_fdm_create(op.h, int(n_overlap), int(sub_mesh_approximation), WEIGHT[weight_type],
+                                     WSEQ[weight_local_global], int(overlap_pre_post), int(element_centric),
+                                     ctypes.byref(self.h)))
+
+    def vmult(self, dst, src, pre=None, post=None):
+        if pre is None and post is None:
+            _check(lib().dasm_fdm_vmult(self.h, _ptr(dst), _ptr(src)))
+        else:
+            _check(lib().dasm_fdm_vmult_hooks(self.h, _ptr(dst), _ptr(src), ctypes.byref(pre) if pre else None,
+                                              ctypes.byref(post) if post else None))
+
+    def is_symmetric(self):
+        return bool(lib().dasm_fdm_is_symmetric(self.h))
+
+    def n_fdm_instances(self):
+        return lib().dasm_fdm_n_instances(self.h)
+
+    def memory_consumption(self):
+        return lib().dasm_fdm_memory_consumption(self.h)
+
+    def patch_size_1d(self):
+        return lib().dasm_fdm_patch_size_1d(self.h)
+
+    def weights(self):
+        out = np.zeros(self.op.n_dofs())
+        _check(lib().dasm_fdm_weights(self.h, out.ctypes.data_as(ctypes.c_void_p)))
+        return out
+
+    def instance(self, cell, direction):
+        m = self.patch_size_1d()
+        S = np.zeros((m, m))
+        lam = np.zeros(m)
+        _check(lib().dasm_fdm_instance(self.h, ctypes.c_longlong(cell), int(direction), S.ctypes.data_as(ctypes.c_void_p),
+                                       lam.ctypes.data_as(ctypes.c_void_p)))
+        return S, lam
+
+    def step(self, dst, src):
+        raise NotImplementedError("ExcNotImplemented")  # PreconditionerBase::step default, preconditioners.h:735-741
+
+    def __del__(self):
+        try:
+            lib().dasm_fdm_destroy(self.h)
+        except Exception:
+            pass
+
+
+class PreconditionChebyshev:
+    """deal.II PreconditionChebyshev as configured by create_chebyshev_preconditioner
+    (include/precondition.templates.h:89-158) around an FDM or point-Jacobi (fdm=None) preconditioner."""
+
+    POLY = {"1st kind": 0, "4th kind": 1}
+    EV = {"lanczos": 0, "power iteration": 1, None: 2}
+
+    def __init__(self, op, fdm=None, degree=3, smoothing_range=20., polynomial_type="1st kind", ev_algorithm=None, optimize=2,
+                 eig_cg_n_iterations=40):
+        self.op = op
+        self.fdm = fdm
+        self.degree = degree
+        if polynomial_type not in self.POLY:
+            raise DasmError("Polynomial type <%s> is not known!" % polynomial_type)
+        if ev_algorithm not in self.EV:
+            raise DasmError("Eigen-value algorithm <%s> is not known!" % ev_algorithm)
+        self.h = ctypes.c_void_p()
+        _check(lib().dasm_cheb_create(op.h, fdm.h if fdm is not None else None, int(degree), float(smoothing_range),
+                                      self.POLY[polynomial_type], self.EV[ev_algorithm], int(optimize), int(eig_cg_n_iterations),
+                                      ctypes.byref(self.h)))
+
+    def estimate_eigenvalues(self):
+        mn, mx = ctypes.c_double(), ctypes.c_double()
+        _check(lib().dasm_cheb_estimate_eigenvalues(self.h, ctypes.byref(mn), ctypes.byref(mx)))
+        return mn.value, mx.value
+
+    def set_eigenvalues(self, min_ev, max_ev):
+        _check(lib().dasm_cheb_set_eigenvalues(self.h, float(min_ev), float(max_ev)))
+
+    def vmult(self, dst, src):
+        _check(lib().dasm_cheb_vmult(self.h, _ptr(dst), _ptr(src)))
+
+    def step(self, dst, src):
+        _check(lib().dasm_cheb_step(self.h, _ptr(dst), _ptr(src)))
+
+    def step_host(self, dst_np, src_np):
+        """host-buffer call (float64 numpy arrays of the owned size; dst is updated in place)."""
+        _check(lib().dasm_cheb_step_host(self.h, dst_np.ctypes.data_as(ctypes.c_void_p), src_np.ctypes.data_as(ctypes.c_void_p)))
+
+    def vmult_host(self, dst_np, src_np):
+        _check(lib().dasm_cheb_vmult_host(self.h, dst_np.ctypes.data_as(ctypes.c_void_p), src_np.ctypes.data_as(ctypes.c_void_p)))
+
+    def __del__(self):
+        try:
+            lib().dasm_cheb_destroy(self.h)
+        except Exception:
+            pass
+
+
+# ---- factories (JSON vocabulary of the reference) -----------------------------------------------
+def get_weighting_type(params):
+    """include/precondition.templates.h:10-29."""
+    t = params.get("weighting type", "symm")
+    if t not in WEIGHT:
+        raise DasmError("Weighting type <" + t + "> is not known!")
+    return t
+
+
+def _as_bool(v):
+    if isinstance(v, str):
+        return v.lower() == "true"
+    return bool(v)
+
+
+def create_fdm_preconditioner(op, params):
+    """include/precondition.templates.h:162-247."""
+    n_overlap = min(int(params.get("n overlap", 1)), op.degree)
+    weight_type = get_weighting_type(params)
+    sub_mesh = int(params.get("sub mesh approximation", 3))
+    seq = params.get("weight sequence", "global" if n_overlap > 1 else "compressed")
+    return ASPoissonPreconditioner(op, n_overlap, sub_mesh, weight_type, seq, _as_bool(params.get("overlap pre post", True)),
+                                   _as_bool(params.get("element centric", True)))
+
+
+def create_system_preconditioner(op, params):
+    """include/precondition.templates.h:251-818; the types on the hot path: Chebyshev (around FDM or
+    Diagonal) and FDM.  Other types (AMG, AdditiveSchwarzPreconditioner, ...) are out of scope."""
+    t = params.get("type", "")
+    if t == "Chebyshev":
+        pp = params.get("preconditioner", {})
+        pt = pp.get("type", "")
+        if pt == "":
+            raise DasmError("ExcNotImplemented")
+        if pt == "Diagonal":
+            fdm = None
+            optimize = int(params.get("optimize", 3))
+        elif pt == "FDM":
+            fdm = create_fdm_preconditioner(op, pp)
+            optimize = int(params.get("optimize", 2 if int(pp.get("n overlap", 1)) == 1 else 1))
+        else:
+            raise DasmError("Preconditioner <" + pt + "> is not known!")
+        cheb = PreconditionChebyshev(op, fdm, int(params.get("degree", 3)), float(params.get("smoothing range", 20.)),
+                                     params.get("polynomial type", "1st kind"), params.get("ev algorithm", None), optimize)
+        cheb.estimate_eigenvalues()
+        return cheb
+    if t == "FDM":
+        return create_fdm_preconditioner(op, params)
+    raise DasmError("Preconditioner <" + t + "> is not known!")

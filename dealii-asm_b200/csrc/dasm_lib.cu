@@ -1,0 +1,1922 @@
+// libdasm: C ABI (include/dasm.h) + host orchestration of the CUDA kernels.
+//
+// Host orchestration mirrors the reference's cell-loop schedule MFRunner::loop
+// (include/matrix_free_internal.h:309-359): pre-operation, ghost update, cell kernel, compress(add),
+// post-operation; constrained DoFs get dst = src when a post operation is given (226-255).
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/dasm.h"
+#include "kernels.cuh"
+#include "mesh.h"
+
+using namespace dasm;
+
+// ------------------------------------------------------------------------------------------------
+// error handling
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+#define CUDA_CHECK(expr)                                                                                      \
+  do                                                                                                          \
+    {                                                                                                         \
+      cudaError_t _e = (expr);                                                                                \
+      if (_e != cudaSuccess)                                                                                  \
+        throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " + __FILE__ + ":" + \
+                                 std::to_string(__LINE__));                                                   \
+    }                                                                                                         \
+  while (0)
+
+#define NCCL_CHECK(expr)                                                                                      \
+  do                                                                                                          \
+    {                                                                                                         \
+      ncclResult_t _e = (expr);                                                                               \
+      if (_e != ncclSuccess)                                                                                  \
+        throw std::runtime_error(std::string("NCCL error: ") + ncclGetErrorString(_e) + " at " + __FILE__ + ":" + \
+                                 std::to_string(__LINE__));                                                   \
+    }                                                                                                         \
+  while (0)
+
+#define DASM_API_BEGIN try {
+#define DASM_API_END                      \
+  return 0;                               \
+  }                                       \
+  catch (const std::exception &e)         \
+  {                                       \
+    g_last_error = e.what();              \
+    return 1;                             \
+  }                                       \
+  catch (...)                             \
+  {                                       \
+    g_last_error = "unknown exception";   \
+    return 1;                             \
+  }
+
+#define DASM_REQUIRE(cond, msg)             \
+  do                                        \
+    {                                       \
+      if (!(cond))                          \
+        throw std::runtime_error(msg);      \
+    }                                       \
+  while (0)
+
+// ------------------------------------------------------------------------------------------------
+// objects
+// ------------------------------------------------------------------------------------------------
+struct dasm_ctx
+{
+  int          device   = 0;
+  cudaStream_t stream   = nullptr;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t  ev_a = nullptr, ev_b = nullptr;
+  long long    launches = 0;
+  ncclComm_t   comm     = nullptr;
+  int          n_ranks = 1, rank = 0;
+  double *     d_partial = nullptr; // [1024]
+  double *     d_scalar  = nullptr; // [8]
+  double *     h_scalar  = nullptr; // pinned [8]
+};
+
+struct dasm_mesh
+{
+  dasm_ctx *            ctx;
+  std::unique_ptr<Mesh> mesh;
+};
+
+template <typename T>
+static T *
+dev_alloc(size_t n)
+{
+  T *p = nullptr;
+  CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+  return p;
+}
+
+template <typename T>
+static T *
+dev_upload(const std::vector<T> &v, cudaStream_t)
+{
+  T *p = dev_alloc<T>(v.size());
+  if (!v.empty())
+    CUDA_CHECK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return p;
+}
+
+// ghost exchange (replaces VectorDataExchange, matrix_free_internal.h:3-109)
+struct Exchange
+{
+  dasm_ctx *            ctx = nullptr;
+  std::vector<int>      peers;
+  std::vector<size_t>   send_off, recv_off; // per peer offsets (+ end) in elements
+  uint32_t *            d_send_map = nullptr, *d_recv_map = nullptr;
+  void *                d_send_buf = nullptr, *d_recv_buf = nullptr;
+  size_t                n_send = 0, n_recv = 0;
+  size_t                elem_size = 8;
+
+  void
+  init(dasm_ctx *c, const std::vector<ExchangeList> &lists, size_t esize)
+  {
+    ctx       = c;
+    elem_size = esize;
+    std::vector<uint32_t> smap, rmap;
+    send_off.push_back(0);
+    recv_off.push_back(0);
+    for (const auto &l : lists)
+      {
+        peers.push_back(l.peer);
+        for (size_t i = 0; i < l.send_start.size(); ++i)
+          for (uint32_t t = 0; t < l.send_len[i]; ++t)
+            smap.push_back(l.send_start[i] + t);
+        for (size_t i = 0; i < l.recv_start.size(); ++i)
+          for (uint32_t t = 0; t < l.recv_len[i]; ++t)
+            rmap.push_back(l.recv_start[i] + t);
+        send_off.push_back(smap.size());
+        recv_off.push_back(rmap.size());
+      }
+    n_send     = smap.size();
+    n_recv     = rmap.size();
+    d_send_map = dev_upload(smap, nullptr);
+    d_recv_map = dev_upload(rmap, nullptr);
+    CUDA_CHECK(cudaMalloc(&d_send_buf, std::max<size_t>(std::max(n_send, n_recv), 1) * elem_size));
+    CUDA_CHECK(cudaMalloc(&d_recv_buf, std::max<size_t>(std::max(n_send, n_recv), 1) * elem_size));
+  }
+
+  bool
+  active() const
+  {
+    return !peers.empty();
+  }
+
+  // owner -> ghost (update_ghost_values) or ghost -> owner with add (compress)
+  template <typename T>
+  void
+  run(T *vec, bool compress)
+  {
+    if (!active())
+      return;
+    DASM_REQUIRE(ctx->comm != nullptr, "multi-rank mesh needs dasm_ctx_comm_init before any operator application");
+    cudaStream_t    s     = ctx->stream;
+    const size_t    n_out = compress ? n_recv : n_send;
+    const size_t    n_in  = compress ? n_send : n_recv;
+    const uint32_t *omap  = compress ? d_recv_map : d_send_map;
+    const uint32_t *imap  = compress ? d_send_map : d_recv_map;
+    const auto &    ooff  = compress ? recv_off : send_off;
+    const auto &    ioff  = compress ? send_off : recv_off;
+    if (n_out)
+      {
+        pack_kernel<T><<<(unsigned)((n_out + 255) / 256), 256, 0, s>>>((T *)d_send_buf, vec, omap, (long long)n_out);
+        ctx->launches++;
+      }
+    NCCL_CHECK(ncclGroupStart());
+    for (size_t pidx = 0; pidx < peers.size(); ++pidx)
+      {
+        const size_t so = ooff[pidx], sn = ooff[pidx + 1] - so;
+        const size_t ro = ioff[pidx], rn = ioff[pidx + 1] - ro;
+        if (sn)
+          NCCL_CHECK(ncclSend((const char *)d_send_buf + so * sizeof(T), sn * sizeof(T), ncclChar, peers[pidx], ctx->comm, s));
+        if (rn)
+          NCCL_CHECK(ncclRecv((char *)d_recv_buf + ro * sizeof(T), rn * sizeof(T), ncclChar, peers[pidx], ctx->comm, s));
+      }
+    NCCL_CHECK(ncclGroupEnd());
+    if (n_in)
+      {
+        if (compress)
+          unpack_kernel<T, true><<<(unsigned)((n_in + 255) / 256), 256, 0, s>>>(vec, (const T *)d_recv_buf, imap, (long long)n_in);
+        else
+          unpack_kernel<T, false><<<(unsigned)((n_in + 255) / 256), 256, 0, s>>>(vec, (const T *)d_recv_buf, imap, (long long)n_in);
+        ctx->launches++;
+      }
+  }
+
+  void
+  destroy()
+  {
+    cudaFree(d_send_map);
+    cudaFree(d_recv_map);
+    cudaFree(d_send_buf);
+    cudaFree(d_recv_buf);
+  }
+};
+
+struct dasm_op
+{
+  dasm_ctx *        ctx;
+  dasm_mesh *       mesh;
+  int               k;
+  int               ntype;
+  bool              compress_indices;
+  std::string       mapping_type;
+  Basis1D           basis;
+  Mesh::Numbering   nb;
+  long long         n_cells;
+  long long         n_owned, n_ghost, n_vec;
+  long long         n_global_dofs;
+  uint32_t *        d_cidx        = nullptr;
+  uint32_t *        d_constrained = nullptr;
+  long long         n_constrained = 0;
+  int               geom_mode     = 0; // 0 cartesian, 1 merged
+  void *            d_geom        = nullptr;
+  CartesianCoef     cart;
+  Exchange          exchange;
+  std::vector<void *> scratch; // owned by op, freed at destroy
+
+  dasm_op(int degree)
+    : basis(degree)
+  {}
+  size_t
+  esize() const
+  {
+    return ntype == DASM_F64 ? 8 : 4;
+  }
+};
+
+struct dasm_fdm
+{
+  dasm_op * op;
+  int       n_overlap, weight_type, weight_sequence, element_centric;
+  int       m;          // 1-D patch size
+  long long n_instances; // unique 1-D (S, lambda) instances
+  uint32_t *d_inst   = nullptr;
+  void *    d_S      = nullptr;
+  void *    d_lam    = nullptr;
+  void *    d_wvec   = nullptr; // global weight vector (owned+ghost)
+  void *    d_cw     = nullptr; // compressed weights [cell][27] or per-entry [cell][m^3]
+  uint32_t *d_pidx   = nullptr; // explicit patch index list for n_overlap > 1
+  int       wmode    = 0;       // kernel weight mode
+  bool      w_pre = false, w_post = false;
+  std::vector<double>   h_S, h_lam; // double copies for inspection
+  std::vector<uint32_t> h_inst;
+  std::vector<double>   h_weights;
+};
+
+struct dasm_cheb
+{
+  dasm_op * op;
+  dasm_fdm *fdm;
+  int       degree, poly, ev_algo, optimize, n_ev_it;
+  double    smoothing_range;
+  bool      ev_ready = false;
+  double    min_ev = 0, max_ev = 0, delta = 0, theta = 0;
+  void *    d_inv_diag = nullptr;
+  void *    t1 = nullptr, *t2 = nullptr, *xold = nullptr, *xin = nullptr, *bin = nullptr;
+};
+
+// ------------------------------------------------------------------------------------------------
+// dispatch helpers
+// ------------------------------------------------------------------------------------------------
+#define DISPATCH_DEGREE(k, ...)                                         \
+  switch (k)                                                            \
+    {                                                                   \
+      case 1: { constexpr int K = 1; __VA_ARGS__; } break;              \
+      case 2: { constexpr int K = 2; __VA_ARGS__; } break;              \
+      case 3: { constexpr int K = 3; __VA_ARGS__; } break;              \
+      case 4: { constexpr int K = 4; __VA_ARGS__; } break;              \
+      case 5: { constexpr int K = 5; __VA_ARGS__; } break;              \
+      case 6: { constexpr int K = 6; __VA_ARGS__; } break;              \
+      case 7: { constexpr int K = 7; __VA_ARGS__; } break;              \
+      case 8: { constexpr int K = 8; __VA_ARGS__; } break;              \
+      default: throw std::runtime_error("degree must be in 1..8");      \
+    }
+
+#define DISPATCH_PATCH(m, ...)                                                        \
+  switch (m)                                                                          \
+    {                                                                                 \
+      case 2: { constexpr int M = 2; __VA_ARGS__; } break;                            \
+      case 3: { constexpr int M = 3; __VA_ARGS__; } break;                            \
+      case 4: { constexpr int M = 4; __VA_ARGS__; } break;                            \
+      case 5: { constexpr int M = 5; __VA_ARGS__; } break;                            \
+      case 6: { constexpr int M = 6; __VA_ARGS__; } break;                            \
+      case 7: { constexpr int M = 7; __VA_ARGS__; } break;                            \
+      case 8: { constexpr int M = 8; __VA_ARGS__; } break;                            \
+      case 9: { constexpr int M = 9; __VA_ARGS__; } break;                            \
+      case 10: { constexpr int M = 10; __VA_ARGS__; } break;                          \
+      case 11: { constexpr int M = 11; __VA_ARGS__; } break;                          \
+      default: throw std::runtime_error("patch size " + std::to_string(m) + " not instantiated"); \
+    }
+
+#define DISPATCH_TYPE(ntype, ...)                 \
+  if (ntype == DASM_F64)                          \
+    {                                             \
+      using T = double;                           \
+      __VA_ARGS__;                                \
+    }                                             \
+  else                                            \
+    {                                             \
+      using T = float;                            \
+      __VA_ARGS__;                                \
+    }
+
+static inline unsigned
+nblocks(long long n, int bs = 256)
+{
+  return (unsigned)((n + bs - 1) / bs);
+}
+
+// ------------------------------------------------------------------------------------------------
+// vector helpers
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+static double
+device_dot(dasm_ctx *ctx, const T *a, const T *b, long long n)
+{
+  const int nb = (int)std::min<long long>(1024, std::max<long long>(1, (n + 255) / 256));
+  vec_dot_kernel<T><<<nb, 256, 0, ctx->stream>>>(a, b, ctx->d_partial, n);
+  reduce_partials_kernel<<<1, 256, 0, ctx->stream>>>(ctx->d_partial, ctx->d_scalar, nb);
+  ctx->launches += 2;
+  if (ctx->n_ranks > 1 && ctx->comm)
+    NCCL_CHECK(ncclAllReduce(ctx->d_scalar, ctx->d_scalar, 1, ncclDouble, ncclSum, ctx->comm, ctx->stream));
+  CUDA_CHECK(cudaMemcpyAsync(ctx->h_scalar, ctx->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  return ctx->h_scalar[0];
+}
+
+template <typename T>
+static void
+apply_hook_post(dasm_op *op, T *dst, const T *src, const dasm_hook *post)
+{
+  dasm_ctx *ctx = op->ctx;
+  if (post == nullptr || post->kind == DASM_HOOK_NONE)
+    return;
+  // unit-matrix operation on constrained DoFs (matrix_free_internal.h:226-229, 247-255)
+  if (op->n_constrained > 0)
+    {
+      vec_copy_indexed_kernel<T><<<nblocks(op->n_constrained), 256, 0, ctx->stream>>>(dst, src, op->d_constrained, op->n_constrained);
+      ctx->launches++;
+    }
+  const long long n = op->n_owned;
+  switch (post->kind)
+    {
+      case DASM_HOOK_RESIDUAL:
+        vec_residual_kernel<T><<<nblocks(n), 256, 0, ctx->stream>>>(dst, (const T *)post->v0, n);
+        break;
+      case DASM_HOOK_CHEB_UPDATE:
+        vec_cheb_update_kernel<T><<<nblocks(n), 256, 0, ctx->stream>>>(dst, dst, (const T *)post->v0, (const T *)post->v1, (T)post->f1, (T)post->f2, n);
+        break;
+      case DASM_HOOK_SCALE:
+        vec_scale_kernel<T><<<nblocks(n), 256, 0, ctx->stream>>>(dst, dst, (T)post->f2, n);
+        break;
+      default:
+        throw std::runtime_error("unsupported post hook kind " + std::to_string(post->kind));
+    }
+  ctx->launches++;
+}
+
+// ------------------------------------------------------------------------------------------------
+// operator application
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+static void
+launch_laplace(dasm_op *op, T *dst, const T *src)
+{
+  dasm_ctx *ctx = op->ctx;
+  DISPATCH_DEGREE(op->k, {
+    constexpr int n = K + 1, CPB = cells_per_block<K>();
+    const size_t  smem = (size_t)CPB * 4 * n * n * n * sizeof(T);
+    const unsigned grid = (unsigned)((op->n_cells + CPB - 1) / CPB);
+    if (op->geom_mode == 0)
+      {
+        auto kern = laplace_generic_kernel<K, T, 0>;
+        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, CPB * n * n, smem, ctx->stream>>>(src, dst, op->d_cidx, (const T *)nullptr, op->cart, op->n_cells);
+      }
+    else
+      {
+        auto kern = laplace_generic_kernel<K, T, 1>;
+        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, CPB * n * n, smem, ctx->stream>>>(src, dst, op->d_cidx, (const T *)op->d_geom, op->cart, op->n_cells);
+      }
+  });
+  ctx->launches++;
+  CUDA_CHECK(cudaGetLastError());
+}
+
+template <typename T>
+static void
+op_vmult(dasm_op *op, T *dst, const T *src, const dasm_hook *pre, const dasm_hook *post)
+{
+  dasm_ctx *ctx = op->ctx;
+  if (pre != nullptr && pre->kind != DASM_HOOK_NONE && pre->kind != DASM_HOOK_ZERO_DST)
+    throw std::runtime_error("LaplaceOperatorMatrixFree::vmult: only the zeroing pre-operation is supported");
+  DASM_REQUIRE((const void *)dst != (const void *)src, "vmult: dst and src must not alias");
+  // pre: dst = 0 (the reference's default pre-operation, operator.h:1356-1363; the cell kernel
+  // accumulates, so dst must start from zero in all cases)
+  CUDA_CHECK(cudaMemsetAsync(dst, 0, (size_t)op->n_vec * sizeof(T), ctx->stream));
+  op->exchange.run<T>(const_cast<T *>(src), false); // update_ghost_values(src)
+  launch_laplace<T>(op, dst, src);
+  op->exchange.run<T>(dst, true); // compress(add)
+  apply_hook_post<T>(op, dst, src, post);
+}
+
+// ------------------------------------------------------------------------------------------------
+// FDM application
+// ------------------------------------------------------------------------------------------------
+template <int M, typename T>
+static void
+launch_fdm_m(dasm_fdm *f, T *dst, const T *src)
+{
+  dasm_op *      op   = f->op;
+  dasm_ctx *     ctx  = op->ctx;
+  constexpr int  CPB  = fdm_cells_per_block<M>();
+  const size_t   smem = (size_t)CPB * (M * M * M + 3 * M * M + 3 * M) * sizeof(T);
+  const unsigned grid = (unsigned)((op->n_cells + CPB - 1) / CPB);
+  const void *   w    = (f->wmode == 3) ? f->d_wvec : f->d_cw;
+  if (f->d_pidx == nullptr)
+    {
+      if (M - 1 != op->k)
+        throw std::runtime_error("internal: compressed FDM patch needs m == k+1");
+      if constexpr (M <= 9)
+        {
+          auto kern = fdm_generic_kernel<M, T, 0>;
+          CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          kern<<<grid, CPB * M * M, smem, ctx->stream>>>(src, dst, op->d_cidx, f->d_inst, (const T *)f->d_S, (const T *)f->d_lam,
+                                                         (const T *)w, f->wmode, (int)f->w_pre, (int)f->w_post, op->n_cells);
+        }
+    }
+  else
+    {
+      if constexpr (M >= 4)
+        {
+          auto kern = fdm_generic_kernel<M, T, 1>;
+          CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          kern<<<grid, CPB * M * M, smem, ctx->stream>>>(src, dst, f->d_pidx, f->d_inst, (const T *)f->d_S, (const T *)f->d_lam,
+                                                         (const T *)w, f->wmode, (int)f->w_pre, (int)f->w_post, op->n_cells);
+        }
+      else
+        throw std::runtime_error("internal: explicit patch list with m < 4");
+    }
+  ctx->launches++;
+  CUDA_CHECK(cudaGetLastError());
+}
+
+template <typename T>
+static void
+launch_fdm(dasm_fdm *f, T *dst, const T *src)
+{
+  DISPATCH_PATCH(f->m, launch_fdm_m<M, T>(f, dst, src));
+}
+
+template <typename T>
+static void
+fdm_vmult(dasm_fdm *f, T *dst, const T *src, const dasm_hook *pre, const dasm_hook *post)
+{
+  dasm_op * op  = f->op;
+  dasm_ctx *ctx = op->ctx;
+  if (pre != nullptr && pre->kind != DASM_HOOK_NONE && pre->kind != DASM_HOOK_ZERO_DST)
+    throw std::runtime_error("ASPoissonPreconditioner::vmult: only the zeroing pre-operation is supported");
+  DASM_REQUIRE((const void *)dst != (const void *)src, "vmult: dst and src must not alias");
+  CUDA_CHECK(cudaMemsetAsync(dst, 0, (size_t)op->n_vec * sizeof(T), ctx->stream));
+  op->exchange.run<T>(const_cast<T *>(src), false);
+  launch_fdm<T>(f, dst, src);
+  if (f->weight_type != DASM_WEIGHT_RAS) // RAS needs no compression (matrix_free.h:654-668)
+    op->exchange.run<T>(dst, true);
+  // post hook without the constrained-DoF copy: the preconditioner leaves constrained DoFs at zero
+  if (post != nullptr && post->kind != DASM_HOOK_NONE)
+    {
+      const long long n = op->n_owned;
+      switch (post->kind)
+        {
+          case DASM_HOOK_RESIDUAL:
+            vec_residual_kernel<T><<<nblocks(n), 256, 0, ctx->stream>>>(dst, (const T *)post->v0, n);
+            break;
+          case DASM_HOOK_CHEB_UPDATE:
+            vec_cheb_update_kernel<T><<<nblocks(n), 256, 0, ctx->stream>>>(dst, dst, (const T *)post->v0, (const T *)post->v1, (T)post->f1, (T)post->f2, n);
+            break;
+          case DASM_HOOK_SCALE:
+            vec_scale_kernel<T><<<nblocks(n), 256, 0, ctx->stream>>>(dst, dst, (T)post->f2, n);
+            break;
+          default:
+            throw std::runtime_error("unsupported post hook kind");
+        }
+      ctx->launches++;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI: context
+// ------------------------------------------------------------------------------------------------
+extern "C" const char *
+dasm_last_error(void)
+{
+  return g_last_error.c_str();
+}
+
+extern "C" const char *
+dasm_version(void)
+{
+  return "libdasm 0.1 (sm_100a)";
+}
+
+static void
+upload_basis_tables()
+{
+  DevBasis<double> hd[9];
+  DevBasis<float>  hf[9];
+  memset(hd, 0, sizeof(hd));
+  memset(hf, 0, sizeof(hf));
+  for (int k = 1; k <= MAX_DEGREE; ++k)
+    {
+      Basis1D   b(k);
+      const int n = k + 1;
+      // Dn = Dq * N (derivative of the nodal basis at the Gauss points) equals b.D
+      for (int i = 0; i < n * n; ++i)
+        {
+          hd[k].N[i]  = b.N[i];
+          hd[k].Dq[i] = b.Dq[i];
+          hd[k].Dn[i] = b.D[i];
+          hf[k].N[i]  = (float)b.N[i];
+          hf[k].Dq[i] = (float)b.Dq[i];
+          hf[k].Dn[i] = (float)b.D[i];
+        }
+      for (int i = 0; i < n; ++i)
+        {
+          hd[k].qw[i] = b.qw[i];
+          hf[k].qw[i] = (float)b.qw[i];
+        }
+    }
+  CUDA_CHECK(cudaMemcpyToSymbol(c_basis_d, hd, sizeof(hd)));
+  CUDA_CHECK(cudaMemcpyToSymbol(c_basis_f, hf, sizeof(hf)));
+}
+
+extern "C" int
+dasm_ctx_create(int device, dasm_ctx **out)
+{
+  DASM_API_BEGIN
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    throw std::runtime_error("libdasm needs a CUDA device (sm_100a); there is no CPU fallback");
+  DASM_REQUIRE(device >= 0 && device < count, "invalid device ordinal");
+  CUDA_CHECK(cudaSetDevice(device));
+  auto ctx    = new dasm_ctx;
+  ctx->device = device;
+  CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+  CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_a, cudaEventDisableTiming));
+  CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_b, cudaEventDisableTiming));
+  CUDA_CHECK(cudaMalloc(&ctx->d_partial, 1024 * sizeof(double)));
+  CUDA_CHECK(cudaMalloc(&ctx->d_scalar, 8 * sizeof(double)));
+  CUDA_CHECK(cudaMallocHost(&ctx->h_scalar, 8 * sizeof(double)));
+  upload_basis_tables();
+  *out = ctx;
+  DASM_API_END
+}
+
+extern "C" int
+dasm_ctx_destroy(dasm_ctx *ctx)
+{
+  DASM_API_BEGIN
+  if (ctx == nullptr)
+    return 0;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->comm)
+    ncclCommDestroy(ctx->comm);
+  cudaFree(ctx->d_partial);
+  cudaFree(ctx->d_scalar);
+  cudaFreeHost(ctx->h_scalar);
+  cudaEventDestroy(ctx->ev_a);
+  cudaEventDestroy(ctx->ev_b);
+  cudaStreamDestroy(ctx->stream);
+  cudaStreamDestroy(ctx->comm_stream);
+  delete ctx;
+  DASM_API_END
+}
+
+extern "C" int
+dasm_ctx_sync(dasm_ctx *ctx)
+{
+  DASM_API_BEGIN
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  DASM_API_END
+}
+
+extern "C" long long
+dasm_ctx_launch_count(const dasm_ctx *ctx)
+{
+  return ctx->launches;
+}
+
+extern "C" void *
+dasm_ctx_stream(dasm_ctx *ctx)
+{
+  return (void *)ctx->stream;
+}
+
+extern "C" int
+dasm_nccl_unique_id(void *id128)
+{
+  DASM_API_BEGIN
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  ncclUniqueId id;
+  NCCL_CHECK(ncclGetUniqueId(&id));
+  memcpy(id128, &id, 128);
+  DASM_API_END
+}
+
+extern "C" int
+dasm_ctx_comm_init(dasm_ctx *ctx, int n_ranks, int rank, const void *id128)
+{
+  DASM_API_BEGIN
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  ncclUniqueId id;
+  memcpy(&id, id128, 128);
+  NCCL_CHECK(ncclCommInitRank(&ctx->comm, n_ranks, id, rank));
+  ctx->n_ranks = n_ranks;
+  ctx->rank    = rank;
+  DASM_API_END
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI: mesh
+// ------------------------------------------------------------------------------------------------
+extern "C" int
+dasm_decompose_balanced(int s, int *n_refine, int subdivisions[3])
+{
+  DASM_API_BEGIN
+  // include/grid_generator.h:107-135
+  int       nr        = s / 6;
+  const int remainder = s % 6;
+  int       sub[3]    = {1, 1, 1};
+  if (remainder == 1 && s > 1)
+    {
+      sub[0] = 3;
+      sub[1] = 2;
+      sub[2] = 2;
+      nr -= 1;
+    }
+  if (remainder == 2)
+    sub[0] = 2;
+  else if (remainder == 3)
+    sub[0] = 3;
+  else if (remainder == 4)
+    sub[0] = sub[1] = 2;
+  else if (remainder == 5)
+    {
+      sub[0] = 3;
+      sub[1] = 2;
+    }
+  *n_refine = nr;
+  for (int d = 0; d < 3; ++d)
+    subdivisions[d] = sub[d];
+  DASM_API_END
+}
+
+extern "C" int
+dasm_mesh_create_structured(dasm_ctx *ctx, const int n_cells[3], const int periodic[3], int dirichlet, const double length[3],
+                            int map_kind, const double map_params[4], const int partition[3], int rank, dasm_mesh **out)
+{
+  DASM_API_BEGIN
+  MeshParams p;
+  for (int d = 0; d < 3; ++d)
+    {
+      DASM_REQUIRE(n_cells[d] >= 1, "n_cells must be positive");
+      p.nc[d]       = n_cells[d];
+      p.periodic[d] = periodic ? periodic[d] : 0;
+      p.length[d]   = length ? length[d] : 1.0;
+      p.part[d]     = partition ? partition[d] : 1;
+      DASM_REQUIRE(p.part[d] >= 1 && p.part[d] <= p.nc[d], "invalid partition");
+      if (p.periodic[d] && p.part[d] > 1)
+        DASM_REQUIRE(p.nc[d] / p.part[d] >= 2, "periodic partitioned direction needs >= 2 cells per rank");
+    }
+  p.dirichlet = dirichlet;
+  p.map_kind  = map_kind;
+  DASM_REQUIRE(map_kind >= 0 && map_kind <= 2, "unknown map kind");
+  if (map_params)
+    for (int i = 0; i < 4; ++i)
+      p.map_par[i] = map_params[i];
+  p.rank = rank;
+  DASM_REQUIRE(rank >= 0 && rank < p.part[0] * p.part[1] * p.part[2], "rank outside partition");
+  auto m  = new dasm_mesh;
+  m->ctx  = ctx;
+  m->mesh = std::make_unique<Mesh>(p);
+  *out    = m;
+  DASM_API_END
+}
+
+extern "C" int
+dasm_mesh_destroy(dasm_mesh *mesh)
+{
+  delete mesh;
+  return 0;
+}
+
+extern "C" long long
+dasm_mesh_n_cells(const dasm_mesh *mesh)
+{
+  return (long long)mesh->mesh->n_cells;
+}
+
+extern "C" long long
+dasm_mesh_n_global_cells(const dasm_mesh *mesh)
+{
+  const auto &p = mesh->mesh->p;
+  return (long long)p.nc[0] * p.nc[1] * p.nc[2];
+}
+
+extern "C" int
+dasm_mesh_cell_coordinates(const dasm_mesh *mesh, int *out)
+{
+  for (size_t i = 0; i < mesh->mesh->n_cells; ++i)
+    for (int d = 0; d < 3; ++d)
+      out[3 * i + d] = mesh->mesh->cell_ijk[i][d];
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI: operator
+// ------------------------------------------------------------------------------------------------
+extern "C" int
+dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping_type, int compress_indices, dasm_op **out)
+{
+  DASM_API_BEGIN
+  DASM_REQUIRE(degree >= 1 && degree <= MAX_DEGREE, "degree must be in 1..8");
+  DASM_REQUIRE(number_type == DASM_F64 || number_type == DASM_F32, "unknown number type");
+  const std::string mt = mapping_type ? mapping_type : "";
+  if (mt == "linear geometry" || mt == "quadratic geometry" || mt == "construct q")
+    throw std::runtime_error("Mapping type <" + mt + "> is not implemented in libdasm yet (use \"\" or \"merged\")");
+  if (mt != "" && mt != "merged")
+    throw std::runtime_error("Mapping type <" + mt + "> is not known!"); // operator.h:747-752
+  dasm_ctx *ctx = mesh->ctx;
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  auto op              = new dasm_op(degree);
+  op->ctx              = ctx;
+  op->mesh             = mesh;
+  op->k                = degree;
+  op->ntype            = number_type;
+  op->compress_indices = compress_indices != 0;
+  op->mapping_type     = mt;
+  const Mesh &M        = *mesh->mesh;
+  op->nb               = M.number_dofs(degree);
+  op->n_cells          = (long long)M.n_cells;
+  op->n_owned          = op->nb.n_owned;
+  op->n_ghost          = op->nb.n_ghost;
+  op->n_vec            = op->n_owned + op->n_ghost;
+  {
+    long long g = 1;
+    for (int d = 0; d < 3; ++d)
+      g *= (long long)M.p.nc[d] * degree + (M.p.periodic[d] ? 0 : 1);
+    op->n_global_dofs = g;
+  }
+  op->d_cidx        = dev_upload(op->nb.cidx, ctx->stream);
+  op->d_constrained = dev_upload(op->nb.constrained, ctx->stream);
+  op->n_constrained = (long long)op->nb.constrained.size();
+  op->exchange.init(ctx, op->nb.exchange, op->esize());
+  // geometry
+  const int n3 = (degree + 1) * (degree + 1) * (degree + 1);
+  if (M.is_cartesian() && mt == "")
+    {
+      op->geom_mode   = 0;
+      const double h0 = M.h(0), h1 = M.h(1), h2 = M.h(2), det = h0 * h1 * h2;
+      op->cart.g[0] = det / (h0 * h0);
+      op->cart.g[1] = det / (h1 * h1);
+      op->cart.g[2] = det / (h2 * h2);
+    }
+  else
+    {
+      op->geom_mode = 1;
+      std::vector<double> tmp(6 * n3);
+      if (number_type == DASM_F64)
+        {
+          std::vector<double> g((size_t)op->n_cells * 6 * n3);
+          for (long long c = 0; c < op->n_cells; ++c)
+            {
+              const int cc[3] = {M.cell_ijk[c][0], M.cell_ijk[c][1], M.cell_ijk[c][2]};
+              M.merged_coefficients(cc, op->basis, g.data() + (size_t)c * 6 * n3);
+            }
+          op->d_geom = dev_upload(g, ctx->stream);
+        }
+      else
+        {
+          std::vector<float> g((size_t)op->n_cells * 6 * n3);
+          for (long long c = 0; c < op->n_cells; ++c)
+            {
+              const int cc[3] = {M.cell_ijk[c][0], M.cell_ijk[c][1], M.cell_ijk[c][2]};
+              M.merged_coefficients(cc, op->basis, tmp.data());
+              for (int i = 0; i < 6 * n3; ++i)
+                g[(size_t)c * 6 * n3 + i] = (float)tmp[i];
+            }
+          op->d_geom = dev_upload(g, ctx->stream);
+        }
+      op->cart.g[0] = op->cart.g[1] = op->cart.g[2] = 0;
+    }
+  *out = op;
+  DASM_API_END
+}
+
+extern "C" int
+dasm_op_destroy(dasm_op *op)
+{
+  DASM_API_BEGIN
+  if (!op)
+    return 0;
+  cudaStreamSynchronize(op->ctx->stream);
+  cudaFree(op->d_cidx);
+  cudaFree(op->d_constrained);
+  cudaFree(op->d_geom);
+  op->exchange.destroy();
+  for (void *p : op->scratch)
+    cudaFree(p);
+  delete op;
+  DASM_API_END
+}
+
+extern "C" long long dasm_op_n_dofs(const dasm_op *op) { return op->n_owned; }
+extern "C" long long dasm_op_n_ghost(const dasm_op *op) { return op->n_ghost; }
+extern "C" long long dasm_op_vec_size(const dasm_op *op) { return op->n_vec; }
+extern "C" long long dasm_op_n_global_dofs(const dasm_op *op) { return op->n_global_dofs; }
+extern "C" int dasm_op_degree(const dasm_op *op) { return op->k; }
+extern "C" int dasm_op_number_type(const dasm_op *op) { return op->ntype; }
+extern "C" int dasm_op_uses_compressed_indices(const dasm_op *op) { return op->compress_indices ? 1 : 0; }
+
+extern "C" int
+dasm_op_vmult(dasm_op *op, void *dst, const void *src)
+{
+  DASM_API_BEGIN
+  CUDA_CHECK(cudaSetDevice(op->ctx->device));
+  DISPATCH_TYPE(op->ntype, op_vmult<T>(op, (T *)dst, (const T *)src, nullptr, nullptr));
+  DASM_API_END
+}
+
+extern "C" int
+dasm_op_vmult_hooks(dasm_op *op, void *dst, const void *src, const dasm_hook *pre, const dasm_hook *post)
+{
+  DASM_API_BEGIN
+  CUDA_CHECK(cudaSetDevice(op->ctx->device));
+  DISPATCH_TYPE(op->ntype, op_vmult<T>(op, (T *)dst, (const T *)src, pre, post));
+  DASM_API_END
+}
+
+template <typename T>
+static void
+op_inverse_diagonal(dasm_op *op, T *diag)
+{
+  dasm_ctx *ctx = op->ctx;
+  CUDA_CHECK(cudaMemsetAsync(diag, 0, (size_t)op->n_vec * sizeof(T), ctx->stream));
+  DISPATCH_DEGREE(op->k, {
+    constexpr int   n3    = (K + 1) * (K + 1) * (K + 1);
+    const long long total = op->n_cells * n3;
+    if (op->geom_mode == 0)
+      laplace_diagonal_kernel<K, T, 0><<<nblocks(total, 128), 128, 0, ctx->stream>>>(diag, op->d_cidx, (const T *)nullptr, op->cart, op->n_cells);
+    else
+      laplace_diagonal_kernel<K, T, 1><<<nblocks(total, 128), 128, 0, ctx->stream>>>(diag, op->d_cidx, (const T *)op->d_geom, op->cart, op->n_cells);
+  });
+  ctx->launches++;
+  op->exchange.run<T>(diag, true);
+  if (op->n_constrained > 0)
+    {
+      vec_set_indexed_kernel<T><<<nblocks(op->n_constrained), 256, 0, ctx->stream>>>(diag, T(1), op->d_constrained, op->n_constrained);
+      ctx->launches++;
+    }
+  vec_invert_diag_kernel<T><<<nblocks(op->n_owned), 256, 0, ctx->stream>>>(diag, op->n_owned);
+  ctx->launches++;
+  CUDA_CHECK(cudaGetLastError());
+}
+
+extern "C" int
+dasm_op_inverse_diagonal(dasm_op *op, void *diag)
+{
+  DASM_API_BEGIN
+  CUDA_CHECK(cudaSetDevice(op->ctx->device));
+  DISPATCH_TYPE(op->ntype, op_inverse_diagonal<T>(op, (T *)diag));
+  DASM_API_END
+}
+
+extern "C" int
+dasm_op_compressed_indices(const dasm_op *op, int plain, uint32_t *out)
+{
+  const auto &v = plain ? op->nb.cidx_plain : op->nb.cidx;
+  memcpy(out, v.data(), v.size() * sizeof(uint32_t));
+  return 0;
+}
+
+extern "C" long long
+dasm_op_constrained_dofs(const dasm_op *op, uint32_t *out)
+{
+  if (out)
+    memcpy(out, op->nb.constrained.data(), op->nb.constrained.size() * sizeof(uint32_t));
+  return (long long)op->nb.constrained.size();
+}
+
+extern "C" int
+dasm_op_merged_coefficients(const dasm_op *op, long long cell, double *out)
+{
+  DASM_API_BEGIN
+  DASM_REQUIRE(cell >= 0 && cell < op->n_cells, "cell out of range");
+  const Mesh &M    = *op->mesh->mesh;
+  const int   c[3] = {M.cell_ijk[cell][0], M.cell_ijk[cell][1], M.cell_ijk[cell][2]};
+  M.merged_coefficients(c, op->basis, out);
+  DASM_API_END
+}
+
+extern "C" int
+dasm_op_vec_alloc(dasm_op *op, void **dev)
+{
+  DASM_API_BEGIN
+  CUDA_CHECK(cudaSetDevice(op->ctx->device));
+  CUDA_CHECK(cudaMalloc(dev, std::max<size_t>(1, (size_t)op->n_vec) * op->esize()));
+  CUDA_CHECK(cudaMemsetAsync(*dev, 0, (size_t)op->n_vec * op->esize(), op->ctx->stream));
+  DASM_API_END
+}
+
+extern "C" int
+dasm_op_vec_free(dasm_op *op, void *dev)
+{
+  DASM_API_BEGIN
+  CUDA_CHECK(cudaStreamSynchronize(op->ctx->stream));
+  CUDA_CHECK(cudaFree(dev));
+  DASM_API_END
+}
+
+template <typename T>
+static void
+vec_upload(dasm_op *op, T *dev, const double *host)
+{
+  std::vector<T> tmp(op->n_vec, T(0));
+  for (long long i = 0; i < op->n_owned; ++i)
+    tmp[i] = (T)host[i];
+  CUDA_CHECK(cudaMemcpyAsync(dev, tmp.data(), (size_t)op->n_vec * sizeof(T), cudaMemcpyHostToDevice, op->ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(op->ctx->stream));
+}
+
+template <typename T>
+static void
+vec_download(dasm_op *op, double *host, const T *dev)
+{
+  std::vector<T> tmp(op->n_owned);
+  CUDA_CHECK(cudaMemcpyAsync(tmp.data(), dev, (size_t)op->n_owned * sizeof(T), cudaMemcpyDeviceToHost, op->ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(op->ctx->stream));
+  for (long long i = 0; i < op->n_owned; ++i)
+    host[i] = (double)tmp[i];
+}
+
+extern "C" int
+dasm_op_vec_upload(dasm_op *op, void *dev, const double *host_owned)
+{
+  DASM_API_BEGIN
+  CUDA_CHECK(cudaSetDevice(op->ctx->device));
+  DISPATCH_TYPE(op->ntype, vec_upload<T>(op, (T *)dev, host_owned));
+  DASM_API_END
+}
+
+extern "C" int
+dasm_op_vec_download(dasm_op *op, double *host_owned, const void *dev)
+{
+  DASM_API_BEGIN
+  CUDA_CHECK(cudaSetDevice(op->ctx->device));
+  DISPATCH_TYPE(op->ntype, vec_download<T>(op, host_owned, (const T *)dev));
+  DASM_API_END
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI: FDM preconditioner
+// ------------------------------------------------------------------------------------------------
+// [deal.II TensorProductMatrixCreator::create_laplace_tensor_product_matrix, one direction]
+static void
+laplace_tp_matrix_1d(const Basis1D &b, const double ext[3], const int btype[2], int n_overlap, std::vector<double> &Mo,
+                     std::vector<double> &Ko)
+{
+  const int n = b.n, m = n - 2 + 2 * n_overlap;
+  Mo.assign(m * m, 0.);
+  Ko.assign(m * m, 0.);
+  const int o = n_overlap - 1;
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j)
+      {
+        Mo[(i + o) * m + j + o] = b.M_ref[i * n + j] * ext[1];
+        Ko[(i + o) * m + j + o] = b.K_ref[i * n + j] / ext[1];
+      }
+  auto clear = [&](int r) {
+    for (int i = 0; i < m; ++i)
+      Mo[r * m + i] = Mo[i * m + r] = Ko[r * m + i] = Ko[i * m + r] = 0;
+  };
+  if (btype[0] == 0)
+    {
+      for (int i = 0; i < n_overlap; ++i)
+        for (int j = 0; j < n_overlap; ++j)
+          {
+            Mo[i * m + j] += b.M_ref[(n - n_overlap + i) * n + (n - n_overlap + j)] * ext[0];
+            Ko[i * m + j] += b.K_ref[(n - n_overlap + i) * n + (n - n_overlap + j)] / ext[0];
+          }
+    }
+  else if (btype[0] == 1)
+    clear(n_overlap - 1);
+  if (btype[1] == 0)
+    {
+      const int s = n_overlap + n - 2;
+      for (int i = 0; i < n_overlap; ++i)
+        for (int j = 0; j < n_overlap; ++j)
+          {
+            Mo[(s + i) * m + s + j] += b.M_ref[i * n + j] * ext[2];
+            Ko[(s + i) * m + s + j] += b.K_ref[i * n + j] / ext[2];
+          }
+    }
+  else if (btype[1] == 1)
+    clear(n_overlap + n - 2);
+}
+
+template <typename T>
+__global__ void
+valence_kernel(T *val, const uint32_t *idx, const long long n)
+{
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && idx[i] != DEV_INVALID)
+    atomicAdd(val + idx[i], T(1));
+}
+
+template <int k>
+__global__ void
+expand_compressed_kernel(uint32_t *out, const uint32_t *cidx, const long long n_cells)
+{
+  constexpr int   n = k + 1, n3 = n * n * n;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_cells * n3)
+    return;
+  const long long c = i / n3;
+  const int       l = i % n3;
+  out[i]            = compressed_index<k>(cidx + c * 27, l % n, (l / n) % n, l / (n * n));
+}
+
+template <typename T>
+__global__ void
+weights_from_valence_kernel(T *w, const int symm, const long long n)
+{
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    {
+      const double v = (double)w[i];
+      w[i]           = (v == 0.0) ? T(0) : (T)(1.0 / (symm ? sqrt(v) : v));
+    }
+}
+
+template <typename T>
+__global__ void
+gather_entity_weights_kernel(T *cw, const T *w, const uint32_t *cidx, const long long n)
+{
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    cw[i] = (cidx[i] == DEV_INVALID) ? T(0) : w[cidx[i]];
+}
+
+template <typename T>
+static void
+fdm_setup_device(dasm_fdm *f, const std::vector<double> &S, const std::vector<double> &lam, const std::vector<float> &ras_cw)
+{
+  dasm_op * op  = f->op;
+  dasm_ctx *ctx = op->ctx;
+  std::vector<T> Sd(S.begin(), S.end()), ld(lam.begin(), lam.end());
+  f->d_S   = dev_upload(Sd, ctx->stream);
+  f->d_lam = dev_upload(ld, ctx->stream);
+  const int       m3      = f->m * f->m * f->m;
+  const bool      compressed_idx = (f->d_pidx == nullptr);
+  const long long n_entries = compressed_idx ? op->n_cells * (op->k + 1) * (op->k + 1) * (op->k + 1) : op->n_cells * m3;
+  f->w_pre  = (f->weight_type == DASM_WEIGHT_PRE || f->weight_type == DASM_WEIGHT_SYMM);
+  f->w_post = (f->weight_type == DASM_WEIGHT_POST || f->weight_type == DASM_WEIGHT_SYMM || f->weight_type == DASM_WEIGHT_RAS);
+  if (f->weight_type == DASM_WEIGHT_NONE)
+    {
+      f->wmode = 0;
+      return;
+    }
+  if (f->weight_type == DASM_WEIGHT_RAS)
+    {
+      // 0/1 ownership weights per (cell, entity) computed on the host
+      std::vector<T> cw(ras_cw.begin(), ras_cw.end());
+      f->d_cw  = dev_upload(cw, ctx->stream);
+      f->wmode = compressed_idx ? 1 : 2;
+      return;
+    }
+  // valence = number of patches containing a DoF (matrix_free.h:674-712)
+  T *w = dev_alloc<T>(op->n_vec);
+  CUDA_CHECK(cudaMemsetAsync(w, 0, (size_t)op->n_vec * sizeof(T), ctx->stream));
+  uint32_t *d_full = nullptr;
+  if (compressed_idx)
+    {
+      d_full = dev_alloc<uint32_t>(n_entries);
+      DISPATCH_DEGREE(op->k, expand_compressed_kernel<K><<<nblocks(n_entries), 256, 0, ctx->stream>>>(d_full, op->d_cidx, op->n_cells));
+    }
+  valence_kernel<T><<<nblocks(n_entries), 256, 0, ctx->stream>>>(w, compressed_idx ? d_full : f->d_pidx, n_entries);
+  ctx->launches += 2;
+  op->exchange.run<T>(w, true);
+  weights_from_valence_kernel<T><<<nblocks(op->n_owned), 256, 0, ctx->stream>>>(w, f->weight_type == DASM_WEIGHT_SYMM ? 1 : 0, op->n_owned);
+  ctx->launches++;
+  op->exchange.run<T>(w, false);
+  f->d_wvec = w;
+  {
+    std::vector<T> hw(op->n_owned);
+    CUDA_CHECK(cudaMemcpyAsync(hw.data(), w, (size_t)op->n_owned * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    f->h_weights.assign(hw.begin(), hw.end());
+  }
+  if (compressed_idx && f->weight_sequence == DASM_WSEQ_COMPRESSED && op->k >= 2)
+    {
+      // 27 weights per cell by entity (compute_weights_fe_q_dofs_by_entity, matrix_free.h:756-764)
+      T *cw = dev_alloc<T>(op->n_cells * 27);
+      gather_entity_weights_kernel<T><<<nblocks(op->n_cells * 27), 256, 0, ctx->stream>>>(cw, w, op->d_cidx, op->n_cells * 27);
+      ctx->launches++;
+      f->d_cw  = cw;
+      f->wmode = 1;
+    }
+  else if (f->weight_sequence == DASM_WSEQ_DG)
+    {
+      T *wl = dev_alloc<T>(n_entries);
+      gather_entity_weights_kernel<T><<<nblocks(n_entries), 256, 0, ctx->stream>>>(wl, w, compressed_idx ? d_full : f->d_pidx, n_entries);
+      ctx->launches++;
+      f->d_cw  = wl;
+      f->wmode = 2;
+    }
+  else
+    f->wmode = 3; // global / local: gathered from the weight vector
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  if (d_full)
+    cudaFree(d_full);
+}
+
+extern "C" int
+dasm_fdm_create(dasm_op *op, int n_overlap, int sub_mesh_approximation, int weight_type, int weight_sequence, int overlap_pre_post,
+                int element_centric, dasm_fdm **out)
+{
+  DASM_API_BEGIN
+  (void)overlap_pre_post;
+  (void)sub_mesh_approximation;
+  CUDA_CHECK(cudaSetDevice(op->ctx->device));
+  DASM_REQUIRE(weight_type >= 0 && weight_type <= 4, "Weighting type is not known!");
+  DASM_REQUIRE(weight_sequence >= 0 && weight_sequence <= 3, "weight sequence is not known!");
+  if (!element_centric)
+    throw std::runtime_error("vertex-patch FDM (element centric = false) is not implemented in libdasm yet");
+  const int k = op->k;
+  n_overlap   = std::min(std::max(n_overlap, 1), k); // precondition.templates.h:195-196
+  const Mesh &M = *op->mesh->mesh;
+  if (n_overlap > 1)
+    DASM_REQUIRE(M.n_ranks() == 1, "n overlap > 1 on several ranks is not implemented in libdasm yet");
+  auto f             = new dasm_fdm;
+  f->op              = op;
+  f->n_overlap       = n_overlap;
+  f->weight_type     = weight_type;
+  f->weight_sequence = weight_sequence;
+  f->element_centric = element_centric;
+  f->m               = k - 1 + 2 * n_overlap;
+  const int m        = f->m;
+
+  // 1-D instances, deduplicated like TensorProductMatrixSymmetricSumCollection::finalize
+  // (matrix_free.h:389-392)
+  std::map<std::array<uint64_t, 4>, uint32_t> cache;
+  std::vector<double>                         S_all, lam_all;
+  f->h_inst.resize((size_t)op->n_cells * 3);
+  for (long long c = 0; c < op->n_cells; ++c)
+    {
+      const int cc[3] = {M.cell_ijk[c][0], M.cell_ijk[c][1], M.cell_ijk[c][2]};
+      for (int d = 0; d < 3; ++d)
+        {
+          double ext[3] = {0, M.harmonic_extent(cc, d, op->basis), 0};
+          int    bt[2];
+          for (int side = 0; side < 2; ++side)
+            {
+              int nbc[3];
+              if (M.neighbor(cc, d, side, nbc))
+                {
+                  bt[side]      = 0;
+                  ext[2 * side] = M.harmonic_extent(nbc, d, op->basis);
+                }
+              else
+                bt[side] = M.p.dirichlet ? 1 : 2;
+            }
+          std::array<uint64_t, 4> key;
+          memcpy(&key[0], &ext[0], 8);
+          memcpy(&key[1], &ext[1], 8);
+          memcpy(&key[2], &ext[2], 8);
+          key[3]  = (uint64_t)(bt[0] * 3 + bt[1]);
+          auto it = cache.find(key);
+          if (it == cache.end())
+            {
+              std::vector<double> Mm, Km, S, lam;
+              laplace_tp_matrix_1d(op->basis, ext, bt, n_overlap, Mm, Km);
+              generalized_eig(m, Mm, Km, S, lam);
+              const uint32_t id = (uint32_t)cache.size();
+              cache[key]        = id;
+              S_all.insert(S_all.end(), S.begin(), S.end());
+              lam_all.insert(lam_all.end(), lam.begin(), lam.end());
+              f->h_inst[c * 3 + d] = id;
+            }
+          else
+            f->h_inst[c * 3 + d] = it->second;
+        }
+    }
+  f->n_instances = (long long)cache.size();
+  f->h_S         = S_all;
+  f->h_lam       = lam_all;
+  f->d_inst      = dev_upload(f->h_inst, op->ctx->stream);
+
+  // explicit patch indices for n_overlap > 1 (dof_tools.h:78-137)
+  if (n_overlap > 1)
+    {
+      const int n = k + 1, n3 = n * n * n, m3 = m * m * m;
+      // expand the plain compressed indices of every cell on the host
+      std::vector<uint32_t> full((size_t)op->n_cells * n3);
+      std::map<std::array<int, 3>, long long> cell_of;
+      for (long long c = 0; c < op->n_cells; ++c)
+        {
+          cell_of[{M.cell_ijk[c][0], M.cell_ijk[c][1], M.cell_ijk[c][2]}] = c;
+          const uint32_t *ci = op->nb.cidx.data() + c * 27;
+          for (int z = 0; z < n; ++z)
+            for (int y = 0; y < n; ++y)
+              for (int x = 0; x < n; ++x)
+                {
+                  const int ex = x == 0 ? 0 : (x == k ? 2 : 1), ey = y == 0 ? 0 : (y == k ? 2 : 1), ez = z == 0 ? 0 : (z == k ? 2 : 1);
+                  const uint32_t st = ci[ex + 3 * ey + 9 * ez];
+                  uint32_t       v  = INVALID_INDEX;
+                  if (st != INVALID_INDEX)
+                    {
+                      const int sx = ex == 1 ? k - 1 : 1, sy = ey == 1 ? k - 1 : 1;
+                      v = st + (ex == 1 ? x - 1 : 0) + sx * ((ey == 1 ? y - 1 : 0) + sy * (ez == 1 ? z - 1 : 0));
+                    }
+                  full[(size_t)c * n3 + (z * n + y) * n + x] = v;
+                }
+        }
+      auto translate = [&](int i, int &which, int &l) {
+        if (i < n_overlap - 1)
+          {
+            which = 0;
+            l     = k + 1 - n_overlap + i;
+          }
+        else if (i < k + n_overlap)
+          {
+            which = 1;
+            l     = i - (n_overlap - 1);
+          }
+        else
+          {
+            which = 2;
+            l     = i - (n_overlap + k - 1);
+          }
+      };
+      std::vector<uint32_t> pidx((size_t)op->n_cells * m3, INVALID_INDEX);
+      for (long long c = 0; c < op->n_cells; ++c)
+        {
+          const int cc[3] = {M.cell_ijk[c][0], M.cell_ijk[c][1], M.cell_ijk[c][2]};
+          for (int pz = 0; pz < m; ++pz)
+            for (int py = 0; py < m; ++py)
+              for (int px = 0; px < m; ++px)
+                {
+                  const int pp[3] = {px, py, pz};
+                  int       cur[3] = {cc[0], cc[1], cc[2]}, li[3];
+                  bool      ok = true;
+                  for (int d = 0; d < 3 && ok; ++d)
+                    {
+                      int which;
+                      translate(pp[d], which, li[d]);
+                      if (which != 1)
+                        {
+                          int nbc[3];
+                          if (!M.neighbor(cur, d, which == 0 ? 0 : 1, nbc))
+                            ok = false;
+                          else
+                            {
+                              cur[0] = nbc[0];
+                              cur[1] = nbc[1];
+                              cur[2] = nbc[2];
+                            }
+                        }
+                    }
+                  if (!ok)
+                    continue;
+                  const long long nc = cell_of[{cur[0], cur[1], cur[2]}];
+                  pidx[(size_t)c * m3 + (pz * m + py) * m + px] = full[(size_t)nc * n3 + (li[2] * n + li[1]) * n + li[0]];
+                }
+        }
+      f->d_pidx = dev_upload(pidx, op->ctx->stream);
+    }
+
+  // RAS ownership: the patch of the touching cell with the smallest global lexicographic id owns
+  // the DoF (matrix_free.h:536-673 uses the global cell-batch numbering for the same purpose)
+  std::vector<float> ras_cw;
+  if (weight_type == DASM_WEIGHT_RAS)
+    {
+      auto gid = [&](const int c[3]) { return ((long long)c[2] * M.p.nc[1] + c[1]) * M.p.nc[0] + c[0]; };
+      auto entity_owner_is = [&](const int cc[3], int e) {
+        int s[3];
+        M.cell_slot(cc, e, s);
+        long long best = -1;
+        int       cand[3][2], ncand[3];
+        for (int d = 0; d < 3; ++d)
+          {
+            ncand[d] = 0;
+            if (s[d] % 2 == 1)
+              cand[d][ncand[d]++] = s[d] / 2;
+            else
+              {
+                int a = s[d] / 2 - 1, b2 = s[d] / 2;
+                if (M.p.periodic[d])
+                  {
+                    a  = (a + M.p.nc[d]) % M.p.nc[d];
+                    b2 = b2 % M.p.nc[d];
+                  }
+                if (a >= 0 && a < M.p.nc[d])
+                  cand[d][ncand[d]++] = a;
+                if (b2 >= 0 && b2 < M.p.nc[d] && (ncand[d] == 0 || cand[d][0] != b2))
+                  cand[d][ncand[d]++] = b2;
+              }
+          }
+        for (int a = 0; a < ncand[0]; ++a)
+          for (int b2 = 0; b2 < ncand[1]; ++b2)
+            for (int g = 0; g < ncand[2]; ++g)
+              {
+                const int       tc[3] = {cand[0][a], cand[1][b2], cand[2][g]};
+                const long long id    = gid(tc);
+                if (best < 0 || id < best)
+                  best = id;
+              }
+        return best == gid(cc);
+      };
+      if (n_overlap == 1)
+        {
+          ras_cw.resize((size_t)op->n_cells * 27);
+          for (long long c = 0; c < op->n_cells; ++c)
+            {
+              const int cc[3] = {M.cell_ijk[c][0], M.cell_ijk[c][1], M.cell_ijk[c][2]};
+              for (int e = 0; e < 27; ++e)
+                ras_cw[c * 27 + e] = entity_owner_is(cc, e) ? 1.f : 0.f;
+            }
+        }
+      else
+        {
+          const int m3 = m * m * m;
+          ras_cw.assign((size_t)op->n_cells * m3, 0.f);
+          for (long long c = 0; c < op->n_cells; ++c)
+            {
+              const int cc[3] = {M.cell_ijk[c][0], M.cell_ijk[c][1], M.cell_ijk[c][2]};
+              for (int pz = 0; pz < m; ++pz)
+                for (int py = 0; py < m; ++py)
+                  for (int px = 0; px < m; ++px)
+                    {
+                      const int pp[3] = {px, py, pz};
+                      int       e = 0, mul = 1;
+                      bool      core = true;
+                      for (int d = 0; d < 3; ++d, mul *= 3)
+                        {
+                          const int i = pp[d];
+                          if (i < n_overlap - 1 || i >= k + n_overlap)
+                            core = false;
+                          const int l = i - (n_overlap - 1);
+                          e += mul * (l == 0 ? 0 : (l == k ? 2 : 1));
+                        }
+                      if (core && entity_owner_is(cc, e))
+                        ras_cw[(size_t)c * m3 + (pz * m + py) * m + px] = 1.f;
+                    }
+            }
+        }
+    }
+  DISPATCH_TYPE(op->ntype, fdm_setup_device<T>(f, S_all, lam_all, ras_cw));
+  *out = f;
+  DASM_API_END
+}
+
+extern "C" int
+dasm_fdm_destroy(dasm_fdm *f)
+{
+  DASM_API_BEGIN
+  if (!f)
+    return 0;
+  cudaStreamSynchronize(f->op->ctx->stream);
+  cudaFree(f->d_inst);
+  cudaFree(f->d_S);
+  cudaFree(f->d_lam);
+  cudaFree(f->d_wvec);
+  cudaFree(f->d_cw);
+  cudaFree(f->d_pidx);
+  delete f;
+  DASM_API_END
+}
+
+extern "C" int
+dasm_fdm_vmult(dasm_fdm *f, void *dst, const void *src)
+{
+  DASM_API_BEGIN
+  CUDA_CHECK(cudaSetDevice(f->op->ctx->device));
+  DISPATCH_TYPE(f->op->ntype, fdm_vmult<T>(f, (T *)dst, (const T *)src, nullptr, nullptr));
+  DASM_API_END
+}
+
+extern "C" int
+dasm_fdm_vmult_hooks(dasm_fdm *f, void *dst, const void *src, const dasm_hook *pre, const dasm_hook *post)
+{
+  DASM_API_BEGIN
+  CUDA_CHECK(cudaSetDevice(f->op->ctx->device));
+  DISPATCH_TYPE(f->op->ntype, fdm_vmult<T>(f, (T *)dst, (const T *)src, pre, post));
+  DASM_API_END
+}
+
+extern "C" long long dasm_fdm_n_instances(const dasm_fdm *f) { return f->n_instances; }
+extern "C" long long
+dasm_fdm_memory_consumption(const dasm_fdm *f)
+{
+  return (long long)(f->n_instances * (f->m * f->m + f->m) * f->op->esize() + f->op->n_cells * 3 * sizeof(uint32_t));
+}
+extern "C" int
+dasm_fdm_is_symmetric(const dasm_fdm *f)
+{
+  return (f->weight_type == DASM_WEIGHT_NONE || f->weight_type == DASM_WEIGHT_SYMM) ? 1 : 0;
+}
+extern "C" int dasm_fdm_patch_size_1d(const dasm_fdm *f) { return f->m; }
+
+extern "C" int
+dasm_fdm_weights(const dasm_fdm *f, double *out)
+{
+  DASM_API_BEGIN
+  DASM_REQUIRE(!f->h_weights.empty(), "no global weight vector for this weighting type");
+  memcpy(out, f->h_weights.data(), f->h_weights.size() * sizeof(double));
+  DASM_API_END
+}
+
+extern "C" int
+dasm_fdm_instance(const dasm_fdm *f, long long cell, int d, double *S, double *lambda)
+{
+  DASM_API_BEGIN
+  DASM_REQUIRE(cell >= 0 && cell < f->op->n_cells && d >= 0 && d < 3, "cell/direction out of range");
+  const uint32_t id = f->h_inst[cell * 3 + d];
+  memcpy(S, f->h_S.data() + (size_t)id * f->m * f->m, sizeof(double) * f->m * f->m);
+  memcpy(lambda, f->h_lam.data() + (size_t)id * f->m, sizeof(double) * f->m);
+  DASM_API_END
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI: Chebyshev smoother  [deal.II PreconditionChebyshev restated]
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+static void
+precon_apply(dasm_cheb *c, T *dst, const T *src, const dasm_hook *post)
+{
+  dasm_op * op  = c->op;
+  dasm_ctx *ctx = op->ctx;
+  if (c->fdm)
+    fdm_vmult<T>(c->fdm, dst, src, nullptr, post);
+  else
+    {
+      // DiagonalMatrixPrePost::vmult, preconditioners.h:965-993
+      const long long n = op->n_owned;
+      vec_mul_kernel<T><<<nblocks(n), 256, 0, ctx->stream>>>(dst, (const T *)c->d_inv_diag, src, n);
+      ctx->launches++;
+      if (post != nullptr && post->kind != DASM_HOOK_NONE)
+        {
+          if (post->kind == DASM_HOOK_CHEB_UPDATE)
+            vec_cheb_update_kernel<T><<<nblocks(n), 256, 0, ctx->stream>>>(dst, dst, (const T *)post->v0, (const T *)post->v1, (T)post->f1, (T)post->f2, n);
+          else if (post->kind == DASM_HOOK_SCALE)
+            vec_scale_kernel<T><<<nblocks(n), 256, 0, ctx->stream>>>(dst, dst, (T)post->f2, n);
+          else
+            throw std::runtime_error("unsupported post hook kind");
+          ctx->launches++;
+        }
+    }
+}
+
+static void
+cheb_set_ev(dasm_cheb *c, double min_ev, double max_ev)
+{
+  c->min_ev = min_ev;
+  c->max_ev = max_ev;
+  const double alpha = c->smoothing_range > 1. ? max_ev / c->smoothing_range : std::min(0.9 * max_ev, min_ev);
+  if (c->poly == DASM_POLY_FOURTH_KIND)
+    c->delta = c->theta = max_ev;
+  else
+    {
+      c->delta = (max_ev - alpha) * 0.5;
+      c->theta = (max_ev + alpha) * 0.5;
+    }
+  c->ev_ready = true;
+}
+
+template <typename T>
+__global__ void
+initial_guess_kernel(T *v, const long long first, const long long n)
+{
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    v[i] = (T)((i + first) % 11);
+}
+
+template <typename T>
+__global__ void
+vec_add_scalar_kernel(T *v, const T a, const long long n)
+{
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    v[i] += a;
+}
+
+template <typename T>
+__global__ void
+vec_axpy_kernel(T *y, const T a, const T *x, const long long n)
+{
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    y[i] += a * x[i];
+}
+
+template <typename T>
+__global__ void
+vec_xpay_kernel(T *y, const T a, const T *x, const long long n) // y = x + a y
+{
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    y[i] = x[i] + a * y[i];
+}
+
+// symmetric tridiagonal eigenvalues (Ritz values of the Lanczos/CG process), ascending
+static std::vector<double>
+tridiagonal_eigenvalues(std::vector<double> d, std::vector<double> e)
+{
+  // implicit QL (tql1-style)
+  const int n = d.size();
+  e.push_back(0.);
+  for (int l = 0; l < n; ++l)
+    {
+      int iter = 0, m;
+      do
+        {
+          for (m = l; m < n - 1; ++m)
+            {
+              const double dd = std::fabs(d[m]) + std::fabs(d[m + 1]);
+              if (std::fabs(e[m]) <= 1e-300 + 2.3e-16 * dd)
+                break;
+            }
+          if (m != l)
+            {
+              if (++iter > 200)
+                break;
+              double g = (d[l + 1] - d[l]) / (2. * e[l]);
+              double r = std::hypot(g, 1.);
+              g        = d[m] - d[l] + e[l] / (g + (g >= 0 ? std::fabs(r) : -std::fabs(r)));
+              double s = 1., c = 1., p = 0.;
+              int    i;
+              for (i = m - 1; i >= l; --i)
+                {
+                  double f = s * e[i], b = c * e[i];
+                  r        = std::hypot(f, g);
+                  e[i + 1] = r;
+                  if (r == 0.)
+                    {
+                      d[i + 1] -= p;
+                      e[m] = 0.;
+                      break;
+                    }
+                  s        = f / r;
+                  c        = g / r;
+                  g        = d[i + 1] - p;
+                  r        = (d[i] - g) * s + 2. * c * b;
+                  p        = s * r;
+                  d[i + 1] = g + p;
+                  g        = c * r - b;
+                }
+              if (r == 0. && i >= l)
+                continue;
+              d[l] -= p;
+              e[l] = g;
+              e[m] = 0.;
+            }
+        }
+      while (m != l);
+    }
+  std::sort(d.begin(), d.end());
+  return d;
+}
+
+template <typename T>
+static void
+cheb_estimate(dasm_cheb *c)
+{
+  dasm_op *       op  = c->op;
+  dasm_ctx *      ctx = op->ctx;
+  const long long n   = op->n_owned;
+  cudaStream_t    s   = ctx->stream;
+  T *v = dev_alloc<T>(op->n_vec), *w = dev_alloc<T>(op->n_vec), *t = dev_alloc<T>(op->n_vec), *pv = dev_alloc<T>(op->n_vec);
+  CUDA_CHECK(cudaMemsetAsync(v, 0, op->n_vec * sizeof(T), s));
+  // set_initial_guess: v_i = (global index) mod 11, minus mean; constrained DoFs zeroed.  The
+  // global index is the local one plus the rank's offset (first_local_range) - with one rank 0.
+  long long first = 0, n_global = n;
+  if (ctx->n_ranks > 1)
+    {
+      // offsets via allgather of owned sizes
+      std::vector<long long> sizes(ctx->n_ranks);
+      long long *            d_sizes = dev_alloc<long long>(ctx->n_ranks);
+      CUDA_CHECK(cudaMemcpyAsync(d_sizes + ctx->rank, &n, sizeof(long long), cudaMemcpyHostToDevice, s));
+      NCCL_CHECK(ncclAllGather(d_sizes + ctx->rank, d_sizes, sizeof(long long), ncclChar, ctx->comm, s));
+      CUDA_CHECK(cudaMemcpyAsync(sizes.data(), d_sizes, sizeof(long long) * ctx->n_ranks, cudaMemcpyDeviceToHost, s));
+      CUDA_CHECK(cudaStreamSynchronize(s));
+      cudaFree(d_sizes);
+      n_global = 0;
+      for (int r = 0; r < ctx->n_ranks; ++r)
+        {
+          if (r < ctx->rank)
+            first += sizes[r];
+          n_global += sizes[r];
+        }
+    }
+  initial_guess_kernel<T><<<nblocks(n), 256, 0, s>>>(v, first, n);
+  ctx->launches++;
+  {
+    // mean value
+    T *ones = w;
+    vec_scale_kernel<T><<<nblocks(n), 256, 0, s>>>(ones, v, T(0), n);
+    vec_add_scalar_kernel<T><<<nblocks(n), 256, 0, s>>>(ones, T(1), n);
+    const double sum = device_dot<T>(ctx, v, ones, n);
+    vec_add_scalar_kernel<T><<<nblocks(n), 256, 0, s>>>(v, (T)(-sum / (double)n_global), n);
+    ctx->launches += 3;
+  }
+  if (op->n_constrained > 0)
+    {
+      vec_set_indexed_kernel<T><<<nblocks(op->n_constrained), 256, 0, s>>>(v, T(0), op->d_constrained, op->n_constrained);
+      ctx->launches++;
+    }
+  const bool symmetric = (c->fdm == nullptr) || dasm_fdm_is_symmetric(c->fdm);
+  int        algo      = c->ev_algo;
+  if (algo == DASM_EV_DEFAULT)
+    algo = symmetric ? DASM_EV_LANCZOS : DASM_EV_POWER_ITERATION;
+  if (algo == DASM_EV_POWER_ITERATION)
+    {
+      double lam = 0;
+      double nrm = std::sqrt(device_dot<T>(ctx, v, v, n));
+      vec_scale_kernel<T><<<nblocks(n), 256, 0, s>>>(v, v, (T)(1. / nrm), n);
+      ctx->launches++;
+      for (int it = 0; it < c->n_ev_it; ++it)
+        {
+          op_vmult<T>(op, t, v, nullptr, nullptr);
+          precon_apply<T>(c, w, t, nullptr);
+          lam = device_dot<T>(ctx, v, w, n);
+          nrm = std::sqrt(device_dot<T>(ctx, w, w, n));
+          vec_scale_kernel<T><<<nblocks(n), 256, 0, s>>>(v, w, (T)(1. / nrm), n);
+          ctx->launches++;
+        }
+      cheb_set_ev(c, std::fabs(lam), 1.2 * std::fabs(lam));
+    }
+  else
+    {
+      // preconditioned CG on A x = v, Ritz values from the CG coefficients
+      T *x = dev_alloc<T>(op->n_vec), *r = v, *z = w, *p = pv, *Ap = t;
+      (void)x;
+      precon_apply<T>(c, z, r, nullptr);
+      CUDA_CHECK(cudaMemcpyAsync(p, z, op->n_vec * sizeof(T), cudaMemcpyDeviceToDevice, s));
+      double              rz = device_dot<T>(ctx, r, z, n);
+      const double        r0 = std::sqrt(device_dot<T>(ctx, r, r, n));
+      std::vector<double> alphas, betas;
+      for (int it = 0; it < c->n_ev_it; ++it)
+        {
+          op_vmult<T>(op, Ap, p, nullptr, nullptr);
+          const double pAp = device_dot<T>(ctx, p, Ap, n);
+          if (pAp == 0)
+            break;
+          const double alpha = rz / pAp;
+          alphas.push_back(alpha);
+          vec_axpy_kernel<T><<<nblocks(n), 256, 0, s>>>(r, (T)(-alpha), Ap, n);
+          ctx->launches++;
+          const double rn = std::sqrt(device_dot<T>(ctx, r, r, n));
+          if (rn < 1e-10 * r0)
+            break;
+          precon_apply<T>(c, z, r, nullptr);
+          const double rz_new = device_dot<T>(ctx, r, z, n);
+          const double beta   = rz_new / rz;
+          betas.push_back(beta);
+          rz = rz_new;
+          vec_xpay_kernel<T><<<nblocks(n), 256, 0, s>>>(p, (T)beta, z, n);
+          ctx->launches++;
+        }
+      const int           kk = alphas.size();
+      std::vector<double> d(kk), e(std::max(kk - 1, 0));
+      for (int i = 0; i < kk; ++i)
+        {
+          d[i] = 1. / alphas[i] + (i > 0 ? betas[i - 1] / alphas[i - 1] : 0.);
+          if (i + 1 < kk)
+            e[i] = std::sqrt(betas[i]) / alphas[i];
+        }
+      const auto ev = tridiagonal_eigenvalues(d, e);
+      DASM_REQUIRE(!ev.empty(), "eigenvalue estimation failed");
+      cheb_set_ev(c, ev.front(), 1.2 * ev.back());
+      cudaFree(x);
+    }
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  cudaFree(v);
+  cudaFree(w);
+  cudaFree(t);
+  cudaFree(pv);
+}
+
+extern "C" int
+dasm_cheb_create(dasm_op *op, dasm_fdm *fdm, int degree, double smoothing_range, int polynomial_type, int ev_algorithm, int optimize,
+                 int eig_cg_n_iterations, dasm_cheb **out)
+{
+  DASM_API_BEGIN
+  CUDA_CHECK(cudaSetDevice(op->ctx->device));
+  DASM_REQUIRE(degree >= 1, "Chebyshev degree must be >= 1");
+  DASM_REQUIRE(polynomial_type == DASM_POLY_FIRST_KIND || polynomial_type == DASM_POLY_FOURTH_KIND, "Polynomial type is not known!");
+  DASM_REQUIRE(ev_algorithm >= 0 && ev_algorithm <= 2, "Eigen-value algorithm is not known!");
+  DASM_REQUIRE(optimize >= 0 && optimize <= 3, "optimize level not implemented"); // templates.h:497-527
+  DASM_REQUIRE(fdm == nullptr || fdm->op == op, "preconditioner belongs to another operator");
+  auto c             = new dasm_cheb;
+  c->op              = op;
+  c->fdm             = fdm;
+  c->degree          = degree;
+  c->smoothing_range = smoothing_range > 0 ? smoothing_range : 20.;
+  c->poly            = polynomial_type;
+  c->ev_algo         = ev_algorithm;
+  c->optimize        = optimize;
+  c->n_ev_it         = eig_cg_n_iterations > 0 ? eig_cg_n_iterations : 40; // templates.h:109
+  const size_t bytes = std::max<size_t>(1, (size_t)op->n_vec) * op->esize();
+  for (void **p : {&c->t1, &c->t2, &c->xold, &c->xin, &c->bin})
+    {
+      CUDA_CHECK(cudaMalloc(p, bytes));
+      CUDA_CHECK(cudaMemsetAsync(*p, 0, bytes, op->ctx->stream));
+    }
+  if (fdm == nullptr)
+    {
+      CUDA_CHECK(cudaMalloc(&c->d_inv_diag, bytes));
+      DISPATCH_TYPE(op->ntype, op_inverse_diagonal<T>(op, (T *)c->d_inv_diag));
+    }
+  *out = c;
+  DASM_API_END
+}
+
+extern "C" int
+dasm_cheb_destroy(dasm_cheb *c)
+{
+  DASM_API_BEGIN
+  if (!c)
+    return 0;
+  cudaStreamSynchronize(c->op->ctx->stream);
+  for (void *p : {c->t1, c->t2, c->xold, c->xin, c->bin, c->d_inv_diag})
+    cudaFree(p);
+  delete c;
+  DASM_API_END
+}
+
+extern "C" int
+dasm_cheb_estimate_eigenvalues(dasm_cheb *c, double *min_ev, double *max_ev)
+{
+  DASM_API_BEGIN
+  CUDA_CHECK(cudaSetDevice(c->op->ctx->device));
+  DISPATCH_TYPE(c->op->ntype, cheb_estimate<T>(c));
+  if (min_ev)
+    *min_ev = c->min_ev;
+  if (max_ev)
+    *max_ev = c->max_ev;
+  DASM_API_END
+}
+
+extern "C" int
+dasm_cheb_set_eigenvalues(dasm_cheb *c, double min_ev, double max_ev)
+{
+  DASM_API_BEGIN
+  cheb_set_ev(c, min_ev, max_ev);
+  DASM_API_END
+}
+
+// x (in/out) = dst.  first_is_step: x1 = x0 + f2 P^-1 (b - A x0), else x1 = f2 P^-1 b.
+template <typename T>
+static void
+cheb_run(dasm_cheb *c, T *x_user, const T *b, bool first_is_step)
+{
+  dasm_op *       op  = c->op;
+  dasm_ctx *      ctx = op->ctx;
+  const long long n   = op->n_owned;
+  if (!c->ev_ready)
+    cheb_estimate<T>(c);
+  T *t1 = (T *)c->t1, *t2 = (T *)c->t2;
+  const double f2_0 = (c->poly == DASM_POLY_FOURTH_KIND) ? 4. / (3. * c->theta) : 1. / c->theta;
+  const int    n_terms = (c->degree < 2 || std::fabs(c->delta) < 1e-40) ? 1 : c->degree;
+
+  // buffers: cur = current iterate, old = previous iterate.  The new iterate is produced in t2 by
+  // the preconditioner sweep + update and the three buffers rotate; the last term writes to x_user.
+  T *cur = x_user, *old = (T *)c->xold, *nxt = t2, *spare = nullptr;
+  (void)spare;
+  dasm_hook res_hook  = {DASM_HOOK_RESIDUAL, 0, 0, b, nullptr};
+  bool      have_old  = false;
+  double    rho_old   = 0, sigma = 0;
+  if (n_terms > 1)
+    {
+      sigma   = c->theta / c->delta;
+      rho_old = 1. / sigma;
+    }
+  for (int term = 0; term < n_terms; ++term)
+    {
+      double f1 = 0, f2 = f2_0;
+      if (term > 0)
+        {
+          const int j = term - 1;
+          if (c->poly == DASM_POLY_FOURTH_KIND)
+            {
+              f1 = (2 * j + 1.) / (2 * j + 5.);
+              f2 = (8 * j + 12.) / (c->theta * (2 * j + 5.));
+            }
+          else
+            {
+              const double rho = 1. / (2. * sigma - rho_old);
+              f1               = rho * rho_old;
+              f2               = 2. * rho / c->delta;
+              rho_old          = rho;
+            }
+        }
+      const T *rhs_for_P;
+      if (term == 0 && !first_is_step)
+        rhs_for_P = b; // x0 = 0: residual is b
+      else
+        {
+          op_vmult<T>(op, t1, cur, nullptr, &res_hook); // t1 = b - A cur
+          rhs_for_P = t1;
+        }
+      // nxt = P^-1 rhs, then nxt = (1+f1) cur - f1 old + f2 nxt
+      dasm_hook upd;
+      if (term == 0 && !first_is_step)
+        upd = {DASM_HOOK_SCALE, 0, f2, nullptr, nullptr};
+      else
+        upd = {DASM_HOOK_CHEB_UPDATE, f1, f2, cur, (have_old && f1 != 0.) ? old : nullptr};
+      precon_apply<T>(c, nxt, rhs_for_P, &upd);
+      // rotate: old <- cur, cur <- nxt, nxt <- (old buffer)
+      T *tmp = old;
+      old    = cur;
+      cur    = nxt;
+      nxt    = tmp;
+      have_old = (term > 0) || first_is_step;
+      if (nxt == x_user) // never hand the user's buffer out as scratch before the end
+        {
+          // old buffer was x_user two rotations ago; fine to reuse: its content is dead
+        }
+    }
+  if (cur != x_user)
+    {
+      CUDA_CHECK(cudaMemcpyAsync(x_user, cur, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+  CUDA_CHECK(cudaGetLastError());
+}
+
+extern "C" int
+dasm_cheb_vmult(dasm_cheb *c, void *dst, const void *src)
+{
+  DASM_API_BEGIN
+  CUDA_CHECK(cudaSetDevice(c->op->ctx->device));
+  DISPATCH_TYPE(c->op->ntype, cheb_run<T>(c, (T *)dst, (const T *)src, false));
+  DASM_API_END
+}
+
+extern "C" int
+dasm_cheb_step(dasm_cheb *c, void *dst, const void *src)
+{
+  DASM_API_BEGIN
+  CUDA_CHECK(cudaSetDevice(c->op->ctx->device));
+  DISPATCH_TYPE(c->op->ntype, cheb_run<T>(c, (T *)dst, (const T *)src, true));
+  DASM_API_END
+}
+
+template <typename T>
+static void
+cheb_host(dasm_cheb *c, double *dst, const double *src, bool step)
+{
+  dasm_op *       op = c->op;
+  cudaStream_t    s  = op->ctx->stream;
+  const long long n  = op->n_owned;
+  // host vectors are double (the reference's outer vectors); converted on the device
+  static thread_local double *d_stage = nullptr;
+  static thread_local size_t  stage_n = 0;
+  if (stage_n < (size_t)n)
+    {
+      if (d_stage)
+        cudaFree(d_stage);
+      CUDA_CHECK(cudaMalloc(&d_stage, (size_t)n * sizeof(double)));
+      stage_n = n;
+    }
+  T *x = (T *)c->xin, *b = (T *)c->bin;
+  CUDA_CHECK(cudaMemcpyAsync(d_stage, src, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s));
+  vec_convert_kernel<T, double><<<nblocks(n), 256, 0, s>>>(b, d_stage, n);
+  op->ctx->launches++;
+  if (step)
+    {
+      CUDA_CHECK(cudaMemcpyAsync(d_stage, dst, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s));
+      vec_convert_kernel<T, double><<<nblocks(n), 256, 0, s>>>(x, d_stage, n);
+      op->ctx->launches++;
+    }
+  cheb_run<T>(c, x, b, step);
+  vec_convert_kernel<double, T><<<nblocks(n), 256, 0, s>>>(d_stage, x, n);
+  op->ctx->launches++;
+  CUDA_CHECK(cudaMemcpyAsync(dst, d_stage, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+}
+
+extern "C" int
+dasm_cheb_step_host(dasm_cheb *c, double *dst_owned, const double *src_owned)
+{
+  DASM_API_BEGIN
+  CUDA_CHECK(cudaSetDevice(c->op->ctx->device));
+  DISPATCH_TYPE(c->op->ntype, cheb_host<T>(c, dst_owned, src_owned, true));
+  DASM_API_END
+}
+
+extern "C" int
+dasm_cheb_vmult_host(dasm_cheb *c, double *dst_owned, const double *src_owned)
+{
+  DASM_API_BEGIN
+  CUDA_CHECK(cudaSetDevice(c->op->ctx->device));
+  DISPATCH_TYPE(c->op->ntype, cheb_host<T>(c, dst_owned, src_owned, false));
+  DASM_API_END
+}

@@ -1,0 +1,597 @@
+// Structured hexahedral mesh (Cartesian / sine-deformed / Kershaw), its brick partition over ranks,
+// the native DoF numbering with 3^dim-compressed indices, geometry factors and harmonic extents.
+//
+// Reference behaviour restated (file:line into the reference tree):
+//   mesh + mapping of the benchmark driver      matrix_free_loop_08.likwid.cc:160-199
+//   Kershaw map                                 include/kershaw.h:4-80
+//   3^dim compressed DoF indices per cell       include/vector_access_reduced.h:30-164,
+//                                               include/reduced_access.h:154-285
+//   merged geometry coefficients                include/operator.h:674-711
+//   harmonic cell / patch extents               include/grid_tools.h:11-138
+//
+// Numbering ("owner-cell numbering", the data-locality numbering of this library; the reference uses
+// DoFRenumbering::matrix_free_data_locality, matrix_free_loop_08.likwid.cc:216-222, for the same
+// purpose): every mesh entity (vertex/line/quad/hex interior) is owned by the cell for which it is
+// a "lower" entity (or an upper-boundary entity of the last cell in a non-periodic direction).  Cells
+// are processed brick-major; each cell numbers its owned entities contiguously in lexicographic
+// entity order, so all DoFs of an entity are contiguous and a cell needs only 27 start indices.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <vector>
+
+#include "basis.h"
+
+namespace dasm
+{
+  constexpr uint32_t INVALID_INDEX = 0xFFFFFFFFu;
+
+  enum MapKind
+  {
+    MAP_CARTESIAN = 0,
+    MAP_SINE      = 1,
+    MAP_KERSHAW   = 2
+  };
+
+  struct MeshParams
+  {
+    int    nc[3]       = {1, 1, 1};  // global cells per direction
+    int    periodic[3] = {0, 0, 0};
+    int    dirichlet   = 1;          // non-periodic boundaries: 1 = homogeneous Dirichlet, 0 = natural
+    double length[3]   = {1, 1, 1};
+    int    map_kind    = MAP_CARTESIAN;
+    double map_par[4]  = {0, 0, 0, 0};
+    int    part[3]     = {1, 1, 1};  // ranks per direction (brick partition)
+    int    rank        = 0;
+    int    brick[3]    = {4, 4, 4};  // cells per thread-block brick
+  };
+
+  inline double
+  kershaw_right(double eps, double x)
+  {
+    return (x <= 0.5) ? (2 - eps) * x : 1 + eps * (x - 1);
+  }
+  inline double
+  kershaw_left(double eps, double x)
+  {
+    return 1 - kershaw_right(eps, 1 - x);
+  }
+  inline double
+  kershaw_step(double x)
+  {
+    if (x <= 0)
+      return 0;
+    if (x >= 1)
+      return 1;
+    return ((6 * x - 15) * x + 10) * x * x * x;
+  }
+
+  struct ExchangeList
+  {
+    int                   peer = -1;
+    std::vector<uint32_t> send_start, send_len; // owned ranges this rank sends for ghost update
+    std::vector<uint32_t> recv_start, recv_len; // ghost ranges filled from the peer
+    size_t                n_send = 0, n_recv = 0;
+  };
+
+  class Mesh
+  {
+  public:
+    MeshParams p;
+    int        lo[3], hi[3], nl[3]; // local cell box (global coordinates) and its size
+    int        S[3];                // entity slot lattice size per direction
+    size_t     n_cells = 0;         // local cells
+    std::vector<std::array<int, 3>> cell_ijk; // processing order -> global cell coordinates
+    std::vector<uint32_t>           brick_ptr; // first cell of each brick (+ end)
+
+    explicit Mesh(const MeshParams &params)
+      : p(params)
+    {
+      int r = p.rank;
+      for (int d = 0; d < 3; ++d)
+        {
+          const int pr = r % p.part[d];
+          r /= p.part[d];
+          lo[d] = (int)((long)p.nc[d] * pr / p.part[d]);
+          hi[d] = (int)((long)p.nc[d] * (pr + 1) / p.part[d]);
+          nl[d] = hi[d] - lo[d];
+          S[d]  = 2 * p.nc[d] + (p.periodic[d] ? 0 : 1);
+        }
+      n_cells = (size_t)nl[0] * nl[1] * nl[2];
+      cell_ijk.reserve(n_cells);
+      const int *B = p.brick;
+      for (int bz = 0; bz < nl[2]; bz += B[2])
+        for (int by = 0; by < nl[1]; by += B[1])
+          for (int bx = 0; bx < nl[0]; bx += B[0])
+            {
+              brick_ptr.push_back(cell_ijk.size());
+              for (int z = bz; z < std::min(bz + B[2], nl[2]); ++z)
+                for (int y = by; y < std::min(by + B[1], nl[1]); ++y)
+                  for (int x = bx; x < std::min(bx + B[0], nl[0]); ++x)
+                    cell_ijk.push_back({lo[0] + x, lo[1] + y, lo[2] + z});
+            }
+      brick_ptr.push_back(cell_ijk.size());
+    }
+
+    int
+    n_ranks() const
+    {
+      return p.part[0] * p.part[1] * p.part[2];
+    }
+
+    int
+    rank_of_cell(const int c[3]) const
+    {
+      int r = 0;
+      for (int d = 2; d >= 0; --d)
+        {
+          // inverse of lo = nc*pr/part
+          int pr = (int)(((long)c[d] * p.part[d]) / p.nc[d]);
+          while ((long)p.nc[d] * pr / p.part[d] > c[d])
+            --pr;
+          while ((long)p.nc[d] * (pr + 1) / p.part[d] <= c[d])
+            ++pr;
+          r = r * p.part[d] + pr;
+        }
+      return r;
+    }
+
+    bool
+    neighbor(const int c[3], int d, int side, int out[3]) const
+    {
+      out[0] = c[0];
+      out[1] = c[1];
+      out[2] = c[2];
+      out[d] += side ? 1 : -1;
+      if (out[d] < 0 || out[d] >= p.nc[d])
+        {
+          if (!p.periodic[d])
+            return false;
+          out[d] = (out[d] + p.nc[d]) % p.nc[d];
+        }
+      return true;
+    }
+
+    // ---- geometry -----------------------------------------------------------------------
+    void
+    map_point(const double X[3], double x[3]) const
+    {
+      if (p.map_kind == MAP_CARTESIAN)
+        {
+          x[0] = X[0];
+          x[1] = X[1];
+          x[2] = X[2];
+        }
+      else if (p.map_kind == MAP_SINE)
+        {
+          const double pi = 3.14159265358979323846;
+          for (int d = 0; d < 3; ++d)
+            x[d] = X[d] + std::sin(2 * pi * X[(d + 1) % 3]) * std::sin(pi * X[d]) * 0.1;
+        }
+      else
+        {
+          const double epsy = p.map_par[0], epsz = p.map_par[1];
+          const double xx = X[0], y = X[1], z = X[2];
+          int          layer = (int)(xx * 6.0);
+          if (layer > 5)
+            layer = 5;
+          const double lambda = (xx - layer / 6.0) * 6;
+          double       Y = 0, Z = 0;
+          switch (layer)
+            {
+              case 0:
+                Y = kershaw_left(epsy, y);
+                Z = kershaw_left(epsz, z);
+                break;
+              case 1:
+              case 4:
+                Y = (1 - kershaw_step(lambda)) * kershaw_left(epsy, y) + kershaw_step(lambda) * kershaw_right(epsy, y);
+                Z = (1 - kershaw_step(lambda)) * kershaw_left(epsz, z) + kershaw_step(lambda) * kershaw_right(epsz, z);
+                break;
+              case 2:
+                Y = (1 - kershaw_step(lambda / 2)) * kershaw_right(epsy, y) + kershaw_step(lambda / 2) * kershaw_left(epsy, y);
+                Z = (1 - kershaw_step(lambda / 2)) * kershaw_right(epsz, z) + kershaw_step(lambda / 2) * kershaw_left(epsz, z);
+                break;
+              case 3:
+                Y = (1 - kershaw_step((1 + lambda) / 2)) * kershaw_right(epsy, y) + kershaw_step((1 + lambda) / 2) * kershaw_left(epsy, y);
+                Z = (1 - kershaw_step((1 + lambda) / 2)) * kershaw_right(epsz, z) + kershaw_step((1 + lambda) / 2) * kershaw_left(epsz, z);
+                break;
+              default:
+                Y = kershaw_right(epsy, y);
+                Z = kershaw_right(epsz, z);
+                break;
+            }
+          x[0] = xx;
+          x[1] = Y;
+          x[2] = Z;
+        }
+    }
+
+    bool
+    is_cartesian() const
+    {
+      return p.map_kind == MAP_CARTESIAN;
+    }
+
+    double
+    h(int d) const
+    {
+      return p.length[d] / p.nc[d];
+    }
+
+    // 27 support points of the Q2 geometry interpolant of a cell (MappingQCache degree 2)
+    void
+    cell_support_points(const int c[3], double X[27][3]) const
+    {
+      static const double nodes[3] = {0., 0.5, 1.};
+      for (int k = 0; k < 3; ++k)
+        for (int j = 0; j < 3; ++j)
+          for (int i = 0; i < 3; ++i)
+            {
+              const double ref[3] = {(c[0] + nodes[i]) * h(0), (c[1] + nodes[j]) * h(1), (c[2] + nodes[k]) * h(2)};
+              map_point(ref, X[9 * k + 3 * j + i]);
+            }
+    }
+
+    // average distance between opposite faces in direction d (grid_tools.h:11-50), Gauss n x n rule
+    double
+    harmonic_extent(const int c[3], int d, const Basis1D &b) const
+    {
+      if (is_cartesian())
+        return h(d);
+      double X[27][3];
+      cell_support_points(c, X);
+      const std::vector<double> q2nodes = {0., 0.5, 1.};
+      std::vector<double>       V, D;
+      lagrange(q2nodes, b.qp, V, D); // [q*3+i]
+      const int d1 = (d + 1) % 3, d2 = (d + 2) % 3;
+      double    ext = 0;
+      for (int qa = 0; qa < b.n; ++qa)
+        for (int qb = 0; qb < b.n; ++qb)
+          {
+            double x0[3] = {0, 0, 0}, x1[3] = {0, 0, 0};
+            for (int ia = 0; ia < 3; ++ia)
+              for (int ib = 0; ib < 3; ++ib)
+                {
+                  const double w = V[qa * 3 + ia] * V[qb * 3 + ib];
+                  int          idx0[3], idx1[3];
+                  idx0[d] = 0;
+                  idx1[d] = 2;
+                  idx0[d1] = idx1[d1] = ia;
+                  idx0[d2] = idx1[d2] = ib;
+                  const double *P0 = X[9 * idx0[2] + 3 * idx0[1] + idx0[0]];
+                  const double *P1 = X[9 * idx1[2] + 3 * idx1[1] + idx1[0]];
+                  for (int e = 0; e < 3; ++e)
+                    {
+                      x0[e] += w * P0[e];
+                      x1[e] += w * P1[e];
+                    }
+                }
+            const double dist = std::sqrt((x0[0] - x1[0]) * (x0[0] - x1[0]) + (x0[1] - x1[1]) * (x0[1] - x1[1]) +
+                                          (x0[2] - x1[2]) * (x0[2] - x1[2]));
+            ext += dist * b.qw[qa] * b.qw[qb];
+          }
+      return ext;
+    }
+
+    // merged coefficients JxW * J^-1 J^-T at the n^3 Gauss points: out[comp*n3 + q], comp order
+    // xx,xy,xz,yy,yz,zz (operator.h:696-704)
+    void
+    merged_coefficients(const int c[3], const Basis1D &b, double *out) const
+    {
+      const int n = b.n, n3 = n * n * n;
+      double    X[27][3];
+      cell_support_points(c, X);
+      const std::vector<double> q2nodes = {0., 0.5, 1.};
+      std::vector<double>       V, D;
+      lagrange(q2nodes, b.qp, V, D);
+      for (int qz = 0; qz < n; ++qz)
+        for (int qy = 0; qy < n; ++qy)
+          for (int qx = 0; qx < n; ++qx)
+            {
+              double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}; // J[d][e] = dx_d/dxi_e
+              for (int k = 0; k < 3; ++k)
+                for (int j = 0; j < 3; ++j)
+                  for (int i = 0; i < 3; ++i)
+                    {
+                      const double *P  = X[9 * k + 3 * j + i];
+                      const double  gx = D[qx * 3 + i] * V[qy * 3 + j] * V[qz * 3 + k];
+                      const double  gy = V[qx * 3 + i] * D[qy * 3 + j] * V[qz * 3 + k];
+                      const double  gz = V[qx * 3 + i] * V[qy * 3 + j] * D[qz * 3 + k];
+                      for (int dd = 0; dd < 3; ++dd)
+                        {
+                          J[dd][0] += P[dd] * gx;
+                          J[dd][1] += P[dd] * gy;
+                          J[dd][2] += P[dd] * gz;
+                        }
+                    }
+              const double det = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) - J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0]) +
+                                 J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+              double I[3][3];
+              I[0][0] = (J[1][1] * J[2][2] - J[1][2] * J[2][1]) / det;
+              I[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) / det;
+              I[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) / det;
+              I[1][0] = (J[1][2] * J[2][0] - J[1][0] * J[2][2]) / det;
+              I[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) / det;
+              I[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) / det;
+              I[2][0] = (J[1][0] * J[2][1] - J[1][1] * J[2][0]) / det;
+              I[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) / det;
+              I[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) / det;
+              const double jxw = det * b.qw[qx] * b.qw[qy] * b.qw[qz];
+              const int    q   = (qz * n + qy) * n + qx;
+              int          cc  = 0;
+              for (int dd = 0; dd < 3; ++dd)
+                for (int e = dd; e < 3; ++e, ++cc)
+                  {
+                    double s = 0;
+                    for (int f = 0; f < 3; ++f)
+                      s += I[dd][f] * I[e][f];
+                    out[cc * n3 + q] = jxw * s;
+                  }
+            }
+    }
+
+    // ---- DoF numbering ------------------------------------------------------------------
+    struct Numbering
+    {
+      int                   k        = 0;
+      uint32_t              n_owned  = 0; // locally owned DoFs
+      uint32_t              n_ghost  = 0; // ghost DoFs appended after the owned range
+      std::vector<uint32_t> cidx;         // [cell*27+e] start index, INVALID if constrained (Dirichlet)
+      std::vector<uint32_t> cidx_plain;   // same, constrained entities keep their index
+      std::vector<uint32_t> constrained;  // list of constrained owned DoFs
+      std::vector<ExchangeList> exchange; // per neighbouring rank
+    };
+
+    static int
+    entity_size(int e, int k)
+    {
+      int s = 1;
+      for (int d = 0; d < 3; ++d, e /= 3)
+        if (e % 3 == 1)
+          s *= (k - 1);
+      return s;
+    }
+
+    // owner cell of slot s (global)
+    void
+    owner_cell(const int s[3], int c[3]) const
+    {
+      for (int d = 0; d < 3; ++d)
+        c[d] = std::min(s[d] / 2, p.nc[d] - 1);
+    }
+
+    bool
+    slot_on_dirichlet_boundary(const int s[3]) const
+    {
+      if (!p.dirichlet)
+        return false;
+      for (int d = 0; d < 3; ++d)
+        if (!p.periodic[d] && (s[d] == 0 || s[d] == S[d] - 1))
+          return true;
+      return false;
+    }
+
+    void
+    cell_slot(const int c[3], int e, int s[3]) const
+    {
+      for (int d = 0; d < 3; ++d, e /= 3)
+        {
+          s[d] = 2 * c[d] + (e % 3);
+          if (p.periodic[d])
+            s[d] %= S[d];
+        }
+    }
+
+    Numbering
+    number_dofs(int k) const
+    {
+      Numbering nb;
+      nb.k = k;
+      // processing index of local cells by local lexicographic position
+      std::vector<uint32_t> proc_of_local(n_cells);
+      for (size_t i = 0; i < n_cells; ++i)
+        {
+          const auto &c = cell_ijk[i];
+          proc_of_local[((size_t)(c[2] - lo[2]) * nl[1] + (c[1] - lo[1])) * nl[0] + (c[0] - lo[0])] = i;
+        }
+      // base offset of each cell + offset of each owned entity inside the cell
+      std::vector<uint32_t> base(n_cells + 1, 0);
+      // offset of owned entity code e within a cell = sum of sizes of owned entities with smaller
+      // code; depends only on which directions the cell is the last one of a non-periodic direction
+      uint32_t offset_table[8][28];
+      for (int t = 0; t < 8; ++t)
+        {
+          uint32_t off = 0;
+          for (int e = 0; e <= 27; ++e)
+            {
+              offset_table[t][e] = off;
+              if (e == 27)
+                break;
+              bool owned = true;
+              for (int d = 0, ee = e; d < 3; ++d, ee /= 3)
+                if (ee % 3 == 2 && !((t >> d) & 1))
+                  owned = false;
+              if (owned)
+                off += entity_size(e, k);
+            }
+        }
+      auto owned_offset = [&](const int c[3], int e_owned, int) {
+        int t = 0;
+        for (int d = 0; d < 3; ++d)
+          if (!p.periodic[d] && c[d] == p.nc[d] - 1)
+            t |= 1 << d;
+        return offset_table[t][e_owned];
+      };
+      for (size_t i = 0; i < n_cells; ++i)
+        {
+          const int c[3] = {cell_ijk[i][0], cell_ijk[i][1], cell_ijk[i][2]};
+          base[i + 1]    = base[i] + owned_offset(c, 27, k);
+        }
+      nb.n_owned = base[n_cells];
+
+      const int my_rank = p.rank;
+      // ghost entities: key (owner rank, owner cell lexicographic global id, entity code) -> index
+      std::map<std::array<long, 3>, uint32_t> ghost_map;
+      struct Ref
+      {
+        size_t cell;
+        int    e;
+        std::array<long, 3> key;
+      };
+      std::vector<Ref> ghost_refs;
+      nb.cidx.assign(n_cells * 27, INVALID_INDEX);
+      nb.cidx_plain.assign(n_cells * 27, INVALID_INDEX);
+      for (size_t i = 0; i < n_cells; ++i)
+        {
+          const int c[3] = {cell_ijk[i][0], cell_ijk[i][1], cell_ijk[i][2]};
+          for (int e = 0; e < 27; ++e)
+            {
+              int s[3], oc[3];
+              cell_slot(c, e, s);
+              owner_cell(s, oc);
+              int eo = 0; // entity code relative to the owner cell
+              for (int d = 2; d >= 0; --d)
+                eo = eo * 3 + (s[d] - 2 * oc[d]);
+              const int orank = rank_of_cell(oc);
+              if (orank == my_rank)
+                {
+                  const size_t oi = proc_of_local[((size_t)(oc[2] - lo[2]) * nl[1] + (oc[1] - lo[1])) * nl[0] + (oc[0] - lo[0])];
+                  const uint32_t idx = base[oi] + owned_offset(oc, eo, k);
+                  nb.cidx_plain[i * 27 + e] = idx;
+                  if (!slot_on_dirichlet_boundary(s))
+                    nb.cidx[i * 27 + e] = idx;
+                  else if (oi == i)
+                    for (int t = 0; t < entity_size(e, k); ++t)
+                      nb.constrained.push_back(idx + t);
+                }
+              else
+                {
+                  const long gid = ((long)oc[2] * p.nc[1] + oc[1]) * p.nc[0] + oc[0];
+                  ghost_refs.push_back({i, e, {orank, gid, eo}});
+                  ghost_map[{orank, gid, eo}] = 0;
+                }
+            }
+        }
+      // number ghosts grouped by owner rank, then owner cell id, then entity code
+      uint32_t next = nb.n_owned;
+      {
+        int           cur_rank = -1;
+        ExchangeList *cur      = nullptr;
+        for (auto &kv : ghost_map)
+          {
+            const int sz = entity_size((int)kv.first[2], k);
+            kv.second    = next;
+            if ((int)kv.first[0] != cur_rank)
+              {
+                cur_rank = (int)kv.first[0];
+                nb.exchange.emplace_back();
+                cur       = &nb.exchange.back();
+                cur->peer = cur_rank;
+              }
+            if (sz > 0)
+              {
+                cur->recv_start.push_back(next);
+                cur->recv_len.push_back(sz);
+                cur->n_recv += sz;
+              }
+            next += sz;
+          }
+      }
+      nb.n_ghost = next - nb.n_owned;
+      for (const auto &r : ghost_refs)
+        {
+          const uint32_t idx = ghost_map[r.key];
+          int            s[3];
+          const int      c[3] = {cell_ijk[r.cell][0], cell_ijk[r.cell][1], cell_ijk[r.cell][2]};
+          cell_slot(c, r.e, s);
+          nb.cidx_plain[r.cell * 27 + r.e] = idx;
+          if (!slot_on_dirichlet_boundary(s))
+            nb.cidx[r.cell * 27 + r.e] = idx;
+        }
+      // send lists: entities owned by this rank that are touched by cells of other ranks.  A cell of
+      // rank q touches an entity of my cell oc iff it is one of the <= 26 neighbours "below" the
+      // slot; enumerate, for every local cell and owned entity, the cells touching the slot.
+      if (n_ranks() > 1)
+        {
+          std::map<int, std::map<std::array<long, 3>, std::pair<uint32_t, uint32_t>>> send; // peer -> key -> (start,len)
+          for (size_t i = 0; i < n_cells; ++i)
+            {
+              const int c[3] = {cell_ijk[i][0], cell_ijk[i][1], cell_ijk[i][2]};
+              bool      near_boundary = false;
+              for (int d = 0; d < 3; ++d)
+                if (c[d] - lo[d] < 1 || hi[d] - c[d] <= 1)
+                  near_boundary = true;
+              if (!near_boundary)
+                continue;
+              for (int e = 0; e < 27; ++e)
+                {
+                  // owned by cell i?
+                  bool owned = true;
+                  for (int d = 0, ee = e; d < 3; ++d, ee /= 3)
+                    if (ee % 3 == 2 && !(!p.periodic[d] && c[d] == p.nc[d] - 1))
+                      owned = false;
+                  if (!owned || entity_size(e, k) == 0)
+                    continue;
+                  int s[3];
+                  cell_slot(c, e, s);
+                  // cells touching slot s: per direction, odd slot -> cell s/2 only; even slot -> cells s/2-1 and s/2
+                  int cand[3][2], ncand[3];
+                  for (int d = 0; d < 3; ++d)
+                    {
+                      ncand[d] = 0;
+                      if (s[d] % 2 == 1)
+                        cand[d][ncand[d]++] = s[d] / 2;
+                      else
+                        {
+                          int a = s[d] / 2 - 1, b2 = s[d] / 2;
+                          if (p.periodic[d])
+                            {
+                              a  = (a + p.nc[d]) % p.nc[d];
+                              b2 = b2 % p.nc[d];
+                            }
+                          if (a >= 0 && a < p.nc[d])
+                            cand[d][ncand[d]++] = a;
+                          if (b2 >= 0 && b2 < p.nc[d] && (ncand[d] == 0 || cand[d][0] != b2))
+                            cand[d][ncand[d]++] = b2;
+                        }
+                    }
+                  const long gid = ((long)c[2] * p.nc[1] + c[1]) * p.nc[0] + c[0];
+                  for (int a = 0; a < ncand[0]; ++a)
+                    for (int b2 = 0; b2 < ncand[1]; ++b2)
+                      for (int g = 0; g < ncand[2]; ++g)
+                        {
+                          const int tc[3] = {cand[0][a], cand[1][b2], cand[2][g]};
+                          const int q     = rank_of_cell(tc);
+                          if (q != my_rank)
+                            send[q][{(long)my_rank, gid, (long)e}] = {base[i] + owned_offset(c, e, k), (uint32_t)entity_size(e, k)};
+                        }
+                }
+            }
+          for (auto &pr : send)
+            {
+              ExchangeList *ex = nullptr;
+              for (auto &x : nb.exchange)
+                if (x.peer == pr.first)
+                  ex = &x;
+              if (!ex)
+                {
+                  nb.exchange.emplace_back();
+                  ex       = &nb.exchange.back();
+                  ex->peer = pr.first;
+                }
+              for (auto &kv : pr.second)
+                {
+                  ex->send_start.push_back(kv.second.first);
+                  ex->send_len.push_back(kv.second.second);
+                  ex->n_send += kv.second.second;
+                }
+            }
+        }
+      return nb;
+    }
+  };
+} // namespace dasm

@@ -1,0 +1,194 @@
+/* libdasm - C ABI of the B200-native multigrid-smoother hot path of dealii-asm.
+ *
+ * The reference (peterrum/dealii-asm) has no FFI layer: its boundary is the C++ class surface
+ * LaplaceOperatorMatrixFree / ASPoissonPreconditioner / PreconditionChebyshev built by the factories
+ * create_fdm_preconditioner / create_system_preconditioner.  Every entry point below cites the
+ * reference interface it replaces (file:line into the reference tree); the C++ mirror classes with
+ * the reference's names live in include/dasm/ (operator.h, preconditioners.h, precondition.h) and are
+ * thin wrappers over these calls.  INTEGRATION.md shows the binding a maintainer would add.
+ *
+ * Conventions: plain pointers and sizes only; every call returns 0 on success and non-zero on
+ * error with the message available from dasm_last_error() (the C++ wrappers rethrow it, mirroring
+ * deal.II's AssertThrow).  Vector arguments named dst/src/vec are DEVICE pointers to
+ * dasm_op_vec_size() numbers of the operator's number type (locally owned DoFs first, then ghost
+ * DoFs, like LinearAlgebra::distributed::Vector); the *_host variants take HOST pointers of the
+ * locally owned size and include the host<->device copies.  All work is enqueued on the context's
+ * CUDA stream; dasm_ctx_sync() waits for it.  Objects are not re-entrant (one host thread per
+ * context), matching the reference's mutable scratch members (matrix_free.h:1545-1564).
+ */
+#ifndef DASM_H
+#define DASM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C"
+{
+#endif
+
+  typedef struct dasm_ctx  dasm_ctx;
+  typedef struct dasm_mesh dasm_mesh;
+  typedef struct dasm_op   dasm_op;
+  typedef struct dasm_fdm  dasm_fdm;
+  typedef struct dasm_cheb dasm_cheb;
+
+  enum dasm_number_type
+  {
+    DASM_F64 = 0,
+    DASM_F32 = 1
+  };
+  /* Restrictors::WeightingType, include/restrictors.h:8-15 */
+  enum dasm_weight_type
+  {
+    DASM_WEIGHT_NONE = 0,
+    DASM_WEIGHT_PRE  = 1,
+    DASM_WEIGHT_POST = 2,
+    DASM_WEIGHT_RAS  = 3,
+    DASM_WEIGHT_SYMM = 4
+  };
+  /* "weight sequence", include/precondition.templates.h:201-203 */
+  enum dasm_weight_sequence
+  {
+    DASM_WSEQ_GLOBAL     = 0,
+    DASM_WSEQ_LOCAL      = 1,
+    DASM_WSEQ_DG         = 2,
+    DASM_WSEQ_COMPRESSED = 3
+  };
+  enum dasm_map_kind
+  {
+    DASM_MAP_CARTESIAN = 0, /* use cartesian mesh = true,  matrix_free_loop_08.likwid.cc:185-191 */
+    DASM_MAP_SINE      = 1, /* use cartesian mesh = false, matrix_free_loop_08.likwid.cc:193-199 */
+    DASM_MAP_KERSHAW   = 2  /* include/kershaw.h:39-80; map_params = {eps_y, eps_z}            */
+  };
+  enum dasm_polynomial_type
+  {
+    DASM_POLY_FIRST_KIND  = 0,
+    DASM_POLY_FOURTH_KIND = 1
+  };
+  enum dasm_ev_algorithm
+  {
+    DASM_EV_LANCZOS         = 0,
+    DASM_EV_POWER_ITERATION = 1,
+    DASM_EV_DEFAULT         = 2 /* lanczos if A and P symmetric else power iteration (templates.h:113-114) */
+  };
+  /* The pre/post DoF-range hooks of the reference are host lambdas
+   * (std::function<void(unsigned,unsigned)>, operator.h:1367-1373, matrix_free.h:960-986); a kernel
+   * cannot call them, so the updates PreconditionChebyshev/PreconditionRelaxation actually pass are
+   * enumerated here and fused into the kernels. */
+  enum dasm_hook_kind
+  {
+    DASM_HOOK_NONE        = 0,
+    DASM_HOOK_ZERO_DST    = 1, /* pre : dst = 0                                            */
+    DASM_HOOK_RESIDUAL    = 2, /* post: dst = v0 - dst                      (t = b - A x)   */
+    DASM_HOOK_CHEB_UPDATE = 3, /* post: dst = (1+f1) v0 - f1 v1 + f2 dst    (x+ from P^-1 t) */
+    DASM_HOOK_SCALE       = 4  /* post: dst = f2 dst                                        */
+  };
+  typedef struct dasm_hook
+  {
+    int         kind;
+    double      f1, f2;
+    const void *v0, *v1; /* device vectors of the operator's number type */
+  } dasm_hook;
+
+  const char *dasm_last_error(void);
+  const char *dasm_version(void);
+
+  /* ---- context ------------------------------------------------------------------------------ */
+  int dasm_ctx_create(int device, dasm_ctx **out);
+  int dasm_ctx_destroy(dasm_ctx *ctx);
+  int dasm_ctx_sync(dasm_ctx *ctx);
+  /* number of kernels this library has launched on the context since creation */
+  long long dasm_ctx_launch_count(const dasm_ctx *ctx);
+  /* the cudaStream_t all work of this context is enqueued on (for CUDA-event timing by the caller) */
+  void *dasm_ctx_stream(dasm_ctx *ctx);
+  /* NCCL communicator for ghost / overlap-layer exchange (replaces the MPI communicator of
+   * Utilities::MPI::Partitioner used in matrix_free_internal.h:21-83).  id = 128-byte ncclUniqueId. */
+  int dasm_nccl_unique_id(void *id128);
+  int dasm_ctx_comm_init(dasm_ctx *ctx, int n_ranks, int rank, const void *id128);
+
+  /* ---- mesh --------------------------------------------------------------------------------- */
+  /* GridGenerator::subdivided_hyper_cube_balanced, include/grid_generator.h:107-156:
+   * n_subdivisions s -> n_refine, subdivisions[3]; cells per direction = subdivisions * 2^n_refine */
+  int dasm_decompose_balanced(int n_subdivisions, int *n_refine, int subdivisions[3]);
+  /* structured hex mesh on [0,length]^3; partition = ranks per direction (brick partition, replaces
+   * the p4est partition of parallel::distributed::Triangulation, matrix_free_loop_08.likwid.cc:160) */
+  int dasm_mesh_create_structured(dasm_ctx *ctx, const int n_cells[3], const int periodic[3], int dirichlet,
+                                  const double length[3], int map_kind, const double map_params[4],
+                                  const int partition[3], int rank, dasm_mesh **out);
+  int       dasm_mesh_destroy(dasm_mesh *mesh);
+  long long dasm_mesh_n_cells(const dasm_mesh *mesh);        /* local cells */
+  long long dasm_mesh_n_global_cells(const dasm_mesh *mesh);
+  /* processing order -> global (i,j,k) of every local cell, out[n_cells*3] (host) */
+  int dasm_mesh_cell_coordinates(const dasm_mesh *mesh, int *out);
+
+  /* ---- LaplaceOperatorMatrixFree (include/operator.h:266-1628) ------------------------------- */
+  /* ctor operator.h:466-482 + setup_mapping_and_indices 490-753.  mapping_type in {"", "merged"}
+   * ("linear geometry", "quadratic geometry", "construct q" are not built yet and return an error,
+   * like operator.h:747-752 does for unknown names). */
+  int dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping_type, int compress_indices,
+                     dasm_op **out);
+  int       dasm_op_destroy(dasm_op *op);
+  long long dasm_op_n_dofs(const dasm_op *op);        /* locally owned (vector_partitioner->locally_owned_size) */
+  long long dasm_op_n_ghost(const dasm_op *op);
+  long long dasm_op_vec_size(const dasm_op *op);      /* owned + ghost */
+  long long dasm_op_n_global_dofs(const dasm_op *op); /* m(), operator.h:1451 */
+  int       dasm_op_degree(const dasm_op *op);
+  int       dasm_op_number_type(const dasm_op *op);
+  int       dasm_op_uses_compressed_indices(const dasm_op *op); /* operator.h:484-488 */
+  /* vmult(dst, src), operator.h:1353-1365 (dst zeroed, constrained DoFs stay zero) */
+  int dasm_op_vmult(dasm_op *op, void *dst, const void *src);
+  /* vmult(dst, src, pre, post), operator.h:1367-1430 (constrained DoFs: dst = src when post given) */
+  int dasm_op_vmult_hooks(dasm_op *op, void *dst, const void *src, const dasm_hook *pre, const dasm_hook *post);
+  /* compute_inverse_diagonal, operator.h:1512-1524 */
+  int dasm_op_inverse_diagonal(dasm_op *op, void *diag);
+  /* 27 compressed start indices per local cell (ConstraintInfoReduced::compressed_dof_indices,
+   * vector_access_reduced.h:30-164); plain != 0 keeps the index of constrained entities instead of
+   * 0xFFFFFFFF.  out[n_cells*27] host. */
+  int dasm_op_compressed_indices(const dasm_op *op, int plain, uint32_t *out);
+  /* list of constrained (homogeneous Dirichlet) owned DoFs; returns count, fills out if non-NULL */
+  long long dasm_op_constrained_dofs(const dasm_op *op, uint32_t *out);
+  /* merged coefficients of one local cell, out[6*(degree+1)^3] host doubles (operator.h:674-711) */
+  int dasm_op_merged_coefficients(const dasm_op *op, long long cell, double *out);
+  /* host <-> device helpers for vectors of the operator's number type (host side double) */
+  int dasm_op_vec_alloc(dasm_op *op, void **dev);
+  int dasm_op_vec_free(dasm_op *op, void *dev);
+  int dasm_op_vec_upload(dasm_op *op, void *dev, const double *host_owned);
+  int dasm_op_vec_download(dasm_op *op, double *host_owned, const void *dev);
+
+  /* ---- ASPoissonPreconditioner (include/matrix_free.h:63-1568) ------------------------------- */
+  /* create_fdm_preconditioner, precondition.templates.h:162-247, + ctor matrix_free.h:73-894 */
+  int dasm_fdm_create(dasm_op *op, int n_overlap, int sub_mesh_approximation, int weight_type, int weight_sequence,
+                      int overlap_pre_post, int element_centric, dasm_fdm **out);
+  int dasm_fdm_destroy(dasm_fdm *fdm);
+  /* vmult(dst, src), matrix_free.h:925-955 */
+  int dasm_fdm_vmult(dasm_fdm *fdm, void *dst, const void *src);
+  /* vmult(dst, src, pre, post), matrix_free.h:960-986 */
+  int dasm_fdm_vmult_hooks(dasm_fdm *fdm, void *dst, const void *src, const dasm_hook *pre, const dasm_hook *post);
+  long long dasm_fdm_n_instances(const dasm_fdm *fdm);      /* n_fdm_instances(), matrix_free.h:1000-1004 */
+  long long dasm_fdm_memory_consumption(const dasm_fdm *fdm); /* matrix_free.h:988-992 */
+  int       dasm_fdm_is_symmetric(const dasm_fdm *fdm);     /* matrix_free.h:896-904 */
+  int       dasm_fdm_patch_size_1d(const dasm_fdm *fdm);    /* matrix_free.h:90-92 */
+  /* global weight vector (1/valence, 1/sqrt(valence)), host doubles of owned size; matrix_free.h:674-712 */
+  int dasm_fdm_weights(const dasm_fdm *fdm, double *out_owned);
+  /* eigenvector matrix S[m*m] (row-major, column = eigenvector) and eigenvalues[m] of cell/direction */
+  int dasm_fdm_instance(const dasm_fdm *fdm, long long cell, int direction, double *S, double *lambda);
+
+  /* ---- PreconditionChebyshev (deal.II; configured in precondition.templates.h:89-158, selected in
+   *      create_system_preconditioner 439-584; invoked via PreconditionerAdapter, preconditioners.h:897-926) */
+  /* fdm == NULL selects the point-Jacobi preconditioner (DiagonalMatrixPrePost, preconditioners.h:951-997) */
+  int dasm_cheb_create(dasm_op *op, dasm_fdm *fdm, int degree, double smoothing_range, int polynomial_type,
+                       int ev_algorithm, int optimize, int eig_cg_n_iterations, dasm_cheb **out);
+  int dasm_cheb_destroy(dasm_cheb *cheb);
+  int dasm_cheb_estimate_eigenvalues(dasm_cheb *cheb, double *min_ev, double *max_ev);
+  int dasm_cheb_set_eigenvalues(dasm_cheb *cheb, double min_ev, double max_ev);
+  int dasm_cheb_vmult(dasm_cheb *cheb, void *dst, const void *src); /* x = p(P^-1 A) P^-1 b, x0 = 0 */
+  int dasm_cheb_step(dasm_cheb *cheb, void *dst, const void *src);  /* PreconditionerBase::step, preconditioners.h:725-742 */
+  /* the call the reference's user makes with host vectors: copies src (and dst for step) in, result out */
+  int dasm_cheb_step_host(dasm_cheb *cheb, double *dst_owned, const double *src_owned);
+  int dasm_cheb_vmult_host(dasm_cheb *cheb, double *dst_owned, const double *src_owned);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

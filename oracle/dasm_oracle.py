@@ -317,81 +317,80 @@ def _entity_of(idx, k):
     return 0 if idx == 0 else (2 if idx == k else 1)
 
 
-def number_dofs_first_touch(mesh, k):
-    """Native numbering of the B200 library, restated independently.
+def brick_major_order(n_cells, brick=(4, 4, 4)):
+    """processing order of the B200 library: bricks of `brick` cells in lexicographic brick order
+    (x fastest), cells lexicographic inside a brick.  Returns lexicographic cell ids."""
+    dim = len(n_cells)
+    nc = list(n_cells) + [1] * (3 - dim)
+    B = list(brick[:dim]) + [1] * (3 - dim)
+    order = []
+    for bz in range(0, nc[2], B[2]):
+        for by in range(0, nc[1], B[1]):
+            for bx in range(0, nc[0], B[0]):
+                for z in range(bz, min(bz + B[2], nc[2])):
+                    for y in range(by, min(by + B[1], nc[1])):
+                        for x in range(bx, min(bx + B[0], nc[0])):
+                            order.append((z * nc[1] + y) * nc[0] + x)
+    return np.array(order, dtype=np.int64)
 
-    Cells are visited in mesh.cell_order; for each cell its 3^dim entities (vertex / line / quad /
-    hex interior, lexicographic 3x3(x3) layout as in vector_access_reduced.h:30-164) are visited in
-    lexicographic order and every entity not yet numbered receives the next contiguous range
-    ((k-1)^codim-free-dims DoFs, lexicographic inside the entity).  Entities on a Dirichlet
-    boundary are numbered as well (they exist in the vector, like constrained DoFs in deal.II) but
+
+def number_dofs_owner_cell(mesh, k):
+    """Native "owner-cell" numbering of the B200 library, restated independently.
+
+    Every mesh entity (3^dim per cell: vertex / line / quad / hex interior in the lexicographic
+    3x3(x3) layout of vector_access_reduced.h:30-164) is owned by the cell for which it is a lower
+    entity (code 0 or 1 per direction); code 2 is owned only by the last cell of a non-periodic
+    direction.  Cells are visited in mesh.cell_order and number their owned entities contiguously in
+    lexicographic entity order, DoFs lexicographic inside an entity.  Entities on a Dirichlet
+    boundary are numbered too (they exist in the vector, like constrained DoFs in deal.II) and are
     flagged constrained.
 
-    returns cell_dofs [C, n^dim] (uint32, indexed by *lexicographic cell id*), n_dofs,
-            constrained [n_dofs] bool, compressed [C, 3^dim] start index per entity
+    returns cell_dofs [C, n^dim] (uint32, by lexicographic cell id), n_dofs, constrained [n_dofs]
+            bool, compressed [C, 3^dim] entity start indices (plain: constrained keep their index)
     """
     dim = mesh.dim
     n = k + 1
     nc = mesh.n_cells
-    # global lattice of entity "slots": per direction 2*nc (+1 if not periodic):  even = vertex layer, odd = interior
+    km1 = k - 1
     size = [2 * nc[d] + (0 if mesh.periodic[d] else 1) for d in range(dim)]
-    ent_start = -np.ones(size[::-1], dtype=np.int64)  # indexed [(z,)y,x]
-    cell_dofs = np.zeros((mesh.C, n ** dim), dtype=np.uint32)
-    compressed = np.zeros((mesh.C, 3 ** dim), dtype=np.uint32)
+    ent_start = -np.ones(size[::-1], dtype=np.int64)  # [(z,)y,x] slot lattice
     next_dof = 0
     constrained_ranges = []
-    km1 = k - 1
+
+    def ent_size(ee):
+        cnt = 1
+        for d in range(dim):
+            if ee[d] == 1:
+                cnt *= km1
+        return cnt
+
     for c in mesh.cell_order:
         ijk = mesh.cell_ijk(int(c))
-        loc = np.zeros((n,) * dim, dtype=np.int64)  # [(z,)y,x]
         for e in range(3 ** dim):
             ee = [(e // 3 ** d) % 3 for d in range(dim)]
-            slot = [(2 * ijk[d] + ee[d]) % size[d] if mesh.periodic[d] else 2 * ijk[d] + ee[d] for d in range(dim)]
-            key = tuple(slot[::-1])
-            cnt = 1
-            for d in range(dim):
-                if ee[d] == 1:
-                    cnt *= km1
-            if ent_start[key] < 0:
-                ent_start[key] = next_dof
-                on_bdry = False
-                if mesh.dirichlet:
-                    for d in range(dim):
-                        if not mesh.periodic[d] and (slot[d] == 0 or slot[d] == size[d] - 1):
-                            on_bdry = True
-                if on_bdry and cnt > 0:
-                    constrained_ranges.append((next_dof, next_dof + cnt))
-                next_dof += cnt
-            start = ent_start[key]
-            compressed[c, e] = start
-            # fill local lexicographic indices
-            rng = []
-            for d in range(dim):
-                if ee[d] == 0:
-                    rng.append([0])
-                elif ee[d] == 2:
-                    rng.append([k])
-                else:
-                    rng.append(list(range(1, k)))
-            if cnt == 0:
+            owned = all(ee[d] < 2 or (not mesh.periodic[d] and ijk[d] == nc[d] - 1) for d in range(dim))
+            if not owned:
                 continue
-            if dim == 2:
-                o = 0
-                for j in rng[1]:
-                    for i in rng[0]:
-                        loc[j, i] = start + o
-                        o += 1
-            else:
-                o = 0
-                for kk in rng[2]:
-                    for j in rng[1]:
-                        for i in rng[0]:
-                            loc[kk, j, i] = start + o
-                            o += 1
-        cell_dofs[c] = loc.reshape(-1)
+            slot = [2 * ijk[d] + ee[d] for d in range(dim)]
+            cnt = ent_size(ee)
+            ent_start[tuple(slot[::-1])] = next_dof
+            if mesh.dirichlet and cnt > 0 and any(
+                    (not mesh.periodic[d]) and (slot[d] == 0 or slot[d] == size[d] - 1) for d in range(dim)):
+                constrained_ranges.append((next_dof, next_dof + cnt))
+            next_dof += cnt
+    assert np.all(ent_start >= 0)
+    cell_dofs = np.zeros((mesh.C, n ** dim), dtype=np.uint32)
+    compressed = np.zeros((mesh.C, 3 ** dim), dtype=np.uint32)
+    for c in range(mesh.C):
+        ijk = mesh.cell_ijk(c)
+        for e in range(3 ** dim):
+            ee = [(e // 3 ** d) % 3 for d in range(dim)]
+            slot = [(2 * ijk[d] + ee[d]) % size[d] for d in range(dim)]
+            compressed[c, e] = ent_start[tuple(slot[::-1])]
+    cell_dofs = expand_compressed(compressed, k, dim)
     constrained = np.zeros(next_dof, dtype=bool)
-    for a, b in constrained_ranges:
-        constrained[a:b] = True
+    for a0, b0 in constrained_ranges:
+        constrained[a0:b0] = True
     return cell_dofs, next_dof, constrained, compressed
 
 
@@ -976,13 +975,13 @@ class Chebyshev:
         b = np.asarray(b, dtype=dt)
         f2 = dt(co[0][1]) if dt != np.float64 else co[0][1]
         if first_is_step:
-            t = b - self.op.vmult(x, copy_constrained=False)
+            t = b - self.op.vmult(x, copy_constrained=True)
             x_new = x + f2 * self.P.vmult(t)
         else:
             x_new = f2 * self.P.vmult(b)
         x_old, x = x, x_new.astype(dt)
         for (f1, f2) in co[1:]:
-            t = b - self.op.vmult(x)
+            t = b - self.op.vmult(x, copy_constrained=True)
             z = self.P.vmult(t)
             x_new = x + f1 * (x - x_old) + f2 * z
             x_old, x = x, x_new.astype(dt)

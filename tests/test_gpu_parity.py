@@ -1,0 +1,290 @@
+"""GPU parity tests: the CUDA path through the C ABI against the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): 1e-12 relative in double, 1e-5 relative in float, measured in the
+l2 norm relative to the result; DoF indexing and constrained-DoF lists bit-exact."""
+import numpy as np
+import pytest
+
+import dasm_oracle as o
+from __graft_entry__ import load_package
+from parity_util import oracle_problem
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"double": 1e-12, "float": 1e-5}
+NPDT = {"double": np.float64, "float": np.float32}
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    return load_package()
+
+
+@pytest.fixture(scope="module")
+def ctx(pkg):
+    return pkg.Context(0)
+
+
+def relerr(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+MESHES = {
+    "periodic": dict(n_cells=(4, 3, 5), periodic=(1, 1, 1)),
+    "dirichlet": dict(n_cells=(3, 4, 2), periodic=(0, 0, 0), dirichlet=True),
+    "mixed_aniso": dict(n_cells=(5, 2, 3), periodic=(1, 0, 0), dirichlet=True, length=(2.0, 1.0, 3.0)),
+    "sine": dict(n_cells=(3, 3, 3), periodic=(1, 1, 1), map_kind="sine"),
+    "kershaw": dict(n_cells=(6, 2, 2), periodic=(0, 0, 0), dirichlet=True, map_kind="kershaw", map_params=(0.3, 0.3, 0, 0)),
+}
+
+
+def run_vmult(pkg, ctx, meshkw, k, number):
+    mesh = pkg.Mesh(ctx, **meshkw)
+    op = pkg.LaplaceOperatorMatrixFree(mesh, k, number)
+    oop, _ = oracle_problem(pkg, mesh, op, with_fdm=False)
+    rng = np.random.default_rng(k)
+    x = rng.uniform(-1, 1, op.n_dofs())
+    xd = op.to_device(x)
+    yd = op.initialize_dof_vector()
+    op.vmult(yd, xd)
+    y = op.to_host(yd)
+    ref = oop.vmult(x)
+    return relerr(y, ref)
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("number", ["double", "float"])
+def test_vmult_degrees_periodic(pkg, ctx, k, number):
+    kw = dict(MESHES["periodic"])
+    if k >= 6:
+        kw["n_cells"] = (2, 2, 3)
+    assert run_vmult(pkg, ctx, kw, k, number) < TOL[number]
+
+
+@pytest.mark.parametrize("name", ["dirichlet", "mixed_aniso", "sine", "kershaw"])
+@pytest.mark.parametrize("k", [2, 4])
+def test_vmult_meshes(pkg, ctx, name, k):
+    assert run_vmult(pkg, ctx, MESHES[name], k, "double") < TOL["double"]
+
+
+def test_vmult_merged_on_cartesian_equals_default(pkg, ctx):
+    mesh = pkg.Mesh(ctx, (3, 3, 3), periodic=(1, 1, 1))
+    a = pkg.LaplaceOperatorMatrixFree(mesh, 3, "double", mapping_type="")
+    b = pkg.LaplaceOperatorMatrixFree(mesh, 3, "double", mapping_type="merged")
+    x = np.random.default_rng(1).uniform(-1, 1, a.n_dofs())
+    ya, yb = a.initialize_dof_vector(), b.initialize_dof_vector()
+    a.vmult(ya, a.to_device(x))
+    b.vmult(yb, b.to_device(x))
+    assert relerr(a.to_host(ya), b.to_host(yb)) < 1e-13
+
+
+def test_unknown_mapping_type_raises(pkg, ctx):
+    mesh = pkg.Mesh(ctx, (2, 2, 2), periodic=(1, 1, 1))
+    with pytest.raises(pkg.DasmError, match="is not known"):
+        pkg.LaplaceOperatorMatrixFree(mesh, 2, "double", mapping_type="cubic geometry")
+
+
+def test_vmult_linearity_and_symmetry_large(pkg, ctx):
+    """size-independent properties on a mesh too large for the oracle: linearity, symmetry x'Ay = y'Ax,
+    constant in the null space of the periodic Laplacian."""
+    mesh = pkg.Mesh(ctx, (16, 16, 16), periodic=(1, 1, 1))
+    op = pkg.LaplaceOperatorMatrixFree(mesh, 4, "double")
+    rng = np.random.default_rng(7)
+    n = op.n_dofs()
+    x, y = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
+    out = op.initialize_dof_vector()
+
+    def A(v):
+        op.vmult(out, op.to_device(v))
+        return op.to_host(out).copy()
+
+    Ax, Ay = A(x), A(y)
+    assert relerr(A(2.5 * x - 0.5 * y), 2.5 * Ax - 0.5 * Ay) < 1e-12
+    assert abs(x @ Ay - y @ Ax) < 1e-10 * abs(x @ Ay)
+    assert np.linalg.norm(A(np.ones(n))) < 1e-9 * np.linalg.norm(Ax)
+
+
+@pytest.mark.parametrize("name,k", [("periodic", 4), ("dirichlet", 3), ("sine", 2), ("kershaw", 2), ("mixed_aniso", 3)])
+def test_inverse_diagonal(pkg, ctx, name, k):
+    mesh = pkg.Mesh(ctx, **MESHES[name])
+    op = pkg.LaplaceOperatorMatrixFree(mesh, k, "double")
+    oop, _ = oracle_problem(pkg, mesh, op, with_fdm=False)
+    d = op.initialize_dof_vector()
+    op.compute_inverse_diagonal(d)
+    assert relerr(op.to_host(d), oop.inverse_diagonal()) < 1e-12
+
+
+@pytest.mark.parametrize("wt", ["none", "pre", "post", "symm", "ras"])
+@pytest.mark.parametrize("seq", ["compressed", "global", "dg"])
+def test_fdm_weightings(pkg, ctx, wt, seq):
+    mesh = pkg.Mesh(ctx, **MESHES["mixed_aniso"])
+    op = pkg.LaplaceOperatorMatrixFree(mesh, 3, "double")
+    fdm = pkg.create_fdm_preconditioner(op, {"n overlap": 1, "weighting type": wt, "weight sequence": seq})
+    oop, oP = oracle_problem(pkg, mesh, op, 1, wt)
+    x = np.random.default_rng(3).uniform(-1, 1, op.n_dofs())
+    zd = op.initialize_dof_vector()
+    fdm.vmult(zd, op.to_device(x))
+    assert relerr(op.to_host(zd), oP.vmult(x)) < 1e-12
+    assert fdm.is_symmetric() == oP.is_symmetric()
+    if wt in ("pre", "post", "symm"):
+        assert relerr(fdm.weights(), oP.weights) < 1e-14
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("number", ["double", "float"])
+def test_fdm_degrees(pkg, ctx, k, number):
+    kw = dict(MESHES["periodic"])
+    if k >= 6:
+        kw["n_cells"] = (2, 2, 3)
+    mesh = pkg.Mesh(ctx, **kw)
+    op = pkg.LaplaceOperatorMatrixFree(mesh, k, number)
+    fdm = pkg.create_fdm_preconditioner(op, {"weighting type": "symm"})
+    oop, oP = oracle_problem(pkg, mesh, op, 1, "symm")
+    x = np.random.default_rng(k).uniform(-1, 1, op.n_dofs())
+    x -= x.mean()
+    zd = op.initialize_dof_vector()
+    fdm.vmult(zd, op.to_device(x))
+    assert relerr(op.to_host(zd), oP.vmult(x)) < (1e-11 if number == "double" else 2e-4)
+
+
+@pytest.mark.parametrize("name", ["dirichlet", "sine", "kershaw"])
+def test_fdm_meshes(pkg, ctx, name):
+    mesh = pkg.Mesh(ctx, **MESHES[name])
+    op = pkg.LaplaceOperatorMatrixFree(mesh, 3, "double")
+    fdm = pkg.create_fdm_preconditioner(op, {"weighting type": "post"})
+    oop, oP = oracle_problem(pkg, mesh, op, 1, "post")
+    x = np.random.default_rng(5).uniform(-1, 1, op.n_dofs())
+    zd = op.initialize_dof_vector()
+    fdm.vmult(zd, op.to_device(x))
+    assert relerr(op.to_host(zd), oP.vmult(x)) < 1e-12
+    # eigen-decomposition of one cell/direction: S^T M S = I is invariant to sign/order; compare S diag(1/l) S^T
+    S, lam = fdm.instance(0, 0)
+    So, lo = oP.S[oP.mesh.cell_order[0], 0], oP.lam[oP.mesh.cell_order[0], 0]
+    assert np.allclose(S @ np.diag(1 / lam) @ S.T, So @ np.diag(1 / lo) @ So.T, rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("n_overlap,wt", [(2, "post"), (2, "symm"), (2, "none"), (3, "post"), (2, "ras")])
+def test_fdm_overlap(pkg, ctx, n_overlap, wt):
+    mesh = pkg.Mesh(ctx, (3, 4, 3), periodic=(1, 0, 0), dirichlet=True)
+    op = pkg.LaplaceOperatorMatrixFree(mesh, 3, "double")
+    fdm = pkg.create_fdm_preconditioner(op, {"n overlap": n_overlap, "weighting type": wt})
+    assert fdm.patch_size_1d() == 3 - 1 + 2 * n_overlap
+    oop, oP = oracle_problem(pkg, mesh, op, n_overlap, wt)
+    x = np.random.default_rng(11).uniform(-1, 1, op.n_dofs())
+    zd = op.initialize_dof_vector()
+    fdm.vmult(zd, op.to_device(x))
+    assert relerr(op.to_host(zd), oP.vmult(x)) < 1e-11
+
+
+def test_fdm_n_instances_cartesian(pkg, ctx):
+    mesh = pkg.Mesh(ctx, (4, 4, 4), periodic=(1, 1, 1))
+    op = pkg.LaplaceOperatorMatrixFree(mesh, 4, "double")
+    fdm = pkg.create_fdm_preconditioner(op, {})
+    assert fdm.n_fdm_instances() == 1  # O(1) instances on a Cartesian mesh (matrix_free.h:1000-1004)
+    mesh2 = pkg.Mesh(ctx, (4, 4, 4), periodic=(0, 0, 0))
+    op2 = pkg.LaplaceOperatorMatrixFree(mesh2, 4, "double")
+    assert pkg.create_fdm_preconditioner(op2, {}).n_fdm_instances() == 3  # left boundary / interior / right boundary
+
+
+CHEB_CASES = [
+    ("periodic", 4, "double", "symm", 3, "1st kind", True),
+    ("periodic", 4, "double", "post", 1, "1st kind", True),
+    ("periodic", 3, "float", "symm", 3, "1st kind", True),
+    ("dirichlet", 3, "double", "post", 3, "4th kind", True),
+    ("kershaw", 2, "double", "symm", 2, "1st kind", False),
+    ("sine", 3, "double", "pre", 4, "4th kind", False),
+    ("mixed_aniso", 2, "double", "diag", 3, "1st kind", True),
+    ("dirichlet", 4, "float", "diag", 2, "4th kind", False),
+]
+
+
+@pytest.mark.parametrize("name,k,number,wt,degree,poly,is_step", CHEB_CASES)
+def test_chebyshev_step_and_vmult(pkg, ctx, name, k, number, wt, degree, poly, is_step):
+    mesh = pkg.Mesh(ctx, **MESHES[name])
+    op = pkg.LaplaceOperatorMatrixFree(mesh, k, number)
+    dt = NPDT[number]
+    if wt == "diag":
+        fdm = None
+        oop, _ = oracle_problem(pkg, mesh, op, with_fdm=False, dtype=dt)
+        oP = o.JacobiPreconditioner(oop)
+    else:
+        fdm = pkg.create_fdm_preconditioner(op, {"weighting type": wt})
+        oop, oP = oracle_problem(pkg, mesh, op, 1, wt, dtype=dt)
+    cheb = pkg.PreconditionChebyshev(op, fdm, degree=degree, polynomial_type=poly)
+    cheb.set_eigenvalues(0.9, 2.2)
+    och = o.Chebyshev(oop, oP, degree=degree, polynomial_type=poly)
+    och.set_eigenvalues(2.2, 0.9)
+    rng = np.random.default_rng(13)
+    b = rng.uniform(-1, 1, op.n_dofs())
+    x0 = rng.uniform(-1, 1, op.n_dofs())
+    xd = op.to_device(x0)
+    bd = op.to_device(b)
+    if is_step:
+        cheb.step(xd, bd)
+        ref = och.step(x0.astype(dt), b.astype(dt))
+    else:
+        cheb.vmult(xd, bd)
+        ref = och.vmult(b.astype(dt))
+    assert relerr(op.to_host(xd), ref.astype(np.float64)) < (1e-12 if number == "double" else 1e-5)
+    # host-buffer entry point (the e2e path of bench.py)
+    xh = x0.copy()
+    if is_step:
+        cheb.step_host(xh, b)
+    else:
+        cheb.vmult_host(xh, b)
+    assert relerr(xh, ref.astype(np.float64)) < (1e-12 if number == "double" else 1e-5)
+
+
+@pytest.mark.parametrize("wt,alg", [("post", "power iteration"), ("symm", "lanczos"), ("diag", "lanczos"), ("none", "power iteration")])
+def test_eigenvalue_estimates(pkg, ctx, wt, alg):
+    mesh = pkg.Mesh(ctx, (3, 3, 2), periodic=(0, 0, 0), dirichlet=True)
+    op = pkg.LaplaceOperatorMatrixFree(mesh, 3, "double")
+    if wt == "diag":
+        fdm = None
+        oop, _ = oracle_problem(pkg, mesh, op, with_fdm=False)
+        oP = o.JacobiPreconditioner(oop)
+    else:
+        fdm = pkg.create_fdm_preconditioner(op, {"weighting type": wt})
+        oop, oP = oracle_problem(pkg, mesh, op, 1, wt)
+    cheb = pkg.PreconditionChebyshev(op, fdm, degree=3, ev_algorithm=alg, eig_cg_n_iterations=20)
+    mn, mx = cheb.estimate_eigenvalues()
+    och = o.Chebyshev(oop, oP, degree=3, ev_algorithm=alg, eig_cg_n_iterations=20)
+    omn, omx = och.estimate_eigenvalues()
+    assert mx == pytest.approx(omx, rel=1e-8)
+    assert mn == pytest.approx(omn, rel=1e-6)
+
+
+def test_factory_system_preconditioner(pkg, ctx):
+    mesh = pkg.Mesh(ctx, (3, 3, 3), periodic=(1, 1, 1))
+    op = pkg.LaplaceOperatorMatrixFree(mesh, 3, "double")
+    pc = pkg.create_system_preconditioner(op, {"type": "Chebyshev", "degree": 2, "preconditioner": {"type": "FDM", "n overlap": 1,
+                                                                                                  "weighting type": "post"}})
+    assert isinstance(pc, pkg.PreconditionChebyshev)
+    with pytest.raises(pkg.DasmError, match="is not known"):
+        pkg.create_system_preconditioner(op, {"type": "Bogus"})
+    with pytest.raises(pkg.DasmError, match="is not known"):
+        pkg.create_fdm_preconditioner(op, {"weighting type": "bogus"})
+
+
+def test_smoother_reduces_residual_large(pkg, ctx):
+    """property at a larger size: a Chebyshev(3)+FDM step reduces the high-frequency residual."""
+    mesh = pkg.Mesh(ctx, (12, 12, 12), periodic=(0, 0, 0), dirichlet=True)
+    op = pkg.LaplaceOperatorMatrixFree(mesh, 4, "double")
+    fdm = pkg.create_fdm_preconditioner(op, {"weighting type": "symm"})
+    cheb = pkg.PreconditionChebyshev(op, fdm, degree=3)
+    mn, mx = cheb.estimate_eigenvalues()
+    assert 1.0 < mx < 4.0
+    rng = np.random.default_rng(0)
+    n = op.n_dofs()
+    con = op.constrained_dofs()
+    xt = rng.uniform(-1, 1, n)
+    xt[con] = 0
+    xtd = op.to_device(xt)
+    bd = op.initialize_dof_vector()
+    op.vmult(bd, xtd)
+    xd = op.initialize_dof_vector()
+    e0 = np.linalg.norm(xt)
+    for _ in range(3):
+        cheb.step(xd, bd)
+    e1 = np.linalg.norm(op.to_host(xd) - xt)
+    assert e1 < 0.5 * e0

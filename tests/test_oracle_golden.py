@@ -133,6 +133,6 @@ def test_tridiagonal_round_trip():
 def test_compressed_indices_round_trip():
     for dim, k in ((2, 3), (3, 2), (3, 4)):
         mesh = o.StructuredMesh(dim, (3,) * dim, (True,) + (False,) * (dim - 1))
-        cd, nd, con, comp = o.number_dofs_first_touch(mesh, k)
+        cd, nd, con, comp = o.number_dofs_owner_cell(mesh, k)
         assert np.array_equal(o.expand_compressed(comp, k, dim), cd)
         assert sorted(set(cd.reshape(-1).tolist())) == list(range(nd))
