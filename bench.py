@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""Benchmark of the smoother hot path (driver contract: one JSON line on stdout from rank 0).
+
+A "step" is one Chebyshev(3) smoother step around the element-centred FDM additive-Schwarz preconditioner
+(label `cheby-3-2-symm-1-c` of the reference's matrix_free_loop_08) on a periodic Cartesian hyper-rectangle,
+FE_Q degree 4, double precision, ~1e8 DoFs per GPU (192x128x64 cells per GPU = `n subdivisions` 41).
+Throughput follows the reference's definition (matrix_free_loop_08.likwid.cc:390-395):
+    DoFs/s = n_dofs * chebyshev_degree * steps / time        ("DoFs/s per Chebyshev term").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PARTITION = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
+METRIC = "DoFs/s per Chebyshev term of the Chebyshev(3)+FDM-ASM smoother step (n_dofs*degree*steps/time)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--degree", type=int, default=4)
+    ap.add_argument("--number", default="double", choices=["double", "float"])
+    ap.add_argument("--cheb-degree", type=int, default=3)
+    ap.add_argument("--weighting", default="symm")
+    ap.add_argument("--cells", default="192,128,64", help="cells per GPU (x,y,z)")
+    ap.add_argument("--cpu-cells", default="32,32,32", help="bounded CPU-baseline sample mesh")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--extra", action="store_true", help="also time vmult / FDM alone (printed to stderr)")
+    return ap.parse_args()
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, reasons, mx = [], set(), None
+        for r in rows:
+            if len(r) < 8:
+                continue
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[4:8]):
+                if v.strip().lower() == "active":
+                    reasons.add(name)
+        if sm:
+            hi = [s for s in sm if s >= 0.5 * max(sm)]
+            out["sm_mhz"] = float(np.median(hi))
+            out["sm_max_mhz"] = mx
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU arm: the C restatement of the reference algorithm (oracle/), all host threads, bounded sample
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_smoother(args):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import dasm_oracle as o
+    import oracle_c
+    nc = tuple(int(c) for c in args.cpu_cells.split(","))
+    k = args.degree
+    mesh = o.StructuredMesh(3, nc, (True, True, True), lengths=tuple(c / 64.0 for c in nc))
+    mesh.cell_order = o.brick_major_order(nc)
+    cd, nd, con, comp = o.number_dofs_owner_cell(mesh, k)
+    b = o.Basis1D(k)
+    # Cartesian: identical Jacobian in every cell
+    h = [mesh.lengths[d] / nc[d] for d in range(3)]
+    J = np.broadcast_to(np.diag(h), (mesh.C, (k + 1) ** 3, 3, 3)).copy()
+    G = o.merged_coefficients(J, b, 3)
+    oop = o.LaplaceOperator(3, k, cd, nd, con, G)
+    oP = o.FDMPreconditioner(mesh, k, cd, nd, con, 1, args.weighting)
+    sm = oracle_c.CSmoother(mesh, oop, oP, args.cheb_degree, max_ev=2.4, min_ev=1.0)
+    return sm, nd, oracle_c.max_threads(), nc
+
+
+def time_cpu(args, steps, warmup):
+    sm, nd, threads, nc = cpu_smoother(args)
+    rng = np.random.default_rng(0)
+    x = rng.uniform(-1, 1, nd)
+    b = rng.uniform(-1, 1, nd)
+    for _ in range(warmup):
+        x = sm.step(x, b)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        x = sm.step(x, b)
+    dt = time.perf_counter() - t0
+    value = nd * args.cheb_degree * steps / dt
+    sample = "Chebyshev(%d)+FDM(symm,n=1) step, degree %d, %dx%dx%d periodic Cartesian cells (%d DoFs), %d steps, %.2f s" % (
+        args.cheb_degree, args.degree, nc[0], nc[1], nc[2], nd, steps, dt)
+    return value, threads, sample, dt / steps * 1e3
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, args.steps)
+    value, threads, sample, ms = time_cpu(args, steps, max(1, min(args.warmup, 2)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "DoFs/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "cheby-3-2-symm-1-c, FE_Q(%d), periodic Cartesian; CPU restatement of the reference algorithm "
+                               "(oracle/dasm_oracle_c.c; deal.II itself cannot be built here), bounded sample" % args.degree,
+                   "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "DoFs/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "DoFs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from __graft_entry__ import load_package
+    pkg = load_package()
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("WORLD_SIZE %d != --gpus %d" % (world, args.gpus))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    ctx = pkg.Context(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        ident = [pkg.Context.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ident, src=0)
+        ctx.comm_init(world, rank, ident[0])
+    if world not in PARTITION:
+        raise SystemExit("--gpus must be 1, 2, 4 or 8")
+    part = PARTITION[world]
+    cpg = tuple(int(c) for c in args.cells.split(","))
+    nc = tuple(cpg[d] * part[d] for d in range(3))
+    length = tuple(c / 64.0 for c in nc)  # unit cells of the n_refine = 6 hyper-rectangle
+
+    def barrier():
+        torch.cuda.synchronize()
+        ctx.sync()
+        if world > 1:
+            dist.barrier()
+
+    k = args.degree
+    S = 8 if args.number == "double" else 4
+    t_setup = time.perf_counter()
+    mesh = pkg.Mesh(ctx, nc, periodic=(1, 1, 1), length=length, partition=part, rank=rank)
+    op = pkg.LaplaceOperatorMatrixFree(mesh, k, args.number)
+    fdm = pkg.create_fdm_preconditioner(op, {"n overlap": 1, "weighting type": args.weighting, "weight sequence": "compressed"})
+    cheb = pkg.PreconditionChebyshev(op, fdm, degree=args.cheb_degree, optimize=2)
+    cheb.set_eigenvalues(1.0, 2.4)  # fixed so that every rank count does identical arithmetic
+    ctx.sync()
+    t_setup = time.perf_counter() - t_setup
+    n_own = op.n_dofs()
+    n_glob = op.m()
+    n_cells_local = mesh.n_cells
+
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    x = torch.zeros(op.vec_size(), dtype=op.torch_dtype, device=dev)
+    b = torch.zeros(op.vec_size(), dtype=op.torch_dtype, device=dev)
+    x[:n_own] = torch.rand(n_own, generator=g, dtype=op.torch_dtype, device=dev) * 2 - 1
+    b[:n_own] = torch.rand(n_own, generator=g, dtype=op.torch_dtype, device=dev) * 2 - 1
+    torch.cuda.synchronize()
+
+    stream = torch.cuda.ExternalStream(ctx.stream_ptr(), device=dev)
+    for _ in range(max(args.warmup, 3)):
+        cheb.step(x, b)
+    barrier()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    ctx.enable_kernel_timing(True)
+    l0 = ctx.launch_count()
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        cheb.step(x, b)
+    e1.record(stream)
+    barrier()
+    launches = ctx.launch_count() - l0
+    ms = e0.elapsed_time(e1)
+    ktimes = [ctx.kernel_time(c) for c in range(4)]
+    ctx.enable_kernel_timing(False)
+    clocks = sampler.stop() if sampler else None
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = n_glob * args.cheb_degree * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the host-buffer entry point (pinned host memory, H2D + D2H inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        ke = max(1, min(args.steps, 5))
+        xh = torch.empty(n_own, dtype=torch.float64).pin_memory()
+        bh = torch.empty(n_own, dtype=torch.float64).pin_memory()
+        xh.copy_(x[:n_own].double().cpu())
+        bh.copy_(b[:n_own].double().cpu())
+        xn, bn = xh.numpy(), bh.numpy()
+        cheb.step_host(xn, bn)  # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            cheb.step_host(xn, bn)
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": n_glob * args.cheb_degree * ke / dt, "unit": "DoFs/s", "h2d_bytes_per_step": int(2 * n_own * 8 * world),
+               "d2h_bytes_per_step": int(n_own * 8 * world), "steps": ke,
+               "note": "dasm_cheb_step_host: x and b copied from pinned host memory, result copied back, per step"}
+
+    extra = {}
+    if args.extra:
+        y = torch.zeros_like(x)
+        for name, fn in (("vmult", lambda: op.vmult(y, x)), ("fdm", lambda: fdm.vmult(y, x))):
+            for _ in range(3):
+                fn()
+            barrier()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(stream)
+            for _ in range(10):
+                fn()
+            a1.record(stream)
+            barrier()
+            extra[name + "_dofs_per_s"] = n_glob * 10 / (a0.elapsed_time(a1) * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (by accumulated device time inside the timed region)
+    peak, peak_src = measured_peak()
+    names = ["laplace cell kernel (A-sweep)", "FDM cell kernel (P-sweep)", "vector epilogues", "ghost exchange"]
+    dom = int(np.argmax([t[0] for t in ktimes[:2]]))
+    dom_ms, dom_n = ktimes[dom]
+    idx_bytes = 27 * 4
+    d_c = k ** 3
+    fused = bool(os.environ.get("DASM_FUSED", "1") != "0") and hasattr(pkg, "FUSED_KERNELS") and pkg.FUSED_KERNELS
+    if fused:
+        # A-sweep: read x, read b, write t1 (3 S) + indices; P-sweep: read t1, x, x_old, write x+ (4 S) + indices + 27 weights + 3 ids
+        per_dof = [3 * S + idx_bytes / d_c, 4 * S + (idx_bytes + 27 * S + 12) / d_c][dom]
+    else:
+        # unfused cell kernels: read src, write dst (2 S) + per-cell metadata (SURVEY.md 8(d) `vmult` / `FDM-ASM vmult` rows)
+        per_dof = [2 * S + idx_bytes / d_c, 2 * S + (idx_bytes + 27 * S + 12) / d_c][dom]
+    bytes_per_launch = per_dof * n_own
+    achieved = bytes_per_launch / (dom_ms / max(dom_n, 1) * 1e-3) / 1e9 if dom_n else None
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(["laplace", "fdm"][dom])
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_dof": per_dof, "avg_launch_ms": dom_ms / max(dom_n, 1), "launches_timed": dom_n,
+                "share_of_step": dom_ms / ms,
+                "kernel_time_ms": {names[i]: ktimes[i][0] for i in range(4)},
+                # whole Chebyshev term against the 7 S + metadata model of SURVEY.md 8(d)
+                "step_algorithmic_bytes_per_dof_per_term": 7 * S + (2 * idx_bytes + 27 * S + 12) / d_c,
+                "step_frac_of_hbm_roofline": value * (7 * S + (2 * idx_bytes + 27 * S + 12) / d_c) / world / (peak * 1e9)}
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            v, threads, sample, _ = time_cpu(args, 3, 1)
+            cpu = {"value": v, "unit": "DoFs/s", "cores": threads, "kind": "port", "sample": sample}
+        except Exception as e:  # the baseline must never take the GPU number down
+            cpu = {"value": None, "unit": "DoFs/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "DoFs/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64" if args.number == "double" else "f32", "data": "synthetic",
+        "config": {"workload": "matrix_free_loop_08 label cheby-%d-2-%s-1-c: FE_Q(%d), periodic Cartesian hyper-rectangle, "
+                               "%dx%dx%d cells per GPU (n subdivisions 41), brick partition %dx%dx%d" % (
+                                   args.cheb_degree, args.weighting, k, cpg[0], cpg[1], cpg[2], part[0], part[1], part[2]),
+                   "n_dofs": int(n_glob), "n_dofs_per_gpu": int(n_own), "n_cells_per_gpu": int(n_cells_local),
+                   "chebyshev_degree": args.cheb_degree, "l2": "inputs larger than L2 (each vector %.0f MB)" % (n_own * S / 1e6),
+                   "setup_s": t_setup},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+    }
+    if extra:
+        line["extra"] = extra
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -91,6 +91,15 @@ class Context:
     def launch_count(self):
         return lib().dasm_ctx_launch_count(self.h)
 
+    def enable_kernel_timing(self, on=True):
+        _check(lib().dasm_ctx_enable_kernel_timing(self.h, int(on)))
+
+    def kernel_time(self, klass):
+        """(total ms, launches) of kernel class 0 Laplace / 1 FDM / 2 vector / 3 exchange since enable_kernel_timing."""
+        ms, n = ctypes.c_double(), ctypes.c_longlong()
+        _check(lib().dasm_ctx_kernel_time(self.h, int(klass), ctypes.byref(ms), ctypes.byref(n)))
+        return ms.value, n.value
+
     def stream_ptr(self):
         return lib().dasm_ctx_stream(self.h)
 
@@ -316,7 +325,7 @@ class PreconditionChebyshev:
         if ev_algorithm not in self.EV:
             raise DasmError("Eigen-value algorithm <%s> is not known!" % ev_algorithm)
         self.h = ctypes.c_void_p()
-        _check(lib().dasm_cheb_create(op.h, fdm.h if fdm is not None else None, int(degree), float(smoothing_range),
+        _check(lib().dasm_cheb_create(op.h, fdm.h if fdm is not None else None, int(degree), ctypes.c_double(smoothing_range),
                                       self.POLY[polynomial_type], self.EV[ev_algorithm], int(optimize), int(eig_cg_n_iterations),
                                       ctypes.byref(self.h)))
 
@@ -326,7 +335,7 @@ class PreconditionChebyshev:
         return mn.value, mx.value
 
     def set_eigenvalues(self, min_ev, max_ev):
-        _check(lib().dasm_cheb_set_eigenvalues(self.h, float(min_ev), float(max_ev)))
+        _check(lib().dasm_cheb_set_eigenvalues(self.h, ctypes.c_double(min_ev), ctypes.c_double(max_ev)))
 
     def vmult(self, dst, src):
         _check(lib().dasm_cheb_vmult(self.h, _ptr(dst), _ptr(src)))

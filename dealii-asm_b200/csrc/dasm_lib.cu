@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <nccl.h>
 
+#include <array>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -82,6 +83,51 @@ struct dasm_ctx
   double *     d_partial = nullptr; // [1024]
   double *     d_scalar  = nullptr; // [8]
   double *     h_scalar  = nullptr; // pinned [8]
+  // optional per-kernel-class timing with CUDA events on `stream`
+  bool                                  timing = false;
+  std::vector<std::array<cudaEvent_t, 2>> ev_pool;
+  std::vector<int>                      ev_class;
+  size_t                                ev_used = 0;
+};
+
+// kernel classes for dasm_ctx_kernel_time
+enum
+{
+  KC_LAPLACE = 0,
+  KC_FDM     = 1,
+  KC_VECTOR  = 2,
+  KC_EXCHANGE = 3,
+  KC_COUNT   = 4
+};
+
+struct KernelTimer
+{
+  dasm_ctx *ctx;
+  size_t    slot = 0;
+  bool      on;
+  KernelTimer(dasm_ctx *c, int klass)
+    : ctx(c)
+    , on(c->timing)
+  {
+    if (!on)
+      return;
+    if (ctx->ev_used == ctx->ev_pool.size())
+      {
+        std::array<cudaEvent_t, 2> e;
+        cudaEventCreate(&e[0]);
+        cudaEventCreate(&e[1]);
+        ctx->ev_pool.push_back(e);
+        ctx->ev_class.push_back(klass);
+      }
+    slot                = ctx->ev_used++;
+    ctx->ev_class[slot] = klass;
+    cudaEventRecord(ctx->ev_pool[slot][0], ctx->stream);
+  }
+  ~KernelTimer()
+  {
+    if (on)
+      cudaEventRecord(ctx->ev_pool[slot][1], ctx->stream);
+  }
 };
 
 struct dasm_mesh
@@ -376,6 +422,7 @@ static void
 launch_laplace(dasm_op *op, T *dst, const T *src)
 {
   dasm_ctx *ctx = op->ctx;
+  KernelTimer timer(ctx, KC_LAPLACE);
   DISPATCH_DEGREE(op->k, {
     constexpr int n = K + 1, CPB = cells_per_block<K>();
     const size_t  smem = (size_t)CPB * 4 * n * n * n * sizeof(T);
@@ -423,6 +470,7 @@ launch_fdm_m(dasm_fdm *f, T *dst, const T *src)
 {
   dasm_op *      op   = f->op;
   dasm_ctx *     ctx  = op->ctx;
+  KernelTimer    timer(ctx, KC_FDM);
   constexpr int  CPB  = fdm_cells_per_block<M>();
   const size_t   smem = (size_t)CPB * (M * M * M + 3 * M * M + 3 * M) * sizeof(T);
   const unsigned grid = (unsigned)((op->n_cells + CPB - 1) / CPB);
@@ -601,6 +649,36 @@ extern "C" long long
 dasm_ctx_launch_count(const dasm_ctx *ctx)
 {
   return ctx->launches;
+}
+
+extern "C" int
+dasm_ctx_enable_kernel_timing(dasm_ctx *ctx, int on)
+{
+  DASM_API_BEGIN
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  ctx->timing  = on != 0;
+  ctx->ev_used = 0;
+  DASM_API_END
+}
+
+extern "C" int
+dasm_ctx_kernel_time(dasm_ctx *ctx, int klass, double *ms, long long *count)
+{
+  DASM_API_BEGIN
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  double    t = 0;
+  long long n = 0;
+  for (size_t i = 0; i < ctx->ev_used; ++i)
+    if (ctx->ev_class[i] == klass)
+      {
+        float e = 0;
+        CUDA_CHECK(cudaEventElapsedTime(&e, ctx->ev_pool[i][0], ctx->ev_pool[i][1]));
+        t += e;
+        ++n;
+      }
+  *ms    = t;
+  *count = n;
+  DASM_API_END
 }
 
 extern "C" void *

@@ -102,6 +102,11 @@ extern "C"
   long long dasm_ctx_launch_count(const dasm_ctx *ctx);
   /* the cudaStream_t all work of this context is enqueued on (for CUDA-event timing by the caller) */
   void *dasm_ctx_stream(dasm_ctx *ctx);
+  /* per-kernel-class device timing with CUDA events on the context's stream (replaces the LIKWID
+   * marker regions of matrix_free_loop_08.likwid.cc:365-377).  klass: 0 Laplace cell kernel,
+   * 1 FDM cell kernel, 2 vector epilogues, 3 ghost exchange.  enable(1) resets the counters. */
+  int dasm_ctx_enable_kernel_timing(dasm_ctx *ctx, int on);
+  int dasm_ctx_kernel_time(dasm_ctx *ctx, int klass, double *ms, long long *count);
   /* NCCL communicator for ghost / overlap-layer exchange (replaces the MPI communicator of
    * Utilities::MPI::Partitioner used in matrix_free_internal.h:21-83).  id = 128-byte ncclUniqueId. */
   int dasm_nccl_unique_id(void *id128);
