@@ -8,6 +8,7 @@
 
 #include <array>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -16,6 +17,7 @@
 
 #include "../../include/dasm.h"
 #include "kernels.cuh"
+#include "kernels_brick.cuh"
 #include "mesh.h"
 
 using namespace dasm;
@@ -272,6 +274,15 @@ struct dasm_op
   CartesianCoef     cart;
   Exchange          exchange;
   std::vector<void *> scratch; // owned by op, freed at destroy
+  // tuned brick path
+  bool              use_brick = false;
+  int               brick_bz  = 4;
+  BrickDesc *       d_bricks  = nullptr;
+  int               n_bricks  = 0;
+  void *            d_acc     = nullptr; // zero-invariant accumulator of shared-face DoFs (n_vec)
+  uint32_t *        d_shared_list = nullptr; // owned DoFs on brick faces shared with other bricks
+  long long         n_shared  = 0;
+  int               n_sm      = 148;
 
   dasm_op(int degree)
     : basis(degree)
@@ -445,6 +456,124 @@ launch_laplace(dasm_op *op, T *dst, const T *src)
 }
 
 template <typename T>
+static Epilogue<T>
+epilogue_from_hook(const dasm_hook *post)
+{
+  Epilogue<T> e;
+  e.kind = EPI_STORE;
+  e.f1   = 0;
+  e.f2   = 0;
+  e.v0   = nullptr;
+  e.v1   = nullptr;
+  if (post == nullptr || post->kind == DASM_HOOK_NONE)
+    return e;
+  switch (post->kind)
+    {
+      case DASM_HOOK_RESIDUAL:
+        e.kind = EPI_RESIDUAL;
+        e.v0   = (const T *)post->v0;
+        break;
+      case DASM_HOOK_CHEB_UPDATE:
+        e.kind = EPI_CHEB;
+        e.f1   = (T)post->f1;
+        e.f2   = (T)post->f2;
+        e.v0   = (const T *)post->v0;
+        e.v1   = (const T *)post->v1;
+        break;
+      case DASM_HOOK_SCALE:
+        e.kind = EPI_SCALE;
+        e.f2   = (T)post->f2;
+        break;
+      default:
+        throw std::runtime_error("unsupported post hook kind " + std::to_string(post->kind));
+    }
+  return e;
+}
+
+template <int K, int BZ, typename T, typename Kern>
+static int
+brick_grid(dasm_op *op, Kern kern, size_t smem)
+{
+  CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 1;
+  CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BrickGeom<K, BZ>::NT, smem));
+  occ = std::max(occ, 1);
+  return std::min(op->n_bricks, op->n_sm * occ);
+}
+
+// finish the shared-face DoFs (dst = epilogue(acc), acc = 0) and run the epilogue on constrained DoFs
+template <int K, int BZ, typename T>
+static void
+brick_finish(dasm_op *op, T *dst, const T *src_for_constrained, const Epilogue<T> &epi)
+{
+  dasm_ctx *ctx = op->ctx;
+  if (op->n_shared > 0)
+    {
+      KernelTimer timer(ctx, KC_VECTOR);
+      finish_shared_kernel<T><<<nblocks(op->n_shared), 256, 0, ctx->stream>>>(dst, (T *)op->d_acc, epi, op->d_shared_list, op->n_shared);
+      ctx->launches++;
+    }
+  if (op->n_constrained > 0)
+    {
+      epilogue_indexed_kernel<T><<<nblocks(op->n_constrained), 256, 0, ctx->stream>>>(dst, src_for_constrained, epi, op->d_constrained,
+                                                                                      op->n_constrained);
+      ctx->launches++;
+    }
+}
+
+template <int K, int BZ, typename T>
+static void
+launch_laplace_brick(dasm_op *op, T *dst, const T *src, const Epilogue<T> &epi, bool copy_constrained)
+{
+  dasm_ctx *   ctx  = op->ctx;
+  const size_t smem = BrickGeom<K, BZ>::template smem_bytes<T>();
+  static const int dbg = getenv("DASM_DEBUG_SKIP") ? atoi(getenv("DASM_DEBUG_SKIP")) : 0; // timing experiments only
+  {
+    KernelTimer timer(ctx, KC_LAPLACE);
+    if (op->geom_mode == 0)
+      {
+        auto      kern = laplace_brick_kernel<K, T, BZ, 0>;
+        const int grid = brick_grid<K, BZ, T>(op, kern, smem);
+        kern<<<grid, BrickGeom<K, BZ>::NT, smem, ctx->stream>>>(src, dst, (T *)op->d_acc, epi, op->d_cidx, op->d_bricks, op->n_bricks,
+                                                                 (const T *)nullptr, op->cart, dbg);
+      }
+    else
+      {
+        auto      kern = laplace_brick_kernel<K, T, BZ, 1>;
+        const int grid = brick_grid<K, BZ, T>(op, kern, smem);
+        kern<<<grid, BrickGeom<K, BZ>::NT, smem, ctx->stream>>>(src, dst, (T *)op->d_acc, epi, op->d_cidx, op->d_bricks, op->n_bricks,
+                                                                 (const T *)op->d_geom, op->cart, dbg);
+      }
+    ctx->launches++;
+  }
+  CUDA_CHECK(cudaGetLastError());
+  brick_finish<K, BZ, T>(op, dst, copy_constrained ? src : nullptr, epi);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+template <typename T>
+static void
+op_vmult_brick(dasm_op *op, T *dst, const T *src, const dasm_hook *post)
+{
+  const Epilogue<T> epi  = epilogue_from_hook<T>(post);
+  const bool        copy = (post != nullptr && post->kind != DASM_HOOK_NONE);
+  switch (op->k)
+    {
+      case 1: launch_laplace_brick<1, 4, T>(op, dst, src, epi, copy); break;
+      case 2: launch_laplace_brick<2, 4, T>(op, dst, src, epi, copy); break;
+      case 3: launch_laplace_brick<3, 4, T>(op, dst, src, epi, copy); break;
+      case 4:
+        if (op->brick_bz == 2)
+          launch_laplace_brick<4, 2, T>(op, dst, src, epi, copy);
+        else
+          launch_laplace_brick<4, 4, T>(op, dst, src, epi, copy);
+        break;
+      case 5: launch_laplace_brick<5, 2, T>(op, dst, src, epi, copy); break;
+      default: throw std::runtime_error("internal: brick path for unsupported degree");
+    }
+}
+
+template <typename T>
 static void
 op_vmult(dasm_op *op, T *dst, const T *src, const dasm_hook *pre, const dasm_hook *post)
 {
@@ -452,6 +581,11 @@ op_vmult(dasm_op *op, T *dst, const T *src, const dasm_hook *pre, const dasm_hoo
   if (pre != nullptr && pre->kind != DASM_HOOK_NONE && pre->kind != DASM_HOOK_ZERO_DST)
     throw std::runtime_error("LaplaceOperatorMatrixFree::vmult: only the zeroing pre-operation is supported");
   DASM_REQUIRE((const void *)dst != (const void *)src, "vmult: dst and src must not alias");
+  if (op->use_brick)
+    {
+      op_vmult_brick<T>(op, dst, src, post);
+      return;
+    }
   // pre: dst = 0 (the reference's default pre-operation, operator.h:1356-1363; the cell kernel
   // accumulates, so dst must start from zero in all cases)
   CUDA_CHECK(cudaMemsetAsync(dst, 0, (size_t)op->n_vec * sizeof(T), ctx->stream));
@@ -510,6 +644,27 @@ launch_fdm(dasm_fdm *f, T *dst, const T *src)
   DISPATCH_PATCH(f->m, launch_fdm_m<M, T>(f, dst, src));
 }
 
+template <int K, int BZ, typename T>
+static void
+launch_fdm_brick(dasm_fdm *f, T *dst, const T *src, const Epilogue<T> &epi)
+{
+  dasm_op *    op   = f->op;
+  dasm_ctx *   ctx  = op->ctx;
+  const size_t smem = BrickGeom<K, BZ>::template smem_bytes<T>();
+  {
+    KernelTimer timer(ctx, KC_FDM);
+    auto        kern = fdm_brick_kernel<K, T, BZ>;
+    const int   grid = brick_grid<K, BZ, T>(op, kern, smem);
+    kern<<<grid, BrickGeom<K, BZ>::NT, smem, ctx->stream>>>(src, dst, (T *)op->d_acc, epi, op->d_cidx, op->d_bricks, op->n_bricks, f->d_inst,
+                                                             (const T *)f->d_S, (const T *)f->d_lam, (const T *)(f->wmode == 1 ? f->d_cw : nullptr),
+                                                             (int)f->w_pre, (int)f->w_post);
+    ctx->launches++;
+  }
+  CUDA_CHECK(cudaGetLastError());
+  brick_finish<K, BZ, T>(op, dst, (const T *)nullptr, epi);
+  CUDA_CHECK(cudaGetLastError());
+}
+
 template <typename T>
 static void
 fdm_vmult(dasm_fdm *f, T *dst, const T *src, const dasm_hook *pre, const dasm_hook *post)
@@ -519,6 +674,25 @@ fdm_vmult(dasm_fdm *f, T *dst, const T *src, const dasm_hook *pre, const dasm_ho
   if (pre != nullptr && pre->kind != DASM_HOOK_NONE && pre->kind != DASM_HOOK_ZERO_DST)
     throw std::runtime_error("ASPoissonPreconditioner::vmult: only the zeroing pre-operation is supported");
   DASM_REQUIRE((const void *)dst != (const void *)src, "vmult: dst and src must not alias");
+  if (op->use_brick && f->d_pidx == nullptr && (f->wmode == 0 || f->wmode == 1))
+    {
+      const Epilogue<T> epi = epilogue_from_hook<T>(post);
+      switch (op->k)
+        {
+          case 1: launch_fdm_brick<1, 4, T>(f, dst, src, epi); break;
+          case 2: launch_fdm_brick<2, 4, T>(f, dst, src, epi); break;
+          case 3: launch_fdm_brick<3, 4, T>(f, dst, src, epi); break;
+          case 4:
+            if (op->brick_bz == 2)
+              launch_fdm_brick<4, 2, T>(f, dst, src, epi);
+            else
+              launch_fdm_brick<4, 4, T>(f, dst, src, epi);
+            break;
+          case 5: launch_fdm_brick<5, 2, T>(f, dst, src, epi); break;
+          default: throw std::runtime_error("internal: brick path for unsupported degree");
+        }
+      return;
+    }
   CUDA_CHECK(cudaMemsetAsync(dst, 0, (size_t)op->n_vec * sizeof(T), ctx->stream));
   op->exchange.run<T>(const_cast<T *>(src), false);
   launch_fdm<T>(f, dst, src);
@@ -884,6 +1058,108 @@ dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping
         }
       op->cart.g[0] = op->cart.g[1] = op->cart.g[2] = 0;
     }
+  // tuned brick path: degrees 1..5, one rank (the multi-rank path uses the generic kernels for now)
+  {
+    const char *force = getenv("DASM_FORCE_GENERIC");
+    op->use_brick     = (degree <= 5) && !(force && force[0] == '1') && M.n_ranks() == 1;
+    if (op->use_brick)
+      {
+        op->brick_bz = (degree <= 4) ? 4 : 2;
+        if (const char *bz = getenv("DASM_BRICK_BZ"))
+          if (degree == 4 && (bz[0] == '2' || bz[0] == '4'))
+            op->brick_bz = bz[0] - '0';
+        std::vector<BrickDesc> bricks;
+        // mesh bricks are 4x4x4 boxes of consecutive cells (x fastest); kernel bricks are z-slabs of them
+        const int *B = M.p.brick;
+        size_t     first = 0;
+        int        ibz_base = 0, nbz_total = 0;
+        for (int bz = 0; bz < M.nl[2]; bz += B[2])
+          {
+            const int dz      = std::min(B[2], M.nl[2] - bz);
+            const int n_slabs = (dz + op->brick_bz - 1) / op->brick_bz;
+            for (int by = 0; by < M.nl[1]; by += B[1])
+              for (int bx = 0; bx < M.nl[0]; bx += B[0])
+                {
+                  const int dx = std::min(B[0], M.nl[0] - bx), dy = std::min(B[1], M.nl[1] - by);
+                  for (int z0 = 0, sl = 0; z0 < dz; z0 += op->brick_bz, ++sl)
+                    {
+                      const int sz = std::min(op->brick_bz, dz - z0);
+                      BrickDesc bd;
+                      bd.first_cell = (uint32_t)(first + (size_t)z0 * dx * dy);
+                      bd.b[0]       = dx;
+                      bd.b[1]       = dy;
+                      bd.b[2]       = sz;
+                      bd.shared     = 0;
+                      bd.ib[0]      = bx / B[0];
+                      bd.ib[1]      = by / B[1];
+                      bd.ib[2]      = ibz_base + sl;
+                      bd.pad        = 0;
+                      const int lo_c[3] = {M.lo[0] + bx, M.lo[1] + by, M.lo[2] + bz + z0};
+                      const int hi_c[3] = {lo_c[0] + dx - 1, lo_c[1] + dy - 1, lo_c[2] + sz - 1};
+                      for (int d = 0; d < 3; ++d)
+                        {
+                          int nbc[3];
+                          if (M.neighbor(lo_c, d, 0, nbc))
+                            bd.shared |= (1u << (2 * d));
+                          if (M.neighbor(hi_c, d, 1, nbc))
+                            bd.shared |= (1u << (2 * d + 1));
+                        }
+                      bricks.push_back(bd);
+                    }
+                  first += (size_t)dx * dy * dz;
+                }
+            ibz_base += n_slabs;
+            nbz_total += n_slabs;
+          }
+        op->n_bricks = (int)bricks.size();
+        op->d_bricks = dev_upload(bricks, ctx->stream);
+        // list of the DoFs on shared brick faces: every brick contributes the shared entities it owns
+        // (lower entities of its cells, or upper entities on a domain-boundary face) lying on a
+        // shared lower face
+        {
+          std::vector<uint32_t> list;
+          for (const BrickDesc &bd : bricks)
+            {
+              const int ncells = bd.b[0] * bd.b[1] * bd.b[2];
+              for (int c = 0; c < ncells; ++c)
+                {
+                  const int cc[3] = {c % bd.b[0], (c / bd.b[0]) % bd.b[1], c / (bd.b[0] * bd.b[1])};
+                  if (cc[0] != 0 && cc[1] != 0 && cc[2] != 0)
+                    continue;
+                  for (int e = 0; e < 27; ++e)
+                    {
+                      const int ee[3] = {e % 3, (e / 3) % 3, e / 9};
+                      bool      owned = true, shared = false;
+                      for (int d = 0; d < 3; ++d)
+                        {
+                          if (ee[d] == 2 && !(cc[d] == bd.b[d] - 1 && !((bd.shared >> (2 * d + 1)) & 1u)))
+                            owned = false;
+                          if (ee[d] == 0 && cc[d] == 0 && ((bd.shared >> (2 * d)) & 1u))
+                            shared = true;
+                        }
+                      if (!owned || !shared)
+                        continue;
+                      const uint32_t g0 = op->nb.cidx[(size_t)(bd.first_cell + c) * 27 + e];
+                      if (g0 == INVALID_INDEX)
+                        continue;
+                      const int size = Mesh::entity_size(e, degree);
+                      for (int i = 0; i < size; ++i)
+                        list.push_back(g0 + i);
+                    }
+                }
+            }
+          std::sort(list.begin(), list.end());
+          list.erase(std::unique(list.begin(), list.end()), list.end());
+          op->n_shared      = (long long)list.size();
+          op->d_shared_list = dev_upload(list, ctx->stream);
+        }
+        CUDA_CHECK(cudaMalloc(&op->d_acc, std::max<size_t>(1, (size_t)op->n_vec) * op->esize()));
+        CUDA_CHECK(cudaMemset(op->d_acc, 0, std::max<size_t>(1, (size_t)op->n_vec) * op->esize()));
+        cudaDeviceProp prop;
+        CUDA_CHECK(cudaGetDeviceProperties(&prop, ctx->device));
+        op->n_sm = prop.multiProcessorCount;
+      }
+  }
   *out = op;
   DASM_API_END
 }
@@ -898,6 +1174,9 @@ dasm_op_destroy(dasm_op *op)
   cudaFree(op->d_cidx);
   cudaFree(op->d_constrained);
   cudaFree(op->d_geom);
+  cudaFree(op->d_bricks);
+  cudaFree(op->d_acc);
+  cudaFree(op->d_shared_list);
   op->exchange.destroy();
   for (void *p : op->scratch)
     cudaFree(p);

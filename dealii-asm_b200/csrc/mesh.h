@@ -9,12 +9,14 @@
 //   merged geometry coefficients                include/operator.h:674-711
 //   harmonic cell / patch extents               include/grid_tools.h:11-138
 //
-// Numbering ("owner-cell numbering", the data-locality numbering of this library; the reference uses
-// DoFRenumbering::matrix_free_data_locality, matrix_free_loop_08.likwid.cc:216-222, for the same
-// purpose): every mesh entity (vertex/line/quad/hex interior) is owned by the cell for which it is
-// a "lower" entity (or an upper-boundary entity of the last cell in a non-periodic direction).  Cells
-// are processed brick-major; each cell numbers its owned entities contiguously in lexicographic
-// entity order, so all DoFs of an entity are contiguous and a cell needs only 27 start indices.
+// Numbering ("brick-grouped owner-cell numbering", the data-locality numbering of this library; the
+// reference uses DoFRenumbering::matrix_free_data_locality, matrix_free_loop_08.likwid.cc:216-222, for
+// the same purpose): every mesh entity (vertex/line/quad/hex interior) is owned by the cell for which it
+// is a "lower" entity (or an upper-boundary entity of the last cell in a non-periodic direction).  Cells
+// are processed brick-major (4x4x4 bricks); inside a brick the entities touched only by cells of the
+// brick are numbered first (cell by cell, lexicographic entity order), then the entities on lower brick
+// faces shared with neighbouring bricks.  All DoFs of an entity are contiguous, so a cell needs only 27
+// start indices, and the DoFs a brick shares with its neighbours are one contiguous range.
 #pragma once
 #include <array>
 #include <cstdint>
@@ -398,40 +400,42 @@ namespace dasm
           const auto &c = cell_ijk[i];
           proc_of_local[((size_t)(c[2] - lo[2]) * nl[1] + (c[1] - lo[1])) * nl[0] + (c[0] - lo[0])] = i;
         }
-      // base offset of each cell + offset of each owned entity inside the cell
-      std::vector<uint32_t> base(n_cells + 1, 0);
-      // offset of owned entity code e within a cell = sum of sizes of owned entities with smaller
-      // code; depends only on which directions the cell is the last one of a non-periodic direction
-      uint32_t offset_table[8][28];
-      for (int t = 0; t < 8; ++t)
-        {
-          uint32_t off = 0;
-          for (int e = 0; e <= 27; ++e)
-            {
-              offset_table[t][e] = off;
-              if (e == 27)
-                break;
-              bool owned = true;
-              for (int d = 0, ee = e; d < 3; ++d, ee /= 3)
-                if (ee % 3 == 2 && !((t >> d) & 1))
-                  owned = false;
-              if (owned)
-                off += entity_size(e, k);
-            }
-        }
-      auto owned_offset = [&](const int c[3], int e_owned, int) {
-        int t = 0;
-        for (int d = 0; d < 3; ++d)
-          if (!p.periodic[d] && c[d] == p.nc[d] - 1)
-            t |= 1 << d;
-        return offset_table[t][e_owned];
-      };
-      for (size_t i = 0; i < n_cells; ++i)
-        {
-          const int c[3] = {cell_ijk[i][0], cell_ijk[i][1], cell_ijk[i][2]};
-          base[i + 1]    = base[i] + owned_offset(c, 27, k);
-        }
-      nb.n_owned = base[n_cells];
+      // start index of every owned entity: bricks in order; inside a brick first the entities touched only
+      // by cells of this brick ("private", cell by cell in lexicographic entity order), then the entities on
+      // the brick's lower faces that are shared with neighbouring bricks - so that the DoFs a brick shares
+      // with its neighbours form one contiguous range
+      std::vector<uint32_t> own_start(n_cells * 27, INVALID_INDEX);
+      {
+        uint32_t next = 0;
+        for (size_t b = 0; b + 1 < brick_ptr.size(); ++b)
+          {
+            const size_t first = brick_ptr[b], last = brick_ptr[b + 1];
+            const int    org[3] = {cell_ijk[first][0], cell_ijk[first][1], cell_ijk[first][2]};
+            for (int pass = 0; pass < 2; ++pass)
+              for (size_t i = first; i < last; ++i)
+                {
+                  const int c[3] = {cell_ijk[i][0], cell_ijk[i][1], cell_ijk[i][2]};
+                  for (int e = 0; e < 27; ++e)
+                    {
+                      bool owned = true, shared = false;
+                      for (int d = 0, ee = e; d < 3; ++d, ee /= 3)
+                        {
+                          const int ed = ee % 3;
+                          if (ed == 2 && !(!p.periodic[d] && c[d] == p.nc[d] - 1))
+                            owned = false;
+                          int nbc[3];
+                          if (ed == 0 && c[d] == org[d] && neighbor(c, d, 0, nbc))
+                            shared = true;
+                        }
+                      if (!owned || (shared ? 1 : 0) != pass)
+                        continue;
+                      own_start[i * 27 + e] = next;
+                      next += entity_size(e, k);
+                    }
+                }
+          }
+        nb.n_owned = next;
+      }
 
       const int my_rank = p.rank;
       // ghost entities: key (owner rank, owner cell lexicographic global id, entity code) -> index
@@ -460,7 +464,7 @@ namespace dasm
               if (orank == my_rank)
                 {
                   const size_t oi = proc_of_local[((size_t)(oc[2] - lo[2]) * nl[1] + (oc[1] - lo[1])) * nl[0] + (oc[0] - lo[0])];
-                  const uint32_t idx = base[oi] + owned_offset(oc, eo, k);
+                  const uint32_t idx = own_start[oi * 27 + eo];
                   nb.cidx_plain[i * 27 + e] = idx;
                   if (!slot_on_dirichlet_boundary(s))
                     nb.cidx[i * 27 + e] = idx;
@@ -567,7 +571,7 @@ namespace dasm
                           const int tc[3] = {cand[0][a], cand[1][b2], cand[2][g]};
                           const int q     = rank_of_cell(tc);
                           if (q != my_rank)
-                            send[q][{(long)my_rank, gid, (long)e}] = {base[i] + owned_offset(c, e, k), (uint32_t)entity_size(e, k)};
+                            send[q][{(long)my_rank, gid, (long)e}] = {own_start[i * 27 + e], (uint32_t)entity_size(e, k)};
                         }
                 }
             }

@@ -334,16 +334,18 @@ def brick_major_order(n_cells, brick=(4, 4, 4)):
     return np.array(order, dtype=np.int64)
 
 
-def number_dofs_owner_cell(mesh, k):
-    """Native "owner-cell" numbering of the B200 library, restated independently.
+def number_dofs_owner_cell(mesh, k, brick=(4, 4, 4)):
+    """Native "brick-grouped owner-cell" numbering of the B200 library, restated independently.
 
     Every mesh entity (3^dim per cell: vertex / line / quad / hex interior in the lexicographic
     3x3(x3) layout of vector_access_reduced.h:30-164) is owned by the cell for which it is a lower
     entity (code 0 or 1 per direction); code 2 is owned only by the last cell of a non-periodic
-    direction.  Cells are visited in mesh.cell_order and number their owned entities contiguously in
-    lexicographic entity order, DoFs lexicographic inside an entity.  Entities on a Dirichlet
-    boundary are numbered too (they exist in the vector, like constrained DoFs in deal.II) and are
-    flagged constrained.
+    direction.  Cells are grouped in bricks of `brick` cells (brick-major order = mesh.cell_order).
+    Per brick, first the owned entities that do not lie on a lower brick face with a neighbour cell
+    across it ("private") are numbered, cell by cell in lexicographic entity order, then the shared
+    ones in the same order; DoFs are lexicographic inside an entity.  Entities on a Dirichlet boundary
+    are numbered too (they exist in the vector, like constrained DoFs in deal.II) and flagged
+    constrained.
 
     returns cell_dofs [C, n^dim] (uint32, by lexicographic cell id), n_dofs, constrained [n_dofs]
             bool, compressed [C, 3^dim] entity start indices (plain: constrained keep their index)
@@ -364,22 +366,34 @@ def number_dofs_owner_cell(mesh, k):
                 cnt *= km1
         return cnt
 
+    # group the processing order into bricks (cells of a brick are consecutive in mesh.cell_order)
+    bricks = {}
     for c in mesh.cell_order:
         ijk = mesh.cell_ijk(int(c))
-        for e in range(3 ** dim):
-            ee = [(e // 3 ** d) % 3 for d in range(dim)]
-            owned = all(ee[d] < 2 or (not mesh.periodic[d] and ijk[d] == nc[d] - 1) for d in range(dim))
-            if not owned:
-                continue
-            slot = [2 * ijk[d] + ee[d] for d in range(dim)]
-            cnt = ent_size(ee)
-            ent_start[tuple(slot[::-1])] = next_dof
-            if mesh.dirichlet and cnt > 0 and any(
-                    (not mesh.periodic[d]) and (slot[d] == 0 or slot[d] == size[d] - 1) for d in range(dim)):
-                constrained_ranges.append((next_dof, next_dof + cnt))
-            next_dof += cnt
+        key = tuple(ijk[d] // brick[d] for d in reversed(range(dim)))
+        bricks.setdefault(key, []).append(int(c))
+    for key in sorted(bricks.keys()):
+        cells = bricks[key]
+        org = [key[dim - 1 - d] * brick[d] for d in range(dim)]
+        for pass_ in (0, 1):
+            for c in cells:
+                ijk = mesh.cell_ijk(c)
+                for e in range(3 ** dim):
+                    ee = [(e // 3 ** d) % 3 for d in range(dim)]
+                    owned = all(ee[d] < 2 or (not mesh.periodic[d] and ijk[d] == nc[d] - 1) for d in range(dim))
+                    if not owned:
+                        continue
+                    shared = any(ee[d] == 0 and ijk[d] == org[d] and mesh.neighbor(ijk, d, 0) is not None for d in range(dim))
+                    if int(shared) != pass_:
+                        continue
+                    slot = [2 * ijk[d] + ee[d] for d in range(dim)]
+                    cnt = ent_size(ee)
+                    ent_start[tuple(slot[::-1])] = next_dof
+                    if mesh.dirichlet and cnt > 0 and any(
+                            (not mesh.periodic[d]) and (slot[d] == 0 or slot[d] == size[d] - 1) for d in range(dim)):
+                        constrained_ranges.append((next_dof, next_dof + cnt))
+                    next_dof += cnt
     assert np.all(ent_start >= 0)
-    cell_dofs = np.zeros((mesh.C, n ** dim), dtype=np.uint32)
     compressed = np.zeros((mesh.C, 3 ** dim), dtype=np.uint32)
     for c in range(mesh.C):
         ijk = mesh.cell_ijk(c)
