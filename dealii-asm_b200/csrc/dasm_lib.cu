@@ -521,13 +521,24 @@ brick_finish(dasm_op *op, T *dst, const T *src_for_constrained, const Epilogue<T
     }
 }
 
+template <typename T>
+static int
+epilogue_n_operands(const Epilogue<T> &epi)
+{
+  if (epi.kind == EPI_RESIDUAL)
+    return 1;
+  if (epi.kind == EPI_CHEB)
+    return (epi.f1 != T(0) && epi.v1 != nullptr) ? 2 : 1;
+  return 0;
+}
+
 template <int K, int BZ, typename T>
 static void
 launch_laplace_brick(dasm_op *op, T *dst, const T *src, const Epilogue<T> &epi, bool copy_constrained)
 {
-  dasm_ctx *   ctx  = op->ctx;
-  const size_t smem = BrickGeom<K, BZ>::template smem_bytes<T>();
-  static const int dbg = getenv("DASM_DEBUG_SKIP") ? atoi(getenv("DASM_DEBUG_SKIP")) : 0; // timing experiments only
+  dasm_ctx *   ctx   = op->ctx;
+  const int    n_ops = epilogue_n_operands(epi);
+  const size_t smem  = BrickGeom<K, BZ>::template smem_bytes<T>(n_ops);
   {
     KernelTimer timer(ctx, KC_LAPLACE);
     if (op->geom_mode == 0)
@@ -535,14 +546,14 @@ launch_laplace_brick(dasm_op *op, T *dst, const T *src, const Epilogue<T> &epi, 
         auto      kern = laplace_brick_kernel<K, T, BZ, 0>;
         const int grid = brick_grid<K, BZ, T>(op, kern, smem);
         kern<<<grid, BrickGeom<K, BZ>::NT, smem, ctx->stream>>>(src, dst, (T *)op->d_acc, epi, op->d_cidx, op->d_bricks, op->n_bricks,
-                                                                 (const T *)nullptr, op->cart, dbg);
+                                                                 (const T *)nullptr, op->cart, n_ops);
       }
     else
       {
         auto      kern = laplace_brick_kernel<K, T, BZ, 1>;
         const int grid = brick_grid<K, BZ, T>(op, kern, smem);
         kern<<<grid, BrickGeom<K, BZ>::NT, smem, ctx->stream>>>(src, dst, (T *)op->d_acc, epi, op->d_cidx, op->d_bricks, op->n_bricks,
-                                                                 (const T *)op->d_geom, op->cart, dbg);
+                                                                 (const T *)op->d_geom, op->cart, n_ops);
       }
     ctx->launches++;
   }
@@ -648,16 +659,17 @@ template <int K, int BZ, typename T>
 static void
 launch_fdm_brick(dasm_fdm *f, T *dst, const T *src, const Epilogue<T> &epi)
 {
-  dasm_op *    op   = f->op;
-  dasm_ctx *   ctx  = op->ctx;
-  const size_t smem = BrickGeom<K, BZ>::template smem_bytes<T>();
+  dasm_op *    op    = f->op;
+  dasm_ctx *   ctx   = op->ctx;
+  const int    n_ops = epilogue_n_operands(epi);
+  const size_t smem  = BrickGeom<K, BZ>::template smem_bytes<T>(n_ops);
   {
     KernelTimer timer(ctx, KC_FDM);
     auto        kern = fdm_brick_kernel<K, T, BZ>;
     const int   grid = brick_grid<K, BZ, T>(op, kern, smem);
     kern<<<grid, BrickGeom<K, BZ>::NT, smem, ctx->stream>>>(src, dst, (T *)op->d_acc, epi, op->d_cidx, op->d_bricks, op->n_bricks, f->d_inst,
                                                              (const T *)f->d_S, (const T *)f->d_lam, (const T *)(f->wmode == 1 ? f->d_cw : nullptr),
-                                                             (int)f->w_pre, (int)f->w_post);
+                                                             (int)f->w_pre, (int)f->w_post, n_ops);
     ctx->launches++;
   }
   CUDA_CHECK(cudaGetLastError());

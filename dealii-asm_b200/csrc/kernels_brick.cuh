@@ -101,12 +101,13 @@ namespace dasm
     // (registers are allocated per warp in units of 512)
     static constexpr int NWARPS = (NT + 31) / 32;
     static constexpr int MAXREG = ((65536 / NWARPS / 512) * 512 / 32) >= 255 ? 255 : ((65536 / NWARPS / 512) * 512 / 32);
+    // layout: tile | operand tiles (n_ops) | slots | gidx | cidx[2]
     template <typename T>
     static constexpr size_t
-    smem_bytes()
+    smem_bytes(int n_ops)
     {
-      return (size_t)NPTS * sizeof(T) + (size_t)NCELLS * CS * sizeof(T) + (size_t)NPTS * sizeof(uint32_t) +
-             (size_t)NCELLS * 27 * sizeof(uint32_t);
+      return (size_t)(1 + n_ops) * NPTS * sizeof(T) + (size_t)NCELLS * CS * sizeof(T) + (size_t)NPTS * sizeof(uint32_t) +
+             (size_t)2 * NCELLS * 27 * sizeof(uint32_t);
     }
   };
 
@@ -223,41 +224,64 @@ namespace dasm
   // Thread -> tile point mapping: every thread owns "pencils" (px, py) of the tile and walks along pz, so
   // that everything depending on (px, py) (canonical cell, entity codes, offsets, slot addresses) is
   // computed once and the per-point work is a handful of integer instructions.  The 27 compressed indices
-  // of the brick's cells are staged in shared memory by one coalesced copy (the cells of a brick are
-  // consecutive).
-  template <int k>
-  __device__ __forceinline__ bool
-  point_shared(const BrickDesc &bd, int px, int py, int pz)
+  // of the brick's cells are staged in shared memory by one contiguous copy (the cells of a brick are
+  // consecutive) that is issued one brick ahead.  All global->shared traffic uses cp.async (LDGSTS): the
+  // source values are awaited before the first cell phase, the epilogue operands only before the store
+  // phase, so their latency hides behind the sum factorisation.
+  __device__ __forceinline__ void
+  cp_async_4(void *smem, const void *gmem)
   {
-    const int ex = bd.b[0] * k, ey = bd.b[1] * k, ez = bd.b[2] * k;
-    unsigned  s  = 0;
-    s |= (px == 0) ? (bd.shared & 1u) : 0u;
-    s |= (px == ex) ? (bd.shared & 2u) : 0u;
-    s |= (py == 0) ? (bd.shared & 4u) : 0u;
-    s |= (py == ey) ? (bd.shared & 8u) : 0u;
-    s |= (pz == 0) ? (bd.shared & 16u) : 0u;
-    s |= (pz == ez) ? (bd.shared & 32u) : 0u;
-    return s != 0;
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem));
+  }
+  __device__ __forceinline__ void
+  cp_async_8(void *smem, const void *gmem)
+  {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem));
+  }
+  template <typename T>
+  __device__ __forceinline__ void
+  cp_async_value(T *smem, const T *gmem)
+  {
+    if (sizeof(T) == 8)
+      cp_async_8(smem, gmem);
+    else
+      cp_async_4(smem, gmem);
+  }
+  __device__ __forceinline__ void
+  cp_async_commit()
+  {
+    asm volatile("cp.async.commit_group;\n" ::);
+  }
+  template <int N>
+  __device__ __forceinline__ void
+  cp_async_wait()
+  {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
   }
 
   template <int k, int BZ>
   __device__ __forceinline__ void
-  brick_stage_cidx(const BrickDesc &bd, const uint32_t *__restrict__ cidx, uint32_t *s_cidx)
+  brick_stage_cidx_async(const BrickDesc &bd, const uint32_t *__restrict__ cidx, uint32_t *s_cidx)
   {
-    using G          = BrickGeom<k, BZ>;
-    const int      n = bd.b[0] * bd.b[1] * bd.b[2] * 27;
+    using G             = BrickGeom<k, BZ>;
+    const int       n   = bd.b[0] * bd.b[1] * bd.b[2] * 27;
     const uint32_t *src = cidx + (size_t)bd.first_cell * 27;
     for (int i = threadIdx.x; i < n; i += G::NT)
-      s_cidx[i] = src[i];
+      cp_async_4(s_cidx + i, src + i);
   }
 
-  template <int k, int BZ, typename T, typename LoadFn>
+  // gather of the brick closure: global index of every tile point (kept in gidx), source values -> tile
+  // (commit group 1), epilogue operands at private points -> operand tiles (commit group 2)
+  template <int k, int BZ, typename T>
   __device__ __forceinline__ void
-  brick_load_tile(const BrickDesc &bd, const uint32_t *s_cidx, T *tile, uint32_t *gidx, LoadFn load)
+  brick_issue_loads(const BrickDesc &bd, const uint32_t *s_cidx, T *tile, T *ops0, T *ops1, uint32_t *gidx,
+                    const T *__restrict__ src, const T *__restrict__ v0, const T *__restrict__ v1)
   {
-    using G              = BrickGeom<k, BZ>;
-    constexpr int NPENC  = G::TX * G::TY;
-    constexpr int PITER  = (NPENC + G::NT - 1) / G::NT;
+    using G             = BrickGeom<k, BZ>;
+    constexpr int NPENC = G::TX * G::TY;
+    constexpr int PITER = (NPENC + G::NT - 1) / G::NT;
     const int     ex = bd.b[0] * k + 1, ey = bd.b[1] * k + 1, ez = bd.b[2] * k + 1;
 #pragma unroll 1
     for (int pi = 0; pi < PITER; ++pi)
@@ -273,83 +297,40 @@ namespace dasm
         const int sx = (ecx == 1) ? (k - 1) : 1, sy = (ecy == 1) ? (k - 1) : 1;
         const int cxy = cy * bd.b[0] + cx, exy = ecx + 3 * ecy, oxy = ox + sx * oy, sxy = sx * sy;
         const int czs = bd.b[0] * bd.b[1];
-        uint32_t  g[G::TZ];
+        const int base = py * G::TX + px;
 #pragma unroll
         for (int pz = 0; pz < G::TZ; ++pz)
           {
             const int cz = min(pz / k, bd.b[2] - 1), lz = pz - cz * k;
             const int ecz = (lz == 0) ? 0 : ((lz == k) ? 2 : 1), oz = (ecz == 1) ? lz - 1 : 0;
-            g[pz]         = DEV_INVALID;
             if (pz < ez)
               {
                 const uint32_t st = s_cidx[(cz * czs + cxy) * 27 + exy + 9 * ecz];
-                g[pz]             = (st == DEV_INVALID) ? DEV_INVALID : st + oxy + sxy * oz;
+                const uint32_t g  = (st == DEV_INVALID) ? DEV_INVALID : st + oxy + sxy * oz;
+                const int      p  = pz * NPENC + base;
+                gidx[p]           = g;
+                if (g == DEV_INVALID)
+                  tile[p] = T(0);
+                else
+                  cp_async_value(tile + p, src + g);
               }
           }
-        T v[G::TZ];
-#pragma unroll
-        for (int pz = 0; pz < G::TZ; ++pz)
-          v[pz] = (g[pz] == DEV_INVALID) ? T(0) : load(g[pz]);
-#pragma unroll
-        for (int pz = 0; pz < G::TZ; ++pz)
-          if (pz < ez)
-            {
-              gidx[(pz * G::TY + py) * G::TX + px] = g[pz];
-              tile[(pz * G::TY + py) * G::TX + px] = v[pz];
-            }
       }
   }
 
-  // The cell results are accumulated into the (re-used) tile by the cell threads themselves, colour by
-  // colour: cells of equal parity (cx&1, cy&1, cz&1) share no tile point, so the 8 colour steps need no
-  // atomics and the summation order is fixed (deterministic results).
+  // epilogue operands (v0, v1 of the epilogue) at the private points of the tile -> operand tiles
   template <int k, int BZ, typename T>
   __device__ __forceinline__ void
-  brick_accumulate(const bool act, const int cx, const int cy, const int cz, const int t, T *tile, const T (&v)[k + 1][k + 1])
-  {
-    using G         = BrickGeom<k, BZ>;
-    constexpr int n = k + 1;
-    const int     colour = (cx & 1) | ((cy & 1) << 1) | ((cz & 1) << 2);
-    T *           tp     = tile + ((cz * k + t) * G::TY + cy * k) * G::TX + cx * k;
-#pragma unroll 1
-    for (int col = 0; col < 8; ++col)
-      {
-        if (act && colour == col)
-          {
-#pragma unroll
-            for (int y = 0; y < n; ++y)
-#pragma unroll
-              for (int x = 0; x < n; ++x)
-                tp[y * G::TX + x] += v[y][x];
-          }
-        __syncthreads();
-      }
-  }
-
-  template <int k, int BZ, typename T>
-  __device__ __forceinline__ void
-  brick_zero_tile(T *tile)
-  {
-    using G = BrickGeom<k, BZ>;
-    for (int p = threadIdx.x; p < G::NPTS; p += G::NT)
-      tile[p] = T(0);
-  }
-
-  // fused epilogue (private points: plain stores) / accumulation (points on shared faces: red.global.add
-  // into the zero-invariant accumulator; finish_shared_kernel completes them: the numbering makes the shared
-  // DoFs of a brick one contiguous range, so that pass is a coalesced sweep over ~18 % of the vector).
-  // (An in-kernel variant where the last-arriving brick finishes a shared piece - arrival counters,
-  // threadfence-reduction pattern - was measured slower: the fence + counter round trips are exposed.)
-  template <int k, int BZ, typename T>
-  __device__ __forceinline__ void
-  brick_store_tile(const BrickDesc &bd, const T *tile, const uint32_t *gidx, T *__restrict__ dst, T *__restrict__ acc,
-                   const Epilogue<T> &epi)
+  brick_issue_loads_ops(const BrickDesc &bd, const uint32_t *gidx, T *ops0, T *ops1, const Epilogue<T> &epi)
   {
     using G             = BrickGeom<k, BZ>;
     constexpr int NPENC = G::TX * G::TY;
     constexpr int PITER = (NPENC + G::NT - 1) / G::NT;
-    constexpr int CH    = (G::TZ + 2) / 3; // points along z whose global loads are in flight together
-    const int     ex = bd.b[0] * k + 1, ey = bd.b[1] * k + 1, ez = bd.b[2] * k + 1;
+    const bool    need0 = (epi.kind == EPI_RESIDUAL || epi.kind == EPI_CHEB);
+    const bool    need1 = (epi.kind == EPI_CHEB && epi.f1 != T(0) && epi.v1 != nullptr);
+    if (!need0)
+      return;
+    const int ex = bd.b[0] * k + 1, ey = bd.b[1] * k + 1, ez = bd.b[2] * k + 1;
 #pragma unroll 1
     for (int pi = 0; pi < PITER; ++pi)
       {
@@ -360,37 +341,96 @@ namespace dasm
         const unsigned shxy = ((px == 0) ? (bd.shared & 1u) : 0u) | ((px == ex - 1) ? (bd.shared & 2u) : 0u) |
                               ((py == 0) ? (bd.shared & 4u) : 0u) | ((py == ey - 1) ? (bd.shared & 8u) : 0u);
         const int base = py * G::TX + px;
-#pragma unroll 1
-        for (int z0 = 0; z0 < ez; z0 += CH)
-          {
-            uint32_t g[CH];
-            T        ea[CH], eb[CH], y[CH];
-            bool     sh[CH];
 #pragma unroll
-            for (int j = 0; j < CH; ++j)
+        for (int pz = 0; pz < G::TZ; ++pz)
+          if (pz < ez)
+            {
+              const int      p  = pz * NPENC + base;
+              const uint32_t g  = gidx[p]; // written by this thread in brick_issue_loads
+              const bool     sh = (shxy | ((pz == 0) ? (bd.shared & 16u) : 0u) | ((pz == ez - 1) ? (bd.shared & 32u) : 0u)) != 0;
+              if (g != DEV_INVALID && !sh)
+                {
+                  cp_async_value(ops0 + p, epi.v0 + g);
+                  if (need1)
+                    cp_async_value(ops1 + p, epi.v1 + g);
+                }
+            }
+      }
+  }
+
+  // reduction of the cell results (slots) per tile point in a fixed order (deterministic, no shared-memory
+  // atomics), fused epilogue at private points (plain stores), red.global.add into the zero-invariant
+  // accumulator at points on shared brick faces (completed by finish_shared_kernel)
+  template <int k, int BZ, typename T>
+  __device__ __forceinline__ void
+  brick_reduce_store(const BrickDesc &bd, const T *slots, const T *ops0, const T *ops1, const uint32_t *gidx,
+                     T *__restrict__ dst, T *__restrict__ acc, const Epilogue<T> &epi)
+  {
+    using G             = BrickGeom<k, BZ>;
+    constexpr int n     = k + 1;
+    constexpr int NPENC = G::TX * G::TY;
+    constexpr int PITER = (NPENC + G::NT - 1) / G::NT;
+    const int     ex = bd.b[0] * k + 1, ey = bd.b[1] * k + 1, ez = bd.b[2] * k + 1;
+    const bool    need0 = (epi.kind == EPI_RESIDUAL || epi.kind == EPI_CHEB);
+    const bool    need1 = (epi.kind == EPI_CHEB && epi.f1 != T(0) && epi.v1 != nullptr);
+#pragma unroll 1
+    for (int pi = 0; pi < PITER; ++pi)
+      {
+        const int q  = threadIdx.x + pi * G::NT;
+        const int px = q % G::TX, py = q / G::TX;
+        if (q >= NPENC || px >= ex || py >= ey)
+          continue;
+        // the <= 2 x 2 cells containing the pencil in x and y: primary (c = p / k, l = p % k) and, on a cell
+        // boundary, the lower neighbour with l = k.  Missing ones get mask 0 and a valid dummy offset.
+        int o0, o1, o2, o3;
+        T   m0, m1, m2, m3;
+        {
+          const int  chx = px / k, llx = px - chx * k, chy = py / k, lly = py - chy * k;
+          const bool xa = chx < bd.b[0], xb = (llx == 0 && chx > 0), ya = chy < bd.b[1], yb = (lly == 0 && chy > 0);
+          const int  cxa = xa ? chx : chx - 1, lxa = xa ? llx : k, cxb = xb ? chx - 1 : cxa, lxb = xb ? k : lxa;
+          const int  cya = ya ? chy : chy - 1, lya = ya ? lly : k, cyb = yb ? chy - 1 : cya, lyb = yb ? k : lya;
+          // (xa || xb) and (ya || yb) always hold for points of the tile
+          o0 = (cya * bd.b[0] + cxa) * G::CS + lya * n + lxa;
+          o1 = (cya * bd.b[0] + cxb) * G::CS + lya * n + lxb;
+          o2 = (cyb * bd.b[0] + cxa) * G::CS + lyb * n + lxa;
+          o3 = (cyb * bd.b[0] + cxb) * G::CS + lyb * n + lxb;
+          m0 = T(1);
+          m1 = (xa && xb) ? T(1) : T(0);
+          m2 = (ya && yb) ? T(1) : T(0);
+          m3 = m1 * m2;
+        }
+        const unsigned shxy = ((px == 0) ? (bd.shared & 1u) : 0u) | ((px == ex - 1) ? (bd.shared & 2u) : 0u) |
+                              ((py == 0) ? (bd.shared & 4u) : 0u) | ((py == ey - 1) ? (bd.shared & 8u) : 0u);
+        const int base = py * G::TX + px;
+        const int czs  = bd.b[0] * bd.b[1] * G::CS;
+#pragma unroll
+        for (int pz = 0; pz < G::TZ; ++pz)
+          {
+            if (pz < ez)
               {
-                const int pz = z0 + j;
-                g[j]         = DEV_INVALID;
-                sh[j]        = false;
-                ea[j] = eb[j] = y[j] = T(0);
-                if (pz < ez)
+                const int      p = pz * NPENC + base;
+                const uint32_t g = gidx[p];
+                if (g != DEV_INVALID)
                   {
-                    g[j]  = gidx[pz * NPENC + base];
-                    y[j]  = tile[pz * NPENC + base];
-                    sh[j] = (shxy | ((pz == 0) ? (bd.shared & 16u) : 0u) | ((pz == ez - 1) ? (bd.shared & 32u) : 0u)) != 0;
-                    if (g[j] != DEV_INVALID && !sh[j])
-                      epilogue_load(epi, g[j], ea[j], eb[j]);
+                    constexpr int dummy = 0;
+                    (void)dummy;
+                    const int  chz = pz / k, llz = pz - chz * k;
+                    const bool za  = chz < bd.b[2];
+                    const int  oza = (za ? chz : chz - 1) * czs + (za ? llz : k) * n * n;
+                    T          y   = slots[oza + o0] + m1 * slots[oza + o1] + m2 * slots[oza + o2] + m3 * slots[oza + o3];
+                    if (llz == 0 && chz > 0)
+                      {
+                        const T   mz  = za ? T(1) : T(0); // the lower cell was already taken as primary if !za
+                        const int ozb = (chz - 1) * czs + k * n * n;
+                        y += mz * (slots[ozb + o0] + m1 * slots[ozb + o1] + m2 * slots[ozb + o2] + m3 * slots[ozb + o3]);
+                      }
+                    const bool sh = (shxy | ((pz == 0) ? (bd.shared & 16u) : 0u) | ((pz == ez - 1) ? (bd.shared & 32u) : 0u)) != 0;
+                    if (sh)
+                      atomic_add(acc + g, y);
+                    else
+                      dst[g] = epilogue_compute(epi, y, need0 ? ops0[p] : T(0), need1 ? ops1[p] : T(0));
                   }
               }
-#pragma unroll
-            for (int j = 0; j < CH; ++j)
-              if (g[j] != DEV_INVALID)
-                {
-                  if (sh[j])
-                    atomic_add(acc + g[j], y[j]);
-                  else
-                    dst[g[j]] = epilogue_compute(epi, y[j], ea[j], eb[j]);
-                }
           }
       }
   }
@@ -408,31 +448,45 @@ namespace dasm
                        const int n_bricks,
                        const T *__restrict__ geom,
                        const CartesianCoef cart,
-                       const int dbg)
+                       const int n_ops)
   {
     using G         = BrickGeom<k, BZ>;
     constexpr int n = k + 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T *       tile  = reinterpret_cast<T *>(smem_raw);
-    T *       slots = tile + G::NPTS;
-    uint32_t *gidx  = reinterpret_cast<uint32_t *>(slots + G::NCELLS * G::CS);
-    uint32_t *s_cidx = gidx + G::NPTS;
+    T *       tile   = reinterpret_cast<T *>(smem_raw);
+    T *       ops0   = (n_ops > 0) ? tile + G::NPTS : tile;
+    T *       ops1   = (n_ops > 1) ? tile + 2 * G::NPTS : ops0;
+    T *       slots  = tile + (1 + n_ops) * G::NPTS;
+    uint32_t *gidx   = reinterpret_cast<uint32_t *>(slots + G::NCELLS * G::CS);
+    uint32_t *s_cidx = gidx + G::NPTS; // two buffers of NCELLS * 27
 
     const auto &B = BasisOf<T>::template get<k>();
     const int   c = threadIdx.x / n; // cell in brick
     const int   t = threadIdx.x % n; // plane index
 
-    for (int bi = blockIdx.x; bi < n_bricks; bi += gridDim.x)
+    if (blockIdx.x < n_bricks)
+      brick_stage_cidx_async<k, BZ>(bricks[blockIdx.x], cidx, s_cidx);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    int buf = 0;
+    for (int bi = blockIdx.x; bi < n_bricks; bi += gridDim.x, buf ^= 1)
       {
         const BrickDesc bd     = bricks[bi];
         const int       ncells = bd.b[0] * bd.b[1] * bd.b[2];
-        brick_stage_cidx<k, BZ>(bd, cidx, s_cidx);
-        __syncthreads();
-        if (!(dbg & 1))
-          brick_load_tile<k, BZ, T>(bd, s_cidx, tile, gidx, [&](uint32_t g) { return src[g]; });
+        const uint32_t *cur_cidx = s_cidx + buf * (G::NCELLS * 27);
+        // group 1: source values, group 2: epilogue operands, group 3: indices of the next brick
+        brick_issue_loads<k, BZ, T>(bd, cur_cidx, tile, ops0, ops1, gidx, src, (const T *)nullptr, (const T *)nullptr);
+        cp_async_commit();
+        brick_issue_loads_ops<k, BZ, T>(bd, gidx, ops0, ops1, epi);
+        cp_async_commit();
+        if (bi + (int)gridDim.x < n_bricks)
+          brick_stage_cidx_async<k, BZ>(bricks[bi + gridDim.x], cidx, s_cidx + (buf ^ 1) * (G::NCELLS * 27));
+        cp_async_commit();
+        cp_async_wait<2>();
         __syncthreads();
 
-        const bool act = (c < ncells) && !(dbg & 2);
+        const bool act = (c < ncells);
         const int  cx = c % bd.b[0], cy = (c / bd.b[0]) % bd.b[1], cz = c / (bd.b[0] * bd.b[1]);
         T *        S  = slots + c * G::CS;
         T          r[n][n]; // partial result of the x/z directions, plane y = t, [z][x]
@@ -456,7 +510,6 @@ namespace dasm
                 S[(t * n + y) * n + x] = v[y][x];
           }
         __syncthreads();
-        brick_zero_tile<k, BZ, T>(tile); // the source values are consumed; the tile now collects the results
         if (GEOM == 0)
           {
             // phase B: plane y = t, [z][x]: interpolate in z; x and z parts of the Laplacian
@@ -616,24 +669,27 @@ namespace dasm
                 S[(z * n + t) * n + x] = r[z][x];
           }
         __syncthreads();
-        // phase E: plane z = t: N^T in y and x; the result stays in registers and is accumulated into the tile
-        {
-          T v[n][n];
-          if (act)
-            {
+        // phase E: plane z = t: N^T in y and x -> final cell result in the slot
+        if (act)
+          {
+            T v[n][n];
 #pragma unroll
-              for (int y = 0; y < n; ++y)
+            for (int y = 0; y < n; ++y)
 #pragma unroll
-                for (int x = 0; x < n; ++x)
-                  v[y][x] = S[(t * n + y) * n + x];
-              apply_slow<n, T, true>(v, B.N);
-              apply_fast<n, T, true>(v, B.N);
-            }
-          if (!(dbg & 4))
-            brick_accumulate<k, BZ, T>(act, cx, cy, cz, t, tile, v);
-        }
-        if (!(dbg & 8))
-          brick_store_tile<k, BZ, T>(bd, tile, gidx, dst, acc, epi);
+              for (int x = 0; x < n; ++x)
+                v[y][x] = S[(t * n + y) * n + x];
+            apply_slow<n, T, true>(v, B.N);
+            apply_fast<n, T, true>(v, B.N);
+#pragma unroll
+            for (int y = 0; y < n; ++y)
+#pragma unroll
+              for (int x = 0; x < n; ++x)
+                S[(t * n + y) * n + x] = v[y][x];
+          }
+        cp_async_wait<1>(); // epilogue operands have landed
+        __syncthreads();
+        brick_reduce_store<k, BZ, T>(bd, slots, ops0, ops1, gidx, dst, acc, epi);
+        cp_async_wait<0>(); // indices of the next brick
         __syncthreads();
       }
   }
@@ -653,27 +709,42 @@ namespace dasm
                    const T *__restrict__ lam,
                    const T *__restrict__ cw, // [cell][27] or nullptr
                    const int w_pre,
-                   const int w_post)
+                   const int w_post,
+                   const int n_ops)
   {
     using G          = BrickGeom<k, BZ>;
     constexpr int n  = k + 1;
     constexpr int n2 = n * n;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T *       tile  = reinterpret_cast<T *>(smem_raw);
-    T *       slots = tile + G::NPTS;
-    uint32_t *gidx  = reinterpret_cast<uint32_t *>(slots + G::NCELLS * G::CS);
-    uint32_t *s_cidx = gidx + G::NPTS;
+    T *       tile   = reinterpret_cast<T *>(smem_raw);
+    T *       ops0   = (n_ops > 0) ? tile + G::NPTS : tile;
+    T *       ops1   = (n_ops > 1) ? tile + 2 * G::NPTS : ops0;
+    T *       slots  = tile + (1 + n_ops) * G::NPTS;
+    uint32_t *gidx   = reinterpret_cast<uint32_t *>(slots + G::NCELLS * G::CS);
+    uint32_t *s_cidx = gidx + G::NPTS; // two buffers of NCELLS * 27
 
     const int c = threadIdx.x / n;
     const int t = threadIdx.x % n;
 
-    for (int bi = blockIdx.x; bi < n_bricks; bi += gridDim.x)
+    if (blockIdx.x < n_bricks)
+      brick_stage_cidx_async<k, BZ>(bricks[blockIdx.x], cidx, s_cidx);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    int buf = 0;
+    for (int bi = blockIdx.x; bi < n_bricks; bi += gridDim.x, buf ^= 1)
       {
         const BrickDesc bd     = bricks[bi];
         const int       ncells = bd.b[0] * bd.b[1] * bd.b[2];
-        brick_stage_cidx<k, BZ>(bd, cidx, s_cidx);
-        __syncthreads();
-        brick_load_tile<k, BZ, T>(bd, s_cidx, tile, gidx, [&](uint32_t g) { return src[g]; });
+        const uint32_t *cur_cidx = s_cidx + buf * (G::NCELLS * 27);
+        brick_issue_loads<k, BZ, T>(bd, cur_cidx, tile, ops0, ops1, gidx, src, (const T *)nullptr, (const T *)nullptr);
+        cp_async_commit();
+        brick_issue_loads_ops<k, BZ, T>(bd, gidx, ops0, ops1, epi);
+        cp_async_commit();
+        if (bi + (int)gridDim.x < n_bricks)
+          brick_stage_cidx_async<k, BZ>(bricks[bi + gridDim.x], cidx, s_cidx + (buf ^ 1) * (G::NCELLS * 27));
+        cp_async_commit();
+        cp_async_wait<2>();
         __syncthreads();
 
         const bool     act  = c < ncells;
@@ -732,7 +803,6 @@ namespace dasm
                 S[(t * n + y) * n + x] = v[y][x];
           }
         __syncthreads();
-        brick_zero_tile<k, BZ, T>(tile);
         // phase B: plane y = t, [z][x]: S2^T in z, scale by 1/(l0[x] + l1[t] + l2[z]), S2 in z, S0 in x
         if (act)
           {
@@ -774,37 +844,42 @@ namespace dasm
                 S[(z * n + t) * n + x] = w[z][x];
           }
         __syncthreads();
-        // phase C: plane z = t, [y][x]: S1 in y, (post-weights); result accumulated into the tile
-        {
-          T v[n][n];
-          if (act)
-            {
+        // phase C: plane z = t, [y][x]: S1 in y, (post-weights) -> final cell result in the slot
+        if (act)
+          {
+            T v[n][n];
 #pragma unroll
-              for (int y = 0; y < n; ++y)
+            for (int y = 0; y < n; ++y)
 #pragma unroll
-                for (int x = 0; x < n; ++x)
-                  v[y][x] = S[(t * n + y) * n + x];
-              T M[n2];
+              for (int x = 0; x < n; ++x)
+                v[y][x] = S[(t * n + y) * n + x];
+            T M[n2];
 #pragma unroll
-              for (int i = 0; i < n2; ++i)
-                M[i] = Smat[(size_t)i1 * n2 + i];
-              apply_slow<n, T, false>(v, M);
-              if (cw != nullptr && w_post)
-                {
-                  T wloc[9];
+            for (int i = 0; i < n2; ++i)
+              M[i] = Smat[(size_t)i1 * n2 + i];
+            apply_slow<n, T, false>(v, M);
+            if (cw != nullptr && w_post)
+              {
+                T wloc[9];
 #pragma unroll
-                  for (int e = 0; e < 9; ++e)
-                    wloc[e] = cw[(size_t)cell * 27 + e + 9 * et];
+                for (int e = 0; e < 9; ++e)
+                  wloc[e] = cw[(size_t)cell * 27 + e + 9 * et];
 #pragma unroll
-                  for (int y = 0; y < n; ++y)
+                for (int y = 0; y < n; ++y)
 #pragma unroll
-                    for (int x = 0; x < n; ++x)
-                      v[y][x] *= wloc[((x == 0) ? 0 : ((x == k) ? 2 : 1)) + 3 * ((y == 0) ? 0 : ((y == k) ? 2 : 1))];
-                }
-            }
-          brick_accumulate<k, BZ, T>(act, cx, cy, cz, t, tile, v);
-        }
-        brick_store_tile<k, BZ, T>(bd, tile, gidx, dst, acc, epi);
+                  for (int x = 0; x < n; ++x)
+                    v[y][x] *= wloc[((x == 0) ? 0 : ((x == k) ? 2 : 1)) + 3 * ((y == 0) ? 0 : ((y == k) ? 2 : 1))];
+              }
+#pragma unroll
+            for (int y = 0; y < n; ++y)
+#pragma unroll
+              for (int x = 0; x < n; ++x)
+                S[(t * n + y) * n + x] = v[y][x];
+          }
+        cp_async_wait<1>();
+        __syncthreads();
+        brick_reduce_store<k, BZ, T>(bd, slots, ops0, ops1, gidx, dst, acc, epi);
+        cp_async_wait<0>();
         __syncthreads();
       }
   }
