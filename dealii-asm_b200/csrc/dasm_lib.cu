@@ -282,6 +282,7 @@ struct dasm_op
   void *            d_acc     = nullptr; // zero-invariant accumulator of shared-face DoFs (n_vec)
   uint32_t *        d_shared_list = nullptr; // owned DoFs on brick faces shared with other bricks
   long long         n_shared  = 0;
+  bool              shared_ranges_ok = false; // every brick's own shared DoFs are one contiguous range
   int               n_sm      = 148;
 
   dasm_op(int degree)
@@ -322,7 +323,7 @@ struct dasm_cheb
   bool      ev_ready = false;
   double    min_ev = 0, max_ev = 0, delta = 0, theta = 0;
   void *    d_inv_diag = nullptr;
-  void *    t1 = nullptr, *t2 = nullptr, *xold = nullptr, *xin = nullptr, *bin = nullptr;
+  void *    t1 = nullptr, *t1b = nullptr, *t2 = nullptr, *xold = nullptr, *xin = nullptr, *bin = nullptr;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -504,10 +505,10 @@ brick_grid(dasm_op *op, Kern kern, size_t smem)
 // finish the shared-face DoFs (dst = epilogue(acc), acc = 0) and run the epilogue on constrained DoFs
 template <int K, int BZ, typename T>
 static void
-brick_finish(dasm_op *op, T *dst, const T *src_for_constrained, const Epilogue<T> &epi)
+brick_finish(dasm_op *op, T *dst, const T *src_for_constrained, const Epilogue<T> &epi, const int shared_mode)
 {
   dasm_ctx *ctx = op->ctx;
-  if (op->n_shared > 0)
+  if (op->n_shared > 0 && shared_mode == SHARED_ACC)
     {
       KernelTimer timer(ctx, KC_VECTOR);
       finish_shared_kernel<T><<<nblocks(op->n_shared), 256, 0, ctx->stream>>>(dst, (T *)op->d_acc, epi, op->d_shared_list, op->n_shared);
@@ -534,7 +535,8 @@ epilogue_n_operands(const Epilogue<T> &epi)
 
 template <int K, int BZ, typename T>
 static void
-launch_laplace_brick(dasm_op *op, T *dst, const T *src, const Epilogue<T> &epi, bool copy_constrained)
+launch_laplace_brick(dasm_op *op, T *dst, const T *src, const Epilogue<T> &epi, bool copy_constrained, const int shared_mode,
+                     const NextInit<T> &ni)
 {
   dasm_ctx *   ctx   = op->ctx;
   const int    n_ops = epilogue_n_operands(epi);
@@ -546,42 +548,67 @@ launch_laplace_brick(dasm_op *op, T *dst, const T *src, const Epilogue<T> &epi, 
         auto      kern = laplace_brick_kernel<K, T, BZ, 0>;
         const int grid = brick_grid<K, BZ, T>(op, kern, smem);
         kern<<<grid, BrickGeom<K, BZ>::NT, smem, ctx->stream>>>(src, dst, (T *)op->d_acc, epi, op->d_cidx, op->d_bricks, op->n_bricks,
-                                                                 (const T *)nullptr, op->cart, n_ops);
+                                                                 (const T *)nullptr, op->cart, n_ops, shared_mode, ni);
       }
     else
       {
         auto      kern = laplace_brick_kernel<K, T, BZ, 1>;
         const int grid = brick_grid<K, BZ, T>(op, kern, smem);
         kern<<<grid, BrickGeom<K, BZ>::NT, smem, ctx->stream>>>(src, dst, (T *)op->d_acc, epi, op->d_cidx, op->d_bricks, op->n_bricks,
-                                                                 (const T *)op->d_geom, op->cart, n_ops);
+                                                                 (const T *)op->d_geom, op->cart, n_ops, shared_mode, ni);
       }
     ctx->launches++;
   }
   CUDA_CHECK(cudaGetLastError());
-  brick_finish<K, BZ, T>(op, dst, copy_constrained ? src : nullptr, epi);
+  brick_finish<K, BZ, T>(op, dst, copy_constrained ? src : nullptr, epi, shared_mode);
   CUDA_CHECK(cudaGetLastError());
 }
 
 template <typename T>
+static NextInit<T>
+no_next_init()
+{
+  NextInit<T> ni;
+  ni.out = nullptr;
+  ni.v0  = nullptr;
+  ni.v1  = nullptr;
+  ni.f1  = 0;
+  return ni;
+}
+
+template <typename T>
 static void
-op_vmult_brick(dasm_op *op, T *dst, const T *src, const dasm_hook *post)
+op_vmult_brick(dasm_op *op, T *dst, const T *src, const dasm_hook *post, const int shared_mode = SHARED_ACC,
+               const NextInit<T> &ni = no_next_init<T>())
 {
   const Epilogue<T> epi  = epilogue_from_hook<T>(post);
   const bool        copy = (post != nullptr && post->kind != DASM_HOOK_NONE);
   switch (op->k)
     {
-      case 1: launch_laplace_brick<1, 4, T>(op, dst, src, epi, copy); break;
-      case 2: launch_laplace_brick<2, 4, T>(op, dst, src, epi, copy); break;
-      case 3: launch_laplace_brick<3, 4, T>(op, dst, src, epi, copy); break;
+      case 1: launch_laplace_brick<1, 4, T>(op, dst, src, epi, copy, shared_mode, ni); break;
+      case 2: launch_laplace_brick<2, 4, T>(op, dst, src, epi, copy, shared_mode, ni); break;
+      case 3: launch_laplace_brick<3, 4, T>(op, dst, src, epi, copy, shared_mode, ni); break;
       case 4:
         if (op->brick_bz == 2)
-          launch_laplace_brick<4, 2, T>(op, dst, src, epi, copy);
+          launch_laplace_brick<4, 2, T>(op, dst, src, epi, copy, shared_mode, ni);
         else
-          launch_laplace_brick<4, 4, T>(op, dst, src, epi, copy);
+          launch_laplace_brick<4, 4, T>(op, dst, src, epi, copy, shared_mode, ni);
         break;
-      case 5: launch_laplace_brick<5, 2, T>(op, dst, src, epi, copy); break;
+      case 5: launch_laplace_brick<5, 2, T>(op, dst, src, epi, copy, shared_mode, ni); break;
       default: throw std::runtime_error("internal: brick path for unsupported degree");
     }
+}
+
+// stand-alone pre-initialisation of a destination on all shared DoFs
+template <typename T>
+static void
+init_shared(dasm_op *op, const NextInit<T> &ni)
+{
+  if (op->n_shared == 0)
+    return;
+  KernelTimer timer(op->ctx, KC_VECTOR);
+  init_shared_kernel<T><<<nblocks(op->n_shared), 256, 0, op->ctx->stream>>>(ni, op->d_shared_list, op->n_shared);
+  op->ctx->launches++;
 }
 
 template <typename T>
@@ -657,7 +684,7 @@ launch_fdm(dasm_fdm *f, T *dst, const T *src)
 
 template <int K, int BZ, typename T>
 static void
-launch_fdm_brick(dasm_fdm *f, T *dst, const T *src, const Epilogue<T> &epi)
+launch_fdm_brick(dasm_fdm *f, T *dst, const T *src, const Epilogue<T> &epi, const int shared_mode, const NextInit<T> &ni)
 {
   dasm_op *    op    = f->op;
   dasm_ctx *   ctx   = op->ctx;
@@ -669,12 +696,41 @@ launch_fdm_brick(dasm_fdm *f, T *dst, const T *src, const Epilogue<T> &epi)
     const int   grid = brick_grid<K, BZ, T>(op, kern, smem);
     kern<<<grid, BrickGeom<K, BZ>::NT, smem, ctx->stream>>>(src, dst, (T *)op->d_acc, epi, op->d_cidx, op->d_bricks, op->n_bricks, f->d_inst,
                                                              (const T *)f->d_S, (const T *)f->d_lam, (const T *)(f->wmode == 1 ? f->d_cw : nullptr),
-                                                             (int)f->w_pre, (int)f->w_post, n_ops);
+                                                             (int)f->w_pre, (int)f->w_post, n_ops, shared_mode, ni);
     ctx->launches++;
   }
   CUDA_CHECK(cudaGetLastError());
-  brick_finish<K, BZ, T>(op, dst, (const T *)nullptr, epi);
+  brick_finish<K, BZ, T>(op, dst, (const T *)nullptr, epi, shared_mode);
   CUDA_CHECK(cudaGetLastError());
+}
+
+static bool
+fdm_uses_brick(const dasm_fdm *f)
+{
+  return f->op->use_brick && f->d_pidx == nullptr && (f->wmode == 0 || f->wmode == 1);
+}
+
+template <typename T>
+static void
+fdm_vmult_brick(dasm_fdm *f, T *dst, const T *src, const dasm_hook *post, const int shared_mode = SHARED_ACC,
+                const NextInit<T> &ni = no_next_init<T>())
+{
+  dasm_op *         op  = f->op;
+  const Epilogue<T> epi = epilogue_from_hook<T>(post);
+  switch (op->k)
+    {
+      case 1: launch_fdm_brick<1, 4, T>(f, dst, src, epi, shared_mode, ni); break;
+      case 2: launch_fdm_brick<2, 4, T>(f, dst, src, epi, shared_mode, ni); break;
+      case 3: launch_fdm_brick<3, 4, T>(f, dst, src, epi, shared_mode, ni); break;
+      case 4:
+        if (op->brick_bz == 2)
+          launch_fdm_brick<4, 2, T>(f, dst, src, epi, shared_mode, ni);
+        else
+          launch_fdm_brick<4, 4, T>(f, dst, src, epi, shared_mode, ni);
+        break;
+      case 5: launch_fdm_brick<5, 2, T>(f, dst, src, epi, shared_mode, ni); break;
+      default: throw std::runtime_error("internal: brick path for unsupported degree");
+    }
 }
 
 template <typename T>
@@ -686,23 +742,9 @@ fdm_vmult(dasm_fdm *f, T *dst, const T *src, const dasm_hook *pre, const dasm_ho
   if (pre != nullptr && pre->kind != DASM_HOOK_NONE && pre->kind != DASM_HOOK_ZERO_DST)
     throw std::runtime_error("ASPoissonPreconditioner::vmult: only the zeroing pre-operation is supported");
   DASM_REQUIRE((const void *)dst != (const void *)src, "vmult: dst and src must not alias");
-  if (op->use_brick && f->d_pidx == nullptr && (f->wmode == 0 || f->wmode == 1))
+  if (fdm_uses_brick(f))
     {
-      const Epilogue<T> epi = epilogue_from_hook<T>(post);
-      switch (op->k)
-        {
-          case 1: launch_fdm_brick<1, 4, T>(f, dst, src, epi); break;
-          case 2: launch_fdm_brick<2, 4, T>(f, dst, src, epi); break;
-          case 3: launch_fdm_brick<3, 4, T>(f, dst, src, epi); break;
-          case 4:
-            if (op->brick_bz == 2)
-              launch_fdm_brick<4, 2, T>(f, dst, src, epi);
-            else
-              launch_fdm_brick<4, 4, T>(f, dst, src, epi);
-            break;
-          case 5: launch_fdm_brick<5, 2, T>(f, dst, src, epi); break;
-          default: throw std::runtime_error("internal: brick path for unsupported degree");
-        }
+      fdm_vmult_brick<T>(f, dst, src, post);
       return;
     }
   CUDA_CHECK(cudaMemsetAsync(dst, 0, (size_t)op->n_vec * sizeof(T), ctx->stream));
@@ -1102,10 +1144,8 @@ dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping
                       bd.b[1]       = dy;
                       bd.b[2]       = sz;
                       bd.shared     = 0;
-                      bd.ib[0]      = bx / B[0];
-                      bd.ib[1]      = by / B[1];
-                      bd.ib[2]      = ibz_base + sl;
-                      bd.pad        = 0;
+                      bd.sh_base    = 0;
+                      bd.sh_count   = 0;
                       const int lo_c[3] = {M.lo[0] + bx, M.lo[1] + by, M.lo[2] + bz + z0};
                       const int hi_c[3] = {lo_c[0] + dx - 1, lo_c[1] + dy - 1, lo_c[2] + sz - 1};
                       for (int d = 0; d < 3; ++d)
@@ -1130,9 +1170,11 @@ dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping
         // shared lower face
         {
           std::vector<uint32_t> list;
-          for (const BrickDesc &bd : bricks)
+          op->shared_ranges_ok = true;
+          for (BrickDesc &bd : bricks)
             {
-              const int ncells = bd.b[0] * bd.b[1] * bd.b[2];
+              const size_t list_begin = list.size();
+              const int    ncells = bd.b[0] * bd.b[1] * bd.b[2];
               for (int c = 0; c < ncells; ++c)
                 {
                   const int cc[3] = {c % bd.b[0], (c / bd.b[0]) % bd.b[1], c / (bd.b[0] * bd.b[1])};
@@ -1159,7 +1201,23 @@ dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping
                         list.push_back(g0 + i);
                     }
                 }
+              // contiguous range of the brick's own shared DoFs (holds when the kernel brick is a mesh brick)
+              bd.sh_count = (uint32_t)(list.size() - list_begin);
+              if (bd.sh_count > 0)
+                {
+                  uint32_t mn = 0xFFFFFFFFu, mx = 0;
+                  for (size_t i = list_begin; i < list.size(); ++i)
+                    {
+                      mn = std::min(mn, list[i]);
+                      mx = std::max(mx, list[i]);
+                    }
+                  bd.sh_base = mn;
+                  if (mx - mn + 1 != bd.sh_count)
+                    op->shared_ranges_ok = false;
+                }
             }
+          cudaFree(op->d_bricks);
+          op->d_bricks = dev_upload(bricks, ctx->stream);
           std::sort(list.begin(), list.end());
           list.erase(std::unique(list.begin(), list.end()), list.end());
           op->n_shared      = (long long)list.size();
@@ -2094,7 +2152,7 @@ dasm_cheb_create(dasm_op *op, dasm_fdm *fdm, int degree, double smoothing_range,
   c->optimize        = optimize;
   c->n_ev_it         = eig_cg_n_iterations > 0 ? eig_cg_n_iterations : 40; // templates.h:109
   const size_t bytes = std::max<size_t>(1, (size_t)op->n_vec) * op->esize();
-  for (void **p : {&c->t1, &c->t2, &c->xold, &c->xin, &c->bin})
+  for (void **p : {&c->t1, &c->t1b, &c->t2, &c->xold, &c->xin, &c->bin})
     {
       CUDA_CHECK(cudaMalloc(p, bytes));
       CUDA_CHECK(cudaMemsetAsync(*p, 0, bytes, op->ctx->stream));
@@ -2115,7 +2173,7 @@ dasm_cheb_destroy(dasm_cheb *c)
   if (!c)
     return 0;
   cudaStreamSynchronize(c->op->ctx->stream);
-  for (void *p : {c->t1, c->t2, c->xold, c->xin, c->bin, c->d_inv_diag})
+  for (void *p : {c->t1, c->t1b, c->t2, c->xold, c->xin, c->bin, c->d_inv_diag})
     cudaFree(p);
   delete c;
   DASM_API_END
@@ -2168,6 +2226,13 @@ cheb_run(dasm_cheb *c, T *x_user, const T *b, bool first_is_step)
       sigma   = c->theta / c->delta;
       rho_old = 1. / sigma;
     }
+  // Fully fused sequence (optimize 2 with the FDM brick preconditioner): DoFs on shared brick faces receive
+  // their contributions by red.add directly in the destination, which the PREVIOUS kernel pre-initialised
+  // with the part of the epilogue that does not depend on the operator result; no pass over the shared
+  // DoFs remains except one at the start of the step.
+  const bool direct = op->use_brick && op->shared_ranges_ok && c->fdm != nullptr && fdm_uses_brick(c->fdm) && c->optimize >= 2 &&
+                      !(getenv("DASM_NO_DIRECT") && getenv("DASM_NO_DIRECT")[0] == '1');
+  T *t1buf[2] = {t1, (T *)c->t1b};
   for (int term = 0; term < n_terms; ++term)
     {
       double f1 = 0, f2 = f2_0;
@@ -2187,31 +2252,63 @@ cheb_run(dasm_cheb *c, T *x_user, const T *b, bool first_is_step)
               rho_old          = rho;
             }
         }
-      const T *rhs_for_P;
-      if (term == 0 && !first_is_step)
-        rhs_for_P = b; // x0 = 0: residual is b
-      else
-        {
-          op_vmult<T>(op, t1, cur, nullptr, &res_hook); // t1 = b - A cur
-          rhs_for_P = t1;
-        }
-      // nxt = P^-1 rhs, then nxt = (1+f1) cur - f1 old + f2 nxt
-      dasm_hook upd;
-      if (term == 0 && !first_is_step)
+      const bool  need_A   = !(term == 0 && !first_is_step);
+      const bool  last     = (term == n_terms - 1);
+      T *         t1cur    = t1buf[term & 1];
+      const T *   old_used = (have_old && f1 != 0.) ? old : nullptr;
+      dasm_hook   upd;
+      if (!need_A)
         upd = {DASM_HOOK_SCALE, 0, f2, nullptr, nullptr};
       else
-        upd = {DASM_HOOK_CHEB_UPDATE, f1, f2, cur, (have_old && f1 != 0.) ? old : nullptr};
-      precon_apply<T>(c, nxt, rhs_for_P, &upd);
-      // rotate: old <- cur, cur <- nxt, nxt <- (old buffer)
-      T *tmp = old;
-      old    = cur;
-      cur    = nxt;
-      nxt    = tmp;
-      have_old = (term > 0) || first_is_step;
-      if (nxt == x_user) // never hand the user's buffer out as scratch before the end
+        upd = {DASM_HOOK_CHEB_UPDATE, f1, f2, cur, old_used};
+      if (direct)
         {
-          // old buffer was x_user two rotations ago; fine to reuse: its content is dead
+          // base of the update epilogue on the shared DoFs of nxt: cur + f1 (cur - old)   (0 for the scale epilogue)
+          NextInit<T> ni_upd;
+          ni_upd.out = nxt;
+          ni_upd.v0  = need_A ? cur : nullptr;
+          ni_upd.v1  = old_used;
+          ni_upd.f1  = (T)(need_A ? f1 : 0.);
+          // base of the residual epilogue on the shared DoFs of the next t1 buffer: b
+          NextInit<T> ni_res;
+          ni_res.out = t1buf[(term + 1) & 1];
+          ni_res.v0  = b;
+          ni_res.v1  = nullptr;
+          ni_res.f1  = 0;
+          const T *rhs_for_P = b;
+          if (need_A)
+            {
+              if (term == 0)
+                {
+                  NextInit<T> first = ni_res;
+                  first.out         = t1cur;
+                  init_shared<T>(op, first);
+                }
+              op_vmult_brick<T>(op, t1cur, cur, &res_hook, SHARED_DIRECT, ni_upd); // t1 = b - A cur
+              rhs_for_P = t1cur;
+            }
+          else
+            init_shared<T>(op, ni_upd);
+          fdm_vmult_brick<T>(c->fdm, nxt, rhs_for_P, &upd, SHARED_DIRECT, last ? no_next_init<T>() : ni_res);
         }
+      else
+        {
+          const T *rhs_for_P;
+          if (!need_A)
+            rhs_for_P = b; // x0 = 0: residual is b
+          else
+            {
+              op_vmult<T>(op, t1, cur, nullptr, &res_hook); // t1 = b - A cur
+              rhs_for_P = t1;
+            }
+          precon_apply<T>(c, nxt, rhs_for_P, &upd); // nxt = P^-1 rhs, then nxt = (1+f1) cur - f1 old + f2 nxt
+        }
+      // rotate: old <- cur, cur <- nxt, nxt <- (old buffer)
+      T *tmp   = old;
+      old      = cur;
+      cur      = nxt;
+      nxt      = tmp;
+      have_old = (term > 0) || first_is_step;
     }
   if (cur != x_user)
     {

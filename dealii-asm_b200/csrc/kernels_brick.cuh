@@ -27,8 +27,27 @@ namespace dasm
     uint32_t first_cell; // processing index of the first cell (cells of a brick are consecutive, x fastest)
     uint8_t  b[3];       // cells per direction
     uint8_t  shared;     // bit (2 d + side): the tile face is shared with cells outside the brick
-    uint16_t ib[3];      // position in the lattice of kernel bricks
-    uint16_t pad;
+    uint32_t sh_base;    // first DoF of the contiguous range of shared-face DoFs this brick owns
+    uint32_t sh_count;   // (only meaningful when the kernel brick is a whole mesh brick)
+  };
+
+  // how contributions to DoFs on shared brick faces are combined
+  enum
+  {
+    SHARED_ACC    = 0, // red.add y into the zero-invariant accumulator, finish_shared_kernel runs the epilogue
+    SHARED_DIRECT = 1  // dst was pre-initialised with the epilogue's base value; red.add (alpha y) into dst
+  };
+
+  // pre-initialisation of the NEXT kernel's destination on the shared DoFs owned by a brick (fused into the
+  // current kernel): out = v0 + f1 (v0 - v1)   (v0 / v1 == nullptr: 0), i.e. the part of the next epilogue
+  // that does not depend on its operator result
+  template <typename T>
+  struct NextInit
+  {
+    T *      out;
+    const T *v0;
+    const T *v1;
+    T        f1;
   };
 
   enum
@@ -358,14 +377,33 @@ namespace dasm
       }
   }
 
+  // fused pre-initialisation of the next kernel's destination on the brick's own shared DoFs
+  template <int k, int BZ, typename T>
+  __device__ __forceinline__ void
+  brick_next_init(const BrickDesc &bd, const NextInit<T> &ni)
+  {
+    using G = BrickGeom<k, BZ>;
+    if (ni.out == nullptr)
+      return;
+    for (uint32_t i = threadIdx.x; i < bd.sh_count; i += G::NT)
+      {
+        const uint32_t g = bd.sh_base + i;
+        const T        a = (ni.v0 != nullptr) ? ni.v0[g] : T(0);
+        const T        b = (ni.v1 != nullptr && ni.f1 != T(0)) ? ni.v1[g] : T(0);
+        ni.out[g]        = a + ni.f1 * (a - b);
+      }
+  }
+
   // reduction of the cell results (slots) per tile point in a fixed order (deterministic, no shared-memory
   // atomics), fused epilogue at private points (plain stores), red.global.add into the zero-invariant
   // accumulator at points on shared brick faces (completed by finish_shared_kernel)
   template <int k, int BZ, typename T>
   __device__ __forceinline__ void
   brick_reduce_store(const BrickDesc &bd, const T *slots, const T *ops0, const T *ops1, const uint32_t *gidx,
-                     T *__restrict__ dst, T *__restrict__ acc, const Epilogue<T> &epi)
+                     T *__restrict__ dst, T *__restrict__ acc, const Epilogue<T> &epi, const int shared_mode)
   {
+    // affine form of the epilogue: dst = base + alpha * y
+    const T alpha = (epi.kind == EPI_RESIDUAL) ? T(-1) : ((epi.kind == EPI_CHEB || epi.kind == EPI_SCALE) ? epi.f2 : T(1));
     using G             = BrickGeom<k, BZ>;
     constexpr int n     = k + 1;
     constexpr int NPENC = G::TX * G::TY;
@@ -426,7 +464,12 @@ namespace dasm
                       }
                     const bool sh = (shxy | ((pz == 0) ? (bd.shared & 16u) : 0u) | ((pz == ez - 1) ? (bd.shared & 32u) : 0u)) != 0;
                     if (sh)
-                      atomic_add(acc + g, y);
+                      {
+                        if (shared_mode == SHARED_DIRECT)
+                          atomic_add(dst + g, alpha * y);
+                        else
+                          atomic_add(acc + g, y);
+                      }
                     else
                       dst[g] = epilogue_compute(epi, y, need0 ? ops0[p] : T(0), need1 ? ops1[p] : T(0));
                   }
@@ -448,7 +491,9 @@ namespace dasm
                        const int n_bricks,
                        const T *__restrict__ geom,
                        const CartesianCoef cart,
-                       const int n_ops)
+                       const int n_ops,
+                       const int shared_mode,
+                       const NextInit<T> ni)
   {
     using G         = BrickGeom<k, BZ>;
     constexpr int n = k + 1;
@@ -483,6 +528,7 @@ namespace dasm
         if (bi + (int)gridDim.x < n_bricks)
           brick_stage_cidx_async<k, BZ>(bricks[bi + gridDim.x], cidx, s_cidx + (buf ^ 1) * (G::NCELLS * 27));
         cp_async_commit();
+        brick_next_init<k, BZ, T>(bd, ni);
         cp_async_wait<2>();
         __syncthreads();
 
@@ -688,7 +734,7 @@ namespace dasm
           }
         cp_async_wait<1>(); // epilogue operands have landed
         __syncthreads();
-        brick_reduce_store<k, BZ, T>(bd, slots, ops0, ops1, gidx, dst, acc, epi);
+        brick_reduce_store<k, BZ, T>(bd, slots, ops0, ops1, gidx, dst, acc, epi, shared_mode);
         cp_async_wait<0>(); // indices of the next brick
         __syncthreads();
       }
@@ -710,7 +756,9 @@ namespace dasm
                    const T *__restrict__ cw, // [cell][27] or nullptr
                    const int w_pre,
                    const int w_post,
-                   const int n_ops)
+                   const int n_ops,
+                   const int shared_mode,
+                   const NextInit<T> ni)
   {
     using G          = BrickGeom<k, BZ>;
     constexpr int n  = k + 1;
@@ -744,6 +792,7 @@ namespace dasm
         if (bi + (int)gridDim.x < n_bricks)
           brick_stage_cidx_async<k, BZ>(bricks[bi + gridDim.x], cidx, s_cidx + (buf ^ 1) * (G::NCELLS * 27));
         cp_async_commit();
+        brick_next_init<k, BZ, T>(bd, ni);
         cp_async_wait<2>();
         __syncthreads();
 
@@ -878,7 +927,7 @@ namespace dasm
           }
         cp_async_wait<1>();
         __syncthreads();
-        brick_reduce_store<k, BZ, T>(bd, slots, ops0, ops1, gidx, dst, acc, epi);
+        brick_reduce_store<k, BZ, T>(bd, slots, ops0, ops1, gidx, dst, acc, epi, shared_mode);
         cp_async_wait<0>();
         __syncthreads();
       }
@@ -899,6 +948,21 @@ namespace dasm
         epilogue_load(epi, g, a, b);
         acc[g] = T(0);
         dst[g] = epilogue_compute(epi, y, a, b);
+      }
+  }
+
+  // stand-alone pre-initialisation of a destination on all shared DoFs (first kernel of a fused sequence)
+  template <typename T>
+  __global__ void
+  init_shared_kernel(const NextInit<T> ni, const uint32_t *__restrict__ list, const long long n)
+  {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+      {
+        const uint32_t g = list[i];
+        const T        a = (ni.v0 != nullptr) ? ni.v0[g] : T(0);
+        const T        b = (ni.v1 != nullptr && ni.f1 != T(0)) ? ni.v1[g] : T(0);
+        ni.out[g]        = a + ni.f1 * (a - b);
       }
   }
 
