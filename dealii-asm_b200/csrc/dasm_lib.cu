@@ -491,6 +491,37 @@ epilogue_from_hook(const dasm_hook *post)
   return e;
 }
 
+// multi-rank: ghost values of the source are updated before a brick kernel (update_ghost_values,
+// matrix_free_internal.h:321-324); contributions to ghost DoFs are sent to and added at their owners after it
+// (compress(add), 350-352).  In SHARED_DIRECT mode the owners hold base + local contributions in dst, so the
+// ghost part of dst starts from zero; in SHARED_ACC mode the accumulator is exchanged and its ghost part
+// re-zeroed (zero-invariant).
+template <typename T>
+static void
+brick_pre_exchange(dasm_op *op, T *dst, const T *src, const int shared_mode)
+{
+  if (!op->exchange.active())
+    return;
+  KernelTimer timer(op->ctx, KC_EXCHANGE);
+  op->exchange.run<T>(const_cast<T *>(src), false);
+  if (shared_mode == SHARED_DIRECT && op->n_ghost > 0)
+    CUDA_CHECK(cudaMemsetAsync(dst + op->n_owned, 0, (size_t)op->n_ghost * sizeof(T), op->ctx->stream));
+}
+
+template <typename T>
+static void
+brick_post_exchange(dasm_op *op, T *dst, const int shared_mode, const bool needs_compression)
+{
+  if (!op->exchange.active())
+    return;
+  KernelTimer timer(op->ctx, KC_EXCHANGE);
+  T *         vec = (shared_mode == SHARED_DIRECT) ? dst : (T *)op->d_acc;
+  if (needs_compression)
+    op->exchange.run<T>(vec, true);
+  if (shared_mode == SHARED_ACC && op->n_ghost > 0)
+    CUDA_CHECK(cudaMemsetAsync((T *)op->d_acc + op->n_owned, 0, (size_t)op->n_ghost * sizeof(T), op->ctx->stream));
+}
+
 template <int K, int BZ, typename T, typename Kern>
 static int
 brick_grid(dasm_op *op, Kern kern, size_t smem)
@@ -541,6 +572,7 @@ launch_laplace_brick(dasm_op *op, T *dst, const T *src, const Epilogue<T> &epi, 
   dasm_ctx *   ctx   = op->ctx;
   const int    n_ops = epilogue_n_operands(epi);
   const size_t smem  = BrickGeom<K, BZ>::template smem_bytes<T>(n_ops);
+  brick_pre_exchange<T>(op, dst, src, shared_mode);
   {
     KernelTimer timer(ctx, KC_LAPLACE);
     if (op->geom_mode == 0)
@@ -560,6 +592,7 @@ launch_laplace_brick(dasm_op *op, T *dst, const T *src, const Epilogue<T> &epi, 
     ctx->launches++;
   }
   CUDA_CHECK(cudaGetLastError());
+  brick_post_exchange<T>(op, dst, shared_mode, true);
   brick_finish<K, BZ, T>(op, dst, copy_constrained ? src : nullptr, epi, shared_mode);
   CUDA_CHECK(cudaGetLastError());
 }
@@ -690,6 +723,7 @@ launch_fdm_brick(dasm_fdm *f, T *dst, const T *src, const Epilogue<T> &epi, cons
   dasm_ctx *   ctx   = op->ctx;
   const int    n_ops = epilogue_n_operands(epi);
   const size_t smem  = BrickGeom<K, BZ>::template smem_bytes<T>(n_ops);
+  brick_pre_exchange<T>(op, dst, src, shared_mode);
   {
     KernelTimer timer(ctx, KC_FDM);
     auto        kern = fdm_brick_kernel<K, T, BZ>;
@@ -700,6 +734,7 @@ launch_fdm_brick(dasm_fdm *f, T *dst, const T *src, const Epilogue<T> &epi, cons
     ctx->launches++;
   }
   CUDA_CHECK(cudaGetLastError());
+  brick_post_exchange<T>(op, dst, shared_mode, f->weight_type != DASM_WEIGHT_RAS);
   brick_finish<K, BZ, T>(op, dst, (const T *)nullptr, epi, shared_mode);
   CUDA_CHECK(cudaGetLastError());
 }
@@ -1115,7 +1150,7 @@ dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping
   // tuned brick path: degrees 1..5, one rank (the multi-rank path uses the generic kernels for now)
   {
     const char *force = getenv("DASM_FORCE_GENERIC");
-    op->use_brick     = (degree <= 5) && !(force && force[0] == '1') && M.n_ranks() == 1;
+    op->use_brick     = (degree <= 5) && !(force && force[0] == '1');
     if (op->use_brick)
       {
         op->brick_bz = (degree <= 4) ? 4 : 2;

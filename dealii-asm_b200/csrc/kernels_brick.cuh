@@ -115,7 +115,8 @@ namespace dasm
     static constexpr int NCELLS = BX * BY * BZ;
     static constexpr int NT     = NCELLS * n;   // threads per block
     static constexpr int MINB   = (NT <= 160) ? 2 : 1; // resident blocks per SM the register budget is set for
-    static constexpr int CS     = n * n * n;    // slot stride per cell
+    static constexpr int CS     = (n * n * n) | 1; // slot stride per cell, odd: with cell-major lanes (lane = cell) every
+                                                   // plane access of a half-warp hits 16 different banks
     // registers per thread with one resident block per SM (64 K registers, allocation granularity 8)
     // (registers are allocated per warp in units of 512)
     static constexpr int NWARPS = (NT + 31) / 32;
@@ -131,6 +132,9 @@ namespace dasm
   };
 
   // ---- register-plane contractions --------------------------------------------------------------
+  // All loops are written input-major (for i: for o: r[o] += M[o][i] v[i]) so that n independent FMA
+  // chains are interleaved in program order (the FP64 pipe needs >= 4 independent FMAs in flight per
+  // warp at 10 warps/SM, see tools/fp64_peak.cu).
   // v[a][b]: apply M along b (fast index): v[a][:] = M v[a][:]   (TRANS: M^T)
   template <int n, typename T, bool TRANS>
   __device__ __forceinline__ void
@@ -142,13 +146,12 @@ namespace dasm
         T r[n];
 #pragma unroll
         for (int o = 0; o < n; ++o)
-          {
-            T s = (TRANS ? M[o] : M[o * n]) * v[a][0];
+          r[o] = (TRANS ? M[o] : M[o * n]) * v[a][0];
 #pragma unroll
-            for (int i = 1; i < n; ++i)
-              s += (TRANS ? M[i * n + o] : M[o * n + i]) * v[a][i];
-            r[o] = s;
-          }
+        for (int i = 1; i < n; ++i)
+#pragma unroll
+          for (int o = 0; o < n; ++o)
+            r[o] += (TRANS ? M[i * n + o] : M[o * n + i]) * v[a][i];
 #pragma unroll
         for (int o = 0; o < n; ++o)
           v[a][o] = r[o];
@@ -166,13 +169,12 @@ namespace dasm
         T r[n];
 #pragma unroll
         for (int o = 0; o < n; ++o)
-          {
-            T s = (TRANS ? M[o] : M[o * n]) * v[0][b];
+          r[o] = (TRANS ? M[o] : M[o * n]) * v[0][b];
 #pragma unroll
-            for (int i = 1; i < n; ++i)
-              s += (TRANS ? M[i * n + o] : M[o * n + i]) * v[i][b];
-            r[o] = s;
-          }
+        for (int i = 1; i < n; ++i)
+#pragma unroll
+          for (int o = 0; o < n; ++o)
+            r[o] += (TRANS ? M[i * n + o] : M[o * n + i]) * v[i][b];
 #pragma unroll
         for (int o = 0; o < n; ++o)
           v[o][b] = r[o];
@@ -190,22 +192,20 @@ namespace dasm
         T f[n];
 #pragma unroll
         for (int q = 0; q < n; ++q)
-          {
-            T s = D[q * n] * v[a][0];
+          f[q] = D[q * n] * v[a][0];
 #pragma unroll
-            for (int i = 1; i < n; ++i)
-              s += D[q * n + i] * v[a][i];
-            f[q] = s * (wfast[q] * wslow[a]);
-          }
+        for (int i = 1; i < n; ++i)
 #pragma unroll
-        for (int o = 0; o < n; ++o)
-          {
-            T s = r[a][o];
+          for (int q = 0; q < n; ++q)
+            f[q] += D[q * n + i] * v[a][i];
 #pragma unroll
-            for (int q = 0; q < n; ++q)
-              s += D[q * n + o] * f[q];
-            r[a][o] = s;
-          }
+        for (int q = 0; q < n; ++q)
+          f[q] *= (wfast[q] * wslow[a]);
+#pragma unroll
+        for (int q = 0; q < n; ++q)
+#pragma unroll
+          for (int o = 0; o < n; ++o)
+            r[a][o] += D[q * n + o] * f[q];
       }
   }
 
@@ -220,22 +220,20 @@ namespace dasm
         T f[n];
 #pragma unroll
         for (int q = 0; q < n; ++q)
-          {
-            T s = D[q * n] * v[0][b];
+          f[q] = D[q * n] * v[0][b];
 #pragma unroll
-            for (int i = 1; i < n; ++i)
-              s += D[q * n + i] * v[i][b];
-            f[q] = s * (wfast[b] * wslow[q]);
-          }
+        for (int i = 1; i < n; ++i)
 #pragma unroll
-        for (int o = 0; o < n; ++o)
-          {
-            T s = r[o][b];
+          for (int q = 0; q < n; ++q)
+            f[q] += D[q * n + i] * v[i][b];
 #pragma unroll
-            for (int q = 0; q < n; ++q)
-              s += D[q * n + o] * f[q];
-            r[o][b] = s;
-          }
+        for (int q = 0; q < n; ++q)
+          f[q] *= (wfast[b] * wslow[q]);
+#pragma unroll
+        for (int q = 0; q < n; ++q)
+#pragma unroll
+          for (int o = 0; o < n; ++o)
+            r[o][b] += D[q * n + o] * f[q];
       }
   }
 
@@ -506,8 +504,8 @@ namespace dasm
     uint32_t *s_cidx = gidx + G::NPTS; // two buffers of NCELLS * 27
 
     const auto &B = BasisOf<T>::template get<k>();
-    const int   c = threadIdx.x / n; // cell in brick
-    const int   t = threadIdx.x % n; // plane index
+    const int   c = threadIdx.x % G::NCELLS; // cell in brick (lane-major: conflict-free slot access)
+    const int   t = threadIdx.x / G::NCELLS; // plane index (warp-uniform)
 
     if (blockIdx.x < n_bricks)
       brick_stage_cidx_async<k, BZ>(bricks[blockIdx.x], cidx, s_cidx);
@@ -658,7 +656,8 @@ namespace dasm
             __syncthreads();
             if (act) // plane y = t: quadrature-point operation
               {
-                const T *Gc = geom + (size_t)(bd.first_cell + c) * 6 * G::CS;
+                constexpr int n3 = n * n * n;
+                const T *     Gc = geom + (size_t)(bd.first_cell + c) * 6 * n3;
 #pragma unroll
                 for (int z = 0; z < n; ++z)
 #pragma unroll
@@ -667,8 +666,8 @@ namespace dasm
                       const int q   = (z * n + t) * n + x;
                       const T   gyv = S[q];
                       const T   a = gx[z][x], cc = gz[z][x];
-                      const T   gxx = Gc[q], gxy = Gc[G::CS + q], gxz = Gc[2 * G::CS + q], gyy = Gc[3 * G::CS + q],
-                              gyz = Gc[4 * G::CS + q], gzz = Gc[5 * G::CS + q];
+                      const T   gxx = Gc[q], gxy = Gc[n3 + q], gxz = Gc[2 * n3 + q], gyy = Gc[3 * n3 + q], gyz = Gc[4 * n3 + q],
+                              gzz = Gc[5 * n3 + q];
                       gx[z][x] = gxx * a + gxy * gyv + gxz * cc;
                       S[q]     = gxy * a + gyy * gyv + gyz * cc;
                       gz[z][x] = gxz * a + gyz * gyv + gzz * cc;
@@ -771,8 +770,8 @@ namespace dasm
     uint32_t *gidx   = reinterpret_cast<uint32_t *>(slots + G::NCELLS * G::CS);
     uint32_t *s_cidx = gidx + G::NPTS; // two buffers of NCELLS * 27
 
-    const int c = threadIdx.x / n;
-    const int t = threadIdx.x % n;
+    const int c = threadIdx.x % G::NCELLS; // cell in brick (lane-major: conflict-free slot access)
+    const int t = threadIdx.x / G::NCELLS; // plane index (warp-uniform)
 
     if (blockIdx.x < n_bricks)
       brick_stage_cidx_async<k, BZ>(bricks[blockIdx.x], cidx, s_cidx);

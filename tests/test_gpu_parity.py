@@ -62,7 +62,7 @@ def test_vmult_degrees_periodic(pkg, ctx, k, number):
 
 
 @pytest.mark.parametrize("name", ["dirichlet", "mixed_aniso", "sine", "kershaw"])
-@pytest.mark.parametrize("k", [2, 4])
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 6])
 def test_vmult_meshes(pkg, ctx, name, k):
     assert run_vmult(pkg, ctx, MESHES[name], k, "double") < TOL["double"]
 
