@@ -19,6 +19,10 @@ import time
 
 import numpy as np
 
+# exactly one JSON line on stdout: keep NCCL's version banner off it
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -299,7 +303,7 @@ def run_ours(args):
     dom_ms, dom_n = ktimes[dom]
     idx_bytes = 27 * 4
     d_c = k ** 3
-    fused = bool(os.environ.get("DASM_FUSED", "1") != "0") and hasattr(pkg, "FUSED_KERNELS") and pkg.FUSED_KERNELS
+    fused = getattr(pkg, "FUSED_KERNELS", False) and os.environ.get("DASM_FORCE_GENERIC", "0") != "1" and k <= 5
     if fused:
         # A-sweep: read x, read b, write t1 (3 S) + indices; P-sweep: read t1, x, x_old, write x+ (4 S) + indices + 27 weights + 3 ids
         per_dof = [3 * S + idx_bytes / d_c, 4 * S + (idx_bytes + 27 * S + 12) / d_c][dom]

@@ -21,6 +21,9 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdasm.so")
 
+# the Chebyshev step runs as two fused brick kernels per term (vector updates in the kernel epilogues)
+FUSED_KERNELS = True
+
 F64, F32 = 0, 1
 WEIGHT = {"none": 0, "pre": 1, "post": 2, "ras": 3, "symm": 4}
 WSEQ = {"global": 0, "local": 1, "dg": 2, "DG": 2, "compressed": 3}
