@@ -283,6 +283,8 @@ struct dasm_op
   uint32_t *        d_shared_list = nullptr; // owned DoFs on brick faces shared with other bricks
   long long         n_shared  = 0;
   bool              shared_ranges_ok = false; // every brick's own shared DoFs are one contiguous range
+  BrickMaps         maps = {nullptr, nullptr, nullptr, nullptr, 0}; // per-variant tile maps (coalesced gather / store)
+  uint32_t *        d_map_own = nullptr, *d_map_foreign = nullptr, *d_map_nforeign = nullptr, *d_map_flags = nullptr;
   int               n_sm      = 148;
 
   dasm_op(int degree)
@@ -571,8 +573,9 @@ launch_laplace_brick(dasm_op *op, T *dst, const T *src, const Epilogue<T> &epi, 
 {
   dasm_ctx *   ctx   = op->ctx;
   const int    n_ops = epilogue_n_operands(epi);
-  const size_t smem  = BrickGeom<K, BZ>::template smem_bytes<T>(n_ops);
+  const size_t smem  = BrickGeom<K, BZ>::template smem_bytes<T>(n_ops, op->maps.own != nullptr);
   brick_pre_exchange<T>(op, dst, src, shared_mode);
+  static const int dbg = getenv("DASM_DEBUG_SKIP") ? atoi(getenv("DASM_DEBUG_SKIP")) : 0; // timing experiments only
   {
     KernelTimer timer(ctx, KC_LAPLACE);
     if (op->geom_mode == 0)
@@ -580,14 +583,14 @@ launch_laplace_brick(dasm_op *op, T *dst, const T *src, const Epilogue<T> &epi, 
         auto      kern = laplace_brick_kernel<K, T, BZ, 0>;
         const int grid = brick_grid<K, BZ, T>(op, kern, smem);
         kern<<<grid, BrickGeom<K, BZ>::NT, smem, ctx->stream>>>(src, dst, (T *)op->d_acc, epi, op->d_cidx, op->d_bricks, op->n_bricks,
-                                                                 (const T *)nullptr, op->cart, n_ops, shared_mode, ni);
+                                                                 (const T *)nullptr, op->cart, n_ops, shared_mode, ni, op->maps, dbg);
       }
     else
       {
         auto      kern = laplace_brick_kernel<K, T, BZ, 1>;
         const int grid = brick_grid<K, BZ, T>(op, kern, smem);
         kern<<<grid, BrickGeom<K, BZ>::NT, smem, ctx->stream>>>(src, dst, (T *)op->d_acc, epi, op->d_cidx, op->d_bricks, op->n_bricks,
-                                                                 (const T *)op->d_geom, op->cart, n_ops, shared_mode, ni);
+                                                                 (const T *)op->d_geom, op->cart, n_ops, shared_mode, ni, op->maps, dbg);
       }
     ctx->launches++;
   }
@@ -722,7 +725,7 @@ launch_fdm_brick(dasm_fdm *f, T *dst, const T *src, const Epilogue<T> &epi, cons
   dasm_op *    op    = f->op;
   dasm_ctx *   ctx   = op->ctx;
   const int    n_ops = epilogue_n_operands(epi);
-  const size_t smem  = BrickGeom<K, BZ>::template smem_bytes<T>(n_ops);
+  const size_t smem  = BrickGeom<K, BZ>::template smem_bytes<T>(n_ops, op->maps.own != nullptr);
   brick_pre_exchange<T>(op, dst, src, shared_mode);
   {
     KernelTimer timer(ctx, KC_FDM);
@@ -730,7 +733,7 @@ launch_fdm_brick(dasm_fdm *f, T *dst, const T *src, const Epilogue<T> &epi, cons
     const int   grid = brick_grid<K, BZ, T>(op, kern, smem);
     kern<<<grid, BrickGeom<K, BZ>::NT, smem, ctx->stream>>>(src, dst, (T *)op->d_acc, epi, op->d_cidx, op->d_bricks, op->n_bricks, f->d_inst,
                                                              (const T *)f->d_S, (const T *)f->d_lam, (const T *)(f->wmode == 1 ? f->d_cw : nullptr),
-                                                             (int)f->w_pre, (int)f->w_post, n_ops, shared_mode, ni);
+                                                             (int)f->w_pre, (int)f->w_post, n_ops, shared_mode, ni, op->maps);
     ctx->launches++;
   }
   CUDA_CHECK(cudaGetLastError());
@@ -1181,6 +1184,9 @@ dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping
                       bd.shared     = 0;
                       bd.sh_base    = 0;
                       bd.sh_count   = 0;
+                      bd.base       = 0;
+                      bd.npriv      = 0;
+                      bd.variant    = 0xFFFFu;
                       const int lo_c[3] = {M.lo[0] + bx, M.lo[1] + by, M.lo[2] + bz + z0};
                       const int hi_c[3] = {lo_c[0] + dx - 1, lo_c[1] + dy - 1, lo_c[2] + sz - 1};
                       for (int d = 0; d < 3; ++d)
@@ -1258,6 +1264,172 @@ dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping
           op->n_shared      = (long long)list.size();
           op->d_shared_list = dev_upload(list, ctx->stream);
         }
+        // ---- per-variant tile maps for the coalesced gather / store (kernel brick == mesh brick only)
+        op->maps.own = nullptr;
+        if (op->brick_bz == 4 && !(getenv("DASM_NO_LINEAR") && getenv("DASM_NO_LINEAR")[0] == '1'))
+          {
+            const int k = degree, n = k + 1, TX = 4 * k + 1, TY = 4 * k + 1, TZ = 4 * k + 1, NPTS = TX * TY * TZ;
+            const int CS = (n * n * n) | 1;
+            std::map<uint32_t, uint16_t>       variant_of; // signature -> variant
+            std::vector<std::vector<uint32_t>> v_own, v_foreign;
+            std::vector<uint32_t>              v_flags;
+            bool                               ok = true;
+            auto plain_gidx = [&](const BrickDesc &bd, const std::vector<uint32_t> &tab, int px, int py, int pz) {
+              const int cx = std::min(px / k, bd.b[0] - 1), cy = std::min(py / k, bd.b[1] - 1), cz = std::min(pz / k, bd.b[2] - 1);
+              const int lx = px - cx * k, ly = py - cy * k, lz = pz - cz * k;
+              const int ex = lx == 0 ? 0 : (lx == k ? 2 : 1), ey = ly == 0 ? 0 : (ly == k ? 2 : 1), ez = lz == 0 ? 0 : (lz == k ? 2 : 1);
+              const uint32_t st = tab[(size_t)(bd.first_cell + (cz * bd.b[1] + cy) * bd.b[0] + cx) * 27 + ex + 3 * ey + 9 * ez];
+              if (st == INVALID_INDEX)
+                return INVALID_INDEX;
+              const int sx = ex == 1 ? k - 1 : 1, sy = ey == 1 ? k - 1 : 1;
+              return st + (ex == 1 ? lx - 1 : 0) + sx * ((ey == 1 ? ly - 1 : 0) + sy * (ez == 1 ? lz - 1 : 0));
+            };
+            for (BrickDesc &bd : bricks)
+              {
+                const uint32_t sig = bd.b[0] | (bd.b[1] << 4) | (bd.b[2] << 8) | ((uint32_t)bd.shared << 12);
+                const int      e3[3] = {bd.b[0] * k + 1, bd.b[1] * k + 1, bd.b[2] * k + 1};
+                // range of owned DoFs from the geometric ownership rule (plain indices: constrained DoFs included)
+                uint32_t mn = 0xFFFFFFFFu, mx = 0, cnt = 0, smn = 0xFFFFFFFFu, smx = 0, scnt = 0;
+                auto     owned_point = [&](const int pp[3], bool &on_shared_lo) {
+                  on_shared_lo = false;
+                  for (int d = 0; d < 3; ++d)
+                    {
+                      if (pp[d] == e3[d] - 1 && ((bd.shared >> (2 * d + 1)) & 1u))
+                        return false; // upper face shared: owned by the neighbour brick
+                      if (pp[d] == 0 && ((bd.shared >> (2 * d)) & 1u))
+                        on_shared_lo = true;
+                    }
+                  return true;
+                };
+                const bool first_of_sig = variant_of.find(sig) == variant_of.end();
+                std::vector<uint32_t> own, foreign;
+                uint32_t              flags = 0;
+                // pass 1: ranges
+                for (int pz = 0; pz < e3[2]; ++pz)
+                  for (int py = 0; py < e3[1]; ++py)
+                    for (int px = 0; px < e3[0]; ++px)
+                      {
+                        const int pp[3] = {px, py, pz};
+                        bool      shlo;
+                        if (!owned_point(pp, shlo))
+                          continue;
+                        const uint32_t g = plain_gidx(bd, op->nb.cidx_plain, px, py, pz);
+                        mn               = std::min(mn, g);
+                        mx               = std::max(mx, g);
+                        ++cnt;
+                        if (shlo)
+                          {
+                            smn = std::min(smn, g);
+                            smx = std::max(smx, g);
+                            ++scnt;
+                          }
+                      }
+                if (cnt == 0 || mx - mn + 1 != cnt || (scnt > 0 && (smx - smn + 1 != scnt || smx != mx)) || cnt > 0xFFFFu)
+                  {
+                    ok = false;
+                    break;
+                  }
+                bd.base     = mn;
+                bd.npriv    = (uint16_t)(cnt - scnt);
+                bd.sh_base  = scnt > 0 ? smn : mn + cnt;
+                bd.sh_count = scnt;
+                // pass 2: maps (for the first brick of a signature; verified on every 97th brick)
+                static unsigned verify_counter = 0;
+                const bool      verify         = !first_of_sig && ((++verify_counter) % 97 == 0);
+                if (first_of_sig || verify)
+                  {
+                    own.assign(cnt, 0xFFFFFFFFu);
+                    for (int pz = 0; pz < e3[2]; ++pz)
+                      for (int py = 0; py < e3[1]; ++py)
+                        for (int px = 0; px < e3[0]; ++px)
+                          {
+                            const int pp[3] = {px, py, pz};
+                            // primary contribution and mask of second contributions
+                            int      cc[3], ll[3];
+                            unsigned mask = 0;
+                            for (int d = 0; d < 3; ++d)
+                              {
+                                const int ch = pp[d] / k, l = pp[d] - ch * k;
+                                if (ch < bd.b[d])
+                                  {
+                                    cc[d] = ch;
+                                    ll[d] = l;
+                                    if (l == 0 && ch > 0)
+                                      mask |= 1u << d;
+                                  }
+                                else
+                                  {
+                                    cc[d] = ch - 1;
+                                    ll[d] = k;
+                                  }
+                              }
+                            const uint32_t o     = (uint32_t)(((cc[2] * bd.b[1] + cc[1]) * bd.b[0] + cc[0]) * CS + (ll[2] * n + ll[1]) * n + ll[0]);
+                            const uint32_t plin  = (uint32_t)((pz * TY + py) * TX + px);
+                            const uint32_t entry = plin | (o << 13) | (mask << 29);
+                            const uint32_t gv    = plain_gidx(bd, op->nb.cidx, px, py, pz);
+                            bool           shlo;
+                            if (owned_point(pp, shlo))
+                              {
+                                if (gv != INVALID_INDEX)
+                                  own[gv - mn] = entry;
+                                else
+                                  flags |= 1u;
+                              }
+                            else
+                              {
+                                foreign.push_back(entry);
+                                if (gv == INVALID_INDEX)
+                                  flags |= 1u;
+                              }
+                          }
+                    if (first_of_sig)
+                      {
+                        variant_of[sig] = (uint16_t)v_own.size();
+                        v_own.push_back(own);
+                        v_foreign.push_back(foreign);
+                        v_flags.push_back(flags);
+                      }
+                    else
+                      {
+                        const uint16_t v = variant_of[sig];
+                        if (own != v_own[v] || foreign != v_foreign[v] || flags != v_flags[v])
+                          {
+                            ok = false;
+                            break;
+                          }
+                      }
+                  }
+                bd.variant = variant_of[sig];
+              }
+            if (ok && !v_own.empty())
+              {
+                const int             nv = (int)v_own.size();
+                std::vector<uint32_t> h_own((size_t)nv * NPTS, 0xFFFFFFFFu), h_for((size_t)nv * NPTS, 0), h_nf(nv), h_fl(nv);
+                for (int v = 0; v < nv; ++v)
+                  {
+                    std::copy(v_own[v].begin(), v_own[v].end(), h_own.begin() + (size_t)v * NPTS);
+                    std::copy(v_foreign[v].begin(), v_foreign[v].end(), h_for.begin() + (size_t)v * NPTS);
+                    h_nf[v] = (uint32_t)v_foreign[v].size();
+                    h_fl[v] = v_flags[v];
+                  }
+                op->d_map_own        = dev_upload(h_own, ctx->stream);
+                op->d_map_foreign    = dev_upload(h_for, ctx->stream);
+                op->d_map_nforeign   = dev_upload(h_nf, ctx->stream);
+                op->d_map_flags      = dev_upload(h_fl, ctx->stream);
+                op->maps.own         = op->d_map_own;
+                op->maps.foreign     = op->d_map_foreign;
+                op->maps.n_foreign   = op->d_map_nforeign;
+                op->maps.flags       = op->d_map_flags;
+                op->maps.stride      = NPTS;
+                op->shared_ranges_ok = true;
+                cudaFree(op->d_bricks);
+                op->d_bricks = dev_upload(bricks, ctx->stream);
+              }
+            else
+              for (BrickDesc &bd : bricks)
+                bd.variant = 0xFFFFu;
+            (void)TZ;
+          }
         CUDA_CHECK(cudaMalloc(&op->d_acc, std::max<size_t>(1, (size_t)op->n_vec) * op->esize()));
         CUDA_CHECK(cudaMemset(op->d_acc, 0, std::max<size_t>(1, (size_t)op->n_vec) * op->esize()));
         cudaDeviceProp prop;
@@ -1282,6 +1454,10 @@ dasm_op_destroy(dasm_op *op)
   cudaFree(op->d_bricks);
   cudaFree(op->d_acc);
   cudaFree(op->d_shared_list);
+  cudaFree(op->d_map_own);
+  cudaFree(op->d_map_foreign);
+  cudaFree(op->d_map_nforeign);
+  cudaFree(op->d_map_flags);
   op->exchange.destroy();
   for (void *p : op->scratch)
     cudaFree(p);

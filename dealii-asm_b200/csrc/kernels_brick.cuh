@@ -29,6 +29,22 @@ namespace dasm
     uint8_t  shared;     // bit (2 d + side): the tile face is shared with cells outside the brick
     uint32_t sh_base;    // first DoF of the contiguous range of shared-face DoFs this brick owns
     uint32_t sh_count;   // (only meaningful when the kernel brick is a whole mesh brick)
+    uint32_t base;       // first DoF owned by the brick: [base, base + npriv) private, then the shared range
+    uint16_t npriv;      // number of private DoFs
+    uint16_t variant;    // index of the brick's tile-map variant (BrickMaps), 0xFFFF: none
+  };
+
+  // Per-variant maps between the brick's contiguous range of owned DoFs and its tile (bricks of equal shape,
+  // boundary flags and constraints share a variant).  Entry: bits 0-12 tile point, 13-28 slot offset of the
+  // primary cell contribution, 29-31 mask of the directions with a second contribution (lower neighbour
+  // cell inside the brick).  own[i] describes DoF base + i; foreign[j] the tile points owned by other bricks.
+  struct BrickMaps
+  {
+    const uint32_t *own;       // [variant][stride]
+    const uint32_t *foreign;   // [variant][stride]
+    const uint32_t *n_foreign; // [variant]
+    const uint32_t *flags;     // [variant] bit 0: the tile has unreferenced (constrained) points -> zero it first
+    int             stride;
   };
 
   // how contributions to DoFs on shared brick faces are combined
@@ -121,13 +137,16 @@ namespace dasm
     // (registers are allocated per warp in units of 512)
     static constexpr int NWARPS = (NT + 31) / 32;
     static constexpr int MAXREG = ((65536 / NWARPS / 512) * 512 / 32) >= 255 ? 255 : ((65536 / NWARPS / 512) * 512 / 32);
-    // layout: tile | operand tiles (n_ops) | slots | gidx | cidx[2]
+    static constexpr int NFOREIGN = NPTS - (BX * k) * (BY * k) * (BZ * k); // tile points a brick can not own
+    // layout: tile | operand tiles (n_ops) | slots | gidx | cidx[2] | (lin: own map | foreign map)
+    // gidx holds NPTS entries (tile-ordered access) or NFOREIGN entries (linear access through the maps)
     template <typename T>
     static constexpr size_t
-    smem_bytes(int n_ops)
+    smem_bytes(int n_ops, bool lin)
     {
-      return (size_t)(1 + n_ops) * NPTS * sizeof(T) + (size_t)NCELLS * CS * sizeof(T) + (size_t)NPTS * sizeof(uint32_t) +
-             (size_t)2 * NCELLS * 27 * sizeof(uint32_t);
+      return (size_t)(1 + n_ops) * NPTS * sizeof(T) + (size_t)NCELLS * CS * sizeof(T) +
+             (size_t)(lin ? NFOREIGN : NPTS) * sizeof(uint32_t) + (size_t)2 * NCELLS * 27 * sizeof(uint32_t) +
+             (lin ? (size_t)(NPTS + NFOREIGN) * sizeof(uint32_t) : 0);
     }
   };
 
@@ -375,20 +394,186 @@ namespace dasm
       }
   }
 
-  // fused pre-initialisation of the next kernel's destination on the brick's own shared DoFs
+  // ---- linear (coalesced) gather / store through the per-variant maps ------------------------------------------
+  // The brick's own DoFs are one contiguous range, so consecutive lanes read / write consecutive global
+  // addresses (2 lines per warp instruction instead of ~12 with the tile-ordered access); only the tile points
+  // owned by other bricks (upper faces) are addressed through the compressed indices.
+  constexpr uint32_t MAP_UNUSED = 0xFFFFFFFFu;
+
+  template <int k>
+  __device__ __forceinline__ uint32_t
+  tile_point_gidx(const BrickDesc &bd, const uint32_t *s_cidx, const int p, const int TX, const int TY)
+  {
+    const int px = p % TX, py = (p / TX) % TY, pz = p / (TX * TY);
+    const int cx = min(px / k, bd.b[0] - 1), cy = min(py / k, bd.b[1] - 1), cz = min(pz / k, bd.b[2] - 1);
+    return compressed_index<k>(s_cidx + ((cz * bd.b[1] + cy) * bd.b[0] + cx) * 27, px - cx * k, py - cy * k, pz - cz * k);
+  }
+
   template <int k, int BZ, typename T>
   __device__ __forceinline__ void
-  brick_next_init(const BrickDesc &bd, const NextInit<T> &ni)
+  brick_issue_loads_lin(const BrickDesc &bd, const uint32_t *own, const uint32_t *foreign, const int n_for, const unsigned flags,
+                        const uint32_t *s_cidx, T *tile, uint32_t *gidx_f, const T *__restrict__ src)
+  {
+    using G         = BrickGeom<k, BZ>;
+    const int n_own = bd.npriv + bd.sh_count;
+    if (flags & 1u)
+      {
+        for (int p = threadIdx.x; p < G::NPTS; p += G::NT)
+          tile[p] = T(0);
+        __syncthreads();
+      }
+    for (int i = threadIdx.x; i < n_own; i += G::NT)
+      {
+        const uint32_t e = own[i];
+        if (e != MAP_UNUSED)
+          cp_async_value(tile + (e & 0x1FFFu), src + bd.base + i);
+      }
+    for (int j = threadIdx.x; j < n_for; j += G::NT)
+      {
+        const int      p = foreign[j] & 0x1FFFu;
+        const uint32_t g = tile_point_gidx<k>(bd, s_cidx, p, G::TX, G::TY);
+        gidx_f[j]        = g;
+        if (g != DEV_INVALID)
+          cp_async_value(tile + p, src + g);
+        else
+          tile[p] = T(0);
+      }
+  }
+
+  template <int k, int BZ, typename T>
+  __device__ __forceinline__ void
+  brick_issue_ops_lin(const BrickDesc &bd, T *ops0, T *ops1, const Epilogue<T> &epi)
+  {
+    using G          = BrickGeom<k, BZ>;
+    const bool need0 = (epi.kind == EPI_RESIDUAL || epi.kind == EPI_CHEB);
+    const bool need1 = (epi.kind == EPI_CHEB && epi.f1 != T(0) && epi.v1 != nullptr);
+    if (!need0)
+      return;
+    for (int i = threadIdx.x; i < bd.npriv; i += G::NT)
+      {
+        cp_async_value(ops0 + i, epi.v0 + bd.base + i);
+        if (need1)
+          cp_async_value(ops1 + i, epi.v1 + bd.base + i);
+      }
+  }
+
+  template <typename T>
+  __device__ __forceinline__ T
+  slot_sum(const T *slots, const uint32_t e, const int dx, const int dy, const int dz)
+  {
+    const int      o = (e >> 13) & 0xFFFFu;
+    const unsigned m = e >> 29;
+    T              y = slots[o];
+    if (m & 1u)
+      y += slots[o + dx];
+    if (m & 2u)
+      {
+        y += slots[o + dy];
+        if (m & 1u)
+          y += slots[o + dy + dx];
+      }
+    if (m & 4u)
+      {
+        T z = slots[o + dz];
+        if (m & 1u)
+          z += slots[o + dz + dx];
+        if (m & 2u)
+          {
+            z += slots[o + dz + dy];
+            if (m & 1u)
+              z += slots[o + dz + dy + dx];
+          }
+        y += z;
+      }
+    return y;
+  }
+
+  template <int k, int BZ, typename T>
+  __device__ __forceinline__ void
+  brick_store_lin(const BrickDesc &bd, const uint32_t *own, const uint32_t *foreign, const int n_for, const T *slots, const T *ops0,
+                  const T *ops1, const uint32_t *gidx_f, T *__restrict__ dst, T *__restrict__ acc, const Epilogue<T> &epi,
+                  const int shared_mode)
+  {
+    using G           = BrickGeom<k, BZ>;
+    constexpr int n   = k + 1;
+    const int     n_own = bd.npriv + bd.sh_count;
+    const int       dx = -G::CS + k, dy = -bd.b[0] * G::CS + k * n, dz = -bd.b[0] * bd.b[1] * G::CS + k * n * n;
+    const bool      need0 = (epi.kind == EPI_RESIDUAL || epi.kind == EPI_CHEB);
+    const bool      need1 = (epi.kind == EPI_CHEB && epi.f1 != T(0) && epi.v1 != nullptr);
+    const T         alpha = (epi.kind == EPI_RESIDUAL) ? T(-1) : ((epi.kind == EPI_CHEB || epi.kind == EPI_SCALE) ? epi.f2 : T(1));
+    T *             sh_dst = (shared_mode == SHARED_DIRECT) ? dst : acc;
+    const T         sh_a   = (shared_mode == SHARED_DIRECT) ? alpha : T(1);
+    // private DoFs: fused epilogue, coalesced plain stores
+#pragma unroll 4
+    for (int i = threadIdx.x; i < bd.npriv; i += G::NT)
+      {
+        const uint32_t e = own[i];
+        if (e == MAP_UNUSED)
+          continue;
+        const T y        = slot_sum(slots, e, dx, dy, dz);
+        dst[bd.base + i] = epilogue_compute(epi, y, need0 ? ops0[i] : T(0), need1 ? ops1[i] : T(0));
+      }
+    // own DoFs on shared faces: coalesced red.add
+    for (int i = bd.npriv + threadIdx.x; i < n_own; i += G::NT)
+      {
+        const uint32_t e = own[i];
+        if (e != MAP_UNUSED)
+          atomic_add(sh_dst + bd.base + i, sh_a * slot_sum(slots, e, dx, dy, dz));
+      }
+    // tile points owned by other bricks
+    for (int j = threadIdx.x; j < n_for; j += G::NT)
+      {
+        const uint32_t g = gidx_f[j];
+        if (g != DEV_INVALID)
+          atomic_add(sh_dst + g, sh_a * slot_sum(slots, foreign[j], dx, dy, dz));
+      }
+  }
+
+  // fused pre-initialisation of the next kernel's destination on the brick's own shared DoFs: the operand loads
+  // are issued first thing for a brick, the stores follow after the wait for the tile data, so that the two
+  // latencies overlap
+  template <int k, int BZ>
+  struct NextInitRegs
+  {
+    static constexpr int IT = (BrickGeom<k, BZ>::NPTS - (BrickGeom<k, BZ>::BX * k - 1) * (BrickGeom<k, BZ>::BY * k - 1) * (BZ * k - 1) +
+                               BrickGeom<k, BZ>::NT - 1) / BrickGeom<k, BZ>::NT; // upper bound of shared DoFs per thread
+  };
+
+  template <int k, int BZ, typename T>
+  __device__ __forceinline__ void
+  brick_next_init_load(const BrickDesc &bd, const NextInit<T> &ni, T (&a)[NextInitRegs<k, BZ>::IT], T (&b)[NextInitRegs<k, BZ>::IT])
+  {
+    using G = BrickGeom<k, BZ>;
+#pragma unroll
+    for (int it = 0; it < NextInitRegs<k, BZ>::IT; ++it)
+      {
+        const uint32_t i = threadIdx.x + it * G::NT;
+        a[it]            = T(0);
+        b[it]            = T(0);
+        if (ni.out != nullptr && i < bd.sh_count)
+          {
+            if (ni.v0 != nullptr)
+              a[it] = ni.v0[bd.sh_base + i];
+            if (ni.v1 != nullptr && ni.f1 != T(0))
+              b[it] = ni.v1[bd.sh_base + i];
+          }
+      }
+  }
+
+  template <int k, int BZ, typename T>
+  __device__ __forceinline__ void
+  brick_next_init_store(const BrickDesc &bd, const NextInit<T> &ni, const T (&a)[NextInitRegs<k, BZ>::IT],
+                        const T (&b)[NextInitRegs<k, BZ>::IT])
   {
     using G = BrickGeom<k, BZ>;
     if (ni.out == nullptr)
       return;
-    for (uint32_t i = threadIdx.x; i < bd.sh_count; i += G::NT)
+#pragma unroll
+    for (int it = 0; it < NextInitRegs<k, BZ>::IT; ++it)
       {
-        const uint32_t g = bd.sh_base + i;
-        const T        a = (ni.v0 != nullptr) ? ni.v0[g] : T(0);
-        const T        b = (ni.v1 != nullptr && ni.f1 != T(0)) ? ni.v1[g] : T(0);
-        ni.out[g]        = a + ni.f1 * (a - b);
+        const uint32_t i = threadIdx.x + it * G::NT;
+        if (i < bd.sh_count)
+          ni.out[bd.sh_base + i] = a[it] + ni.f1 * (a[it] - b[it]);
       }
   }
 
@@ -491,7 +676,9 @@ namespace dasm
                        const CartesianCoef cart,
                        const int n_ops,
                        const int shared_mode,
-                       const NextInit<T> ni)
+                       const NextInit<T> ni,
+                       const BrickMaps maps,
+                       const int dbg)
   {
     using G         = BrickGeom<k, BZ>;
     constexpr int n = k + 1;
@@ -501,7 +688,12 @@ namespace dasm
     T *       ops1   = (n_ops > 1) ? tile + 2 * G::NPTS : ops0;
     T *       slots  = tile + (1 + n_ops) * G::NPTS;
     uint32_t *gidx   = reinterpret_cast<uint32_t *>(slots + G::NCELLS * G::CS);
-    uint32_t *s_cidx = gidx + G::NPTS; // two buffers of NCELLS * 27
+    const bool lin_mode = (maps.own != nullptr);
+    uint32_t * s_cidx   = gidx + (lin_mode ? G::NFOREIGN : G::NPTS); // two buffers of NCELLS * 27
+    uint32_t * s_own    = s_cidx + 2 * G::NCELLS * 27;                // lin: staged maps of the current variant
+    uint32_t * s_for    = s_own + G::NPTS;
+    int        cur_variant = -1, n_for = 0;
+    unsigned   var_flags   = 0;
 
     const auto &B = BasisOf<T>::template get<k>();
     const int   c = threadIdx.x % G::NCELLS; // cell in brick (lane-major: conflict-free slot access)
@@ -512,25 +704,62 @@ namespace dasm
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
-    int buf = 0;
+    int       buf = 0;
+    BrickDesc bd_next;
+    if (blockIdx.x < n_bricks)
+      bd_next = bricks[blockIdx.x];
     for (int bi = blockIdx.x; bi < n_bricks; bi += gridDim.x, buf ^= 1)
       {
-        const BrickDesc bd     = bricks[bi];
+        const BrickDesc bd     = bd_next;
+        if (bi + (int)gridDim.x < n_bricks)
+          bd_next = bricks[bi + gridDim.x]; // descriptor of the next brick: latency hidden behind this brick
         const int       ncells = bd.b[0] * bd.b[1] * bd.b[2];
         const uint32_t *cur_cidx = s_cidx + buf * (G::NCELLS * 27);
+        T               ni_a[NextInitRegs<k, BZ>::IT], ni_b[NextInitRegs<k, BZ>::IT];
+        brick_next_init_load<k, BZ, T>(bd, ni, ni_a, ni_b);
         // group 1: source values, group 2: epilogue operands, group 3: indices of the next brick
-        brick_issue_loads<k, BZ, T>(bd, cur_cidx, tile, ops0, ops1, gidx, src, (const T *)nullptr, (const T *)nullptr);
-        cp_async_commit();
-        brick_issue_loads_ops<k, BZ, T>(bd, gidx, ops0, ops1, epi);
-        cp_async_commit();
+        const bool lin = lin_mode;
+        if (lin && (int)bd.variant != cur_variant)
+          {
+            // stage the tile maps of this brick's variant (periodic meshes have a single variant)
+            cur_variant = bd.variant;
+            n_for       = maps.n_foreign[cur_variant];
+            var_flags   = maps.flags[cur_variant];
+            for (int i = threadIdx.x; i < G::NPTS; i += G::NT)
+              s_own[i] = maps.own[(size_t)cur_variant * maps.stride + i];
+            for (int i = threadIdx.x; i < n_for; i += G::NT)
+              s_for[i] = maps.foreign[(size_t)cur_variant * maps.stride + i];
+            __syncthreads();
+          }
+        if (dbg & 1)
+          {
+            cp_async_commit();
+            cp_async_commit();
+          }
+        else if (lin)
+          {
+            brick_issue_loads_lin<k, BZ, T>(bd, s_own, s_for, n_for, var_flags, cur_cidx, tile, gidx, src);
+            cp_async_commit();
+            if (!(dbg & 16))
+              brick_issue_ops_lin<k, BZ, T>(bd, ops0, ops1, epi);
+            cp_async_commit();
+          }
+        else
+          {
+            brick_issue_loads<k, BZ, T>(bd, cur_cidx, tile, ops0, ops1, gidx, src, (const T *)nullptr, (const T *)nullptr);
+            cp_async_commit();
+            brick_issue_loads_ops<k, BZ, T>(bd, gidx, ops0, ops1, epi);
+            cp_async_commit();
+          }
         if (bi + (int)gridDim.x < n_bricks)
-          brick_stage_cidx_async<k, BZ>(bricks[bi + gridDim.x], cidx, s_cidx + (buf ^ 1) * (G::NCELLS * 27));
+          brick_stage_cidx_async<k, BZ>(bd_next, cidx, s_cidx + (buf ^ 1) * (G::NCELLS * 27));
         cp_async_commit();
-        brick_next_init<k, BZ, T>(bd, ni);
         cp_async_wait<2>();
+        if (!(dbg & 4))
+          brick_next_init_store<k, BZ, T>(bd, ni, ni_a, ni_b);
         __syncthreads();
 
-        const bool act = (c < ncells);
+        const bool act = (c < ncells) && !(dbg & 2);
         const int  cx = c % bd.b[0], cy = (c / bd.b[0]) % bd.b[1], cz = c / (bd.b[0] * bd.b[1]);
         T *        S  = slots + c * G::CS;
         T          r[n][n]; // partial result of the x/z directions, plane y = t, [z][x]
@@ -733,7 +962,13 @@ namespace dasm
           }
         cp_async_wait<1>(); // epilogue operands have landed
         __syncthreads();
-        brick_reduce_store<k, BZ, T>(bd, slots, ops0, ops1, gidx, dst, acc, epi, shared_mode);
+        if (dbg & 8)
+          {
+          }
+        else if (lin)
+          brick_store_lin<k, BZ, T>(bd, s_own, s_for, n_for, slots, ops0, ops1, gidx, dst, acc, epi, shared_mode);
+        else
+          brick_reduce_store<k, BZ, T>(bd, slots, ops0, ops1, gidx, dst, acc, epi, shared_mode);
         cp_async_wait<0>(); // indices of the next brick
         __syncthreads();
       }
@@ -757,7 +992,8 @@ namespace dasm
                    const int w_post,
                    const int n_ops,
                    const int shared_mode,
-                   const NextInit<T> ni)
+                   const NextInit<T> ni,
+                   const BrickMaps maps)
   {
     using G          = BrickGeom<k, BZ>;
     constexpr int n  = k + 1;
@@ -768,7 +1004,12 @@ namespace dasm
     T *       ops1   = (n_ops > 1) ? tile + 2 * G::NPTS : ops0;
     T *       slots  = tile + (1 + n_ops) * G::NPTS;
     uint32_t *gidx   = reinterpret_cast<uint32_t *>(slots + G::NCELLS * G::CS);
-    uint32_t *s_cidx = gidx + G::NPTS; // two buffers of NCELLS * 27
+    const bool lin_mode = (maps.own != nullptr);
+    uint32_t * s_cidx   = gidx + (lin_mode ? G::NFOREIGN : G::NPTS); // two buffers of NCELLS * 27
+    uint32_t * s_own    = s_cidx + 2 * G::NCELLS * 27;                // lin: staged maps of the current variant
+    uint32_t * s_for    = s_own + G::NPTS;
+    int        cur_variant = -1, n_for = 0;
+    unsigned   var_flags   = 0;
 
     const int c = threadIdx.x % G::NCELLS; // cell in brick (lane-major: conflict-free slot access)
     const int t = threadIdx.x / G::NCELLS; // plane index (warp-uniform)
@@ -778,21 +1019,51 @@ namespace dasm
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
-    int buf = 0;
+    int       buf = 0;
+    BrickDesc bd_next;
+    if (blockIdx.x < n_bricks)
+      bd_next = bricks[blockIdx.x];
     for (int bi = blockIdx.x; bi < n_bricks; bi += gridDim.x, buf ^= 1)
       {
-        const BrickDesc bd     = bricks[bi];
+        const BrickDesc bd     = bd_next;
+        if (bi + (int)gridDim.x < n_bricks)
+          bd_next = bricks[bi + gridDim.x]; // descriptor of the next brick: latency hidden behind this brick
         const int       ncells = bd.b[0] * bd.b[1] * bd.b[2];
         const uint32_t *cur_cidx = s_cidx + buf * (G::NCELLS * 27);
-        brick_issue_loads<k, BZ, T>(bd, cur_cidx, tile, ops0, ops1, gidx, src, (const T *)nullptr, (const T *)nullptr);
-        cp_async_commit();
-        brick_issue_loads_ops<k, BZ, T>(bd, gidx, ops0, ops1, epi);
-        cp_async_commit();
+        T               ni_a[NextInitRegs<k, BZ>::IT], ni_b[NextInitRegs<k, BZ>::IT];
+        brick_next_init_load<k, BZ, T>(bd, ni, ni_a, ni_b);
+        const bool lin = lin_mode;
+        if (lin && (int)bd.variant != cur_variant)
+          {
+            // stage the tile maps of this brick's variant (periodic meshes have a single variant)
+            cur_variant = bd.variant;
+            n_for       = maps.n_foreign[cur_variant];
+            var_flags   = maps.flags[cur_variant];
+            for (int i = threadIdx.x; i < G::NPTS; i += G::NT)
+              s_own[i] = maps.own[(size_t)cur_variant * maps.stride + i];
+            for (int i = threadIdx.x; i < n_for; i += G::NT)
+              s_for[i] = maps.foreign[(size_t)cur_variant * maps.stride + i];
+            __syncthreads();
+          }
+        if (lin)
+          {
+            brick_issue_loads_lin<k, BZ, T>(bd, s_own, s_for, n_for, var_flags, cur_cidx, tile, gidx, src);
+            cp_async_commit();
+            brick_issue_ops_lin<k, BZ, T>(bd, ops0, ops1, epi);
+            cp_async_commit();
+          }
+        else
+          {
+            brick_issue_loads<k, BZ, T>(bd, cur_cidx, tile, ops0, ops1, gidx, src, (const T *)nullptr, (const T *)nullptr);
+            cp_async_commit();
+            brick_issue_loads_ops<k, BZ, T>(bd, gidx, ops0, ops1, epi);
+            cp_async_commit();
+          }
         if (bi + (int)gridDim.x < n_bricks)
-          brick_stage_cidx_async<k, BZ>(bricks[bi + gridDim.x], cidx, s_cidx + (buf ^ 1) * (G::NCELLS * 27));
+          brick_stage_cidx_async<k, BZ>(bd_next, cidx, s_cidx + (buf ^ 1) * (G::NCELLS * 27));
         cp_async_commit();
-        brick_next_init<k, BZ, T>(bd, ni);
         cp_async_wait<2>();
+        brick_next_init_store<k, BZ, T>(bd, ni, ni_a, ni_b);
         __syncthreads();
 
         const bool     act  = c < ncells;
@@ -926,7 +1197,10 @@ namespace dasm
           }
         cp_async_wait<1>();
         __syncthreads();
-        brick_reduce_store<k, BZ, T>(bd, slots, ops0, ops1, gidx, dst, acc, epi, shared_mode);
+        if (lin)
+          brick_store_lin<k, BZ, T>(bd, s_own, s_for, n_for, slots, ops0, ops1, gidx, dst, acc, epi, shared_mode);
+        else
+          brick_reduce_store<k, BZ, T>(bd, slots, ops0, ops1, gidx, dst, acc, epi, shared_mode);
         cp_async_wait<0>();
         __syncthreads();
       }
