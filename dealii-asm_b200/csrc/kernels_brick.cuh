@@ -1014,6 +1014,17 @@ namespace dasm
     const int c = threadIdx.x % G::NCELLS; // cell in brick (lane-major: conflict-free slot access)
     const int t = threadIdx.x / G::NCELLS; // plane index (warp-uniform)
 
+    // cache of the 1-D eigen-decompositions when all cells of a brick share one instance triple (Cartesian
+    // meshes): matrices, eigenvalues and the table of inverse eigenvalue sums live in shared memory and are
+    // re-staged only when the triple changes; otherwise (deformed meshes) every thread reads its cell's
+    // matrices from global memory and divides on the fly
+    __shared__ T        s_M[3][n * n];
+    __shared__ T        s_lam[3][n];
+    __shared__ T        s_inv[n * n * n];
+    __shared__ uint32_t s_tri[3];
+    if (threadIdx.x < 3)
+      s_tri[threadIdx.x] = 0xFFFFFFFFu;
+
     if (blockIdx.x < n_bricks)
       brick_stage_cidx_async<k, BZ>(bricks[blockIdx.x], cidx, s_cidx);
     cp_async_commit();
@@ -1077,6 +1088,26 @@ namespace dasm
             i1 = inst[(size_t)cell * 3 + 1];
             i2 = inst[(size_t)cell * 3 + 2];
           }
+        const uint32_t r0 = inst[(size_t)bd.first_cell * 3 + 0], r1 = inst[(size_t)bd.first_cell * 3 + 1],
+                       r2 = inst[(size_t)bd.first_cell * 3 + 2];
+        const bool uniform = __syncthreads_and(!act || (i0 == r0 && i1 == r1 && i2 == r2)) != 0;
+        if (uniform && (s_tri[0] != r0 || s_tri[1] != r1 || s_tri[2] != r2))
+          {
+            __syncthreads();
+            for (int i = threadIdx.x; i < 3 * n2; i += G::NT)
+              s_M[i / n2][i % n2] = Smat[(size_t)(i / n2 == 0 ? r0 : (i / n2 == 1 ? r1 : r2)) * n2 + i % n2];
+            for (int i = threadIdx.x; i < 3 * n; i += G::NT)
+              s_lam[i / n][i % n] = lam[(size_t)(i / n == 0 ? r0 : (i / n == 1 ? r1 : r2)) * n + i % n];
+            __syncthreads();
+            for (int i = threadIdx.x; i < n * n2; i += G::NT)
+              s_inv[i] = T(1) / (s_lam[0][i % n] + s_lam[1][(i / n) % n] + s_lam[2][i / n2]);
+            if (threadIdx.x < 3)
+              s_tri[threadIdx.x] = (threadIdx.x == 0 ? r0 : (threadIdx.x == 1 ? r1 : r2));
+            __syncthreads();
+          }
+        const T *M0p = uniform ? s_M[0] : Smat + (size_t)i0 * n2;
+        const T *M1p = uniform ? s_M[1] : Smat + (size_t)i1 * n2;
+        const T *M2p = uniform ? s_M[2] : Smat + (size_t)i2 * n2;
         const int et = (t == 0) ? 0 : ((t == k) ? 2 : 1); // entity code of the plane index
 
         // phase A: plane z = t, [y][x]: (pre-weights) S0^T in x, S1^T in y
@@ -1105,14 +1136,14 @@ namespace dasm
               T M[n2];
 #pragma unroll
               for (int i = 0; i < n2; ++i)
-                M[i] = Smat[(size_t)i0 * n2 + i];
+                M[i] = M0p[i];
               apply_fast<n, T, true>(v, M);
             }
             {
               T M[n2];
 #pragma unroll
               for (int i = 0; i < n2; ++i)
-                M[i] = Smat[(size_t)i1 * n2 + i];
+                M[i] = M1p[i];
               apply_slow<n, T, true>(v, M);
             }
 #pragma unroll
@@ -1134,27 +1165,36 @@ namespace dasm
             T M[n2];
 #pragma unroll
             for (int i = 0; i < n2; ++i)
-              M[i] = Smat[(size_t)i2 * n2 + i];
+              M[i] = M2p[i];
             apply_slow<n, T, true>(w, M);
-            {
-              T       l0[n], l2[n];
-              const T l1 = lam[(size_t)i1 * n + t];
+            if (uniform)
+              {
 #pragma unroll
-              for (int i = 0; i < n; ++i)
-                {
-                  l0[i] = lam[(size_t)i0 * n + i];
-                  l2[i] = lam[(size_t)i2 * n + i];
-                }
+                for (int z = 0; z < n; ++z)
 #pragma unroll
-              for (int z = 0; z < n; ++z)
+                  for (int x = 0; x < n; ++x)
+                    w[z][x] *= s_inv[(z * n + t) * n + x];
+              }
+            else
+              {
+                T       l0[n], l2[n];
+                const T l1 = lam[(size_t)i1 * n + t];
 #pragma unroll
-                for (int x = 0; x < n; ++x)
-                  w[z][x] = w[z][x] / (l0[x] + l1 + l2[z]);
-            }
+                for (int i = 0; i < n; ++i)
+                  {
+                    l0[i] = lam[(size_t)i0 * n + i];
+                    l2[i] = lam[(size_t)i2 * n + i];
+                  }
+#pragma unroll
+                for (int z = 0; z < n; ++z)
+#pragma unroll
+                  for (int x = 0; x < n; ++x)
+                    w[z][x] = w[z][x] / (l0[x] + l1 + l2[z]);
+              }
             apply_slow<n, T, false>(w, M);
 #pragma unroll
             for (int i = 0; i < n2; ++i)
-              M[i] = Smat[(size_t)i0 * n2 + i];
+              M[i] = M0p[i];
             apply_fast<n, T, false>(w, M);
 #pragma unroll
             for (int z = 0; z < n; ++z)
@@ -1175,7 +1215,7 @@ namespace dasm
             T M[n2];
 #pragma unroll
             for (int i = 0; i < n2; ++i)
-              M[i] = Smat[(size_t)i1 * n2 + i];
+              M[i] = M1p[i];
             apply_slow<n, T, false>(v, M);
             if (cw != nullptr && w_post)
               {
