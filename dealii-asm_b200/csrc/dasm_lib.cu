@@ -269,8 +269,10 @@ struct dasm_op
   uint32_t *        d_cidx        = nullptr;
   uint32_t *        d_constrained = nullptr;
   long long         n_constrained = 0;
-  int               geom_mode     = 0; // 0 cartesian, 1 merged
-  void *            d_geom        = nullptr;
+  int               geom_mode     = 0; // 0 cartesian, 1 merged, 2 quadratic / linear coefficients (brick kernel)
+  void *            d_geom        = nullptr; // merged coefficients [cell][6][n^3]
+  void *            d_qcoef       = nullptr; // monomial coefficients of the cell map [cell][27][3]
+  bool              linear_geometry = false;
   CartesianCoef     cart;
   Exchange          exchange;
   std::vector<void *> scratch; // owned by op, freed at destroy
@@ -585,12 +587,19 @@ launch_laplace_brick(dasm_op *op, T *dst, const T *src, const Epilogue<T> &epi, 
         kern<<<grid, BrickGeom<K, BZ>::NT, smem, ctx->stream>>>(src, dst, (T *)op->d_acc, epi, op->d_cidx, op->d_bricks, op->n_bricks,
                                                                  (const T *)nullptr, op->cart, n_ops, shared_mode, ni, op->maps, dbg);
       }
-    else
+    else if (op->geom_mode == 1)
       {
         auto      kern = laplace_brick_kernel<K, T, BZ, 1>;
         const int grid = brick_grid<K, BZ, T>(op, kern, smem);
         kern<<<grid, BrickGeom<K, BZ>::NT, smem, ctx->stream>>>(src, dst, (T *)op->d_acc, epi, op->d_cidx, op->d_bricks, op->n_bricks,
                                                                  (const T *)op->d_geom, op->cart, n_ops, shared_mode, ni, op->maps, dbg);
+      }
+    else
+      {
+        auto      kern = laplace_brick_kernel<K, T, BZ, 2>;
+        const int grid = brick_grid<K, BZ, T>(op, kern, smem);
+        kern<<<grid, BrickGeom<K, BZ>::NT, smem, ctx->stream>>>(src, dst, (T *)op->d_acc, epi, op->d_cidx, op->d_bricks, op->n_bricks,
+                                                                 (const T *)op->d_qcoef, op->cart, n_ops, shared_mode, ni, op->maps, dbg);
       }
     ctx->launches++;
   }
@@ -852,6 +861,8 @@ upload_basis_tables()
         {
           hd[k].qw[i] = b.qw[i];
           hf[k].qw[i] = (float)b.qw[i];
+          hd[k].qp[i] = b.qp[i];
+          hf[k].qp[i] = (float)b.qp[i];
         }
     }
   CUDA_CHECK(cudaMemcpyToSymbol(c_basis_d, hd, sizeof(hd)));
@@ -1083,9 +1094,9 @@ dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping
   DASM_REQUIRE(degree >= 1 && degree <= MAX_DEGREE, "degree must be in 1..8");
   DASM_REQUIRE(number_type == DASM_F64 || number_type == DASM_F32, "unknown number type");
   const std::string mt = mapping_type ? mapping_type : "";
-  if (mt == "linear geometry" || mt == "quadratic geometry" || mt == "construct q")
-    throw std::runtime_error("Mapping type <" + mt + "> is not implemented in libdasm yet (use \"\" or \"merged\")");
-  if (mt != "" && mt != "merged")
+  if (mt == "construct q")
+    throw std::runtime_error("Mapping type <" + mt + "> is not implemented in libdasm yet");
+  if (mt != "" && mt != "merged" && mt != "quadratic geometry" && mt != "linear geometry")
     throw std::runtime_error("Mapping type <" + mt + "> is not known!"); // operator.h:747-752
   dasm_ctx *ctx = mesh->ctx;
   CUDA_CHECK(cudaSetDevice(ctx->device));
@@ -1124,7 +1135,25 @@ dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping
     }
   else
     {
-      op->geom_mode = 1;
+      op->geom_mode       = (mt == "quadratic geometry" || mt == "linear geometry") ? 2 : 1;
+      op->linear_geometry = (mt == "linear geometry");
+      const bool lingeo   = op->linear_geometry;
+      if (op->geom_mode == 2)
+        {
+          std::vector<double> qc((size_t)op->n_cells * 81);
+          for (long long c = 0; c < op->n_cells; ++c)
+            {
+              const int cc[3] = {M.cell_ijk[c][0], M.cell_ijk[c][1], M.cell_ijk[c][2]};
+              M.quadratic_coefficients(cc, lingeo, qc.data() + (size_t)c * 81);
+            }
+          if (number_type == DASM_F64)
+            op->d_qcoef = dev_upload(qc, ctx->stream);
+          else
+            {
+              std::vector<float> qf(qc.begin(), qc.end());
+              op->d_qcoef = dev_upload(qf, ctx->stream);
+            }
+        }
       std::vector<double> tmp(6 * n3);
       if (number_type == DASM_F64)
         {
@@ -1132,7 +1161,7 @@ dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping
           for (long long c = 0; c < op->n_cells; ++c)
             {
               const int cc[3] = {M.cell_ijk[c][0], M.cell_ijk[c][1], M.cell_ijk[c][2]};
-              M.merged_coefficients(cc, op->basis, g.data() + (size_t)c * 6 * n3);
+              M.merged_coefficients(cc, op->basis, g.data() + (size_t)c * 6 * n3, lingeo);
             }
           op->d_geom = dev_upload(g, ctx->stream);
         }
@@ -1142,7 +1171,7 @@ dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping
           for (long long c = 0; c < op->n_cells; ++c)
             {
               const int cc[3] = {M.cell_ijk[c][0], M.cell_ijk[c][1], M.cell_ijk[c][2]};
-              M.merged_coefficients(cc, op->basis, tmp.data());
+              M.merged_coefficients(cc, op->basis, tmp.data(), lingeo);
               for (int i = 0; i < 6 * n3; ++i)
                 g[(size_t)c * 6 * n3 + i] = (float)tmp[i];
             }
@@ -1451,6 +1480,7 @@ dasm_op_destroy(dasm_op *op)
   cudaFree(op->d_cidx);
   cudaFree(op->d_constrained);
   cudaFree(op->d_geom);
+  cudaFree(op->d_qcoef);
   cudaFree(op->d_bricks);
   cudaFree(op->d_acc);
   cudaFree(op->d_shared_list);
@@ -1549,7 +1579,7 @@ dasm_op_merged_coefficients(const dasm_op *op, long long cell, double *out)
   DASM_REQUIRE(cell >= 0 && cell < op->n_cells, "cell out of range");
   const Mesh &M    = *op->mesh->mesh;
   const int   c[3] = {M.cell_ijk[cell][0], M.cell_ijk[cell][1], M.cell_ijk[cell][2]};
-  M.merged_coefficients(c, op->basis, out);
+  M.merged_coefficients(c, op->basis, out, op->linear_geometry);
   DASM_API_END
 }
 

@@ -25,6 +25,7 @@ namespace dasm
     T Dq[81]; // Dq[q*n+p] collocation derivative
     T Dn[81]; // Dn[q*n+i] derivative of nodal basis at Gauss points
     T qw[9];
+    T qp[9];  // Gauss points on [0,1]
   };
 
   __constant__ DevBasis<double> c_basis_d[9];

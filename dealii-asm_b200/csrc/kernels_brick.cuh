@@ -662,7 +662,10 @@ namespace dasm
   }
 
   // ---- K1 (tuned): Laplace brick kernel -----------------------------------------------------------------
-  // GEOM 0: uniform Cartesian;  GEOM 1: merged coefficients geom[cell][6][n^3]
+  // GEOM 0: uniform Cartesian;  GEOM 1: merged coefficients geom[cell][6][n^3];  GEOM 2: Jacobian rebuilt per
+  // quadrature point from the 27 x 3 monomial coefficients of the triquadratic cell map geom[cell][27][3]
+  // ("quadratic geometry", operator.h:1035-1159; "linear geometry" 916-1033 uses the same code with the
+  // trilinear coefficients of the 8 vertices)
   template <int k, typename T, int BZ, int GEOM>
   __global__ void __launch_bounds__(BrickGeom<k, BZ>::NT, BrickGeom<k, BZ>::MINB)
   laplace_brick_kernel(const T *__restrict__ src,
@@ -886,21 +889,85 @@ namespace dasm
             if (act) // plane y = t: quadrature-point operation
               {
                 constexpr int n3 = n * n * n;
-                const T *     Gc = geom + (size_t)(bd.first_cell + c) * 6 * n3;
+                const T *     Gc = geom + (size_t)(bd.first_cell + c) * (GEOM == 1 ? 6 * n3 : 81);
+                const T       eta = B.qp[t];
 #pragma unroll
                 for (int z = 0; z < n; ++z)
+                  {
+                    // GEOM 2: coefficients reduced in zeta and eta for this (z, t): position derivative pieces
+                    T Bx[3][3], By[3][3], Bz[3][3]; // [power of xi][component]
+                    if (GEOM == 2)
+                      {
+                        const T zeta = B.qp[z];
 #pragma unroll
-                  for (int x = 0; x < n; ++x)
-                    {
-                      const int q   = (z * n + t) * n + x;
-                      const T   gyv = S[q];
-                      const T   a = gx[z][x], cc = gz[z][x];
-                      const T   gxx = Gc[q], gxy = Gc[n3 + q], gxz = Gc[2 * n3 + q], gyy = Gc[3 * n3 + q], gyz = Gc[4 * n3 + q],
-                              gzz = Gc[5 * n3 + q];
-                      gx[z][x] = gxx * a + gxy * gyv + gxz * cc;
-                      S[q]     = gxy * a + gyy * gyv + gyz * cc;
-                      gz[z][x] = gxz * a + gyz * gyv + gzz * cc;
-                    }
+                        for (int i = 0; i < 3; ++i)
+#pragma unroll
+                          for (int d = 0; d < 3; ++d)
+                            {
+                              T A[3], dA[3];
+#pragma unroll
+                              for (int j = 0; j < 3; ++j)
+                                {
+                                  const T v0 = Gc[(3 * j + i) * 3 + d], v1 = Gc[(9 + 3 * j + i) * 3 + d], v2 = Gc[(18 + 3 * j + i) * 3 + d];
+                                  A[j]  = v0 + zeta * (v1 + zeta * v2);
+                                  dA[j] = v1 + (zeta + zeta) * v2;
+                                }
+                              Bx[i][d] = A[0] + eta * (A[1] + eta * A[2]);
+                              By[i][d] = A[1] + (eta + eta) * A[2];
+                              Bz[i][d] = dA[0] + eta * (dA[1] + eta * dA[2]);
+                            }
+                      }
+#pragma unroll
+                    for (int x = 0; x < n; ++x)
+                      {
+                        const int q   = (z * n + t) * n + x;
+                        const T   gyv = S[q];
+                        const T   a = gx[z][x], cc = gz[z][x];
+                        T         gxx, gxy, gxz, gyy, gyz, gzz;
+                        if (GEOM == 1)
+                          {
+                            gxx = Gc[q];
+                            gxy = Gc[n3 + q];
+                            gxz = Gc[2 * n3 + q];
+                            gyy = Gc[3 * n3 + q];
+                            gyz = Gc[4 * n3 + q];
+                            gzz = Gc[5 * n3 + q];
+                          }
+                        else
+                          {
+                            const T xi = B.qp[x];
+                            T       J[3][3]; // J[d][e] = d x_d / d xi_e
+#pragma unroll
+                            for (int d = 0; d < 3; ++d)
+                              {
+                                J[d][0] = Bx[1][d] + (xi + xi) * Bx[2][d];
+                                J[d][1] = By[0][d] + xi * (By[1][d] + xi * By[2][d]);
+                                J[d][2] = Bz[0][d] + xi * (Bz[1][d] + xi * Bz[2][d]);
+                              }
+                            const T c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1], c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2],
+                                    c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+                            const T det  = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02;
+                            const T idet = T(1) / det;
+                            // inverse I[e][d] = d xi_e / d x_d
+                            const T I00 = c00 * idet, I01 = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * idet,
+                                    I02 = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * idet;
+                            const T I10 = c01 * idet, I11 = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * idet,
+                                    I12 = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * idet;
+                            const T I20 = c02 * idet, I21 = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * idet,
+                                    I22 = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * idet;
+                            const T jxw = det * (B.qw[x] * B.qw[t] * B.qw[z]);
+                            gxx         = jxw * (I00 * I00 + I01 * I01 + I02 * I02);
+                            gxy         = jxw * (I00 * I10 + I01 * I11 + I02 * I12);
+                            gxz         = jxw * (I00 * I20 + I01 * I21 + I02 * I22);
+                            gyy         = jxw * (I10 * I10 + I11 * I11 + I12 * I12);
+                            gyz         = jxw * (I10 * I20 + I11 * I21 + I12 * I22);
+                            gzz         = jxw * (I20 * I20 + I21 * I21 + I22 * I22);
+                          }
+                        gx[z][x] = gxx * a + gxy * gyv + gxz * cc;
+                        S[q]     = gxy * a + gyy * gyv + gyz * cc;
+                        gz[z][x] = gxz * a + gyz * gyv + gzz * cc;
+                      }
+                  }
                 apply_fast<n, T, true>(gx, B.Dq);
                 apply_slow<n, T, true>(gz, B.Dq);
 #pragma unroll

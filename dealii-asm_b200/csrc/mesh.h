@@ -225,8 +225,10 @@ namespace dasm
     }
 
     // 27 support points of the Q2 geometry interpolant of a cell (MappingQCache degree 2)
+    // linear = true: the trilinear map through the 8 mapped vertices (the geometry "linear geometry" of the
+    // reference sees, operator.h:512-591), sampled at the same 27 nodes
     void
-    cell_support_points(const int c[3], double X[27][3]) const
+    cell_support_points(const int c[3], double X[27][3], const bool linear = false) const
     {
       static const double nodes[3] = {0., 0.5, 1.};
       for (int k = 0; k < 3; ++k)
@@ -236,6 +238,64 @@ namespace dasm
               const double ref[3] = {(c[0] + nodes[i]) * h(0), (c[1] + nodes[j]) * h(1), (c[2] + nodes[k]) * h(2)};
               map_point(ref, X[9 * k + 3 * j + i]);
             }
+      if (linear)
+        for (int k = 0; k < 3; ++k)
+          for (int j = 0; j < 3; ++j)
+            for (int i = 0; i < 3; ++i)
+              if (i == 1 || j == 1 || k == 1)
+                for (int d = 0; d < 3; ++d)
+                  {
+                    double v = 0;
+                    for (int c2 = 0; c2 < 2; ++c2)
+                      for (int b2 = 0; b2 < 2; ++b2)
+                        for (int a2 = 0; a2 < 2; ++a2)
+                          {
+                            const double w = (a2 ? nodes[i] : 1 - nodes[i]) * (b2 ? nodes[j] : 1 - nodes[j]) * (c2 ? nodes[k] : 1 - nodes[k]);
+                            v += w * X[9 * (2 * c2) + 3 * (2 * b2) + 2 * a2][d];
+                          }
+                    X[9 * k + 3 * j + i][d] = v;
+                  }
+    }
+
+    // 27 x 3 monomial coefficients of the triquadratic cell map x(xi) = sum c[9k+3j+i] xi^i eta^j zeta^k
+    // (cell_quadratic_coefficients, operator.h:592-673): out[(9k+3j+i)*3 + d]
+    void
+    quadratic_coefficients(const int c[3], const bool linear, double *out) const
+    {
+      double X[27][3];
+      cell_support_points(c, X, linear);
+      static const double T[3][3] = {{1, 0, 0}, {-3, 4, -1}, {2, -4, 2}}; // nodal values at (0, 1/2, 1) -> monomials
+      double             A[27][3], Bm[27][3];
+      for (int k = 0; k < 3; ++k)
+        for (int j = 0; j < 3; ++j)
+          for (int i = 0; i < 3; ++i)
+            for (int d = 0; d < 3; ++d)
+              {
+                double v = 0;
+                for (int a = 0; a < 3; ++a)
+                  v += T[i][a] * X[9 * k + 3 * j + a][d];
+                A[9 * k + 3 * j + i][d] = v;
+              }
+      for (int k = 0; k < 3; ++k)
+        for (int j = 0; j < 3; ++j)
+          for (int i = 0; i < 3; ++i)
+            for (int d = 0; d < 3; ++d)
+              {
+                double v = 0;
+                for (int a = 0; a < 3; ++a)
+                  v += T[j][a] * A[9 * k + 3 * a + i][d];
+                Bm[9 * k + 3 * j + i][d] = v;
+              }
+      for (int k = 0; k < 3; ++k)
+        for (int j = 0; j < 3; ++j)
+          for (int i = 0; i < 3; ++i)
+            for (int d = 0; d < 3; ++d)
+              {
+                double v = 0;
+                for (int a = 0; a < 3; ++a)
+                  v += T[k][a] * Bm[9 * a + 3 * j + i][d];
+                out[(9 * k + 3 * j + i) * 3 + d] = v;
+              }
     }
 
     // average distance between opposite faces in direction d (grid_tools.h:11-50), Gauss n x n rule
@@ -282,11 +342,11 @@ namespace dasm
     // merged coefficients JxW * J^-1 J^-T at the n^3 Gauss points: out[comp*n3 + q], comp order
     // xx,xy,xz,yy,yz,zz (operator.h:696-704)
     void
-    merged_coefficients(const int c[3], const Basis1D &b, double *out) const
+    merged_coefficients(const int c[3], const Basis1D &b, double *out, const bool linear = false) const
     {
       const int n = b.n, n3 = n * n * n;
       double    X[27][3];
-      cell_support_points(c, X);
+      cell_support_points(c, X, linear);
       const std::vector<double> q2nodes = {0., 0.5, 1.};
       std::vector<double>       V, D;
       lagrange(q2nodes, b.qp, V, D);

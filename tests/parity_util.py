@@ -5,23 +5,24 @@ import numpy as np
 import dasm_oracle as o
 
 
-def oracle_mesh(pmesh, brick=(4, 4, 4)):
+def oracle_mesh(pmesh, brick=(4, 4, 4), mapping_degree=2):
     mapfun = None
     if pmesh.map_kind == "sine":
         mapfun = o.sine_map
     elif pmesh.map_kind == "kershaw":
         mapfun = o.kershaw_map(pmesh.map_params[0], pmesh.map_params[1])
     mesh = o.StructuredMesh(3, pmesh.n_cells_dir, pmesh.periodic, dirichlet=pmesh.dirichlet, mapfun=mapfun,
-                            lengths=pmesh.length)
+                            lengths=pmesh.length, mapping_degree=mapping_degree)
     mesh.cell_order = o.brick_major_order(pmesh.n_cells_dir, brick)
     return mesh
 
 
-def oracle_problem(pkg, pmesh, op, n_overlap=1, weight_type="symm", dtype=np.float64, check_indices=True, with_fdm=True):
+def oracle_problem(pkg, pmesh, op, n_overlap=1, weight_type="symm", dtype=np.float64, check_indices=True, with_fdm=True,
+                   mapping_degree=2):
     """returns (oracle LaplaceOperator, oracle FDMPreconditioner) in the library's DoF numbering; the numbering
     itself is recomputed by the oracle and compared bit-exactly with the library's compressed indices."""
     k = op.degree
-    mesh = oracle_mesh(pmesh)
+    mesh = oracle_mesh(pmesh, mapping_degree=mapping_degree)
     cd, nd, con, comp = o.number_dofs_owner_cell(mesh, k)
     if check_indices:
         lib_comp = op.compressed_indices(plain=True)  # rows in processing order

@@ -67,6 +67,35 @@ def test_vmult_meshes(pkg, ctx, name, k):
     assert run_vmult(pkg, ctx, MESHES[name], k, "double") < TOL["double"]
 
 
+@pytest.mark.parametrize("name", ["sine", "kershaw", "mixed_aniso"])
+@pytest.mark.parametrize("k,number", [(2, "double"), (4, "double"), (3, "float"), (6, "double")])
+def test_vmult_quadratic_geometry(pkg, ctx, name, k, number):
+    """mapping type "quadratic geometry" (operator.h:1035-1159): Jacobian rebuilt from 27 coefficients per cell."""
+    mesh = pkg.Mesh(ctx, **MESHES[name])
+    op = pkg.LaplaceOperatorMatrixFree(mesh, k, number, mapping_type="quadratic geometry")
+    oop, _ = oracle_problem(pkg, mesh, op, with_fdm=False)
+    x = np.random.default_rng(k).uniform(-1, 1, op.n_dofs())
+    yd = op.initialize_dof_vector()
+    op.vmult(yd, op.to_device(x))
+    assert relerr(op.to_host(yd), oop.vmult(x)) < (1e-12 if number == "double" else 2e-5)
+
+
+@pytest.mark.parametrize("name", ["sine", "kershaw"])
+@pytest.mark.parametrize("k", [2, 4])
+def test_vmult_linear_geometry(pkg, ctx, name, k):
+    """mapping type "linear geometry" (operator.h:916-1033): trilinear map through the 8 cell vertices."""
+    mesh = pkg.Mesh(ctx, **MESHES[name])
+    op = pkg.LaplaceOperatorMatrixFree(mesh, k, "double", mapping_type="linear geometry")
+    oop, _ = oracle_problem(pkg, mesh, op, with_fdm=False, mapping_degree=1)
+    x = np.random.default_rng(k).uniform(-1, 1, op.n_dofs())
+    yd = op.initialize_dof_vector()
+    op.vmult(yd, op.to_device(x))
+    assert relerr(op.to_host(yd), oop.vmult(x)) < 1e-12
+    d = op.initialize_dof_vector()
+    op.compute_inverse_diagonal(d)
+    assert relerr(op.to_host(d), oop.inverse_diagonal()) < 1e-12
+
+
 def test_vmult_merged_on_cartesian_equals_default(pkg, ctx):
     mesh = pkg.Mesh(ctx, (3, 3, 3), periodic=(1, 1, 1))
     a = pkg.LaplaceOperatorMatrixFree(mesh, 3, "double", mapping_type="")
