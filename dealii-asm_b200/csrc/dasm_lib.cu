@@ -706,7 +706,7 @@ launch_fdm_m(dasm_fdm *f, T *dst, const T *src)
     }
   else
     {
-      if constexpr (M >= 4)
+      if constexpr (M >= 3)
         {
           auto kern = fdm_generic_kernel<M, T, 1>;
           CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -714,7 +714,7 @@ launch_fdm_m(dasm_fdm *f, T *dst, const T *src)
                                                          (const T *)w, f->wmode, (int)f->w_pre, (int)f->w_post, op->n_cells);
         }
       else
-        throw std::runtime_error("internal: explicit patch list with m < 4");
+        throw std::runtime_error("explicit patch lists are instantiated for patch sizes >= 3");
     }
   ctx->launches++;
   CUDA_CHECK(cudaGetLastError());
@@ -1815,20 +1815,23 @@ dasm_fdm_create(dasm_op *op, int n_overlap, int sub_mesh_approximation, int weig
   CUDA_CHECK(cudaSetDevice(op->ctx->device));
   DASM_REQUIRE(weight_type >= 0 && weight_type <= 4, "Weighting type is not known!");
   DASM_REQUIRE(weight_sequence >= 0 && weight_sequence <= 3, "weight sequence is not known!");
-  if (!element_centric)
-    throw std::runtime_error("vertex-patch FDM (element centric = false) is not implemented in libdasm yet");
   const int k = op->k;
   n_overlap   = std::min(std::max(n_overlap, 1), k); // precondition.templates.h:195-196
   const Mesh &M = *op->mesh->mesh;
-  if (n_overlap > 1)
-    DASM_REQUIRE(M.n_ranks() == 1, "n overlap > 1 on several ranks is not implemented in libdasm yet");
+  if (n_overlap > 1 || !element_centric)
+    DASM_REQUIRE(M.n_ranks() == 1, "n overlap > 1 / vertex patches on several ranks are not implemented in libdasm yet");
+  if (!element_centric)
+    {
+      DASM_REQUIRE(weight_type != DASM_WEIGHT_RAS, "RAS weighting with vertex patches is not implemented in libdasm yet");
+      DASM_REQUIRE(2 * k - 1 <= 11, "vertex patches are instantiated up to degree 6");
+    }
   auto f             = new dasm_fdm;
   f->op              = op;
   f->n_overlap       = n_overlap;
   f->weight_type     = weight_type;
   f->weight_sequence = weight_sequence;
   f->element_centric = element_centric;
-  f->m               = k - 1 + 2 * n_overlap;
+  f->m               = element_centric ? (k - 1 + 2 * n_overlap) : (2 * k - 1); // matrix_free.h:90-92
   const int m        = f->m;
 
   // 1-D instances, deduplicated like TensorProductMatrixSymmetricSumCollection::finalize
@@ -1854,6 +1857,15 @@ dasm_fdm_create(dasm_op *op, int n_overlap, int sub_mesh_approximation, int weig
               else
                 bt[side] = M.p.dirichlet ? 1 : 2;
             }
+          if (!element_centric)
+            {
+              // vertex patch of the cell's upper corner: own cell + right neighbour, extents replaced by 1 when
+              // there is no neighbour (collect_patch_extend, matrix_free.h:1511-1524)
+              ext[0] = ext[1] != 0.0 ? ext[1] : 1.0;
+              ext[1] = ext[2] != 0.0 ? ext[2] : 1.0;
+              ext[2] = -1.0; // marks the vertex-patch instances in the cache key
+              bt[0] = bt[1] = 0;
+            }
           std::array<uint64_t, 4> key;
           memcpy(&key[0], &ext[0], 8);
           memcpy(&key[1], &ext[1], 8);
@@ -1863,7 +1875,23 @@ dasm_fdm_create(dasm_op *op, int n_overlap, int sub_mesh_approximation, int weig
           if (it == cache.end())
             {
               std::vector<double> Mm, Km, S, lam;
-              laplace_tp_matrix_1d(op->basis, ext, bt, n_overlap, Mm, Km);
+              if (element_centric)
+                laplace_tp_matrix_1d(op->basis, ext, bt, n_overlap, Mm, Km);
+              else
+                {
+                  // include/tensor_product_matrix_creator.h:7-61: two cells glued at the vertex, outer nodes dropped
+                  const int n = k + 1;
+                  Mm.assign(m * m, 0.);
+                  Km.assign(m * m, 0.);
+                  for (int i = 0; i < n - 1; ++i)
+                    for (int j = 0; j < n - 1; ++j)
+                      {
+                        Mm[i * m + j] += op->basis.M_ref[(i + 1) * n + j + 1] * ext[0];
+                        Km[i * m + j] += op->basis.K_ref[(i + 1) * n + j + 1] / ext[0];
+                        Mm[(i + n - 2) * m + j + n - 2] += op->basis.M_ref[i * n + j] * ext[1];
+                        Km[(i + n - 2) * m + j + n - 2] += op->basis.K_ref[i * n + j] / ext[1];
+                      }
+                }
               generalized_eig(m, Mm, Km, S, lam);
               const uint32_t id = (uint32_t)cache.size();
               cache[key]        = id;
@@ -1880,8 +1908,8 @@ dasm_fdm_create(dasm_op *op, int n_overlap, int sub_mesh_approximation, int weig
   f->h_lam       = lam_all;
   f->d_inst      = dev_upload(f->h_inst, op->ctx->stream);
 
-  // explicit patch indices for n_overlap > 1 (dof_tools.h:78-137)
-  if (n_overlap > 1)
+  // explicit patch indices for n_overlap > 1 (dof_tools.h:78-137) and vertex patches (dof_tools.h:206-300)
+  if (n_overlap > 1 || !element_centric)
     {
       const int n = k + 1, n3 = n * n * n, m3 = m * m * m;
       // expand the plain compressed indices of every cell on the host
@@ -1924,7 +1952,48 @@ dasm_fdm_create(dasm_op *op, int n_overlap, int sub_mesh_approximation, int weig
           }
       };
       std::vector<uint32_t> pidx((size_t)op->n_cells * m3, INVALID_INDEX);
-      for (long long c = 0; c < op->n_cells; ++c)
+      for (long long c = 0; c < op->n_cells && !element_centric; ++c)
+        {
+          // the 2x2x2 cells above the cell (collect_cells_for_vertex_patch, matrix_free.h:1490-1509); if one is
+          // missing the whole patch is invalid (dof_tools.h:222-227)
+          const int cc[3] = {M.cell_ijk[c][0], M.cell_ijk[c][1], M.cell_ijk[c][2]};
+          long long cells8[8];
+          bool      all = true;
+          for (int q = 0; q < 8 && all; ++q)
+            {
+              int cur[3] = {cc[0], cc[1], cc[2]};
+              for (int d = 0; d < 3 && all; ++d)
+                if ((q >> d) & 1)
+                  {
+                    int nbc[3];
+                    if (!M.neighbor(cur, d, 1, nbc))
+                      all = false;
+                    else
+                      for (int e = 0; e < 3; ++e)
+                        cur[e] = nbc[e];
+                  }
+              if (all)
+                cells8[q] = cell_of[{cur[0], cur[1], cur[2]}];
+            }
+          if (!all)
+            continue;
+          // positions 1 .. 2k-1 of the (2k+1)^3 lattice of the 8 cells
+          for (int pz = 0; pz < m; ++pz)
+            for (int py = 0; py < m; ++py)
+              for (int px = 0; px < m; ++px)
+                {
+                  const int g[3] = {px + 1, py + 1, pz + 1};
+                  int       q = 0, l[3];
+                  for (int d = 0; d < 3; ++d)
+                    {
+                      const int half = (g[d] > k) ? 1 : 0; // the shared plane g = k is taken from the lower cell
+                      q |= half << d;
+                      l[d] = g[d] - half * k;
+                    }
+                  pidx[(size_t)c * m3 + (pz * m + py) * m + px] = full[(size_t)cells8[q] * n3 + (l[2] * n + l[1]) * n + l[0]];
+                }
+        }
+      for (long long c = 0; c < op->n_cells && element_centric; ++c)
         {
           const int cc[3] = {M.cell_ijk[c][0], M.cell_ijk[c][1], M.cell_ijk[c][2]};
           for (int pz = 0; pz < m; ++pz)

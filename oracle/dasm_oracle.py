@@ -762,6 +762,63 @@ def patch_dof_indices(mesh, k, cell_dofs, n_overlap):
     return out
 
 
+def vertex_patch_dof_indices(mesh, k, cell_dofs):
+    """vertex-patch index lists, include/dof_tools.h:206-300 with the cell selection of
+    collect_cells_for_vertex_patch (include/matrix_free.h:1490-1509): the patch of a cell is the
+    (2k-1)^dim interior of the 2^dim cells above it; all INVALID if one of them does not exist."""
+    dim = mesh.dim
+    n = k + 1
+    m = 2 * k - 1
+    out = np.full((mesh.C, m ** dim), int(INVALID), dtype=np.int64)
+    for c in range(mesh.C):
+        ijk = mesh.cell_ijk(c)
+        cells = []
+        ok = True
+        for q in range(2 ** dim):
+            cur = ijk
+            for d in range(dim):
+                if (q >> d) & 1:
+                    cur = mesh.neighbor(cur, d, 1) if cur is not None else None
+                    if cur is None:
+                        break
+            if cur is None:
+                ok = False
+                break
+            cells.append(mesh.cell_lex(cur))
+        if not ok:
+            continue
+        loc = np.zeros((m,) * dim, dtype=np.int64)
+        for pidx in np.ndindex(*(m,) * dim):
+            p = pidx[::-1]
+            q = 0
+            lex = 0
+            ls = []
+            for d in range(dim):
+                g = p[d] + 1
+                half = 1 if g > k else 0
+                q |= half << d
+                ls.append(g - half * k)
+            for d in reversed(range(dim)):
+                lex = lex * n + ls[d]
+            loc[pidx] = cell_dofs[cells[q], lex]
+        out[c] = loc.reshape(-1)
+    return out
+
+
+def vertex_patch_matrix_1d(M_ref, K_ref, h0, h1):
+    """include/tensor_product_matrix_creator.h:7-61: two cells of extents h0, h1 glued at the patch
+    vertex, outermost nodes dropped."""
+    n = M_ref.shape[0]
+    m = 2 * (n - 1) - 1
+    M = np.zeros((m, m))
+    K = np.zeros((m, m))
+    M[:n - 1, :n - 1] += M_ref[1:, 1:] * h0
+    K[:n - 1, :n - 1] += K_ref[1:, 1:] / h0
+    M[n - 2:, n - 2:] += M_ref[:n - 1, :n - 1] * h1
+    K[n - 2:, n - 2:] += K_ref[:n - 1, :n - 1] / h1
+    return M, K
+
+
 class FDMPreconditioner:
     """ASPoissonPreconditioner restated (include/matrix_free.h:73-1364), element-centred patches.
 
@@ -771,7 +828,7 @@ class FDMPreconditioner:
     """
 
     def __init__(self, mesh, k, cell_dofs, n_dofs, constrained, n_overlap=1, weight_type="symm",
-                 dtype=np.float64, cell_rank=None):
+                 dtype=np.float64, cell_rank=None, element_centric=True):
         self.mesh = mesh
         self.k = k
         self.dim = mesh.dim
@@ -782,11 +839,12 @@ class FDMPreconditioner:
         self.constrained = constrained
         basis = Basis1D(k)
         M_ref, K_ref = basis.reference_mass_stiffness()
-        self.m = k - 1 + 2 * n_overlap
+        self.element_centric = element_centric
+        self.m = (k - 1 + 2 * n_overlap) if element_centric else (2 * k - 1)
         m, dim = self.m, self.dim
         ext = harmonic_patch_extents(mesh, basis)
         self.extents = ext
-        idx = patch_dof_indices(mesh, k, cell_dofs, n_overlap)
+        idx = patch_dof_indices(mesh, k, cell_dofs, n_overlap) if element_centric else vertex_patch_dof_indices(mesh, k, cell_dofs)
         valid = idx != int(INVALID)
         valid &= ~constrained[np.where(valid, idx, 0)]
         self.idx = np.where(valid, idx, 0)
@@ -804,6 +862,14 @@ class FDMPreconditioner:
                         bt.append(INTERNAL)
                     else:
                         bt.append(DIRICHLET if mesh.dirichlet else NEUMANN)
+                if not element_centric:
+                    h0 = ext[c, d, 1] if ext[c, d, 1] != 0 else 1.0   # collect_patch_extend, matrix_free.h:1511-1524
+                    h1 = ext[c, d, 2] if ext[c, d, 2] != 0 else 1.0
+                    key = ("v", h0, h1)
+                    if key not in cache:
+                        cache[key] = generalized_eig(*vertex_patch_matrix_1d(M_ref, K_ref, h0, h1))
+                    self.S[c, d], self.lam[c, d] = cache[key]
+                    continue
                 key = (tuple(ext[c, d]), tuple(bt))
                 if key not in cache:
                     M, K = laplace_tensor_product_matrix_1d(M_ref, K_ref, ext[c, d], bt, n_overlap)

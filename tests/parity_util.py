@@ -18,7 +18,7 @@ def oracle_mesh(pmesh, brick=(4, 4, 4), mapping_degree=2):
 
 
 def oracle_problem(pkg, pmesh, op, n_overlap=1, weight_type="symm", dtype=np.float64, check_indices=True, with_fdm=True,
-                   mapping_degree=2):
+                   mapping_degree=2, element_centric=True):
     """returns (oracle LaplaceOperator, oracle FDMPreconditioner) in the library's DoF numbering; the numbering
     itself is recomputed by the oracle and compared bit-exactly with the library's compressed indices."""
     k = op.degree
@@ -36,5 +36,6 @@ def oracle_problem(pkg, pmesh, op, n_overlap=1, weight_type="symm", dtype=np.flo
     oP = None
     if with_fdm:
         lex_rank = np.arange(mesh.C)  # RAS ownership by lexicographic cell id
-        oP = o.FDMPreconditioner(mesh, k, cd, nd, con, n_overlap, weight_type, dtype=dtype, cell_rank=lex_rank)
+        oP = o.FDMPreconditioner(mesh, k, cd, nd, con, n_overlap, weight_type, dtype=dtype, cell_rank=lex_rank,
+                                 element_centric=element_centric)
     return oop, oP

@@ -205,6 +205,31 @@ def test_fdm_overlap(pkg, ctx, n_overlap, wt):
     assert relerr(op.to_host(zd), oP.vmult(x)) < 1e-11
 
 
+@pytest.mark.parametrize("name,k,wt", [("periodic", 3, "symm"), ("dirichlet", 2, "post"), ("mixed_aniso", 4, "pre"), ("kershaw", 3, "none"),
+                                       ("periodic", 4, "post")])
+def test_fdm_vertex_patch(pkg, ctx, name, k, wt):
+    """fdmv: element centric = false, patches of (2k-1)^3 DoFs around vertices (matrix_free.h:90-92, dof_tools.h:206-300,
+    tensor_product_matrix_creator.h:7-61)."""
+    mesh = pkg.Mesh(ctx, **MESHES[name])
+    op = pkg.LaplaceOperatorMatrixFree(mesh, k, "double")
+    fdm = pkg.create_fdm_preconditioner(op, {"element centric": False, "weighting type": wt})
+    assert fdm.patch_size_1d() == 2 * k - 1
+    oop, oP = oracle_problem(pkg, mesh, op, 1, wt, element_centric=False)
+    x = np.random.default_rng(17).uniform(-1, 1, op.n_dofs())
+    zd = op.initialize_dof_vector()
+    fdm.vmult(zd, op.to_device(x))
+    assert relerr(op.to_host(zd), oP.vmult(x)) < 1e-11
+    # as Chebyshev preconditioner (label cheby-2-1-<wt>-v-c of matrix_free_loop_08)
+    cheb = pkg.PreconditionChebyshev(op, fdm, degree=2, optimize=1)
+    cheb.set_eigenvalues(0.5, 3.0)
+    och = o.Chebyshev(oop, oP, degree=2)
+    och.set_eigenvalues(3.0, 0.5)
+    b = np.random.default_rng(18).uniform(-1, 1, op.n_dofs())
+    xd = op.to_device(x)
+    cheb.step(xd, op.to_device(b))
+    assert relerr(op.to_host(xd), och.step(x, b)) < 1e-11
+
+
 def test_fdm_n_instances_cartesian(pkg, ctx):
     mesh = pkg.Mesh(ctx, (4, 4, 4), periodic=(1, 1, 1))
     op = pkg.LaplaceOperatorMatrixFree(mesh, 4, "double")

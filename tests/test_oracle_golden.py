@@ -136,3 +136,31 @@ def test_compressed_indices_round_trip():
         cd, nd, con, comp = o.number_dofs_owner_cell(mesh, k)
         assert np.array_equal(o.expand_compressed(comp, k, dim), cd)
         assert sorted(set(cd.reshape(-1).tolist())) == list(range(nd))
+
+
+def test_vertex_patch_fdm_equals_restricted_matrix_inverse():
+    """fdm_01.cc:148-177 for vertex patches (tensor_product_matrix_creator.h:7-61, dof_tools.h:206-300): on a Cartesian mesh
+    the FDM inverse of the (2k-1)^3 vertex patch equals the inverse of the restricted assembled matrix."""
+    k, nc = 2, (3, 3, 3)
+    mesh = o.StructuredMesh(3, nc, (False,) * 3, dirichlet=True)
+    mesh.cell_order = o.brick_major_order(nc)
+    cd, nd, con, comp = o.number_dofs_owner_cell(mesh, k)
+    b = o.Basis1D(k)
+    G = o.merged_coefficients(mesh.jacobians(b), b, 3)
+    op = o.LaplaceOperator(3, k, cd, nd, con, G)
+    P = o.FDMPreconditioner(mesh, k, cd, nd, con, 1, "none", element_centric=False)
+    A = op.dense()
+    for c in (0, 4, 13):
+        sel = P.mask[c] > 0
+        if not sel.any():
+            continue
+        ii = P.idx[c][sel]
+        Ainv = np.linalg.inv(A[np.ix_(ii, ii)])
+        B = np.zeros_like(Ainv)
+        for j in range(len(ii)):
+            e = np.zeros((mesh.C, P.m ** 3))
+            e[c, np.nonzero(sel)[0][j]] = 1
+            B[:, j] = P.apply_inverse(e)[c][sel]
+        assert np.allclose(B, Ainv, rtol=1e-10, atol=1e-12)
+    # cells without a complete 2x2x2 neighbourhood have an empty patch
+    assert not (P.mask[mesh.C - 1] > 0).any()
