@@ -575,9 +575,8 @@ launch_laplace_brick(dasm_op *op, T *dst, const T *src, const Epilogue<T> &epi, 
 {
   dasm_ctx *   ctx   = op->ctx;
   const int    n_ops = epilogue_n_operands(epi);
-  const size_t smem  = BrickGeom<K, BZ>::template smem_bytes<T>(n_ops, op->maps.own != nullptr);
+  const size_t smem  = BrickGeom<K, BZ>::template smem_bytes<T>(n_ops, BZ == 4);
   brick_pre_exchange<T>(op, dst, src, shared_mode);
-  static const int dbg = getenv("DASM_DEBUG_SKIP") ? atoi(getenv("DASM_DEBUG_SKIP")) : 0; // timing experiments only
   {
     KernelTimer timer(ctx, KC_LAPLACE);
     if (op->geom_mode == 0)
@@ -585,21 +584,21 @@ launch_laplace_brick(dasm_op *op, T *dst, const T *src, const Epilogue<T> &epi, 
         auto      kern = laplace_brick_kernel<K, T, BZ, 0>;
         const int grid = brick_grid<K, BZ, T>(op, kern, smem);
         kern<<<grid, BrickGeom<K, BZ>::NT, smem, ctx->stream>>>(src, dst, (T *)op->d_acc, epi, op->d_cidx, op->d_bricks, op->n_bricks,
-                                                                 (const T *)nullptr, op->cart, n_ops, shared_mode, ni, op->maps, dbg);
+                                                                 (const T *)nullptr, op->cart, n_ops, shared_mode, ni, op->maps);
       }
     else if (op->geom_mode == 1)
       {
         auto      kern = laplace_brick_kernel<K, T, BZ, 1>;
         const int grid = brick_grid<K, BZ, T>(op, kern, smem);
         kern<<<grid, BrickGeom<K, BZ>::NT, smem, ctx->stream>>>(src, dst, (T *)op->d_acc, epi, op->d_cidx, op->d_bricks, op->n_bricks,
-                                                                 (const T *)op->d_geom, op->cart, n_ops, shared_mode, ni, op->maps, dbg);
+                                                                 (const T *)op->d_geom, op->cart, n_ops, shared_mode, ni, op->maps);
       }
     else
       {
         auto      kern = laplace_brick_kernel<K, T, BZ, 2>;
         const int grid = brick_grid<K, BZ, T>(op, kern, smem);
         kern<<<grid, BrickGeom<K, BZ>::NT, smem, ctx->stream>>>(src, dst, (T *)op->d_acc, epi, op->d_cidx, op->d_bricks, op->n_bricks,
-                                                                 (const T *)op->d_qcoef, op->cart, n_ops, shared_mode, ni, op->maps, dbg);
+                                                                 (const T *)op->d_qcoef, op->cart, n_ops, shared_mode, ni, op->maps);
       }
     ctx->launches++;
   }
@@ -734,7 +733,7 @@ launch_fdm_brick(dasm_fdm *f, T *dst, const T *src, const Epilogue<T> &epi, cons
   dasm_op *    op    = f->op;
   dasm_ctx *   ctx   = op->ctx;
   const int    n_ops = epilogue_n_operands(epi);
-  const size_t smem  = BrickGeom<K, BZ>::template smem_bytes<T>(n_ops, op->maps.own != nullptr);
+  const size_t smem  = BrickGeom<K, BZ>::template smem_bytes<T>(n_ops, BZ == 4);
   brick_pre_exchange<T>(op, dst, src, shared_mode);
   {
     KernelTimer timer(ctx, KC_FDM);
@@ -1295,7 +1294,7 @@ dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping
         }
         // ---- per-variant tile maps for the coalesced gather / store (kernel brick == mesh brick only)
         op->maps.own = nullptr;
-        if (op->brick_bz == 4 && !(getenv("DASM_NO_LINEAR") && getenv("DASM_NO_LINEAR")[0] == '1'))
+        if (op->brick_bz == 4)
           {
             const int k = degree, n = k + 1, TX = 4 * k + 1, TY = 4 * k + 1, TZ = 4 * k + 1, NPTS = TX * TY * TZ;
             const int CS = (n * n * n) | 1;
@@ -1455,8 +1454,7 @@ dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping
                 op->d_bricks = dev_upload(bricks, ctx->stream);
               }
             else
-              for (BrickDesc &bd : bricks)
-                bd.variant = 0xFFFFu;
+              op->use_brick = false; // no consistent tile maps: use the generic kernels
             (void)TZ;
           }
         CUDA_CHECK(cudaMalloc(&op->d_acc, std::max<size_t>(1, (size_t)op->n_vec) * op->esize()));

@@ -145,7 +145,7 @@ namespace dasm
     smem_bytes(int n_ops, bool lin)
     {
       return (size_t)(1 + n_ops) * NPTS * sizeof(T) + (size_t)NCELLS * CS * sizeof(T) +
-             (size_t)(lin ? NFOREIGN : NPTS) * sizeof(uint32_t) + (size_t)2 * NCELLS * 27 * sizeof(uint32_t) +
+             (size_t)(lin ? 2 * NFOREIGN : NPTS) * sizeof(uint32_t) + (size_t)2 * NCELLS * 27 * sizeof(uint32_t) +
              (lin ? (size_t)(NPTS + NFOREIGN) * sizeof(uint32_t) : 0);
     }
   };
@@ -492,7 +492,7 @@ namespace dasm
   __device__ __forceinline__ void
   brick_store_lin(const BrickDesc &bd, const uint32_t *own, const uint32_t *foreign, const int n_for, const T *slots, const T *ops0,
                   const T *ops1, const uint32_t *gidx_f, T *__restrict__ dst, T *__restrict__ acc, const Epilogue<T> &epi,
-                  const int shared_mode)
+                  const int shared_mode, const int dbg = 0)
   {
     using G           = BrickGeom<k, BZ>;
     constexpr int n   = k + 1;
@@ -513,6 +513,8 @@ namespace dasm
         const T y        = slot_sum(slots, e, dx, dy, dz);
         dst[bd.base + i] = epilogue_compute(epi, y, need0 ? ops0[i] : T(0), need1 ? ops1[i] : T(0));
       }
+    if (dbg & 32)
+      return;
     // own DoFs on shared faces: coalesced red.add
     for (int i = bd.npriv + threadIdx.x; i < n_own; i += G::NT)
       {
@@ -680,8 +682,7 @@ namespace dasm
                        const int n_ops,
                        const int shared_mode,
                        const NextInit<T> ni,
-                       const BrickMaps maps,
-                       const int dbg)
+                       const BrickMaps maps)
   {
     using G         = BrickGeom<k, BZ>;
     constexpr int n = k + 1;
@@ -692,7 +693,7 @@ namespace dasm
     T *       slots  = tile + (1 + n_ops) * G::NPTS;
     uint32_t *gidx   = reinterpret_cast<uint32_t *>(slots + G::NCELLS * G::CS);
     const bool lin_mode = (maps.own != nullptr);
-    uint32_t * s_cidx   = gidx + (lin_mode ? G::NFOREIGN : G::NPTS); // two buffers of NCELLS * 27
+    uint32_t * s_cidx   = gidx + (lin_mode ? 2 * G::NFOREIGN : G::NPTS); // two buffers of NCELLS * 27
     uint32_t * s_own    = s_cidx + 2 * G::NCELLS * 27;                // lin: staged maps of the current variant
     uint32_t * s_for    = s_own + G::NPTS;
     int        cur_variant = -1, n_for = 0;
@@ -702,50 +703,58 @@ namespace dasm
     const int   c = threadIdx.x % G::NCELLS; // cell in brick (lane-major: conflict-free slot access)
     const int   t = threadIdx.x / G::NCELLS; // plane index (warp-uniform)
 
-    if (blockIdx.x < n_bricks)
-      brick_stage_cidx_async<k, BZ>(bricks[blockIdx.x], cidx, s_cidx);
+    // Software pipeline over the bricks of this block (LIN: kernel brick == mesh brick, coalesced access through
+    // the tile maps).  The tile is dead after phase A, so the gather of the NEXT brick is issued right after
+    // phase A and overlaps with phases B-E and the store of the current brick.  cp.async groups per iteration:
+    //   [ops(i)] at the top, [tile(i+1)] and [cidx(i+2)] after phase A.
+    constexpr bool LIN = (BZ == 4);
+    if (blockIdx.x >= n_bricks)
+      return;
+    brick_stage_cidx_async<k, BZ>(bricks[blockIdx.x], cidx, s_cidx);
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
     int       buf = 0;
-    BrickDesc bd_next;
-    if (blockIdx.x < n_bricks)
-      bd_next = bricks[blockIdx.x];
+    BrickDesc bd_next = bricks[blockIdx.x];
+    bool      late_tile = false;
+    auto      stage_maps = [&](const int variant) {
+      cur_variant = variant;
+      n_for       = maps.n_foreign[cur_variant];
+      var_flags   = maps.flags[cur_variant];
+      for (int i = threadIdx.x; i < G::NPTS; i += G::NT)
+        s_own[i] = maps.own[(size_t)cur_variant * maps.stride + i];
+      for (int i = threadIdx.x; i < n_for; i += G::NT)
+        s_for[i] = maps.foreign[(size_t)cur_variant * maps.stride + i];
+      __syncthreads();
+    };
+    if (LIN)
+      {
+        stage_maps(bd_next.variant);
+        brick_issue_loads_lin<k, BZ, T>(bd_next, s_own, s_for, n_for, var_flags, s_cidx, tile, gidx, src);
+        cp_async_commit(); // [tile(b0)]
+        if (blockIdx.x + gridDim.x < (unsigned)n_bricks)
+          brick_stage_cidx_async<k, BZ>(bricks[blockIdx.x + gridDim.x], cidx, s_cidx + G::NCELLS * 27);
+        cp_async_commit(); // [cidx(b1)]
+      }
     for (int bi = blockIdx.x; bi < n_bricks; bi += gridDim.x, buf ^= 1)
       {
-        const BrickDesc bd     = bd_next;
-        if (bi + (int)gridDim.x < n_bricks)
+        const BrickDesc bd       = bd_next;
+        const bool      has_next = bi + (int)gridDim.x < n_bricks;
+        if (has_next)
           bd_next = bricks[bi + gridDim.x]; // descriptor of the next brick: latency hidden behind this brick
-        const int       ncells = bd.b[0] * bd.b[1] * bd.b[2];
+        const int       ncells   = bd.b[0] * bd.b[1] * bd.b[2];
         const uint32_t *cur_cidx = s_cidx + buf * (G::NCELLS * 27);
+        uint32_t *      cur_gidx = LIN ? gidx + buf * G::NFOREIGN : gidx;
         T               ni_a[NextInitRegs<k, BZ>::IT], ni_b[NextInitRegs<k, BZ>::IT];
         brick_next_init_load<k, BZ, T>(bd, ni, ni_a, ni_b);
-        // group 1: source values, group 2: epilogue operands, group 3: indices of the next brick
-        const bool lin = lin_mode;
-        if (lin && (int)bd.variant != cur_variant)
+        if (LIN)
           {
-            // stage the tile maps of this brick's variant (periodic meshes have a single variant)
-            cur_variant = bd.variant;
-            n_for       = maps.n_foreign[cur_variant];
-            var_flags   = maps.flags[cur_variant];
-            for (int i = threadIdx.x; i < G::NPTS; i += G::NT)
-              s_own[i] = maps.own[(size_t)cur_variant * maps.stride + i];
-            for (int i = threadIdx.x; i < n_for; i += G::NT)
-              s_for[i] = maps.foreign[(size_t)cur_variant * maps.stride + i];
-            __syncthreads();
-          }
-        if (dbg & 1)
-          {
-            cp_async_commit();
-            cp_async_commit();
-          }
-        else if (lin)
-          {
-            brick_issue_loads_lin<k, BZ, T>(bd, s_own, s_for, n_for, var_flags, cur_cidx, tile, gidx, src);
-            cp_async_commit();
-            if (!(dbg & 16))
-              brick_issue_ops_lin<k, BZ, T>(bd, ops0, ops1, epi);
-            cp_async_commit();
+            brick_issue_ops_lin<k, BZ, T>(bd, ops0, ops1, epi);
+            cp_async_commit(); // [ops(i)]
+            if (late_tile)
+              cp_async_wait<1>(); // pending: ops(i), tile(i) issued late
+            else
+              cp_async_wait<2>(); // pending: ops(i), cidx(i+1), tile(i)
           }
         else
           {
@@ -753,16 +762,15 @@ namespace dasm
             cp_async_commit();
             brick_issue_loads_ops<k, BZ, T>(bd, gidx, ops0, ops1, epi);
             cp_async_commit();
+            if (has_next)
+              brick_stage_cidx_async<k, BZ>(bd_next, cidx, s_cidx + (buf ^ 1) * (G::NCELLS * 27));
+            cp_async_commit();
+            cp_async_wait<2>();
           }
-        if (bi + (int)gridDim.x < n_bricks)
-          brick_stage_cidx_async<k, BZ>(bd_next, cidx, s_cidx + (buf ^ 1) * (G::NCELLS * 27));
-        cp_async_commit();
-        cp_async_wait<2>();
-        if (!(dbg & 4))
-          brick_next_init_store<k, BZ, T>(bd, ni, ni_a, ni_b);
+        brick_next_init_store<k, BZ, T>(bd, ni, ni_a, ni_b);
         __syncthreads();
 
-        const bool act = (c < ncells) && !(dbg & 2);
+        const bool act = (c < ncells);
         const int  cx = c % bd.b[0], cy = (c / bd.b[0]) % bd.b[1], cz = c / (bd.b[0] * bd.b[1]);
         T *        S  = slots + c * G::CS;
         T          r[n][n]; // partial result of the x/z directions, plane y = t, [z][x]
@@ -785,7 +793,21 @@ namespace dasm
               for (int x = 0; x < n; ++x)
                 S[(t * n + y) * n + x] = v[y][x];
           }
+        if (LIN)
+          cp_async_wait<1>(); // indices of the next brick (staged one iteration ago); pending: ops(i)
         __syncthreads();
+        if (LIN)
+          {
+            // the tile is dead from here on: gather the next brick into it while this brick is computed
+            late_tile = has_next && ((int)bd_next.variant != cur_variant);
+            if (has_next && !late_tile)
+              brick_issue_loads_lin<k, BZ, T>(bd_next, s_own, s_for, n_for, var_flags, s_cidx + (buf ^ 1) * (G::NCELLS * 27), tile,
+                                              gidx + (buf ^ 1) * G::NFOREIGN, src);
+            cp_async_commit(); // [tile(i+1)]
+            if (bi + 2 * (int)gridDim.x < n_bricks)
+              brick_stage_cidx_async<k, BZ>(bricks[bi + 2 * gridDim.x], cidx, s_cidx + buf * (G::NCELLS * 27));
+            cp_async_commit(); // [cidx(i+2)]
+          }
         if (GEOM == 0)
           {
             // phase B: plane y = t, [z][x]: interpolate in z; x and z parts of the Laplacian
@@ -1027,17 +1049,32 @@ namespace dasm
               for (int x = 0; x < n; ++x)
                 S[(t * n + y) * n + x] = v[y][x];
           }
-        cp_async_wait<1>(); // epilogue operands have landed
+        if (LIN)
+          cp_async_wait<2>(); // epilogue operands have landed; pending: cidx(i+2), tile(i+1)
+        else
+          cp_async_wait<1>();
         __syncthreads();
-        if (dbg & 8)
-          {
-          }
-        else if (lin)
-          brick_store_lin<k, BZ, T>(bd, s_own, s_for, n_for, slots, ops0, ops1, gidx, dst, acc, epi, shared_mode);
+        if (LIN)
+          brick_store_lin<k, BZ, T>(bd, s_own, s_for, n_for, slots, ops0, ops1, cur_gidx, dst, acc, epi, shared_mode);
         else
           brick_reduce_store<k, BZ, T>(bd, slots, ops0, ops1, gidx, dst, acc, epi, shared_mode);
-        cp_async_wait<0>(); // indices of the next brick
-        __syncthreads();
+        if (LIN)
+          {
+            if (late_tile)
+              {
+                // the next brick has another tile-map variant: its maps can only be staged once this brick is stored
+                __syncthreads();
+                stage_maps(bd_next.variant);
+                brick_issue_loads_lin<k, BZ, T>(bd_next, s_own, s_for, n_for, var_flags, s_cidx + (buf ^ 1) * (G::NCELLS * 27), tile,
+                                                gidx + (buf ^ 1) * G::NFOREIGN, src);
+                cp_async_commit();
+              }
+          }
+        else
+          {
+            cp_async_wait<0>(); // indices of the next brick
+            __syncthreads();
+          }
       }
   }
 
@@ -1072,7 +1109,7 @@ namespace dasm
     T *       slots  = tile + (1 + n_ops) * G::NPTS;
     uint32_t *gidx   = reinterpret_cast<uint32_t *>(slots + G::NCELLS * G::CS);
     const bool lin_mode = (maps.own != nullptr);
-    uint32_t * s_cidx   = gidx + (lin_mode ? G::NFOREIGN : G::NPTS); // two buffers of NCELLS * 27
+    uint32_t * s_cidx   = gidx + (lin_mode ? 2 * G::NFOREIGN : G::NPTS); // two buffers of NCELLS * 27
     uint32_t * s_own    = s_cidx + 2 * G::NCELLS * 27;                // lin: staged maps of the current variant
     uint32_t * s_for    = s_own + G::NPTS;
     int        cur_variant = -1, n_for = 0;
@@ -1092,43 +1129,58 @@ namespace dasm
     if (threadIdx.x < 3)
       s_tri[threadIdx.x] = 0xFFFFFFFFu;
 
-    if (blockIdx.x < n_bricks)
-      brick_stage_cidx_async<k, BZ>(bricks[blockIdx.x], cidx, s_cidx);
+    // Software pipeline over the bricks of this block (LIN: kernel brick == mesh brick, coalesced access through
+    // the tile maps).  The tile is dead after phase A, so the gather of the NEXT brick is issued right after
+    // phase A and overlaps with phases B-E and the store of the current brick.  cp.async groups per iteration:
+    //   [ops(i)] at the top, [tile(i+1)] and [cidx(i+2)] after phase A.
+    constexpr bool LIN = (BZ == 4);
+    if (blockIdx.x >= n_bricks)
+      return;
+    brick_stage_cidx_async<k, BZ>(bricks[blockIdx.x], cidx, s_cidx);
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
     int       buf = 0;
-    BrickDesc bd_next;
-    if (blockIdx.x < n_bricks)
-      bd_next = bricks[blockIdx.x];
+    BrickDesc bd_next = bricks[blockIdx.x];
+    bool      late_tile = false;
+    auto      stage_maps = [&](const int variant) {
+      cur_variant = variant;
+      n_for       = maps.n_foreign[cur_variant];
+      var_flags   = maps.flags[cur_variant];
+      for (int i = threadIdx.x; i < G::NPTS; i += G::NT)
+        s_own[i] = maps.own[(size_t)cur_variant * maps.stride + i];
+      for (int i = threadIdx.x; i < n_for; i += G::NT)
+        s_for[i] = maps.foreign[(size_t)cur_variant * maps.stride + i];
+      __syncthreads();
+    };
+    if (LIN)
+      {
+        stage_maps(bd_next.variant);
+        brick_issue_loads_lin<k, BZ, T>(bd_next, s_own, s_for, n_for, var_flags, s_cidx, tile, gidx, src);
+        cp_async_commit(); // [tile(b0)]
+        if (blockIdx.x + gridDim.x < (unsigned)n_bricks)
+          brick_stage_cidx_async<k, BZ>(bricks[blockIdx.x + gridDim.x], cidx, s_cidx + G::NCELLS * 27);
+        cp_async_commit(); // [cidx(b1)]
+      }
     for (int bi = blockIdx.x; bi < n_bricks; bi += gridDim.x, buf ^= 1)
       {
-        const BrickDesc bd     = bd_next;
-        if (bi + (int)gridDim.x < n_bricks)
+        const BrickDesc bd       = bd_next;
+        const bool      has_next = bi + (int)gridDim.x < n_bricks;
+        if (has_next)
           bd_next = bricks[bi + gridDim.x]; // descriptor of the next brick: latency hidden behind this brick
-        const int       ncells = bd.b[0] * bd.b[1] * bd.b[2];
+        const int       ncells   = bd.b[0] * bd.b[1] * bd.b[2];
         const uint32_t *cur_cidx = s_cidx + buf * (G::NCELLS * 27);
+        uint32_t *      cur_gidx = LIN ? gidx + buf * G::NFOREIGN : gidx;
         T               ni_a[NextInitRegs<k, BZ>::IT], ni_b[NextInitRegs<k, BZ>::IT];
         brick_next_init_load<k, BZ, T>(bd, ni, ni_a, ni_b);
-        const bool lin = lin_mode;
-        if (lin && (int)bd.variant != cur_variant)
+        if (LIN)
           {
-            // stage the tile maps of this brick's variant (periodic meshes have a single variant)
-            cur_variant = bd.variant;
-            n_for       = maps.n_foreign[cur_variant];
-            var_flags   = maps.flags[cur_variant];
-            for (int i = threadIdx.x; i < G::NPTS; i += G::NT)
-              s_own[i] = maps.own[(size_t)cur_variant * maps.stride + i];
-            for (int i = threadIdx.x; i < n_for; i += G::NT)
-              s_for[i] = maps.foreign[(size_t)cur_variant * maps.stride + i];
-            __syncthreads();
-          }
-        if (lin)
-          {
-            brick_issue_loads_lin<k, BZ, T>(bd, s_own, s_for, n_for, var_flags, cur_cidx, tile, gidx, src);
-            cp_async_commit();
             brick_issue_ops_lin<k, BZ, T>(bd, ops0, ops1, epi);
-            cp_async_commit();
+            cp_async_commit(); // [ops(i)]
+            if (late_tile)
+              cp_async_wait<1>(); // pending: ops(i), tile(i) issued late
+            else
+              cp_async_wait<2>(); // pending: ops(i), cidx(i+1), tile(i)
           }
         else
           {
@@ -1136,11 +1188,11 @@ namespace dasm
             cp_async_commit();
             brick_issue_loads_ops<k, BZ, T>(bd, gidx, ops0, ops1, epi);
             cp_async_commit();
+            if (has_next)
+              brick_stage_cidx_async<k, BZ>(bd_next, cidx, s_cidx + (buf ^ 1) * (G::NCELLS * 27));
+            cp_async_commit();
+            cp_async_wait<2>();
           }
-        if (bi + (int)gridDim.x < n_bricks)
-          brick_stage_cidx_async<k, BZ>(bd_next, cidx, s_cidx + (buf ^ 1) * (G::NCELLS * 27));
-        cp_async_commit();
-        cp_async_wait<2>();
         brick_next_init_store<k, BZ, T>(bd, ni, ni_a, ni_b);
         __syncthreads();
 
@@ -1219,7 +1271,21 @@ namespace dasm
               for (int x = 0; x < n; ++x)
                 S[(t * n + y) * n + x] = v[y][x];
           }
+        if (LIN)
+          cp_async_wait<1>(); // indices of the next brick (staged one iteration ago); pending: ops(i)
         __syncthreads();
+        if (LIN)
+          {
+            // the tile is dead from here on: gather the next brick into it while this brick is computed
+            late_tile = has_next && ((int)bd_next.variant != cur_variant);
+            if (has_next && !late_tile)
+              brick_issue_loads_lin<k, BZ, T>(bd_next, s_own, s_for, n_for, var_flags, s_cidx + (buf ^ 1) * (G::NCELLS * 27), tile,
+                                              gidx + (buf ^ 1) * G::NFOREIGN, src);
+            cp_async_commit(); // [tile(i+1)]
+            if (bi + 2 * (int)gridDim.x < n_bricks)
+              brick_stage_cidx_async<k, BZ>(bricks[bi + 2 * gridDim.x], cidx, s_cidx + buf * (G::NCELLS * 27));
+            cp_async_commit(); // [cidx(i+2)]
+          }
         // phase B: plane y = t, [z][x]: S2^T in z, scale by 1/(l0[x] + l1[t] + l2[z]), S2 in z, S0 in x
         if (act)
           {
@@ -1302,14 +1368,32 @@ namespace dasm
               for (int x = 0; x < n; ++x)
                 S[(t * n + y) * n + x] = v[y][x];
           }
-        cp_async_wait<1>();
+        if (LIN)
+          cp_async_wait<2>(); // epilogue operands have landed; pending: cidx(i+2), tile(i+1)
+        else
+          cp_async_wait<1>();
         __syncthreads();
-        if (lin)
-          brick_store_lin<k, BZ, T>(bd, s_own, s_for, n_for, slots, ops0, ops1, gidx, dst, acc, epi, shared_mode);
+        if (LIN)
+          brick_store_lin<k, BZ, T>(bd, s_own, s_for, n_for, slots, ops0, ops1, cur_gidx, dst, acc, epi, shared_mode);
         else
           brick_reduce_store<k, BZ, T>(bd, slots, ops0, ops1, gidx, dst, acc, epi, shared_mode);
-        cp_async_wait<0>();
-        __syncthreads();
+        if (LIN)
+          {
+            if (late_tile)
+              {
+                // the next brick has another tile-map variant: its maps can only be staged once this brick is stored
+                __syncthreads();
+                stage_maps(bd_next.variant);
+                brick_issue_loads_lin<k, BZ, T>(bd_next, s_own, s_for, n_for, var_flags, s_cidx + (buf ^ 1) * (G::NCELLS * 27), tile,
+                                                gidx + (buf ^ 1) * G::NFOREIGN, src);
+                cp_async_commit();
+              }
+          }
+        else
+          {
+            cp_async_wait<0>(); // indices of the next brick
+            __syncthreads();
+          }
       }
   }
 
