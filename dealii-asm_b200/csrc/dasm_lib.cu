@@ -310,6 +310,9 @@ struct dasm_fdm
   void *    d_lam    = nullptr;
   void *    d_wvec   = nullptr; // global weight vector (owned+ghost)
   void *    d_cw     = nullptr; // compressed weights [cell][27] or per-entry [cell][m^3]
+  uint8_t * d_cwcode = nullptr; // brick kernel: weight codes [cell][32] (code = valence, 0 = weight 0)
+  double    wtab[16] = {0};     // weight value per code
+  uint4 *   d_brick_tri = nullptr; // per kernel brick: instance triple of the first cell + uniform flag
   uint32_t *d_pidx   = nullptr; // explicit patch index list for n_overlap > 1
   int       wmode    = 0;       // kernel weight mode
   bool      w_pre = false, w_post = false;
@@ -735,13 +738,17 @@ launch_fdm_brick(dasm_fdm *f, T *dst, const T *src, const Epilogue<T> &epi, cons
   const int    n_ops = epilogue_n_operands(epi);
   const size_t smem  = BrickGeom<K, BZ>::template smem_bytes<T>(n_ops, BZ == 4);
   brick_pre_exchange<T>(op, dst, src, shared_mode);
+  static const int dbg = getenv("DASM_DEBUG_SKIP") ? atoi(getenv("DASM_DEBUG_SKIP")) : 0; // timing experiments only
+  WeightTable<T>   wt;
+  for (int i = 0; i < 16; ++i)
+    wt.v[i] = (T)f->wtab[i];
   {
     KernelTimer timer(ctx, KC_FDM);
     auto        kern = fdm_brick_kernel<K, T, BZ>;
     const int   grid = brick_grid<K, BZ, T>(op, kern, smem);
     kern<<<grid, BrickGeom<K, BZ>::NT, smem, ctx->stream>>>(src, dst, (T *)op->d_acc, epi, op->d_cidx, op->d_bricks, op->n_bricks, f->d_inst,
-                                                             (const T *)f->d_S, (const T *)f->d_lam, (const T *)(f->wmode == 1 ? f->d_cw : nullptr),
-                                                             (int)f->w_pre, (int)f->w_post, n_ops, shared_mode, ni, op->maps);
+                                                             (const T *)f->d_S, (const T *)f->d_lam, (const uint8_t *)(f->wmode == 1 ? f->d_cwcode : nullptr), wt, f->d_brick_tri,
+                                                             (int)f->w_pre, (int)f->w_post, n_ops, shared_mode, ni, op->maps, dbg);
     ctx->launches++;
   }
   CUDA_CHECK(cudaGetLastError());
@@ -2107,6 +2114,68 @@ dasm_fdm_create(dasm_op *op, int n_overlap, int sub_mesh_approximation, int weig
         }
     }
   DISPATCH_TYPE(op->ntype, fdm_setup_device<T>(f, S_all, lam_all, ras_cw));
+  if (op->use_brick && f->d_pidx == nullptr)
+    {
+      // weight codes for the brick kernel: every compressed weight is a function of the integer patch valence of
+      // its entity (1/v, 1/sqrt(v), RAS 0/1), so 1 byte per entity + a 16-entry table replace 27 numbers per cell
+      if (f->wmode == 1)
+        {
+          std::vector<double> cw((size_t)op->n_cells * 27);
+          if (op->ntype == DASM_F64)
+            CUDA_CHECK(cudaMemcpy(cw.data(), f->d_cw, cw.size() * sizeof(double), cudaMemcpyDeviceToHost));
+          else
+            {
+              std::vector<float> tmp(cw.size());
+              CUDA_CHECK(cudaMemcpy(tmp.data(), f->d_cw, tmp.size() * sizeof(float), cudaMemcpyDeviceToHost));
+              cw.assign(tmp.begin(), tmp.end());
+            }
+          std::vector<uint8_t> codes((size_t)op->n_cells * 32, 0);
+          bool                 ok = true;
+          bool                 seen[16] = {false};
+          for (size_t i = 0; i < cw.size() && ok; ++i)
+            {
+              const double w = cw[i];
+              int          code = 0;
+              if (w != 0.0)
+                {
+                  const double v = (weight_type == DASM_WEIGHT_SYMM) ? 1.0 / (w * w) : 1.0 / w;
+                  code           = (int)std::lround(v);
+                  if (code < 1 || code > 15)
+                    ok = false;
+                }
+              if (ok)
+                {
+                  if (!seen[code])
+                    {
+                      seen[code]    = true;
+                      f->wtab[code] = w;
+                    }
+                  else if (f->wtab[code] != w)
+                    ok = false;
+                  codes[(i / 27) * 32 + (i % 27)] = (uint8_t)code;
+                }
+            }
+          DASM_REQUIRE(ok, "internal: compressed weights are not a function of the patch valence");
+          f->d_cwcode = dev_upload(codes, op->ctx->stream);
+        }
+      // per kernel brick: instance triple of the first cell, and whether all cells of the brick share it
+      std::vector<BrickDesc> bricks(op->n_bricks);
+      CUDA_CHECK(cudaMemcpy(bricks.data(), op->d_bricks, bricks.size() * sizeof(BrickDesc), cudaMemcpyDeviceToHost));
+      std::vector<uint4> tri(op->n_bricks);
+      for (int b = 0; b < op->n_bricks; ++b)
+        {
+          const BrickDesc &bd = bricks[b];
+          const uint32_t * i0 = f->h_inst.data() + (size_t)bd.first_cell * 3;
+          bool             uniform = true;
+          const int        nc = bd.b[0] * bd.b[1] * bd.b[2];
+          for (int c = 1; c < nc && uniform; ++c)
+            for (int d = 0; d < 3; ++d)
+              if (i0[c * 3 + d] != i0[d])
+                uniform = false;
+          tri[b] = make_uint4(i0[0], i0[1], i0[2], uniform ? 1u : 0u);
+        }
+      f->d_brick_tri = dev_upload(tri, op->ctx->stream);
+    }
   *out = f;
   DASM_API_END
 }
@@ -2123,6 +2192,8 @@ dasm_fdm_destroy(dasm_fdm *f)
   cudaFree(f->d_lam);
   cudaFree(f->d_wvec);
   cudaFree(f->d_cw);
+  cudaFree(f->d_cwcode);
+  cudaFree(f->d_brick_tri);
   cudaFree(f->d_pidx);
   delete f;
   DASM_API_END

@@ -47,6 +47,13 @@ namespace dasm
     int             stride;
   };
 
+  // compressed weights as codes: code = patch valence of the entity (0: weight 0), value from this table
+  template <typename T>
+  struct WeightTable
+  {
+    T v[16];
+  };
+
   // how contributions to DoFs on shared brick faces are combined
   enum
   {
@@ -505,7 +512,7 @@ namespace dasm
     const T         sh_a   = (shared_mode == SHARED_DIRECT) ? alpha : T(1);
     // private DoFs: fused epilogue, coalesced plain stores
 #pragma unroll 4
-    for (int i = threadIdx.x; i < bd.npriv; i += G::NT)
+    for (int i = threadIdx.x; i < ((dbg & 8) ? 0 : (int)bd.npriv); i += G::NT)
       {
         const uint32_t e = own[i];
         if (e == MAP_UNUSED)
@@ -514,6 +521,8 @@ namespace dasm
         dst[bd.base + i] = epilogue_compute(epi, y, need0 ? ops0[i] : T(0), need1 ? ops1[i] : T(0));
       }
     if (dbg & 32)
+      return;
+    if (dbg & 8)
       return;
     // own DoFs on shared faces: coalesced red.add
     for (int i = bd.npriv + threadIdx.x; i < n_own; i += G::NT)
@@ -1091,13 +1100,16 @@ namespace dasm
                    const uint32_t *__restrict__ inst,
                    const T *__restrict__ Smat,
                    const T *__restrict__ lam,
-                   const T *__restrict__ cw, // [cell][27] or nullptr
+                   const uint8_t *__restrict__ cw, // weight codes [cell][32] (27 used) or nullptr
+                   const WeightTable<T> wtab,      // weight value of every code
+                   const uint4 *__restrict__ brick_tri, // per brick: instance triple of its first cell, w = all cells equal
                    const int w_pre,
                    const int w_post,
                    const int n_ops,
                    const int shared_mode,
                    const NextInit<T> ni,
-                   const BrickMaps maps)
+                   const BrickMaps maps,
+                   const int dbg)
   {
     using G          = BrickGeom<k, BZ>;
     constexpr int n  = k + 1;
@@ -1126,6 +1138,7 @@ namespace dasm
     __shared__ T        s_lam[3][n];
     __shared__ T        s_inv[n * n * n];
     __shared__ uint32_t s_tri[3];
+    __shared__ __align__(16) uint8_t s_wc[2][G::NCELLS * 32];
     if (threadIdx.x < 3)
       s_tri[threadIdx.x] = 0xFFFFFFFFu;
 
@@ -1153,8 +1166,24 @@ namespace dasm
         s_for[i] = maps.foreign[(size_t)cur_variant * maps.stride + i];
       __syncthreads();
     };
+    auto stage_codes = [&](const BrickDesc &b2, const int which) {
+      if (cw != nullptr)
+        {
+          const int nb16 = b2.b[0] * b2.b[1] * b2.b[2] * 2; // 32 bytes per cell
+          for (int i = threadIdx.x; i < nb16; i += G::NT)
+            {
+              const unsigned sa = (unsigned)__cvta_generic_to_shared(&s_wc[which][i * 16]);
+              asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(cw + (size_t)b2.first_cell * 32 + i * 16));
+            }
+        }
+    };
+    if (!LIN)
+      {
+        // non-pipelined variant: codes of the current brick are staged at the top of each iteration (see below)
+      }
     if (LIN)
       {
+        stage_codes(bd_next, 0);
         stage_maps(bd_next.variant);
         brick_issue_loads_lin<k, BZ, T>(bd_next, s_own, s_for, n_for, var_flags, s_cidx, tile, gidx, src);
         cp_async_commit(); // [tile(b0)]
@@ -1184,6 +1213,7 @@ namespace dasm
           }
         else
           {
+            stage_codes(bd, buf);
             brick_issue_loads<k, BZ, T>(bd, cur_cidx, tile, ops0, ops1, gidx, src, (const T *)nullptr, (const T *)nullptr);
             cp_async_commit();
             brick_issue_loads_ops<k, BZ, T>(bd, gidx, ops0, ops1, epi);
@@ -1196,20 +1226,20 @@ namespace dasm
         brick_next_init_store<k, BZ, T>(bd, ni, ni_a, ni_b);
         __syncthreads();
 
-        const bool     act  = c < ncells;
+        const bool     act  = (c < ncells) && !(dbg & 2);
         const int      cx = c % bd.b[0], cy = (c / bd.b[0]) % bd.b[1], cz = c / (bd.b[0] * bd.b[1]);
         const uint32_t cell = bd.first_cell + c;
         T *            S    = slots + c * G::CS;
-        uint32_t       i0 = 0, i1 = 0, i2 = 0;
-        if (act)
+        const uint4    tri     = brick_tri[bi];
+        const uint32_t r0 = tri.x, r1 = tri.y, r2 = tri.z;
+        const bool     uniform = tri.w != 0;
+        uint32_t       i0 = r0, i1 = r1, i2 = r2;
+        if (act && !uniform)
           {
             i0 = inst[(size_t)cell * 3 + 0];
             i1 = inst[(size_t)cell * 3 + 1];
             i2 = inst[(size_t)cell * 3 + 2];
           }
-        const uint32_t r0 = inst[(size_t)bd.first_cell * 3 + 0], r1 = inst[(size_t)bd.first_cell * 3 + 1],
-                       r2 = inst[(size_t)bd.first_cell * 3 + 2];
-        const bool uniform = __syncthreads_and(!act || (i0 == r0 && i1 == r1 && i2 == r2)) != 0;
         if (uniform && (s_tri[0] != r0 || s_tri[1] != r1 || s_tri[2] != r2))
           {
             __syncthreads();
@@ -1224,9 +1254,21 @@ namespace dasm
               s_tri[threadIdx.x] = (threadIdx.x == 0 ? r0 : (threadIdx.x == 1 ? r1 : r2));
             __syncthreads();
           }
-        const T *M0p = uniform ? s_M[0] : Smat + (size_t)i0 * n2;
-        const T *M1p = uniform ? s_M[1] : Smat + (size_t)i1 * n2;
-        const T *M2p = uniform ? s_M[2] : Smat + (size_t)i2 * n2;
+        // matrix d of this thread's cell into registers: LDS (broadcast) for uniform bricks, else global
+        auto load_matrix = [&](T(&M)[n2], const int d, const uint32_t id) {
+          if (uniform)
+            {
+#pragma unroll
+              for (int i = 0; i < n2; ++i)
+                M[i] = s_M[d][i];
+            }
+          else
+            {
+#pragma unroll
+              for (int i = 0; i < n2; ++i)
+                M[i] = Smat[(size_t)id * n2 + i];
+            }
+        };
         const int et = (t == 0) ? 0 : ((t == k) ? 2 : 1); // entity code of the plane index
 
         // phase A: plane z = t, [y][x]: (pre-weights) S0^T in x, S1^T in y
@@ -1239,12 +1281,12 @@ namespace dasm
 #pragma unroll
               for (int x = 0; x < n; ++x)
                 v[y][x] = tp[y * G::TX + x];
-            if (cw != nullptr && w_pre)
+            if (cw != nullptr && w_pre && !(dbg & 4))
               {
                 T wloc[9];
 #pragma unroll
                 for (int e = 0; e < 9; ++e)
-                  wloc[e] = cw[(size_t)cell * 27 + e + 9 * et];
+                  wloc[e] = wtab.v[s_wc[buf][c * 32 + e + 9 * et]];
 #pragma unroll
                 for (int y = 0; y < n; ++y)
 #pragma unroll
@@ -1253,16 +1295,12 @@ namespace dasm
               }
             {
               T M[n2];
-#pragma unroll
-              for (int i = 0; i < n2; ++i)
-                M[i] = M0p[i];
+              load_matrix(M, 0, i0);
               apply_fast<n, T, true>(v, M);
             }
             {
               T M[n2];
-#pragma unroll
-              for (int i = 0; i < n2; ++i)
-                M[i] = M1p[i];
+              load_matrix(M, 1, i1);
               apply_slow<n, T, true>(v, M);
             }
 #pragma unroll
@@ -1278,6 +1316,8 @@ namespace dasm
           {
             // the tile is dead from here on: gather the next brick into it while this brick is computed
             late_tile = has_next && ((int)bd_next.variant != cur_variant);
+            if (has_next)
+              stage_codes(bd_next, buf ^ 1);
             if (has_next && !late_tile)
               brick_issue_loads_lin<k, BZ, T>(bd_next, s_own, s_for, n_for, var_flags, s_cidx + (buf ^ 1) * (G::NCELLS * 27), tile,
                                               gidx + (buf ^ 1) * G::NFOREIGN, src);
@@ -1296,9 +1336,7 @@ namespace dasm
               for (int x = 0; x < n; ++x)
                 w[z][x] = S[(z * n + t) * n + x];
             T M[n2];
-#pragma unroll
-            for (int i = 0; i < n2; ++i)
-              M[i] = M2p[i];
+            load_matrix(M, 2, i2);
             apply_slow<n, T, true>(w, M);
             if (uniform)
               {
@@ -1325,9 +1363,7 @@ namespace dasm
                     w[z][x] = w[z][x] / (l0[x] + l1 + l2[z]);
               }
             apply_slow<n, T, false>(w, M);
-#pragma unroll
-            for (int i = 0; i < n2; ++i)
-              M[i] = M0p[i];
+            load_matrix(M, 0, i0);
             apply_fast<n, T, false>(w, M);
 #pragma unroll
             for (int z = 0; z < n; ++z)
@@ -1346,16 +1382,14 @@ namespace dasm
               for (int x = 0; x < n; ++x)
                 v[y][x] = S[(t * n + y) * n + x];
             T M[n2];
-#pragma unroll
-            for (int i = 0; i < n2; ++i)
-              M[i] = M1p[i];
+            load_matrix(M, 1, i1);
             apply_slow<n, T, false>(v, M);
-            if (cw != nullptr && w_post)
+            if (cw != nullptr && w_post && !(dbg & 4))
               {
                 T wloc[9];
 #pragma unroll
                 for (int e = 0; e < 9; ++e)
-                  wloc[e] = cw[(size_t)cell * 27 + e + 9 * et];
+                  wloc[e] = wtab.v[s_wc[buf][c * 32 + e + 9 * et]];
 #pragma unroll
                 for (int y = 0; y < n; ++y)
 #pragma unroll
@@ -1374,7 +1408,7 @@ namespace dasm
           cp_async_wait<1>();
         __syncthreads();
         if (LIN)
-          brick_store_lin<k, BZ, T>(bd, s_own, s_for, n_for, slots, ops0, ops1, cur_gidx, dst, acc, epi, shared_mode);
+          brick_store_lin<k, BZ, T>(bd, s_own, s_for, n_for, slots, ops0, ops1, cur_gidx, dst, acc, epi, shared_mode, dbg);
         else
           brick_reduce_store<k, BZ, T>(bd, slots, ops0, ops1, gidx, dst, acc, epi, shared_mode);
         if (LIN)
