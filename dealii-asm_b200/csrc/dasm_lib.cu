@@ -285,8 +285,8 @@ struct dasm_op
   uint32_t *        d_shared_list = nullptr; // owned DoFs on brick faces shared with other bricks
   long long         n_shared  = 0;
   bool              shared_ranges_ok = false; // every brick's own shared DoFs are one contiguous range
-  BrickMaps         maps = {nullptr, nullptr, nullptr, nullptr, 0}; // per-variant tile maps (coalesced gather / store)
-  uint32_t *        d_map_own = nullptr, *d_map_foreign = nullptr, *d_map_nforeign = nullptr, *d_map_flags = nullptr;
+  BrickMaps         maps = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0}; // tile maps (coalesced gather / store)
+  void *            d_map_bufs[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int               n_sm      = 148;
 
   dasm_op(int degree)
@@ -1300,15 +1300,30 @@ dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping
           op->d_shared_list = dev_upload(list, ctx->stream);
         }
         // ---- per-variant tile maps for the coalesced gather / store (kernel brick == mesh brick only)
-        op->maps.own = nullptr;
+        op->maps.load_tab = nullptr;
         if (op->brick_bz == 4)
           {
-            const int k = degree, n = k + 1, TX = 4 * k + 1, TY = 4 * k + 1, TZ = 4 * k + 1, NPTS = TX * TY * TZ;
-            const int CS = (n * n * n) | 1;
-            std::map<uint32_t, uint16_t>       variant_of; // signature -> variant
-            std::vector<std::vector<uint32_t>> v_own, v_foreign;
-            std::vector<uint32_t>              v_flags;
-            bool                               ok = true;
+            const int k = degree, n = k + 1, TX = 4 * k + 1, TY = 4 * k + 1, NPTS = TX * TY * TX;
+            const int CS  = (n * n * n) | 1;
+            const int NFP = (NPTS - (4 * k) * (4 * k) * (4 * k) + 3) / 4 * 4;
+            struct Variant
+            {
+              std::vector<uint16_t> load;       // [NPTS]
+              std::vector<uint32_t> store;      // sorted by class
+              std::vector<uint32_t> store_off;  // [17]
+              std::vector<uint32_t> ftab;       // sorted by mask
+              std::vector<uint32_t> for_off;    // [9]
+              uint32_t              flags = 0;
+              bool operator==(const Variant &o) const
+              {
+                return load == o.load && store == o.store && store_off == o.store_off && ftab == o.ftab && for_off == o.for_off &&
+                       flags == o.flags;
+              }
+            };
+            std::map<uint32_t, uint16_t> variant_of; // signature -> variant
+            std::vector<Variant>         variants;
+            std::vector<uint32_t>        foreign_gidx((size_t)bricks.size() * NFP, INVALID_INDEX);
+            bool                         ok = true;
             auto plain_gidx = [&](const BrickDesc &bd, const std::vector<uint32_t> &tab, int px, int py, int pz) {
               const int cx = std::min(px / k, bd.b[0] - 1), cy = std::min(py / k, bd.b[1] - 1), cz = std::min(pz / k, bd.b[2] - 1);
               const int lx = px - cx * k, ly = py - cy * k, lz = pz - cz * k;
@@ -1319,13 +1334,13 @@ dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping
               const int sx = ex == 1 ? k - 1 : 1, sy = ey == 1 ? k - 1 : 1;
               return st + (ex == 1 ? lx - 1 : 0) + sx * ((ey == 1 ? ly - 1 : 0) + sy * (ez == 1 ? lz - 1 : 0));
             };
-            for (BrickDesc &bd : bricks)
+            unsigned verify_counter = 0;
+            for (size_t bidx = 0; bidx < bricks.size() && ok; ++bidx)
               {
+                BrickDesc &    bd  = bricks[bidx];
                 const uint32_t sig = bd.b[0] | (bd.b[1] << 4) | (bd.b[2] << 8) | ((uint32_t)bd.shared << 12);
                 const int      e3[3] = {bd.b[0] * k + 1, bd.b[1] * k + 1, bd.b[2] * k + 1};
-                // range of owned DoFs from the geometric ownership rule (plain indices: constrained DoFs included)
-                uint32_t mn = 0xFFFFFFFFu, mx = 0, cnt = 0, smn = 0xFFFFFFFFu, smx = 0, scnt = 0;
-                auto     owned_point = [&](const int pp[3], bool &on_shared_lo) {
+                auto owned_point = [&](const int pp[3], bool &on_shared_lo) {
                   on_shared_lo = false;
                   for (int d = 0; d < 3; ++d)
                     {
@@ -1336,10 +1351,8 @@ dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping
                     }
                   return true;
                 };
-                const bool first_of_sig = variant_of.find(sig) == variant_of.end();
-                std::vector<uint32_t> own, foreign;
-                uint32_t              flags = 0;
-                // pass 1: ranges
+                // pass 1: ranges of owned DoFs (plain indices: constrained DoFs included)
+                uint32_t mn = 0xFFFFFFFFu, mx = 0, cnt = 0, smn = 0xFFFFFFFFu, smx = 0, scnt = 0;
                 for (int pz = 0; pz < e3[2]; ++pz)
                   for (int py = 0; py < e3[1]; ++py)
                     for (int px = 0; px < e3[0]; ++px)
@@ -1359,7 +1372,7 @@ dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping
                             ++scnt;
                           }
                       }
-                if (cnt == 0 || mx - mn + 1 != cnt || (scnt > 0 && (smx - smn + 1 != scnt || smx != mx)) || cnt > 0xFFFFu)
+                if (cnt == 0 || mx - mn + 1 != cnt || (scnt > 0 && (smx - smn + 1 != scnt || smx != mx)) || cnt >= 0x1FFFu)
                   {
                     ok = false;
                     break;
@@ -1368,101 +1381,141 @@ dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping
                 bd.npriv    = (uint16_t)(cnt - scnt);
                 bd.sh_base  = scnt > 0 ? smn : mn + cnt;
                 bd.sh_count = scnt;
-                // pass 2: maps (for the first brick of a signature; verified on every 97th brick)
-                static unsigned verify_counter = 0;
-                const bool      verify         = !first_of_sig && ((++verify_counter) % 97 == 0);
-                if (first_of_sig || verify)
-                  {
-                    own.assign(cnt, 0xFFFFFFFFu);
-                    for (int pz = 0; pz < e3[2]; ++pz)
-                      for (int py = 0; py < e3[1]; ++py)
-                        for (int px = 0; px < e3[0]; ++px)
+                // pass 2: variant tables for the first brick of a signature (verified on every 97th brick), foreign
+                // indices for every brick
+                const bool first_of_sig = variant_of.find(sig) == variant_of.end();
+                const bool verify       = !first_of_sig && ((++verify_counter) % 97 == 0);
+                Variant    var;
+                struct E
+                {
+                  uint32_t cls, key, entry;
+                };
+                std::vector<E> st_entries, f_entries;
+                std::vector<uint32_t> f_gidx_by_p; // parallel to f_entries before sorting
+                var.load.assign(NPTS, 0xFFFFu);
+                for (int pz = 0; pz < e3[2]; ++pz)
+                  for (int py = 0; py < e3[1]; ++py)
+                    for (int px = 0; px < e3[0]; ++px)
+                      {
+                        const int pp[3] = {px, py, pz};
+                        int       cc[3], ll[3];
+                        unsigned  mask = 0;
+                        for (int d = 0; d < 3; ++d)
                           {
-                            const int pp[3] = {px, py, pz};
-                            // primary contribution and mask of second contributions
-                            int      cc[3], ll[3];
-                            unsigned mask = 0;
-                            for (int d = 0; d < 3; ++d)
+                            const int ch = pp[d] / k, l = pp[d] - ch * k;
+                            if (ch < bd.b[d])
                               {
-                                const int ch = pp[d] / k, l = pp[d] - ch * k;
-                                if (ch < bd.b[d])
-                                  {
-                                    cc[d] = ch;
-                                    ll[d] = l;
-                                    if (l == 0 && ch > 0)
-                                      mask |= 1u << d;
-                                  }
-                                else
-                                  {
-                                    cc[d] = ch - 1;
-                                    ll[d] = k;
-                                  }
-                              }
-                            const uint32_t o     = (uint32_t)(((cc[2] * bd.b[1] + cc[1]) * bd.b[0] + cc[0]) * CS + (ll[2] * n + ll[1]) * n + ll[0]);
-                            const uint32_t plin  = (uint32_t)((pz * TY + py) * TX + px);
-                            const uint32_t entry = plin | (o << 13) | (mask << 29);
-                            const uint32_t gv    = plain_gidx(bd, op->nb.cidx, px, py, pz);
-                            bool           shlo;
-                            if (owned_point(pp, shlo))
-                              {
-                                if (gv != INVALID_INDEX)
-                                  own[gv - mn] = entry;
-                                else
-                                  flags |= 1u;
+                                cc[d] = ch;
+                                ll[d] = l;
+                                if (l == 0 && ch > 0)
+                                  mask |= 1u << d;
                               }
                             else
                               {
-                                foreign.push_back(entry);
-                                if (gv == INVALID_INDEX)
-                                  flags |= 1u;
+                                cc[d] = ch - 1;
+                                ll[d] = k;
                               }
                           }
+                        const uint32_t o    = (uint32_t)(((cc[2] * bd.b[1] + cc[1]) * bd.b[0] + cc[0]) * CS + (ll[2] * n + ll[1]) * n + ll[0]);
+                        const uint32_t plin = (uint32_t)((pz * TY + py) * TX + px);
+                        const uint32_t gv   = plain_gidx(bd, op->nb.cidx, px, py, pz);
+                        bool           shlo;
+                        if (owned_point(pp, shlo))
+                          {
+                            if (gv != INVALID_INDEX)
+                              {
+                                const uint32_t i = gv - mn;
+                                var.load[i]      = (uint16_t)plin;
+                                st_entries.push_back({(shlo ? 8u : 0u) + mask, i, i | (o << 13) | (mask << 26)});
+                              }
+                            else
+                              var.flags |= 1u;
+                          }
+                        else
+                          {
+                            f_entries.push_back({mask, plin, plin | (o << 13) | (mask << 26)});
+                            f_gidx_by_p.push_back(gv);
+                            if (gv == INVALID_INDEX)
+                              var.flags |= 1u;
+                          }
+                      }
+                // foreign entries sorted by (mask, tile point); the per-brick index list follows the same order
+                std::vector<size_t> perm(f_entries.size());
+                for (size_t i = 0; i < perm.size(); ++i)
+                  perm[i] = i;
+                std::stable_sort(perm.begin(), perm.end(), [&](size_t a, size_t b2) { return f_entries[a].cls < f_entries[b2].cls; });
+                if ((int)perm.size() > NFP)
+                  {
+                    ok = false;
+                    break;
+                  }
+                for (size_t j = 0; j < perm.size(); ++j)
+                  foreign_gidx[bidx * NFP + j] = f_gidx_by_p[perm[j]];
+                if (first_of_sig || verify)
+                  {
+                    // store table in the order of the own range (entry i describes DoF base + i)
+                    var.store_off.assign(17, 0);
+                    var.store.assign(cnt, 0xFFFFFFFFu);
+                    for (const E &x : st_entries)
+                      var.store[x.key] = x.entry;
+                    var.for_off.assign(9, 0);
+                    for (size_t j = 0; j < perm.size(); ++j)
+                      {
+                        var.ftab.push_back(f_entries[perm[j]].entry);
+                        var.for_off[f_entries[perm[j]].cls + 1]++;
+                      }
+                    for (int c = 0; c < 8; ++c)
+                      var.for_off[c + 1] += var.for_off[c];
                     if (first_of_sig)
                       {
-                        variant_of[sig] = (uint16_t)v_own.size();
-                        v_own.push_back(own);
-                        v_foreign.push_back(foreign);
-                        v_flags.push_back(flags);
+                        variant_of[sig] = (uint16_t)variants.size();
+                        variants.push_back(var);
                       }
-                    else
+                    else if (!(var == variants[variant_of[sig]]))
                       {
-                        const uint16_t v = variant_of[sig];
-                        if (own != v_own[v] || foreign != v_foreign[v] || flags != v_flags[v])
-                          {
-                            ok = false;
-                            break;
-                          }
+                        ok = false;
+                        break;
                       }
                   }
                 bd.variant = variant_of[sig];
               }
-            if (ok && !v_own.empty())
+            if (ok && !variants.empty())
               {
-                const int             nv = (int)v_own.size();
-                std::vector<uint32_t> h_own((size_t)nv * NPTS, 0xFFFFFFFFu), h_for((size_t)nv * NPTS, 0), h_nf(nv), h_fl(nv);
+                const int             nv = (int)variants.size();
+                std::vector<uint16_t> h_load((size_t)nv * NPTS, 0xFFFFu);
+                std::vector<uint32_t> h_store((size_t)nv * NPTS, 0xFFFFFFFFu), h_soff((size_t)nv * 17), h_for((size_t)nv * NFP, 0), h_foff((size_t)nv * 9),
+                  h_fl(nv);
                 for (int v = 0; v < nv; ++v)
                   {
-                    std::copy(v_own[v].begin(), v_own[v].end(), h_own.begin() + (size_t)v * NPTS);
-                    std::copy(v_foreign[v].begin(), v_foreign[v].end(), h_for.begin() + (size_t)v * NPTS);
-                    h_nf[v] = (uint32_t)v_foreign[v].size();
-                    h_fl[v] = v_flags[v];
+                    std::copy(variants[v].load.begin(), variants[v].load.end(), h_load.begin() + (size_t)v * NPTS);
+                    std::copy(variants[v].store.begin(), variants[v].store.end(), h_store.begin() + (size_t)v * NPTS);
+                    std::copy(variants[v].store_off.begin(), variants[v].store_off.end(), h_soff.begin() + (size_t)v * 17);
+                    std::copy(variants[v].ftab.begin(), variants[v].ftab.end(), h_for.begin() + (size_t)v * NFP);
+                    std::copy(variants[v].for_off.begin(), variants[v].for_off.end(), h_foff.begin() + (size_t)v * 9);
+                    h_fl[v] = variants[v].flags;
                   }
-                op->d_map_own        = dev_upload(h_own, ctx->stream);
-                op->d_map_foreign    = dev_upload(h_for, ctx->stream);
-                op->d_map_nforeign   = dev_upload(h_nf, ctx->stream);
-                op->d_map_flags      = dev_upload(h_fl, ctx->stream);
-                op->maps.own         = op->d_map_own;
-                op->maps.foreign     = op->d_map_foreign;
-                op->maps.n_foreign   = op->d_map_nforeign;
-                op->maps.flags       = op->d_map_flags;
-                op->maps.stride      = NPTS;
-                op->shared_ranges_ok = true;
+                op->d_map_bufs[0]      = dev_upload(h_load, ctx->stream);
+                op->d_map_bufs[1]      = dev_upload(h_store, ctx->stream);
+                op->d_map_bufs[2]      = dev_upload(h_soff, ctx->stream);
+                op->d_map_bufs[3]      = dev_upload(h_for, ctx->stream);
+                op->d_map_bufs[4]      = dev_upload(h_foff, ctx->stream);
+                op->d_map_bufs[5]      = dev_upload(h_fl, ctx->stream);
+                op->d_map_bufs[6]      = dev_upload(foreign_gidx, ctx->stream);
+                op->maps.load_tab      = (const uint16_t *)op->d_map_bufs[0];
+                op->maps.store_tab     = (const uint32_t *)op->d_map_bufs[1];
+                op->maps.store_off     = (const uint32_t *)op->d_map_bufs[2];
+                op->maps.for_tab       = (const uint32_t *)op->d_map_bufs[3];
+                op->maps.for_off       = (const uint32_t *)op->d_map_bufs[4];
+                op->maps.flags         = (const uint32_t *)op->d_map_bufs[5];
+                op->maps.foreign_gidx  = (const uint32_t *)op->d_map_bufs[6];
+                op->maps.stride        = NPTS;
+                op->maps.nfp           = NFP;
+                op->shared_ranges_ok   = true;
                 cudaFree(op->d_bricks);
                 op->d_bricks = dev_upload(bricks, ctx->stream);
               }
             else
               op->use_brick = false; // no consistent tile maps: use the generic kernels
-            (void)TZ;
           }
         CUDA_CHECK(cudaMalloc(&op->d_acc, std::max<size_t>(1, (size_t)op->n_vec) * op->esize()));
         CUDA_CHECK(cudaMemset(op->d_acc, 0, std::max<size_t>(1, (size_t)op->n_vec) * op->esize()));
@@ -1489,10 +1542,8 @@ dasm_op_destroy(dasm_op *op)
   cudaFree(op->d_bricks);
   cudaFree(op->d_acc);
   cudaFree(op->d_shared_list);
-  cudaFree(op->d_map_own);
-  cudaFree(op->d_map_foreign);
-  cudaFree(op->d_map_nforeign);
-  cudaFree(op->d_map_flags);
+  for (void *p : op->d_map_bufs)
+    cudaFree(p);
   op->exchange.destroy();
   for (void *p : op->scratch)
     cudaFree(p);

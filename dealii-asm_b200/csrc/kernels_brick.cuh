@@ -35,16 +35,25 @@ namespace dasm
   };
 
   // Per-variant maps between the brick's contiguous range of owned DoFs and its tile (bricks of equal shape,
-  // boundary flags and constraints share a variant).  Entry: bits 0-12 tile point, 13-28 slot offset of the
-  // primary cell contribution, 29-31 mask of the directions with a second contribution (lower neighbour
-  // cell inside the brick).  own[i] describes DoF base + i; foreign[j] the tile points owned by other bricks.
+  // boundary flags and constraints share a variant) + per-brick global indices of the tile points owned by
+  // other bricks.
+  //   load_tab[i]   tile point of own DoF base + i (0xFFFF: constrained / unused)
+  //   store_tab[i]  for own DoF base + i: bits 13-25 slot offset of the primary cell contribution, 26-28 mask of
+  //                 the directions with a second contribution (lower neighbour cell inside the brick);
+  //                 0xFFFFFFFF unused (store_off: reserved)
+  //   for_tab[j]    tile points owned by other bricks sorted by mask: bits 0-12 tile point, 13-25 slot offset,
+  //                 26-28 mask; for_off[m] class offsets (8 + end); foreign_gidx[brick][j] their global index
   struct BrickMaps
   {
-    const uint32_t *own;       // [variant][stride]
-    const uint32_t *foreign;   // [variant][stride]
-    const uint32_t *n_foreign; // [variant]
-    const uint32_t *flags;     // [variant] bit 0: the tile has unreferenced (constrained) points -> zero it first
+    const uint16_t *load_tab;     // [variant][stride]
+    const uint32_t *store_tab;    // [variant][stride]
+    const uint32_t *store_off;    // [variant][17]
+    const uint32_t *for_tab;      // [variant][nfp]
+    const uint32_t *for_off;      // [variant][9]
+    const uint32_t *flags;        // [variant] bit 0: the tile has unreferenced (constrained) points -> zero it first
+    const uint32_t *foreign_gidx; // [brick][nfp]
     int             stride;
+    int             nfp;
   };
 
   // compressed weights as codes: code = patch valence of the entity (0: weight 0), value from this table
@@ -145,15 +154,18 @@ namespace dasm
     static constexpr int NWARPS = (NT + 31) / 32;
     static constexpr int MAXREG = ((65536 / NWARPS / 512) * 512 / 32) >= 255 ? 255 : ((65536 / NWARPS / 512) * 512 / 32);
     static constexpr int NFOREIGN = NPTS - (BX * k) * (BY * k) * (BZ * k); // tile points a brick can not own
-    // layout: tile | operand tiles (n_ops) | slots | gidx | cidx[2] | (lin: own map | foreign map)
-    // gidx holds NPTS entries (tile-ordered access) or NFOREIGN entries (linear access through the maps)
+    static constexpr int NFP      = (NFOREIGN + 3) / 4 * 4;                 // padded to 16 bytes
+    static constexpr int NLT      = (NPTS + 1) / 2 * 2;                     // u16 load table padded to 4 bytes
+    // non-lin layout: tile | operand tiles (n_ops) | slots | gidx[NPTS] | cidx[2]
+    // lin layout    : tile | operand tiles (n_ops) | slots | gidx_f[3][NFP] | store_tab[NPTS] | for_tab[NFP] | offsets[32] |
+    //                 load_tab u16[NLT]
     template <typename T>
     static constexpr size_t
     smem_bytes(int n_ops, bool lin)
     {
       return (size_t)(1 + n_ops) * NPTS * sizeof(T) + (size_t)NCELLS * CS * sizeof(T) +
-             (size_t)(lin ? 2 * NFOREIGN : NPTS) * sizeof(uint32_t) + (size_t)2 * NCELLS * 27 * sizeof(uint32_t) +
-             (lin ? (size_t)(NPTS + NFOREIGN) * sizeof(uint32_t) : 0);
+             16 + (lin ? (size_t)(3 * NFP + NPTS + NFP + 32) * sizeof(uint32_t) + (size_t)NLT * sizeof(uint16_t) :
+                    (size_t)NPTS * sizeof(uint32_t) + (size_t)2 * NCELLS * 27 * sizeof(uint32_t));
     }
   };
 
@@ -405,41 +417,39 @@ namespace dasm
   // The brick's own DoFs are one contiguous range, so consecutive lanes read / write consecutive global
   // addresses (2 lines per warp instruction instead of ~12 with the tile-ordered access); only the tile points
   // owned by other bricks (upper faces) are addressed through the compressed indices.
-  constexpr uint32_t MAP_UNUSED = 0xFFFFFFFFu;
-
-  template <int k>
-  __device__ __forceinline__ uint32_t
-  tile_point_gidx(const BrickDesc &bd, const uint32_t *s_cidx, const int p, const int TX, const int TY)
+  // staged tables of the current variant (shared memory)
+  struct LinTables
   {
-    const int px = p % TX, py = (p / TX) % TY, pz = p / (TX * TY);
-    const int cx = min(px / k, bd.b[0] - 1), cy = min(py / k, bd.b[1] - 1), cz = min(pz / k, bd.b[2] - 1);
-    return compressed_index<k>(s_cidx + ((cz * bd.b[1] + cy) * bd.b[0] + cx) * 27, px - cx * k, py - cy * k, pz - cz * k);
-  }
+    const uint16_t *load_tab;
+    const uint32_t *store_tab;
+    const uint32_t *for_tab;
+    const uint32_t *off; // [0..16] store classes, [17..25] foreign classes
+    unsigned        flags;
+  };
 
   template <int k, int BZ, typename T>
   __device__ __forceinline__ void
-  brick_issue_loads_lin(const BrickDesc &bd, const uint32_t *own, const uint32_t *foreign, const int n_for, const unsigned flags,
-                        const uint32_t *s_cidx, T *tile, uint32_t *gidx_f, const T *__restrict__ src)
+  brick_issue_loads_lin(const BrickDesc &bd, const LinTables &tb, const uint32_t *gidx_f, T *tile, const T *__restrict__ src)
   {
     using G         = BrickGeom<k, BZ>;
-    const int n_own = bd.npriv + bd.sh_count;
-    if (flags & 1u)
+    const int n_own = bd.npriv + bd.sh_count, n_for = tb.off[25];
+    if (tb.flags & 1u)
       {
         for (int p = threadIdx.x; p < G::NPTS; p += G::NT)
           tile[p] = T(0);
         __syncthreads();
       }
+#pragma unroll 4
     for (int i = threadIdx.x; i < n_own; i += G::NT)
       {
-        const uint32_t e = own[i];
-        if (e != MAP_UNUSED)
-          cp_async_value(tile + (e & 0x1FFFu), src + bd.base + i);
+        const unsigned p = tb.load_tab[i];
+        if (p != 0xFFFFu)
+          cp_async_value(tile + p, src + bd.base + i);
       }
     for (int j = threadIdx.x; j < n_for; j += G::NT)
       {
-        const int      p = foreign[j] & 0x1FFFu;
-        const uint32_t g = tile_point_gidx<k>(bd, s_cidx, p, G::TX, G::TY);
-        gidx_f[j]        = g;
+        const int      p = tb.for_tab[j] & 0x1FFFu;
+        const uint32_t g = gidx_f[j];
         if (g != DEV_INVALID)
           cp_async_value(tile + p, src + g);
         else
@@ -456,6 +466,7 @@ namespace dasm
     const bool need1 = (epi.kind == EPI_CHEB && epi.f1 != T(0) && epi.v1 != nullptr);
     if (!need0)
       return;
+#pragma unroll 4
     for (int i = threadIdx.x; i < bd.npriv; i += G::NT)
       {
         cp_async_value(ops0 + i, epi.v0 + bd.base + i);
@@ -464,13 +475,13 @@ namespace dasm
       }
   }
 
+  // sum of the cell contributions of one DoF in a fixed order (deterministic); m = mask of the directions with
+  // a second contribution
   template <typename T>
   __device__ __forceinline__ T
-  slot_sum(const T *slots, const uint32_t e, const int dx, const int dy, const int dz)
+  slot_sum(const T *slots, const int o, const unsigned m, const int dx, const int dy, const int dz)
   {
-    const int      o = (e >> 13) & 0xFFFFu;
-    const unsigned m = e >> 29;
-    T              y = slots[o];
+    T y = slots[o];
     if (m & 1u)
       y += slots[o + dx];
     if (m & 2u)
@@ -495,49 +506,89 @@ namespace dasm
     return y;
   }
 
+  // store of a brick in the order of its own DoF range (coalesced global access; a class-sorted order with
+  // compile-time masks was measured slower: the stores lose their coalescing)
   template <int k, int BZ, typename T>
   __device__ __forceinline__ void
-  brick_store_lin(const BrickDesc &bd, const uint32_t *own, const uint32_t *foreign, const int n_for, const T *slots, const T *ops0,
-                  const T *ops1, const uint32_t *gidx_f, T *__restrict__ dst, T *__restrict__ acc, const Epilogue<T> &epi,
-                  const int shared_mode, const int dbg = 0)
+  brick_store_lin(const BrickDesc &bd, const LinTables &tb, const T *slots, const T *ops0, const T *ops1, const uint32_t *gidx_f,
+                  T *__restrict__ dst, T *__restrict__ acc, const Epilogue<T> &epi, const int shared_mode)
   {
-    using G           = BrickGeom<k, BZ>;
-    constexpr int n   = k + 1;
-    const int     n_own = bd.npriv + bd.sh_count;
-    const int       dx = -G::CS + k, dy = -bd.b[0] * G::CS + k * n, dz = -bd.b[0] * bd.b[1] * G::CS + k * n * n;
-    const bool      need0 = (epi.kind == EPI_RESIDUAL || epi.kind == EPI_CHEB);
-    const bool      need1 = (epi.kind == EPI_CHEB && epi.f1 != T(0) && epi.v1 != nullptr);
-    const T         alpha = (epi.kind == EPI_RESIDUAL) ? T(-1) : ((epi.kind == EPI_CHEB || epi.kind == EPI_SCALE) ? epi.f2 : T(1));
-    T *             sh_dst = (shared_mode == SHARED_DIRECT) ? dst : acc;
-    const T         sh_a   = (shared_mode == SHARED_DIRECT) ? alpha : T(1);
+    using G          = BrickGeom<k, BZ>;
+    constexpr int n  = k + 1;
+    const int     dx = -G::CS + k, dy = -bd.b[0] * G::CS + k * n, dz = -bd.b[0] * bd.b[1] * G::CS + k * n * n;
+    const bool    need0 = (epi.kind == EPI_RESIDUAL || epi.kind == EPI_CHEB);
+    const bool    need1 = (epi.kind == EPI_CHEB && epi.f1 != T(0) && epi.v1 != nullptr);
+    const T       alpha = (epi.kind == EPI_RESIDUAL) ? T(-1) : ((epi.kind == EPI_CHEB || epi.kind == EPI_SCALE) ? epi.f2 : T(1));
+    T *           sh_dst = (shared_mode == SHARED_DIRECT) ? dst : acc;
+    const T       sh_a   = (shared_mode == SHARED_DIRECT) ? alpha : T(1);
+    const int     n_own = bd.npriv + bd.sh_count, n_for = tb.off[25];
     // private DoFs: fused epilogue, coalesced plain stores
 #pragma unroll 4
-    for (int i = threadIdx.x; i < ((dbg & 8) ? 0 : (int)bd.npriv); i += G::NT)
+    for (int i = threadIdx.x; i < bd.npriv; i += G::NT)
       {
-        const uint32_t e = own[i];
-        if (e == MAP_UNUSED)
+        const uint32_t e = tb.store_tab[i];
+        if (e == 0xFFFFFFFFu)
           continue;
-        const T y        = slot_sum(slots, e, dx, dy, dz);
+        const T y        = slot_sum(slots, (e >> 13) & 0x1FFFu, e >> 26, dx, dy, dz);
         dst[bd.base + i] = epilogue_compute(epi, y, need0 ? ops0[i] : T(0), need1 ? ops1[i] : T(0));
       }
-    if (dbg & 32)
-      return;
-    if (dbg & 8)
-      return;
     // own DoFs on shared faces: coalesced red.add
     for (int i = bd.npriv + threadIdx.x; i < n_own; i += G::NT)
       {
-        const uint32_t e = own[i];
-        if (e != MAP_UNUSED)
-          atomic_add(sh_dst + bd.base + i, sh_a * slot_sum(slots, e, dx, dy, dz));
+        const uint32_t e = tb.store_tab[i];
+        if (e != 0xFFFFFFFFu)
+          atomic_add(sh_dst + bd.base + i, sh_a * slot_sum(slots, (e >> 13) & 0x1FFFu, e >> 26, dx, dy, dz));
       }
     // tile points owned by other bricks
     for (int j = threadIdx.x; j < n_for; j += G::NT)
       {
         const uint32_t g = gidx_f[j];
         if (g != DEV_INVALID)
-          atomic_add(sh_dst + g, sh_a * slot_sum(slots, foreign[j], dx, dy, dz));
+          {
+            const uint32_t e = tb.for_tab[j];
+            atomic_add(sh_dst + g, sh_a * slot_sum(slots, (e >> 13) & 0x1FFFu, e >> 26, dx, dy, dz));
+          }
       }
+  }
+
+  // stage the foreign index list of a brick (contiguous, 16-byte cp.async)
+  template <int k, int BZ>
+  __device__ __forceinline__ void
+  brick_stage_foreign_async(const BrickMaps &maps, const int brick, uint32_t *gidx_f)
+  {
+    using G             = BrickGeom<k, BZ>;
+    const uint32_t *src = maps.foreign_gidx + (size_t)brick * maps.nfp;
+    for (int i = threadIdx.x; i < maps.nfp / 4; i += G::NT)
+      {
+        const unsigned sa = (unsigned)__cvta_generic_to_shared(gidx_f + 4 * i);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(src + 4 * i));
+      }
+  }
+
+  // copy the tables of a variant into shared memory
+  template <int k, int BZ>
+  __device__ __forceinline__ void
+  brick_stage_tables(const BrickMaps &maps, const int variant, uint16_t *s_load, uint32_t *s_store, uint32_t *s_for, uint32_t *s_off,
+                     LinTables &tb)
+  {
+    using G = BrickGeom<k, BZ>;
+    for (int i = threadIdx.x; i < G::NPTS; i += G::NT)
+      {
+        s_load[i]  = maps.load_tab[(size_t)variant * maps.stride + i];
+        s_store[i] = maps.store_tab[(size_t)variant * maps.stride + i];
+      }
+    for (int i = threadIdx.x; i < maps.nfp; i += G::NT)
+      s_for[i] = maps.for_tab[(size_t)variant * maps.nfp + i];
+    if (threadIdx.x < 17)
+      s_off[threadIdx.x] = maps.store_off[variant * 17 + threadIdx.x];
+    if (threadIdx.x >= 32 && threadIdx.x < 41)
+      s_off[17 + threadIdx.x - 32] = maps.for_off[variant * 9 + threadIdx.x - 32];
+    tb.load_tab  = s_load;
+    tb.store_tab = s_store;
+    tb.for_tab   = s_for;
+    tb.off       = s_off;
+    tb.flags     = maps.flags[variant];
+    __syncthreads();
   }
 
   // fused pre-initialisation of the next kernel's destination on the brick's own shared DoFs: the operand loads
@@ -700,13 +751,15 @@ namespace dasm
     T *       ops0   = (n_ops > 0) ? tile + G::NPTS : tile;
     T *       ops1   = (n_ops > 1) ? tile + 2 * G::NPTS : ops0;
     T *       slots  = tile + (1 + n_ops) * G::NPTS;
-    uint32_t *gidx   = reinterpret_cast<uint32_t *>(slots + G::NCELLS * G::CS);
-    const bool lin_mode = (maps.own != nullptr);
-    uint32_t * s_cidx   = gidx + (lin_mode ? 2 * G::NFOREIGN : G::NPTS); // two buffers of NCELLS * 27
-    uint32_t * s_own    = s_cidx + 2 * G::NCELLS * 27;                // lin: staged maps of the current variant
-    uint32_t * s_for    = s_own + G::NPTS;
-    int        cur_variant = -1, n_for = 0;
-    unsigned   var_flags   = 0;
+    uint32_t *gidx   = reinterpret_cast<uint32_t *>((reinterpret_cast<uintptr_t>(slots + G::NCELLS * G::CS) + 15) & ~uintptr_t(15));
+    // non-lin: gidx[NPTS] | cidx[2];   lin: gidx_f[3][NFP] | store_tab[NPTS] | for_tab[NFP] | offsets[32] | load_tab u16
+    uint32_t * s_cidx  = gidx + G::NPTS; // non-lin only: two buffers of NCELLS * 27
+    uint32_t * s_store = gidx + 3 * G::NFP;
+    uint32_t * s_for   = s_store + G::NPTS;
+    uint32_t * s_off   = s_for + G::NFP;
+    uint16_t * s_load  = reinterpret_cast<uint16_t *>(s_off + 32);
+    int        cur_variant = -1;
+    LinTables  tb;
 
     const auto &B = BasisOf<T>::template get<k>();
     const int   c = threadIdx.x % G::NCELLS; // cell in brick (lane-major: conflict-free slot access)
@@ -719,33 +772,30 @@ namespace dasm
     constexpr bool LIN = (BZ == 4);
     if (blockIdx.x >= n_bricks)
       return;
-    brick_stage_cidx_async<k, BZ>(bricks[blockIdx.x], cidx, s_cidx);
-    cp_async_commit();
-    cp_async_wait<0>();
-    __syncthreads();
-    int       buf = 0;
-    BrickDesc bd_next = bricks[blockIdx.x];
+    int       buf = 0, fb = 0; // buf: parity of the brick; fb: ring position (mod 3) of its foreign-index buffer
+    BrickDesc bd_next   = bricks[blockIdx.x];
     bool      late_tile = false;
-    auto      stage_maps = [&](const int variant) {
-      cur_variant = variant;
-      n_for       = maps.n_foreign[cur_variant];
-      var_flags   = maps.flags[cur_variant];
-      for (int i = threadIdx.x; i < G::NPTS; i += G::NT)
-        s_own[i] = maps.own[(size_t)cur_variant * maps.stride + i];
-      for (int i = threadIdx.x; i < n_for; i += G::NT)
-        s_for[i] = maps.foreign[(size_t)cur_variant * maps.stride + i];
-      __syncthreads();
-    };
     if (LIN)
       {
-        stage_maps(bd_next.variant);
-        brick_issue_loads_lin<k, BZ, T>(bd_next, s_own, s_for, n_for, var_flags, s_cidx, tile, gidx, src);
+        brick_stage_foreign_async<k, BZ>(maps, blockIdx.x, gidx);
+        cp_async_commit();
+        cp_async_wait<0>();
+        cur_variant = bd_next.variant;
+        brick_stage_tables<k, BZ>(maps, cur_variant, s_load, s_store, s_for, s_off, tb); // ends with __syncthreads
+        brick_issue_loads_lin<k, BZ, T>(bd_next, tb, gidx, tile, src);
         cp_async_commit(); // [tile(b0)]
         if (blockIdx.x + gridDim.x < (unsigned)n_bricks)
-          brick_stage_cidx_async<k, BZ>(bricks[blockIdx.x + gridDim.x], cidx, s_cidx + G::NCELLS * 27);
-        cp_async_commit(); // [cidx(b1)]
+          brick_stage_foreign_async<k, BZ>(maps, blockIdx.x + gridDim.x, gidx + G::NFP);
+        cp_async_commit(); // [foreign(b1)]
       }
-    for (int bi = blockIdx.x; bi < n_bricks; bi += gridDim.x, buf ^= 1)
+    else
+      {
+        brick_stage_cidx_async<k, BZ>(bd_next, cidx, s_cidx);
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+      }
+    for (int bi = blockIdx.x; bi < n_bricks; bi += gridDim.x, buf ^= 1, fb = (fb + 1) % 3)
       {
         const BrickDesc bd       = bd_next;
         const bool      has_next = bi + (int)gridDim.x < n_bricks;
@@ -753,7 +803,7 @@ namespace dasm
           bd_next = bricks[bi + gridDim.x]; // descriptor of the next brick: latency hidden behind this brick
         const int       ncells   = bd.b[0] * bd.b[1] * bd.b[2];
         const uint32_t *cur_cidx = s_cidx + buf * (G::NCELLS * 27);
-        uint32_t *      cur_gidx = LIN ? gidx + buf * G::NFOREIGN : gidx;
+        uint32_t *      cur_gidx = LIN ? gidx + fb * G::NFP : gidx;
         T               ni_a[NextInitRegs<k, BZ>::IT], ni_b[NextInitRegs<k, BZ>::IT];
         brick_next_init_load<k, BZ, T>(bd, ni, ni_a, ni_b);
         if (LIN)
@@ -810,12 +860,11 @@ namespace dasm
             // the tile is dead from here on: gather the next brick into it while this brick is computed
             late_tile = has_next && ((int)bd_next.variant != cur_variant);
             if (has_next && !late_tile)
-              brick_issue_loads_lin<k, BZ, T>(bd_next, s_own, s_for, n_for, var_flags, s_cidx + (buf ^ 1) * (G::NCELLS * 27), tile,
-                                              gidx + (buf ^ 1) * G::NFOREIGN, src);
+              brick_issue_loads_lin<k, BZ, T>(bd_next, tb, gidx + ((fb + 1) % 3) * G::NFP, tile, src);
             cp_async_commit(); // [tile(i+1)]
             if (bi + 2 * (int)gridDim.x < n_bricks)
-              brick_stage_cidx_async<k, BZ>(bricks[bi + 2 * gridDim.x], cidx, s_cidx + buf * (G::NCELLS * 27));
-            cp_async_commit(); // [cidx(i+2)]
+              brick_stage_foreign_async<k, BZ>(maps, bi + 2 * gridDim.x, gidx + ((fb + 2) % 3) * G::NFP);
+            cp_async_commit(); // [foreign(i+2)]
           }
         if (GEOM == 0)
           {
@@ -1064,7 +1113,7 @@ namespace dasm
           cp_async_wait<1>();
         __syncthreads();
         if (LIN)
-          brick_store_lin<k, BZ, T>(bd, s_own, s_for, n_for, slots, ops0, ops1, cur_gidx, dst, acc, epi, shared_mode);
+          brick_store_lin<k, BZ, T>(bd, tb, slots, ops0, ops1, cur_gidx, dst, acc, epi, shared_mode);
         else
           brick_reduce_store<k, BZ, T>(bd, slots, ops0, ops1, gidx, dst, acc, epi, shared_mode);
         if (LIN)
@@ -1073,9 +1122,9 @@ namespace dasm
               {
                 // the next brick has another tile-map variant: its maps can only be staged once this brick is stored
                 __syncthreads();
-                stage_maps(bd_next.variant);
-                brick_issue_loads_lin<k, BZ, T>(bd_next, s_own, s_for, n_for, var_flags, s_cidx + (buf ^ 1) * (G::NCELLS * 27), tile,
-                                                gidx + (buf ^ 1) * G::NFOREIGN, src);
+                cur_variant = bd_next.variant;
+                brick_stage_tables<k, BZ>(maps, cur_variant, s_load, s_store, s_for, s_off, tb);
+                brick_issue_loads_lin<k, BZ, T>(bd_next, tb, gidx + ((fb + 1) % 3) * G::NFP, tile, src);
                 cp_async_commit();
               }
           }
@@ -1119,13 +1168,15 @@ namespace dasm
     T *       ops0   = (n_ops > 0) ? tile + G::NPTS : tile;
     T *       ops1   = (n_ops > 1) ? tile + 2 * G::NPTS : ops0;
     T *       slots  = tile + (1 + n_ops) * G::NPTS;
-    uint32_t *gidx   = reinterpret_cast<uint32_t *>(slots + G::NCELLS * G::CS);
-    const bool lin_mode = (maps.own != nullptr);
-    uint32_t * s_cidx   = gidx + (lin_mode ? 2 * G::NFOREIGN : G::NPTS); // two buffers of NCELLS * 27
-    uint32_t * s_own    = s_cidx + 2 * G::NCELLS * 27;                // lin: staged maps of the current variant
-    uint32_t * s_for    = s_own + G::NPTS;
-    int        cur_variant = -1, n_for = 0;
-    unsigned   var_flags   = 0;
+    uint32_t *gidx   = reinterpret_cast<uint32_t *>((reinterpret_cast<uintptr_t>(slots + G::NCELLS * G::CS) + 15) & ~uintptr_t(15));
+    // non-lin: gidx[NPTS] | cidx[2];   lin: gidx_f[3][NFP] | store_tab[NPTS] | for_tab[NFP] | offsets[32] | load_tab u16
+    uint32_t * s_cidx  = gidx + G::NPTS; // non-lin only: two buffers of NCELLS * 27
+    uint32_t * s_store = gidx + 3 * G::NFP;
+    uint32_t * s_for   = s_store + G::NPTS;
+    uint32_t * s_off   = s_for + G::NFP;
+    uint16_t * s_load  = reinterpret_cast<uint16_t *>(s_off + 32);
+    int        cur_variant = -1;
+    LinTables  tb;
 
     const int c = threadIdx.x % G::NCELLS; // cell in brick (lane-major: conflict-free slot access)
     const int t = threadIdx.x / G::NCELLS; // plane index (warp-uniform)
@@ -1149,24 +1200,10 @@ namespace dasm
     constexpr bool LIN = (BZ == 4);
     if (blockIdx.x >= n_bricks)
       return;
-    brick_stage_cidx_async<k, BZ>(bricks[blockIdx.x], cidx, s_cidx);
-    cp_async_commit();
-    cp_async_wait<0>();
-    __syncthreads();
-    int       buf = 0;
-    BrickDesc bd_next = bricks[blockIdx.x];
+    int       buf = 0, fb = 0; // buf: parity of the brick; fb: ring position (mod 3) of its foreign-index buffer
+    BrickDesc bd_next   = bricks[blockIdx.x];
     bool      late_tile = false;
-    auto      stage_maps = [&](const int variant) {
-      cur_variant = variant;
-      n_for       = maps.n_foreign[cur_variant];
-      var_flags   = maps.flags[cur_variant];
-      for (int i = threadIdx.x; i < G::NPTS; i += G::NT)
-        s_own[i] = maps.own[(size_t)cur_variant * maps.stride + i];
-      for (int i = threadIdx.x; i < n_for; i += G::NT)
-        s_for[i] = maps.foreign[(size_t)cur_variant * maps.stride + i];
-      __syncthreads();
-    };
-    auto stage_codes = [&](const BrickDesc &b2, const int which) {
+    auto      stage_codes = [&](const BrickDesc &b2, const int which) {
       if (cw != nullptr)
         {
           const int nb16 = b2.b[0] * b2.b[1] * b2.b[2] * 2; // 32 bytes per cell
@@ -1177,21 +1214,28 @@ namespace dasm
             }
         }
     };
-    if (!LIN)
-      {
-        // non-pipelined variant: codes of the current brick are staged at the top of each iteration (see below)
-      }
     if (LIN)
       {
+        brick_stage_foreign_async<k, BZ>(maps, blockIdx.x, gidx);
+        cp_async_commit();
+        cp_async_wait<0>();
+        cur_variant = bd_next.variant;
+        brick_stage_tables<k, BZ>(maps, cur_variant, s_load, s_store, s_for, s_off, tb); // ends with __syncthreads
         stage_codes(bd_next, 0);
-        stage_maps(bd_next.variant);
-        brick_issue_loads_lin<k, BZ, T>(bd_next, s_own, s_for, n_for, var_flags, s_cidx, tile, gidx, src);
+        brick_issue_loads_lin<k, BZ, T>(bd_next, tb, gidx, tile, src);
         cp_async_commit(); // [tile(b0)]
         if (blockIdx.x + gridDim.x < (unsigned)n_bricks)
-          brick_stage_cidx_async<k, BZ>(bricks[blockIdx.x + gridDim.x], cidx, s_cidx + G::NCELLS * 27);
-        cp_async_commit(); // [cidx(b1)]
+          brick_stage_foreign_async<k, BZ>(maps, blockIdx.x + gridDim.x, gidx + G::NFP);
+        cp_async_commit(); // [foreign(b1)]
       }
-    for (int bi = blockIdx.x; bi < n_bricks; bi += gridDim.x, buf ^= 1)
+    else
+      {
+        brick_stage_cidx_async<k, BZ>(bd_next, cidx, s_cidx);
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+      }
+    for (int bi = blockIdx.x; bi < n_bricks; bi += gridDim.x, buf ^= 1, fb = (fb + 1) % 3)
       {
         const BrickDesc bd       = bd_next;
         const bool      has_next = bi + (int)gridDim.x < n_bricks;
@@ -1199,7 +1243,7 @@ namespace dasm
           bd_next = bricks[bi + gridDim.x]; // descriptor of the next brick: latency hidden behind this brick
         const int       ncells   = bd.b[0] * bd.b[1] * bd.b[2];
         const uint32_t *cur_cidx = s_cidx + buf * (G::NCELLS * 27);
-        uint32_t *      cur_gidx = LIN ? gidx + buf * G::NFOREIGN : gidx;
+        uint32_t *      cur_gidx = LIN ? gidx + fb * G::NFP : gidx;
         T               ni_a[NextInitRegs<k, BZ>::IT], ni_b[NextInitRegs<k, BZ>::IT];
         brick_next_init_load<k, BZ, T>(bd, ni, ni_a, ni_b);
         if (LIN)
@@ -1319,12 +1363,11 @@ namespace dasm
             if (has_next)
               stage_codes(bd_next, buf ^ 1);
             if (has_next && !late_tile)
-              brick_issue_loads_lin<k, BZ, T>(bd_next, s_own, s_for, n_for, var_flags, s_cidx + (buf ^ 1) * (G::NCELLS * 27), tile,
-                                              gidx + (buf ^ 1) * G::NFOREIGN, src);
+              brick_issue_loads_lin<k, BZ, T>(bd_next, tb, gidx + ((fb + 1) % 3) * G::NFP, tile, src);
             cp_async_commit(); // [tile(i+1)]
             if (bi + 2 * (int)gridDim.x < n_bricks)
-              brick_stage_cidx_async<k, BZ>(bricks[bi + 2 * gridDim.x], cidx, s_cidx + buf * (G::NCELLS * 27));
-            cp_async_commit(); // [cidx(i+2)]
+              brick_stage_foreign_async<k, BZ>(maps, bi + 2 * gridDim.x, gidx + ((fb + 2) % 3) * G::NFP);
+            cp_async_commit(); // [foreign(i+2)]
           }
         // phase B: plane y = t, [z][x]: S2^T in z, scale by 1/(l0[x] + l1[t] + l2[z]), S2 in z, S0 in x
         if (act)
@@ -1408,7 +1451,7 @@ namespace dasm
           cp_async_wait<1>();
         __syncthreads();
         if (LIN)
-          brick_store_lin<k, BZ, T>(bd, s_own, s_for, n_for, slots, ops0, ops1, cur_gidx, dst, acc, epi, shared_mode, dbg);
+          brick_store_lin<k, BZ, T>(bd, tb, slots, ops0, ops1, cur_gidx, dst, acc, epi, shared_mode);
         else
           brick_reduce_store<k, BZ, T>(bd, slots, ops0, ops1, gidx, dst, acc, epi, shared_mode);
         if (LIN)
@@ -1417,9 +1460,9 @@ namespace dasm
               {
                 // the next brick has another tile-map variant: its maps can only be staged once this brick is stored
                 __syncthreads();
-                stage_maps(bd_next.variant);
-                brick_issue_loads_lin<k, BZ, T>(bd_next, s_own, s_for, n_for, var_flags, s_cidx + (buf ^ 1) * (G::NCELLS * 27), tile,
-                                                gidx + (buf ^ 1) * G::NFOREIGN, src);
+                cur_variant = bd_next.variant;
+                brick_stage_tables<k, BZ>(maps, cur_variant, s_load, s_store, s_for, s_off, tb);
+                brick_issue_loads_lin<k, BZ, T>(bd_next, tb, gidx + ((fb + 1) % 3) * G::NFP, tile, src);
                 cp_async_commit();
               }
           }
