@@ -476,34 +476,19 @@ namespace dasm
   }
 
   // sum of the cell contributions of one DoF in a fixed order (deterministic); m = mask of the directions with
-  // a second contribution
+  // a second contribution.  Branch-free: absent contributions are read from the primary slot with weight 0
+  // (the branchy form costs more in divergence than the extra shared-memory reads).
   template <typename T>
   __device__ __forceinline__ T
   slot_sum(const T *slots, const int o, const unsigned m, const int dx, const int dy, const int dz)
   {
-    T y = slots[o];
-    if (m & 1u)
-      y += slots[o + dx];
-    if (m & 2u)
-      {
-        y += slots[o + dy];
-        if (m & 1u)
-          y += slots[o + dy + dx];
-      }
-    if (m & 4u)
-      {
-        T z = slots[o + dz];
-        if (m & 1u)
-          z += slots[o + dz + dx];
-        if (m & 2u)
-          {
-            z += slots[o + dz + dy];
-            if (m & 1u)
-              z += slots[o + dz + dy + dx];
-          }
-        y += z;
-      }
-    return y;
+    const int ex = (m & 1u) ? dx : 0, ey = (m & 2u) ? dy : 0, ez = (m & 4u) ? dz : 0;
+    const T   wx = (m & 1u) ? T(1) : T(0), wy = (m & 2u) ? T(1) : T(0), wz = (m & 4u) ? T(1) : T(0);
+    const T   a  = slots[o] + wx * slots[o + ex];
+    const T   b  = slots[o + ey] + wx * slots[o + ey + ex];
+    const T   c  = slots[o + ez] + wx * slots[o + ez + ex];
+    const T   d  = slots[o + ez + ey] + wx * slots[o + ez + ey + ex];
+    return (a + wy * b) + wz * (c + wy * d);
   }
 
   // store of a brick in the order of its own DoF range (coalesced global access; a class-sorted order with
