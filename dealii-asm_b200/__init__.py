@@ -59,7 +59,7 @@ def lib():
         _lib.dasm_ctx_stream.restype = ctypes.c_void_p
         for name in ("dasm_ctx_launch_count", "dasm_mesh_n_cells", "dasm_mesh_n_global_cells", "dasm_op_n_dofs",
                      "dasm_op_n_ghost", "dasm_op_vec_size", "dasm_op_n_global_dofs", "dasm_op_constrained_dofs",
-                     "dasm_fdm_n_instances", "dasm_fdm_memory_consumption"):
+                     "dasm_fdm_n_instances", "dasm_fdm_memory_consumption", "dasm_op_n_fast_bricks", "dasm_fdm_n_fast_bricks"):
             getattr(_lib, name).restype = ctypes.c_longlong
     return _lib
 
@@ -180,6 +180,9 @@ class LaplaceOperatorMatrixFree:
     def n_dofs(self):
         return lib().dasm_op_n_dofs(self.h)
 
+    def n_fast_bricks(self):
+        return lib().dasm_op_n_fast_bricks(self.h)
+
     def vec_size(self):
         return lib().dasm_op_vec_size(self.h)
 
@@ -281,6 +284,9 @@ class ASPoissonPreconditioner:
 
     def n_fdm_instances(self):
         return lib().dasm_fdm_n_instances(self.h)
+
+    def n_fast_bricks(self):
+        return lib().dasm_fdm_n_fast_bricks(self.h)
 
     def memory_consumption(self):
         return lib().dasm_fdm_memory_consumption(self.h)

@@ -18,6 +18,7 @@
 #include "../../include/dasm.h"
 #include "kernels.cuh"
 #include "kernels_brick.cuh"
+#include "kernels_fast.cuh"
 #include "mesh.h"
 
 using namespace dasm;
@@ -288,6 +289,16 @@ struct dasm_op
   BrickMaps         maps = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0}; // tile maps (coalesced gather / store)
   void *            d_map_bufs[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int               n_sm      = 148;
+  int               max_smem  = 48 * 1024; // opt-in dynamic shared memory per block
+  // warp-specialised kernels (kernels_fast.cuh) for the regular bricks; the other bricks go through the brick kernels
+  bool              fast_ok     = false;
+  uint16_t *        d_fast_ltab = nullptr;
+  uint16_t *        d_fast_ftab = nullptr;
+  uint32_t *        d_fast_ids  = nullptr; // regular bricks
+  uint32_t *        d_slow_ids  = nullptr; // all other bricks
+  int               n_fast = 0, n_slow = 0;
+  std::vector<uint32_t> h_fast_ids;
+  double            lap_mats[4][81]; // M, g0 K, g1 K, g2 K (row-major n x n)
 
   dasm_op(int degree)
     : basis(degree)
@@ -316,6 +327,12 @@ struct dasm_fdm
   uint32_t *d_pidx   = nullptr; // explicit patch index list for n_overlap > 1
   int       wmode    = 0;       // kernel weight mode
   bool      w_pre = false, w_post = false;
+  // warp-specialised kernel: bricks with the most frequent instance triple and weight pattern
+  bool      fast_ok    = false;
+  uint32_t *d_fast_ids = nullptr, *d_slow_ids = nullptr;
+  int       n_fast = 0, n_slow = 0;
+  double    fast_mats[6][81]; // Ax Ay Az Bx By Bz
+  double    fast_inv[729];
   std::vector<double>   h_S, h_lam; // double copies for inspection
   std::vector<uint32_t> h_inst;
   std::vector<double>   h_weights;
@@ -377,6 +394,34 @@ struct dasm_cheb
       using T = float;                            \
       __VA_ARGS__;                                \
     }
+
+// tile layout parameters of kernels_fast.cuh (FastSkew) for the host-side table construction
+static void
+fast_tile_params(const int k, const int esize, int &skew, int &padz)
+{
+  skew = 0;
+  padz = 0;
+  if (esize == 8)
+    {
+      switch (k)
+        {
+          case 3: skew = FastSkew<3, 8>::skew; padz = FastSkew<3, 8>::padz; break;
+          case 4: skew = FastSkew<4, 8>::skew; padz = FastSkew<4, 8>::padz; break;
+          case 5: skew = FastSkew<5, 8>::skew; padz = FastSkew<5, 8>::padz; break;
+          default: break;
+        }
+    }
+  else
+    {
+      switch (k)
+        {
+          case 3: skew = FastSkew<3, 4>::skew; padz = FastSkew<3, 4>::padz; break;
+          case 4: skew = FastSkew<4, 4>::skew; padz = FastSkew<4, 4>::padz; break;
+          case 5: skew = FastSkew<5, 4>::skew; padz = FastSkew<5, 4>::padz; break;
+          default: break;
+        }
+    }
+}
 
 static inline unsigned
 nblocks(long long n, int bs = 256)
@@ -571,6 +616,33 @@ epilogue_n_operands(const Epilogue<T> &epi)
   return 0;
 }
 
+// warp-specialised Laplace kernel over the regular bricks; false: not available (shared memory), nothing launched
+template <int K, typename T>
+static bool
+launch_laplace_fast(dasm_op *op, T *dst, const T *src, const Epilogue<T> &epi, const int shared_mode, const NextInit<T> &ni)
+{
+  using G             = FastGeom<K, T>;
+  constexpr size_t smem = G::smem_bytes(1, 2, 1);
+  if (smem > (size_t)op->max_smem)
+    return false;
+  constexpr int             n = K + 1;
+  FastLaplaceMats<T, K + 1> mats;
+  for (int i = 0; i < n * n; ++i)
+    {
+      mats.M[i]  = (T)op->lap_mats[0][i];
+      mats.K0[i] = (T)op->lap_mats[1][i];
+      mats.K1[i] = (T)op->lap_mats[2][i];
+      mats.K2[i] = (T)op->lap_mats[3][i];
+    }
+  FastMaps fm = {op->d_fast_ltab, op->d_fast_ftab, op->maps.foreign_gidx, op->d_fast_ids, op->n_fast};
+  auto     kern = laplace_fast_kernel<K, T>;
+  CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = std::min(op->n_fast, op->n_sm);
+  kern<<<grid, G::NT, smem, op->ctx->stream>>>(src, dst, (T *)op->d_acc, epi, op->d_bricks, mats, shared_mode, ni, fm);
+  op->ctx->launches++;
+  return true;
+}
+
 template <int K, int BZ, typename T>
 static void
 launch_laplace_brick(dasm_op *op, T *dst, const T *src, const Epilogue<T> &epi, bool copy_constrained, const int shared_mode,
@@ -584,26 +656,42 @@ launch_laplace_brick(dasm_op *op, T *dst, const T *src, const Epilogue<T> &epi, 
     KernelTimer timer(ctx, KC_LAPLACE);
     if (op->geom_mode == 0)
       {
-        auto      kern = laplace_brick_kernel<K, T, BZ, 0>;
-        const int grid = brick_grid<K, BZ, T>(op, kern, smem);
-        kern<<<grid, BrickGeom<K, BZ>::NT, smem, ctx->stream>>>(src, dst, (T *)op->d_acc, epi, op->d_cidx, op->d_bricks, op->n_bricks,
-                                                                 (const T *)nullptr, op->cart, n_ops, shared_mode, ni, op->maps);
+        // regular bricks: warp-specialised kernel; the rest (if any): brick kernel over the list of the other bricks
+        const uint32_t *order    = nullptr;
+        int             n_bricks = op->n_bricks;
+        if constexpr (BZ == 4 && K >= 2 && K <= 4)
+          {
+            if (op->fast_ok && launch_laplace_fast<K, T>(op, dst, src, epi, shared_mode, ni))
+              {
+                order    = op->d_slow_ids;
+                n_bricks = op->n_slow;
+              }
+          }
+        if (n_bricks > 0)
+          {
+            auto      kern = laplace_brick_kernel<K, T, BZ, 0>;
+            const int grid = std::min(n_bricks, brick_grid<K, BZ, T>(op, kern, smem));
+            kern<<<grid, BrickGeom<K, BZ>::NT, smem, ctx->stream>>>(src, dst, (T *)op->d_acc, epi, op->d_cidx, op->d_bricks, n_bricks,
+                                                                     (const T *)nullptr, op->cart, n_ops, shared_mode, ni, op->maps, order);
+            ctx->launches++;
+          }
       }
     else if (op->geom_mode == 1)
       {
         auto      kern = laplace_brick_kernel<K, T, BZ, 1>;
         const int grid = brick_grid<K, BZ, T>(op, kern, smem);
         kern<<<grid, BrickGeom<K, BZ>::NT, smem, ctx->stream>>>(src, dst, (T *)op->d_acc, epi, op->d_cidx, op->d_bricks, op->n_bricks,
-                                                                 (const T *)op->d_geom, op->cart, n_ops, shared_mode, ni, op->maps);
+                                                                 (const T *)op->d_geom, op->cart, n_ops, shared_mode, ni, op->maps, (const uint32_t *)nullptr);
+        ctx->launches++;
       }
     else
       {
         auto      kern = laplace_brick_kernel<K, T, BZ, 2>;
         const int grid = brick_grid<K, BZ, T>(op, kern, smem);
         kern<<<grid, BrickGeom<K, BZ>::NT, smem, ctx->stream>>>(src, dst, (T *)op->d_acc, epi, op->d_cidx, op->d_bricks, op->n_bricks,
-                                                                 (const T *)op->d_qcoef, op->cart, n_ops, shared_mode, ni, op->maps);
+                                                                 (const T *)op->d_qcoef, op->cart, n_ops, shared_mode, ni, op->maps, (const uint32_t *)nullptr);
+        ctx->launches++;
       }
-    ctx->launches++;
   }
   CUDA_CHECK(cudaGetLastError());
   brick_post_exchange<T>(op, dst, shared_mode, true);
@@ -729,6 +817,37 @@ launch_fdm(dasm_fdm *f, T *dst, const T *src)
   DISPATCH_PATCH(f->m, launch_fdm_m<M, T>(f, dst, src));
 }
 
+template <int K, typename T>
+static bool
+launch_fdm_fast(dasm_fdm *f, T *dst, const T *src, const Epilogue<T> &epi, const int shared_mode, const NextInit<T> &ni)
+{
+  using G               = FastGeom<K, T>;
+  dasm_op *        op   = f->op;
+  constexpr size_t smem = G::smem_bytes(2, 1, 2);
+  if (smem > (size_t)op->max_smem)
+    return false;
+  constexpr int         n = K + 1;
+  FastFdmMats<T, K + 1> mats;
+  for (int i = 0; i < n * n; ++i)
+    {
+      mats.Ax[i] = (T)f->fast_mats[0][i];
+      mats.Ay[i] = (T)f->fast_mats[1][i];
+      mats.Az[i] = (T)f->fast_mats[2][i];
+      mats.Bx[i] = (T)f->fast_mats[3][i];
+      mats.By[i] = (T)f->fast_mats[4][i];
+      mats.Bz[i] = (T)f->fast_mats[5][i];
+    }
+  for (int i = 0; i < n * n * n; ++i)
+    mats.inv[i] = (T)f->fast_inv[i];
+  FastMaps fm = {op->d_fast_ltab, op->d_fast_ftab, op->maps.foreign_gidx, f->d_fast_ids, f->n_fast};
+  auto     kern = fdm_fast_kernel<K, T>;
+  CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = std::min(f->n_fast, op->n_sm);
+  kern<<<grid, G::NT, smem, op->ctx->stream>>>(src, dst, (T *)op->d_acc, epi, op->d_bricks, mats, shared_mode, ni, fm);
+  op->ctx->launches++;
+  return true;
+}
+
 template <int K, int BZ, typename T>
 static void
 launch_fdm_brick(dasm_fdm *f, T *dst, const T *src, const Epilogue<T> &epi, const int shared_mode, const NextInit<T> &ni)
@@ -743,13 +862,26 @@ launch_fdm_brick(dasm_fdm *f, T *dst, const T *src, const Epilogue<T> &epi, cons
   for (int i = 0; i < 16; ++i)
     wt.v[i] = (T)f->wtab[i];
   {
-    KernelTimer timer(ctx, KC_FDM);
-    auto        kern = fdm_brick_kernel<K, T, BZ>;
-    const int   grid = brick_grid<K, BZ, T>(op, kern, smem);
-    kern<<<grid, BrickGeom<K, BZ>::NT, smem, ctx->stream>>>(src, dst, (T *)op->d_acc, epi, op->d_cidx, op->d_bricks, op->n_bricks, f->d_inst,
-                                                             (const T *)f->d_S, (const T *)f->d_lam, (const uint8_t *)(f->wmode == 1 ? f->d_cwcode : nullptr), wt, f->d_brick_tri,
-                                                             (int)f->w_pre, (int)f->w_post, n_ops, shared_mode, ni, op->maps, dbg);
-    ctx->launches++;
+    KernelTimer     timer(ctx, KC_FDM);
+    const uint32_t *order    = nullptr;
+    int             n_bricks = op->n_bricks;
+    if constexpr (BZ == 4 && K >= 2 && K <= 4)
+      {
+        if (f->fast_ok && launch_fdm_fast<K, T>(f, dst, src, epi, shared_mode, ni))
+          {
+            order    = f->d_slow_ids;
+            n_bricks = f->n_slow;
+          }
+      }
+    if (n_bricks > 0)
+      {
+        auto      kern = fdm_brick_kernel<K, T, BZ>;
+        const int grid = std::min(n_bricks, brick_grid<K, BZ, T>(op, kern, smem));
+        kern<<<grid, BrickGeom<K, BZ>::NT, smem, ctx->stream>>>(src, dst, (T *)op->d_acc, epi, op->d_cidx, op->d_bricks, n_bricks, f->d_inst,
+                                                                 (const T *)f->d_S, (const T *)f->d_lam, (const uint8_t *)(f->wmode == 1 ? f->d_cwcode : nullptr), wt, f->d_brick_tri,
+                                                                 (int)f->w_pre, (int)f->w_post, n_ops, shared_mode, ni, op->maps, dbg, order);
+        ctx->launches++;
+      }
   }
   CUDA_CHECK(cudaGetLastError());
   brick_post_exchange<T>(op, dst, shared_mode, f->weight_type != DASM_WEIGHT_RAS);
@@ -1513,6 +1645,67 @@ dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping
                 op->shared_ranges_ok   = true;
                 cudaFree(op->d_bricks);
                 op->d_bricks = dev_upload(bricks, ctx->stream);
+                // ---- warp-specialised kernels: tables of the regular variant (full brick, six shared faces, no
+                // constrained DoFs) in the skewed tile layout of kernels_fast.cuh, and the lists of regular / other bricks
+                const char *nofast = getenv("DASM_NO_FAST");
+                if (degree >= 2 && degree <= 4 && !(nofast && nofast[0] == '1'))
+                  {
+                    const uint32_t reg_sig = 4u | (4u << 4) | (4u << 8) | (0x3Fu << 12);
+                    const auto     itv     = variant_of.find(reg_sig);
+                    int            skew = 0, padz = 0;
+                    fast_tile_params(k, (int)op->esize(), skew, padz);
+                    const int  SZ    = TX * TX + 4 * skew + padz;
+                    const int  NOWN  = 64 * k * k * k, NPRIV = (4 * k - 1) * (4 * k - 1) * (4 * k - 1);
+                    auto       faddr = [&](uint32_t plin) {
+                      const int px = plin % TX, py = (plin / TX) % TY, pz = plin / (TX * TY);
+                      return (uint16_t)(pz * SZ + py * TX + skew * (py / k) + px);
+                    };
+                    bool regular = itv != variant_of.end() && variants[itv->second].flags == 0 &&
+                                   (int)variants[itv->second].store.size() == NOWN && (int)variants[itv->second].ftab.size() == NPTS - NOWN;
+                    if (regular)
+                      {
+                        const Variant &       var = variants[itv->second];
+                        std::vector<uint16_t> lt((NOWN + 7) / 8 * 8, 0), ft(NFP, 0);
+                        for (int i = 0; i < NOWN && regular; ++i)
+                          {
+                            if (var.load[i] == 0xFFFFu)
+                              regular = false;
+                            else
+                              lt[i] = faddr(var.load[i]);
+                          }
+                        for (size_t j = 0; j < var.ftab.size(); ++j)
+                          ft[j] = faddr(var.ftab[j] & 0x1FFFu);
+                        std::vector<uint32_t> fast_ids, slow_ids;
+                        for (size_t b = 0; b < bricks.size(); ++b)
+                          {
+                            const BrickDesc &bd = bricks[b];
+                            bool             r  = regular && bd.variant == itv->second && bd.npriv == NPRIV && bd.sh_count == (uint32_t)(NOWN - NPRIV) &&
+                                     bd.sh_base == bd.base + NPRIV;
+                            for (int j = 0; r && j < NPTS - NOWN; ++j)
+                              if (foreign_gidx[b * NFP + j] == INVALID_INDEX)
+                                r = false;
+                            (r ? fast_ids : slow_ids).push_back((uint32_t)b);
+                          }
+                        if (regular && !fast_ids.empty())
+                          {
+                            op->fast_ok     = true;
+                            op->d_fast_ltab = dev_upload(lt, ctx->stream);
+                            op->d_fast_ftab = dev_upload(ft, ctx->stream);
+                            op->d_fast_ids  = dev_upload(fast_ids, ctx->stream);
+                            op->d_slow_ids  = dev_upload(slow_ids, ctx->stream);
+                            op->n_fast      = (int)fast_ids.size();
+                            op->n_slow      = (int)slow_ids.size();
+                            op->h_fast_ids  = fast_ids;
+                          }
+                      }
+                    // 1-D matrices of the Kronecker form of the Cartesian cell matrix
+                    for (int i = 0; i < n * n; ++i)
+                      {
+                        op->lap_mats[0][i] = op->basis.M_ref[i];
+                        for (int d = 0; d < 3; ++d)
+                          op->lap_mats[1 + d][i] = op->cart.g[d] * op->basis.K_ref[i];
+                      }
+                  }
               }
             else
               op->use_brick = false; // no consistent tile maps: use the generic kernels
@@ -1522,6 +1715,7 @@ dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping
         cudaDeviceProp prop;
         CUDA_CHECK(cudaGetDeviceProperties(&prop, ctx->device));
         op->n_sm = prop.multiProcessorCount;
+        op->max_smem = (int)prop.sharedMemPerBlockOptin;
       }
   }
   *out = op;
@@ -1542,6 +1736,10 @@ dasm_op_destroy(dasm_op *op)
   cudaFree(op->d_bricks);
   cudaFree(op->d_acc);
   cudaFree(op->d_shared_list);
+  cudaFree(op->d_fast_ltab);
+  cudaFree(op->d_fast_ftab);
+  cudaFree(op->d_fast_ids);
+  cudaFree(op->d_slow_ids);
   for (void *p : op->d_map_bufs)
     cudaFree(p);
   op->exchange.destroy();
@@ -1552,6 +1750,7 @@ dasm_op_destroy(dasm_op *op)
 }
 
 extern "C" long long dasm_op_n_dofs(const dasm_op *op) { return op->n_owned; }
+extern "C" long long dasm_op_n_fast_bricks(const dasm_op *op) { return (op->fast_ok && op->geom_mode == 0) ? op->n_fast : 0; }
 extern "C" long long dasm_op_n_ghost(const dasm_op *op) { return op->n_ghost; }
 extern "C" long long dasm_op_vec_size(const dasm_op *op) { return op->n_vec; }
 extern "C" long long dasm_op_n_global_dofs(const dasm_op *op) { return op->n_global_dofs; }
@@ -2169,6 +2368,7 @@ dasm_fdm_create(dasm_op *op, int n_overlap, int sub_mesh_approximation, int weig
     {
       // weight codes for the brick kernel: every compressed weight is a function of the integer patch valence of
       // its entity (1/v, 1/sqrt(v), RAS 0/1), so 1 byte per entity + a 16-entry table replace 27 numbers per cell
+      std::vector<uint8_t> codes;
       if (f->wmode == 1)
         {
           std::vector<double> cw((size_t)op->n_cells * 27);
@@ -2180,8 +2380,8 @@ dasm_fdm_create(dasm_op *op, int n_overlap, int sub_mesh_approximation, int weig
               CUDA_CHECK(cudaMemcpy(tmp.data(), f->d_cw, tmp.size() * sizeof(float), cudaMemcpyDeviceToHost));
               cw.assign(tmp.begin(), tmp.end());
             }
-          std::vector<uint8_t> codes((size_t)op->n_cells * 32, 0);
-          bool                 ok = true;
+          codes.assign((size_t)op->n_cells * 32, 0);
+          bool ok = true;
           bool                 seen[16] = {false};
           for (size_t i = 0; i < cw.size() && ok; ++i)
             {
@@ -2226,6 +2426,98 @@ dasm_fdm_create(dasm_op *op, int n_overlap, int sub_mesh_approximation, int weig
           tri[b] = make_uint4(i0[0], i0[1], i0[2], uniform ? 1u : 0u);
         }
       f->d_brick_tri = dev_upload(tri, op->ctx->stream);
+      // ---- warp-specialised kernel: the regular bricks with the most frequent instance triple whose cells all have
+      // the weight pattern of the first one; the 27 weights must be a tensor product so that they fold into the
+      // 1-D matrices (true for 1/valence, 1/sqrt(valence) and the RAS ownership weights away from boundaries)
+      if (op->fast_ok && f->m == op->k + 1 && (f->wmode == 0 || f->wmode == 1))
+        {
+          const int                                     n = op->k + 1;
+          std::map<std::array<uint32_t, 3>, int>        count;
+          for (const uint32_t b : op->h_fast_ids)
+            if (tri[b].w)
+              count[{tri[b].x, tri[b].y, tri[b].z}]++;
+          std::array<uint32_t, 3> best = {0, 0, 0};
+          int                     nbest = 0;
+          for (const auto &kv : count)
+            if (kv.second > nbest)
+              {
+                nbest = kv.second;
+                best  = kv.first;
+              }
+          std::vector<uint32_t> fast_ids, slow_ids;
+          const uint8_t *       ref_codes = nullptr;
+          std::vector<char>     is_fast(op->n_bricks, 0);
+          for (const uint32_t b : op->h_fast_ids)
+            {
+              if (nbest == 0 || !tri[b].w || tri[b].x != best[0] || tri[b].y != best[1] || tri[b].z != best[2])
+                continue;
+              bool same = true;
+              if (f->wmode == 1)
+                {
+                  const uint8_t *cb = codes.data() + (size_t)bricks[b].first_cell * 32;
+                  if (ref_codes == nullptr)
+                    ref_codes = cb;
+                  for (int c = 0; c < 64 && same; ++c)
+                    same = (memcmp(cb + c * 32, ref_codes, 27) == 0);
+                }
+              is_fast[b] = same;
+            }
+          // tensor-product factorisation of the weights
+          double w1[3][3] = {{1, 1, 1}, {1, 1, 1}, {1, 1, 1}};
+          bool   w_ok     = true;
+          if (f->wmode == 1 && ref_codes != nullptr)
+            {
+              double W[27];
+              for (int e = 0; e < 27; ++e)
+                W[e] = f->wtab[ref_codes[e]];
+              const double c = W[13];
+              if (c == 0.)
+                w_ok = false;
+              else
+                {
+                  for (int e = 0; e < 3; ++e)
+                    {
+                      w1[0][e] = W[e + 3 + 9] / c;
+                      w1[1][e] = W[1 + 3 * e + 9] / c;
+                      w1[2][e] = W[1 + 3 + 9 * e];
+                    }
+                  for (int e = 0; e < 27; ++e)
+                    {
+                      const double p = w1[0][e % 3] * w1[1][(e / 3) % 3] * w1[2][e / 9];
+                      if (std::fabs(p - W[e]) > (op->ntype == DASM_F64 ? 1e-14 : 1e-6) * std::max(1., std::fabs(W[e])))
+                        w_ok = false;
+                    }
+                }
+            }
+          for (int b = 0; b < op->n_bricks; ++b)
+            ((w_ok && is_fast[b]) ? fast_ids : slow_ids).push_back((uint32_t)b);
+          if (!fast_ids.empty())
+            {
+              auto ent = [&](int i) { return i == 0 ? 0 : (i == n - 1 ? 2 : 1); };
+              for (int d = 0; d < 3; ++d)
+                {
+                  const double *S = f->h_S.data() + (size_t)best[d] * n * n;
+                  for (int a = 0; a < n; ++a)
+                    for (int i = 0; i < n; ++i)
+                      {
+                        // first stage: u_a = sum_i S[i][a] w_i v_i;  second stage: y_o = w_o sum_i S[o][i] u_i
+                        f->fast_mats[d][a * n + i]     = S[i * n + a] * ((f->wmode == 1 && f->w_pre) ? w1[d][ent(i)] : 1.);
+                        f->fast_mats[3 + d][a * n + i] = S[a * n + i] * ((f->wmode == 1 && f->w_post) ? w1[d][ent(a)] : 1.);
+                      }
+                }
+              const double *l0 = f->h_lam.data() + (size_t)best[0] * n, *l1 = f->h_lam.data() + (size_t)best[1] * n,
+                           *l2 = f->h_lam.data() + (size_t)best[2] * n;
+              for (int z = 0; z < n; ++z)
+                for (int y = 0; y < n; ++y)
+                  for (int x = 0; x < n; ++x)
+                    f->fast_inv[(z * n + y) * n + x] = 1. / (l0[x] + l1[y] + l2[z]);
+              f->fast_ok    = true;
+              f->n_fast     = (int)fast_ids.size();
+              f->n_slow     = (int)slow_ids.size();
+              f->d_fast_ids = dev_upload(fast_ids, op->ctx->stream);
+              f->d_slow_ids = dev_upload(slow_ids, op->ctx->stream);
+            }
+        }
     }
   *out = f;
   DASM_API_END
@@ -2245,6 +2537,8 @@ dasm_fdm_destroy(dasm_fdm *f)
   cudaFree(f->d_cw);
   cudaFree(f->d_cwcode);
   cudaFree(f->d_brick_tri);
+  cudaFree(f->d_fast_ids);
+  cudaFree(f->d_slow_ids);
   cudaFree(f->d_pidx);
   delete f;
   DASM_API_END
@@ -2269,6 +2563,7 @@ dasm_fdm_vmult_hooks(dasm_fdm *f, void *dst, const void *src, const dasm_hook *p
 }
 
 extern "C" long long dasm_fdm_n_instances(const dasm_fdm *f) { return f->n_instances; }
+extern "C" long long dasm_fdm_n_fast_bricks(const dasm_fdm *f) { return f->fast_ok ? f->n_fast : 0; }
 extern "C" long long
 dasm_fdm_memory_consumption(const dasm_fdm *f)
 {

@@ -727,8 +727,10 @@ namespace dasm
                        const int n_ops,
                        const int shared_mode,
                        const NextInit<T> ni,
-                       const BrickMaps maps)
+                       const BrickMaps maps,
+                       const uint32_t *__restrict__ order) // optional: bricks to process (nullptr: all, in order)
   {
+    auto BID = [&](const int i) { return order != nullptr ? (int)order[i] : i; };
     using G         = BrickGeom<k, BZ>;
     constexpr int n = k + 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -758,11 +760,11 @@ namespace dasm
     if (blockIdx.x >= n_bricks)
       return;
     int       buf = 0, fb = 0; // buf: parity of the brick; fb: ring position (mod 3) of its foreign-index buffer
-    BrickDesc bd_next   = bricks[blockIdx.x];
+    BrickDesc bd_next   = bricks[BID(blockIdx.x)];
     bool      late_tile = false;
     if (LIN)
       {
-        brick_stage_foreign_async<k, BZ>(maps, blockIdx.x, gidx);
+        brick_stage_foreign_async<k, BZ>(maps, BID(blockIdx.x), gidx);
         cp_async_commit();
         cp_async_wait<0>();
         cur_variant = bd_next.variant;
@@ -770,7 +772,7 @@ namespace dasm
         brick_issue_loads_lin<k, BZ, T>(bd_next, tb, gidx, tile, src);
         cp_async_commit(); // [tile(b0)]
         if (blockIdx.x + gridDim.x < (unsigned)n_bricks)
-          brick_stage_foreign_async<k, BZ>(maps, blockIdx.x + gridDim.x, gidx + G::NFP);
+          brick_stage_foreign_async<k, BZ>(maps, BID(blockIdx.x + gridDim.x), gidx + G::NFP);
         cp_async_commit(); // [foreign(b1)]
       }
     else
@@ -785,7 +787,7 @@ namespace dasm
         const BrickDesc bd       = bd_next;
         const bool      has_next = bi + (int)gridDim.x < n_bricks;
         if (has_next)
-          bd_next = bricks[bi + gridDim.x]; // descriptor of the next brick: latency hidden behind this brick
+          bd_next = bricks[BID(bi + gridDim.x)]; // descriptor of the next brick: latency hidden behind this brick
         const int       ncells   = bd.b[0] * bd.b[1] * bd.b[2];
         const uint32_t *cur_cidx = s_cidx + buf * (G::NCELLS * 27);
         uint32_t *      cur_gidx = LIN ? gidx + fb * G::NFP : gidx;
@@ -848,7 +850,7 @@ namespace dasm
               brick_issue_loads_lin<k, BZ, T>(bd_next, tb, gidx + ((fb + 1) % 3) * G::NFP, tile, src);
             cp_async_commit(); // [tile(i+1)]
             if (bi + 2 * (int)gridDim.x < n_bricks)
-              brick_stage_foreign_async<k, BZ>(maps, bi + 2 * gridDim.x, gidx + ((fb + 2) % 3) * G::NFP);
+              brick_stage_foreign_async<k, BZ>(maps, BID(bi + 2 * gridDim.x), gidx + ((fb + 2) % 3) * G::NFP);
             cp_async_commit(); // [foreign(i+2)]
           }
         if (GEOM == 0)
@@ -1143,8 +1145,10 @@ namespace dasm
                    const int shared_mode,
                    const NextInit<T> ni,
                    const BrickMaps maps,
-                   const int dbg)
+                   const int dbg,
+                   const uint32_t *__restrict__ order) // optional: bricks to process (nullptr: all, in order)
   {
+    auto BID = [&](const int i) { return order != nullptr ? (int)order[i] : i; };
     using G          = BrickGeom<k, BZ>;
     constexpr int n  = k + 1;
     constexpr int n2 = n * n;
@@ -1186,7 +1190,7 @@ namespace dasm
     if (blockIdx.x >= n_bricks)
       return;
     int       buf = 0, fb = 0; // buf: parity of the brick; fb: ring position (mod 3) of its foreign-index buffer
-    BrickDesc bd_next   = bricks[blockIdx.x];
+    BrickDesc bd_next   = bricks[BID(blockIdx.x)];
     bool      late_tile = false;
     auto      stage_codes = [&](const BrickDesc &b2, const int which) {
       if (cw != nullptr)
@@ -1201,7 +1205,7 @@ namespace dasm
     };
     if (LIN)
       {
-        brick_stage_foreign_async<k, BZ>(maps, blockIdx.x, gidx);
+        brick_stage_foreign_async<k, BZ>(maps, BID(blockIdx.x), gidx);
         cp_async_commit();
         cp_async_wait<0>();
         cur_variant = bd_next.variant;
@@ -1210,7 +1214,7 @@ namespace dasm
         brick_issue_loads_lin<k, BZ, T>(bd_next, tb, gidx, tile, src);
         cp_async_commit(); // [tile(b0)]
         if (blockIdx.x + gridDim.x < (unsigned)n_bricks)
-          brick_stage_foreign_async<k, BZ>(maps, blockIdx.x + gridDim.x, gidx + G::NFP);
+          brick_stage_foreign_async<k, BZ>(maps, BID(blockIdx.x + gridDim.x), gidx + G::NFP);
         cp_async_commit(); // [foreign(b1)]
       }
     else
@@ -1225,7 +1229,7 @@ namespace dasm
         const BrickDesc bd       = bd_next;
         const bool      has_next = bi + (int)gridDim.x < n_bricks;
         if (has_next)
-          bd_next = bricks[bi + gridDim.x]; // descriptor of the next brick: latency hidden behind this brick
+          bd_next = bricks[BID(bi + gridDim.x)]; // descriptor of the next brick: latency hidden behind this brick
         const int       ncells   = bd.b[0] * bd.b[1] * bd.b[2];
         const uint32_t *cur_cidx = s_cidx + buf * (G::NCELLS * 27);
         uint32_t *      cur_gidx = LIN ? gidx + fb * G::NFP : gidx;
@@ -1259,7 +1263,7 @@ namespace dasm
         const int      cx = c % bd.b[0], cy = (c / bd.b[0]) % bd.b[1], cz = c / (bd.b[0] * bd.b[1]);
         const uint32_t cell = bd.first_cell + c;
         T *            S    = slots + c * G::CS;
-        const uint4    tri     = brick_tri[bi];
+        const uint4    tri     = brick_tri[BID(bi)];
         const uint32_t r0 = tri.x, r1 = tri.y, r2 = tri.z;
         const bool     uniform = tri.w != 0;
         uint32_t       i0 = r0, i1 = r1, i2 = r2;
@@ -1351,7 +1355,7 @@ namespace dasm
               brick_issue_loads_lin<k, BZ, T>(bd_next, tb, gidx + ((fb + 1) % 3) * G::NFP, tile, src);
             cp_async_commit(); // [tile(i+1)]
             if (bi + 2 * (int)gridDim.x < n_bricks)
-              brick_stage_foreign_async<k, BZ>(maps, bi + 2 * gridDim.x, gidx + ((fb + 2) % 3) * G::NFP);
+              brick_stage_foreign_async<k, BZ>(maps, BID(bi + 2 * gridDim.x), gidx + ((fb + 2) % 3) * G::NFP);
             cp_async_commit(); // [foreign(i+2)]
           }
         // phase B: plane y = t, [z][x]: S2^T in z, scale by 1/(l0[x] + l1[t] + l2[z]), S2 in z, S0 in x

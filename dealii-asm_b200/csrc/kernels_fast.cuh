@@ -1,0 +1,675 @@
+// Warp-specialised brick kernels (sm_100a) for the regular part of a mesh: full 4 x 4 x 4 bricks whose six
+// faces are shared with other bricks, without constrained DoFs, uniform Cartesian geometry (Laplace) or one
+// 1-D eigen-decomposition triple for all cells of the brick (FDM).  Everything else is processed by the kernels
+// of kernels_brick.cuh in a second launch (the shared-face protocol is order independent).
+//
+//   block = 64 n compute threads + 64 mover threads (n = k + 1)
+//
+//   compute warps   thread (cell c, plane t), lanes = cells.  The operators are applied in their
+//                   Kronecker form with ALL 1-D matrices as kernel parameters (constant-bank operands of the
+//                   FMAs, no matrix loads):
+//                     Laplace (operator.h:866-875 on a Cartesian cell; N^T D^T W D N = K, N^T W N = M exactly):
+//                       A_cell = g0 K(x)M(x)M + g1 M(x)K(x)M + g2 M(x)M(x)K          7 sweeps instead of 12
+//                       phase A  planes y = t:  q = Mx Mz v,  p = (g0 Kx Mz + g2 Mx Kz) v
+//                       phase B  planes z = t:  r = My p + g1 Ky q
+//                     FDM (matrix_free.h:1046-1052 apply_inverse, weights 1366-1488 folded into the first / last
+//                     1-D matrices when they are a tensor product):
+//                       phase A  planes z = t:  Sx^T Wx, Sy^T Wy      phase B  planes y = t:  Sz^T Wz, 1/(lx+ly+lz), Sz, Sx
+//                       phase C  planes z = t:  Wy' Sy
+//                   The last contraction is linear and uses the same matrix in every cell, so the plane z = k of the
+//                   cell below is added to the plane z = 0 BEFORE it; the contributions of the x / y neighbours
+//                   are merged with warp shuffles (lane - 1, lane - 4).  Every DoF of the brick closure is then
+//                   written exactly once to the output tile: no slot reduction, no shared-memory atomics.
+//                   The tile of the NEXT brick is gathered by the compute threads themselves with cp.async (fire and
+//                   forget, coalesced: the own DoFs of a brick are one contiguous range) as soon as the current tile
+//                   has been read (after phase A), and awaited at the top of the next brick.
+//   mover warps     stage the epilogue operands (b, or x and x_old) of a brick in shared memory with cp.async one
+//                   brick ahead, and run the fused vector epilogue + coalesced stores / red.add of the PREVIOUS
+//                   result from the output tile while the compute warps work on the next brick; also the
+//                   pre-initialisation of the next kernel's destination on the brick's shared DoFs.
+//                   Hand-over through named barriers (bar.arrive / bar.sync producer-consumer pairs).
+//
+// Tile layout: point (X, Y, Z) at Z * SZ + Y * TP + SKEW * (Y / k) + X; SKEW / SZ make the plane accesses of a
+// half-warp (16 cells (cx, cy)) hit 16 different 8-byte banks (32 lanes / 32 banks for float).
+#pragma once
+#include "kernels_brick.cuh"
+
+namespace dasm
+{
+  template <int k, int ES>
+  struct FastSkew
+  {
+    static constexpr int skew = 0, padz = 0;
+  };
+  template <> struct FastSkew<3, 8> { static constexpr int skew = 5, padz = 0; };
+  template <> struct FastSkew<3, 4> { static constexpr int skew = 1, padz = 7; };
+  template <> struct FastSkew<4, 8> { static constexpr int skew = 1, padz = 0; };
+  template <> struct FastSkew<4, 4> { static constexpr int skew = 1, padz = 7; };
+  template <> struct FastSkew<5, 8> { static constexpr int skew = 3, padz = 0; };
+  template <> struct FastSkew<5, 4> { static constexpr int skew = 3, padz = 11; };
+
+  template <int k, typename T>
+  struct FastGeom
+  {
+    static constexpr int n      = k + 1;
+    static constexpr int TP     = 4 * k + 1;
+    static constexpr int SKEW   = FastSkew<k, (int)sizeof(T)>::skew;
+    static constexpr int SZ     = TP * TP + 4 * SKEW + FastSkew<k, (int)sizeof(T)>::padz;
+    static constexpr int TILE   = (TP * SZ + 3) / 4 * 4;
+    static constexpr int NCELLS = 64;
+    static constexpr int NCT    = NCELLS * n; // compute threads
+    static constexpr int NMT    = 64;         // mover threads
+    static constexpr int NT     = NCT + NMT;
+    static constexpr int CS     = (n * n * n) | 1;
+    static constexpr int NOWN   = 64 * k * k * k;
+    static constexpr int NPRIV  = (4 * k - 1) * (4 * k - 1) * (4 * k - 1);
+    static constexpr int NFOR   = TP * TP * TP - NOWN;
+    static constexpr int NFP    = (NFOR + 3) / 4 * 4;
+    static constexpr int NOWNP  = (NOWN + 7) / 8 * 8;
+    static constexpr int NPRIVP = (NPRIV + 3) / 4 * 4;
+    // tile | [out] | X (n_x slots of 64 CS) | operands (n_ops x NPRIVP) | ltab u16[NOWNP] | ftab u16[NFP]
+    // (Laplace: n_x = 2 and the output tile aliases the first X slot; FDM: n_x = 1 and a separate output tile)
+    static constexpr size_t
+    smem_bytes(int n_tiles, int n_x, int n_ops)
+    {
+      return (size_t)(n_tiles * TILE + n_x * NCELLS * CS + 4 + n_ops * NPRIVP) * sizeof(T) + 16 +
+             (size_t)(NOWNP + NFP) * sizeof(uint16_t);
+    }
+    __host__ __device__ static constexpr int
+    addr(int X, int Y, int Z)
+    {
+      return Z * SZ + Y * TP + SKEW * (Y / k) + X;
+    }
+  };
+
+  // tables of the regular brick variant and the list of bricks the kernel processes
+  struct FastMaps
+  {
+    const uint16_t *ltab;         // [NOWN]  tile address of own DoF base + i
+    const uint16_t *ftab;         // [NFP]   tile address of the j-th foreign point
+    const uint32_t *foreign_gidx; // [brick][NFP] global index of the j-th foreign point
+    const uint32_t *brick_ids;    // bricks to process
+    int             n;
+  };
+
+  template <typename T, int n>
+  struct FastLaplaceMats
+  {
+    T M[n * n], K0[n * n], K1[n * n], K2[n * n]; // row-major [o * n + i]; Kd = g_d K
+  };
+
+  template <typename T, int n>
+  struct FastFdmMats
+  {
+    T Ax[n * n], Ay[n * n], Az[n * n]; // first stage (S^T diag(w_pre)), applied as A v
+    T Bx[n * n], By[n * n], Bz[n * n]; // second stage (diag(w_post) S)
+    T inv[n * n * n];                  // 1 / (lx[x] + ly[y] + lz[z]) at (z n + y) n + x
+  };
+
+  enum
+  {
+    FB_OUT_FULL  = 1, // compute -> movers: the result of a brick is in the output tile
+    FB_OUT_EMPTY = 2, // movers -> compute: the output tile has been stored
+    FB_COMPUTE   = 3, // compute warps only
+    FB_MOVERS    = 4  // mover warps only
+  };
+
+  __device__ __forceinline__ void
+  bar_sync(const int id, const int count)
+  {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+  }
+  __device__ __forceinline__ void
+  bar_arrive(const int id, const int count)
+  {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+  }
+  __device__ __forceinline__ void
+  cp_async_wait_all()
+  {
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
+  }
+
+  // r[o] (+)= sum_i M[o n + i] v[i]
+  template <int n, typename T, bool ADD>
+  __device__ __forceinline__ void
+  mat_vec(T (&r)[n], const T *M, const T (&v)[n])
+  {
+    if (!ADD)
+      {
+#pragma unroll
+        for (int o = 0; o < n; ++o)
+          r[o] = M[o * n] * v[0];
+      }
+#pragma unroll
+    for (int i = ADD ? 0 : 1; i < n; ++i)
+#pragma unroll
+      for (int o = 0; o < n; ++o)
+        r[o] += M[o * n + i] * v[i];
+  }
+
+
+  // ---- gather of a brick closure into the tile by the compute threads (cp.async, awaited one brick later) ----
+  template <int k, typename T>
+  struct FastCounts
+  {
+    static constexpr int NFT = (FastGeom<k, T>::NFOR + FastGeom<k, T>::NCT - 1) / FastGeom<k, T>::NCT; // foreign points per compute thread
+    static constexpr int NFM = (FastGeom<k, T>::NFOR + FastGeom<k, T>::NMT - 1) / FastGeom<k, T>::NMT; // ... per mover thread
+    static constexpr int NSI = (FastGeom<k, T>::NOWN - FastGeom<k, T>::NPRIV + FastGeom<k, T>::NMT - 1) / FastGeom<k, T>::NMT;
+  };
+
+  template <int k, typename T, int NTH, int NF>
+  __device__ __forceinline__ void
+  fast_load_foreign_idx(uint32_t (&gf)[NF], const FastMaps &maps, const uint32_t brick, const int tid)
+  {
+    using G             = FastGeom<k, T>;
+    const uint32_t *src = maps.foreign_gidx + (size_t)brick * G::NFP;
+#pragma unroll
+    for (int jj = 0; jj < NF; ++jj)
+      {
+        const int j = tid + jj * NTH;
+        gf[jj]      = (j < G::NFOR) ? __ldg(src + j) : 0u;
+      }
+  }
+
+  template <int k, typename T>
+  __device__ __forceinline__ void
+  fast_gather(T *tile, const uint16_t *ltab, const uint16_t *ftab, const uint32_t (&gf)[FastCounts<k, T>::NFT], const T *__restrict__ src,
+              const uint32_t base, const int tid)
+  {
+    using G    = FastGeom<k, T>;
+    const T *s = src + base;
+#pragma unroll 4
+    for (int i = tid; i < G::NOWN; i += G::NCT)
+      cp_async_value(tile + ltab[i], s + i);
+#pragma unroll
+    for (int jj = 0; jj < FastCounts<k, T>::NFT; ++jj)
+      {
+        const int j = tid + jj * G::NCT;
+        if (j < G::NFOR)
+          cp_async_value(tile + ftab[j], src + gf[jj]);
+      }
+  }
+
+  // ---- mover side ---------------------------------------------------------------------------------------
+  // contiguous copy of the epilogue operands on the private DoFs of a brick into shared memory
+  template <int k, typename T>
+  __device__ __forceinline__ void
+  fast_stage_ops(T *ops0, T *ops1, const Epilogue<T> &epi, const bool need0, const bool need1, const uint32_t base, const int m)
+  {
+    using G         = FastGeom<k, T>;
+    constexpr int V = 16 / (int)sizeof(T);
+    auto copy       = [&](T *s, const T *g) {
+      if ((reinterpret_cast<uintptr_t>(g) & 15) == 0)
+        {
+          for (int i = m; i < G::NPRIV / V; i += G::NMT)
+            {
+              const unsigned sa = (unsigned)__cvta_generic_to_shared(s + V * i);
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(g + V * i));
+            }
+          for (int i = (G::NPRIV / V) * V + m; i < G::NPRIV; i += G::NMT)
+            cp_async_value(s + i, g + i);
+        }
+      else
+        {
+#pragma unroll 4
+          for (int i = m; i < G::NPRIV; i += G::NMT)
+            cp_async_value(s + i, g + i);
+        }
+    };
+    if (need0)
+      copy(ops0, epi.v0 + base);
+    if (need1)
+      copy(ops1, epi.v1 + base);
+  }
+
+  // pre-initialisation of the next kernel's destination on the brick's own shared DoFs: all loads in flight at once
+  template <int k, typename T>
+  __device__ __forceinline__ void
+  fast_next_init(const NextInit<T> &ni, const uint32_t sh_base, const int m)
+  {
+    using G           = FastGeom<k, T>;
+    constexpr int NSI = FastCounts<k, T>::NSI;
+    if (ni.out == nullptr)
+      return;
+    const bool h0 = ni.v0 != nullptr, h1 = (ni.v1 != nullptr && ni.f1 != T(0));
+    T          a[NSI], b[NSI];
+#pragma unroll
+    for (int it = 0; it < NSI; ++it)
+      {
+        const int i = m + it * G::NMT;
+        const bool in = i < G::NOWN - G::NPRIV;
+        a[it]         = (h0 && in) ? __ldg(ni.v0 + sh_base + i) : T(0);
+        b[it]         = (h1 && in) ? __ldg(ni.v1 + sh_base + i) : T(0);
+      }
+#pragma unroll
+    for (int it = 0; it < NSI; ++it)
+      {
+        const int i = m + it * G::NMT;
+        if (i < G::NOWN - G::NPRIV)
+          ni.out[sh_base + i] = a[it] + ni.f1 * (a[it] - b[it]);
+      }
+  }
+
+  template <int k, typename T>
+  __device__ __forceinline__ void
+  fast_mover_loop(const T *out, T *ops0, T *ops1, const uint16_t *ltab, const uint16_t *ftab, T *__restrict__ dst, T *__restrict__ acc,
+                  const Epilogue<T> &epi, const BrickDesc *__restrict__ bricks, const FastMaps &maps, const int shared_mode,
+                  const NextInit<T> &ni, const int m)
+  {
+    using G           = FastGeom<k, T>;
+    constexpr int NFM = FastCounts<k, T>::NFM;
+    const bool need0  = (epi.kind == EPI_RESIDUAL || epi.kind == EPI_CHEB);
+    const bool need1  = (epi.kind == EPI_CHEB && epi.f1 != T(0) && epi.v1 != nullptr);
+    const T    alpha  = (epi.kind == EPI_RESIDUAL) ? T(-1) : ((epi.kind == EPI_CHEB || epi.kind == EPI_SCALE) ? epi.f2 : T(1));
+    T *        sh_dst = (shared_mode == SHARED_DIRECT) ? dst : acc;
+    const T    sh_a   = (shared_mode == SHARED_DIRECT) ? alpha : T(1);
+    int        it     = blockIdx.x;
+    uint32_t   bid    = maps.brick_ids[it];
+    BrickDesc  bd     = bricks[bid];
+    fast_stage_ops<k, T>(ops0, ops1, epi, need0, need1, bd.base, m);
+    for (; it < maps.n; it += gridDim.x)
+      {
+        const bool      has_next = it + (int)gridDim.x < maps.n;
+        const uint32_t  bid_next = has_next ? maps.brick_ids[it + gridDim.x] : bid;
+        const BrickDesc bd_next  = has_next ? bricks[bid_next] : bd;
+        uint32_t        gf[NFM];
+        fast_load_foreign_idx<k, T, G::NMT, NFM>(gf, maps, bid, m);
+        fast_next_init<k, T>(ni, bd.sh_base, m);
+        bar_sync(FB_OUT_FULL, G::NT); // the result of this brick is in the output tile
+        cp_async_wait_all();
+        bar_sync(FB_MOVERS, G::NMT); // operands staged by all movers are visible
+        {
+          T *d = dst + bd.base;
+          // private DoFs: fused epilogue, coalesced plain stores
+#pragma unroll 8
+          for (int i = m; i < G::NPRIV; i += G::NMT)
+            d[i] = epilogue_compute(epi, out[ltab[i]], need0 ? ops0[i] : T(0), need1 ? ops1[i] : T(0));
+          // own DoFs on the lower (shared) faces
+          T *sd = sh_dst + bd.base;
+#pragma unroll 4
+          for (int i = G::NPRIV + m; i < G::NOWN; i += G::NMT)
+            atomic_add(sd + i, sh_a * out[ltab[i]]);
+            // points owned by other bricks
+#pragma unroll
+          for (int jj = 0; jj < NFM; ++jj)
+            {
+              const int j = m + jj * G::NMT;
+              if (j < G::NFOR)
+                atomic_add(sh_dst + gf[jj], sh_a * out[ftab[j]]);
+            }
+        }
+        if (has_next)
+          bar_arrive(FB_OUT_EMPTY, G::NT);
+        bar_sync(FB_MOVERS, G::NMT); // all movers have read the operands: stage those of the next brick
+        if (has_next)
+          fast_stage_ops<k, T>(ops0, ops1, epi, need0, need1, bd_next.base, m);
+        bd  = bd_next;
+        bid = bid_next;
+      }
+  }
+
+  // ---- compute side: merge of the x / y neighbour contributions and exclusive store into the output tile -----
+  template <int k, typename T>
+  __device__ __forceinline__ void
+  fast_merge(T (&r)[k + 1][k + 1], const int cx, const int cy)
+  {
+#pragma unroll
+    for (int y = 0; y <= k; ++y)
+      {
+        const T from = __shfl_up_sync(0xffffffffu, r[y][k], 1);
+        if (cx > 0)
+          r[y][0] += from;
+      }
+#pragma unroll
+    for (int x = 0; x <= k; ++x)
+      {
+        const T from = __shfl_up_sync(0xffffffffu, r[k][x], 4);
+        if (cy > 0)
+          r[0][x] += from;
+      }
+  }
+
+  template <int k, typename T>
+  __device__ __forceinline__ void
+  fast_out_store(const T (&r)[k + 1][k + 1], T *op, const int cx, const int cy)
+  {
+    using G = FastGeom<k, T>;
+#pragma unroll
+    for (int y = 0; y <= k; ++y)
+#pragma unroll
+      for (int x = 0; x <= k; ++x)
+        {
+          const bool w = (x < k || cx == 3) && (y < k || cy == 3);
+          if (w)
+            op[y * G::TP + (y == k ? G::SKEW : 0) + x] = r[y][x];
+        }
+  }
+
+  template <typename T>
+  __device__ __forceinline__ T *
+  align16(T *p)
+  {
+    return reinterpret_cast<T *>((reinterpret_cast<uintptr_t>(p) + 15) & ~uintptr_t(15));
+  }
+
+  // ---- Laplace, uniform Cartesian geometry ---------------------------------------------------------------------
+  template <int k, typename T>
+  __global__ void __launch_bounds__(FastGeom<k, T>::NT, 1)
+  laplace_fast_kernel(const T *__restrict__ src,
+                      T *__restrict__ dst,
+                      T *__restrict__ acc,
+                      const Epilogue<T> epi,
+                      const BrickDesc *__restrict__ bricks,
+                      const __grid_constant__ FastLaplaceMats<T, k + 1> mats,
+                      const int         shared_mode,
+                      const NextInit<T> ni,
+                      const FastMaps    maps)
+  {
+    using G           = FastGeom<k, T>;
+    constexpr int n   = k + 1;
+    constexpr int NFT = FastCounts<k, T>::NFT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *       tile = reinterpret_cast<T *>(smem_raw);
+    T *       Xq   = tile + G::TILE;
+    T *       Xp   = Xq + G::NCELLS * G::CS;
+    T *       out  = Xq; // the output tile aliases the first exchange slot (written after all reads of it)
+    T *       ops0 = align16(Xp + G::NCELLS * G::CS);
+    uint16_t *ltab = reinterpret_cast<uint16_t *>(ops0 + G::NPRIVP);
+    uint16_t *ftab = ltab + G::NOWNP;
+    if ((int)blockIdx.x >= maps.n)
+      return;
+    for (int i = threadIdx.x; i < G::NOWN; i += G::NT)
+      ltab[i] = maps.ltab[i];
+    for (int i = threadIdx.x; i < G::NFP; i += G::NT)
+      ftab[i] = maps.ftab[i];
+    __syncthreads();
+
+    if (threadIdx.x >= G::NCT)
+      {
+        fast_mover_loop<k, T>(out, ops0, ops0, ltab, ftab, dst, acc, epi, bricks, maps, shared_mode, ni, threadIdx.x - G::NCT);
+        return;
+      }
+    const int  tid = threadIdx.x;
+    const int  c = tid % G::NCELLS, t = tid / G::NCELLS;
+    const int  cx = c & 3, cy = (c >> 2) & 3, cz = c >> 4;
+    const bool skip_last = (t == k) && (cz < 2); // whole warp: its plane z = k belongs to the cell above
+    const T *  tp = tile + G::addr(k * cx, k * cy, k * cz) + t * G::TP + (t == k ? G::SKEW : 0); // plane y = t of the cell
+    T *        xq = Xq + c * G::CS, *xp = Xp + c * G::CS;
+    T *        op = out + G::addr(k * cx, k * cy, k * cz + t);
+    int        it = blockIdx.x;
+    {
+      const uint32_t bid = maps.brick_ids[it];
+      uint32_t       gf[NFT];
+      fast_load_foreign_idx<k, T, G::NCT, NFT>(gf, maps, bid, tid);
+      fast_gather<k, T>(tile, ltab, ftab, gf, src, bricks[bid].base, tid);
+    }
+    bool first = true;
+    for (; it < maps.n; it += gridDim.x)
+      {
+        const bool has_next  = it + (int)gridDim.x < maps.n;
+        uint32_t   base_next = 0;
+        uint32_t   gfn[NFT];
+        if (has_next)
+          {
+            const uint32_t bidn = maps.brick_ids[it + gridDim.x];
+            base_next           = bricks[bidn].base;
+            fast_load_foreign_idx<k, T, G::NCT, NFT>(gfn, maps, bidn, tid);
+          }
+        cp_async_wait_all();
+        bar_sync(FB_COMPUTE, G::NCT); // the tile of this brick has landed
+        // phase A: plane y = t, [z][x]: q = Mx Mz v, p = (g0 Kx Mz + g2 Mx Kz) v
+        {
+          T a[n][n], b[n][n];
+#pragma unroll
+          for (int z = 0; z < n; ++z)
+            {
+              T v[n];
+#pragma unroll
+              for (int x = 0; x < n; ++x)
+                v[x] = tp[z * G::SZ + x];
+              mat_vec<n, T, false>(a[z], mats.M, v);
+              mat_vec<n, T, false>(b[z], mats.K0, v);
+            }
+          if (!first)
+            bar_sync(FB_OUT_EMPTY, G::NT); // the previous result (aliased with Xq) has been stored
+#pragma unroll
+          for (int x = 0; x < n; ++x)
+            {
+              T ca[n], cb[n], q[n], p[n];
+#pragma unroll
+              for (int z = 0; z < n; ++z)
+                {
+                  ca[z] = a[z][x];
+                  cb[z] = b[z][x];
+                }
+              mat_vec<n, T, false>(q, mats.M, ca);
+              mat_vec<n, T, false>(p, mats.M, cb);
+              mat_vec<n, T, true>(p, mats.K2, ca);
+#pragma unroll
+              for (int z = 0; z < n; ++z)
+                {
+                  xq[(z * n + t) * n + x] = q[z];
+                  xp[(z * n + t) * n + x] = p[z];
+                }
+            }
+        }
+        bar_sync(FB_COMPUTE, G::NCT);
+        // the tile is dead: gather the next brick into it
+        if (has_next)
+          fast_gather<k, T>(tile, ltab, ftab, gfn, src, base_next, tid);
+        // phase B: plane z = t, [y][x]: r = My p + g1 Ky q  (+ plane z = k of the cell below for t = 0)
+        T r[n][n];
+        if (!skip_last)
+          {
+            const bool below = (t == 0) && (cz > 0);
+#pragma unroll
+            for (int i = 0; i < n; ++i)
+              {
+                T qi[n], pi[n];
+#pragma unroll
+                for (int x = 0; x < n; ++x)
+                  {
+                    qi[x] = xq[(t * n + i) * n + x];
+                    pi[x] = xp[(t * n + i) * n + x];
+                  }
+                if (t == 0)
+                  {
+#pragma unroll
+                    for (int x = 0; x < n; ++x)
+                      {
+                        qi[x] += below ? xq[-16 * G::CS + (k * n + i) * n + x] : T(0);
+                        pi[x] += below ? xp[-16 * G::CS + (k * n + i) * n + x] : T(0);
+                      }
+                  }
+#pragma unroll
+                for (int x = 0; x < n; ++x)
+#pragma unroll
+                  for (int y = 0; y < n; ++y)
+                    {
+                      if (i == 0)
+                        r[y][x] = mats.M[y * n] * pi[x];
+                      else
+                        r[y][x] += mats.M[y * n + i] * pi[x];
+                      r[y][x] += mats.K1[y * n + i] * qi[x];
+                    }
+              }
+            fast_merge<k, T>(r, cx, cy);
+          }
+        bar_sync(FB_COMPUTE, G::NCT); // all reads of the exchange slots are done: the output tile may overwrite Xq
+        if (!skip_last && (t < k || cz == 3))
+          fast_out_store<k, T>(r, op, cx, cy);
+        bar_arrive(FB_OUT_FULL, G::NT);
+        first = false;
+      }
+  }
+
+  // ---- FDM, one eigen-decomposition triple, tensor-product weights folded into the matrices ------------------
+  template <int k, typename T>
+  __global__ void __launch_bounds__(FastGeom<k, T>::NT, 1)
+  fdm_fast_kernel(const T *__restrict__ src,
+                  T *__restrict__ dst,
+                  T *__restrict__ acc,
+                  const Epilogue<T> epi,
+                  const BrickDesc *__restrict__ bricks,
+                  const __grid_constant__ FastFdmMats<T, k + 1> mats,
+                  const int         shared_mode,
+                  const NextInit<T> ni,
+                  const FastMaps    maps)
+  {
+    using G           = FastGeom<k, T>;
+    constexpr int n   = k + 1;
+    constexpr int NFT = FastCounts<k, T>::NFT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *       tile = reinterpret_cast<T *>(smem_raw);
+    T *       out  = tile + G::TILE;
+    T *       X    = out + G::TILE;
+    T *       ops0 = align16(X + G::NCELLS * G::CS);
+    T *       ops1 = ops0 + G::NPRIVP;
+    uint16_t *ltab = reinterpret_cast<uint16_t *>(ops1 + G::NPRIVP);
+    uint16_t *ftab = ltab + G::NOWNP;
+    __shared__ T s_inv[n * n * n];
+    if ((int)blockIdx.x >= maps.n)
+      return;
+    for (int i = threadIdx.x; i < G::NOWN; i += G::NT)
+      ltab[i] = maps.ltab[i];
+    for (int i = threadIdx.x; i < G::NFP; i += G::NT)
+      ftab[i] = maps.ftab[i];
+    for (int i = threadIdx.x; i < n * n * n; i += G::NT)
+      s_inv[i] = mats.inv[i];
+    __syncthreads();
+
+    if (threadIdx.x >= G::NCT)
+      {
+        fast_mover_loop<k, T>(out, ops0, ops1, ltab, ftab, dst, acc, epi, bricks, maps, shared_mode, ni, threadIdx.x - G::NCT);
+        return;
+      }
+    const int  tid = threadIdx.x;
+    const int  c = tid % G::NCELLS, t = tid / G::NCELLS;
+    const int  cx = c & 3, cy = (c >> 2) & 3, cz = c >> 4;
+    const bool skip_last = (t == k) && (cz < 2);
+    const T *  tp = tile + G::addr(k * cx, k * cy, k * cz + t); // plane z = t of the cell
+    T *        xs = X + c * G::CS;
+    T *        op = out + G::addr(k * cx, k * cy, k * cz + t);
+    // inverse eigenvalue sums, row (z, y = t) of this thread's plane in phase B: broadcast reads from shared memory
+    const T *inv = s_inv + t * n;
+    int      it  = blockIdx.x;
+    {
+      const uint32_t bid = maps.brick_ids[it];
+      uint32_t       gf[NFT];
+      fast_load_foreign_idx<k, T, G::NCT, NFT>(gf, maps, bid, tid);
+      fast_gather<k, T>(tile, ltab, ftab, gf, src, bricks[bid].base, tid);
+    }
+    bool first = true;
+    for (; it < maps.n; it += gridDim.x)
+      {
+        const bool has_next  = it + (int)gridDim.x < maps.n;
+        uint32_t   base_next = 0;
+        uint32_t   gfn[NFT];
+        if (has_next)
+          {
+            const uint32_t bidn = maps.brick_ids[it + gridDim.x];
+            base_next           = bricks[bidn].base;
+            fast_load_foreign_idx<k, T, G::NCT, NFT>(gfn, maps, bidn, tid);
+          }
+        cp_async_wait_all();
+        bar_sync(FB_COMPUTE, G::NCT); // the tile of this brick has landed
+        // phase A: plane z = t, [y][x]: Ax in x, Ay in y
+        {
+          T a[n][n];
+#pragma unroll
+          for (int y = 0; y < n; ++y)
+            {
+              T v[n];
+#pragma unroll
+              for (int x = 0; x < n; ++x)
+                v[x] = tp[y * G::TP + (y == k ? G::SKEW : 0) + x];
+              mat_vec<n, T, false>(a[y], mats.Ax, v);
+            }
+#pragma unroll
+          for (int x = 0; x < n; ++x)
+            {
+              T ca[n], q[n];
+#pragma unroll
+              for (int y = 0; y < n; ++y)
+                ca[y] = a[y][x];
+              mat_vec<n, T, false>(q, mats.Ay, ca);
+#pragma unroll
+              for (int y = 0; y < n; ++y)
+                xs[(t * n + y) * n + x] = q[y];
+            }
+        }
+        bar_sync(FB_COMPUTE, G::NCT);
+        // the tile is dead: gather the next brick into it
+        if (has_next)
+          fast_gather<k, T>(tile, ltab, ftab, gfn, src, base_next, tid);
+        // phase B: plane y = t, [z][x]: Az, scale, Bz in z; Bx in x
+        {
+          T w[n][n];
+#pragma unroll
+          for (int x = 0; x < n; ++x)
+            {
+              T col[n], u[n];
+#pragma unroll
+              for (int z = 0; z < n; ++z)
+                col[z] = xs[(z * n + t) * n + x];
+              mat_vec<n, T, false>(u, mats.Az, col);
+#pragma unroll
+              for (int z = 0; z < n; ++z)
+                u[z] *= inv[z * n * n + x];
+              mat_vec<n, T, false>(col, mats.Bz, u);
+#pragma unroll
+              for (int z = 0; z < n; ++z)
+                w[z][x] = col[z];
+            }
+#pragma unroll
+          for (int z = 0; z < n; ++z)
+            {
+              T u[n];
+              mat_vec<n, T, false>(u, mats.Bx, w[z]);
+#pragma unroll
+              for (int x = 0; x < n; ++x)
+                xs[(z * n + t) * n + x] = u[x];
+            }
+        }
+        bar_sync(FB_COMPUTE, G::NCT);
+        // phase C: plane z = t, [y][x]: By in y (+ plane z = k of the cell below for t = 0)
+        T r[n][n];
+        if (!skip_last)
+          {
+            const bool below = (t == 0) && (cz > 0);
+#pragma unroll
+            for (int i = 0; i < n; ++i)
+              {
+                T vi[n];
+#pragma unroll
+                for (int x = 0; x < n; ++x)
+                  vi[x] = xs[(t * n + i) * n + x];
+                if (t == 0)
+                  {
+#pragma unroll
+                    for (int x = 0; x < n; ++x)
+                      vi[x] += below ? xs[-16 * G::CS + (k * n + i) * n + x] : T(0);
+                  }
+#pragma unroll
+                for (int x = 0; x < n; ++x)
+#pragma unroll
+                  for (int y = 0; y < n; ++y)
+                    {
+                      if (i == 0)
+                        r[y][x] = mats.By[y * n] * vi[x];
+                      else
+                        r[y][x] += mats.By[y * n + i] * vi[x];
+                    }
+              }
+            fast_merge<k, T>(r, cx, cy);
+          }
+        if (!first)
+          bar_sync(FB_OUT_EMPTY, G::NT); // the previous result has been stored
+        if (!skip_last && (t < k || cz == 3))
+          fast_out_store<k, T>(r, op, cx, cy);
+        bar_arrive(FB_OUT_FULL, G::NT);
+        first = false;
+      }
+  }
+} // namespace dasm

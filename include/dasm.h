@@ -134,6 +134,7 @@ extern "C"
   int dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping_type, int compress_indices,
                      dasm_op **out);
   int       dasm_op_destroy(dasm_op *op);
+  long long dasm_op_n_fast_bricks(const dasm_op *op); /* diagnostics: bricks processed by the warp-specialised kernel */
   long long dasm_op_n_dofs(const dasm_op *op);        /* locally owned (vector_partitioner->locally_owned_size) */
   long long dasm_op_n_ghost(const dasm_op *op);
   long long dasm_op_vec_size(const dasm_op *op);      /* owned + ghost */
@@ -170,6 +171,7 @@ extern "C"
   int dasm_fdm_vmult(dasm_fdm *fdm, void *dst, const void *src);
   /* vmult(dst, src, pre, post), matrix_free.h:960-986 */
   int dasm_fdm_vmult_hooks(dasm_fdm *fdm, void *dst, const void *src, const dasm_hook *pre, const dasm_hook *post);
+  long long dasm_fdm_n_fast_bricks(const dasm_fdm *fdm);   /* diagnostics, as dasm_op_n_fast_bricks */
   long long dasm_fdm_n_instances(const dasm_fdm *fdm);      /* n_fdm_instances(), matrix_free.h:1000-1004 */
   long long dasm_fdm_memory_consumption(const dasm_fdm *fdm); /* matrix_free.h:988-992 */
   int       dasm_fdm_is_symmetric(const dasm_fdm *fdm);     /* matrix_free.h:896-904 */
