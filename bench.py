@@ -59,49 +59,67 @@ def measured_peak():
 
 
 class ClockSampler:
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
-        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock and throttle reasons DURING the timed region: an in-process NVML polling thread (2 ms period; the timed
+    region is tens of milliseconds, too short for `nvidia-smi -lms`), falling back to one nvidia-smi query."""
 
     def __init__(self, index=0):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+        import threading
+        self.index = index
+        self.samples = []      # (sm_mhz, reasons bitmask)
+        self.max_mhz = None
+        self.stop_flag = False
+        self.thread = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
         except Exception:
-            self.p = None
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((float(mhz), int(rs)))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if self.p is None:
+        out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": []}
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            nv = self.nv
+            names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                     "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                     "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                     "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+            if self.samples:
+                sm = [s[0] for s in self.samples]
+                out["sm_mhz"] = float(np.median(sm))
+                out["samples"] = len(sm)
+                mask = 0
+                for s in self.samples:
+                    mask |= s[1]
+                out["reasons"] = sorted(n for n, bit in names.items() if mask & bit)
             return out
-        time.sleep(0.15)
-        self.p.terminate()
         try:
-            self.p.wait(timeout=5)
+            r = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits"],
+                               capture_output=True, text=True, timeout=10).stdout.strip().split(", ")
+            out["sm_mhz"], out["sm_max_mhz"] = float(r[0]), float(r[1])
+            out["note"] = "single nvidia-smi query after the timed region (NVML python binding unavailable)"
         except Exception:
-            self.p.kill()
-        self.f.flush()
-        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
-        os.unlink(self.f.name)
-        sm, reasons, mx = [], set(), None
-        for r in rows:
-            if len(r) < 8:
-                continue
-            try:
-                sm.append(float(r[0]))
-                mx = float(r[1])
-            except ValueError:
-                continue
-            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[4:8]):
-                if v.strip().lower() == "active":
-                    reasons.add(name)
-        if sm:
-            hi = [s for s in sm if s >= 0.5 * max(sm)]
-            out["sm_mhz"] = float(np.median(hi))
-            out["sm_max_mhz"] = mx
-            out["samples"] = len(sm)
-        out["reasons"] = sorted(reasons)
+            pass
         return out
 
 

@@ -616,6 +616,60 @@ epilogue_n_operands(const Epilogue<T> &epi)
   return 0;
 }
 
+// optional timing instrumentation of the warp-specialised kernels (DASM_FAST_PROF=1): clock64() stamps of compute thread 0
+// (events 0-7, 13, 14) and mover thread 0 (8-12) for the first 16 bricks of every block; average intervals to stderr
+static int
+fast_dbg()
+{
+  static const int v = getenv("DASM_FAST_DBG") ? atoi(getenv("DASM_FAST_DBG")) : 0;
+  return v;
+}
+
+static long long *
+fast_prof_buffer(const int grid)
+{
+  static const bool on = getenv("DASM_FAST_PROF") && getenv("DASM_FAST_PROF")[0] == '1';
+  if (!on)
+    return nullptr;
+  static long long *d = nullptr;
+  if (!d)
+    cudaMalloc(&d, (size_t)1024 * 256 * sizeof(long long));
+  cudaMemset(d, 0, (size_t)1024 * 256 * sizeof(long long));
+  (void)grid;
+  return d;
+}
+
+static void
+fast_prof_report(const char *name, long long *d, const int grid, cudaStream_t s)
+{
+  if (!d)
+    return;
+  cudaStreamSynchronize(s);
+  std::vector<long long> h((size_t)grid * 256);
+  cudaMemcpy(h.data(), d, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+  // average over blocks of the intervals of iterations 4..11
+  double sum[16][16] = {{0}};
+  int    cnt         = 0;
+  for (int b = 0; b < grid; ++b)
+    for (int it = 4; it < 12; ++it)
+      {
+        const long long *e = h.data() + ((size_t)b * 16 + it) * 16;
+        const long long *p = h.data() + ((size_t)b * 16 + it - 1) * 16;
+        if (e[0] == 0 || e[14] == 0 || p[0] == 0)
+          continue;
+        ++cnt;
+        for (int i = 0; i < 16; ++i)
+          sum[0][i] += (double)(e[i] - e[0]);
+        sum[1][0] += (double)(e[0] - p[0]);
+      }
+  if (cnt == 0)
+    return;
+  fprintf(stderr, "[fast prof] %s: brick period %.0f cycles; offsets from compute top:", name, sum[1][0] / cnt);
+  for (int i = 0; i < 16; ++i)
+    fprintf(stderr, " e%d=%.0f", i, sum[0][i] / cnt);
+  fprintf(stderr, "\n");
+}
+
 // warp-specialised Laplace kernel over the regular bricks; false: not available (shared memory), nothing launched
 template <int K, typename T>
 static bool
@@ -634,11 +688,12 @@ launch_laplace_fast(dasm_op *op, T *dst, const T *src, const Epilogue<T> &epi, c
       mats.K1[i] = (T)op->lap_mats[2][i];
       mats.K2[i] = (T)op->lap_mats[3][i];
     }
-  FastMaps fm = {op->d_fast_ltab, op->d_fast_ftab, op->maps.foreign_gidx, op->d_fast_ids, op->n_fast};
-  auto     kern = laplace_fast_kernel<K, T>;
-  CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = std::min(op->n_fast, op->n_sm);
+  FastMaps  fm   = {op->d_fast_ltab, op->d_fast_ftab, op->maps.foreign_gidx, op->d_fast_ids, op->n_fast, fast_prof_buffer(grid), fast_dbg()};
+  auto      kern = laplace_fast_kernel<K, T>;
+  CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, G::NT, smem, op->ctx->stream>>>(src, dst, (T *)op->d_acc, epi, op->d_bricks, mats, shared_mode, ni, fm);
+  fast_prof_report("laplace", fm.prof, grid, op->ctx->stream);
   op->ctx->launches++;
   return true;
 }
@@ -839,11 +894,12 @@ launch_fdm_fast(dasm_fdm *f, T *dst, const T *src, const Epilogue<T> &epi, const
     }
   for (int i = 0; i < n * n * n; ++i)
     mats.inv[i] = (T)f->fast_inv[i];
-  FastMaps fm = {op->d_fast_ltab, op->d_fast_ftab, op->maps.foreign_gidx, f->d_fast_ids, f->n_fast};
-  auto     kern = fdm_fast_kernel<K, T>;
-  CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = std::min(f->n_fast, op->n_sm);
+  FastMaps  fm   = {op->d_fast_ltab, op->d_fast_ftab, op->maps.foreign_gidx, f->d_fast_ids, f->n_fast, fast_prof_buffer(grid), fast_dbg()};
+  auto      kern = fdm_fast_kernel<K, T>;
+  CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, G::NT, smem, op->ctx->stream>>>(src, dst, (T *)op->d_acc, epi, op->d_bricks, mats, shared_mode, ni, fm);
+  fast_prof_report("fdm", fm.prof, grid, op->ctx->stream);
   op->ctx->launches++;
   return true;
 }

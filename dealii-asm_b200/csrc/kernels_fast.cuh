@@ -90,7 +90,24 @@ namespace dasm
     const uint32_t *foreign_gidx; // [brick][NFP] global index of the j-th foreign point
     const uint32_t *brick_ids;    // bricks to process
     int             n;
+    long long *     prof;         // optional timing instrumentation (DASM_FAST_PROF): [block][16 iterations][16 events]
+    int             dbg;          // timing experiments (DASM_FAST_DBG, results invalid): 1 no compute phases, 2 no private stores,
+                                  // 4 no red.add, 8 no gather, 16 no operand staging
   };
+
+  __device__ __forceinline__ void
+  fast_prof(const FastMaps &maps, const int iter, const int event, const bool who)
+  {
+#ifdef DASM_FAST_PROF_BUILD
+    if (maps.prof != nullptr && who && iter < 16)
+      maps.prof[((size_t)blockIdx.x * 16 + iter) * 16 + event] = clock64();
+#else
+    (void)maps;
+    (void)iter;
+    (void)event;
+    (void)who;
+#endif
+  }
 
   template <typename T, int n>
   struct FastLaplaceMats
@@ -128,6 +145,15 @@ namespace dasm
   cp_async_wait_all()
   {
     asm volatile("cp.async.wait_all;\n" ::: "memory");
+  }
+
+  // load issued exactly here (volatile): descriptors / indices of later bricks are requested one phase before their use
+  __device__ __forceinline__ uint32_t
+  ldg_early(const uint32_t *p)
+  {
+    uint32_t v;
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
   }
 
   // r[o] (+)= sum_i M[o n + i] v[i]
@@ -168,7 +194,7 @@ namespace dasm
     for (int jj = 0; jj < NF; ++jj)
       {
         const int j = tid + jj * NTH;
-        gf[jj]      = (j < G::NFOR) ? __ldg(src + j) : 0u;
+        gf[jj]      = (j < G::NFOR) ? ldg_early(src + j) : 0u;
       }
   }
 
@@ -223,31 +249,45 @@ namespace dasm
       copy(ops1, epi.v1 + base);
   }
 
-  // pre-initialisation of the next kernel's destination on the brick's own shared DoFs: all loads in flight at once
+  // pre-initialisation of the next kernel's destination on the brick's own shared DoFs: all loads are issued at the
+  // top of a mover iteration, the stores follow after the epilogue stores of the brick (their latency is hidden)
+  template <int k, typename T>
+  struct FastInitRegs
+  {
+    T a[FastCounts<k, T>::NSI], b[FastCounts<k, T>::NSI];
+  };
+
   template <int k, typename T>
   __device__ __forceinline__ void
-  fast_next_init(const NextInit<T> &ni, const uint32_t sh_base, const int m)
+  fast_next_init_load(FastInitRegs<k, T> &r, const NextInit<T> &ni, const uint32_t sh_base, const int m)
+  {
+    using G           = FastGeom<k, T>;
+    constexpr int NSI = FastCounts<k, T>::NSI;
+    const bool    h0 = (ni.out != nullptr) && ni.v0 != nullptr, h1 = (ni.out != nullptr) && (ni.v1 != nullptr && ni.f1 != T(0));
+#pragma unroll
+    for (int it = 0; it < NSI; ++it)
+      {
+        const int  i  = m + it * G::NMT;
+        const bool in = i < G::NOWN - G::NPRIV;
+        r.a[it]       = (h0 && in) ? __ldg(ni.v0 + sh_base + i) : T(0);
+        r.b[it]       = (h1 && in) ? __ldg(ni.v1 + sh_base + i) : T(0);
+      }
+  }
+
+  template <int k, typename T>
+  __device__ __forceinline__ void
+  fast_next_init_store(const FastInitRegs<k, T> &r, const NextInit<T> &ni, const uint32_t sh_base, const int m)
   {
     using G           = FastGeom<k, T>;
     constexpr int NSI = FastCounts<k, T>::NSI;
     if (ni.out == nullptr)
       return;
-    const bool h0 = ni.v0 != nullptr, h1 = (ni.v1 != nullptr && ni.f1 != T(0));
-    T          a[NSI], b[NSI];
-#pragma unroll
-    for (int it = 0; it < NSI; ++it)
-      {
-        const int i = m + it * G::NMT;
-        const bool in = i < G::NOWN - G::NPRIV;
-        a[it]         = (h0 && in) ? __ldg(ni.v0 + sh_base + i) : T(0);
-        b[it]         = (h1 && in) ? __ldg(ni.v1 + sh_base + i) : T(0);
-      }
 #pragma unroll
     for (int it = 0; it < NSI; ++it)
       {
         const int i = m + it * G::NMT;
         if (i < G::NOWN - G::NPRIV)
-          ni.out[sh_base + i] = a[it] + ni.f1 * (a[it] - b[it]);
+          ni.out[sh_base + i] = r.a[it] + ni.f1 * (r.a[it] - r.b[it]);
       }
   }
 
@@ -264,29 +304,80 @@ namespace dasm
     const T    alpha  = (epi.kind == EPI_RESIDUAL) ? T(-1) : ((epi.kind == EPI_CHEB || epi.kind == EPI_SCALE) ? epi.f2 : T(1));
     T *        sh_dst = (shared_mode == SHARED_DIRECT) ? dst : acc;
     const T    sh_a   = (shared_mode == SHARED_DIRECT) ? alpha : T(1);
-    int        it     = blockIdx.x;
-    uint32_t   bid    = maps.brick_ids[it];
-    BrickDesc  bd     = bricks[bid];
-    fast_stage_ops<k, T>(ops0, ops1, epi, need0, need1, bd.base, m);
-    for (; it < maps.n; it += gridDim.x)
+    const int  G1 = (int)gridDim.x;
+    int        it = blockIdx.x;
+    // descriptors: current brick, next brick (loaded one iteration ahead), id of the brick after it
+    uint32_t bid = ldg_early(maps.brick_ids + it);
+    uint32_t bid_n = (it + G1 < maps.n) ? ldg_early(maps.brick_ids + it + G1) : 0u;
+    uint32_t base = ldg_early(&bricks[bid].base), sh_base = ldg_early(&bricks[bid].sh_base);
+    uint32_t base_n = ldg_early(&bricks[bid_n].base), sh_base_n = ldg_early(&bricks[bid_n].sh_base);
+    fast_stage_ops<k, T>(ops0, ops1, epi, need0, need1, base, m);
+    for (; it < maps.n; it += G1)
       {
-        const bool      has_next = it + (int)gridDim.x < maps.n;
-        const uint32_t  bid_next = has_next ? maps.brick_ids[it + gridDim.x] : bid;
-        const BrickDesc bd_next  = has_next ? bricks[bid_next] : bd;
-        uint32_t        gf[NFM];
+        const bool     has_next = it + G1 < maps.n;
+        const uint32_t bid_nn   = (it + 2 * G1 < maps.n) ? ldg_early(maps.brick_ids + it + 2 * G1) : 0u;
+        uint32_t       gf[NFM];
+        const int      li = (it - (int)blockIdx.x) / G1;
+        fast_prof(maps, li, 8, m == 0);
         fast_load_foreign_idx<k, T, G::NMT, NFM>(gf, maps, bid, m);
-        fast_next_init<k, T>(ni, bd.sh_base, m);
+        FastInitRegs<k, T> nir;
+        fast_next_init_load<k, T>(nir, ni, sh_base, m);
+        fast_prof(maps, li, 9, m == 0);
         bar_sync(FB_OUT_FULL, G::NT); // the result of this brick is in the output tile
+        fast_prof(maps, li, 10, m == 0);
+        const uint32_t base_nn = ldg_early(&bricks[bid_nn].base), sh_base_nn = ldg_early(&bricks[bid_nn].sh_base);
         cp_async_wait_all();
         bar_sync(FB_MOVERS, G::NMT); // operands staged by all movers are visible
         {
-          T *d = dst + bd.base;
-          // private DoFs: fused epilogue, coalesced plain stores
-#pragma unroll 8
-          for (int i = m; i < G::NPRIV; i += G::NMT)
-            d[i] = epilogue_compute(epi, out[ltab[i]], need0 ? ops0[i] : T(0), need1 ? ops1[i] : T(0));
+          T *d = dst + base;
+          // private DoFs: fused epilogue, coalesced plain stores (one straight-line loop per epilogue kind so that the
+          // shared-memory loads of an unrolled batch are in flight together)
+          if (maps.dbg & 2)
+            {
+            }
+          else if (epi.kind == EPI_CHEB && need1)
+            {
+              const T f1 = epi.f1, f2 = epi.f2;
+#pragma unroll 16
+              for (int i = m; i < G::NPRIV; i += G::NMT)
+                {
+                  const T a = ops0[i];
+                  d[i]      = a + f2 * out[ltab[i]] + f1 * (a - ops1[i]);
+                }
+            }
+          else if (epi.kind == EPI_CHEB)
+            {
+              const T f1 = epi.f1, f2 = epi.f2;
+#pragma unroll 16
+              for (int i = m; i < G::NPRIV; i += G::NMT)
+                {
+                  const T a = ops0[i];
+                  d[i]      = a + f2 * out[ltab[i]] + f1 * (a - T(0));
+                }
+            }
+          else if (epi.kind == EPI_RESIDUAL)
+            {
+#pragma unroll 16
+              for (int i = m; i < G::NPRIV; i += G::NMT)
+                d[i] = ops0[i] - out[ltab[i]];
+            }
+          else if (epi.kind == EPI_SCALE)
+            {
+              const T f2 = epi.f2;
+#pragma unroll 16
+              for (int i = m; i < G::NPRIV; i += G::NMT)
+                d[i] = f2 * out[ltab[i]];
+            }
+          else
+            {
+#pragma unroll 16
+              for (int i = m; i < G::NPRIV; i += G::NMT)
+                d[i] = out[ltab[i]];
+            }
+          fast_prof(maps, li, 15, m == 0);
           // own DoFs on the lower (shared) faces
-          T *sd = sh_dst + bd.base;
+          T *sd = sh_dst + base;
+          if (!(maps.dbg & 4))
 #pragma unroll 4
           for (int i = G::NPRIV + m; i < G::NOWN; i += G::NMT)
             atomic_add(sd + i, sh_a * out[ltab[i]]);
@@ -295,17 +386,24 @@ namespace dasm
           for (int jj = 0; jj < NFM; ++jj)
             {
               const int j = m + jj * G::NMT;
-              if (j < G::NFOR)
+              if (j < G::NFOR && !(maps.dbg & 4))
                 atomic_add(sh_dst + gf[jj], sh_a * out[ftab[j]]);
             }
         }
+        fast_prof(maps, li, 11, m == 0);
         if (has_next)
           bar_arrive(FB_OUT_EMPTY, G::NT);
+        fast_next_init_store<k, T>(nir, ni, sh_base, m);
         bar_sync(FB_MOVERS, G::NMT); // all movers have read the operands: stage those of the next brick
-        if (has_next)
-          fast_stage_ops<k, T>(ops0, ops1, epi, need0, need1, bd_next.base, m);
-        bd  = bd_next;
-        bid = bid_next;
+        if (has_next && !(maps.dbg & 16))
+          fast_stage_ops<k, T>(ops0, ops1, epi, need0, need1, base_n, m);
+        fast_prof(maps, li, 12, m == 0);
+        bid       = bid_n;
+        base      = base_n;
+        sh_base   = sh_base_n;
+        bid_n     = bid_nn;
+        base_n    = base_nn;
+        sh_base_n = sh_base_nn;
       }
   }
 
@@ -374,7 +472,7 @@ namespace dasm
     T *       Xq   = tile + G::TILE;
     T *       Xp   = Xq + G::NCELLS * G::CS;
     T *       out  = Xq; // the output tile aliases the first exchange slot (written after all reads of it)
-    T *       ops0 = align16(Xp + G::NCELLS * G::CS);
+    T *       ops0 = Xp + G::NCELLS * G::CS; // 64 CS elements per slot: 16-byte aligned
     uint16_t *ltab = reinterpret_cast<uint16_t *>(ops0 + G::NPRIVP);
     uint16_t *ftab = ltab + G::NOWNP;
     if ((int)blockIdx.x >= maps.n)
@@ -393,46 +491,57 @@ namespace dasm
     const int  tid = threadIdx.x;
     const int  c = tid % G::NCELLS, t = tid / G::NCELLS;
     const int  cx = c & 3, cy = (c >> 2) & 3, cz = c >> 4;
-    const bool skip_last = (t == k) && (cz < 2); // whole warp: its plane z = k belongs to the cell above
+    const bool skip_last = ((t == k) && (cz < 2)) || (maps.dbg & 1); // whole warp: its plane z = k belongs to the cell above
     const T *  tp = tile + G::addr(k * cx, k * cy, k * cz) + t * G::TP + (t == k ? G::SKEW : 0); // plane y = t of the cell
     T *        xq = Xq + c * G::CS, *xp = Xp + c * G::CS;
     T *        op = out + G::addr(k * cx, k * cy, k * cz + t);
+    const int  G1 = (int)gridDim.x;
     int        it = blockIdx.x;
+    // descriptors: next brick (loaded one iteration ahead), id of the brick after it
+    uint32_t bid_next  = (it + G1 < maps.n) ? ldg_early(maps.brick_ids + it + G1) : 0u;
+    uint32_t base_next = 0;
     {
-      const uint32_t bid = maps.brick_ids[it];
+      const uint32_t bid = ldg_early(maps.brick_ids + it);
       uint32_t       gf[NFT];
       fast_load_foreign_idx<k, T, G::NCT, NFT>(gf, maps, bid, tid);
-      fast_gather<k, T>(tile, ltab, ftab, gf, src, bricks[bid].base, tid);
+      base_next = ldg_early(&bricks[bid_next].base);
+      fast_gather<k, T>(tile, ltab, ftab, gf, src, ldg_early(&bricks[bid].base), tid);
     }
     bool first = true;
-    for (; it < maps.n; it += gridDim.x)
+    for (; it < maps.n; it += G1)
       {
-        const bool has_next  = it + (int)gridDim.x < maps.n;
-        uint32_t   base_next = 0;
-        uint32_t   gfn[NFT];
-        if (has_next)
-          {
-            const uint32_t bidn = maps.brick_ids[it + gridDim.x];
-            base_next           = bricks[bidn].base;
-            fast_load_foreign_idx<k, T, G::NCT, NFT>(gfn, maps, bidn, tid);
-          }
+        const bool     has_next = it + G1 < maps.n;
+        const uint32_t bid_nn   = (it + 2 * G1 < maps.n) ? ldg_early(maps.brick_ids + it + 2 * G1) : 0u;
+        uint32_t       gfn[NFT];
+        fast_load_foreign_idx<k, T, G::NCT, NFT>(gfn, maps, bid_next, tid);
+        const int li = (it - (int)blockIdx.x) / (int)gridDim.x;
+        fast_prof(maps, li, 0, tid == 0);
         cp_async_wait_all();
         bar_sync(FB_COMPUTE, G::NCT); // the tile of this brick has landed
+        fast_prof(maps, li, 1, tid == 0);
         // phase A: plane y = t, [z][x]: q = Mx Mz v, p = (g0 Kx Mz + g2 Mx Kz) v
+        if (!(maps.dbg & 1))
         {
-          T a[n][n], b[n][n];
+          // b = g0 Kx v is parked in this thread's part of the p slot (the same addresses p is written to below): the
+          // register budget holds a, one column of b and the column results without spilling
+          T a[n][n];
 #pragma unroll
           for (int z = 0; z < n; ++z)
             {
-              T v[n];
+              T v[n], bz[n];
 #pragma unroll
               for (int x = 0; x < n; ++x)
                 v[x] = tp[z * G::SZ + x];
               mat_vec<n, T, false>(a[z], mats.M, v);
-              mat_vec<n, T, false>(b[z], mats.K0, v);
+              mat_vec<n, T, false>(bz, mats.K0, v);
+#pragma unroll
+              for (int x = 0; x < n; ++x)
+                xp[(z * n + t) * n + x] = bz[x];
             }
+          fast_prof(maps, li, 2, tid == 0);
           if (!first)
             bar_sync(FB_OUT_EMPTY, G::NT); // the previous result (aliased with Xq) has been stored
+          fast_prof(maps, li, 3, tid == 0);
 #pragma unroll
           for (int x = 0; x < n; ++x)
             {
@@ -441,7 +550,7 @@ namespace dasm
               for (int z = 0; z < n; ++z)
                 {
                   ca[z] = a[z][x];
-                  cb[z] = b[z][x];
+                  cb[z] = xp[(z * n + t) * n + x];
                 }
               mat_vec<n, T, false>(q, mats.M, ca);
               mat_vec<n, T, false>(p, mats.M, cb);
@@ -454,10 +563,17 @@ namespace dasm
                 }
             }
         }
+        fast_prof(maps, li, 4, tid == 0);
+        if ((maps.dbg & 1) && !first)
+          bar_sync(FB_OUT_EMPTY, G::NT);
         bar_sync(FB_COMPUTE, G::NCT);
+        fast_prof(maps, li, 5, tid == 0);
         // the tile is dead: gather the next brick into it
-        if (has_next)
+        if (has_next && !(maps.dbg & 8))
           fast_gather<k, T>(tile, ltab, ftab, gfn, src, base_next, tid);
+        bid_next  = bid_nn;
+        base_next = ldg_early(&bricks[bid_nn].base);
+        fast_prof(maps, li, 6, tid == 0);
         // phase B: plane z = t, [y][x]: r = My p + g1 Ky q  (+ plane z = k of the cell below for t = 0)
         T r[n][n];
         if (!skip_last)
@@ -496,10 +612,13 @@ namespace dasm
               }
             fast_merge<k, T>(r, cx, cy);
           }
+        fast_prof(maps, li, 7, tid == 0);
         bar_sync(FB_COMPUTE, G::NCT); // all reads of the exchange slots are done: the output tile may overwrite Xq
+        fast_prof(maps, li, 13, tid == 0);
         if (!skip_last && (t < k || cz == 3))
           fast_out_store<k, T>(r, op, cx, cy);
         bar_arrive(FB_OUT_FULL, G::NT);
+        fast_prof(maps, li, 14, tid == 0);
         first = false;
       }
   }
@@ -524,7 +643,7 @@ namespace dasm
     T *       tile = reinterpret_cast<T *>(smem_raw);
     T *       out  = tile + G::TILE;
     T *       X    = out + G::TILE;
-    T *       ops0 = align16(X + G::NCELLS * G::CS);
+    T *       ops0 = X + G::NCELLS * G::CS; // 64 CS elements per slot: 16-byte aligned
     T *       ops1 = ops0 + G::NPRIVP;
     uint16_t *ltab = reinterpret_cast<uint16_t *>(ops1 + G::NPRIVP);
     uint16_t *ftab = ltab + G::NOWNP;
@@ -547,34 +666,38 @@ namespace dasm
     const int  tid = threadIdx.x;
     const int  c = tid % G::NCELLS, t = tid / G::NCELLS;
     const int  cx = c & 3, cy = (c >> 2) & 3, cz = c >> 4;
-    const bool skip_last = (t == k) && (cz < 2);
+    const bool skip_last = ((t == k) && (cz < 2)) || (maps.dbg & 1);
     const T *  tp = tile + G::addr(k * cx, k * cy, k * cz + t); // plane z = t of the cell
     T *        xs = X + c * G::CS;
     T *        op = out + G::addr(k * cx, k * cy, k * cz + t);
     // inverse eigenvalue sums, row (z, y = t) of this thread's plane in phase B: broadcast reads from shared memory
     const T *inv = s_inv + t * n;
-    int      it  = blockIdx.x;
+    const int  G1 = (int)gridDim.x;
+    int        it = blockIdx.x;
+    // descriptors: next brick (loaded one iteration ahead), id of the brick after it
+    uint32_t bid_next  = (it + G1 < maps.n) ? ldg_early(maps.brick_ids + it + G1) : 0u;
+    uint32_t base_next = 0;
     {
-      const uint32_t bid = maps.brick_ids[it];
+      const uint32_t bid = ldg_early(maps.brick_ids + it);
       uint32_t       gf[NFT];
       fast_load_foreign_idx<k, T, G::NCT, NFT>(gf, maps, bid, tid);
-      fast_gather<k, T>(tile, ltab, ftab, gf, src, bricks[bid].base, tid);
+      base_next = ldg_early(&bricks[bid_next].base);
+      fast_gather<k, T>(tile, ltab, ftab, gf, src, ldg_early(&bricks[bid].base), tid);
     }
     bool first = true;
-    for (; it < maps.n; it += gridDim.x)
+    for (; it < maps.n; it += G1)
       {
-        const bool has_next  = it + (int)gridDim.x < maps.n;
-        uint32_t   base_next = 0;
-        uint32_t   gfn[NFT];
-        if (has_next)
-          {
-            const uint32_t bidn = maps.brick_ids[it + gridDim.x];
-            base_next           = bricks[bidn].base;
-            fast_load_foreign_idx<k, T, G::NCT, NFT>(gfn, maps, bidn, tid);
-          }
+        const bool     has_next = it + G1 < maps.n;
+        const uint32_t bid_nn   = (it + 2 * G1 < maps.n) ? ldg_early(maps.brick_ids + it + 2 * G1) : 0u;
+        uint32_t       gfn[NFT];
+        fast_load_foreign_idx<k, T, G::NCT, NFT>(gfn, maps, bid_next, tid);
+        const int li = (it - (int)blockIdx.x) / (int)gridDim.x;
+        fast_prof(maps, li, 0, tid == 0);
         cp_async_wait_all();
         bar_sync(FB_COMPUTE, G::NCT); // the tile of this brick has landed
+        fast_prof(maps, li, 1, tid == 0);
         // phase A: plane z = t, [y][x]: Ax in x, Ay in y
+        if (!(maps.dbg & 1))
         {
           T a[n][n];
 #pragma unroll
@@ -599,11 +722,17 @@ namespace dasm
                 xs[(t * n + y) * n + x] = q[y];
             }
         }
+        fast_prof(maps, li, 2, tid == 0);
         bar_sync(FB_COMPUTE, G::NCT);
+        fast_prof(maps, li, 3, tid == 0);
         // the tile is dead: gather the next brick into it
-        if (has_next)
+        if (has_next && !(maps.dbg & 8))
           fast_gather<k, T>(tile, ltab, ftab, gfn, src, base_next, tid);
+        bid_next  = bid_nn;
+        base_next = ldg_early(&bricks[bid_nn].base);
+        fast_prof(maps, li, 4, tid == 0);
         // phase B: plane y = t, [z][x]: Az, scale, Bz in z; Bx in x
+        if (!(maps.dbg & 1))
         {
           T w[n][n];
 #pragma unroll
@@ -632,7 +761,9 @@ namespace dasm
                 xs[(z * n + t) * n + x] = u[x];
             }
         }
+        fast_prof(maps, li, 5, tid == 0);
         bar_sync(FB_COMPUTE, G::NCT);
+        fast_prof(maps, li, 6, tid == 0);
         // phase C: plane z = t, [y][x]: By in y (+ plane z = k of the cell below for t = 0)
         T r[n][n];
         if (!skip_last)
@@ -664,11 +795,14 @@ namespace dasm
               }
             fast_merge<k, T>(r, cx, cy);
           }
+        fast_prof(maps, li, 7, tid == 0);
         if (!first)
           bar_sync(FB_OUT_EMPTY, G::NT); // the previous result has been stored
+        fast_prof(maps, li, 13, tid == 0);
         if (!skip_last && (t < k || cz == 3))
           fast_out_store<k, T>(r, op, cx, cy);
         bar_arrive(FB_OUT_FULL, G::NT);
+        fast_prof(maps, li, 14, tid == 0);
         first = false;
       }
   }
