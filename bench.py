@@ -19,9 +19,14 @@ import time
 
 import numpy as np
 
-# exactly one JSON line on stdout: keep NCCL's version banner off it
-if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-    os.environ["NCCL_DEBUG"] = "WARN"
+# exactly one JSON line on stdout: native libraries (NCCL's version banner) write to file descriptor 1 directly, so the
+# real stdout is kept aside for the JSON line and descriptor 1 points to stderr for everything else
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -180,7 +185,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "DoFs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -368,7 +373,7 @@ def run_ours(args):
     }
     if extra:
         line["extra"] = extra
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
