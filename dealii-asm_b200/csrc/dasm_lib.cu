@@ -677,7 +677,7 @@ launch_laplace_fast(dasm_op *op, T *dst, const T *src, const Epilogue<T> &epi, c
 {
   using G             = FastGeom<K, T>;
   constexpr size_t smem = G::smem_bytes(1, 2, 1);
-  if (smem > (size_t)op->max_smem)
+  if (smem > (size_t)op->max_smem || epilogue_n_operands(epi) > 1) // one operand buffer (b of the residual epilogue)
     return false;
   constexpr int             n = K + 1;
   FastLaplaceMats<T, K + 1> mats;
@@ -1735,8 +1735,9 @@ dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping
                         for (size_t b = 0; b < bricks.size(); ++b)
                           {
                             const BrickDesc &bd = bricks[b];
+                            // (the operands on the private range are fetched by 16-byte aligned bulk copies)
                             bool             r  = regular && bd.variant == itv->second && bd.npriv == NPRIV && bd.sh_count == (uint32_t)(NOWN - NPRIV) &&
-                                     bd.sh_base == bd.base + NPRIV;
+                                     bd.sh_base == bd.base + NPRIV && ((size_t)bd.base * op->esize()) % 16 == 0;
                             for (int j = 0; r && j < NPTS - NOWN; ++j)
                               if (foreign_gidx[b * NFP + j] == INVALID_INDEX)
                                 r = false;
