@@ -135,7 +135,7 @@ class Mesh:
         ln = (ctypes.c_double * 3)(*self.length)
         mp = (ctypes.c_double * 4)(*[float(x) for x in map_params])
         pt = (ctypes.c_int * 3)(*[int(x) for x in partition])
-        _check(lib().dasm_mesh_create_structured(ctx.h, nc, per, int(bool(dirichlet)), ln, MAP[map_kind], mp, pt, int(rank),
+        _check(lib().dasm_mesh_create_structured(ctx.h if ctx is not None else None, nc, per, int(bool(dirichlet)), ln, MAP[map_kind], mp, pt, int(rank),
                                                  ctypes.byref(self.h)))
 
     @classmethod
@@ -148,6 +148,21 @@ class Mesh:
     @property
     def n_cells(self):
         return lib().dasm_mesh_n_cells(self.h)
+
+    def host_numbering(self, degree):
+        """host-only (no device needed): numbering sizes, plain compressed indices and the ghost-exchange lists of this rank"""
+        sizes = (ctypes.c_longlong * 6)()
+        none = ctypes.c_void_p()
+        _check(lib().dasm_mesh_host_numbering(self.h, int(degree), sizes, none, none, none, none, none, none))
+        n_owned, n_ghost, n_cells, n_peers, ns, nr = [int(v) for v in sizes]
+        cidx = np.zeros((n_cells, 27), dtype=np.uint32)
+        peers = np.zeros(max(n_peers, 1), dtype=np.int32)
+        sc, rc = np.zeros(max(n_peers, 1), dtype=np.int64), np.zeros(max(n_peers, 1), dtype=np.int64)
+        si, ri = np.zeros(max(ns, 1), dtype=np.uint32), np.zeros(max(nr, 1), dtype=np.uint32)
+        p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        _check(lib().dasm_mesh_host_numbering(self.h, int(degree), sizes, p(cidx), p(peers), p(sc), p(rc), p(si), p(ri)))
+        return dict(n_owned=n_owned, n_ghost=n_ghost, n_cells=n_cells, cidx_plain=cidx, peers=peers[:n_peers], send_count=sc[:n_peers],
+                    recv_count=rc[:n_peers], send_idx=si[:ns], recv_idx=ri[:nr])
 
     def cell_coordinates(self):
         out = np.zeros((self.n_cells, 3), dtype=np.int32)

@@ -1250,6 +1250,52 @@ dasm_mesh_create_structured(dasm_ctx *ctx, const int n_cells[3], const int perio
 }
 
 extern "C" int
+dasm_mesh_host_numbering(const dasm_mesh *mesh, int degree, long long sizes[6], unsigned int *cidx_plain, int *peers, long long *send_count,
+                         long long *recv_count, unsigned int *send_idx, unsigned int *recv_idx)
+{
+  DASM_API_BEGIN
+  DASM_REQUIRE(mesh != nullptr && degree >= 1 && degree <= MAX_DEGREE, "invalid arguments");
+  const Mesh::Numbering nb = mesh->mesh->number_dofs(degree);
+  long long             ns = 0, nr = 0;
+  for (const ExchangeList &l : nb.exchange)
+    {
+      ns += (long long)l.n_send;
+      nr += (long long)l.n_recv;
+    }
+  if (sizes)
+    {
+      sizes[0] = nb.n_owned;
+      sizes[1] = nb.n_ghost;
+      sizes[2] = (long long)mesh->mesh->n_cells;
+      sizes[3] = (long long)nb.exchange.size();
+      sizes[4] = ns;
+      sizes[5] = nr;
+    }
+  if (cidx_plain)
+    std::copy(nb.cidx_plain.begin(), nb.cidx_plain.end(), cidx_plain);
+  size_t so = 0, ro = 0;
+  for (size_t p = 0; p < nb.exchange.size(); ++p)
+    {
+      const ExchangeList &l = nb.exchange[p];
+      if (peers)
+        peers[p] = l.peer;
+      if (send_count)
+        send_count[p] = (long long)l.n_send;
+      if (recv_count)
+        recv_count[p] = (long long)l.n_recv;
+      if (send_idx)
+        for (size_t r = 0; r < l.send_start.size(); ++r)
+          for (uint32_t i = 0; i < l.send_len[r]; ++i)
+            send_idx[so++] = l.send_start[r] + i;
+      if (recv_idx)
+        for (size_t r = 0; r < l.recv_start.size(); ++r)
+          for (uint32_t i = 0; i < l.recv_len[r]; ++i)
+            recv_idx[ro++] = l.recv_start[r] + i;
+    }
+  DASM_API_END
+}
+
+extern "C" int
 dasm_mesh_destroy(dasm_mesh *mesh)
 {
   delete mesh;

@@ -127,6 +127,15 @@ extern "C"
   /* processing order -> global (i,j,k) of every local cell, out[n_cells*3] (host) */
   int dasm_mesh_cell_coordinates(const dasm_mesh *mesh, int *out);
 
+  /* Host-only view (no device, `ctx` of the mesh may be NULL) of what dasm_op_create sets up for this rank's part of a
+   * partitioned mesh: the brick-grouped owner-cell numbering and the ghost-exchange lists (the counterpart of
+   * Utilities::MPI::Partitioner, include/matrix_free_internal.h:21-83).  Used by the multi-process CPU tests.
+   * sizes = {n_owned, n_ghost, n_local_cells, n_peers, n_send_total, n_recv_total}; every array may be NULL:
+   * cidx_plain[n_local_cells*27], peers[n_peers], send_count[n_peers], recv_count[n_peers], send_idx[n_send_total]
+   * (owned DoFs sent to the peers for a ghost update, peer after peer), recv_idx[n_recv_total] (ghost DoFs filled). */
+  int dasm_mesh_host_numbering(const dasm_mesh *mesh, int degree, long long sizes[6], unsigned int *cidx_plain, int *peers,
+                               long long *send_count, long long *recv_count, unsigned int *send_idx, unsigned int *recv_idx);
+
   /* ---- LaplaceOperatorMatrixFree (include/operator.h:266-1628) ------------------------------- */
   /* ctor operator.h:466-482 + setup_mapping_and_indices 490-753.  mapping_type in {"", "merged"}
    * ("linear geometry", "quadratic geometry", "construct q" are not built yet and return an error,
