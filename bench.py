@@ -50,6 +50,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--extra", action="store_true", help="also time vmult / FDM alone (printed to stderr)")
+    ap.add_argument("--map", default="cartesian", choices=["cartesian", "kershaw", "sine"],
+                    help="secondary workloads: kershaw = BASELINE configs[2] (eps 0.3, Dirichlet), not the headline")
+    ap.add_argument("--mapping-type", default="", help='operator mapping type ("", "merged", "quadratic geometry", "linear geometry")')
     return ap.parse_args()
 
 
@@ -228,8 +231,13 @@ def run_ours(args):
     k = args.degree
     S = 8 if args.number == "double" else 4
     t_setup = time.perf_counter()
-    mesh = pkg.Mesh(ctx, nc, periodic=(1, 1, 1), length=length, partition=part, rank=rank)
-    op = pkg.LaplaceOperatorMatrixFree(mesh, k, args.number)
+    if args.map == "cartesian":
+        mesh = pkg.Mesh(ctx, nc, periodic=(1, 1, 1), length=length, partition=part, rank=rank)
+    else:
+        mp_ = (0.3, 0.3, 0., 0.) if args.map == "kershaw" else (0., 0., 0., 0.)
+        mesh = pkg.Mesh(ctx, nc, periodic=(0, 0, 0) if args.map == "kershaw" else (1, 1, 1), dirichlet=True, length=(1., 1., 1.),
+                        map_kind=args.map, map_params=mp_, partition=part, rank=rank)
+    op = pkg.LaplaceOperatorMatrixFree(mesh, k, args.number, mapping_type=args.mapping_type)
     fdm = pkg.create_fdm_preconditioner(op, {"n overlap": 1, "weighting type": args.weighting, "weight sequence": "compressed"})
     cheb = pkg.PreconditionChebyshev(op, fdm, degree=args.cheb_degree, optimize=2)
     cheb.set_eigenvalues(1.0, 2.4)  # fixed so that every rank count does identical arithmetic
@@ -363,9 +371,12 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": "DoFs/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64" if args.number == "double" else "f32", "data": "synthetic",
-        "config": {"workload": "matrix_free_loop_08 label cheby-%d-2-%s-1-c: FE_Q(%d), periodic Cartesian hyper-rectangle, "
+        "config": {"workload": "matrix_free_loop_08 label cheby-%d-2-%s-1-c: FE_Q(%d), %s, "
                                "%dx%dx%d cells per GPU (n subdivisions 41), brick partition %dx%dx%d" % (
-                                   args.cheb_degree, args.weighting, k, cpg[0], cpg[1], cpg[2], part[0], part[1], part[2]),
+                                   args.cheb_degree, args.weighting, k,
+                                   "periodic Cartesian hyper-rectangle" if args.map == "cartesian" else
+                                   "%s-deformed mesh, mapping type '%s' (secondary workload; the roofline bytes omit the geometry data)" % (args.map, args.mapping_type),
+                                   cpg[0], cpg[1], cpg[2], part[0], part[1], part[2]),
                    "n_dofs": int(n_glob), "n_dofs_per_gpu": int(n_own), "n_cells_per_gpu": int(n_cells_local),
                    "chebyshev_degree": args.cheb_degree, "l2": "inputs larger than L2 (each vector %.0f MB)" % (n_own * S / 1e6),
                    "setup_s": t_setup},

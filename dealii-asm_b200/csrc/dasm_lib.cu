@@ -1422,7 +1422,10 @@ dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping
   // tuned brick path: degrees 1..5, one rank (the multi-rank path uses the generic kernels for now)
   {
     const char *force = getenv("DASM_FORCE_GENERIC");
-    op->use_brick     = (degree <= 5) && !(force && force[0] == '1');
+    // (degree 5 runs faster through the generic kernels: 1.70e10 vs 1.24e10 DoFs/s per Chebyshev term, profiles/r01c_secondary.log;
+    // DASM_BRICK_K5=1 selects the 4x4x2 brick kernels)
+    const char *k5    = getenv("DASM_BRICK_K5");
+    op->use_brick     = (degree <= 4 || (degree == 5 && k5 && k5[0] == '1')) && !(force && force[0] == '1');
     if (op->use_brick)
       {
         op->brick_bz = (degree <= 4) ? 4 : 2;
