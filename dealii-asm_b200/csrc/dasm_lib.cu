@@ -298,7 +298,7 @@ struct dasm_op
   uint32_t *        d_slow_ids  = nullptr; // all other bricks
   int               n_fast = 0, n_slow = 0;
   std::vector<uint32_t> h_fast_ids;
-  double            lap_mats[4][81]; // M, g0 K, g1 K, g2 K (row-major n x n)
+  double            lap_P[4][25], lap_Q[4][25]; // even-odd blocks (kernels_fast.cuh EOMat) of M, g0 K, g1 K, g2 K
 
   dasm_op(int degree)
     : basis(degree)
@@ -331,7 +331,7 @@ struct dasm_fdm
   bool      fast_ok    = false;
   uint32_t *d_fast_ids = nullptr, *d_slow_ids = nullptr;
   int       n_fast = 0, n_slow = 0;
-  double    fast_mats[6][81]; // Ax Ay Az Bx By Bz
+  double    fast_P[6][25], fast_Q[6][25]; // even-odd blocks of Ax Ay Az Bx By Bz
   double    fast_inv[729];
   std::vector<double>   h_S, h_lam; // double copies for inspection
   std::vector<uint32_t> h_inst;
@@ -394,6 +394,85 @@ struct dasm_cheb
       using T = float;                            \
       __VA_ARGS__;                                \
     }
+
+// ---- even-odd blocks of the 1-D matrices of the warp-specialised kernels (EOMat in kernels_fast.cuh) -------------------
+// centrosymmetric matrix A[o][i] = A[n-1-o][n-1-i] (mass / stiffness on symmetric nodes), nodal -> nodal
+static bool
+eo_pack_centrosymmetric(const int n, const double *A, double *P, double *Q)
+{
+  const int m = (n + 1) / 2, h = n / 2;
+  double    amax = 0;
+  for (int i = 0; i < n * n; ++i)
+    amax = std::max(amax, std::fabs(A[i]));
+  for (int o = 0; o < n; ++o)
+    for (int i = 0; i < n; ++i)
+      if (std::fabs(A[o * n + i] - A[(n - 1 - o) * n + (n - 1 - i)]) > 1e-12 * amax)
+        return false;
+  for (int o = 0; o < m; ++o)
+    {
+      for (int i = 0; i < h; ++i)
+        P[o * m + i] = 0.5 * (A[o * n + i] + A[o * n + n - 1 - i]);
+      if (m > h)
+        P[o * m + h] = A[o * n + h];
+    }
+  for (int o = 0; o < h; ++o)
+    for (int i = 0; i < h; ++i)
+      Q[o * h + i] = 0.5 * (A[o * n + i] - A[o * n + n - 1 - i]);
+  return true;
+}
+
+// forward matrix B[a][i] (rows: eigen index in even-first order, columns: nodal) with B[a][n-1-i] = +-B[a][i]
+static bool
+eo_pack_forward(const int n, const double *B, double *P, double *Q)
+{
+  const int m = (n + 1) / 2, h = n / 2;
+  double    bmax = 0;
+  for (int i = 0; i < n * n; ++i)
+    bmax = std::max(bmax, std::fabs(B[i]));
+  for (int a = 0; a < n; ++a)
+    for (int i = 0; i < n; ++i)
+      if (std::fabs(B[a * n + n - 1 - i] - (a < m ? 1. : -1.) * B[a * n + i]) > 1e-11 * bmax)
+        return false;
+  for (int a = 0; a < m; ++a)
+    for (int i = 0; i < m; ++i)
+      P[a * m + i] = B[a * n + i];
+  for (int a = 0; a < h; ++a)
+    for (int i = 0; i < h; ++i)
+      Q[a * h + i] = B[(m + a) * n + i];
+  return true;
+}
+
+// backward matrix C[o][a] (rows: nodal, columns: eigen index in even-first order) with C[n-1-o][a] = +-C[o][a]
+static bool
+eo_pack_backward(const int n, const double *C, double *P, double *Q)
+{
+  const int m = (n + 1) / 2, h = n / 2;
+  double    cmax = 0;
+  for (int i = 0; i < n * n; ++i)
+    cmax = std::max(cmax, std::fabs(C[i]));
+  for (int o = 0; o < n; ++o)
+    for (int a = 0; a < n; ++a)
+      if (std::fabs(C[(n - 1 - o) * n + a] - (a < m ? 1. : -1.) * C[o * n + a]) > 1e-11 * cmax)
+        return false;
+  for (int o = 0; o < m; ++o)
+    for (int a = 0; a < m; ++a)
+      P[o * m + a] = C[o * n + a];
+  for (int o = 0; o < h; ++o)
+    for (int a = 0; a < h; ++a)
+      Q[o * h + a] = C[o * n + m + a];
+  return true;
+}
+
+template <typename T, int n>
+static void
+eo_fill(EOMat<T, n> &E, const double *P, const double *Q)
+{
+  constexpr int m = (n + 1) / 2, h = n / 2;
+  for (int i = 0; i < m * m; ++i)
+    E.P[i] = (T)P[i];
+  for (int i = 0; i < h * h; ++i)
+    E.Q[i] = (T)Q[i];
+}
 
 // tile layout parameters of kernels_fast.cuh (FastSkew) for the host-side table construction
 static void
@@ -679,15 +758,11 @@ launch_laplace_fast(dasm_op *op, T *dst, const T *src, const Epilogue<T> &epi, c
   constexpr size_t smem = G::smem_bytes(1, 2, 1);
   if (smem > (size_t)op->max_smem || epilogue_n_operands(epi) > 1) // one operand buffer (b of the residual epilogue)
     return false;
-  constexpr int             n = K + 1;
   FastLaplaceMats<T, K + 1> mats;
-  for (int i = 0; i < n * n; ++i)
-    {
-      mats.M[i]  = (T)op->lap_mats[0][i];
-      mats.K0[i] = (T)op->lap_mats[1][i];
-      mats.K1[i] = (T)op->lap_mats[2][i];
-      mats.K2[i] = (T)op->lap_mats[3][i];
-    }
+  eo_fill(mats.M, op->lap_P[0], op->lap_Q[0]);
+  eo_fill(mats.K0, op->lap_P[1], op->lap_Q[1]);
+  eo_fill(mats.K1, op->lap_P[2], op->lap_Q[2]);
+  eo_fill(mats.K2, op->lap_P[3], op->lap_Q[3]);
   const int grid = std::min(op->n_fast, op->n_sm);
   FastMaps  fm   = {op->d_fast_ltab, op->d_fast_ftab, op->maps.foreign_gidx, op->d_fast_ids, op->n_fast, fast_prof_buffer(grid), fast_dbg()};
   auto      kern = laplace_fast_kernel<K, T>;
@@ -883,15 +958,12 @@ launch_fdm_fast(dasm_fdm *f, T *dst, const T *src, const Epilogue<T> &epi, const
     return false;
   constexpr int         n = K + 1;
   FastFdmMats<T, K + 1> mats;
-  for (int i = 0; i < n * n; ++i)
-    {
-      mats.Ax[i] = (T)f->fast_mats[0][i];
-      mats.Ay[i] = (T)f->fast_mats[1][i];
-      mats.Az[i] = (T)f->fast_mats[2][i];
-      mats.Bx[i] = (T)f->fast_mats[3][i];
-      mats.By[i] = (T)f->fast_mats[4][i];
-      mats.Bz[i] = (T)f->fast_mats[5][i];
-    }
+  eo_fill(mats.Ax, f->fast_P[0], f->fast_Q[0]);
+  eo_fill(mats.Ay, f->fast_P[1], f->fast_Q[1]);
+  eo_fill(mats.Az, f->fast_P[2], f->fast_Q[2]);
+  eo_fill(mats.Bx, f->fast_P[3], f->fast_Q[3]);
+  eo_fill(mats.By, f->fast_P[4], f->fast_Q[4]);
+  eo_fill(mats.Bz, f->fast_P[5], f->fast_Q[5]);
   for (int i = 0; i < n * n * n; ++i)
     mats.inv[i] = (T)f->fast_inv[i];
   const int grid = std::min(f->n_fast, op->n_sm);
@@ -1804,13 +1876,19 @@ dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping
                             op->h_fast_ids  = fast_ids;
                           }
                       }
-                    // 1-D matrices of the Kronecker form of the Cartesian cell matrix
-                    for (int i = 0; i < n * n; ++i)
-                      {
-                        op->lap_mats[0][i] = op->basis.M_ref[i];
-                        for (int d = 0; d < 3; ++d)
-                          op->lap_mats[1 + d][i] = op->cart.g[d] * op->basis.K_ref[i];
-                      }
+                    // 1-D matrices of the Kronecker form of the Cartesian cell matrix in even-odd form
+                    {
+                      std::vector<double> A(n * n);
+                      bool                eo = eo_pack_centrosymmetric(n, op->basis.M_ref.data(), op->lap_P[0], op->lap_Q[0]);
+                      for (int d = 0; d < 3; ++d)
+                        {
+                          for (int i = 0; i < n * n; ++i)
+                            A[i] = op->cart.g[d] * op->basis.K_ref[i];
+                          eo = eo_pack_centrosymmetric(n, A.data(), op->lap_P[1 + d], op->lap_Q[1 + d]) && eo;
+                        }
+                      if (!eo)
+                        op->fast_ok = false;
+                    }
                   }
               }
             else
@@ -2599,24 +2677,68 @@ dasm_fdm_create(dasm_op *op, int n_overlap, int sub_mesh_approximation, int weig
             ((w_ok && is_fast[b]) ? fast_ids : slow_ids).push_back((uint32_t)b);
           if (!fast_ids.empty())
             {
-              auto ent = [&](int i) { return i == 0 ? 0 : (i == n - 1 ? 2 : 1); };
-              for (int d = 0; d < 3; ++d)
+              // even-odd form: the eigenvectors of the symmetric 1-D problem are even or odd under i -> n-1-i; the even
+              // ones are ordered first (the eigenvalues follow), the weights must be symmetric
+              auto   ent   = [&](int i) { return i == 0 ? 0 : (i == n - 1 ? 2 : 1); };
+              const int m_ev = (n + 1) / 2;
+              bool   eo_ok = true;
+              double lam_p[3][9];
+              for (int d = 0; d < 3 && eo_ok; ++d)
                 {
                   const double *S = f->h_S.data() + (size_t)best[d] * n * n;
+                  const double *l = f->h_lam.data() + (size_t)best[d] * n;
+                  if (f->wmode == 1 && std::fabs(w1[d][0] - w1[d][2]) > 1e-14 * std::fabs(w1[d][0]))
+                    eo_ok = false;
+                  std::vector<int> perm, odd;
+                  double           smax = 0;
+                  for (int i = 0; i < n * n; ++i)
+                    smax = std::max(smax, std::fabs(S[i]));
                   for (int a = 0; a < n; ++a)
-                    for (int i = 0; i < n; ++i)
-                      {
-                        // first stage: u_a = sum_i S[i][a] w_i v_i;  second stage: y_o = w_o sum_i S[o][i] u_i
-                        f->fast_mats[d][a * n + i]     = S[i * n + a] * ((f->wmode == 1 && f->w_pre) ? w1[d][ent(i)] : 1.);
-                        f->fast_mats[3 + d][a * n + i] = S[a * n + i] * ((f->wmode == 1 && f->w_post) ? w1[d][ent(a)] : 1.);
-                      }
+                    {
+                      double de = 0, dod = 0;
+                      for (int i = 0; i < n; ++i)
+                        {
+                          de  = std::max(de, std::fabs(S[(n - 1 - i) * n + a] - S[i * n + a]));
+                          dod = std::max(dod, std::fabs(S[(n - 1 - i) * n + a] + S[i * n + a]));
+                        }
+                      if (de <= 1e-11 * smax)
+                        perm.push_back(a);
+                      else if (dod <= 1e-11 * smax)
+                        odd.push_back(a);
+                      else
+                        eo_ok = false;
+                    }
+                  if ((int)perm.size() != m_ev)
+                    eo_ok = false;
+                  if (!eo_ok)
+                    break;
+                  perm.insert(perm.end(), odd.begin(), odd.end());
+                  std::vector<double> B(n * n), C(n * n);
+                  for (int a = 0; a < n; ++a)
+                    {
+                      lam_p[d][a] = l[perm[a]];
+                      for (int i = 0; i < n; ++i)
+                        {
+                          // first stage: u_a = sum_i S[i][a] w_i v_i;  second stage: y_o = w_o sum_a S[o][a] u_a
+                          B[a * n + i] = S[i * n + perm[a]] * ((f->wmode == 1 && f->w_pre) ? w1[d][ent(i)] : 1.);
+                          C[i * n + a] = S[i * n + perm[a]] * ((f->wmode == 1 && f->w_post) ? w1[d][ent(i)] : 1.);
+                        }
+                    }
+                  eo_ok = eo_pack_forward(n, B.data(), f->fast_P[d], f->fast_Q[d]) && eo_pack_backward(n, C.data(), f->fast_P[3 + d], f->fast_Q[3 + d]);
                 }
-              const double *l0 = f->h_lam.data() + (size_t)best[0] * n, *l1 = f->h_lam.data() + (size_t)best[1] * n,
-                           *l2 = f->h_lam.data() + (size_t)best[2] * n;
-              for (int z = 0; z < n; ++z)
-                for (int y = 0; y < n; ++y)
-                  for (int x = 0; x < n; ++x)
-                    f->fast_inv[(z * n + y) * n + x] = 1. / (l0[x] + l1[y] + l2[z]);
+              if (eo_ok)
+                for (int z = 0; z < n; ++z)
+                  for (int y = 0; y < n; ++y)
+                    for (int x = 0; x < n; ++x)
+                      f->fast_inv[(z * n + y) * n + x] = 1. / (lam_p[0][x] + lam_p[1][y] + lam_p[2][z]);
+              if (!eo_ok)
+                {
+                  fast_ids.clear();
+                  slow_ids.clear();
+                }
+            }
+          if (!fast_ids.empty())
+            {
               f->fast_ok    = true;
               f->n_fast     = (int)fast_ids.size();
               f->n_slow     = (int)slow_ids.size();
