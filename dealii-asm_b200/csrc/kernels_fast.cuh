@@ -658,21 +658,16 @@ namespace dasm
         // phase A: plane y = t, [z][x]: q = Mx Mz v, p = (g0 Kx Mz + g2 Mx Kz) v
         if (!(maps.dbg & 1))
         {
-          // b = g0 Kx v is parked in this thread's part of the p slot (the same addresses p is written to below): the
-          // register budget holds a, one column of b and the column results without spilling
-          T a[n][n];
+          T a[n][n], b[n][n];
 #pragma unroll
           for (int z = 0; z < n; ++z)
             {
-              T v[n], bz[n];
+              T v[n];
 #pragma unroll
               for (int x = 0; x < n; ++x)
                 v[x] = tp[z * G::SZ + x];
               mat_vec<n, T, true, true, false>(a[z], mats.M, v);
-              mat_vec<n, T, true, true, false>(bz, mats.K0, v);
-#pragma unroll
-              for (int x = 0; x < n; ++x)
-                xp[(z * n + t) * n + x] = bz[x];
+              mat_vec<n, T, true, true, false>(b[z], mats.K0, v);
             }
           fast_prof(maps, li, 2, tid == 0);
           if (!first)
@@ -686,7 +681,7 @@ namespace dasm
               for (int z = 0; z < n; ++z)
                 {
                   ca[z] = a[z][x];
-                  cb[z] = xp[(z * n + t) * n + x];
+                  cb[z] = b[z][x];
                 }
               mat_vec<n, T, true, true, false>(q, mats.M, ca);
               mat_vec<n, T, true, true, false>(p, mats.M, cb);
