@@ -378,6 +378,7 @@ def run_ours(args):
                                    "%s-deformed mesh, mapping type '%s' (secondary workload; the roofline bytes omit the geometry data)" % (args.map, args.mapping_type),
                                    cpg[0], cpg[1], cpg[2], part[0], part[1], part[2]),
                    "n_dofs": int(n_glob), "n_dofs_per_gpu": int(n_own), "n_cells_per_gpu": int(n_cells_local),
+                   "regular_bricks_laplace": int(op.n_fast_bricks()), "regular_bricks_fdm": int(fdm.n_fast_bricks()),
                    "chebyshev_degree": args.cheb_degree, "l2": "inputs larger than L2 (each vector %.0f MB)" % (n_own * S / 1e6),
                    "setup_s": t_setup},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,

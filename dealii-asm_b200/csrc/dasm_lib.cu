@@ -2631,6 +2631,27 @@ dasm_fdm_create(dasm_op *op, int n_overlap, int sub_mesh_approximation, int weig
           std::vector<uint32_t> fast_ids, slow_ids;
           const uint8_t *       ref_codes = nullptr;
           std::vector<char>     is_fast(op->n_bricks, 0);
+          if (f->wmode == 1)
+            {
+              // reference weight pattern: the most frequent one among the first cells of the candidate bricks
+              std::map<std::array<uint8_t, 27>, std::pair<int, const uint8_t *>> patterns;
+              for (const uint32_t b : op->h_fast_ids)
+                {
+                  const uint8_t *         cb = codes.data() + (size_t)bricks[b].first_cell * 32;
+                  std::array<uint8_t, 27> key;
+                  std::copy(cb, cb + 27, key.begin());
+                  auto &e = patterns[key];
+                  e.first++;
+                  e.second = cb;
+                }
+              int most = 0;
+              for (const auto &kv : patterns)
+                if (kv.second.first > most)
+                  {
+                    most      = kv.second.first;
+                    ref_codes = kv.second.second;
+                  }
+            }
           for (const uint32_t b : op->h_fast_ids)
             {
               if (nbest == 0 || !tri[b].w || tri[b].x != best[0] || tri[b].y != best[1] || tri[b].z != best[2])
@@ -2639,8 +2660,6 @@ dasm_fdm_create(dasm_op *op, int n_overlap, int sub_mesh_approximation, int weig
               if (f->wmode == 1)
                 {
                   const uint8_t *cb = codes.data() + (size_t)bricks[b].first_cell * 32;
-                  if (ref_codes == nullptr)
-                    ref_codes = cb;
                   for (int c = 0; c < 64 && same; ++c)
                     same = (memcmp(cb + c * 32, ref_codes, 27) == 0);
                 }

@@ -637,7 +637,7 @@ namespace dasm
     if (i < n)
       {
         if (ADD)
-          vec[map[i]] += buf[i];
+          atomic_add(vec + map[i], buf[i]); // an owned DoF on a partition edge / corner receives from several peers
         else
           vec[map[i]] = buf[i];
       }
