@@ -206,12 +206,12 @@ struct Exchange
   // owner -> ghost (update_ghost_values) or ghost -> owner with add (compress)
   template <typename T>
   void
-  run(T *vec, bool compress)
+  run(T *vec, bool compress, cudaStream_t on_stream = nullptr)
   {
     if (!active())
       return;
     DASM_REQUIRE(ctx->comm != nullptr, "multi-rank mesh needs dasm_ctx_comm_init before any operator application");
-    cudaStream_t    s     = ctx->stream;
+    cudaStream_t    s     = on_stream ? on_stream : ctx->stream;
     const size_t    n_out = compress ? n_recv : n_send;
     const size_t    n_in  = compress ? n_send : n_recv;
     const uint32_t *omap  = compress ? d_recv_map : d_send_map;
@@ -298,6 +298,10 @@ struct dasm_op
   uint32_t *        d_slow_ids  = nullptr; // all other bricks
   int               n_fast = 0, n_slow = 0;
   std::vector<uint32_t> h_fast_ids;
+  // overlap of the halo exchange with the interior bricks: d_fast_ids = [bricks on the partition boundary | interior bricks]
+  int               n_fast_boundary = 0;
+  std::vector<char> h_brick_boundary;
+  const void *      last_compressed = nullptr; // vector whose partition-boundary values are final on the comm stream
   double            lap_P[4][25], lap_Q[4][25]; // even-odd blocks (kernels_fast.cuh EOMat) of M, g0 K, g1 K, g2 K
 
   dasm_op(int degree)
@@ -330,7 +334,7 @@ struct dasm_fdm
   // warp-specialised kernel: bricks with the most frequent instance triple and weight pattern
   bool      fast_ok    = false;
   uint32_t *d_fast_ids = nullptr, *d_slow_ids = nullptr;
-  int       n_fast = 0, n_slow = 0;
+  int       n_fast = 0, n_slow = 0, n_fast_boundary = 0;
   double    fast_P[6][25], fast_Q[6][25]; // even-odd blocks of Ax Ay Az Bx By Bz
   double    fast_inv[729];
   std::vector<double>   h_S, h_lam; // double copies for inspection
@@ -749,11 +753,67 @@ fast_prof_report(const char *name, long long *d, const int grid, cudaStream_t s)
   fprintf(stderr, "\n");
 }
 
+// ---- overlap of the halo exchange with the interior bricks (fused SHARED_DIRECT sequences on several ranks) --------------
+// main stream:  [wait ghost update] boundary bricks + irregular bricks | interior bricks                 | [wait compress]
+// comm stream:  ghost update(src)                                     | compress(dst)  (-> ghost update of the next sweep)
+// The source of a sweep is the destination of the previous one: its values on the partition boundary are final once the
+// previous compress has run on the comm stream, so the ghost update of sweep j+1 overlaps with the interior bricks of sweep j.
+static bool
+overlap_enabled(const dasm_op *op, const int shared_mode, const int n_fast_boundary, const int n_fast)
+{
+  static const bool off = getenv("DASM_NO_OVERLAP") && getenv("DASM_NO_OVERLAP")[0] == '1';
+  return !off && op->exchange.active() && shared_mode == SHARED_DIRECT && n_fast > n_fast_boundary;
+}
+
+template <typename T>
+static void
+overlap_pre(dasm_op *op, T *dst, const T *src)
+{
+  dasm_ctx *ctx = op->ctx;
+  if ((const void *)src != op->last_compressed)
+    {
+      // the source was produced on the main stream
+      CUDA_CHECK(cudaEventRecord(ctx->ev_a, ctx->stream));
+      CUDA_CHECK(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_a, 0));
+    }
+  if (op->n_ghost > 0)
+    CUDA_CHECK(cudaMemsetAsync(dst + op->n_owned, 0, (size_t)op->n_ghost * sizeof(T), ctx->stream));
+  op->exchange.run<T>(const_cast<T *>(src), false, ctx->comm_stream);
+  CUDA_CHECK(cudaEventRecord(ctx->ev_b, ctx->comm_stream));
+  CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_b, 0)); // the boundary bricks read the ghost values
+}
+
+// after the boundary (and irregular) bricks have been launched on the main stream
+template <typename T>
+static void
+overlap_mid(dasm_op *op, T *dst, const bool needs_compression)
+{
+  dasm_ctx *ctx = op->ctx;
+  CUDA_CHECK(cudaEventRecord(ctx->ev_a, ctx->stream));
+  CUDA_CHECK(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_a, 0));
+  if (needs_compression)
+    op->exchange.run<T>(dst, true, ctx->comm_stream);
+  CUDA_CHECK(cudaEventRecord(ctx->ev_b, ctx->comm_stream));
+  op->last_compressed = dst;
+}
+
+// after the interior bricks have been launched: later work on the main stream sees the compressed destination
+static void
+overlap_post(dasm_op *op)
+{
+  CUDA_CHECK(cudaStreamWaitEvent(op->ctx->stream, op->ctx->ev_b, 0));
+}
+
 // warp-specialised Laplace kernel over the regular bricks; false: not available (shared memory), nothing launched
 template <int K, typename T>
 static bool
-launch_laplace_fast(dasm_op *op, T *dst, const T *src, const Epilogue<T> &epi, const int shared_mode, const NextInit<T> &ni)
+launch_laplace_fast(dasm_op *op, T *dst, const T *src, const Epilogue<T> &epi, const int shared_mode, const NextInit<T> &ni, const int first = 0,
+                    int count = -1)
 {
+  if (count < 0)
+    count = op->n_fast - first;
+  if (count == 0)
+    return true;
   using G             = FastGeom<K, T>;
   constexpr size_t smem = G::smem_bytes(1, 2, 1);
   if (smem > (size_t)op->max_smem || epilogue_n_operands(epi) > 1) // one operand buffer (b of the residual epilogue)
@@ -763,8 +823,8 @@ launch_laplace_fast(dasm_op *op, T *dst, const T *src, const Epilogue<T> &epi, c
   eo_fill(mats.K0, op->lap_P[1], op->lap_Q[1]);
   eo_fill(mats.K1, op->lap_P[2], op->lap_Q[2]);
   eo_fill(mats.K2, op->lap_P[3], op->lap_Q[3]);
-  const int grid = std::min(op->n_fast, op->n_sm);
-  FastMaps  fm   = {op->d_fast_ltab, op->d_fast_ftab, op->maps.foreign_gidx, op->d_fast_ids, op->n_fast, fast_prof_buffer(grid), fast_dbg()};
+  const int grid = std::min(count, op->n_sm);
+  FastMaps  fm   = {op->d_fast_ltab, op->d_fast_ftab, op->maps.foreign_gidx, op->d_fast_ids + first, count, fast_prof_buffer(grid), fast_dbg()};
   auto      kern = laplace_fast_kernel<K, T>;
   CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, G::NT, smem, op->ctx->stream>>>(src, dst, (T *)op->d_acc, epi, op->d_bricks, mats, shared_mode, ni, fm);
@@ -781,6 +841,34 @@ launch_laplace_brick(dasm_op *op, T *dst, const T *src, const Epilogue<T> &epi, 
   dasm_ctx *   ctx   = op->ctx;
   const int    n_ops = epilogue_n_operands(epi);
   const size_t smem  = BrickGeom<K, BZ>::template smem_bytes<T>(n_ops, BZ == 4);
+  if constexpr (BZ == 4 && K >= 2 && K <= 4)
+    {
+      if (op->geom_mode == 0 && op->fast_ok && n_ops <= 1 && FastGeom<K, T>::smem_bytes(1, 2, 1) <= (size_t)op->max_smem &&
+          overlap_enabled(op, shared_mode, op->n_fast_boundary, op->n_fast))
+        {
+          // halo exchange overlapped with the interior bricks (see overlap_pre)
+          overlap_pre<T>(op, dst, src);
+          {
+            KernelTimer timer(ctx, KC_LAPLACE);
+            launch_laplace_fast<K, T>(op, dst, src, epi, shared_mode, ni, 0, op->n_fast_boundary);
+            if (op->n_slow > 0)
+              {
+                auto      kern = laplace_brick_kernel<K, T, BZ, 0>;
+                const int grid = std::min(op->n_slow, brick_grid<K, BZ, T>(op, kern, smem));
+                kern<<<grid, BrickGeom<K, BZ>::NT, smem, ctx->stream>>>(src, dst, (T *)op->d_acc, epi, op->d_cidx, op->d_bricks, op->n_slow,
+                                                                         (const T *)nullptr, op->cart, n_ops, shared_mode, ni, op->maps, op->d_slow_ids);
+                ctx->launches++;
+              }
+            overlap_mid<T>(op, dst, true);
+            launch_laplace_fast<K, T>(op, dst, src, epi, shared_mode, ni, op->n_fast_boundary, op->n_fast - op->n_fast_boundary);
+          }
+          overlap_post(op);
+          CUDA_CHECK(cudaGetLastError());
+          brick_finish<K, BZ, T>(op, dst, copy_constrained ? src : nullptr, epi, shared_mode);
+          CUDA_CHECK(cudaGetLastError());
+          return;
+        }
+    }
   brick_pre_exchange<T>(op, dst, src, shared_mode);
   {
     KernelTimer timer(ctx, KC_LAPLACE);
@@ -949,8 +1037,13 @@ launch_fdm(dasm_fdm *f, T *dst, const T *src)
 
 template <int K, typename T>
 static bool
-launch_fdm_fast(dasm_fdm *f, T *dst, const T *src, const Epilogue<T> &epi, const int shared_mode, const NextInit<T> &ni)
+launch_fdm_fast(dasm_fdm *f, T *dst, const T *src, const Epilogue<T> &epi, const int shared_mode, const NextInit<T> &ni, const int first = 0,
+                int count = -1)
 {
+  if (count < 0)
+    count = f->n_fast - first;
+  if (count == 0)
+    return true;
   using G               = FastGeom<K, T>;
   dasm_op *        op   = f->op;
   constexpr size_t smem = G::smem_bytes(2, 1, 2);
@@ -966,8 +1059,8 @@ launch_fdm_fast(dasm_fdm *f, T *dst, const T *src, const Epilogue<T> &epi, const
   eo_fill(mats.Bz, f->fast_P[5], f->fast_Q[5]);
   for (int i = 0; i < n * n * n; ++i)
     mats.inv[i] = (T)f->fast_inv[i];
-  const int grid = std::min(f->n_fast, op->n_sm);
-  FastMaps  fm   = {op->d_fast_ltab, op->d_fast_ftab, op->maps.foreign_gidx, f->d_fast_ids, f->n_fast, fast_prof_buffer(grid), fast_dbg()};
+  const int grid = std::min(count, op->n_sm);
+  FastMaps  fm   = {op->d_fast_ltab, op->d_fast_ftab, op->maps.foreign_gidx, f->d_fast_ids + first, count, fast_prof_buffer(grid), fast_dbg()};
   auto      kern = fdm_fast_kernel<K, T>;
   CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, G::NT, smem, op->ctx->stream>>>(src, dst, (T *)op->d_acc, epi, op->d_bricks, mats, shared_mode, ni, fm);
@@ -984,11 +1077,40 @@ launch_fdm_brick(dasm_fdm *f, T *dst, const T *src, const Epilogue<T> &epi, cons
   dasm_ctx *   ctx   = op->ctx;
   const int    n_ops = epilogue_n_operands(epi);
   const size_t smem  = BrickGeom<K, BZ>::template smem_bytes<T>(n_ops, BZ == 4);
-  brick_pre_exchange<T>(op, dst, src, shared_mode);
   static const int dbg = getenv("DASM_DEBUG_SKIP") ? atoi(getenv("DASM_DEBUG_SKIP")) : 0; // timing experiments only
   WeightTable<T>   wt;
   for (int i = 0; i < 16; ++i)
     wt.v[i] = (T)f->wtab[i];
+  if constexpr (BZ == 4 && K >= 2 && K <= 4)
+    {
+      if (f->fast_ok && FastGeom<K, T>::smem_bytes(2, 1, 2) <= (size_t)op->max_smem &&
+          overlap_enabled(op, shared_mode, f->n_fast_boundary, f->n_fast))
+        {
+          // halo exchange overlapped with the interior bricks (see overlap_pre)
+          overlap_pre<T>(op, dst, src);
+          {
+            KernelTimer timer(ctx, KC_FDM);
+            launch_fdm_fast<K, T>(f, dst, src, epi, shared_mode, ni, 0, f->n_fast_boundary);
+            if (f->n_slow > 0)
+              {
+                auto      kern = fdm_brick_kernel<K, T, BZ>;
+                const int grid = std::min(f->n_slow, brick_grid<K, BZ, T>(op, kern, smem));
+                kern<<<grid, BrickGeom<K, BZ>::NT, smem, ctx->stream>>>(src, dst, (T *)op->d_acc, epi, op->d_cidx, op->d_bricks, f->n_slow, f->d_inst,
+                                                                         (const T *)f->d_S, (const T *)f->d_lam, (const uint8_t *)(f->wmode == 1 ? f->d_cwcode : nullptr), wt, f->d_brick_tri,
+                                                                         (int)f->w_pre, (int)f->w_post, n_ops, shared_mode, ni, op->maps, dbg, f->d_slow_ids);
+                ctx->launches++;
+              }
+            overlap_mid<T>(op, dst, f->weight_type != DASM_WEIGHT_RAS);
+            launch_fdm_fast<K, T>(f, dst, src, epi, shared_mode, ni, f->n_fast_boundary, f->n_fast - f->n_fast_boundary);
+          }
+          overlap_post(op);
+          CUDA_CHECK(cudaGetLastError());
+          brick_finish<K, BZ, T>(op, dst, (const T *)nullptr, epi, shared_mode);
+          CUDA_CHECK(cudaGetLastError());
+          return;
+        }
+    }
+  brick_pre_exchange<T>(op, dst, src, shared_mode);
   {
     KernelTimer     timer(ctx, KC_FDM);
     const uint32_t *order    = nullptr;
@@ -1542,6 +1664,15 @@ dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping
                             bd.shared |= (1u << (2 * d + 1));
                         }
                       bricks.push_back(bd);
+                      {
+                        // on the boundary of this rank's box in a partitioned direction?
+                        const int bl[3] = {bx, by, bz + z0}, bh[3] = {bx + dx, by + dy, bz + z0 + sz};
+                        bool      onb   = false;
+                        for (int d = 0; d < 3; ++d)
+                          if (M.p.part[d] > 1 && (bl[d] == 0 || bh[d] == M.nl[d]))
+                            onb = true;
+                        op->h_brick_boundary.push_back(onb ? 1 : 0);
+                      }
                     }
                   first += (size_t)dx * dy * dz;
                 }
@@ -1866,6 +1997,10 @@ dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping
                           }
                         if (regular && !fast_ids.empty())
                           {
+                            std::stable_partition(fast_ids.begin(), fast_ids.end(), [&](uint32_t b) { return op->h_brick_boundary[b] != 0; });
+                            op->n_fast_boundary = 0;
+                            for (const uint32_t b : fast_ids)
+                              op->n_fast_boundary += op->h_brick_boundary[b] ? 1 : 0;
                             op->fast_ok     = true;
                             op->d_fast_ltab = dev_upload(lt, ctx->stream);
                             op->d_fast_ftab = dev_upload(ft, ctx->stream);
@@ -2758,6 +2893,10 @@ dasm_fdm_create(dasm_op *op, int n_overlap, int sub_mesh_approximation, int weig
             }
           if (!fast_ids.empty())
             {
+              std::stable_partition(fast_ids.begin(), fast_ids.end(), [&](uint32_t b) { return op->h_brick_boundary[b] != 0; });
+              f->n_fast_boundary = 0;
+              for (const uint32_t b : fast_ids)
+                f->n_fast_boundary += op->h_brick_boundary[b] ? 1 : 0;
               f->fast_ok    = true;
               f->n_fast     = (int)fast_ids.size();
               f->n_slow     = (int)slow_ids.size();
@@ -3182,6 +3321,7 @@ cheb_run(dasm_cheb *c, T *x_user, const T *b, bool first_is_step)
   const long long n   = op->n_owned;
   if (!c->ev_ready)
     cheb_estimate<T>(c);
+  op->last_compressed = nullptr; // the first sweep waits for the main stream
   T *t1 = (T *)c->t1, *t2 = (T *)c->t2;
   const double f2_0 = (c->poly == DASM_POLY_FOURTH_KIND) ? 4. / (3. * c->theta) : 1. / c->theta;
   const int    n_terms = (c->degree < 2 || std::fabs(c->delta) < 1e-40) ? 1 : c->degree;

@@ -56,7 +56,9 @@ def main():
         ctx.comm_init(world, rank, ident[0])
     part = PART[world]
     ok = True
-    for k, number, nc, wt in ((4, "double", (8, 8, 8), "symm"), (3, "double", (8, 6, 4), "post"), (2, "double", (8, 8, 8), "none")):
+    # the (24, 8, 8) mesh has interior bricks on every rank of a 2 x 1 x 1 partition: the halo exchange overlaps with them
+    for k, number, nc, wt in ((4, "double", (8, 8, 8), "symm"), (3, "double", (8, 6, 4), "post"), (2, "double", (8, 8, 8), "none"),
+                              (4, "double", (24, 8, 8), "symm"), (3, "float", (24, 8, 8), "post")):
         L = tuple(float(c) / 4 for c in nc)
         vsize = None
         results = {}
@@ -100,7 +102,7 @@ def main():
                 den += np.sum(r[m] ** 2)
             err = np.sqrt(num / max(den, 1e-300))
             print("rank %d/%d k=%d %s %-6s rel.err multi vs single = %.3e" % (rank, world, k, wt, name, err), flush=True)
-            ok &= bool(err < 1e-12)
+            ok &= bool(err < (1e-12 if number == "double" else 2e-5))
     if world > 1:
         t = torch.tensor([1.0 if ok else 0.0], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
