@@ -16,6 +16,8 @@
 //                     1-D matrices when they are a tensor product):
 //                       phase A  planes z = t:  Sx^T Wx, Sy^T Wy      phase B  planes y = t:  Sz^T Wz, 1/(lx+ly+lz), Sz, Sx
 //                       phase C  planes z = t:  Wy' Sy
+//                   Every 1-D contraction runs in even-odd form (EOMat / mat_vec below): M and K are centrosymmetric,
+//                   the eigenvectors of the symmetric 1-D problem are even or odd and ordered even-first by the host.
 //                   The last contraction is linear and uses the same matrix in every cell, so the plane z = k of the
 //                   cell below is added to the plane z = 0 BEFORE it; the contributions of the x / y neighbours
 //                   are merged with warp shuffles (lane - 1, lane - 4).  Every DoF of the brick closure is then
@@ -23,8 +25,8 @@
 //                   The tile of the NEXT brick is gathered by the compute threads themselves with cp.async (fire and
 //                   forget, coalesced: the own DoFs of a brick are one contiguous range) as soon as the current tile
 //                   has been read (after phase A), and awaited at the top of the next brick.
-//   mover warps     stage the epilogue operands (b, or x and x_old) of a brick in shared memory with cp.async one
-//                   brick ahead, and run the fused vector epilogue + coalesced stores / red.add of the PREVIOUS
+//   mover warps     stage the epilogue operands (b, or x and x_old) of a brick in shared memory one brick ahead (1-D bulk
+//                   copies of the TMA engine with mbarrier completion; cp.async for unaligned user vectors), and run the fused vector epilogue + coalesced stores / red.add of the PREVIOUS
 //                   result from the output tile while the compute warps work on the next brick; also the
 //                   pre-initialisation of the next kernel's destination on the brick's shared DoFs.
 //                   Hand-over through named barriers (bar.arrive / bar.sync producer-consumer pairs).
@@ -575,13 +577,6 @@ namespace dasm
           if (w)
             op[y * G::TP + (y == k ? G::SKEW : 0) + x] = r[y][x];
         }
-  }
-
-  template <typename T>
-  __device__ __forceinline__ T *
-  align16(T *p)
-  {
-    return reinterpret_cast<T *>((reinterpret_cast<uintptr_t>(p) + 15) & ~uintptr_t(15));
   }
 
   // ---- Laplace, uniform Cartesian geometry ---------------------------------------------------------------------
