@@ -1501,6 +1501,16 @@ dasm_mesh_host_numbering(const dasm_mesh *mesh, int degree, long long sizes[6], 
 }
 
 extern "C" int
+dasm_test_eo_pack(int n, int kind, const double *A, double *P, double *Q)
+{
+  DASM_API_BEGIN
+  DASM_REQUIRE(n >= 2 && n <= 9 && kind >= 0 && kind <= 2 && A && P && Q, "invalid arguments");
+  const bool ok = kind == 0 ? eo_pack_centrosymmetric(n, A, P, Q) : (kind == 1 ? eo_pack_forward(n, A, P, Q) : eo_pack_backward(n, A, P, Q));
+  DASM_REQUIRE(ok, "matrix does not have the even-odd structure");
+  DASM_API_END
+}
+
+extern "C" int
 dasm_mesh_destroy(dasm_mesh *mesh)
 {
   delete mesh;

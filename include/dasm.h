@@ -136,6 +136,12 @@ extern "C"
   int dasm_mesh_host_numbering(const dasm_mesh *mesh, int degree, long long sizes[6], unsigned int *cidx_plain, int *peers,
                                long long *send_count, long long *recv_count, unsigned int *send_idx, unsigned int *recv_idx);
 
+  /* Host-only test hook: even-odd blocks (m x m block P on the even parts, h x h block Q on the odd parts, m = ceil(n/2),
+   * h = floor(n/2)) of an n x n 1-D matrix as the warp-specialised kernels use them.  kind 0: centrosymmetric matrix
+   * (mass / stiffness), 1: forward eigenvector matrix (rows = eigen index, even eigenvectors first), 2: backward.
+   * Returns 0, or 1 (with dasm_last_error) when the matrix does not have the symmetry. */
+  int dasm_test_eo_pack(int n, int kind, const double *A, double *P, double *Q);
+
   /* ---- LaplaceOperatorMatrixFree (include/operator.h:266-1628) ------------------------------- */
   /* ctor operator.h:466-482 + setup_mapping_and_indices 490-753.  mapping_type in {"", "merged"}
    * ("linear geometry", "quadratic geometry", "construct q" are not built yet and return an error,
