@@ -71,6 +71,8 @@ namespace dasm
     }
     std::size_t  memory_consumption() const { return (std::size_t)dasm_fdm_memory_consumption(h); }
     unsigned int n_fdm_instances() const { return (unsigned int)dasm_fdm_n_instances(h); }
+    // diagnostics (no counterpart in the reference): bricks processed by the warp-specialised kernel
+    long long    n_fast_bricks() const { return dasm_fdm_n_fast_bricks(h); }
     dasm_fdm *   handle() const { return h; }
 
   private:
