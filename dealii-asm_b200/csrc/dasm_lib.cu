@@ -286,8 +286,8 @@ struct dasm_op
   uint32_t *        d_shared_list = nullptr; // owned DoFs on brick faces shared with other bricks
   long long         n_shared  = 0;
   bool              shared_ranges_ok = false; // every brick's own shared DoFs are one contiguous range
-  BrickMaps         maps = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0}; // tile maps (coalesced gather / store)
-  void *            d_map_bufs[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  BrickMaps         maps = {}; // tile maps (coalesced gather / store)
+  void *            d_map_bufs[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int               n_sm      = 148;
   int               max_smem  = 48 * 1024; // opt-in dynamic shared memory per block
   // warp-specialised kernels (kernels_fast.cuh) for the regular bricks; the other bricks go through the brick kernels
@@ -1650,14 +1650,14 @@ dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping
         std::vector<BrickDesc> bricks;
         // mesh bricks are 4x4x4 boxes of consecutive cells (x fastest); kernel bricks are z-slabs of them
         const int *B = M.p.brick;
-        size_t     first = 0;
+        size_t     first = 0, mesh_brick = 0;
         int        ibz_base = 0, nbz_total = 0;
         for (int bz = 0; bz < M.nl[2]; bz += B[2])
           {
             const int dz      = std::min(B[2], M.nl[2] - bz);
             const int n_slabs = (dz + op->brick_bz - 1) / op->brick_bz;
             for (int by = 0; by < M.nl[1]; by += B[1])
-              for (int bx = 0; bx < M.nl[0]; bx += B[0])
+              for (int bx = 0; bx < M.nl[0]; bx += B[0], ++mesh_brick)
                 {
                   const int dx = std::min(B[0], M.nl[0] - bx), dy = std::min(B[1], M.nl[1] - by);
                   for (int z0 = 0, sl = 0; z0 < dz; z0 += op->brick_bz, ++sl)
@@ -1684,6 +1684,8 @@ dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping
                           if (M.neighbor(hi_c, d, 1, nbc))
                             bd.shared |= (1u << (2 * d + 1));
                         }
+                      if (op->brick_bz == 4 && op->nb.brick_lex[mesh_brick])
+                        bd.shared |= BRICK_LEX; // lexicographic box numbering (mesh.h)
                       bricks.push_back(bd);
                       {
                         // on the boundary of this rank's box in a partitioned direction?
@@ -1730,12 +1732,20 @@ dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping
                         }
                       if (!owned || !shared)
                         continue;
-                      const uint32_t g0 = op->nb.cidx[(size_t)(bd.first_cell + c) * 27 + e];
-                      if (g0 == INVALID_INDEX)
+                      const uint32_t *ci = op->nb.cidx.data() + (size_t)(bd.first_cell + c) * 27;
+                      if (ci[e] == INVALID_INDEX)
                         continue;
-                      const int size = Mesh::entity_size(e, degree);
-                      for (int i = 0; i < size; ++i)
-                        list.push_back(g0 + i);
+                      // all DoFs of the entity (local coordinates 0, 1..k-1 or k per direction)
+                      int lo3[3], hi3[3];
+                      for (int d = 0; d < 3; ++d)
+                        {
+                          lo3[d] = ee[d] == 0 ? 0 : (ee[d] == 2 ? degree : 1);
+                          hi3[d] = ee[d] == 1 ? degree - 1 : lo3[d];
+                        }
+                      for (int z = lo3[2]; z <= hi3[2]; ++z)
+                        for (int y = lo3[1]; y <= hi3[1]; ++y)
+                          for (int x = lo3[0]; x <= hi3[0]; ++x)
+                            list.push_back(expand_start_index(ci, degree, x, y, z));
                     }
                 }
               // contiguous range of the brick's own shared DoFs (holds when the kernel brick is a mesh brick)
@@ -1749,7 +1759,7 @@ dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping
                       mx = std::max(mx, list[i]);
                     }
                   bd.sh_base = mn;
-                  if (mx - mn + 1 != bd.sh_count)
+                  if (mx - mn + 1 != bd.sh_count && !(bd.shared & BRICK_LEX))
                     op->shared_ranges_ok = false;
                 }
             }
@@ -1774,11 +1784,12 @@ dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping
               std::vector<uint32_t> store_off;  // [17]
               std::vector<uint32_t> ftab;       // sorted by mask
               std::vector<uint32_t> for_off;    // [9]
+              std::vector<uint16_t> sh_tab;     // offsets (in the own range) of the brick's own DoFs on shared lower faces
               uint32_t              flags = 0;
               bool operator==(const Variant &o) const
               {
                 return load == o.load && store == o.store && store_off == o.store_off && ftab == o.ftab && for_off == o.for_off &&
-                       flags == o.flags;
+                       sh_tab == o.sh_tab && flags == o.flags;
               }
             };
             std::map<uint32_t, uint16_t> variant_of; // signature -> variant
@@ -1787,13 +1798,8 @@ dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping
             bool                         ok = true;
             auto plain_gidx = [&](const BrickDesc &bd, const std::vector<uint32_t> &tab, int px, int py, int pz) {
               const int cx = std::min(px / k, bd.b[0] - 1), cy = std::min(py / k, bd.b[1] - 1), cz = std::min(pz / k, bd.b[2] - 1);
-              const int lx = px - cx * k, ly = py - cy * k, lz = pz - cz * k;
-              const int ex = lx == 0 ? 0 : (lx == k ? 2 : 1), ey = ly == 0 ? 0 : (ly == k ? 2 : 1), ez = lz == 0 ? 0 : (lz == k ? 2 : 1);
-              const uint32_t st = tab[(size_t)(bd.first_cell + (cz * bd.b[1] + cy) * bd.b[0] + cx) * 27 + ex + 3 * ey + 9 * ez];
-              if (st == INVALID_INDEX)
-                return INVALID_INDEX;
-              const int sx = ex == 1 ? k - 1 : 1, sy = ey == 1 ? k - 1 : 1;
-              return st + (ex == 1 ? lx - 1 : 0) + sx * ((ey == 1 ? ly - 1 : 0) + sy * (ez == 1 ? lz - 1 : 0));
+              return expand_start_index(tab.data() + (size_t)(bd.first_cell + (cz * bd.b[1] + cy) * bd.b[0] + cx) * 27, k, px - cx * k,
+                                        py - cy * k, pz - cz * k);
             };
             unsigned verify_counter = 0;
             for (size_t bidx = 0; bidx < bricks.size() && ok; ++bidx)
@@ -1833,7 +1839,8 @@ dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping
                             ++scnt;
                           }
                       }
-                if (cnt == 0 || mx - mn + 1 != cnt || (scnt > 0 && (smx - smn + 1 != scnt || smx != mx)) || cnt >= 0x1FFFu)
+                const bool lexb = (bd.shared & BRICK_LEX) != 0;
+                if (cnt == 0 || mx - mn + 1 != cnt || (!lexb && scnt > 0 && (smx - smn + 1 != scnt || smx != mx)) || cnt >= 0x1FFFu)
                   {
                     ok = false;
                     break;
@@ -1887,7 +1894,7 @@ dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping
                               {
                                 const uint32_t i = gv - mn;
                                 var.load[i]      = (uint16_t)plin;
-                                st_entries.push_back({(shlo ? 8u : 0u) + mask, i, i | (o << 13) | (mask << 26)});
+                                st_entries.push_back({(shlo ? 8u : 0u) + mask, i, i | (o << 13) | (mask << 26) | (shlo ? STORE_SHARED : 0u)});
                               }
                             else
                               var.flags |= 1u;
@@ -1919,6 +1926,11 @@ dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping
                     var.store.assign(cnt, 0xFFFFFFFFu);
                     for (const E &x : st_entries)
                       var.store[x.key] = x.entry;
+                    for (uint32_t i = 0; i < cnt; ++i)
+                      if (var.store[i] != 0xFFFFFFFFu && (var.store[i] & STORE_SHARED))
+                        var.sh_tab.push_back((uint16_t)i);
+                    if (lexb)
+                      var.flags |= 2u; // the private / shared DoFs are interleaved in the own range
                     var.for_off.assign(9, 0);
                     for (size_t j = 0; j < perm.size(); ++j)
                       {
@@ -1955,6 +1967,22 @@ dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping
                     std::copy(variants[v].for_off.begin(), variants[v].for_off.end(), h_foff.begin() + (size_t)v * 9);
                     h_fl[v] = variants[v].flags;
                   }
+                // own shared DoFs per variant (pre-initialisation of the next kernel's destination on lex bricks)
+                const int             NSH = NPTS - (4 * k - 1) * (4 * k - 1) * (4 * k - 1);
+                std::vector<uint16_t> h_sh((size_t)nv * NSH, 0);
+                std::vector<uint32_t> h_shc(nv, 0);
+                for (int v = 0; v < nv; ++v)
+                  {
+                    h_shc[v] = (uint32_t)variants[v].sh_tab.size();
+                    if ((int)h_shc[v] > NSH)
+                      throw std::runtime_error("internal: shared table overflow");
+                    std::copy(variants[v].sh_tab.begin(), variants[v].sh_tab.end(), h_sh.begin() + (size_t)v * NSH);
+                  }
+                op->d_map_bufs[7] = dev_upload(h_sh, ctx->stream);
+                op->d_map_bufs[8] = dev_upload(h_shc, ctx->stream);
+                op->maps.sh_tab   = (const uint16_t *)op->d_map_bufs[7];
+                op->maps.sh_cnt   = (const uint32_t *)op->d_map_bufs[8];
+                op->maps.sh_stride = NSH;
                 op->d_map_bufs[0]      = dev_upload(h_load, ctx->stream);
                 op->d_map_bufs[1]      = dev_upload(h_store, ctx->stream);
                 op->d_map_bufs[2]      = dev_upload(h_soff, ctx->stream);
@@ -2324,7 +2352,7 @@ gather_entity_weights_kernel(T *cw, const T *w, const uint32_t *cidx, const long
 {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n)
-    cw[i] = (cidx[i] == DEV_INVALID) ? T(0) : w[cidx[i]];
+    cw[i] = (cidx[i] == DEV_INVALID) ? T(0) : w[cidx[i] & ~DEV_LEX_FLAG];
 }
 
 template <typename T>
@@ -2517,17 +2545,7 @@ dasm_fdm_create(dasm_op *op, int n_overlap, int sub_mesh_approximation, int weig
           for (int z = 0; z < n; ++z)
             for (int y = 0; y < n; ++y)
               for (int x = 0; x < n; ++x)
-                {
-                  const int ex = x == 0 ? 0 : (x == k ? 2 : 1), ey = y == 0 ? 0 : (y == k ? 2 : 1), ez = z == 0 ? 0 : (z == k ? 2 : 1);
-                  const uint32_t st = ci[ex + 3 * ey + 9 * ez];
-                  uint32_t       v  = INVALID_INDEX;
-                  if (st != INVALID_INDEX)
-                    {
-                      const int sx = ex == 1 ? k - 1 : 1, sy = ey == 1 ? k - 1 : 1;
-                      v = st + (ex == 1 ? x - 1 : 0) + sx * ((ey == 1 ? y - 1 : 0) + sy * (ez == 1 ? z - 1 : 0));
-                    }
-                  full[(size_t)c * n3 + (z * n + y) * n + x] = v;
-                }
+                full[(size_t)c * n3 + (z * n + y) * n + x] = expand_start_index(ci, k, x, y, z);
         }
       auto translate = [&](int i, int &which, int &l) {
         if (i < n_overlap - 1)

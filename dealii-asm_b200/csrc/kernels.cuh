@@ -65,7 +65,9 @@ namespace dasm
   }
 
   // global index of local DoF (x,y,z) of a cell from its 27 compressed indices
-  // (standard orientation branch of vector_access_reduced.h:267-405)
+  // (standard orientation branch of vector_access_reduced.h:267-405); an entity stored in a lex brick (LEX_FLAG,
+  // mesh.h) is expanded with the strides 1, 4k, 16k^2 of the brick's box
+  constexpr uint32_t DEV_LEX_FLAG = 0x80000000u;
   template <int k>
   __device__ __forceinline__ uint32_t
   compressed_index(const uint32_t *__restrict__ ci, int x, int y, int z)
@@ -77,9 +79,10 @@ namespace dasm
     const uint32_t start = ci[ex + 3 * ey + 9 * ez];
     if (start == DEV_INVALID)
       return DEV_INVALID;
-    const int sx = (ex == 1) ? (k - 1) : 1;
-    const int sy = (ey == 1) ? (k - 1) : 1;
-    return start + ox + sx * (oy + sy * oz);
+    const bool lex = (start & DEV_LEX_FLAG) != 0;
+    const int  sx  = lex ? 4 * k : ((ex == 1) ? (k - 1) : 1);
+    const int  sy  = lex ? 4 * k : ((ey == 1) ? (k - 1) : 1);
+    return (start & ~DEV_LEX_FLAG) + ox + sx * (oy + sy * oz);
   }
 
   template <typename T>

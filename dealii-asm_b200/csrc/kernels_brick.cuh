@@ -26,7 +26,7 @@ namespace dasm
   {
     uint32_t first_cell; // processing index of the first cell (cells of a brick are consecutive, x fastest)
     uint8_t  b[3];       // cells per direction
-    uint8_t  shared;     // bit (2 d + side): the tile face is shared with cells outside the brick
+    uint8_t  shared;     // bit (2 d + side): the tile face is shared with cells outside the brick; bit 6: BRICK_LEX
     uint32_t sh_base;    // first DoF of the contiguous range of shared-face DoFs this brick owns
     uint32_t sh_count;   // (only meaningful when the kernel brick is a whole mesh brick)
     uint32_t base;       // first DoF owned by the brick: [base, base + npriv) private, then the shared range
@@ -54,7 +54,13 @@ namespace dasm
     const uint32_t *foreign_gidx; // [brick][nfp]
     int             stride;
     int             nfp;
+    const uint16_t *sh_tab;       // [variant][sh_stride] offsets of the own DoFs on shared lower faces
+    const uint32_t *sh_cnt;       // [variant]
+    int             sh_stride;
   };
+
+  constexpr uint8_t  BRICK_LEX    = 0x40u;       // BrickDesc::shared: the brick's own DoFs are the lexicographic box [0, 4k)^3 (mesh.h)
+  constexpr uint32_t STORE_SHARED = 0x20000000u; // store_tab entry: own DoF on a shared lower face (red.add instead of a store)
 
   // compressed weights as codes: code = patch valence of the entity (0: weight 0), value from this table
   template <typename T>
@@ -361,7 +367,8 @@ namespace dasm
             if (pz < ez)
               {
                 const uint32_t st = s_cidx[(cz * czs + cxy) * 27 + exy + 9 * ecz];
-                const uint32_t g  = (st == DEV_INVALID) ? DEV_INVALID : st + oxy + sxy * oz;
+                const uint32_t g  = (st == DEV_INVALID) ? DEV_INVALID :
+                                    ((st & DEV_LEX_FLAG) ? (st & ~DEV_LEX_FLAG) + ox + 4 * k * (oy + 4 * k * oz) : st + oxy + sxy * oz);
                 const int      p  = pz * NPENC + base;
                 gidx[p]           = g;
                 if (g == DEV_INVALID)
@@ -424,7 +431,9 @@ namespace dasm
     const uint32_t *store_tab;
     const uint32_t *for_tab;
     const uint32_t *off; // [0..16] store classes, [17..25] foreign classes
-    unsigned        flags;
+    unsigned        flags;  // bit 0: zero the tile first; bit 1: private / shared own DoFs are interleaved (lex brick)
+    const uint16_t *sh_tab; // global memory: offsets of the own shared DoFs
+    unsigned        sh_cnt;
   };
 
   template <int k, int BZ, typename T>
@@ -466,8 +475,10 @@ namespace dasm
     const bool need1 = (epi.kind == EPI_CHEB && epi.f1 != T(0) && epi.v1 != nullptr);
     if (!need0)
       return;
+    // (lex bricks: the private DoFs are interleaved with the shared ones, the whole own range is staged)
+    const int n_stage = (bd.shared & BRICK_LEX) ? (int)(bd.npriv + bd.sh_count) : (int)bd.npriv;
 #pragma unroll 4
-    for (int i = threadIdx.x; i < bd.npriv; i += G::NT)
+    for (int i = threadIdx.x; i < n_stage; i += G::NT)
       {
         cp_async_value(ops0 + i, epi.v0 + bd.base + i);
         if (need1)
@@ -507,22 +518,19 @@ namespace dasm
     T *           sh_dst = (shared_mode == SHARED_DIRECT) ? dst : acc;
     const T       sh_a   = (shared_mode == SHARED_DIRECT) ? alpha : T(1);
     const int     n_own = bd.npriv + bd.sh_count, n_for = tb.off[25];
-    // private DoFs: fused epilogue, coalesced plain stores
+    // own DoFs in the order of the own range (coalesced): private ones get the fused epilogue and a plain store, the
+    // ones on shared lower faces (STORE_SHARED; the tail of the range, or interleaved in a lex brick) a red.add
 #pragma unroll 4
-    for (int i = threadIdx.x; i < bd.npriv; i += G::NT)
+    for (int i = threadIdx.x; i < n_own; i += G::NT)
       {
         const uint32_t e = tb.store_tab[i];
         if (e == 0xFFFFFFFFu)
           continue;
-        const T y        = slot_sum(slots, (e >> 13) & 0x1FFFu, e >> 26, dx, dy, dz);
-        dst[bd.base + i] = epilogue_compute(epi, y, need0 ? ops0[i] : T(0), need1 ? ops1[i] : T(0));
-      }
-    // own DoFs on shared faces: coalesced red.add
-    for (int i = bd.npriv + threadIdx.x; i < n_own; i += G::NT)
-      {
-        const uint32_t e = tb.store_tab[i];
-        if (e != 0xFFFFFFFFu)
-          atomic_add(sh_dst + bd.base + i, sh_a * slot_sum(slots, (e >> 13) & 0x1FFFu, e >> 26, dx, dy, dz));
+        const T y = slot_sum(slots, (e >> 13) & 0x1FFFu, (e >> 26) & 7u, dx, dy, dz);
+        if (e & STORE_SHARED)
+          atomic_add(sh_dst + bd.base + i, sh_a * y);
+        else
+          dst[bd.base + i] = epilogue_compute(epi, y, need0 ? ops0[i] : T(0), need1 ? ops1[i] : T(0));
       }
     // tile points owned by other bricks
     for (int j = threadIdx.x; j < n_for; j += G::NT)
@@ -531,7 +539,7 @@ namespace dasm
         if (g != DEV_INVALID)
           {
             const uint32_t e = tb.for_tab[j];
-            atomic_add(sh_dst + g, sh_a * slot_sum(slots, (e >> 13) & 0x1FFFu, e >> 26, dx, dy, dz));
+            atomic_add(sh_dst + g, sh_a * slot_sum(slots, (e >> 13) & 0x1FFFu, (e >> 26) & 7u, dx, dy, dz));
           }
       }
   }
@@ -573,6 +581,8 @@ namespace dasm
     tb.for_tab   = s_for;
     tb.off       = s_off;
     tb.flags     = maps.flags[variant];
+    tb.sh_tab    = maps.sh_tab + (size_t)variant * maps.sh_stride;
+    tb.sh_cnt    = maps.sh_cnt[variant];
     __syncthreads();
   }
 
@@ -586,9 +596,11 @@ namespace dasm
                                BrickGeom<k, BZ>::NT - 1) / BrickGeom<k, BZ>::NT; // upper bound of shared DoFs per thread
   };
 
+  // lex == nullptr: the own shared DoFs are the contiguous range [sh_base, sh_base + sh_count); else base + lex[i]
   template <int k, int BZ, typename T>
   __device__ __forceinline__ void
-  brick_next_init_load(const BrickDesc &bd, const NextInit<T> &ni, T (&a)[NextInitRegs<k, BZ>::IT], T (&b)[NextInitRegs<k, BZ>::IT])
+  brick_next_init_load(const BrickDesc &bd, const NextInit<T> &ni, T (&a)[NextInitRegs<k, BZ>::IT], T (&b)[NextInitRegs<k, BZ>::IT],
+                       const uint16_t *__restrict__ lex = nullptr)
   {
     using G = BrickGeom<k, BZ>;
 #pragma unroll
@@ -599,10 +611,11 @@ namespace dasm
         b[it]            = T(0);
         if (ni.out != nullptr && i < bd.sh_count)
           {
+            const uint32_t g = lex ? bd.base + lex[i] : bd.sh_base + i;
             if (ni.v0 != nullptr)
-              a[it] = ni.v0[bd.sh_base + i];
+              a[it] = ni.v0[g];
             if (ni.v1 != nullptr && ni.f1 != T(0))
-              b[it] = ni.v1[bd.sh_base + i];
+              b[it] = ni.v1[g];
           }
       }
   }
@@ -610,7 +623,7 @@ namespace dasm
   template <int k, int BZ, typename T>
   __device__ __forceinline__ void
   brick_next_init_store(const BrickDesc &bd, const NextInit<T> &ni, const T (&a)[NextInitRegs<k, BZ>::IT],
-                        const T (&b)[NextInitRegs<k, BZ>::IT])
+                        const T (&b)[NextInitRegs<k, BZ>::IT], const uint16_t *__restrict__ lex = nullptr)
   {
     using G = BrickGeom<k, BZ>;
     if (ni.out == nullptr)
@@ -620,7 +633,7 @@ namespace dasm
       {
         const uint32_t i = threadIdx.x + it * G::NT;
         if (i < bd.sh_count)
-          ni.out[bd.sh_base + i] = a[it] + ni.f1 * (a[it] - b[it]);
+          ni.out[lex ? bd.base + lex[i] : bd.sh_base + i] = a[it] + ni.f1 * (a[it] - b[it]);
       }
   }
 
@@ -792,7 +805,8 @@ namespace dasm
         const uint32_t *cur_cidx = s_cidx + buf * (G::NCELLS * 27);
         uint32_t *      cur_gidx = LIN ? gidx + fb * G::NFP : gidx;
         T               ni_a[NextInitRegs<k, BZ>::IT], ni_b[NextInitRegs<k, BZ>::IT];
-        brick_next_init_load<k, BZ, T>(bd, ni, ni_a, ni_b);
+        const uint16_t *ni_lex = (LIN && (bd.shared & BRICK_LEX)) ? tb.sh_tab : nullptr;
+        brick_next_init_load<k, BZ, T>(bd, ni, ni_a, ni_b, ni_lex);
         if (LIN)
           {
             brick_issue_ops_lin<k, BZ, T>(bd, ops0, ops1, epi);
@@ -813,7 +827,7 @@ namespace dasm
             cp_async_commit();
             cp_async_wait<2>();
           }
-        brick_next_init_store<k, BZ, T>(bd, ni, ni_a, ni_b);
+        brick_next_init_store<k, BZ, T>(bd, ni, ni_a, ni_b, ni_lex);
         __syncthreads();
 
         const bool act = (c < ncells);
@@ -1234,7 +1248,8 @@ namespace dasm
         const uint32_t *cur_cidx = s_cidx + buf * (G::NCELLS * 27);
         uint32_t *      cur_gidx = LIN ? gidx + fb * G::NFP : gidx;
         T               ni_a[NextInitRegs<k, BZ>::IT], ni_b[NextInitRegs<k, BZ>::IT];
-        brick_next_init_load<k, BZ, T>(bd, ni, ni_a, ni_b);
+        const uint16_t *ni_lex = (LIN && (bd.shared & BRICK_LEX)) ? tb.sh_tab : nullptr;
+        brick_next_init_load<k, BZ, T>(bd, ni, ni_a, ni_b, ni_lex);
         if (LIN)
           {
             brick_issue_ops_lin<k, BZ, T>(bd, ops0, ops1, epi);
@@ -1256,7 +1271,7 @@ namespace dasm
             cp_async_commit();
             cp_async_wait<2>();
           }
-        brick_next_init_store<k, BZ, T>(bd, ni, ni_a, ni_b);
+        brick_next_init_store<k, BZ, T>(bd, ni, ni_a, ni_b, ni_lex);
         __syncthreads();
 
         const bool     act  = (c < ncells) && !(dbg & 2);

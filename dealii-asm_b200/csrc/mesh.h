@@ -17,12 +17,22 @@
 // brick are numbered first (cell by cell, lexicographic entity order), then the entities on lower brick
 // faces shared with neighbouring bricks.  All DoFs of an entity are contiguous, so a cell needs only 27
 // start indices, and the DoFs a brick shares with its neighbours are one contiguous range.
+//
+// "Lex" bricks: a full 4 x 4 x 4 brick whose six faces all have neighbour cells (interior or periodic; hence no
+// constrained DoFs) owns the half-open box [0, 4k)^3 of its tile.  Its DoFs are numbered LEXICOGRAPHICALLY in
+// that box (x fastest: base + X + 4k Y + 16k^2 Z) and all lex bricks come first in the owned range, so the
+// box of brick i is the i-th block of 64 k^3 entries of every vector: a 4-D tensor (x, y, z, brick) that the TMA
+// engine moves with box copies (kernels_tma.cuh).  The 27 start indices of a cell stay; an entity that lives in a
+// lex brick has bit 31 (LEX_FLAG) set in its start index, which then is the index of its first DoF, and its DoFs
+// are expanded with the strides (1, 4k, 16k^2) instead of the entity-contiguous ones.
 #pragma once
 #include <array>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <map>
+#include <stdexcept>
 #include <vector>
 
 #include "basis.h"
@@ -30,6 +40,22 @@
 namespace dasm
 {
   constexpr uint32_t INVALID_INDEX = 0xFFFFFFFFu;
+  constexpr uint32_t LEX_FLAG      = 0x80000000u; // start index of an entity stored in a lex brick (INVALID_INDEX is tested first)
+
+  // index of local DoF (x, y, z) of a cell from its 27 start indices (host twin of compressed_index<k>, kernels.cuh)
+  inline uint32_t
+  expand_start_index(const uint32_t *ci, const int k, const int x, const int y, const int z)
+  {
+    const int      ex = x == 0 ? 0 : (x == k ? 2 : 1), ey = y == 0 ? 0 : (y == k ? 2 : 1), ez = z == 0 ? 0 : (z == k ? 2 : 1);
+    const uint32_t st = ci[ex + 3 * ey + 9 * ez];
+    if (st == INVALID_INDEX)
+      return INVALID_INDEX;
+    const int ox = ex == 1 ? x - 1 : 0, oy = ey == 1 ? y - 1 : 0, oz = ez == 1 ? z - 1 : 0;
+    if (st & LEX_FLAG)
+      return (st & ~LEX_FLAG) + ox + 4 * k * (oy + 4 * k * oz);
+    const int sx = ex == 1 ? k - 1 : 1, sy = ey == 1 ? k - 1 : 1;
+    return st + ox + sx * (oy + sy * oz);
+  }
 
   enum MapKind
   {
@@ -406,7 +432,28 @@ namespace dasm
       std::vector<uint32_t> cidx_plain;   // same, constrained entities keep their index
       std::vector<uint32_t> constrained;  // list of constrained owned DoFs
       std::vector<ExchangeList> exchange; // per neighbouring rank
+      std::vector<char>     brick_lex;    // per mesh brick: lexicographic box numbering
+      std::vector<uint32_t> brick_base;   // per mesh brick: first owned DoF
+      uint32_t              n_lex = 0;    // number of lex bricks: their boxes are [i 64k^3, (i+1) 64k^3), i < n_lex
     };
+
+    // a brick whose own DoFs form the full box [0, 4k)^3: 4 x 4 x 4 cells, neighbour cells across all six faces
+    bool
+    brick_is_lex(const size_t b) const
+    {
+      static const bool off = getenv("DASM_NO_LEX") && getenv("DASM_NO_LEX")[0] == '1';
+      if (off || p.brick[0] != 4 || p.brick[1] != 4 || p.brick[2] != 4 || brick_ptr[b + 1] - brick_ptr[b] != 64)
+        return false;
+      const auto &c0 = cell_ijk[brick_ptr[b]], &c1 = cell_ijk[brick_ptr[b + 1] - 1];
+      const int   lo_c[3] = {c0[0], c0[1], c0[2]}, hi_c[3] = {c1[0], c1[1], c1[2]};
+      for (int d = 0; d < 3; ++d)
+        {
+          int nbc[3];
+          if (hi_c[d] - lo_c[d] != 3 || !neighbor(lo_c, d, 0, nbc) || !neighbor(hi_c, d, 1, nbc))
+            return false;
+        }
+      return true;
+    }
 
     static int
     entity_size(int e, int k)
@@ -466,9 +513,38 @@ namespace dasm
       // with its neighbours form one contiguous range
       std::vector<uint32_t> own_start(n_cells * 27, INVALID_INDEX);
       {
+        const size_t n_bricks = brick_ptr.size() - 1;
+        nb.brick_lex.assign(n_bricks, 0);
+        nb.brick_base.assign(n_bricks, 0);
         uint32_t next = 0;
+        // lex bricks first: box [0, 4k)^3 in lexicographic order, start index = first DoF of the entity | LEX_FLAG
+        for (size_t b = 0; b < n_bricks; ++b)
+          {
+            if (!brick_is_lex(b))
+              continue;
+            nb.brick_lex[b]  = 1;
+            nb.brick_base[b] = next;
+            ++nb.n_lex;
+            const size_t first = brick_ptr[b];
+            for (size_t i = first; i < brick_ptr[b + 1]; ++i)
+              {
+                const int cc[3] = {cell_ijk[i][0] - cell_ijk[first][0], cell_ijk[i][1] - cell_ijk[first][1], cell_ijk[i][2] - cell_ijk[first][2]};
+                for (int e = 0; e < 27; ++e)
+                  {
+                    const int ee[3] = {e % 3, (e / 3) % 3, e / 9};
+                    if (ee[0] == 2 || ee[1] == 2 || ee[2] == 2)
+                      continue; // upper entities belong to the neighbour cell
+                    const uint32_t X = cc[0] * k + (ee[0] ? 1 : 0), Y = cc[1] * k + (ee[1] ? 1 : 0), Z = cc[2] * k + (ee[2] ? 1 : 0);
+                    own_start[i * 27 + e] = (next + X + 4 * k * (Y + 4 * k * Z)) | LEX_FLAG;
+                  }
+              }
+            next += 64u * k * k * k;
+          }
         for (size_t b = 0; b + 1 < brick_ptr.size(); ++b)
           {
+            if (nb.brick_lex[b])
+              continue;
+            nb.brick_base[b] = next;
             const size_t first = brick_ptr[b], last = brick_ptr[b + 1];
             const int    org[3] = {cell_ijk[first][0], cell_ijk[first][1], cell_ijk[first][2]};
             for (int pass = 0; pass < 2; ++pass)
@@ -495,6 +571,8 @@ namespace dasm
                 }
           }
         nb.n_owned = next;
+        if (next >= LEX_FLAG)
+          throw std::runtime_error("too many DoFs per rank for 31-bit start indices");
       }
 
       const int my_rank = p.rank;
@@ -581,7 +659,7 @@ namespace dasm
       // slot; enumerate, for every local cell and owned entity, the cells touching the slot.
       if (n_ranks() > 1)
         {
-          std::map<int, std::map<std::array<long, 3>, std::pair<uint32_t, uint32_t>>> send; // peer -> key -> (start,len)
+          std::map<int, std::map<std::array<long, 3>, uint32_t>> send; // peer -> key -> start index (with LEX_FLAG)
           for (size_t i = 0; i < n_cells; ++i)
             {
               const int c[3] = {cell_ijk[i][0], cell_ijk[i][1], cell_ijk[i][2]};
@@ -631,7 +709,7 @@ namespace dasm
                           const int tc[3] = {cand[0][a], cand[1][b2], cand[2][g]};
                           const int q     = rank_of_cell(tc);
                           if (q != my_rank)
-                            send[q][{(long)my_rank, gid, (long)e}] = {own_start[i * 27 + e], (uint32_t)entity_size(e, k)};
+                            send[q][{(long)my_rank, gid, (long)e}] = own_start[i * 27 + e];
                         }
                 }
             }
@@ -649,9 +727,25 @@ namespace dasm
                 }
               for (auto &kv : pr.second)
                 {
-                  ex->send_start.push_back(kv.second.first);
-                  ex->send_len.push_back(kv.second.second);
-                  ex->n_send += kv.second.second;
+                  // runs in the lexicographic order of the DoFs inside the entity (the receiver's ghost copy is contiguous)
+                  const int      e  = (int)kv.first[2];
+                  const uint32_t st = kv.second;
+                  const int      ex1 = (e % 3 == 1) ? k - 1 : 1, ey1 = ((e / 3) % 3 == 1) ? k - 1 : 1, ez1 = (e / 9 == 1) ? k - 1 : 1;
+                  if (st & LEX_FLAG)
+                    {
+                      for (int l = 0; l < ez1; ++l)
+                        for (int j = 0; j < ey1; ++j)
+                          {
+                            ex->send_start.push_back((st & ~LEX_FLAG) + 4 * k * (j + 4 * k * l));
+                            ex->send_len.push_back((uint32_t)ex1);
+                          }
+                    }
+                  else
+                    {
+                      ex->send_start.push_back(st);
+                      ex->send_len.push_back((uint32_t)(ex1 * ey1 * ez1));
+                    }
+                  ex->n_send += (size_t)ex1 * ey1 * ez1;
                 }
             }
         }

@@ -334,17 +334,45 @@ def brick_major_order(n_cells, brick=(4, 4, 4)):
     return np.array(order, dtype=np.int64)
 
 
-def number_dofs_owner_cell(mesh, k, brick=(4, 4, 4)):
+LEX_FLAG = 0x80000000  # start index of an entity stored in a "lex" brick (first DoF of the entity, box strides)
+
+
+def lex_bricks(mesh, brick=(4, 4, 4)):
+    """keys (reversed brick coordinates) of the bricks numbered lexicographically: full 4^dim bricks with a
+    neighbour cell across every face (interior or periodic), hence without constrained DoFs."""
+    dim = mesh.dim
+    nc = mesh.n_cells
+    out = set()
+    if any(b != 4 for b in brick[:dim]):
+        return out
+    for key in np.ndindex(*[(nc[d] + 3) // 4 for d in reversed(range(dim))]):
+        org = [key[dim - 1 - d] * 4 for d in range(dim)]
+        ok = True
+        for d in range(dim):
+            if org[d] + 4 > nc[d]:
+                ok = False
+            elif not mesh.periodic[d] and (org[d] == 0 or org[d] + 4 == nc[d]):
+                ok = False
+        if ok:
+            out.add(tuple(key))
+    return out
+
+
+def number_dofs_owner_cell(mesh, k, brick=(4, 4, 4), lex=True):
     """Native "brick-grouped owner-cell" numbering of the B200 library, restated independently.
 
     Every mesh entity (3^dim per cell: vertex / line / quad / hex interior in the lexicographic
     3x3(x3) layout of vector_access_reduced.h:30-164) is owned by the cell for which it is a lower
     entity (code 0 or 1 per direction); code 2 is owned only by the last cell of a non-periodic
     direction.  Cells are grouped in bricks of `brick` cells (brick-major order = mesh.cell_order).
-    Per brick, first the owned entities that do not lie on a lower brick face with a neighbour cell
-    across it ("private") are numbered, cell by cell in lexicographic entity order, then the shared
-    ones in the same order; DoFs are lexicographic inside an entity.  Entities on a Dirichlet boundary
-    are numbered too (they exist in the vector, like constrained DoFs in deal.II) and flagged
+
+    "Lex" bricks (lex_bricks above) come first: brick i owns the box [0, 4k)^dim of its tile, numbered
+    lexicographically (x fastest) from i (4k)^dim; the start index of an entity of such a brick is the index of
+    its first DoF with LEX_FLAG set, and the DoFs of the entity are expanded with the box strides 1, 4k, (4k)^2.
+    Then the other bricks: per brick, first the owned entities that do not lie on a lower brick face with a
+    neighbour cell across it ("private"), cell by cell in lexicographic entity order, then the shared
+    ones in the same order; DoFs are lexicographic and contiguous inside an entity.  Entities on a Dirichlet
+    boundary are numbered too (they exist in the vector, like constrained DoFs in deal.II) and flagged
     constrained.
 
     returns cell_dofs [C, n^dim] (uint32, by lexicographic cell id), n_dofs, constrained [n_dofs]
@@ -372,7 +400,25 @@ def number_dofs_owner_cell(mesh, k, brick=(4, 4, 4)):
         ijk = mesh.cell_ijk(int(c))
         key = tuple(ijk[d] // brick[d] for d in reversed(range(dim)))
         bricks.setdefault(key, []).append(int(c))
+    lexset = lex_bricks(mesh, brick) if lex else set()
+    box = (4 * k) ** dim
     for key in sorted(bricks.keys()):
+        if key not in lexset:
+            continue
+        org = [key[dim - 1 - d] * 4 for d in range(dim)]
+        # slots 2 org .. 2 org + 7 per direction: even slot 2c -> box coordinate c k, odd slot 2c+1 -> c k + 1
+        for loc in np.ndindex(*([8] * dim)):  # loc[0] is the slowest direction
+            first = 0
+            slot = []
+            for d in reversed(range(dim)):
+                sl = loc[dim - 1 - d]
+                first = first * (4 * k) + (sl // 2) * k + (sl % 2)
+                slot.append((2 * org[d] + sl))
+            ent_start[tuple(slot)] = (next_dof + first) | LEX_FLAG
+        next_dof += box
+    for key in sorted(bricks.keys()):
+        if key in lexset:
+            continue
         cells = bricks[key]
         org = [key[dim - 1 - d] * brick[d] for d in range(dim)]
         for pass_ in (0, 1):
@@ -410,7 +456,8 @@ def number_dofs_owner_cell(mesh, k, brick=(4, 4, 4)):
 
 def expand_compressed(compressed, k, dim):
     """27 (9) entity start indices -> n^dim lexicographic indices per cell; the standard-orientation
-    case of vector_access_reduced.h:267-405 (vertex idx, line idx+i, quad idx+j*(k-1)+i, ...)."""
+    case of vector_access_reduced.h:267-405 (vertex idx, line idx+i, quad idx+j*(k-1)+i, ...); entities of lex
+    bricks (LEX_FLAG) use the strides 1, 4k, (4k)^2 of the brick's box instead."""
     n = k + 1
     C = compressed.shape[0]
     out = np.zeros((C,) + (n,) * dim, dtype=np.uint32)
@@ -433,8 +480,16 @@ def expand_compressed(compressed, k, dim):
         if cnt == 0:
             continue
         off = np.arange(cnt, dtype=np.int64).reshape(shape[::-1])
-        val = compressed[:, e].astype(np.int64).reshape((C,) + (1,) * dim) + off[None]
-        val = np.where(compressed[:, e].reshape((C,) + (1,) * dim) == INVALID, np.int64(INVALID), val)
+        # offsets with the box strides: sum_d i_d (4k)^d
+        grids = np.meshgrid(*[np.arange(shape[d], dtype=np.int64) for d in reversed(range(dim))], indexing="ij")
+        off_lex = np.zeros(shape[::-1], dtype=np.int64)
+        for j, d in enumerate(reversed(range(dim))):
+            off_lex += grids[j] * (4 * k) ** d
+        st = compressed[:, e].astype(np.int64).reshape((C,) + (1,) * dim)
+        invalid = st == INVALID
+        is_lex = (~invalid) & ((st & LEX_FLAG) != 0)
+        val = np.where(is_lex, (st & (LEX_FLAG - 1)) + off_lex[None], st + off[None])
+        val = np.where(invalid, np.int64(INVALID), val)
         out[(slice(None),) + tuple(sl[::-1])] = val.astype(np.uint32)
     return out.reshape(C, n ** dim)
 
