@@ -13,6 +13,7 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/dasm.h"
@@ -20,6 +21,7 @@
 #include "kernels_brick.cuh"
 #include "kernels_fast.cuh"
 #include "mesh.h"
+#include "tma_launch.h"
 
 using namespace dasm;
 
@@ -303,6 +305,13 @@ struct dasm_op
   std::vector<char> h_brick_boundary;
   const void *      last_compressed = nullptr; // vector whose partition-boundary values are final on the comm stream
   double            lap_P[4][25], lap_Q[4][25]; // even-odd blocks (kernels_fast.cuh EOMat) of M, g0 K, g1 K, g2 K
+  // TMA-fed kernels (kernels_tma.cuh) on the lex bricks: the fast lists above then hold lex bricks
+  bool                  tma_ok = false;
+  std::vector<TmaBrick> h_tma;           // per kernel brick (valid for lex bricks)
+  TmaBrick *            d_tma_lap     = nullptr; // descriptors in the order of d_fast_ids
+  uint32_t *            d_tma_foreign = nullptr; // foreign index lists of the mode-1 bricks
+  int                   tma_any_mode1 = 0;
+  std::unordered_map<const void *, TmaMaps> tma_cache; // tensor maps per vector
 
   dasm_op(int degree)
     : basis(degree)
@@ -335,6 +344,8 @@ struct dasm_fdm
   bool      fast_ok    = false;
   uint32_t *d_fast_ids = nullptr, *d_slow_ids = nullptr;
   int       n_fast = 0, n_slow = 0, n_fast_boundary = 0;
+  TmaBrick *d_tma_list = nullptr; // TMA-fed kernel: descriptors in the order of d_fast_ids
+  int       tma_any_mode1 = 0;
   double    fast_P[6][25], fast_Q[6][25]; // even-odd blocks of Ax Ay Az Bx By Bz
   double    fast_inv[729];
   std::vector<double>   h_S, h_lam; // double copies for inspection
@@ -815,6 +826,28 @@ overlap_post(dasm_op *op)
   CUDA_CHECK(cudaStreamWaitEvent(op->ctx->stream, op->ctx->ev_b, 0));
 }
 
+// tensor maps of a vector for the TMA-fed kernels (cached per pointer); nullptr: not usable (alignment)
+static const TmaMaps *
+tma_maps_for(dasm_op *op, const void *vec)
+{
+  auto it = op->tma_cache.find(vec);
+  if (it != op->tma_cache.end())
+    return &it->second;
+  TmaMaps     m;
+  std::string err;
+  if (!tma_encode_maps(m, vec, op->k, (int)op->esize(), (long long)op->nb.n_lex, err))
+    return nullptr;
+  if (op->tma_cache.size() > 64)
+    op->tma_cache.clear();
+  return &op->tma_cache.emplace(vec, m).first->second;
+}
+
+static bool
+tma_aligned(const void *a, const void *b, const void *c)
+{
+  return ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c)) & 15) == 0;
+}
+
 // warp-specialised Laplace kernel over the regular bricks; false: not available (shared memory), nothing launched
 template <int K, typename T>
 static bool
@@ -829,6 +862,17 @@ launch_laplace_fast(dasm_op *op, T *dst, const T *src, const Epilogue<T> &epi, c
   constexpr size_t smem = G::smem_bytes(1, 2, 1);
   if (smem > (size_t)op->max_smem || epilogue_n_operands(epi) > 1) // one operand buffer (b of the residual epilogue)
     return false;
+  if (op->tma_ok)
+    {
+      const TmaMaps *tm = tma_maps_for(op, src);
+      if (tm == nullptr || !tma_aligned(dst, epi.v0, epi.v1) || tma_laplace_smem(K, (int)sizeof(T)) > (size_t)op->max_smem)
+        return false;
+      const int     grid = std::min(count, std::max(1, op->n_sm - reserve_sms));
+      const TmaList list = {op->d_tma_lap + first, op->d_tma_foreign, count, op->tma_any_mode1};
+      launch_laplace_tma<T>(K, op->ctx->stream, grid, src, dst, (T *)op->d_acc, epi, op->lap_P, op->lap_Q, *tm, shared_mode, ni, list, fast_dbg());
+      op->ctx->launches++;
+      return true;
+    }
   FastLaplaceMats<T, K + 1> mats;
   eo_fill(mats.M, op->lap_P[0], op->lap_Q[0]);
   eo_fill(mats.K0, op->lap_P[1], op->lap_Q[1]);
@@ -1060,6 +1104,19 @@ launch_fdm_fast(dasm_fdm *f, T *dst, const T *src, const Epilogue<T> &epi, const
   constexpr size_t smem = G::smem_bytes(2, 1, 2);
   if (smem > (size_t)op->max_smem)
     return false;
+  if (op->tma_ok)
+    {
+      const TmaMaps *tm = tma_maps_for(op, src);
+      if (tm == nullptr || f->d_tma_list == nullptr || !tma_aligned(dst, epi.v0, epi.v1) ||
+          tma_fdm_smem(K, (int)sizeof(T)) > (size_t)op->max_smem)
+        return false;
+      const int     grid = std::min(count, std::max(1, op->n_sm - reserve_sms));
+      const TmaList list = {f->d_tma_list + first, op->d_tma_foreign, count, f->tma_any_mode1};
+      launch_fdm_tma<T>(K, op->ctx->stream, grid, src, dst, (T *)op->d_acc, epi, f->fast_P, f->fast_Q, f->fast_inv, *tm, shared_mode, ni, list,
+                        fast_dbg());
+      op->ctx->launches++;
+      return true;
+    }
   constexpr int         n = K + 1;
   FastFdmMats<T, K + 1> mats;
   eo_fill(mats.Ax, f->fast_P[0], f->fast_Q[0]);
@@ -2060,6 +2117,105 @@ dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping
                             op->h_fast_ids  = fast_ids;
                           }
                       }
+                    // ---- TMA-fed kernels (kernels_tma.cuh): every lex brick with its 7 upper neighbours
+                    if (op->nb.n_lex > 0)
+                      {
+                        const int nbx = (M.nl[0] + 3) / 4, nby = (M.nl[1] + 3) / 4;
+                        const int R   = 4 * k;
+                        op->h_tma.assign(bricks.size(), TmaBrick());
+                        std::vector<uint32_t> foreign;
+                        std::vector<uint32_t> fast_ids, slow_ids;
+                        static const int      off7[7][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {1, 1, 0}, {1, 0, 1}, {0, 1, 1}, {1, 1, 1}};
+                        const int             NFORt = 3 * R * R + 3 * R + 1, NFPt = (NFORt + 3) / 4 * 4;
+                        for (size_t b = 0; b < bricks.size(); ++b)
+                          {
+                            const BrickDesc &bd = bricks[b];
+                            if (!(bd.shared & BRICK_LEX))
+                              {
+                                slow_ids.push_back((uint32_t)b);
+                                continue;
+                              }
+                            fast_ids.push_back((uint32_t)b);
+                            TmaBrick &t  = op->h_tma[b];
+                            t.base       = bd.base;
+                            t.mode       = 0;
+                            t.list_off   = 0;
+                            const auto &o = M.cell_ijk[bd.first_cell];
+                            for (int q = 0; q < 7; ++q)
+                              {
+                                int  c2[3];
+                                bool local = true;
+                                for (int d = 0; d < 3; ++d)
+                                  {
+                                    c2[d] = o[d] + 4 * off7[q][d];
+                                    if (c2[d] >= M.p.nc[d])
+                                      c2[d] -= M.p.nc[d]; // periodic wrap (a lex brick has neighbours across all faces)
+                                    if (c2[d] < M.lo[d] || c2[d] >= M.hi[d])
+                                      local = false;
+                                  }
+                                t.nb[q] = 0;
+                                if (local)
+                                  {
+                                    const size_t nbk = ((size_t)((c2[2] - M.lo[2]) / 4) * nby + (c2[1] - M.lo[1]) / 4) * nbx + (c2[0] - M.lo[0]) / 4;
+                                    if ((bricks[nbk].shared & BRICK_LEX) && (c2[0] - M.lo[0]) % 4 == 0 && (c2[1] - M.lo[1]) % 4 == 0 &&
+                                        (c2[2] - M.lo[2]) % 4 == 0)
+                                      t.nb[q] = bricks[nbk].base;
+                                    else
+                                      local = false;
+                                  }
+                                if (!local)
+                                  t.mode = 1;
+                              }
+                            if (t.mode == 1)
+                              {
+                                t.list_off = (uint32_t)foreign.size();
+                                for (int j = 0; j < NFPt; ++j)
+                                  {
+                                    int X = R, Y = R, Z = R;
+                                    if (j < R * R)
+                                      Y = j % R, Z = j / R;
+                                    else if (j < 2 * R * R)
+                                      X = (j - R * R) % R, Z = (j - R * R) / R;
+                                    else if (j < 3 * R * R)
+                                      X = (j - 2 * R * R) % R, Y = (j - 2 * R * R) / R;
+                                    else if (j < 3 * R * R + R)
+                                      Z = j - 3 * R * R;
+                                    else if (j < 3 * R * R + 2 * R)
+                                      Y = j - 3 * R * R - R;
+                                    else if (j < 3 * R * R + 3 * R)
+                                      X = j - 3 * R * R - 2 * R;
+                                    uint32_t g = 0;
+                                    if (j < NFORt)
+                                      {
+                                        g = plain_gidx(bd, op->nb.cidx, X, Y, Z);
+                                        if (g == INVALID_INDEX)
+                                          throw std::runtime_error("internal: constrained DoF in the closure of a lex brick");
+                                      }
+                                    foreign.push_back(g);
+                                  }
+                              }
+                          }
+                        std::stable_partition(fast_ids.begin(), fast_ids.end(), [&](uint32_t b) { return op->h_brick_boundary[b] != 0; });
+                        op->n_fast_boundary = 0;
+                        std::vector<TmaBrick> ordered;
+                        for (const uint32_t b : fast_ids)
+                          {
+                            op->n_fast_boundary += op->h_brick_boundary[b] ? 1 : 0;
+                            ordered.push_back(op->h_tma[b]);
+                            op->tma_any_mode1 |= (int)op->h_tma[b].mode;
+                          }
+                        cudaFree(op->d_fast_ids);
+                        cudaFree(op->d_slow_ids);
+                        op->tma_ok        = true;
+                        op->fast_ok       = true;
+                        op->d_tma_lap     = dev_upload(ordered, ctx->stream);
+                        op->d_tma_foreign = dev_upload(foreign, ctx->stream);
+                        op->d_fast_ids    = dev_upload(fast_ids, ctx->stream);
+                        op->d_slow_ids    = dev_upload(slow_ids, ctx->stream);
+                        op->n_fast        = (int)fast_ids.size();
+                        op->n_slow        = (int)slow_ids.size();
+                        op->h_fast_ids    = fast_ids;
+                      }
                     // 1-D matrices of the Kronecker form of the Cartesian cell matrix in even-odd form
                     {
                       std::vector<double> A(n * n);
@@ -2108,6 +2264,8 @@ dasm_op_destroy(dasm_op *op)
   cudaFree(op->d_fast_ftab);
   cudaFree(op->d_fast_ids);
   cudaFree(op->d_slow_ids);
+  cudaFree(op->d_tma_lap);
+  cudaFree(op->d_tma_foreign);
   for (void *p : op->d_map_bufs)
     cudaFree(p);
   op->exchange.destroy();
@@ -2941,6 +3099,16 @@ dasm_fdm_create(dasm_op *op, int n_overlap, int sub_mesh_approximation, int weig
               f->n_slow     = (int)slow_ids.size();
               f->d_fast_ids = dev_upload(fast_ids, op->ctx->stream);
               f->d_slow_ids = dev_upload(slow_ids, op->ctx->stream);
+              if (op->tma_ok)
+                {
+                  std::vector<TmaBrick> ordered;
+                  for (const uint32_t b : fast_ids)
+                    {
+                      ordered.push_back(op->h_tma[b]);
+                      f->tma_any_mode1 |= (int)op->h_tma[b].mode;
+                    }
+                  f->d_tma_list = dev_upload(ordered, op->ctx->stream);
+                }
             }
         }
     }
@@ -2964,6 +3132,7 @@ dasm_fdm_destroy(dasm_fdm *f)
   cudaFree(f->d_brick_tri);
   cudaFree(f->d_fast_ids);
   cudaFree(f->d_slow_ids);
+  cudaFree(f->d_tma_list);
   cudaFree(f->d_pidx);
   delete f;
   DASM_API_END

@@ -28,8 +28,8 @@ namespace dasm
     T qp[9];  // Gauss points on [0,1]
   };
 
-  __constant__ DevBasis<double> c_basis_d[9];
-  __constant__ DevBasis<float>  c_basis_f[9];
+  static __constant__ DevBasis<double> c_basis_d[9];
+  static __constant__ DevBasis<float>  c_basis_f[9];
 
   template <typename T>
   struct BasisOf;
@@ -600,7 +600,7 @@ namespace dasm
       }
   }
 
-  __global__ void
+  static __global__ void
   reduce_partials_kernel(const double *partial, double *out, const int n)
   {
     __shared__ double sh[32];

@@ -1,0 +1,889 @@
+// Warp-specialised, TMA-fed brick kernels (sm_100a) for the "lex" bricks of a mesh (mesh.h): full 4 x 4 x 4 bricks whose
+// own DoFs are the lexicographic box [0, 4k)^3 = block i of 64 k^3 entries of every vector, i.e. a 4-D tensor
+// (x, y, z, brick) that the TMA engine moves with box copies (cp.async.bulk.tensor, SASS UTMALDG):
+//
+//   tile of a brick = own box {R, R, R} (R = 4k)                                  one tensor copy
+//                   + the faces / edges / corner owned by the 7 upper neighbours   7 tensor copies: {XW,R,R} (x = 0 plane of the
+//                     +x brick, XW = 16 bytes wide), {R,1,R}, {R,R,1}, {XW,1,R}, {XW,R,1}, {R,1,1}, {XW,1,1}
+//   all issued by ONE thread on one mbarrier (complete_tx); no index tables, no LSU work, no per-brick index traffic.
+//   Bricks with an upper neighbour that is not a local lex brick (partition boundary: ghost entries; irregular bricks)
+//   fetch the foreign points through an index list with cp.async instead (mode 1).
+//   epilogue operands (b; x and x_old) of the own box: 1-D bulk copies (the box is contiguous in global memory).
+//
+// Compute phases, even-odd contractions, the merge by shuffles and the named-barrier hand-over to the mover warps are
+// those of kernels_fast.cuh (which remains the path for the old numbering, DASM_NO_LEX=1).  The mover warps run the
+// fused vector epilogue in the order of the box: 16-byte shared-memory loads and global stores, red.global.add for the
+// box points on the shared lower faces (X = 0, Y = 0 or Z = 0) and for the points owned by the upper neighbours.
+#pragma once
+#include <cuda.h>
+
+#include "kernels_fast.cuh"
+
+namespace dasm
+{
+  // descriptor of a lex brick in the processing order of a kernel launch
+  struct TmaBrick
+  {
+    uint32_t base;     // first DoF of the own box (a multiple of 64 k^3)
+    uint32_t mode;     // 0: the 7 upper neighbours are local lex bricks (nb = their bases); 1: index list
+    uint32_t nb[7];    // +x, +y, +z, +xy, +xz, +yz, +xyz
+    uint32_t list_off; // mode 1: offset of the brick's foreign index list (NFP entries, face order)
+  };
+  constexpr int TMA_DW = sizeof(TmaBrick) / 4;
+
+  // tensor maps of one vector (kernel parameters)
+  struct TmaMaps
+  {
+    CUtensorMap main, fx, fy, fz, exy, exz, eyz, cxyz;
+  };
+
+  struct TmaList
+  {
+    const TmaBrick *bricks;  // [n] in processing order
+    const uint32_t *foreign; // index lists of the mode-1 bricks
+    int             n;
+    int             any_mode1;
+  };
+
+  template <int k, typename T>
+  struct TmaGeom
+  {
+    static constexpr int n      = k + 1;
+    static constexpr int R      = 4 * k;
+    static constexpr int XW     = 16 / (int)sizeof(T);
+    static constexpr int NB     = R * R * R;
+    static constexpr int NCELLS = 64;
+    static constexpr int NCT    = NCELLS * n;
+    static constexpr int NMT    = 64;
+    static constexpr int NT     = NCT + NMT;
+    static constexpr int CS     = (n * n * n) | 1;
+    static constexpr int V      = 16 / (int)sizeof(T); // elements per 16-byte vector
+    __host__ __device__ static constexpr int
+    pad(const int e)
+    {
+      return (e * (int)sizeof(T) + 127) / 128 * 128 / (int)sizeof(T);
+    }
+    // tile regions (element offsets, 128-byte aligned: TMA destinations)
+    static constexpr int O_MAIN = 0;
+    static constexpr int O_FX   = O_MAIN + pad(NB);
+    static constexpr int O_FY   = O_FX + pad(R * R * XW);
+    static constexpr int O_FZ   = O_FY + pad(R * R);
+    static constexpr int O_EXY  = O_FZ + pad(R * R);
+    static constexpr int O_EXZ  = O_EXY + pad(R * XW);
+    static constexpr int O_EYZ  = O_EXZ + pad(R * XW);
+    static constexpr int O_C    = O_EYZ + pad(R);
+    static constexpr int TILE   = O_C + pad(XW);
+    static constexpr unsigned BYTES_MAIN = (unsigned)(NB * sizeof(T));
+    static constexpr unsigned BYTES_FOR  = (unsigned)((R * R * XW + 2 * R * R + 2 * R * XW + R + XW) * sizeof(T));
+    // points owned by the upper neighbours in face order: fx[Z][Y] | fy[Z][X] | fz[Y][X] | exy[Z] | exz[Y] | eyz[X] | c
+    static constexpr int J_FY   = R * R;
+    static constexpr int J_FZ   = 2 * R * R;
+    static constexpr int J_EXY  = 3 * R * R;
+    static constexpr int J_EXZ  = J_EXY + R;
+    static constexpr int J_EYZ  = J_EXZ + R;
+    static constexpr int J_C    = J_EYZ + R;
+    static constexpr int NFOR   = J_C + 1;
+    static constexpr int NFP    = (NFOR + 3) / 4 * 4;
+    static constexpr int NFORP  = pad(NFOR);
+    static constexpr int NSH    = NB - (R - 1) * (R - 1) * (R - 1); // own DoFs on the shared lower faces
+    static constexpr int NFT    = (NFOR + NCT - 1) / NCT;
+    static constexpr int NFM    = (NFOR + NMT - 1) / NMT;
+    static constexpr int NSI    = (NSH + NMT - 1) / NMT;
+    static constexpr int XSLOT  = pad(NCELLS * CS);
+    // shared memory: (alignment slack, 128 B) barriers + descriptor (128 B) | tile | X slots (n_x; Laplace: the output box aliases the first one)
+    //                | [output box] | output faces | operand boxes (n_ops)
+    static constexpr size_t
+    smem_bytes(const int n_x, const bool separate_out, const int n_ops)
+    {
+      return 256 + (size_t)(TILE + n_x * XSLOT + (separate_out ? pad(NB) : 0) + NFORP + n_ops * pad(NB)) * sizeof(T);
+    }
+    // tile offset of the j-th foreign point
+    __host__ __device__ static constexpr int
+    foreign_tile_offset(const int j)
+    {
+      return j < J_FY ? O_FX + j * XW :
+                        (j < J_FZ ? O_FY + (j - J_FY) :
+                                    (j < J_EXY ? O_FZ + (j - J_FZ) :
+                                                 (j < J_EXZ ? O_EXY + (j - J_EXY) * XW :
+                                                              (j < J_EYZ ? O_EXZ + (j - J_EXZ) * XW : (j < J_C ? O_EYZ + (j - J_EYZ) : O_C)))));
+    }
+    // offset of the j-th foreign point relative to the base of the neighbour brick that owns it, and which neighbour
+    __host__ __device__ static constexpr int
+    foreign_owner(const int j)
+    {
+      return j < J_FY ? 0 : (j < J_FZ ? 1 : (j < J_EXY ? 2 : (j < J_EXZ ? 3 : (j < J_EYZ ? 4 : (j < J_C ? 5 : 6)))));
+    }
+    __host__ __device__ static constexpr int
+    foreign_box_offset(const int j)
+    {
+      // fx (Z, Y): R Y + R^2 Z = R j;  fy (Z, X): X + R^2 Z;  fz (Y, X): X + R Y;  exy (Z): R^2 Z;  exz (Y): R Y;  eyz (X): X
+      return j < J_FY ? R * j :
+                        (j < J_FZ ? ((j - J_FY) % R) + R * R * ((j - J_FY) / R) :
+                                    (j < J_EXY ? (j - J_FZ) : (j < J_EXZ ? R * R * (j - J_EXY) : (j < J_EYZ ? R * (j - J_EXZ) : (j < J_C ? (j - J_EYZ) : 0)))));
+    }
+    // box index of the s-th own DoF on the shared lower faces: plane Z = 0, then per Z >= 1 the row Y = 0 and the column X = 0
+    __host__ __device__ static constexpr int
+    shared_box_index(const int s)
+    {
+      if (s < R * R)
+        return s;
+      const int q = s - R * R, Z = 1 + q / (2 * R - 1), w = q % (2 * R - 1);
+      return Z * R * R + (w < R ? w : (w - R + 1) * R);
+    }
+  };
+
+  // ---- TMA primitives ------------------------------------------------------------------------------------------------------
+  __device__ __forceinline__ void
+  tma_load_4d(const unsigned dst, const CUtensorMap *map, const int c0, const int c1, const int c2, const int c3, const unsigned mbar)
+  {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(mbar)
+                 : "memory");
+  }
+
+  // all tensor copies of one tile (one elected thread)
+  template <int k, typename T>
+  __device__ __forceinline__ void
+  tma_issue_tile(T *tile, const TmaMaps &maps, const uint32_t *desc, const unsigned mbar)
+  {
+    using G                = TmaGeom<k, T>;
+    const unsigned t0      = (unsigned)__cvta_generic_to_shared(tile);
+    const uint32_t base    = desc[0];
+    const bool     mode0   = desc[1] == 0u;
+    constexpr unsigned ES  = (unsigned)sizeof(T);
+    mbar_expect_tx(mbar, mode0 ? G::BYTES_MAIN + G::BYTES_FOR : G::BYTES_MAIN);
+    tma_load_4d(t0 + G::O_MAIN * ES, &maps.main, 0, 0, 0, (int)(base / G::NB), mbar);
+    if (mode0)
+      {
+        tma_load_4d(t0 + G::O_FX * ES, &maps.fx, 0, 0, 0, (int)(desc[2] / G::NB), mbar);
+        tma_load_4d(t0 + G::O_FY * ES, &maps.fy, 0, 0, 0, (int)(desc[3] / G::NB), mbar);
+        tma_load_4d(t0 + G::O_FZ * ES, &maps.fz, 0, 0, 0, (int)(desc[4] / G::NB), mbar);
+        tma_load_4d(t0 + G::O_EXY * ES, &maps.exy, 0, 0, 0, (int)(desc[5] / G::NB), mbar);
+        tma_load_4d(t0 + G::O_EXZ * ES, &maps.exz, 0, 0, 0, (int)(desc[6] / G::NB), mbar);
+        tma_load_4d(t0 + G::O_EYZ * ES, &maps.eyz, 0, 0, 0, (int)(desc[7] / G::NB), mbar);
+        tma_load_4d(t0 + G::O_C * ES, &maps.cxyz, 0, 0, 0, (int)(desc[8] / G::NB), mbar);
+      }
+  }
+
+  // mode 1: foreign points of the tile through the index list (cp.async by the compute threads)
+  template <int k, typename T>
+  __device__ __forceinline__ void
+  tma_foreign_idx_load(uint32_t (&gf)[TmaGeom<k, T>::NFT], const TmaList &list, const uint32_t mode, const uint32_t list_off, const int tid)
+  {
+    using G = TmaGeom<k, T>;
+#pragma unroll
+    for (int jj = 0; jj < G::NFT; ++jj)
+      {
+        const int j = tid + jj * G::NCT;
+        gf[jj]      = (mode != 0u && j < G::NFOR) ? ldg_early(list.foreign + list_off + j) : 0u;
+      }
+  }
+
+  template <int k, typename T>
+  __device__ __forceinline__ void
+  tma_foreign_gather(T *tile, const uint32_t (&gf)[TmaGeom<k, T>::NFT], const T *__restrict__ src, const int tid)
+  {
+    using G = TmaGeom<k, T>;
+#pragma unroll
+    for (int jj = 0; jj < G::NFT; ++jj)
+      {
+        const int j = tid + jj * G::NCT;
+        if (j < G::NFOR)
+          cp_async_value(tile + G::foreign_tile_offset(j), src + gf[jj]);
+      }
+  }
+
+  // per-thread addressing of a cell plane in the tile: rows r = 0..k (stride rs for r < k, separate offset for r = k when it
+  // lies on the upper face of the brick), each row x = 0..k-1 contiguous and x = k through a second set of offsets
+  struct PlaneAddr
+  {
+    int r0, rs, rk; // row r < k at r0 + r rs, row k at rk
+    int x0, xs, xk; // point x = k of row r < k at x0 + r xs, of row k at xk
+  };
+
+  // Laplace phase A: plane y = t of cell (cx, cy, cz), rows z
+  template <int k, typename T>
+  __device__ __forceinline__ PlaneAddr
+  tile_plane_y(const int cx, const int cy, const int cz, const int t)
+  {
+    using G       = TmaGeom<k, T>;
+    constexpr int R = G::R, XW = G::XW;
+    const int     Y = k * cy + t, Z0 = k * cz;
+    const bool    yR = (Y == R), xR = (cx == 3), zR = (cz == 3);
+    PlaneAddr     a;
+    a.r0 = (yR ? G::O_FY + Z0 * R : G::O_MAIN + (Z0 * R + Y) * R) + k * cx;
+    a.rs = yR ? R : R * R;
+    a.rk = zR ? (yR ? G::O_EYZ : G::O_FZ + Y * R) + k * cx : a.r0 + k * a.rs;
+    a.x0 = xR ? (yR ? G::O_EXY + Z0 * XW : G::O_FX + (Z0 * R + Y) * XW) : a.r0 + k;
+    a.xs = xR ? (yR ? XW : R * XW) : a.rs;
+    a.xk = xR ? (zR ? (yR ? G::O_C : G::O_EXZ + Y * XW) : a.x0 + k * a.xs) : a.rk + k;
+    return a;
+  }
+
+  // FDM phase A: plane z = t of cell (cx, cy, cz), rows y
+  template <int k, typename T>
+  __device__ __forceinline__ PlaneAddr
+  tile_plane_z(const int cx, const int cy, const int cz, const int t)
+  {
+    using G       = TmaGeom<k, T>;
+    constexpr int R = G::R, XW = G::XW;
+    const int     Z = k * cz + t, Y0 = k * cy;
+    const bool    zR = (Z == R), xR = (cx == 3), yR = (cy == 3);
+    PlaneAddr     a;
+    a.r0 = (zR ? G::O_FZ + Y0 * R : G::O_MAIN + (Z * R + Y0) * R) + k * cx;
+    a.rs = R;
+    a.rk = yR ? (zR ? G::O_EYZ : G::O_FY + Z * R) + k * cx : a.r0 + k * R;
+    a.x0 = xR ? (zR ? G::O_EXZ + Y0 * XW : G::O_FX + (Z * R + Y0) * XW) : a.r0 + k;
+    a.xs = xR ? XW : R;
+    a.xk = xR ? (yR ? (zR ? G::O_C : G::O_EXY + Z * XW) : a.x0 + k * XW) : a.rk + k;
+    return a;
+  }
+
+  // output of plane z = t (rows y): the own box at `box`, the points owned by the upper neighbours in face order at `ofor`;
+  // offsets relative to box, with ofor = box + ofo
+  template <int k, typename T>
+  __device__ __forceinline__ PlaneAddr
+  out_plane_z(const int cx, const int cy, const int cz, const int t, const int ofo)
+  {
+    using G       = TmaGeom<k, T>;
+    constexpr int R = G::R;
+    const int     Z = k * cz + t, Y0 = k * cy, X0 = k * cx;
+    const bool    zR = (Z == R);
+    PlaneAddr     a;
+    a.r0 = zR ? ofo + G::J_FZ + Y0 * R + X0 : (Z * R + Y0) * R + X0;
+    a.rs = R;
+    a.rk = zR ? ofo + G::J_EYZ + X0 : ofo + G::J_FY + Z * R + X0; // only used for cy == 3
+    a.x0 = zR ? ofo + G::J_EXZ + Y0 : ofo + Z * R + Y0;           // only used for cx == 3
+    a.xs = 1;
+    a.xk = zR ? ofo + G::J_C : ofo + G::J_EXY + Z; // cx == 3 and cy == 3
+    return a;
+  }
+
+  template <int k, typename T>
+  __device__ __forceinline__ void
+  tma_out_store(const T (&r)[k + 1][k + 1], T *box, const PlaneAddr &a, const int cx, const int cy)
+  {
+#pragma unroll
+    for (int y = 0; y <= k; ++y)
+#pragma unroll
+      for (int x = 0; x <= k; ++x)
+        {
+          const bool w = (x < k || cx == 3) && (y < k || cy == 3);
+          if (w)
+            {
+              const int o = (x < k) ? ((y < k) ? a.r0 + y * a.rs + x : a.rk + x) : ((y < k) ? a.x0 + y * a.xs : a.xk);
+              box[o]      = r[y][x];
+            }
+        }
+  }
+
+  // ---- mover side ------------------------------------------------------------------------------------------------------------
+  template <typename T>
+  struct Vec16;
+  template <>
+  struct Vec16<double>
+  {
+    typedef double2 type;
+  };
+  template <>
+  struct Vec16<float>
+  {
+    typedef float4 type;
+  };
+
+  template <int k, typename T>
+  struct TmaInitRegs
+  {
+    T a[TmaGeom<k, T>::NSI], b[TmaGeom<k, T>::NSI];
+  };
+
+  template <int k, typename T>
+  __device__ __forceinline__ void
+  tma_next_init_load(TmaInitRegs<k, T> &r, const NextInit<T> &ni, const uint32_t base, const int m)
+  {
+    using G       = TmaGeom<k, T>;
+    const bool h0 = (ni.out != nullptr) && ni.v0 != nullptr, h1 = (ni.out != nullptr) && (ni.v1 != nullptr && ni.f1 != T(0));
+#pragma unroll
+    for (int it = 0; it < G::NSI; ++it)
+      {
+        const int  s  = m + it * G::NMT;
+        const bool in = s < G::NSH;
+        const int  i  = G::shared_box_index(in ? s : 0);
+        r.a[it]       = (h0 && in) ? __ldg(ni.v0 + base + i) : T(0);
+        r.b[it]       = (h1 && in) ? __ldg(ni.v1 + base + i) : T(0);
+      }
+  }
+
+  template <int k, typename T>
+  __device__ __forceinline__ void
+  tma_next_init_store(const TmaInitRegs<k, T> &r, const NextInit<T> &ni, const uint32_t base, const int m)
+  {
+    using G = TmaGeom<k, T>;
+    if (ni.out == nullptr)
+      return;
+#pragma unroll
+    for (int it = 0; it < G::NSI; ++it)
+      {
+        const int s = m + it * G::NMT;
+        if (s < G::NSH)
+          ni.out[base + G::shared_box_index(s)] = r.a[it] + ni.f1 * (r.a[it] - r.b[it]);
+      }
+  }
+
+  // fused epilogue of the own box in box order.  KIND: EPI_*; TWO: the Chebyshev update reads x_old
+  template <int k, typename T, int KIND, bool TWO>
+  __device__ __forceinline__ void
+  tma_store_box(const T *out, const T *ops0, const T *ops1, T *__restrict__ d, T *__restrict__ sd, const T sh_a, const T f1, const T f2,
+                const int m, const bool skip_red)
+  {
+    using G  = TmaGeom<k, T>;
+    using VT = typename Vec16<T>::type;
+    constexpr int V = G::V, R = G::R;
+#pragma unroll 4
+    for (int p = m; p < G::NB / V; p += G::NMT)
+      {
+        const int i = p * V;
+        const int X = i % R, Y = (i / R) % R, Z = i / (R * R);
+        T         y[V], a[V], b[V], res[V];
+        *reinterpret_cast<VT *>(y) = *reinterpret_cast<const VT *>(out + i);
+        if (Y == 0 || Z == 0)
+          {
+            if (!skip_red)
+#pragma unroll
+              for (int e = 0; e < V; ++e)
+                atomic_add(sd + i + e, sh_a * y[e]);
+            continue;
+          }
+        if (KIND == EPI_RESIDUAL || KIND == EPI_CHEB)
+          *reinterpret_cast<VT *>(a) = *reinterpret_cast<const VT *>(ops0 + i);
+        if (KIND == EPI_CHEB && TWO)
+          *reinterpret_cast<VT *>(b) = *reinterpret_cast<const VT *>(ops1 + i);
+#pragma unroll
+        for (int e = 0; e < V; ++e)
+          {
+            if (KIND == EPI_RESIDUAL)
+              res[e] = a[e] - y[e];
+            else if (KIND == EPI_CHEB)
+              res[e] = a[e] + f2 * y[e] + f1 * (a[e] - (TWO ? b[e] : T(0)));
+            else if (KIND == EPI_SCALE)
+              res[e] = f2 * y[e];
+            else
+              res[e] = y[e];
+          }
+        if (X == 0)
+          {
+            if (!skip_red)
+              atomic_add(sd + i, sh_a * y[0]);
+#pragma unroll
+            for (int e = 1; e < V; ++e)
+              d[i + e] = res[e];
+          }
+        else
+          *reinterpret_cast<VT *>(d + i) = *reinterpret_cast<const VT *>(res);
+      }
+  }
+
+  template <int k, typename T>
+  __device__ __forceinline__ void
+  tma_mover_loop(const T *out, const T *ofor, T *ops0, T *ops1, T *__restrict__ dst, T *__restrict__ acc, const Epilogue<T> &epi,
+                 const TmaList &list, const int shared_mode, const NextInit<T> &ni, const int m, const unsigned mbar, const FastMaps &dbgmaps)
+  {
+    using G           = TmaGeom<k, T>;
+    constexpr int NFM = G::NFM;
+    const bool need0  = (epi.kind == EPI_RESIDUAL || epi.kind == EPI_CHEB);
+    const bool need1  = (epi.kind == EPI_CHEB && epi.f1 != T(0) && epi.v1 != nullptr);
+    const T    alpha  = (epi.kind == EPI_RESIDUAL) ? T(-1) : ((epi.kind == EPI_CHEB || epi.kind == EPI_SCALE) ? epi.f2 : T(1));
+    T *        sh_dst = (shared_mode == SHARED_DIRECT) ? dst : acc;
+    const T    sh_a   = (shared_mode == SHARED_DIRECT) ? alpha : T(1);
+    const int  G1 = (int)gridDim.x;
+    int        it = blockIdx.x;
+    const uint32_t *dw = reinterpret_cast<const uint32_t *>(list.bricks);
+    // descriptor words of the current brick; base of the next one (operand staging)
+    uint32_t base = ldg_early(dw + (size_t)it * TMA_DW), mode = ldg_early(dw + (size_t)it * TMA_DW + 1);
+    uint32_t base_n = (it + G1 < list.n) ? ldg_early(dw + (size_t)(it + G1) * TMA_DW) : 0u;
+    unsigned phase  = 0;
+    auto     stage  = [&](const uint32_t b) {
+      if (m == 0 && need0)
+        {
+          constexpr unsigned bytes = (unsigned)(G::NB * sizeof(T));
+          mbar_expect_tx(mbar, need1 ? 2 * bytes : bytes);
+          bulk_load((unsigned)__cvta_generic_to_shared(ops0), epi.v0 + b, bytes, mbar);
+          if (need1)
+            bulk_load((unsigned)__cvta_generic_to_shared(ops1), epi.v1 + b, bytes, mbar);
+        }
+    };
+    stage(base);
+    for (; it < list.n; it += G1)
+      {
+        const bool has_next = it + G1 < list.n;
+        // global indices of the points owned by the upper neighbours
+        uint32_t gf[NFM];
+        if (mode == 0u)
+          {
+            uint32_t nb[7];
+#pragma unroll
+            for (int q = 0; q < 7; ++q)
+              nb[q] = ldg_early(dw + (size_t)it * TMA_DW + 2 + q);
+#pragma unroll
+            for (int jj = 0; jj < NFM; ++jj)
+              {
+                const int j  = m + jj * G::NMT;
+                const int jc = j < G::NFOR ? j : 0;
+                const int o  = G::foreign_owner(jc);
+                uint32_t  b  = nb[0];
+#pragma unroll
+                for (int q = 1; q < 7; ++q)
+                  b = (o == q) ? nb[q] : b;
+                gf[jj] = b + (uint32_t)G::foreign_box_offset(jc);
+              }
+          }
+        else
+          {
+            const uint32_t lo = ldg_early(dw + (size_t)it * TMA_DW + 9);
+#pragma unroll
+            for (int jj = 0; jj < NFM; ++jj)
+              {
+                const int j = m + jj * G::NMT;
+                gf[jj]      = (j < G::NFOR) ? ldg_early(list.foreign + lo + j) : 0u;
+              }
+          }
+        const uint32_t base_nn = (it + 2 * G1 < list.n) ? ldg_early(dw + (size_t)(it + 2 * G1) * TMA_DW) : 0u;
+        const uint32_t mode_n  = has_next ? ldg_early(dw + (size_t)(it + G1) * TMA_DW + 1) : 0u;
+        TmaInitRegs<k, T> nir;
+        tma_next_init_load<k, T>(nir, ni, base, m);
+        bar_sync(FB_OUT_FULL, G::NT); // the result of this brick is in the output box
+        if (need0)
+          mbar_wait(mbar, phase); // the bulk copies of the operands have landed
+        phase ^= 1u;
+        {
+          T *        d  = dst + base;
+          T *        sd = sh_dst + base;
+          const bool skip_red = (dbgmaps.dbg & 4) != 0;
+          if (dbgmaps.dbg & 2)
+            {
+            }
+          else if (epi.kind == EPI_CHEB && need1)
+            tma_store_box<k, T, EPI_CHEB, true>(out, ops0, ops1, d, sd, sh_a, epi.f1, epi.f2, m, skip_red);
+          else if (epi.kind == EPI_CHEB)
+            tma_store_box<k, T, EPI_CHEB, false>(out, ops0, ops1, d, sd, sh_a, epi.f1, epi.f2, m, skip_red);
+          else if (epi.kind == EPI_RESIDUAL)
+            tma_store_box<k, T, EPI_RESIDUAL, false>(out, ops0, ops1, d, sd, sh_a, epi.f1, epi.f2, m, skip_red);
+          else if (epi.kind == EPI_SCALE)
+            tma_store_box<k, T, EPI_SCALE, false>(out, ops0, ops1, d, sd, sh_a, epi.f1, epi.f2, m, skip_red);
+          else
+            tma_store_box<k, T, EPI_STORE, false>(out, ops0, ops1, d, sd, sh_a, epi.f1, epi.f2, m, skip_red);
+          // points owned by the upper neighbours
+#pragma unroll
+          for (int jj = 0; jj < NFM; ++jj)
+            {
+              const int j = m + jj * G::NMT;
+              if (j < G::NFOR && !skip_red)
+                atomic_add(sh_dst + gf[jj], sh_a * ofor[j]);
+            }
+        }
+        if (has_next)
+          bar_arrive(FB_OUT_EMPTY, G::NT);
+        tma_next_init_store<k, T>(nir, ni, base, m);
+        bar_sync(FB_MOVERS, G::NMT); // all movers have read the operands: stage those of the next brick
+        if (has_next)
+          stage(base_n);
+        base   = base_n;
+        base_n = base_nn;
+        mode   = mode_n;
+      }
+  }
+
+  // ---- Laplace, uniform Cartesian geometry --------------------------------------------------------------------------------------
+  template <int k, typename T>
+  __global__ void __launch_bounds__(TmaGeom<k, T>::NT, 1)
+  laplace_tma_kernel(const T *__restrict__ src,
+                     T *__restrict__ dst,
+                     T *__restrict__ acc,
+                     const Epilogue<T> epi,
+                     const __grid_constant__ FastLaplaceMats<T, k + 1> mats,
+                     const __grid_constant__ TmaMaps tmaps,
+                     const int         shared_mode,
+                     const NextInit<T> ni,
+                     const TmaList     list,
+                     const FastMaps    dbgmaps)
+  {
+    using G           = TmaGeom<k, T>;
+    constexpr int n   = k + 1;
+    constexpr int NFT = G::NFT;
+    extern __shared__ __align__(16) unsigned char smem_dyn[];
+    // TMA destinations must be 128-byte aligned
+    unsigned char *smem_raw = smem_dyn + ((128u - ((unsigned)__cvta_generic_to_shared(smem_dyn) & 127u)) & 127u);
+    // [0] mbarrier of the tile, [8] mbarrier of the operand staging, [16..] descriptor of the next brick
+    const unsigned mb_tile = (unsigned)__cvta_generic_to_shared(smem_raw);
+    const unsigned mb_ops  = mb_tile + 8;
+    uint32_t *     s_desc  = reinterpret_cast<uint32_t *>(smem_raw + 16);
+    T *            tile    = reinterpret_cast<T *>(smem_raw + 128);
+    T *            Xq      = tile + G::TILE;
+    T *            Xp      = Xq + G::XSLOT;
+    T *            out     = Xq; // the output box aliases the first exchange slot (written after all reads of it)
+    T *            ofor    = Xp + G::XSLOT;
+    T *            ops0    = ofor + G::NFORP;
+    if ((int)blockIdx.x >= list.n)
+      return;
+    if (threadIdx.x == 0)
+      {
+        mbar_init(mb_tile, 1);
+        mbar_init(mb_ops, 1);
+      }
+    __syncthreads();
+
+    if (threadIdx.x >= G::NCT)
+      {
+        tma_mover_loop<k, T>(out, ofor, ops0, ops0, dst, acc, epi, list, shared_mode, ni, threadIdx.x - G::NCT, mb_ops, dbgmaps);
+        return;
+      }
+    const int       tid = threadIdx.x;
+    const int       c = tid % G::NCELLS, t = tid / G::NCELLS;
+    const int       cx = c & 3, cy = (c >> 2) & 3, cz = c >> 4;
+    const bool      skip_last = ((t == k) && (cz < 2)) || (dbgmaps.dbg & 1); // whole warp: its plane z = k belongs to the cell above
+    const PlaneAddr pa = tile_plane_y<k, T>(cx, cy, cz, t);
+    const PlaneAddr po = out_plane_z<k, T>(cx, cy, cz, t, (int)(ofor - out));
+    T *             xq = Xq + c * G::CS, *xp = Xp + c * G::CS;
+    const int       G1 = (int)gridDim.x;
+    int             it = blockIdx.x;
+    const uint32_t *dw = reinterpret_cast<const uint32_t *>(list.bricks);
+    unsigned        tphase = 0;
+    // first tile
+    uint32_t mode_next = 0, lo_next = 0;
+    {
+      if (tid < TMA_DW)
+        s_desc[tid] = ldg_early(dw + (size_t)it * TMA_DW + tid);
+      bar_sync(FB_COMPUTE, G::NCT);
+      if (tid == 0)
+        tma_issue_tile<k, T>(tile, tmaps, s_desc, mb_tile);
+      if (list.any_mode1)
+        {
+          uint32_t gf[NFT];
+          tma_foreign_idx_load<k, T>(gf, list, s_desc[1], s_desc[9], tid);
+          if (s_desc[1] != 0u)
+            tma_foreign_gather<k, T>(tile, gf, src, tid);
+        }
+      bar_sync(FB_COMPUTE, G::NCT); // s_desc may be overwritten
+      if (it + G1 < list.n)
+        {
+          mode_next = ldg_early(dw + (size_t)(it + G1) * TMA_DW + 1);
+          lo_next   = ldg_early(dw + (size_t)(it + G1) * TMA_DW + 9);
+        }
+    }
+    bool first = true;
+    for (; it < list.n; it += G1)
+      {
+        const bool has_next = it + G1 < list.n;
+        // descriptor of the next brick -> shared memory (fire and forget, awaited before the barrier after phase A)
+        if (has_next && tid < TMA_DW)
+          cp_async_4(s_desc + tid, dw + (size_t)(it + G1) * TMA_DW + tid);
+        uint32_t gfn[NFT];
+        if (list.any_mode1)
+          tma_foreign_idx_load<k, T>(gfn, list, has_next ? mode_next : 0u, lo_next, tid);
+        mbar_wait(mb_tile, tphase); // the tensor copies of this brick's tile have landed
+        tphase ^= 1u;
+        if (list.any_mode1)
+          {
+            cp_async_wait_all();
+            bar_sync(FB_COMPUTE, G::NCT); // foreign points gathered by the other threads
+          }
+        // phase A: plane y = t, [z][x]: q = Mx Mz v, p = (g0 Kx Mz + g2 Mx Kz) v
+        if (!(dbgmaps.dbg & 1))
+          {
+            T a[n][n], b[n][n];
+#pragma unroll
+            for (int z = 0; z < n; ++z)
+              {
+                T         v[n];
+                const T * row = tile + (z < k ? pa.r0 + z * pa.rs : pa.rk);
+#pragma unroll
+                for (int x = 0; x < k; ++x)
+                  v[x] = row[x];
+                v[k] = tile[z < k ? pa.x0 + z * pa.xs : pa.xk];
+                mat_vec<n, T, true, true, false>(a[z], mats.M, v);
+                mat_vec<n, T, true, true, false>(b[z], mats.K0, v);
+              }
+            if (!first)
+              bar_sync(FB_OUT_EMPTY, G::NT); // the previous result (aliased with Xq) has been stored
+#pragma unroll
+            for (int x = 0; x < n; ++x)
+              {
+                T ca[n], cb[n], q[n], p[n];
+#pragma unroll
+                for (int z = 0; z < n; ++z)
+                  {
+                    ca[z] = a[z][x];
+                    cb[z] = b[z][x];
+                  }
+                mat_vec<n, T, true, true, false>(q, mats.M, ca);
+                mat_vec<n, T, true, true, false>(p, mats.M, cb);
+                mat_vec<n, T, true, true, true>(p, mats.K2, ca);
+#pragma unroll
+                for (int z = 0; z < n; ++z)
+                  {
+                    xq[(z * n + t) * n + x] = q[z];
+                    xp[(z * n + t) * n + x] = p[z];
+                  }
+              }
+          }
+        else if (!first)
+          bar_sync(FB_OUT_EMPTY, G::NT);
+        if (has_next && tid < TMA_DW)
+          cp_async_wait_all();
+        bar_sync(FB_COMPUTE, G::NCT);
+        // the tile is dead: fetch the next brick into it
+        if (has_next)
+          {
+            if (tid == 0)
+              tma_issue_tile<k, T>(tile, tmaps, s_desc, mb_tile);
+            if (list.any_mode1 && mode_next != 0u)
+              tma_foreign_gather<k, T>(tile, gfn, src, tid);
+          }
+        if (it + 2 * G1 < list.n)
+          {
+            mode_next = ldg_early(dw + (size_t)(it + 2 * G1) * TMA_DW + 1);
+            lo_next   = ldg_early(dw + (size_t)(it + 2 * G1) * TMA_DW + 9);
+          }
+        // phase B: plane z = t, [y][x]: r = My p + g1 Ky q  (+ plane z = k of the cell below for t = 0)
+        T r[n][n];
+        if (!skip_last)
+          {
+            const bool below = (t == 0) && (cz > 0);
+#pragma unroll
+            for (int x = 0; x < n; ++x)
+              {
+                T qi[n], pi[n], rc[n];
+#pragma unroll
+                for (int i = 0; i < n; ++i)
+                  {
+                    qi[i] = xq[(t * n + i) * n + x];
+                    pi[i] = xp[(t * n + i) * n + x];
+                  }
+                if (t == 0)
+                  {
+#pragma unroll
+                    for (int i = 0; i < n; ++i)
+                      {
+                        qi[i] += below ? xq[-16 * G::CS + (k * n + i) * n + x] : T(0);
+                        pi[i] += below ? xp[-16 * G::CS + (k * n + i) * n + x] : T(0);
+                      }
+                  }
+                mat_vec<n, T, true, true, false>(rc, mats.M, pi);
+                mat_vec<n, T, true, true, true>(rc, mats.K1, qi);
+#pragma unroll
+                for (int y = 0; y < n; ++y)
+                  r[y][x] = rc[y];
+              }
+            fast_merge<k, T>(r, cx, cy);
+          }
+        bar_sync(FB_COMPUTE, G::NCT); // all reads of the exchange slots are done: the output box may overwrite Xq
+        if (!skip_last && (t < k || cz == 3))
+          tma_out_store<k, T>(r, out, po, cx, cy);
+        bar_arrive(FB_OUT_FULL, G::NT);
+        first = false;
+      }
+  }
+
+  // ---- FDM, one eigen-decomposition triple, tensor-product weights folded into the matrices ----------------------------------
+  template <int k, typename T>
+  __global__ void __launch_bounds__(TmaGeom<k, T>::NT, 1)
+  fdm_tma_kernel(const T *__restrict__ src,
+                 T *__restrict__ dst,
+                 T *__restrict__ acc,
+                 const Epilogue<T> epi,
+                 const __grid_constant__ FastFdmMats<T, k + 1> mats,
+                 const __grid_constant__ TmaMaps tmaps,
+                 const int         shared_mode,
+                 const NextInit<T> ni,
+                 const TmaList     list,
+                 const FastMaps    dbgmaps)
+  {
+    using G           = TmaGeom<k, T>;
+    constexpr int n   = k + 1;
+    constexpr int NFT = G::NFT;
+    extern __shared__ __align__(16) unsigned char smem_dyn[];
+    unsigned char *smem_raw = smem_dyn + ((128u - ((unsigned)__cvta_generic_to_shared(smem_dyn) & 127u)) & 127u);
+    const unsigned mb_tile = (unsigned)__cvta_generic_to_shared(smem_raw);
+    const unsigned mb_ops  = mb_tile + 8;
+    uint32_t *     s_desc  = reinterpret_cast<uint32_t *>(smem_raw + 16);
+    T *            tile    = reinterpret_cast<T *>(smem_raw + 128);
+    T *            X       = tile + G::TILE;
+    T *            out     = X + G::XSLOT;
+    T *            ofor    = out + G::pad(G::NB);
+    T *            ops0    = ofor + G::NFORP;
+    T *            ops1    = ops0 + G::pad(G::NB);
+    __shared__ T   s_inv[n * n * n];
+    if ((int)blockIdx.x >= list.n)
+      return;
+    for (int i = threadIdx.x; i < n * n * n; i += G::NT)
+      s_inv[i] = mats.inv[i];
+    if (threadIdx.x == 0)
+      {
+        mbar_init(mb_tile, 1);
+        mbar_init(mb_ops, 1);
+      }
+    __syncthreads();
+
+    if (threadIdx.x >= G::NCT)
+      {
+        tma_mover_loop<k, T>(out, ofor, ops0, ops1, dst, acc, epi, list, shared_mode, ni, threadIdx.x - G::NCT, mb_ops, dbgmaps);
+        return;
+      }
+    const int       tid = threadIdx.x;
+    const int       c = tid % G::NCELLS, t = tid / G::NCELLS;
+    const int       cx = c & 3, cy = (c >> 2) & 3, cz = c >> 4;
+    const bool      skip_last = ((t == k) && (cz < 2)) || (dbgmaps.dbg & 1);
+    const PlaneAddr pa = tile_plane_z<k, T>(cx, cy, cz, t);
+    const PlaneAddr po = out_plane_z<k, T>(cx, cy, cz, t, (int)(ofor - out));
+    T *             xs = X + c * G::CS;
+    const T *       inv = s_inv + t * n; // row (z, y = t) of this thread's plane in phase B: broadcast reads
+    const int       G1 = (int)gridDim.x;
+    int             it = blockIdx.x;
+    const uint32_t *dw = reinterpret_cast<const uint32_t *>(list.bricks);
+    unsigned        tphase = 0;
+    uint32_t        mode_next = 0, lo_next = 0;
+    {
+      if (tid < TMA_DW)
+        s_desc[tid] = ldg_early(dw + (size_t)it * TMA_DW + tid);
+      bar_sync(FB_COMPUTE, G::NCT);
+      if (tid == 0)
+        tma_issue_tile<k, T>(tile, tmaps, s_desc, mb_tile);
+      if (list.any_mode1)
+        {
+          uint32_t gf[NFT];
+          tma_foreign_idx_load<k, T>(gf, list, s_desc[1], s_desc[9], tid);
+          if (s_desc[1] != 0u)
+            tma_foreign_gather<k, T>(tile, gf, src, tid);
+        }
+      bar_sync(FB_COMPUTE, G::NCT);
+      if (it + G1 < list.n)
+        {
+          mode_next = ldg_early(dw + (size_t)(it + G1) * TMA_DW + 1);
+          lo_next   = ldg_early(dw + (size_t)(it + G1) * TMA_DW + 9);
+        }
+    }
+    bool first = true;
+    for (; it < list.n; it += G1)
+      {
+        const bool has_next = it + G1 < list.n;
+        if (has_next && tid < TMA_DW)
+          cp_async_4(s_desc + tid, dw + (size_t)(it + G1) * TMA_DW + tid);
+        uint32_t gfn[NFT];
+        if (list.any_mode1)
+          tma_foreign_idx_load<k, T>(gfn, list, has_next ? mode_next : 0u, lo_next, tid);
+        mbar_wait(mb_tile, tphase);
+        tphase ^= 1u;
+        if (list.any_mode1)
+          cp_async_wait_all();
+        // foreign points gathered by the other threads (mode 1); all phase C reads of the exchange slot of the previous brick are
+        // done before phase A overwrites it
+        bar_sync(FB_COMPUTE, G::NCT);
+        // phase A: plane z = t, [y][x]: Ax in x, Ay in y
+        if (!(dbgmaps.dbg & 1))
+          {
+            T a[n][n];
+#pragma unroll
+            for (int y = 0; y < n; ++y)
+              {
+                T        v[n];
+                const T *row = tile + (y < k ? pa.r0 + y * pa.rs : pa.rk);
+#pragma unroll
+                for (int x = 0; x < k; ++x)
+                  v[x] = row[x];
+                v[k] = tile[y < k ? pa.x0 + y * pa.xs : pa.xk];
+                mat_vec<n, T, true, false, false>(a[y], mats.Ax, v);
+              }
+#pragma unroll
+            for (int x = 0; x < n; ++x)
+              {
+                T ca[n], q[n];
+#pragma unroll
+                for (int y = 0; y < n; ++y)
+                  ca[y] = a[y][x];
+                mat_vec<n, T, true, false, false>(q, mats.Ay, ca);
+#pragma unroll
+                for (int y = 0; y < n; ++y)
+                  xs[(t * n + y) * n + x] = q[y];
+              }
+          }
+        if (has_next && tid < TMA_DW)
+          cp_async_wait_all();
+        bar_sync(FB_COMPUTE, G::NCT);
+        // the tile is dead: fetch the next brick into it
+        if (has_next)
+          {
+            if (tid == 0)
+              tma_issue_tile<k, T>(tile, tmaps, s_desc, mb_tile);
+            if (list.any_mode1 && mode_next != 0u)
+              tma_foreign_gather<k, T>(tile, gfn, src, tid);
+          }
+        if (it + 2 * G1 < list.n)
+          {
+            mode_next = ldg_early(dw + (size_t)(it + 2 * G1) * TMA_DW + 1);
+            lo_next   = ldg_early(dw + (size_t)(it + 2 * G1) * TMA_DW + 9);
+          }
+        // phase B: plane y = t, [z][x]: Az, scale, Bz in z; Bx in x
+        if (!(dbgmaps.dbg & 1))
+          {
+            T w[n][n];
+#pragma unroll
+            for (int x = 0; x < n; ++x)
+              {
+                T col[n], u[n];
+#pragma unroll
+                for (int z = 0; z < n; ++z)
+                  col[z] = xs[(z * n + t) * n + x];
+                mat_vec<n, T, true, false, false>(u, mats.Az, col);
+#pragma unroll
+                for (int z = 0; z < n; ++z)
+                  u[z] *= inv[z * n * n + x];
+                mat_vec<n, T, false, true, false>(col, mats.Bz, u);
+#pragma unroll
+                for (int z = 0; z < n; ++z)
+                  w[z][x] = col[z];
+              }
+#pragma unroll
+            for (int z = 0; z < n; ++z)
+              {
+                T u[n];
+                mat_vec<n, T, false, true, false>(u, mats.Bx, w[z]);
+#pragma unroll
+                for (int x = 0; x < n; ++x)
+                  xs[(z * n + t) * n + x] = u[x];
+              }
+          }
+        bar_sync(FB_COMPUTE, G::NCT);
+        // phase C: plane z = t, [y][x]: By in y (+ plane z = k of the cell below for t = 0)
+        T r[n][n];
+        if (!skip_last)
+          {
+            const bool below = (t == 0) && (cz > 0);
+#pragma unroll
+            for (int x = 0; x < n; ++x)
+              {
+                T vi[n], rc[n];
+#pragma unroll
+                for (int i = 0; i < n; ++i)
+                  vi[i] = xs[(t * n + i) * n + x];
+                if (t == 0)
+                  {
+#pragma unroll
+                    for (int i = 0; i < n; ++i)
+                      vi[i] += below ? xs[-16 * G::CS + (k * n + i) * n + x] : T(0);
+                  }
+                mat_vec<n, T, false, true, false>(rc, mats.By, vi);
+#pragma unroll
+                for (int y = 0; y < n; ++y)
+                  r[y][x] = rc[y];
+              }
+            fast_merge<k, T>(r, cx, cy);
+          }
+        if (!first)
+          bar_sync(FB_OUT_EMPTY, G::NT); // the previous result has been stored
+        if (!skip_last && (t < k || cz == 3))
+          tma_out_store<k, T>(r, out, po, cx, cy);
+        bar_arrive(FB_OUT_FULL, G::NT);
+        first = false;
+      }
+  }
+} // namespace dasm

@@ -1,0 +1,217 @@
+// Launchers and tensor-map encoding of the TMA-fed kernels (kernels_tma.cuh); separate translation unit of libdasm.so.
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+
+#include "tma_launch.h"
+
+namespace dasm
+{
+  namespace
+  {
+    typedef CUresult (*EncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+    EncodeTiled
+    encode_fn()
+    {
+      static EncodeTiled fn = []() -> EncodeTiled {
+        void *                           p = nullptr;
+        cudaDriverEntryPointQueryResult  q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+          return nullptr;
+        return (EncodeTiled)p;
+      }();
+      return fn;
+    }
+
+    template <typename T, int n>
+    void
+    eo_fill(EOMat<T, n> &E, const double *P, const double *Q)
+    {
+      constexpr int m = (n + 1) / 2, h = n / 2;
+      for (int i = 0; i < m * m; ++i)
+        E.P[i] = (T)P[i];
+      for (int i = 0; i < h * h; ++i)
+        E.Q[i] = (T)Q[i];
+    }
+
+    void
+    check(cudaError_t e, const char *what)
+    {
+      if (e != cudaSuccess)
+        throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
+    }
+  } // namespace
+
+  bool
+  tma_encode_maps(TmaMaps &out, const void *vec, int k, int esize, long long n_lex, std::string &err)
+  {
+    EncodeTiled fn = encode_fn();
+    if (fn == nullptr)
+      {
+        err = "cuTensorMapEncodeTiled is not available";
+        return false;
+      }
+    if ((reinterpret_cast<uintptr_t>(vec) & 15) != 0 || n_lex <= 0)
+      {
+        err = "vector is not 16-byte aligned";
+        return false;
+      }
+    const cuuint64_t R = 4 * k, XW = 16 / esize;
+    const cuuint64_t dims[4]    = {R, R, R, (cuuint64_t)n_lex};
+    const cuuint64_t strides[3] = {R * esize, R * R * esize, R * R * R * esize};
+    const cuuint32_t estr[4]    = {1, 1, 1, 1};
+    const CUtensorMapDataType dt = esize == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    struct
+    {
+      CUtensorMap *m;
+      cuuint32_t   box[4];
+    } specs[8] = {{&out.main, {(cuuint32_t)R, (cuuint32_t)R, (cuuint32_t)R, 1}},
+                  {&out.fx, {(cuuint32_t)XW, (cuuint32_t)R, (cuuint32_t)R, 1}},
+                  {&out.fy, {(cuuint32_t)R, 1, (cuuint32_t)R, 1}},
+                  {&out.fz, {(cuuint32_t)R, (cuuint32_t)R, 1, 1}},
+                  {&out.exy, {(cuuint32_t)XW, 1, (cuuint32_t)R, 1}},
+                  {&out.exz, {(cuuint32_t)XW, (cuuint32_t)R, 1, 1}},
+                  {&out.eyz, {(cuuint32_t)R, 1, 1, 1}},
+                  {&out.cxyz, {(cuuint32_t)XW, 1, 1, 1}}};
+    for (auto &s : specs)
+      {
+        const CUresult r = fn(s.m, dt, 4, const_cast<void *>(vec), dims, strides, s.box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS)
+          {
+            err = "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r);
+            return false;
+          }
+      }
+    return true;
+  }
+
+  size_t
+  tma_laplace_smem(int k, int esize)
+  {
+#define DASM_TMA_SMEM(K) (esize == 8 ? TmaGeom<K, double>::smem_bytes(2, false, 1) : TmaGeom<K, float>::smem_bytes(2, false, 1))
+    switch (k)
+      {
+        case 2:
+          return DASM_TMA_SMEM(2);
+        case 3:
+          return DASM_TMA_SMEM(3);
+        case 4:
+          return DASM_TMA_SMEM(4);
+      }
+#undef DASM_TMA_SMEM
+    return (size_t)-1;
+  }
+
+  size_t
+  tma_fdm_smem(int k, int esize)
+  {
+#define DASM_TMA_SMEM(K) (esize == 8 ? TmaGeom<K, double>::smem_bytes(1, true, 2) : TmaGeom<K, float>::smem_bytes(1, true, 2))
+    switch (k)
+      {
+        case 2:
+          return DASM_TMA_SMEM(2);
+        case 3:
+          return DASM_TMA_SMEM(3);
+        case 4:
+          return DASM_TMA_SMEM(4);
+      }
+#undef DASM_TMA_SMEM
+    return (size_t)-1;
+  }
+
+  template <int K, typename T>
+  static void
+  launch_laplace_tma_k(cudaStream_t stream, int grid, const T *src, T *dst, T *acc, const Epilogue<T> &epi, const double (*P)[25],
+                       const double (*Q)[25], const TmaMaps &maps, int shared_mode, const NextInit<T> &ni, const TmaList &list, int dbg)
+  {
+    using G = TmaGeom<K, T>;
+    FastLaplaceMats<T, K + 1> mats;
+    eo_fill(mats.M, P[0], Q[0]);
+    eo_fill(mats.K0, P[1], Q[1]);
+    eo_fill(mats.K1, P[2], Q[2]);
+    eo_fill(mats.K2, P[3], Q[3]);
+    constexpr size_t smem = G::smem_bytes(2, false, 1);
+    auto             kern = laplace_tma_kernel<K, T>;
+    check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "laplace_tma_kernel attribute");
+    const FastMaps fm = {nullptr, nullptr, nullptr, nullptr, 0, nullptr, dbg};
+    kern<<<grid, G::NT, smem, stream>>>(src, dst, acc, epi, mats, maps, shared_mode, ni, list, fm);
+    check(cudaGetLastError(), "laplace_tma_kernel launch");
+  }
+
+  template <int K, typename T>
+  static void
+  launch_fdm_tma_k(cudaStream_t stream, int grid, const T *src, T *dst, T *acc, const Epilogue<T> &epi, const double (*P)[25],
+                   const double (*Q)[25], const double *inv, const TmaMaps &maps, int shared_mode, const NextInit<T> &ni,
+                   const TmaList &list, int dbg)
+  {
+    using G         = TmaGeom<K, T>;
+    constexpr int n = K + 1;
+    FastFdmMats<T, n> mats;
+    eo_fill(mats.Ax, P[0], Q[0]);
+    eo_fill(mats.Ay, P[1], Q[1]);
+    eo_fill(mats.Az, P[2], Q[2]);
+    eo_fill(mats.Bx, P[3], Q[3]);
+    eo_fill(mats.By, P[4], Q[4]);
+    eo_fill(mats.Bz, P[5], Q[5]);
+    for (int i = 0; i < n * n * n; ++i)
+      mats.inv[i] = (T)inv[i];
+    constexpr size_t smem = G::smem_bytes(1, true, 2);
+    auto             kern = fdm_tma_kernel<K, T>;
+    check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "fdm_tma_kernel attribute");
+    const FastMaps fm = {nullptr, nullptr, nullptr, nullptr, 0, nullptr, dbg};
+    kern<<<grid, G::NT, smem, stream>>>(src, dst, acc, epi, mats, maps, shared_mode, ni, list, fm);
+    check(cudaGetLastError(), "fdm_tma_kernel launch");
+  }
+
+  template <typename T>
+  void
+  launch_laplace_tma(int k, cudaStream_t stream, int grid, const T *src, T *dst, T *acc, const Epilogue<T> &epi, const double (*P)[25],
+                     const double (*Q)[25], const TmaMaps &maps, int shared_mode, const NextInit<T> &ni, const TmaList &list, int dbg)
+  {
+    switch (k)
+      {
+        case 2:
+          return launch_laplace_tma_k<2, T>(stream, grid, src, dst, acc, epi, P, Q, maps, shared_mode, ni, list, dbg);
+        case 3:
+          return launch_laplace_tma_k<3, T>(stream, grid, src, dst, acc, epi, P, Q, maps, shared_mode, ni, list, dbg);
+        case 4:
+          return launch_laplace_tma_k<4, T>(stream, grid, src, dst, acc, epi, P, Q, maps, shared_mode, ni, list, dbg);
+      }
+    throw std::runtime_error("laplace_tma_kernel: degree not instantiated");
+  }
+
+  template <typename T>
+  void
+  launch_fdm_tma(int k, cudaStream_t stream, int grid, const T *src, T *dst, T *acc, const Epilogue<T> &epi, const double (*P)[25],
+                 const double (*Q)[25], const double *inv, const TmaMaps &maps, int shared_mode, const NextInit<T> &ni, const TmaList &list,
+                 int dbg)
+  {
+    switch (k)
+      {
+        case 2:
+          return launch_fdm_tma_k<2, T>(stream, grid, src, dst, acc, epi, P, Q, inv, maps, shared_mode, ni, list, dbg);
+        case 3:
+          return launch_fdm_tma_k<3, T>(stream, grid, src, dst, acc, epi, P, Q, inv, maps, shared_mode, ni, list, dbg);
+        case 4:
+          return launch_fdm_tma_k<4, T>(stream, grid, src, dst, acc, epi, P, Q, inv, maps, shared_mode, ni, list, dbg);
+      }
+    throw std::runtime_error("fdm_tma_kernel: degree not instantiated");
+  }
+
+  template void launch_laplace_tma<double>(int, cudaStream_t, int, const double *, double *, double *, const Epilogue<double> &,
+                                           const double (*)[25], const double (*)[25], const TmaMaps &, int, const NextInit<double> &,
+                                           const TmaList &, int);
+  template void launch_laplace_tma<float>(int, cudaStream_t, int, const float *, float *, float *, const Epilogue<float> &,
+                                          const double (*)[25], const double (*)[25], const TmaMaps &, int, const NextInit<float> &,
+                                          const TmaList &, int);
+  template void launch_fdm_tma<double>(int, cudaStream_t, int, const double *, double *, double *, const Epilogue<double> &,
+                                       const double (*)[25], const double (*)[25], const double *, const TmaMaps &, int,
+                                       const NextInit<double> &, const TmaList &, int);
+  template void launch_fdm_tma<float>(int, cudaStream_t, int, const float *, float *, float *, const Epilogue<float> &, const double (*)[25],
+                                      const double (*)[25], const double *, const TmaMaps &, int, const NextInit<float> &, const TmaList &,
+                                      int);
+} // namespace dasm
