@@ -90,12 +90,12 @@ namespace dasm
     static constexpr int NFM    = (NFOR + NMT - 1) / NMT;
     static constexpr int NSI    = (NSH + NMT - 1) / NMT;
     static constexpr int XSLOT  = pad(NCELLS * CS);
-    // shared memory: (alignment slack, 128 B) barriers + descriptor (128 B) | tile | X slots (n_x; Laplace: the output box aliases the first one)
+    // shared memory: (alignment slack, 1 KB) barriers + descriptor (1 KB) | tile | X slots (n_x; Laplace: the output box aliases the first one)
     //                | [output box] | output faces | operand boxes (n_ops)
     static constexpr size_t
     smem_bytes(const int n_x, const bool separate_out, const int n_ops)
     {
-      return 256 + (size_t)(TILE + n_x * XSLOT + (separate_out ? pad(NB) : 0) + NFORP + n_ops * pad(NB)) * sizeof(T);
+      return 2048 + (size_t)(TILE + n_x * XSLOT + (separate_out ? pad(NB) : 0) + NFORP + n_ops * pad(NB)) * sizeof(T);
     }
     // tile offset of the j-th foreign point
     __host__ __device__ static constexpr int
@@ -132,6 +132,48 @@ namespace dasm
     }
   };
 
+  // Layout of a box [0, R)^3 in shared memory (tile main region, output box).  Natural: row (Y, Z) of R elements at
+  // (Y + R Z) R.  k = 4: a cell row is 4 elements and the rows of the four cells (cx, cy = 0..3) a quarter-warp reads with
+  // one 16-byte load per lane must cover all 32 banks:
+  //   PERM  the rows are stored in the order rho = ((Y >> 2) & 1) + 2 (Y & 3) + 8 (Y >> 3) + 16 Z, i.e. the rows Y and Y + 4
+  //         (cells cy and cy + 1) are adjacent; the tensor map enumerates the box as (x, (Y>>2)&1, Y&3, (Y>>3) + 2 Z) to make
+  //         the TMA engine write it that way.  float: the two adjacent 64-byte rows are one 128-byte line: conflict-free.
+  //   SWZ   double (128-byte rows): additionally the 16-byte chunks of a row are XOR-ed with rho & 7 (the 128-byte swizzle
+  //         mode of the tensor map, CuTe Swizzle<3,4,3>): the lanes (cx, cy & 1) hit the 8 different chunks.
+  template <int k, typename T>
+  struct TmaLayout
+  {
+    static constexpr bool PERM = (k == 4);
+    static constexpr bool SWZ  = (k == 4 && sizeof(T) == 8);
+    static constexpr int  R    = 4 * k;
+    __host__ __device__ static constexpr int
+    row(const int Y, const int Z)
+    {
+      return PERM ? ((Y >> 2) & 1) + 2 * (Y & 3) + 8 * (Y >> 3) + 16 * Z : Y + R * Z;
+    }
+    __host__ __device__ static constexpr int
+    row_y(const int rho) // inverse: Y of a row
+    {
+      return PERM ? (((rho & 1) << 2) | ((rho >> 1) & 3) | (rho & 8)) : rho % R;
+    }
+    __host__ __device__ static constexpr int
+    row_z(const int rho)
+    {
+      return PERM ? (rho >> 4) : rho / R;
+    }
+    __host__ __device__ static constexpr int
+    swz(const int rho)
+    {
+      return SWZ ? (rho & 7) : 0;
+    }
+    // element offset of column X in a row with swizzle s
+    __host__ __device__ static constexpr int
+    col(const int X, const int s)
+    {
+      return SWZ ? ((((X >> 1) ^ s) << 1) | (X & 1)) : X;
+    }
+  };
+
   // ---- TMA primitives ------------------------------------------------------------------------------------------------------
   __device__ __forceinline__ void
   tma_load_4d(const unsigned dst, const CUtensorMap *map, const int c0, const int c1, const int c2, const int c3, const unsigned mbar)
@@ -152,7 +194,7 @@ namespace dasm
     const bool     mode0   = desc[1] == 0u;
     constexpr unsigned ES  = (unsigned)sizeof(T);
     mbar_expect_tx(mbar, mode0 ? G::BYTES_MAIN + G::BYTES_FOR : G::BYTES_MAIN);
-    tma_load_4d(t0 + G::O_MAIN * ES, &maps.main, 0, 0, 0, (int)(base / G::NB), mbar);
+    tma_load_4d(t0 + G::O_MAIN * ES, &maps.main, 0, 0, 0, (int)(base / G::NB) * (TmaLayout<k, T>::PERM ? 32 : 1), mbar);
     if (mode0)
       {
         tma_load_4d(t0 + G::O_FX * ES, &maps.fx, 0, 0, 0, (int)(desc[2] / G::NB), mbar);
@@ -193,12 +235,14 @@ namespace dasm
       }
   }
 
-  // per-thread addressing of a cell plane in the tile: rows r = 0..k (stride rs for r < k, separate offset for r = k when it
-  // lies on the upper face of the brick), each row x = 0..k-1 contiguous and x = k through a second set of offsets
+  // per-thread addressing of a cell plane in the tile / output box: rows r = 0..k (row r < k starts at r0 + r rs, row k at rk;
+  // the x position inside a row depends on the layout and the row's swizzle (s0 ^ (r SX)) & sm, sk), and the point x = k of
+  // the cells cx = 3 (owned by the +x neighbours) through a second set of offsets
   struct PlaneAddr
   {
-    int r0, rs, rk; // row r < k at r0 + r rs, row k at rk
-    int x0, xs, xk; // point x = k of row r < k at x0 + r xs, of row k at xk
+    int r0, rs, rk;
+    int x0, xs, xk;
+    int s0, sm, sk;
   };
 
   // Laplace phase A: plane y = t of cell (cx, cy, cz), rows z
@@ -207,16 +251,21 @@ namespace dasm
   tile_plane_y(const int cx, const int cy, const int cz, const int t)
   {
     using G       = TmaGeom<k, T>;
+    using L       = TmaLayout<k, T>;
     constexpr int R = G::R, XW = G::XW;
     const int     Y = k * cy + t, Z0 = k * cz;
-    const bool    yR = (Y == R), xR = (cx == 3), zR = (cz == 3);
+    const bool    yR = (Y == R), zR = (cz == 3);
     PlaneAddr     a;
-    a.r0 = (yR ? G::O_FY + Z0 * R : G::O_MAIN + (Z0 * R + Y) * R) + k * cx;
+    a.r0 = yR ? G::O_FY + Z0 * R : G::O_MAIN + L::row(Y, Z0) * R;
     a.rs = yR ? R : R * R;
-    a.rk = zR ? (yR ? G::O_EYZ : G::O_FZ + Y * R) + k * cx : a.r0 + k * a.rs;
-    a.x0 = xR ? (yR ? G::O_EXY + Z0 * XW : G::O_FX + (Z0 * R + Y) * XW) : a.r0 + k;
-    a.xs = xR ? (yR ? XW : R * XW) : a.rs;
-    a.xk = xR ? (zR ? (yR ? G::O_C : G::O_EXZ + Y * XW) : a.x0 + k * a.xs) : a.rk + k;
+    a.s0 = yR ? 0 : L::swz(L::row(Y, 0));
+    a.sm = yR ? 0 : 7;
+    a.rk = zR ? (yR ? G::O_EYZ : G::O_FZ + Y * R) : a.r0 + k * a.rs;
+    a.sk = zR ? 0 : a.s0;
+    a.x0 = yR ? G::O_EXY + Z0 * XW : G::O_FX + (Z0 * R + Y) * XW;
+    a.xs = yR ? XW : R * XW;
+    a.xk = zR ? (yR ? G::O_C : G::O_EXZ + Y * XW) : a.x0 + k * a.xs;
+    (void)cx;
     return a;
   }
 
@@ -226,36 +275,83 @@ namespace dasm
   tile_plane_z(const int cx, const int cy, const int cz, const int t)
   {
     using G       = TmaGeom<k, T>;
+    using L       = TmaLayout<k, T>;
     constexpr int R = G::R, XW = G::XW;
     const int     Z = k * cz + t, Y0 = k * cy;
-    const bool    zR = (Z == R), xR = (cx == 3), yR = (cy == 3);
+    const bool    zR = (Z == R), yR = (cy == 3);
     PlaneAddr     a;
-    a.r0 = (zR ? G::O_FZ + Y0 * R : G::O_MAIN + (Z * R + Y0) * R) + k * cx;
-    a.rs = R;
-    a.rk = yR ? (zR ? G::O_EYZ : G::O_FY + Z * R) + k * cx : a.r0 + k * R;
-    a.x0 = xR ? (zR ? G::O_EXZ + Y0 * XW : G::O_FX + (Z * R + Y0) * XW) : a.r0 + k;
-    a.xs = xR ? XW : R;
-    a.xk = xR ? (yR ? (zR ? G::O_C : G::O_EXY + Z * XW) : a.x0 + k * XW) : a.rk + k;
+    a.r0 = zR ? G::O_FZ + Y0 * R : G::O_MAIN + L::row(Y0, Z) * R;
+    a.rs = zR ? R : (L::PERM ? 2 * R : R);
+    a.s0 = zR ? 0 : L::swz(L::row(Y0, 0));
+    a.sm = zR ? 0 : 7;
+    a.rk = yR ? (zR ? G::O_EYZ : G::O_FY + Z * R) : (zR ? a.r0 + k * R : G::O_MAIN + L::row(Y0 + k, Z) * R);
+    a.sk = (yR || zR) ? 0 : L::swz(L::row(Y0 + k, 0));
+    a.x0 = zR ? G::O_EXZ + Y0 * XW : G::O_FX + (Z * R + Y0) * XW;
+    a.xs = XW;
+    a.xk = yR ? (zR ? G::O_C : G::O_EXY + Z * XW) : a.x0 + k * XW;
+    (void)cx;
     return a;
   }
 
-  // output of plane z = t (rows y): the own box at `box`, the points owned by the upper neighbours in face order at `ofor`;
-  // offsets relative to box, with ofor = box + ofo
+  // the n values of row r of a cell plane (SX: swizzle increment per row: 0 for rows z, 2 for rows y)
+  template <int k, typename T, int SX>
+  __device__ __forceinline__ void
+  plane_load_row(T (&v)[k + 1], const T *tile, const PlaneAddr &a, const int r, const int cx)
+  {
+    using L        = TmaLayout<k, T>;
+    const int rowo = r < k ? a.r0 + r * a.rs : a.rk;
+    const int sw   = r < k ? ((a.s0 ^ (r * SX)) & a.sm) : a.sk;
+    if constexpr (L::SWZ)
+      {
+        const double2 p0 = *reinterpret_cast<const double2 *>(tile + rowo + (((2 * cx) ^ sw) << 1));
+        const double2 p1 = *reinterpret_cast<const double2 *>(tile + rowo + (((2 * cx + 1) ^ sw) << 1));
+        v[0]             = p0.x;
+        v[1]             = p0.y;
+        v[2]             = p1.x;
+        v[3]             = p1.y;
+        v[4]             = (cx == 3) ? tile[r < k ? a.x0 + r * a.xs : a.xk] : tile[rowo + (((2 * cx + 2) ^ sw) << 1)];
+      }
+    else if constexpr (L::PERM)
+      {
+        const float4 p0 = *reinterpret_cast<const float4 *>(tile + rowo + 4 * cx);
+        v[0]            = p0.x;
+        v[1]            = p0.y;
+        v[2]            = p0.z;
+        v[3]            = p0.w;
+        v[4]            = (cx == 3) ? tile[r < k ? a.x0 + r * a.xs : a.xk] : tile[rowo + 4 * cx + 4];
+      }
+    else
+      {
+        const T *row = tile + rowo + k * cx;
+#pragma unroll
+        for (int x = 0; x < k; ++x)
+          v[x] = row[x];
+        v[k] = (cx == 3) ? tile[r < k ? a.x0 + r * a.xs : a.xk] : row[k];
+      }
+  }
+
+  // output of plane z = t (rows y): the own box at `box` (layout TmaLayout), the points owned by the upper neighbours in
+  // face order at `ofor` = box + ofo (natural)
   template <int k, typename T>
   __device__ __forceinline__ PlaneAddr
   out_plane_z(const int cx, const int cy, const int cz, const int t, const int ofo)
   {
     using G       = TmaGeom<k, T>;
+    using L       = TmaLayout<k, T>;
     constexpr int R = G::R;
-    const int     Z = k * cz + t, Y0 = k * cy, X0 = k * cx;
+    const int     Z = k * cz + t, Y0 = k * cy;
     const bool    zR = (Z == R);
     PlaneAddr     a;
-    a.r0 = zR ? ofo + G::J_FZ + Y0 * R + X0 : (Z * R + Y0) * R + X0;
-    a.rs = R;
-    a.rk = zR ? ofo + G::J_EYZ + X0 : ofo + G::J_FY + Z * R + X0; // only used for cy == 3
-    a.x0 = zR ? ofo + G::J_EXZ + Y0 : ofo + Z * R + Y0;           // only used for cx == 3
+    a.r0 = zR ? ofo + G::J_FZ + Y0 * R : L::row(Y0, Z) * R;
+    a.rs = zR ? R : (L::PERM ? 2 * R : R);
+    a.s0 = zR ? 0 : L::swz(L::row(Y0, 0));
+    a.sm = zR ? 0 : 7;
+    a.rk = zR ? ofo + G::J_EYZ : ofo + G::J_FY + Z * R; // only used for cy == 3
+    a.sk = 0;
+    a.x0 = zR ? ofo + G::J_EXZ + Y0 : ofo + Z * R + Y0; // only used for cx == 3
     a.xs = 1;
     a.xk = zR ? ofo + G::J_C : ofo + G::J_EXY + Z; // cx == 3 and cy == 3
+    (void)cx;
     return a;
   }
 
@@ -263,18 +359,36 @@ namespace dasm
   __device__ __forceinline__ void
   tma_out_store(const T (&r)[k + 1][k + 1], T *box, const PlaneAddr &a, const int cx, const int cy)
   {
+    using L = TmaLayout<k, T>;
 #pragma unroll
-    for (int y = 0; y <= k; ++y)
+    for (int y = 0; y < k; ++y)
+      {
+        const int rowo = a.r0 + y * a.rs;
+        const int sw   = (a.s0 ^ (2 * y)) & a.sm;
+        if constexpr (L::SWZ)
+          {
+            *reinterpret_cast<double2 *>(box + rowo + (((2 * cx) ^ sw) << 1))     = make_double2(r[y][0], r[y][1]);
+            *reinterpret_cast<double2 *>(box + rowo + (((2 * cx + 1) ^ sw) << 1)) = make_double2(r[y][2], r[y][3]);
+          }
+        else if constexpr (L::PERM)
+          *reinterpret_cast<float4 *>(box + rowo + 4 * cx) = make_float4(r[y][0], r[y][1], r[y][2], r[y][3]);
+        else
+          {
 #pragma unroll
-      for (int x = 0; x <= k; ++x)
-        {
-          const bool w = (x < k || cx == 3) && (y < k || cy == 3);
-          if (w)
-            {
-              const int o = (x < k) ? ((y < k) ? a.r0 + y * a.rs + x : a.rk + x) : ((y < k) ? a.x0 + y * a.xs : a.xk);
-              box[o]      = r[y][x];
-            }
-        }
+            for (int x = 0; x < k; ++x)
+              box[rowo + k * cx + x] = r[y][x];
+          }
+        if (cx == 3)
+          box[a.x0 + y * a.xs] = r[y][k];
+      }
+    if (cy == 3)
+      {
+#pragma unroll
+        for (int x = 0; x < k; ++x)
+          box[a.rk + k * cx + x] = r[k][x];
+        if (cx == 3)
+          box[a.xk] = r[k][k];
+      }
   }
 
   // ---- mover side ------------------------------------------------------------------------------------------------------------
@@ -342,10 +456,13 @@ namespace dasm
 #pragma unroll 4
     for (int p = m; p < G::NB / V; p += G::NMT)
       {
-        const int i = p * V;
-        const int X = i % R, Y = (i / R) % R, Z = i / (R * R);
+        // p: physical 16-byte chunk of the output box; (X, Y, Z): its first point; i: index in the brick's box / operand boxes
+        using L       = TmaLayout<k, T>;
+        const int rho = p / (R / V);
+        const int X = ((p % (R / V)) ^ L::swz(rho)) * V, Y = L::row_y(L::PERM ? (rho & 15) : rho), Z = L::row_z(rho);
+        const int i = X + R * (Y + R * Z);
         T         y[V], a[V], b[V], res[V];
-        *reinterpret_cast<VT *>(y) = *reinterpret_cast<const VT *>(out + i);
+        *reinterpret_cast<VT *>(y) = *reinterpret_cast<const VT *>(out + p * V);
         if (Y == 0 || Z == 0)
           {
             if (!skip_red)
@@ -512,12 +629,12 @@ namespace dasm
     constexpr int NFT = G::NFT;
     extern __shared__ __align__(16) unsigned char smem_dyn[];
     // TMA destinations must be 128-byte aligned
-    unsigned char *smem_raw = smem_dyn + ((128u - ((unsigned)__cvta_generic_to_shared(smem_dyn) & 127u)) & 127u);
+    unsigned char *smem_raw = smem_dyn + ((1024u - ((unsigned)__cvta_generic_to_shared(smem_dyn) & 1023u)) & 1023u);
     // [0] mbarrier of the tile, [8] mbarrier of the operand staging, [16..] descriptor of the next brick
     const unsigned mb_tile = (unsigned)__cvta_generic_to_shared(smem_raw);
     const unsigned mb_ops  = mb_tile + 8;
     uint32_t *     s_desc  = reinterpret_cast<uint32_t *>(smem_raw + 16);
-    T *            tile    = reinterpret_cast<T *>(smem_raw + 128);
+    T *            tile    = reinterpret_cast<T *>(smem_raw + 1024); // 1024-byte aligned: the swizzle pattern of the TMA engine
     T *            Xq      = tile + G::TILE;
     T *            Xp      = Xq + G::XSLOT;
     T *            out     = Xq; // the output box aliases the first exchange slot (written after all reads of it)
@@ -594,12 +711,8 @@ namespace dasm
 #pragma unroll
             for (int z = 0; z < n; ++z)
               {
-                T         v[n];
-                const T * row = tile + (z < k ? pa.r0 + z * pa.rs : pa.rk);
-#pragma unroll
-                for (int x = 0; x < k; ++x)
-                  v[x] = row[x];
-                v[k] = tile[z < k ? pa.x0 + z * pa.xs : pa.xk];
+                T v[n];
+                plane_load_row<k, T, 0>(v, tile, pa, z, cx);
                 mat_vec<n, T, true, true, false>(a[z], mats.M, v);
                 mat_vec<n, T, true, true, false>(b[z], mats.K0, v);
               }
@@ -702,11 +815,11 @@ namespace dasm
     constexpr int n   = k + 1;
     constexpr int NFT = G::NFT;
     extern __shared__ __align__(16) unsigned char smem_dyn[];
-    unsigned char *smem_raw = smem_dyn + ((128u - ((unsigned)__cvta_generic_to_shared(smem_dyn) & 127u)) & 127u);
+    unsigned char *smem_raw = smem_dyn + ((1024u - ((unsigned)__cvta_generic_to_shared(smem_dyn) & 1023u)) & 1023u);
     const unsigned mb_tile = (unsigned)__cvta_generic_to_shared(smem_raw);
     const unsigned mb_ops  = mb_tile + 8;
     uint32_t *     s_desc  = reinterpret_cast<uint32_t *>(smem_raw + 16);
-    T *            tile    = reinterpret_cast<T *>(smem_raw + 128);
+    T *            tile    = reinterpret_cast<T *>(smem_raw + 1024); // 1024-byte aligned: the swizzle pattern of the TMA engine
     T *            X       = tile + G::TILE;
     T *            out     = X + G::XSLOT;
     T *            ofor    = out + G::pad(G::NB);
@@ -785,12 +898,8 @@ namespace dasm
 #pragma unroll
             for (int y = 0; y < n; ++y)
               {
-                T        v[n];
-                const T *row = tile + (y < k ? pa.r0 + y * pa.rs : pa.rk);
-#pragma unroll
-                for (int x = 0; x < k; ++x)
-                  v[x] = row[x];
-                v[k] = tile[y < k ? pa.x0 + y * pa.xs : pa.xk];
+                T v[n];
+                plane_load_row<k, T, 2>(v, tile, pa, y, cx);
                 mat_vec<n, T, true, false, false>(a[y], mats.Ax, v);
               }
 #pragma unroll

@@ -76,8 +76,26 @@ namespace dasm
                   {&out.exz, {(cuuint32_t)XW, (cuuint32_t)R, 1, 1}},
                   {&out.eyz, {(cuuint32_t)R, 1, 1, 1}},
                   {&out.cxyz, {(cuuint32_t)XW, 1, 1, 1}}};
+    if (k == 4)
+      {
+        // TmaLayout PERM: the box enumerated as (x, (Y>>2)&1, Y&3, (Y>>3) + 2 Z + 32 brick); double: 128-byte swizzle
+        const cuuint64_t row        = R * esize;
+        const cuuint64_t pdims[4]   = {R, 2, 4, (cuuint64_t)(32 * n_lex)};
+        const cuuint64_t pstr[3]    = {4 * row, row, 8 * row};
+        const cuuint32_t pbox[4]    = {(cuuint32_t)R, 2, 4, 32};
+        const CUresult   r = fn(&out.main, dt, 4, const_cast<void *>(vec), pdims, pstr, pbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              esize == 8 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS)
+          {
+            err = "cuTensorMapEncodeTiled (permuted box) failed with code " + std::to_string((int)r);
+            return false;
+          }
+      }
     for (auto &s : specs)
       {
+        if (k == 4 && s.m == &out.main)
+          continue;
         const CUresult r = fn(s.m, dt, 4, const_cast<void *>(vec), dims, strides, s.box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS)
