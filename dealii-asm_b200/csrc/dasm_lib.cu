@@ -869,7 +869,11 @@ launch_laplace_fast(dasm_op *op, T *dst, const T *src, const Epilogue<T> &epi, c
         return false;
       const int     grid = std::min(count, std::max(1, op->n_sm - reserve_sms));
       const TmaList list = {op->d_tma_lap + first, op->d_tma_foreign, count, op->tma_any_mode1};
-      launch_laplace_tma<T>(K, op->ctx->stream, grid, src, dst, (T *)op->d_acc, epi, op->lap_P, op->lap_Q, *tm, shared_mode, ni, list, fast_dbg());
+      const TmaMaps *o0 = epi.v0 ? tma_maps_for(op, epi.v0) : tm;
+      if (o0 == nullptr)
+        return false;
+      launch_laplace_tma<T>(K, op->ctx->stream, grid, src, dst, (T *)op->d_acc, epi, op->lap_P, op->lap_Q, *tm, o0->main, shared_mode, ni, list,
+                            fast_dbg());
       op->ctx->launches++;
       return true;
     }
@@ -1112,8 +1116,11 @@ launch_fdm_fast(dasm_fdm *f, T *dst, const T *src, const Epilogue<T> &epi, const
         return false;
       const int     grid = std::min(count, std::max(1, op->n_sm - reserve_sms));
       const TmaList list = {f->d_tma_list + first, op->d_tma_foreign, count, f->tma_any_mode1};
-      launch_fdm_tma<T>(K, op->ctx->stream, grid, src, dst, (T *)op->d_acc, epi, f->fast_P, f->fast_Q, f->fast_inv, *tm, shared_mode, ni, list,
-                        fast_dbg());
+      const TmaMaps *o0 = epi.v0 ? tma_maps_for(op, epi.v0) : tm, *o1 = epi.v1 ? tma_maps_for(op, epi.v1) : tm;
+      if (o0 == nullptr || o1 == nullptr)
+        return false;
+      launch_fdm_tma<T>(K, op->ctx->stream, grid, src, dst, (T *)op->d_acc, epi, f->fast_P, f->fast_Q, f->fast_inv, *tm, o0->main, o1->main,
+                        shared_mode, ni, list, fast_dbg());
       op->ctx->launches++;
       return true;
     }

@@ -54,7 +54,7 @@ namespace dasm
     static constexpr int NB     = R * R * R;
     static constexpr int NCELLS = 64;
     static constexpr int NCT    = NCELLS * n;
-    static constexpr int NMT    = 64;
+    static constexpr int NMT    = 32;
     static constexpr int NT     = NCT + NMT;
     static constexpr int CS     = (n * n * n) | 1;
     static constexpr int V      = 16 / (int)sizeof(T); // elements per 16-byte vector
@@ -90,13 +90,6 @@ namespace dasm
     static constexpr int NFM    = (NFOR + NMT - 1) / NMT;
     static constexpr int NSI    = (NSH + NMT - 1) / NMT;
     static constexpr int XSLOT  = pad(NCELLS * CS);
-    // shared memory: (alignment slack, 1 KB) barriers + descriptor (1 KB) | tile | X slots (n_x; Laplace: the output box aliases the first one)
-    //                | [output box] | output faces | operand boxes (n_ops)
-    static constexpr size_t
-    smem_bytes(const int n_x, const bool separate_out, const int n_ops)
-    {
-      return 2048 + (size_t)(TILE + n_x * XSLOT + (separate_out ? pad(NB) : 0) + NFORP + n_ops * pad(NB)) * sizeof(T);
-    }
     // tile offset of the j-th foreign point
     __host__ __device__ static constexpr int
     foreign_tile_offset(const int j)
@@ -330,285 +323,270 @@ namespace dasm
       }
   }
 
-  // output of plane z = t (rows y): the own box at `box` (layout TmaLayout), the points owned by the upper neighbours in
-  // face order at `ofor` = box + ofo (natural)
-  template <int k, typename T>
-  __device__ __forceinline__ PlaneAddr
-  out_plane_z(const int cx, const int cy, const int cz, const int t, const int ofo)
+
+  // ---- fused vector epilogue from the registers of the compute threads ------------------------------------------------------
+  // After the merge every thread (cell, plane z = t) holds the FINAL values of its exclusive points x < k (or x <= k for
+  // cx = 3), y < k (or y <= k for cy = 3) of the plane Z = k cz + t.  Points inside the own box and off the shared lower
+  // faces are private: epilogue with the operands from the (TMA-staged) operand boxes in shared memory and plain global
+  // stores straight from the registers.  Points on X = 0, Y = 0 or Z = 0 of the own box, and the points owned by the 7 upper
+  // neighbours (X = R, Y = R or Z = R), get red.global.add of alpha y (shared-face protocol of kernels_brick.cuh).
+  template <typename T, int KIND, bool TWO>
+  __device__ __forceinline__ T
+  epi_value(const T y, const T a, const T b, const T f1, const T f2)
   {
-    using G       = TmaGeom<k, T>;
-    using L       = TmaLayout<k, T>;
-    constexpr int R = G::R;
-    const int     Z = k * cz + t, Y0 = k * cy;
-    const bool    zR = (Z == R);
-    PlaneAddr     a;
-    a.r0 = zR ? ofo + G::J_FZ + Y0 * R : L::row(Y0, Z) * R;
-    a.rs = zR ? R : (L::PERM ? 2 * R : R);
-    a.s0 = zR ? 0 : L::swz(L::row(Y0, 0));
-    a.sm = zR ? 0 : 7;
-    a.rk = zR ? ofo + G::J_EYZ : ofo + G::J_FY + Z * R; // only used for cy == 3
-    a.sk = 0;
-    a.x0 = zR ? ofo + G::J_EXZ + Y0 : ofo + Z * R + Y0; // only used for cx == 3
-    a.xs = 1;
-    a.xk = zR ? ofo + G::J_C : ofo + G::J_EXY + Z; // cx == 3 and cy == 3
-    (void)cx;
-    return a;
+    if (KIND == EPI_RESIDUAL)
+      return a - y;
+    if (KIND == EPI_CHEB)
+      return a + f2 * y + f1 * (a - (TWO ? b : T(0)));
+    if (KIND == EPI_SCALE)
+      return f2 * y;
+    return y;
   }
 
-  template <int k, typename T>
-  __device__ __forceinline__ void
-  tma_out_store(const T (&r)[k + 1][k + 1], T *box, const PlaneAddr &a, const int cx, const int cy)
+  // global index of a point owned by upper neighbour q (0 +x, 1 +y, 2 +z, 3 +xy, 4 +xz, 5 +yz, 6 +xyz): box offset `off`
+  // in the neighbour's box (mode 0) or entry j of the brick's index list (mode 1)
+  __device__ __forceinline__ uint32_t
+  foreign_index(const uint32_t *desc, const uint32_t *__restrict__ lists, const int q, const int off, const int j)
   {
-    using L = TmaLayout<k, T>;
-#pragma unroll
-    for (int y = 0; y < k; ++y)
+    return desc[1] == 0u ? desc[2 + q] + (uint32_t)off : __ldg(lists + desc[9] + j);
+  }
+
+  template <int k, typename T, int KIND, bool TWO>
+  __device__ __forceinline__ void
+  tma_epilogue(const T (&r)[k + 1][k + 1], const T *ops0, const T *ops1, T *__restrict__ dst, T *__restrict__ sh_dst, const T sh_a, const T f1,
+               const T f2, const uint32_t *desc, const uint32_t *__restrict__ lists, const int cx, const int cy, const int cz, const int t)
+  {
+    using G         = TmaGeom<k, T>;
+    using L         = TmaLayout<k, T>;
+    constexpr int R = G::R;
+    const uint32_t  base = desc[0];
+    const int       Z = k * cz + t;
+    if (Z < R)
       {
-        const int rowo = a.r0 + y * a.rs;
-        const int sw   = (a.s0 ^ (2 * y)) & a.sm;
-        if constexpr (L::SWZ)
+        const bool zsh = (Z == 0);
+#pragma unroll
+        for (int y = 0; y < k; ++y)
           {
-            *reinterpret_cast<double2 *>(box + rowo + (((2 * cx) ^ sw) << 1))     = make_double2(r[y][0], r[y][1]);
-            *reinterpret_cast<double2 *>(box + rowo + (((2 * cx + 1) ^ sw) << 1)) = make_double2(r[y][2], r[y][3]);
+            const int      Y  = k * cy + y;
+            const uint32_t g  = base + (uint32_t)((Z * R + Y) * R + k * cx);
+            const bool     sh = zsh || (Y == 0);
+            if (sh)
+              {
+#pragma unroll
+                for (int x = 0; x < k; ++x)
+                  atomic_add(sh_dst + g + x, sh_a * r[y][x]);
+              }
+            else
+              {
+                T a[k], b[k], res[k];
+                if (KIND == EPI_RESIDUAL || KIND == EPI_CHEB)
+                  {
+                    const int rho = L::row(Y, Z), rowo = rho * R, sw = L::swz(rho);
+                    if constexpr (L::SWZ)
+                      {
+                        const double2 a0 = *reinterpret_cast<const double2 *>(ops0 + rowo + (((2 * cx) ^ sw) << 1));
+                        const double2 a1 = *reinterpret_cast<const double2 *>(ops0 + rowo + (((2 * cx + 1) ^ sw) << 1));
+                        a[0] = a0.x, a[1] = a0.y, a[2] = a1.x, a[3] = a1.y;
+                        if (TWO)
+                          {
+                            const double2 b0 = *reinterpret_cast<const double2 *>(ops1 + rowo + (((2 * cx) ^ sw) << 1));
+                            const double2 b1 = *reinterpret_cast<const double2 *>(ops1 + rowo + (((2 * cx + 1) ^ sw) << 1));
+                            b[0] = b0.x, b[1] = b0.y, b[2] = b1.x, b[3] = b1.y;
+                          }
+                      }
+                    else if constexpr (L::PERM)
+                      {
+                        const float4 a0 = *reinterpret_cast<const float4 *>(ops0 + rowo + 4 * cx);
+                        a[0] = a0.x, a[1] = a0.y, a[2] = a0.z, a[3] = a0.w;
+                        if (TWO)
+                          {
+                            const float4 b0 = *reinterpret_cast<const float4 *>(ops1 + rowo + 4 * cx);
+                            b[0] = b0.x, b[1] = b0.y, b[2] = b0.z, b[3] = b0.w;
+                          }
+                      }
+                    else
+                      {
+#pragma unroll
+                        for (int x = 0; x < k; ++x)
+                          {
+                            a[x] = ops0[rowo + k * cx + x];
+                            if (TWO)
+                              b[x] = ops1[rowo + k * cx + x];
+                          }
+                      }
+                  }
+#pragma unroll
+                for (int x = 0; x < k; ++x)
+                  res[x] = epi_value<T, KIND, TWO>(r[y][x], a[x], TWO ? b[x] : T(0), f1, f2);
+                if (cx == 0)
+                  {
+                    atomic_add(sh_dst + g, sh_a * r[y][0]);
+#pragma unroll
+                    for (int x = 1; x < k; ++x)
+                      dst[g + x] = res[x];
+                  }
+                else if constexpr (k == 4 && sizeof(T) == 8)
+                  {
+                    *reinterpret_cast<double2 *>(dst + g)     = make_double2(res[0], res[1]);
+                    *reinterpret_cast<double2 *>(dst + g + 2) = make_double2(res[2], res[3]);
+                  }
+                else if constexpr (k == 4 && sizeof(T) == 4)
+                  *reinterpret_cast<float4 *>(dst + g) = make_float4(res[0], res[1], res[2], res[3]);
+                else if constexpr (k == 2 && sizeof(T) == 8)
+                  *reinterpret_cast<double2 *>(dst + g) = make_double2(res[0], res[1]);
+                else
+                  {
+#pragma unroll
+                    for (int x = 0; x < k; ++x)
+                      dst[g + x] = res[x];
+                  }
+              }
+            if (cx == 3) // X = R: face of the +x neighbour
+              atomic_add(sh_dst + foreign_index(desc, lists, 0, R * (Y + R * Z), Z * R + Y), sh_a * r[y][k]);
           }
-        else if constexpr (L::PERM)
-          *reinterpret_cast<float4 *>(box + rowo + 4 * cx) = make_float4(r[y][0], r[y][1], r[y][2], r[y][3]);
-        else
+        if (cy == 3) // Y = R: face of the +y neighbour, edge of the +xy neighbour
           {
 #pragma unroll
             for (int x = 0; x < k; ++x)
-              box[rowo + k * cx + x] = r[y][x];
+              atomic_add(sh_dst + foreign_index(desc, lists, 1, k * cx + x + R * R * Z, G::J_FY + Z * R + k * cx + x), sh_a * r[k][x]);
+            if (cx == 3)
+              atomic_add(sh_dst + foreign_index(desc, lists, 3, R * R * Z, G::J_EXY + Z), sh_a * r[k][k]);
           }
-        if (cx == 3)
-          box[a.x0 + y * a.xs] = r[y][k];
       }
-    if (cy == 3)
+    else
       {
+        // Z = R (cz = 3, t = k): face of the +z neighbour, edges of +xz, +yz, corner of +xyz
 #pragma unroll
-        for (int x = 0; x < k; ++x)
-          box[a.rk + k * cx + x] = r[k][x];
-        if (cx == 3)
-          box[a.xk] = r[k][k];
-      }
-  }
-
-  // ---- mover side ------------------------------------------------------------------------------------------------------------
-  template <typename T>
-  struct Vec16;
-  template <>
-  struct Vec16<double>
-  {
-    typedef double2 type;
-  };
-  template <>
-  struct Vec16<float>
-  {
-    typedef float4 type;
-  };
-
-  template <int k, typename T>
-  struct TmaInitRegs
-  {
-    T a[TmaGeom<k, T>::NSI], b[TmaGeom<k, T>::NSI];
-  };
-
-  template <int k, typename T>
-  __device__ __forceinline__ void
-  tma_next_init_load(TmaInitRegs<k, T> &r, const NextInit<T> &ni, const uint32_t base, const int m)
-  {
-    using G       = TmaGeom<k, T>;
-    const bool h0 = (ni.out != nullptr) && ni.v0 != nullptr, h1 = (ni.out != nullptr) && (ni.v1 != nullptr && ni.f1 != T(0));
-#pragma unroll
-    for (int it = 0; it < G::NSI; ++it)
-      {
-        const int  s  = m + it * G::NMT;
-        const bool in = s < G::NSH;
-        const int  i  = G::shared_box_index(in ? s : 0);
-        r.a[it]       = (h0 && in) ? __ldg(ni.v0 + base + i) : T(0);
-        r.b[it]       = (h1 && in) ? __ldg(ni.v1 + base + i) : T(0);
-      }
-  }
-
-  template <int k, typename T>
-  __device__ __forceinline__ void
-  tma_next_init_store(const TmaInitRegs<k, T> &r, const NextInit<T> &ni, const uint32_t base, const int m)
-  {
-    using G = TmaGeom<k, T>;
-    if (ni.out == nullptr)
-      return;
-#pragma unroll
-    for (int it = 0; it < G::NSI; ++it)
-      {
-        const int s = m + it * G::NMT;
-        if (s < G::NSH)
-          ni.out[base + G::shared_box_index(s)] = r.a[it] + ni.f1 * (r.a[it] - r.b[it]);
-      }
-  }
-
-  // fused epilogue of the own box in box order.  KIND: EPI_*; TWO: the Chebyshev update reads x_old
-  template <int k, typename T, int KIND, bool TWO>
-  __device__ __forceinline__ void
-  tma_store_box(const T *out, const T *ops0, const T *ops1, T *__restrict__ d, T *__restrict__ sd, const T sh_a, const T f1, const T f2,
-                const int m, const bool skip_red)
-  {
-    using G  = TmaGeom<k, T>;
-    using VT = typename Vec16<T>::type;
-    constexpr int V = G::V, R = G::R;
-#pragma unroll 4
-    for (int p = m; p < G::NB / V; p += G::NMT)
-      {
-        // p: physical 16-byte chunk of the output box; (X, Y, Z): its first point; i: index in the brick's box / operand boxes
-        using L       = TmaLayout<k, T>;
-        const int rho = p / (R / V);
-        const int X = ((p % (R / V)) ^ L::swz(rho)) * V, Y = L::row_y(L::PERM ? (rho & 15) : rho), Z = L::row_z(rho);
-        const int i = X + R * (Y + R * Z);
-        T         y[V], a[V], b[V], res[V];
-        *reinterpret_cast<VT *>(y) = *reinterpret_cast<const VT *>(out + p * V);
-        if (Y == 0 || Z == 0)
+        for (int y = 0; y < k; ++y)
           {
-            if (!skip_red)
+            const int Y = k * cy + y;
 #pragma unroll
-              for (int e = 0; e < V; ++e)
-                atomic_add(sd + i + e, sh_a * y[e]);
-            continue;
+            for (int x = 0; x < k; ++x)
+              atomic_add(sh_dst + foreign_index(desc, lists, 2, k * cx + x + R * Y, G::J_FZ + Y * R + k * cx + x), sh_a * r[y][x]);
+            if (cx == 3)
+              atomic_add(sh_dst + foreign_index(desc, lists, 4, R * Y, G::J_EXZ + Y), sh_a * r[y][k]);
           }
-        if (KIND == EPI_RESIDUAL || KIND == EPI_CHEB)
-          *reinterpret_cast<VT *>(a) = *reinterpret_cast<const VT *>(ops0 + i);
-        if (KIND == EPI_CHEB && TWO)
-          *reinterpret_cast<VT *>(b) = *reinterpret_cast<const VT *>(ops1 + i);
-#pragma unroll
-        for (int e = 0; e < V; ++e)
+        if (cy == 3)
           {
-            if (KIND == EPI_RESIDUAL)
-              res[e] = a[e] - y[e];
-            else if (KIND == EPI_CHEB)
-              res[e] = a[e] + f2 * y[e] + f1 * (a[e] - (TWO ? b[e] : T(0)));
-            else if (KIND == EPI_SCALE)
-              res[e] = f2 * y[e];
-            else
-              res[e] = y[e];
-          }
-        if (X == 0)
-          {
-            if (!skip_red)
-              atomic_add(sd + i, sh_a * y[0]);
 #pragma unroll
-            for (int e = 1; e < V; ++e)
-              d[i + e] = res[e];
+            for (int x = 0; x < k; ++x)
+              atomic_add(sh_dst + foreign_index(desc, lists, 5, k * cx + x, G::J_EYZ + k * cx + x), sh_a * r[k][x]);
+            if (cx == 3)
+              atomic_add(sh_dst + foreign_index(desc, lists, 6, 0, G::J_C), sh_a * r[k][k]);
           }
-        else
-          *reinterpret_cast<VT *>(d + i) = *reinterpret_cast<const VT *>(res);
       }
   }
 
   template <int k, typename T>
   __device__ __forceinline__ void
-  tma_mover_loop(const T *out, const T *ofor, T *ops0, T *ops1, T *__restrict__ dst, T *__restrict__ acc, const Epilogue<T> &epi,
-                 const TmaList &list, const int shared_mode, const NextInit<T> &ni, const int m, const unsigned mbar, const FastMaps &dbgmaps)
+  tma_epilogue_dispatch(const T (&r)[k + 1][k + 1], const T *ops0, const T *ops1, T *__restrict__ dst, T *__restrict__ acc, const Epilogue<T> &epi,
+                        const int shared_mode, const uint32_t *desc, const uint32_t *__restrict__ lists, const int cx, const int cy,
+                        const int cz, const int t)
   {
-    using G           = TmaGeom<k, T>;
-    constexpr int NFM = G::NFM;
-    const bool need0  = (epi.kind == EPI_RESIDUAL || epi.kind == EPI_CHEB);
     const bool need1  = (epi.kind == EPI_CHEB && epi.f1 != T(0) && epi.v1 != nullptr);
     const T    alpha  = (epi.kind == EPI_RESIDUAL) ? T(-1) : ((epi.kind == EPI_CHEB || epi.kind == EPI_SCALE) ? epi.f2 : T(1));
     T *        sh_dst = (shared_mode == SHARED_DIRECT) ? dst : acc;
     const T    sh_a   = (shared_mode == SHARED_DIRECT) ? alpha : T(1);
-    const int  G1 = (int)gridDim.x;
-    int        it = blockIdx.x;
-    const uint32_t *dw = reinterpret_cast<const uint32_t *>(list.bricks);
-    // descriptor words of the current brick; base of the next one (operand staging)
-    uint32_t base = ldg_early(dw + (size_t)it * TMA_DW), mode = ldg_early(dw + (size_t)it * TMA_DW + 1);
-    uint32_t base_n = (it + G1 < list.n) ? ldg_early(dw + (size_t)(it + G1) * TMA_DW) : 0u;
-    unsigned phase  = 0;
-    auto     stage  = [&](const uint32_t b) {
-      if (m == 0 && need0)
-        {
-          constexpr unsigned bytes = (unsigned)(G::NB * sizeof(T));
-          mbar_expect_tx(mbar, need1 ? 2 * bytes : bytes);
-          bulk_load((unsigned)__cvta_generic_to_shared(ops0), epi.v0 + b, bytes, mbar);
-          if (need1)
-            bulk_load((unsigned)__cvta_generic_to_shared(ops1), epi.v1 + b, bytes, mbar);
-        }
-    };
-    stage(base);
-    for (; it < list.n; it += G1)
+    if (epi.kind == EPI_CHEB && need1)
+      tma_epilogue<k, T, EPI_CHEB, true>(r, ops0, ops1, dst, sh_dst, sh_a, epi.f1, epi.f2, desc, lists, cx, cy, cz, t);
+    else if (epi.kind == EPI_CHEB)
+      tma_epilogue<k, T, EPI_CHEB, false>(r, ops0, ops1, dst, sh_dst, sh_a, epi.f1, epi.f2, desc, lists, cx, cy, cz, t);
+    else if (epi.kind == EPI_RESIDUAL)
+      tma_epilogue<k, T, EPI_RESIDUAL, false>(r, ops0, ops1, dst, sh_dst, sh_a, epi.f1, epi.f2, desc, lists, cx, cy, cz, t);
+    else if (epi.kind == EPI_SCALE)
+      tma_epilogue<k, T, EPI_SCALE, false>(r, ops0, ops1, dst, sh_dst, sh_a, epi.f1, epi.f2, desc, lists, cx, cy, cz, t);
+    else
+      tma_epilogue<k, T, EPI_STORE, false>(r, ops0, ops1, dst, sh_dst, sh_a, epi.f1, epi.f2, desc, lists, cx, cy, cz, t);
+  }
+
+  // ---- mover warp: operand staging (tensor copies) and pre-initialisation of the next kernel's destination -------------------
+  enum
+  {
+    FB_OPS_EMPTY = 5 // compute -> mover: the operand boxes have been read
+  };
+
+  template <int k, typename T>
+  __device__ __forceinline__ void
+  tma_next_init(const NextInit<T> &ni, const uint32_t base, const int m)
+  {
+    using G = TmaGeom<k, T>;
+    if (ni.out == nullptr)
+      return;
+    const bool    h0 = ni.v0 != nullptr, h1 = (ni.v1 != nullptr && ni.f1 != T(0));
+    constexpr int B  = 12; // loads in flight per thread
+    for (int s0 = 0; s0 < G::NSH; s0 += B * G::NMT)
       {
-        const bool has_next = it + G1 < list.n;
-        // global indices of the points owned by the upper neighbours
-        uint32_t gf[NFM];
-        if (mode == 0u)
+        T a[B], b[B];
+#pragma unroll
+        for (int it = 0; it < B; ++it)
           {
-            uint32_t nb[7];
-#pragma unroll
-            for (int q = 0; q < 7; ++q)
-              nb[q] = ldg_early(dw + (size_t)it * TMA_DW + 2 + q);
-#pragma unroll
-            for (int jj = 0; jj < NFM; ++jj)
-              {
-                const int j  = m + jj * G::NMT;
-                const int jc = j < G::NFOR ? j : 0;
-                const int o  = G::foreign_owner(jc);
-                uint32_t  b  = nb[0];
-#pragma unroll
-                for (int q = 1; q < 7; ++q)
-                  b = (o == q) ? nb[q] : b;
-                gf[jj] = b + (uint32_t)G::foreign_box_offset(jc);
-              }
+            const int  s  = s0 + m + it * G::NMT;
+            const bool in = s < G::NSH;
+            const int  i  = G::shared_box_index(in ? s : 0);
+            a[it]         = (h0 && in) ? __ldg(ni.v0 + base + i) : T(0);
+            b[it]         = (h1 && in) ? __ldg(ni.v1 + base + i) : T(0);
           }
-        else
+#pragma unroll
+        for (int it = 0; it < B; ++it)
           {
-            const uint32_t lo = ldg_early(dw + (size_t)it * TMA_DW + 9);
-#pragma unroll
-            for (int jj = 0; jj < NFM; ++jj)
-              {
-                const int j = m + jj * G::NMT;
-                gf[jj]      = (j < G::NFOR) ? ldg_early(list.foreign + lo + j) : 0u;
-              }
+            const int s = s0 + m + it * G::NMT;
+            if (s < G::NSH)
+              ni.out[base + G::shared_box_index(s)] = a[it] + ni.f1 * (a[it] - b[it]);
           }
-        const uint32_t base_nn = (it + 2 * G1 < list.n) ? ldg_early(dw + (size_t)(it + 2 * G1) * TMA_DW) : 0u;
-        const uint32_t mode_n  = has_next ? ldg_early(dw + (size_t)(it + G1) * TMA_DW + 1) : 0u;
-        TmaInitRegs<k, T> nir;
-        tma_next_init_load<k, T>(nir, ni, base, m);
-        bar_sync(FB_OUT_FULL, G::NT); // the result of this brick is in the output box
-        if (need0)
-          mbar_wait(mbar, phase); // the bulk copies of the operands have landed
-        phase ^= 1u;
-        {
-          T *        d  = dst + base;
-          T *        sd = sh_dst + base;
-          const bool skip_red = (dbgmaps.dbg & 4) != 0;
-          if (dbgmaps.dbg & 2)
-            {
-            }
-          else if (epi.kind == EPI_CHEB && need1)
-            tma_store_box<k, T, EPI_CHEB, true>(out, ops0, ops1, d, sd, sh_a, epi.f1, epi.f2, m, skip_red);
-          else if (epi.kind == EPI_CHEB)
-            tma_store_box<k, T, EPI_CHEB, false>(out, ops0, ops1, d, sd, sh_a, epi.f1, epi.f2, m, skip_red);
-          else if (epi.kind == EPI_RESIDUAL)
-            tma_store_box<k, T, EPI_RESIDUAL, false>(out, ops0, ops1, d, sd, sh_a, epi.f1, epi.f2, m, skip_red);
-          else if (epi.kind == EPI_SCALE)
-            tma_store_box<k, T, EPI_SCALE, false>(out, ops0, ops1, d, sd, sh_a, epi.f1, epi.f2, m, skip_red);
-          else
-            tma_store_box<k, T, EPI_STORE, false>(out, ops0, ops1, d, sd, sh_a, epi.f1, epi.f2, m, skip_red);
-          // points owned by the upper neighbours
-#pragma unroll
-          for (int jj = 0; jj < NFM; ++jj)
-            {
-              const int j = m + jj * G::NMT;
-              if (j < G::NFOR && !skip_red)
-                atomic_add(sh_dst + gf[jj], sh_a * ofor[j]);
-            }
-        }
-        if (has_next)
-          bar_arrive(FB_OUT_EMPTY, G::NT);
-        tma_next_init_store<k, T>(nir, ni, base, m);
-        bar_sync(FB_MOVERS, G::NMT); // all movers have read the operands: stage those of the next brick
-        if (has_next)
-          stage(base_n);
-        base   = base_n;
-        base_n = base_nn;
-        mode   = mode_n;
       }
   }
+
+  template <int k, typename T>
+  __device__ __forceinline__ void
+  tma_mover_loop(T *ops0, T *ops1, const Epilogue<T> &epi, const CUtensorMap *map0, const CUtensorMap *map1, const TmaList &list,
+                 const NextInit<T> &ni, const int m, const unsigned mbar)
+  {
+    using G           = TmaGeom<k, T>;
+    const bool need0  = (epi.kind == EPI_RESIDUAL || epi.kind == EPI_CHEB);
+    const bool need1  = (epi.kind == EPI_CHEB && epi.f1 != T(0) && epi.v1 != nullptr);
+    const int  G1 = (int)gridDim.x;
+    const uint32_t *dw = reinterpret_cast<const uint32_t *>(list.bricks);
+    uint32_t        base = ldg_early(dw + (size_t)blockIdx.x * TMA_DW);
+    bool            first = true;
+    for (int it = blockIdx.x; it < list.n; it += G1)
+      {
+        const uint32_t base_n = (it + G1 < list.n) ? ldg_early(dw + (size_t)(it + G1) * TMA_DW) : 0u;
+        if (!first && need0)
+          bar_sync(FB_OPS_EMPTY, G::NCT + G::NMT); // the compute threads have read the operands of the previous brick
+        if (m == 0 && need0)
+          {
+            constexpr unsigned bytes = (unsigned)(G::NB * sizeof(T));
+            const int          c3    = (int)(base / G::NB) * (TmaLayout<k, T>::PERM ? 32 : 1);
+            mbar_expect_tx(mbar, need1 ? 2 * bytes : bytes);
+            tma_load_4d((unsigned)__cvta_generic_to_shared(ops0), map0, 0, 0, 0, c3, mbar);
+            if (need1)
+              tma_load_4d((unsigned)__cvta_generic_to_shared(ops1), map1, 0, 0, 0, c3, mbar);
+          }
+        tma_next_init<k, T>(ni, base, m);
+        base  = base_n;
+        first = false;
+      }
+  }
+
+  // shared memory of the kernels: header (mbarriers, two brick descriptors) | tile | X slots | operand boxes
+  template <int k, typename T>
+  struct TmaSmem
+  {
+    using G = TmaGeom<k, T>;
+    static constexpr int
+    pad1k(const int e)
+    {
+      return (e * (int)sizeof(T) + 1023) / 1024 * 1024 / (int)sizeof(T);
+    }
+    static constexpr int TILE  = pad1k(G::TILE);
+    static constexpr int XSLOT = pad1k(G::NCELLS * G::CS);
+    static constexpr int OPS   = pad1k(G::NB);
+    static constexpr size_t
+    bytes(const int n_x, const int n_ops)
+    {
+      return 2048 + (size_t)(TILE + n_x * XSLOT + n_ops * OPS) * sizeof(T);
+    }
+  };
 
   // ---- Laplace, uniform Cartesian geometry --------------------------------------------------------------------------------------
   template <int k, typename T>
@@ -619,27 +597,27 @@ namespace dasm
                      const Epilogue<T> epi,
                      const __grid_constant__ FastLaplaceMats<T, k + 1> mats,
                      const __grid_constant__ TmaMaps tmaps,
+                     const __grid_constant__ CUtensorMap omap0,
                      const int         shared_mode,
                      const NextInit<T> ni,
                      const TmaList     list,
                      const FastMaps    dbgmaps)
   {
     using G           = TmaGeom<k, T>;
+    using SM          = TmaSmem<k, T>;
     constexpr int n   = k + 1;
     constexpr int NFT = G::NFT;
     extern __shared__ __align__(16) unsigned char smem_dyn[];
-    // TMA destinations must be 128-byte aligned
+    // the tile and the operand boxes are written by the TMA engine with the 128-byte swizzle pattern: 1024-byte alignment
     unsigned char *smem_raw = smem_dyn + ((1024u - ((unsigned)__cvta_generic_to_shared(smem_dyn) & 1023u)) & 1023u);
-    // [0] mbarrier of the tile, [8] mbarrier of the operand staging, [16..] descriptor of the next brick
+    // [0] mbarrier of the tile, [8] mbarrier of the operand staging, [64..] descriptors of two bricks (ping-pong)
     const unsigned mb_tile = (unsigned)__cvta_generic_to_shared(smem_raw);
     const unsigned mb_ops  = mb_tile + 8;
-    uint32_t *     s_desc  = reinterpret_cast<uint32_t *>(smem_raw + 16);
-    T *            tile    = reinterpret_cast<T *>(smem_raw + 1024); // 1024-byte aligned: the swizzle pattern of the TMA engine
-    T *            Xq      = tile + G::TILE;
-    T *            Xp      = Xq + G::XSLOT;
-    T *            out     = Xq; // the output box aliases the first exchange slot (written after all reads of it)
-    T *            ofor    = Xp + G::XSLOT;
-    T *            ops0    = ofor + G::NFORP;
+    uint32_t *     s_desc  = reinterpret_cast<uint32_t *>(smem_raw + 64);
+    T *            tile    = reinterpret_cast<T *>(smem_raw + 1024);
+    T *            Xq      = tile + SM::TILE;
+    T *            Xp      = Xq + SM::XSLOT;
+    T *            ops0    = Xp + SM::XSLOT;
     if ((int)blockIdx.x >= list.n)
       return;
     if (threadIdx.x == 0)
@@ -651,7 +629,7 @@ namespace dasm
 
     if (threadIdx.x >= G::NCT)
       {
-        tma_mover_loop<k, T>(out, ofor, ops0, ops0, dst, acc, epi, list, shared_mode, ni, threadIdx.x - G::NCT, mb_ops, dbgmaps);
+        tma_mover_loop<k, T>(ops0, ops0, epi, &omap0, &omap0, list, ni, threadIdx.x - G::NCT, mb_ops);
         return;
       }
     const int       tid = threadIdx.x;
@@ -659,12 +637,13 @@ namespace dasm
     const int       cx = c & 3, cy = (c >> 2) & 3, cz = c >> 4;
     const bool      skip_last = ((t == k) && (cz < 2)) || (dbgmaps.dbg & 1); // whole warp: its plane z = k belongs to the cell above
     const PlaneAddr pa = tile_plane_y<k, T>(cx, cy, cz, t);
-    const PlaneAddr po = out_plane_z<k, T>(cx, cy, cz, t, (int)(ofor - out));
     T *             xq = Xq + c * G::CS, *xp = Xp + c * G::CS;
+    const bool      need0 = (epi.kind == EPI_RESIDUAL || epi.kind == EPI_CHEB);
     const int       G1 = (int)gridDim.x;
     int             it = blockIdx.x;
     const uint32_t *dw = reinterpret_cast<const uint32_t *>(list.bricks);
-    unsigned        tphase = 0;
+    unsigned        tphase = 0, ophase = 0;
+    int             par = 0; // s_desc[par]: this brick, s_desc[par ^ 1]: the next one
     // first tile
     uint32_t mode_next = 0, lo_next = 0;
     {
@@ -680,30 +659,30 @@ namespace dasm
           if (s_desc[1] != 0u)
             tma_foreign_gather<k, T>(tile, gf, src, tid);
         }
-      bar_sync(FB_COMPUTE, G::NCT); // s_desc may be overwritten
       if (it + G1 < list.n)
         {
           mode_next = ldg_early(dw + (size_t)(it + G1) * TMA_DW + 1);
           lo_next   = ldg_early(dw + (size_t)(it + G1) * TMA_DW + 9);
         }
     }
-    bool first = true;
-    for (; it < list.n; it += G1)
+    for (; it < list.n; it += G1, par ^= 1)
       {
-        const bool has_next = it + G1 < list.n;
-        // descriptor of the next brick -> shared memory (fire and forget, awaited before the barrier after phase A)
-        if (has_next && tid < TMA_DW)
-          cp_async_4(s_desc + tid, dw + (size_t)(it + G1) * TMA_DW + tid);
+        const bool      has_next = it + G1 < list.n;
+        const uint32_t *desc     = s_desc + par * 16;
         uint32_t gfn[NFT];
         if (list.any_mode1)
           tma_foreign_idx_load<k, T>(gfn, list, has_next ? mode_next : 0u, lo_next, tid);
         mbar_wait(mb_tile, tphase); // the tensor copies of this brick's tile have landed
         tphase ^= 1u;
         if (list.any_mode1)
-          {
-            cp_async_wait_all();
-            bar_sync(FB_COMPUTE, G::NCT); // foreign points gathered by the other threads
-          }
+          cp_async_wait_all();
+        // foreign points gathered by the other threads (mode 1); all phase B reads of the exchange slots of the previous brick are
+        // done before phase A overwrites them
+        bar_sync(FB_COMPUTE, G::NCT);
+        // descriptor of the next brick -> shared memory (fire and forget, awaited before the barrier after phase A; its buffer held
+        // the descriptor of the previous brick, whose epilogue all threads have left)
+        if (has_next && tid < TMA_DW)
+          cp_async_4(s_desc + (par ^ 1) * 16 + tid, dw + (size_t)(it + G1) * TMA_DW + tid);
         // phase A: plane y = t, [z][x]: q = Mx Mz v, p = (g0 Kx Mz + g2 Mx Kz) v
         if (!(dbgmaps.dbg & 1))
           {
@@ -716,8 +695,6 @@ namespace dasm
                 mat_vec<n, T, true, true, false>(a[z], mats.M, v);
                 mat_vec<n, T, true, true, false>(b[z], mats.K0, v);
               }
-            if (!first)
-              bar_sync(FB_OUT_EMPTY, G::NT); // the previous result (aliased with Xq) has been stored
 #pragma unroll
             for (int x = 0; x < n; ++x)
               {
@@ -739,8 +716,6 @@ namespace dasm
                   }
               }
           }
-        else if (!first)
-          bar_sync(FB_OUT_EMPTY, G::NT);
         if (has_next && tid < TMA_DW)
           cp_async_wait_all();
         bar_sync(FB_COMPUTE, G::NCT);
@@ -748,7 +723,7 @@ namespace dasm
         if (has_next)
           {
             if (tid == 0)
-              tma_issue_tile<k, T>(tile, tmaps, s_desc, mb_tile);
+              tma_issue_tile<k, T>(tile, tmaps, s_desc + (par ^ 1) * 16, mb_tile);
             if (list.any_mode1 && mode_next != 0u)
               tma_foreign_gather<k, T>(tile, gfn, src, tid);
           }
@@ -789,11 +764,14 @@ namespace dasm
               }
             fast_merge<k, T>(r, cx, cy);
           }
-        bar_sync(FB_COMPUTE, G::NCT); // all reads of the exchange slots are done: the output box may overwrite Xq
-        if (!skip_last && (t < k || cz == 3))
-          tma_out_store<k, T>(r, out, po, cx, cy);
-        bar_arrive(FB_OUT_FULL, G::NT);
-        first = false;
+        // fused epilogue from the registers
+        if (need0)
+          mbar_wait(mb_ops, ophase); // the operand box has landed
+        ophase ^= 1u;
+        if (!skip_last && (t < k || cz == 3) && !(dbgmaps.dbg & 2))
+          tma_epilogue_dispatch<k, T>(r, ops0, ops0, dst, acc, epi, shared_mode, desc, list.foreign, cx, cy, cz, t);
+        if (has_next && need0)
+          bar_arrive(FB_OPS_EMPTY, G::NCT + G::NMT);
       }
   }
 
@@ -806,25 +784,26 @@ namespace dasm
                  const Epilogue<T> epi,
                  const __grid_constant__ FastFdmMats<T, k + 1> mats,
                  const __grid_constant__ TmaMaps tmaps,
+                 const __grid_constant__ CUtensorMap omap0,
+                 const __grid_constant__ CUtensorMap omap1,
                  const int         shared_mode,
                  const NextInit<T> ni,
                  const TmaList     list,
                  const FastMaps    dbgmaps)
   {
     using G           = TmaGeom<k, T>;
+    using SM          = TmaSmem<k, T>;
     constexpr int n   = k + 1;
     constexpr int NFT = G::NFT;
     extern __shared__ __align__(16) unsigned char smem_dyn[];
     unsigned char *smem_raw = smem_dyn + ((1024u - ((unsigned)__cvta_generic_to_shared(smem_dyn) & 1023u)) & 1023u);
     const unsigned mb_tile = (unsigned)__cvta_generic_to_shared(smem_raw);
     const unsigned mb_ops  = mb_tile + 8;
-    uint32_t *     s_desc  = reinterpret_cast<uint32_t *>(smem_raw + 16);
-    T *            tile    = reinterpret_cast<T *>(smem_raw + 1024); // 1024-byte aligned: the swizzle pattern of the TMA engine
-    T *            X       = tile + G::TILE;
-    T *            out     = X + G::XSLOT;
-    T *            ofor    = out + G::pad(G::NB);
-    T *            ops0    = ofor + G::NFORP;
-    T *            ops1    = ops0 + G::pad(G::NB);
+    uint32_t *     s_desc  = reinterpret_cast<uint32_t *>(smem_raw + 64);
+    T *            tile    = reinterpret_cast<T *>(smem_raw + 1024);
+    T *            X       = tile + SM::TILE;
+    T *            ops0    = X + SM::XSLOT;
+    T *            ops1    = ops0 + SM::OPS;
     __shared__ T   s_inv[n * n * n];
     if ((int)blockIdx.x >= list.n)
       return;
@@ -839,7 +818,7 @@ namespace dasm
 
     if (threadIdx.x >= G::NCT)
       {
-        tma_mover_loop<k, T>(out, ofor, ops0, ops1, dst, acc, epi, list, shared_mode, ni, threadIdx.x - G::NCT, mb_ops, dbgmaps);
+        tma_mover_loop<k, T>(ops0, ops1, epi, &omap0, &omap1, list, ni, threadIdx.x - G::NCT, mb_ops);
         return;
       }
     const int       tid = threadIdx.x;
@@ -847,13 +826,14 @@ namespace dasm
     const int       cx = c & 3, cy = (c >> 2) & 3, cz = c >> 4;
     const bool      skip_last = ((t == k) && (cz < 2)) || (dbgmaps.dbg & 1);
     const PlaneAddr pa = tile_plane_z<k, T>(cx, cy, cz, t);
-    const PlaneAddr po = out_plane_z<k, T>(cx, cy, cz, t, (int)(ofor - out));
     T *             xs = X + c * G::CS;
     const T *       inv = s_inv + t * n; // row (z, y = t) of this thread's plane in phase B: broadcast reads
+    const bool      need0 = (epi.kind == EPI_RESIDUAL || epi.kind == EPI_CHEB);
     const int       G1 = (int)gridDim.x;
     int             it = blockIdx.x;
     const uint32_t *dw = reinterpret_cast<const uint32_t *>(list.bricks);
-    unsigned        tphase = 0;
+    unsigned        tphase = 0, ophase = 0;
+    int             par = 0;
     uint32_t        mode_next = 0, lo_next = 0;
     {
       if (tid < TMA_DW)
@@ -868,19 +848,16 @@ namespace dasm
           if (s_desc[1] != 0u)
             tma_foreign_gather<k, T>(tile, gf, src, tid);
         }
-      bar_sync(FB_COMPUTE, G::NCT);
       if (it + G1 < list.n)
         {
           mode_next = ldg_early(dw + (size_t)(it + G1) * TMA_DW + 1);
           lo_next   = ldg_early(dw + (size_t)(it + G1) * TMA_DW + 9);
         }
     }
-    bool first = true;
-    for (; it < list.n; it += G1)
+    for (; it < list.n; it += G1, par ^= 1)
       {
-        const bool has_next = it + G1 < list.n;
-        if (has_next && tid < TMA_DW)
-          cp_async_4(s_desc + tid, dw + (size_t)(it + G1) * TMA_DW + tid);
+        const bool      has_next = it + G1 < list.n;
+        const uint32_t *desc     = s_desc + par * 16;
         uint32_t gfn[NFT];
         if (list.any_mode1)
           tma_foreign_idx_load<k, T>(gfn, list, has_next ? mode_next : 0u, lo_next, tid);
@@ -891,6 +868,8 @@ namespace dasm
         // foreign points gathered by the other threads (mode 1); all phase C reads of the exchange slot of the previous brick are
         // done before phase A overwrites it
         bar_sync(FB_COMPUTE, G::NCT);
+        if (has_next && tid < TMA_DW)
+          cp_async_4(s_desc + (par ^ 1) * 16 + tid, dw + (size_t)(it + G1) * TMA_DW + tid);
         // phase A: plane z = t, [y][x]: Ax in x, Ay in y
         if (!(dbgmaps.dbg & 1))
           {
@@ -922,7 +901,7 @@ namespace dasm
         if (has_next)
           {
             if (tid == 0)
-              tma_issue_tile<k, T>(tile, tmaps, s_desc, mb_tile);
+              tma_issue_tile<k, T>(tile, tmaps, s_desc + (par ^ 1) * 16, mb_tile);
             if (list.any_mode1 && mode_next != 0u)
               tma_foreign_gather<k, T>(tile, gfn, src, tid);
           }
@@ -987,12 +966,13 @@ namespace dasm
               }
             fast_merge<k, T>(r, cx, cy);
           }
-        if (!first)
-          bar_sync(FB_OUT_EMPTY, G::NT); // the previous result has been stored
-        if (!skip_last && (t < k || cz == 3))
-          tma_out_store<k, T>(r, out, po, cx, cy);
-        bar_arrive(FB_OUT_FULL, G::NT);
-        first = false;
+        if (need0)
+          mbar_wait(mb_ops, ophase);
+        ophase ^= 1u;
+        if (!skip_last && (t < k || cz == 3) && !(dbgmaps.dbg & 2))
+          tma_epilogue_dispatch<k, T>(r, ops0, ops1, dst, acc, epi, shared_mode, desc, list.foreign, cx, cy, cz, t);
+        if (has_next && need0)
+          bar_arrive(FB_OPS_EMPTY, G::NCT + G::NMT);
       }
   }
 } // namespace dasm

@@ -110,7 +110,7 @@ namespace dasm
   size_t
   tma_laplace_smem(int k, int esize)
   {
-#define DASM_TMA_SMEM(K) (esize == 8 ? TmaGeom<K, double>::smem_bytes(2, false, 1) : TmaGeom<K, float>::smem_bytes(2, false, 1))
+#define DASM_TMA_SMEM(K) (esize == 8 ? TmaSmem<K, double>::bytes(2, 1) : TmaSmem<K, float>::bytes(2, 1))
     switch (k)
       {
         case 2:
@@ -127,7 +127,7 @@ namespace dasm
   size_t
   tma_fdm_smem(int k, int esize)
   {
-#define DASM_TMA_SMEM(K) (esize == 8 ? TmaGeom<K, double>::smem_bytes(1, true, 2) : TmaGeom<K, float>::smem_bytes(1, true, 2))
+#define DASM_TMA_SMEM(K) (esize == 8 ? TmaSmem<K, double>::bytes(1, 2) + 8 * 125 : TmaSmem<K, float>::bytes(1, 2) + 8 * 125)
     switch (k)
       {
         case 2:
@@ -144,7 +144,7 @@ namespace dasm
   template <int K, typename T>
   static void
   launch_laplace_tma_k(cudaStream_t stream, int grid, const T *src, T *dst, T *acc, const Epilogue<T> &epi, const double (*P)[25],
-                       const double (*Q)[25], const TmaMaps &maps, int shared_mode, const NextInit<T> &ni, const TmaList &list, int dbg)
+                       const double (*Q)[25], const TmaMaps &maps, const CUtensorMap &omap0, int shared_mode, const NextInit<T> &ni, const TmaList &list, int dbg)
   {
     using G = TmaGeom<K, T>;
     FastLaplaceMats<T, K + 1> mats;
@@ -152,18 +152,18 @@ namespace dasm
     eo_fill(mats.K0, P[1], Q[1]);
     eo_fill(mats.K1, P[2], Q[2]);
     eo_fill(mats.K2, P[3], Q[3]);
-    constexpr size_t smem = G::smem_bytes(2, false, 1);
+    constexpr size_t smem = TmaSmem<K, T>::bytes(2, 1);
     auto             kern = laplace_tma_kernel<K, T>;
     check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "laplace_tma_kernel attribute");
     const FastMaps fm = {nullptr, nullptr, nullptr, nullptr, 0, nullptr, dbg};
-    kern<<<grid, G::NT, smem, stream>>>(src, dst, acc, epi, mats, maps, shared_mode, ni, list, fm);
+    kern<<<grid, G::NT, smem, stream>>>(src, dst, acc, epi, mats, maps, omap0, shared_mode, ni, list, fm);
     check(cudaGetLastError(), "laplace_tma_kernel launch");
   }
 
   template <int K, typename T>
   static void
   launch_fdm_tma_k(cudaStream_t stream, int grid, const T *src, T *dst, T *acc, const Epilogue<T> &epi, const double (*P)[25],
-                   const double (*Q)[25], const double *inv, const TmaMaps &maps, int shared_mode, const NextInit<T> &ni,
+                   const double (*Q)[25], const double *inv, const TmaMaps &maps, const CUtensorMap &omap0, const CUtensorMap &omap1, int shared_mode, const NextInit<T> &ni,
                    const TmaList &list, int dbg)
   {
     using G         = TmaGeom<K, T>;
@@ -177,27 +177,27 @@ namespace dasm
     eo_fill(mats.Bz, P[5], Q[5]);
     for (int i = 0; i < n * n * n; ++i)
       mats.inv[i] = (T)inv[i];
-    constexpr size_t smem = G::smem_bytes(1, true, 2);
+    constexpr size_t smem = TmaSmem<K, T>::bytes(1, 2);
     auto             kern = fdm_tma_kernel<K, T>;
     check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "fdm_tma_kernel attribute");
     const FastMaps fm = {nullptr, nullptr, nullptr, nullptr, 0, nullptr, dbg};
-    kern<<<grid, G::NT, smem, stream>>>(src, dst, acc, epi, mats, maps, shared_mode, ni, list, fm);
+    kern<<<grid, G::NT, smem, stream>>>(src, dst, acc, epi, mats, maps, omap0, omap1, shared_mode, ni, list, fm);
     check(cudaGetLastError(), "fdm_tma_kernel launch");
   }
 
   template <typename T>
   void
   launch_laplace_tma(int k, cudaStream_t stream, int grid, const T *src, T *dst, T *acc, const Epilogue<T> &epi, const double (*P)[25],
-                     const double (*Q)[25], const TmaMaps &maps, int shared_mode, const NextInit<T> &ni, const TmaList &list, int dbg)
+                     const double (*Q)[25], const TmaMaps &maps, const CUtensorMap &omap0, int shared_mode, const NextInit<T> &ni, const TmaList &list, int dbg)
   {
     switch (k)
       {
         case 2:
-          return launch_laplace_tma_k<2, T>(stream, grid, src, dst, acc, epi, P, Q, maps, shared_mode, ni, list, dbg);
+          return launch_laplace_tma_k<2, T>(stream, grid, src, dst, acc, epi, P, Q, maps, omap0, shared_mode, ni, list, dbg);
         case 3:
-          return launch_laplace_tma_k<3, T>(stream, grid, src, dst, acc, epi, P, Q, maps, shared_mode, ni, list, dbg);
+          return launch_laplace_tma_k<3, T>(stream, grid, src, dst, acc, epi, P, Q, maps, omap0, shared_mode, ni, list, dbg);
         case 4:
-          return launch_laplace_tma_k<4, T>(stream, grid, src, dst, acc, epi, P, Q, maps, shared_mode, ni, list, dbg);
+          return launch_laplace_tma_k<4, T>(stream, grid, src, dst, acc, epi, P, Q, maps, omap0, shared_mode, ni, list, dbg);
       }
     throw std::runtime_error("laplace_tma_kernel: degree not instantiated");
   }
@@ -205,31 +205,31 @@ namespace dasm
   template <typename T>
   void
   launch_fdm_tma(int k, cudaStream_t stream, int grid, const T *src, T *dst, T *acc, const Epilogue<T> &epi, const double (*P)[25],
-                 const double (*Q)[25], const double *inv, const TmaMaps &maps, int shared_mode, const NextInit<T> &ni, const TmaList &list,
+                 const double (*Q)[25], const double *inv, const TmaMaps &maps, const CUtensorMap &omap0, const CUtensorMap &omap1, int shared_mode, const NextInit<T> &ni, const TmaList &list,
                  int dbg)
   {
     switch (k)
       {
         case 2:
-          return launch_fdm_tma_k<2, T>(stream, grid, src, dst, acc, epi, P, Q, inv, maps, shared_mode, ni, list, dbg);
+          return launch_fdm_tma_k<2, T>(stream, grid, src, dst, acc, epi, P, Q, inv, maps, omap0, omap1, shared_mode, ni, list, dbg);
         case 3:
-          return launch_fdm_tma_k<3, T>(stream, grid, src, dst, acc, epi, P, Q, inv, maps, shared_mode, ni, list, dbg);
+          return launch_fdm_tma_k<3, T>(stream, grid, src, dst, acc, epi, P, Q, inv, maps, omap0, omap1, shared_mode, ni, list, dbg);
         case 4:
-          return launch_fdm_tma_k<4, T>(stream, grid, src, dst, acc, epi, P, Q, inv, maps, shared_mode, ni, list, dbg);
+          return launch_fdm_tma_k<4, T>(stream, grid, src, dst, acc, epi, P, Q, inv, maps, omap0, omap1, shared_mode, ni, list, dbg);
       }
     throw std::runtime_error("fdm_tma_kernel: degree not instantiated");
   }
 
   template void launch_laplace_tma<double>(int, cudaStream_t, int, const double *, double *, double *, const Epilogue<double> &,
-                                           const double (*)[25], const double (*)[25], const TmaMaps &, int, const NextInit<double> &,
-                                           const TmaList &, int);
+                                           const double (*)[25], const double (*)[25], const TmaMaps &, const CUtensorMap &, int,
+                                           const NextInit<double> &, const TmaList &, int);
   template void launch_laplace_tma<float>(int, cudaStream_t, int, const float *, float *, float *, const Epilogue<float> &,
-                                          const double (*)[25], const double (*)[25], const TmaMaps &, int, const NextInit<float> &,
-                                          const TmaList &, int);
+                                          const double (*)[25], const double (*)[25], const TmaMaps &, const CUtensorMap &, int,
+                                          const NextInit<float> &, const TmaList &, int);
   template void launch_fdm_tma<double>(int, cudaStream_t, int, const double *, double *, double *, const Epilogue<double> &,
-                                       const double (*)[25], const double (*)[25], const double *, const TmaMaps &, int,
-                                       const NextInit<double> &, const TmaList &, int);
+                                       const double (*)[25], const double (*)[25], const double *, const TmaMaps &, const CUtensorMap &,
+                                       const CUtensorMap &, int, const NextInit<double> &, const TmaList &, int);
   template void launch_fdm_tma<float>(int, cudaStream_t, int, const float *, float *, float *, const Epilogue<float> &, const double (*)[25],
-                                      const double (*)[25], const double *, const TmaMaps &, int, const NextInit<float> &, const TmaList &,
-                                      int);
+                                      const double (*)[25], const double *, const TmaMaps &, const CUtensorMap &, const CUtensorMap &, int,
+                                      const NextInit<float> &, const TmaList &, int);
 } // namespace dasm

@@ -16,10 +16,11 @@ namespace dasm
   // P / Q: even-odd blocks (EOMat) of M, g0 K, g1 K, g2 K   (Laplace) and of Ax Ay Az Bx By Bz (FDM)
   template <typename T>
   void launch_laplace_tma(int k, cudaStream_t stream, int grid, const T *src, T *dst, T *acc, const Epilogue<T> &epi, const double (*P)[25],
-                          const double (*Q)[25], const TmaMaps &maps, int shared_mode, const NextInit<T> &ni, const TmaList &list, int dbg);
+                          const double (*Q)[25], const TmaMaps &maps, const CUtensorMap &omap0, int shared_mode, const NextInit<T> &ni,
+                          const TmaList &list, int dbg);
 
   template <typename T>
   void launch_fdm_tma(int k, cudaStream_t stream, int grid, const T *src, T *dst, T *acc, const Epilogue<T> &epi, const double (*P)[25],
-                      const double (*Q)[25], const double *inv, const TmaMaps &maps, int shared_mode, const NextInit<T> &ni,
-                      const TmaList &list, int dbg);
+                      const double (*Q)[25], const double *inv, const TmaMaps &maps, const CUtensorMap &omap0, const CUtensorMap &omap1,
+                      int shared_mode, const NextInit<T> &ni, const TmaList &list, int dbg);
 } // namespace dasm
