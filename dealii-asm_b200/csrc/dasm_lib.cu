@@ -309,6 +309,8 @@ struct dasm_op
   bool                  tma_ok = false;
   std::vector<TmaBrick> h_tma;           // per kernel brick (valid for lex bricks)
   TmaBrick *            d_tma_lap     = nullptr; // descriptors in the order of d_fast_ids
+  uint32_t *            d_tma_lap_chunks = nullptr; // chunk_start of the chunks of +x neighbours (kernels_tma.cuh)
+  int                   tma_lap_n_chunks = 0, tma_lap_n_chunks_boundary = 0;
   uint32_t *            d_tma_foreign = nullptr; // foreign index lists of the mode-1 bricks
   int                   tma_any_mode1 = 0;
   std::unordered_map<const void *, TmaMaps> tma_cache; // tensor maps per vector
@@ -345,6 +347,8 @@ struct dasm_fdm
   uint32_t *d_fast_ids = nullptr, *d_slow_ids = nullptr;
   int       n_fast = 0, n_slow = 0, n_fast_boundary = 0;
   TmaBrick *d_tma_list = nullptr; // TMA-fed kernel: descriptors in the order of d_fast_ids
+  uint32_t *d_tma_chunks = nullptr;
+  int       tma_n_chunks = 0, tma_n_chunks_boundary = 0;
   int       tma_any_mode1 = 0;
   double    fast_P[6][25], fast_Q[6][25]; // even-odd blocks of Ax Ay Az Bx By Bz
   double    fast_inv[729];
@@ -826,6 +830,76 @@ overlap_post(dasm_op *op)
   CUDA_CHECK(cudaStreamWaitEvent(op->ctx->stream, op->ctx->ev_b, 0));
 }
 
+// descriptors of the lex bricks `ids` (boundary bricks first: [0, n_boundary)) in processing order, grouped into chunks of
+// consecutive +x neighbours (kernels_tma.cuh TmaList)
+struct TmaChunked
+{
+  std::vector<TmaBrick> descs;
+  std::vector<uint32_t> chunk_start;
+  int                   n_chunks_boundary = 0;
+  int                   any_mode1         = 0;
+};
+
+static TmaChunked
+tma_build_list(const dasm_op *op, const std::vector<uint32_t> &ids, const int n_boundary)
+{
+  TmaChunked out;
+  const int  n = (int)ids.size();
+  int        L = std::max(1, std::min(8, n / std::max(1, 4 * op->n_sm)));
+  if (const char *e = getenv("DASM_TMA_CHUNK"))
+    L = std::max(1, atoi(e));
+  int len = 0;
+  for (int i = 0; i < n; ++i)
+    {
+      TmaBrick t = op->h_tma[ids[i]];
+      out.any_mode1 |= (int)(t.flags & TMA_MODE1);
+      bool cont = false; // continues the chunk of the previous brick
+      if (i > 0 && i != n_boundary && len < L)
+        {
+          const TmaBrick &p = out.descs.back();
+          cont = !(p.flags & TMA_MODE1) && !(t.flags & TMA_MODE1) && p.nb[0] == t.base;
+        }
+      if (cont)
+        {
+          out.descs.back().flags |= TMA_CARRY_OUT;
+          t.flags |= TMA_CARRY_IN;
+          ++len;
+        }
+      else
+        {
+          if (i > 0)
+            out.descs.back().flags |= TMA_LAST;
+          if (i == n_boundary)
+            out.n_chunks_boundary = (int)out.chunk_start.size();
+          out.chunk_start.push_back((uint32_t)i);
+          len = 1;
+        }
+      out.descs.push_back(t);
+    }
+  if (n > 0)
+    out.descs.back().flags |= TMA_LAST;
+  if (n_boundary >= n)
+    out.n_chunks_boundary = (int)out.chunk_start.size();
+  out.chunk_start.push_back((uint32_t)n);
+  return out;
+}
+
+// chunk range of a launch over the bricks [first, first + count) of a fast list (whole list, boundary part or interior part)
+static bool
+tma_chunk_range(const int first, const int count, const int n_fast, const int n_fast_boundary, const int n_chunks, const int n_chunks_boundary,
+                int &c_first, int &c_count)
+{
+  if (first == 0 && count == n_fast)
+    c_first = 0, c_count = n_chunks;
+  else if (first == 0 && count == n_fast_boundary)
+    c_first = 0, c_count = n_chunks_boundary;
+  else if (first == n_fast_boundary && count == n_fast - n_fast_boundary)
+    c_first = n_chunks_boundary, c_count = n_chunks - n_chunks_boundary;
+  else
+    return false;
+  return true;
+}
+
 // tensor maps of a vector for the TMA-fed kernels (cached per pointer); nullptr: not usable (alignment)
 static const TmaMaps *
 tma_maps_for(dasm_op *op, const void *vec)
@@ -867,8 +941,13 @@ launch_laplace_fast(dasm_op *op, T *dst, const T *src, const Epilogue<T> &epi, c
       const TmaMaps *tm = tma_maps_for(op, src);
       if (tm == nullptr || !tma_aligned(dst, epi.v0, epi.v1) || tma_laplace_smem(K, (int)sizeof(T)) > (size_t)op->max_smem)
         return false;
-      const int     grid = std::min(count, std::max(1, op->n_sm - reserve_sms));
-      const TmaList list = {op->d_tma_lap + first, op->d_tma_foreign, count, op->tma_any_mode1};
+      int c_first = 0, c_count = 0;
+      if (!tma_chunk_range(first, count, op->n_fast, op->n_fast_boundary, op->tma_lap_n_chunks, op->tma_lap_n_chunks_boundary, c_first, c_count))
+        return false;
+      if (c_count == 0)
+        return true;
+      const int     grid = std::min(c_count, std::max(1, op->n_sm - reserve_sms));
+      const TmaList list = {op->d_tma_lap, op->d_tma_foreign, op->d_tma_lap_chunks + c_first, c_count, op->tma_any_mode1};
       const TmaMaps *o0 = epi.v0 ? tma_maps_for(op, epi.v0) : tm;
       if (o0 == nullptr)
         return false;
@@ -1114,8 +1193,13 @@ launch_fdm_fast(dasm_fdm *f, T *dst, const T *src, const Epilogue<T> &epi, const
       if (tm == nullptr || f->d_tma_list == nullptr || !tma_aligned(dst, epi.v0, epi.v1) ||
           tma_fdm_smem(K, (int)sizeof(T)) > (size_t)op->max_smem)
         return false;
-      const int     grid = std::min(count, std::max(1, op->n_sm - reserve_sms));
-      const TmaList list = {f->d_tma_list + first, op->d_tma_foreign, count, f->tma_any_mode1};
+      int c_first = 0, c_count = 0;
+      if (!tma_chunk_range(first, count, f->n_fast, f->n_fast_boundary, f->tma_n_chunks, f->tma_n_chunks_boundary, c_first, c_count))
+        return false;
+      if (c_count == 0)
+        return true;
+      const int     grid = std::min(c_count, std::max(1, op->n_sm - reserve_sms));
+      const TmaList list = {f->d_tma_list, op->d_tma_foreign, f->d_tma_chunks + c_first, c_count, f->tma_any_mode1};
       const TmaMaps *o0 = epi.v0 ? tma_maps_for(op, epi.v0) : tm, *o1 = epi.v1 ? tma_maps_for(op, epi.v1) : tm;
       if (o0 == nullptr || o1 == nullptr)
         return false;
@@ -2145,7 +2229,7 @@ dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping
                             fast_ids.push_back((uint32_t)b);
                             TmaBrick &t  = op->h_tma[b];
                             t.base       = bd.base;
-                            t.mode       = 0;
+                            t.flags      = 0;
                             t.list_off   = 0;
                             const auto &o = M.cell_ijk[bd.first_cell];
                             for (int q = 0; q < 7; ++q)
@@ -2171,9 +2255,9 @@ dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping
                                       local = false;
                                   }
                                 if (!local)
-                                  t.mode = 1;
+                                  t.flags = TMA_MODE1;
                               }
-                            if (t.mode == 1)
+                            if (t.flags & TMA_MODE1)
                               {
                                 t.list_off = (uint32_t)foreign.size();
                                 for (int j = 0; j < NFPt; ++j)
@@ -2204,18 +2288,18 @@ dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping
                           }
                         std::stable_partition(fast_ids.begin(), fast_ids.end(), [&](uint32_t b) { return op->h_brick_boundary[b] != 0; });
                         op->n_fast_boundary = 0;
-                        std::vector<TmaBrick> ordered;
                         for (const uint32_t b : fast_ids)
-                          {
-                            op->n_fast_boundary += op->h_brick_boundary[b] ? 1 : 0;
-                            ordered.push_back(op->h_tma[b]);
-                            op->tma_any_mode1 |= (int)op->h_tma[b].mode;
-                          }
+                          op->n_fast_boundary += op->h_brick_boundary[b] ? 1 : 0;
+                        const TmaChunked ch = tma_build_list(op, fast_ids, op->n_fast_boundary);
                         cudaFree(op->d_fast_ids);
                         cudaFree(op->d_slow_ids);
                         op->tma_ok        = true;
                         op->fast_ok       = true;
-                        op->d_tma_lap     = dev_upload(ordered, ctx->stream);
+                        op->tma_any_mode1 = ch.any_mode1;
+                        op->d_tma_lap     = dev_upload(ch.descs, ctx->stream);
+                        op->d_tma_lap_chunks = dev_upload(ch.chunk_start, ctx->stream);
+                        op->tma_lap_n_chunks = (int)ch.chunk_start.size() - 1;
+                        op->tma_lap_n_chunks_boundary = ch.n_chunks_boundary;
                         op->d_tma_foreign = dev_upload(foreign, ctx->stream);
                         op->d_fast_ids    = dev_upload(fast_ids, ctx->stream);
                         op->d_slow_ids    = dev_upload(slow_ids, ctx->stream);
@@ -2272,6 +2356,7 @@ dasm_op_destroy(dasm_op *op)
   cudaFree(op->d_fast_ids);
   cudaFree(op->d_slow_ids);
   cudaFree(op->d_tma_lap);
+  cudaFree(op->d_tma_lap_chunks);
   cudaFree(op->d_tma_foreign);
   for (void *p : op->d_map_bufs)
     cudaFree(p);
@@ -3108,13 +3193,12 @@ dasm_fdm_create(dasm_op *op, int n_overlap, int sub_mesh_approximation, int weig
               f->d_slow_ids = dev_upload(slow_ids, op->ctx->stream);
               if (op->tma_ok)
                 {
-                  std::vector<TmaBrick> ordered;
-                  for (const uint32_t b : fast_ids)
-                    {
-                      ordered.push_back(op->h_tma[b]);
-                      f->tma_any_mode1 |= (int)op->h_tma[b].mode;
-                    }
-                  f->d_tma_list = dev_upload(ordered, op->ctx->stream);
+                  const TmaChunked ch = tma_build_list(op, fast_ids, f->n_fast_boundary);
+                  f->tma_any_mode1    = ch.any_mode1;
+                  f->d_tma_list       = dev_upload(ch.descs, op->ctx->stream);
+                  f->d_tma_chunks     = dev_upload(ch.chunk_start, op->ctx->stream);
+                  f->tma_n_chunks     = (int)ch.chunk_start.size() - 1;
+                  f->tma_n_chunks_boundary = ch.n_chunks_boundary;
                 }
             }
         }
@@ -3140,6 +3224,7 @@ dasm_fdm_destroy(dasm_fdm *f)
   cudaFree(f->d_fast_ids);
   cudaFree(f->d_slow_ids);
   cudaFree(f->d_tma_list);
+  cudaFree(f->d_tma_chunks);
   cudaFree(f->d_pidx);
   delete f;
   DASM_API_END
@@ -3554,9 +3639,9 @@ cheb_run(dasm_cheb *c, T *x_user, const T *b, bool first_is_step)
       rho_old = 1. / sigma;
     }
   // Fully fused sequence (optimize 2 with the FDM brick preconditioner): DoFs on shared brick faces receive
-  // their contributions by red.add directly in the destination, which the PREVIOUS kernel pre-initialised
-  // with the part of the epilogue that does not depend on the operator result; no pass over the shared
-  // DoFs remains except one at the start of the step.
+  // their contributions by red.add directly in the destination, which the PREVIOUS kernel zeroed there (the
+  // owning brick adds the part of the epilogue that does not depend on the operator result); no pass over the
+  // shared DoFs remains except one at the start of the step.
   const bool direct = op->use_brick && op->shared_ranges_ok && c->fdm != nullptr && fdm_uses_brick(c->fdm) && c->optimize >= 2 &&
                       !(getenv("DASM_NO_DIRECT") && getenv("DASM_NO_DIRECT")[0] == '1');
   T *t1buf[2] = {t1, (T *)c->t1b};
@@ -3590,18 +3675,12 @@ cheb_run(dasm_cheb *c, T *x_user, const T *b, bool first_is_step)
         upd = {DASM_HOOK_CHEB_UPDATE, f1, f2, cur, old_used};
       if (direct)
         {
-          // base of the update epilogue on the shared DoFs of nxt: cur + f1 (cur - old)   (0 for the scale epilogue)
-          NextInit<T> ni_upd;
-          ni_upd.out = nxt;
-          ni_upd.v0  = need_A ? cur : nullptr;
-          ni_upd.v1  = old_used;
-          ni_upd.f1  = (T)(need_A ? f1 : 0.);
-          // base of the residual epilogue on the shared DoFs of the next t1 buffer: b
-          NextInit<T> ni_res;
-          ni_res.out = t1buf[(term + 1) & 1];
-          ni_res.v0  = b;
-          ni_res.v1  = nullptr;
-          ni_res.f1  = 0;
+          // every kernel zeroes the destination of the NEXT kernel on the shared DoFs (the brick that owns a shared DoF adds the
+          // base of the epilogue together with its contribution, kernels_brick.cuh SHARED_DIRECT)
+          NextInit<T> ni_upd = no_next_init<T>();
+          ni_upd.out         = nxt;
+          NextInit<T> ni_res = no_next_init<T>();
+          ni_res.out         = t1buf[(term + 1) & 1];
           const T *rhs_for_P = b;
           if (need_A)
             {

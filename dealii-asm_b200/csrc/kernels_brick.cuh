@@ -73,12 +73,12 @@ namespace dasm
   enum
   {
     SHARED_ACC    = 0, // red.add y into the zero-invariant accumulator, finish_shared_kernel runs the epilogue
-    SHARED_DIRECT = 1  // dst was pre-initialised with the epilogue's base value; red.add (alpha y) into dst
+    SHARED_DIRECT = 1  // dst is ZERO on the shared DoFs before the kernel (zeroed by the previous kernel of the sequence); the brick
+                       // that owns a shared DoF adds the full epilogue value (base + alpha y), every other brick alpha y
   };
 
-  // pre-initialisation of the NEXT kernel's destination on the shared DoFs owned by a brick (fused into the
-  // current kernel): out = v0 + f1 (v0 - v1)   (v0 / v1 == nullptr: 0), i.e. the part of the next epilogue
-  // that does not depend on its operator result
+  // the NEXT kernel's destination is zeroed on the shared DoFs owned by a brick (fused into the current kernel): `out`.
+  // (v0 / v1 / f1 are only used by the stand-alone init_shared_kernel.)
   template <typename T>
   struct NextInit
   {
@@ -409,8 +409,9 @@ namespace dasm
             {
               const int      p  = pz * NPENC + base;
               const uint32_t g  = gidx[p]; // written by this thread in brick_issue_loads
-              const bool     sh = (shxy | ((pz == 0) ? (bd.shared & 16u) : 0u) | ((pz == ez - 1) ? (bd.shared & 32u) : 0u)) != 0;
-              if (g != DEV_INVALID && !sh)
+              // every point the brick owns (not on an upper face shared with the neighbour brick)
+              const bool     up = ((shxy & 10u) | ((pz == ez - 1) ? (bd.shared & 32u) : 0u)) != 0;
+              if (g != DEV_INVALID && !up)
                 {
                   cp_async_value(ops0 + p, epi.v0 + g);
                   if (need1)
@@ -475,8 +476,8 @@ namespace dasm
     const bool need1 = (epi.kind == EPI_CHEB && epi.f1 != T(0) && epi.v1 != nullptr);
     if (!need0)
       return;
-    // (lex bricks: the private DoFs are interleaved with the shared ones, the whole own range is staged)
-    const int n_stage = (bd.shared & BRICK_LEX) ? (int)(bd.npriv + bd.sh_count) : (int)bd.npriv;
+    // the whole own range: the operands on the brick's own shared DoFs enter the value it adds there
+    const int n_stage = (int)(bd.npriv + bd.sh_count);
 #pragma unroll 4
     for (int i = threadIdx.x; i < n_stage; i += G::NT)
       {
@@ -527,10 +528,11 @@ namespace dasm
         if (e == 0xFFFFFFFFu)
           continue;
         const T y = slot_sum(slots, (e >> 13) & 0x1FFFu, (e >> 26) & 7u, dx, dy, dz);
+        const T v = epilogue_compute(epi, y, need0 ? ops0[i] : T(0), need1 ? ops1[i] : T(0));
         if (e & STORE_SHARED)
-          atomic_add(sh_dst + bd.base + i, sh_a * y);
+          atomic_add(sh_dst + bd.base + i, shared_mode == SHARED_DIRECT ? v : y);
         else
-          dst[bd.base + i] = epilogue_compute(epi, y, need0 ? ops0[i] : T(0), need1 ? ops1[i] : T(0));
+          dst[bd.base + i] = v;
       }
     // tile points owned by other bricks
     for (int j = threadIdx.x; j < n_for; j += G::NT)
@@ -596,45 +598,17 @@ namespace dasm
                                BrickGeom<k, BZ>::NT - 1) / BrickGeom<k, BZ>::NT; // upper bound of shared DoFs per thread
   };
 
-  // lex == nullptr: the own shared DoFs are the contiguous range [sh_base, sh_base + sh_count); else base + lex[i]
+  // the next kernel's destination is zeroed on the brick's own shared DoFs
+  // lex == nullptr: they are the contiguous range [sh_base, sh_base + sh_count); else base + lex[i]
   template <int k, int BZ, typename T>
   __device__ __forceinline__ void
-  brick_next_init_load(const BrickDesc &bd, const NextInit<T> &ni, T (&a)[NextInitRegs<k, BZ>::IT], T (&b)[NextInitRegs<k, BZ>::IT],
-                       const uint16_t *__restrict__ lex = nullptr)
-  {
-    using G = BrickGeom<k, BZ>;
-#pragma unroll
-    for (int it = 0; it < NextInitRegs<k, BZ>::IT; ++it)
-      {
-        const uint32_t i = threadIdx.x + it * G::NT;
-        a[it]            = T(0);
-        b[it]            = T(0);
-        if (ni.out != nullptr && i < bd.sh_count)
-          {
-            const uint32_t g = lex ? bd.base + lex[i] : bd.sh_base + i;
-            if (ni.v0 != nullptr)
-              a[it] = ni.v0[g];
-            if (ni.v1 != nullptr && ni.f1 != T(0))
-              b[it] = ni.v1[g];
-          }
-      }
-  }
-
-  template <int k, int BZ, typename T>
-  __device__ __forceinline__ void
-  brick_next_init_store(const BrickDesc &bd, const NextInit<T> &ni, const T (&a)[NextInitRegs<k, BZ>::IT],
-                        const T (&b)[NextInitRegs<k, BZ>::IT], const uint16_t *__restrict__ lex = nullptr)
+  brick_next_init_store(const BrickDesc &bd, const NextInit<T> &ni, const uint16_t *__restrict__ lex = nullptr)
   {
     using G = BrickGeom<k, BZ>;
     if (ni.out == nullptr)
       return;
-#pragma unroll
-    for (int it = 0; it < NextInitRegs<k, BZ>::IT; ++it)
-      {
-        const uint32_t i = threadIdx.x + it * G::NT;
-        if (i < bd.sh_count)
-          ni.out[lex ? bd.base + lex[i] : bd.sh_base + i] = a[it] + ni.f1 * (a[it] - b[it]);
-      }
+    for (uint32_t i = threadIdx.x; i < bd.sh_count; i += G::NT)
+      ni.out[lex ? bd.base + lex[i] : bd.sh_base + i] = T(0);
   }
 
   // reduction of the cell results (slots) per tile point in a fixed order (deterministic, no shared-memory
@@ -706,10 +680,11 @@ namespace dasm
                         y += mz * (slots[ozb + o0] + m1 * slots[ozb + o1] + m2 * slots[ozb + o2] + m3 * slots[ozb + o3]);
                       }
                     const bool sh = (shxy | ((pz == 0) ? (bd.shared & 16u) : 0u) | ((pz == ez - 1) ? (bd.shared & 32u) : 0u)) != 0;
+                    const bool up = ((shxy & 10u) | ((pz == ez - 1) ? (bd.shared & 32u) : 0u)) != 0; // owned by a neighbour brick
                     if (sh)
                       {
                         if (shared_mode == SHARED_DIRECT)
-                          atomic_add(dst + g, alpha * y);
+                          atomic_add(dst + g, up ? alpha * y : epilogue_compute(epi, y, need0 ? ops0[p] : T(0), need1 ? ops1[p] : T(0)));
                         else
                           atomic_add(acc + g, y);
                       }
@@ -804,9 +779,7 @@ namespace dasm
         const int       ncells   = bd.b[0] * bd.b[1] * bd.b[2];
         const uint32_t *cur_cidx = s_cidx + buf * (G::NCELLS * 27);
         uint32_t *      cur_gidx = LIN ? gidx + fb * G::NFP : gidx;
-        T               ni_a[NextInitRegs<k, BZ>::IT], ni_b[NextInitRegs<k, BZ>::IT];
         const uint16_t *ni_lex = (LIN && (bd.shared & BRICK_LEX)) ? tb.sh_tab : nullptr;
-        brick_next_init_load<k, BZ, T>(bd, ni, ni_a, ni_b, ni_lex);
         if (LIN)
           {
             brick_issue_ops_lin<k, BZ, T>(bd, ops0, ops1, epi);
@@ -827,7 +800,7 @@ namespace dasm
             cp_async_commit();
             cp_async_wait<2>();
           }
-        brick_next_init_store<k, BZ, T>(bd, ni, ni_a, ni_b, ni_lex);
+        brick_next_init_store<k, BZ, T>(bd, ni, ni_lex);
         __syncthreads();
 
         const bool act = (c < ncells);
@@ -1247,9 +1220,7 @@ namespace dasm
         const int       ncells   = bd.b[0] * bd.b[1] * bd.b[2];
         const uint32_t *cur_cidx = s_cidx + buf * (G::NCELLS * 27);
         uint32_t *      cur_gidx = LIN ? gidx + fb * G::NFP : gidx;
-        T               ni_a[NextInitRegs<k, BZ>::IT], ni_b[NextInitRegs<k, BZ>::IT];
         const uint16_t *ni_lex = (LIN && (bd.shared & BRICK_LEX)) ? tb.sh_tab : nullptr;
-        brick_next_init_load<k, BZ, T>(bd, ni, ni_a, ni_b, ni_lex);
         if (LIN)
           {
             brick_issue_ops_lin<k, BZ, T>(bd, ops0, ops1, epi);
@@ -1271,7 +1242,7 @@ namespace dasm
             cp_async_commit();
             cp_async_wait<2>();
           }
-        brick_next_init_store<k, BZ, T>(bd, ni, ni_a, ni_b, ni_lex);
+        brick_next_init_store<k, BZ, T>(bd, ni, ni_lex);
         __syncthreads();
 
         const bool     act  = (c < ncells) && !(dbg & 2);

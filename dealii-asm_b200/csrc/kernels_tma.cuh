@@ -25,11 +25,20 @@ namespace dasm
   struct TmaBrick
   {
     uint32_t base;     // first DoF of the own box (a multiple of 64 k^3)
-    uint32_t mode;     // 0: the 7 upper neighbours are local lex bricks (nb = their bases); 1: index list
-    uint32_t nb[7];    // +x, +y, +z, +xy, +xz, +yz, +xyz
+    uint32_t flags;    // TMA_MODE1 | TMA_CARRY_IN | TMA_CARRY_OUT | TMA_LAST
+    uint32_t nb[7];    // bases of the upper neighbours +x, +y, +z, +xy, +xz, +yz, +xyz (mode 0)
     uint32_t list_off; // mode 1: offset of the brick's foreign index list (NFP entries, face order)
   };
   constexpr int TMA_DW = sizeof(TmaBrick) / 4;
+  enum : uint32_t
+  {
+    TMA_MODE1     = 1u, // an upper neighbour is not a local lex brick: foreign points through the index list
+    TMA_CARRY_IN  = 2u, // the previous brick of the chunk is the -x neighbour: its X = R contributions arrive through shared memory,
+                        // the own face X = 0 is complete after this brick (plain stores, no red.add / pre-initialisation)
+    TMA_CARRY_OUT = 4u, // the next brick of the chunk is the +x neighbour: X = R contributions are handed over, not red.add-ed
+    TMA_LAST      = 8u, // last brick of its chunk
+    TMA_NONE      = 0xFFFFFFFFu
+  };
 
   // tensor maps of one vector (kernel parameters)
   struct TmaMaps
@@ -37,12 +46,23 @@ namespace dasm
     CUtensorMap main, fx, fy, fz, exy, exz, eyz, cxyz;
   };
 
+  // Bricks are processed in chunks of consecutive +x neighbours: thread block b walks the chunks b, b + grid, ... and the
+  // bricks [chunk_start[c], chunk_start[c + 1]) of a chunk in order, so that the contributions to the face between two bricks
+  // of a chunk never leave the SM.
   struct TmaList
   {
-    const TmaBrick *bricks;  // [n] in processing order
-    const uint32_t *foreign; // index lists of the mode-1 bricks
-    int             n;
+    const TmaBrick *bricks;      // whole list
+    const uint32_t *foreign;     // index lists of the mode-1 bricks
+    const uint32_t *chunk_start; // [n_chunks + 1] of the chunks this launch processes (indices into bricks)
+    int             n_chunks;
     int             any_mode1;
+  };
+
+  struct TmaWalk
+  {
+    uint32_t idx;        // current brick
+    uint32_t next_start; // first brick of this block's next chunk (TMA_NONE: none)
+    int      chunk;
   };
 
   template <int k, typename T>
@@ -54,8 +74,7 @@ namespace dasm
     static constexpr int NB     = R * R * R;
     static constexpr int NCELLS = 64;
     static constexpr int NCT    = NCELLS * n;
-    static constexpr int NMT    = 32;
-    static constexpr int NT     = NCT + NMT;
+    static constexpr int NT     = NCT;
     static constexpr int CS     = (n * n * n) | 1;
     static constexpr int V      = 16 / (int)sizeof(T); // elements per 16-byte vector
     __host__ __device__ static constexpr int
@@ -87,8 +106,6 @@ namespace dasm
     static constexpr int NFORP  = pad(NFOR);
     static constexpr int NSH    = NB - (R - 1) * (R - 1) * (R - 1); // own DoFs on the shared lower faces
     static constexpr int NFT    = (NFOR + NCT - 1) / NCT;
-    static constexpr int NFM    = (NFOR + NMT - 1) / NMT;
-    static constexpr int NSI    = (NSH + NMT - 1) / NMT;
     static constexpr int XSLOT  = pad(NCELLS * CS);
     // tile offset of the j-th foreign point
     __host__ __device__ static constexpr int
@@ -167,6 +184,31 @@ namespace dasm
     }
   };
 
+  __device__ __forceinline__ void
+  walk_init(TmaWalk &w, const TmaList &list)
+  {
+    w.chunk      = blockIdx.x;
+    w.idx        = ldg_early(list.chunk_start + w.chunk);
+    w.next_start = (w.chunk + (int)gridDim.x < list.n_chunks) ? ldg_early(list.chunk_start + w.chunk + gridDim.x) : (uint32_t)TMA_NONE;
+  }
+  __device__ __forceinline__ uint32_t
+  walk_peek(const TmaWalk &w, const bool last)
+  {
+    return last ? w.next_start : w.idx + 1u;
+  }
+  __device__ __forceinline__ void
+  walk_advance(TmaWalk &w, const bool last, const TmaList &list)
+  {
+    if (!last)
+      {
+        ++w.idx;
+        return;
+      }
+    w.chunk += (int)gridDim.x;
+    w.idx        = w.next_start;
+    w.next_start = (w.chunk + (int)gridDim.x < list.n_chunks) ? ldg_early(list.chunk_start + w.chunk + gridDim.x) : (uint32_t)TMA_NONE;
+  }
+
   // ---- TMA primitives ------------------------------------------------------------------------------------------------------
   __device__ __forceinline__ void
   tma_load_4d(const unsigned dst, const CUtensorMap *map, const int c0, const int c1, const int c2, const int c3, const unsigned mbar)
@@ -184,7 +226,7 @@ namespace dasm
     using G                = TmaGeom<k, T>;
     const unsigned t0      = (unsigned)__cvta_generic_to_shared(tile);
     const uint32_t base    = desc[0];
-    const bool     mode0   = desc[1] == 0u;
+    const bool     mode0   = (desc[1] & TMA_MODE1) == 0u;
     constexpr unsigned ES  = (unsigned)sizeof(T);
     mbar_expect_tx(mbar, mode0 ? G::BYTES_MAIN + G::BYTES_FOR : G::BYTES_MAIN);
     tma_load_4d(t0 + G::O_MAIN * ES, &maps.main, 0, 0, 0, (int)(base / G::NB) * (TmaLayout<k, T>::PERM ? 32 : 1), mbar);
@@ -203,22 +245,16 @@ namespace dasm
   // mode 1: foreign points of the tile through the index list (cp.async by the compute threads)
   template <int k, typename T>
   __device__ __forceinline__ void
-  tma_foreign_idx_load(uint32_t (&gf)[TmaGeom<k, T>::NFT], const TmaList &list, const uint32_t mode, const uint32_t list_off, const int tid)
+  tma_foreign_gather(T *tile, const TmaList &list, const uint32_t list_off, const T *__restrict__ src, const int tid)
   {
     using G = TmaGeom<k, T>;
+    uint32_t gf[G::NFT];
 #pragma unroll
     for (int jj = 0; jj < G::NFT; ++jj)
       {
         const int j = tid + jj * G::NCT;
-        gf[jj]      = (mode != 0u && j < G::NFOR) ? ldg_early(list.foreign + list_off + j) : 0u;
+        gf[jj]      = (j < G::NFOR) ? ldg_early(list.foreign + list_off + j) : 0u;
       }
-  }
-
-  template <int k, typename T>
-  __device__ __forceinline__ void
-  tma_foreign_gather(T *tile, const uint32_t (&gf)[TmaGeom<k, T>::NFT], const T *__restrict__ src, const int tid)
-  {
-    using G = TmaGeom<k, T>;
 #pragma unroll
     for (int jj = 0; jj < G::NFT; ++jj)
       {
@@ -348,19 +384,45 @@ namespace dasm
   __device__ __forceinline__ uint32_t
   foreign_index(const uint32_t *desc, const uint32_t *__restrict__ lists, const int q, const int off, const int j)
   {
-    return desc[1] == 0u ? desc[2 + q] + (uint32_t)off : __ldg(lists + desc[9] + j);
+    return (desc[1] & TMA_MODE1) == 0u ? desc[2 + q] + (uint32_t)off : __ldg(lists + desc[9] + j);
   }
 
+  // carry: [R + 1][R + 1] values of the plane X = R (Z slow, Y fast) handed from a brick to its +x neighbour
   template <int k, typename T, int KIND, bool TWO>
   __device__ __forceinline__ void
-  tma_epilogue(const T (&r)[k + 1][k + 1], const T *ops0, const T *ops1, T *__restrict__ dst, T *__restrict__ sh_dst, const T sh_a, const T f1,
-               const T f2, const uint32_t *desc, const uint32_t *__restrict__ lists, const int cx, const int cy, const int cz, const int t)
+  tma_epilogue(T (&r)[k + 1][k + 1], const T *ops0, const T *ops1, const T *carry_in, T *carry_out, T *__restrict__ dst, T *__restrict__ sh_dst, const T sh_a,
+               const bool direct, T *__restrict__ ni_out, const T f1, const T f2, const uint32_t *desc, const uint32_t *__restrict__ lists, const int cx, const int cy, const int cz,
+               const int t)
   {
     using G         = TmaGeom<k, T>;
     using L         = TmaLayout<k, T>;
     constexpr int R = G::R;
     const uint32_t  base = desc[0];
+    const bool      cin = (desc[1] & TMA_CARRY_IN) != 0u, cout = (desc[1] & TMA_CARRY_OUT) != 0u;
     const int       Z = k * cz + t;
+    // (two carry planes, alternating per brick: no thread writes the plane another one still reads)
+    const T *       c_in  = carry_in + Z * (R + 1) + k * cy;
+    T *             c_out = carry_out + Z * (R + 1) + k * cy;
+    // contributions of the -x neighbour (the previous brick of this block) to the plane X = 0
+    if (cin && cx == 0)
+      {
+#pragma unroll
+        for (int y = 0; y < k; ++y)
+          r[y][0] += c_in[y];
+        if (cy == 3)
+          r[k][0] += c_in[k];
+      }
+    // contributions to the plane X = R: handed to the next brick of this block
+    if (cout && cx == 3)
+      {
+#pragma unroll
+        for (int y = 0; y < k; ++y)
+          c_out[y] = r[y][k];
+        if (cy == 3)
+          c_out[k] = r[k][k];
+      }
+    const bool xred = (cx == 3) && !cout; // X = R points go to the neighbours with red.add
+    const bool x0sh = (cx == 0) && !cin;  // the own face X = 0 is shared with a brick processed elsewhere
     if (Z < R)
       {
         const bool zsh = (Z == 0);
@@ -370,57 +432,65 @@ namespace dasm
             const int      Y  = k * cy + y;
             const uint32_t g  = base + (uint32_t)((Z * R + Y) * R + k * cx);
             const bool     sh = zsh || (Y == 0);
+            T              a[k], b[k], res[k];
+            if (KIND == EPI_RESIDUAL || KIND == EPI_CHEB)
+              {
+                const int rho = L::row(Y, Z), rowo = rho * R, sw = L::swz(rho);
+                if constexpr (L::SWZ)
+                  {
+                    const double2 a0 = *reinterpret_cast<const double2 *>(ops0 + rowo + (((2 * cx) ^ sw) << 1));
+                    const double2 a1 = *reinterpret_cast<const double2 *>(ops0 + rowo + (((2 * cx + 1) ^ sw) << 1));
+                    a[0] = a0.x, a[1] = a0.y, a[2] = a1.x, a[3] = a1.y;
+                    if (TWO)
+                      {
+                        const double2 b0 = *reinterpret_cast<const double2 *>(ops1 + rowo + (((2 * cx) ^ sw) << 1));
+                        const double2 b1 = *reinterpret_cast<const double2 *>(ops1 + rowo + (((2 * cx + 1) ^ sw) << 1));
+                        b[0] = b0.x, b[1] = b0.y, b[2] = b1.x, b[3] = b1.y;
+                      }
+                  }
+                else if constexpr (L::PERM)
+                  {
+                    const float4 a0 = *reinterpret_cast<const float4 *>(ops0 + rowo + 4 * cx);
+                    a[0] = a0.x, a[1] = a0.y, a[2] = a0.z, a[3] = a0.w;
+                    if (TWO)
+                      {
+                        const float4 b0 = *reinterpret_cast<const float4 *>(ops1 + rowo + 4 * cx);
+                        b[0] = b0.x, b[1] = b0.y, b[2] = b0.z, b[3] = b0.w;
+                      }
+                  }
+                else
+                  {
+#pragma unroll
+                    for (int x = 0; x < k; ++x)
+                      {
+                        a[x] = ops0[rowo + k * cx + x];
+                        if (TWO)
+                          b[x] = ops1[rowo + k * cx + x];
+                      }
+                  }
+              }
+#pragma unroll
+            for (int x = 0; x < k; ++x)
+              res[x] = epi_value<T, KIND, TWO>(r[y][x], a[x], TWO ? b[x] : T(0), f1, f2);
             if (sh)
               {
+                // own DoFs on the shared faces Y = 0 / Z = 0: this brick adds the full epilogue value; the next kernel's
+                // destination is zeroed there
 #pragma unroll
                 for (int x = 0; x < k; ++x)
-                  atomic_add(sh_dst + g + x, sh_a * r[y][x]);
+                  {
+                    atomic_add(sh_dst + g + x, direct ? res[x] : r[y][x]);
+                    if (ni_out != nullptr)
+                      ni_out[g + x] = T(0);
+                  }
               }
             else
               {
-                T a[k], b[k], res[k];
-                if (KIND == EPI_RESIDUAL || KIND == EPI_CHEB)
+                if (x0sh)
                   {
-                    const int rho = L::row(Y, Z), rowo = rho * R, sw = L::swz(rho);
-                    if constexpr (L::SWZ)
-                      {
-                        const double2 a0 = *reinterpret_cast<const double2 *>(ops0 + rowo + (((2 * cx) ^ sw) << 1));
-                        const double2 a1 = *reinterpret_cast<const double2 *>(ops0 + rowo + (((2 * cx + 1) ^ sw) << 1));
-                        a[0] = a0.x, a[1] = a0.y, a[2] = a1.x, a[3] = a1.y;
-                        if (TWO)
-                          {
-                            const double2 b0 = *reinterpret_cast<const double2 *>(ops1 + rowo + (((2 * cx) ^ sw) << 1));
-                            const double2 b1 = *reinterpret_cast<const double2 *>(ops1 + rowo + (((2 * cx + 1) ^ sw) << 1));
-                            b[0] = b0.x, b[1] = b0.y, b[2] = b1.x, b[3] = b1.y;
-                          }
-                      }
-                    else if constexpr (L::PERM)
-                      {
-                        const float4 a0 = *reinterpret_cast<const float4 *>(ops0 + rowo + 4 * cx);
-                        a[0] = a0.x, a[1] = a0.y, a[2] = a0.z, a[3] = a0.w;
-                        if (TWO)
-                          {
-                            const float4 b0 = *reinterpret_cast<const float4 *>(ops1 + rowo + 4 * cx);
-                            b[0] = b0.x, b[1] = b0.y, b[2] = b0.z, b[3] = b0.w;
-                          }
-                      }
-                    else
-                      {
-#pragma unroll
-                        for (int x = 0; x < k; ++x)
-                          {
-                            a[x] = ops0[rowo + k * cx + x];
-                            if (TWO)
-                              b[x] = ops1[rowo + k * cx + x];
-                          }
-                      }
-                  }
-#pragma unroll
-                for (int x = 0; x < k; ++x)
-                  res[x] = epi_value<T, KIND, TWO>(r[y][x], a[x], TWO ? b[x] : T(0), f1, f2);
-                if (cx == 0)
-                  {
-                    atomic_add(sh_dst + g, sh_a * r[y][0]);
+                    atomic_add(sh_dst + g, direct ? res[0] : r[y][0]);
+                    if (ni_out != nullptr)
+                      ni_out[g] = T(0);
 #pragma unroll
                     for (int x = 1; x < k; ++x)
                       dst[g + x] = res[x];
@@ -441,7 +511,7 @@ namespace dasm
                       dst[g + x] = res[x];
                   }
               }
-            if (cx == 3) // X = R: face of the +x neighbour
+            if (xred) // X = R: face of the +x neighbour
               atomic_add(sh_dst + foreign_index(desc, lists, 0, R * (Y + R * Z), Z * R + Y), sh_a * r[y][k]);
           }
         if (cy == 3) // Y = R: face of the +y neighbour, edge of the +xy neighbour
@@ -449,7 +519,7 @@ namespace dasm
 #pragma unroll
             for (int x = 0; x < k; ++x)
               atomic_add(sh_dst + foreign_index(desc, lists, 1, k * cx + x + R * R * Z, G::J_FY + Z * R + k * cx + x), sh_a * r[k][x]);
-            if (cx == 3)
+            if (xred)
               atomic_add(sh_dst + foreign_index(desc, lists, 3, R * R * Z, G::J_EXY + Z), sh_a * r[k][k]);
           }
       }
@@ -463,7 +533,7 @@ namespace dasm
 #pragma unroll
             for (int x = 0; x < k; ++x)
               atomic_add(sh_dst + foreign_index(desc, lists, 2, k * cx + x + R * Y, G::J_FZ + Y * R + k * cx + x), sh_a * r[y][x]);
-            if (cx == 3)
+            if (xred)
               atomic_add(sh_dst + foreign_index(desc, lists, 4, R * Y, G::J_EXZ + Y), sh_a * r[y][k]);
           }
         if (cy == 3)
@@ -471,7 +541,7 @@ namespace dasm
 #pragma unroll
             for (int x = 0; x < k; ++x)
               atomic_add(sh_dst + foreign_index(desc, lists, 5, k * cx + x, G::J_EYZ + k * cx + x), sh_a * r[k][x]);
-            if (cx == 3)
+            if (xred)
               atomic_add(sh_dst + foreign_index(desc, lists, 6, 0, G::J_C), sh_a * r[k][k]);
           }
       }
@@ -479,96 +549,42 @@ namespace dasm
 
   template <int k, typename T>
   __device__ __forceinline__ void
-  tma_epilogue_dispatch(const T (&r)[k + 1][k + 1], const T *ops0, const T *ops1, T *__restrict__ dst, T *__restrict__ acc, const Epilogue<T> &epi,
-                        const int shared_mode, const uint32_t *desc, const uint32_t *__restrict__ lists, const int cx, const int cy,
-                        const int cz, const int t)
+  tma_epilogue_dispatch(T (&r)[k + 1][k + 1], const T *ops0, const T *ops1, const T *carry_in, T *carry_out, T *__restrict__ dst, T *__restrict__ acc,
+                        const Epilogue<T> &epi, const int shared_mode, T *__restrict__ ni_out, const uint32_t *desc,
+                        const uint32_t *__restrict__ lists, const int cx, const int cy, const int cz, const int t)
   {
     const bool need1  = (epi.kind == EPI_CHEB && epi.f1 != T(0) && epi.v1 != nullptr);
     const T    alpha  = (epi.kind == EPI_RESIDUAL) ? T(-1) : ((epi.kind == EPI_CHEB || epi.kind == EPI_SCALE) ? epi.f2 : T(1));
     T *        sh_dst = (shared_mode == SHARED_DIRECT) ? dst : acc;
     const T    sh_a   = (shared_mode == SHARED_DIRECT) ? alpha : T(1);
+    const bool direct = (shared_mode == SHARED_DIRECT);
     if (epi.kind == EPI_CHEB && need1)
-      tma_epilogue<k, T, EPI_CHEB, true>(r, ops0, ops1, dst, sh_dst, sh_a, epi.f1, epi.f2, desc, lists, cx, cy, cz, t);
+      tma_epilogue<k, T, EPI_CHEB, true>(r, ops0, ops1, carry_in, carry_out, dst, sh_dst, sh_a, direct, ni_out, epi.f1, epi.f2, desc, lists, cx, cy, cz, t);
     else if (epi.kind == EPI_CHEB)
-      tma_epilogue<k, T, EPI_CHEB, false>(r, ops0, ops1, dst, sh_dst, sh_a, epi.f1, epi.f2, desc, lists, cx, cy, cz, t);
+      tma_epilogue<k, T, EPI_CHEB, false>(r, ops0, ops1, carry_in, carry_out, dst, sh_dst, sh_a, direct, ni_out, epi.f1, epi.f2, desc, lists, cx, cy, cz, t);
     else if (epi.kind == EPI_RESIDUAL)
-      tma_epilogue<k, T, EPI_RESIDUAL, false>(r, ops0, ops1, dst, sh_dst, sh_a, epi.f1, epi.f2, desc, lists, cx, cy, cz, t);
+      tma_epilogue<k, T, EPI_RESIDUAL, false>(r, ops0, ops1, carry_in, carry_out, dst, sh_dst, sh_a, direct, ni_out, epi.f1, epi.f2, desc, lists, cx, cy, cz, t);
     else if (epi.kind == EPI_SCALE)
-      tma_epilogue<k, T, EPI_SCALE, false>(r, ops0, ops1, dst, sh_dst, sh_a, epi.f1, epi.f2, desc, lists, cx, cy, cz, t);
+      tma_epilogue<k, T, EPI_SCALE, false>(r, ops0, ops1, carry_in, carry_out, dst, sh_dst, sh_a, direct, ni_out, epi.f1, epi.f2, desc, lists, cx, cy, cz, t);
     else
-      tma_epilogue<k, T, EPI_STORE, false>(r, ops0, ops1, dst, sh_dst, sh_a, epi.f1, epi.f2, desc, lists, cx, cy, cz, t);
+      tma_epilogue<k, T, EPI_STORE, false>(r, ops0, ops1, carry_in, carry_out, dst, sh_dst, sh_a, direct, ni_out, epi.f1, epi.f2, desc, lists, cx, cy, cz, t);
   }
 
-  // ---- mover warp: operand staging (tensor copies) and pre-initialisation of the next kernel's destination -------------------
-  enum
-  {
-    FB_OPS_EMPTY = 5 // compute -> mover: the operand boxes have been read
-  };
-
+  // operand boxes of a brick (one elected compute thread, after the barrier that ends the previous epilogue)
   template <int k, typename T>
   __device__ __forceinline__ void
-  tma_next_init(const NextInit<T> &ni, const uint32_t base, const int m)
+  tma_issue_ops(T *ops0, T *ops1, const CUtensorMap *map0, const CUtensorMap *map1, const bool need1, const uint32_t base, const unsigned mbar)
   {
-    using G = TmaGeom<k, T>;
-    if (ni.out == nullptr)
-      return;
-    const bool    h0 = ni.v0 != nullptr, h1 = (ni.v1 != nullptr && ni.f1 != T(0));
-    constexpr int B  = 12; // loads in flight per thread
-    for (int s0 = 0; s0 < G::NSH; s0 += B * G::NMT)
-      {
-        T a[B], b[B];
-#pragma unroll
-        for (int it = 0; it < B; ++it)
-          {
-            const int  s  = s0 + m + it * G::NMT;
-            const bool in = s < G::NSH;
-            const int  i  = G::shared_box_index(in ? s : 0);
-            a[it]         = (h0 && in) ? __ldg(ni.v0 + base + i) : T(0);
-            b[it]         = (h1 && in) ? __ldg(ni.v1 + base + i) : T(0);
-          }
-#pragma unroll
-        for (int it = 0; it < B; ++it)
-          {
-            const int s = s0 + m + it * G::NMT;
-            if (s < G::NSH)
-              ni.out[base + G::shared_box_index(s)] = a[it] + ni.f1 * (a[it] - b[it]);
-          }
-      }
+    using G                  = TmaGeom<k, T>;
+    constexpr unsigned bytes = (unsigned)(G::NB * sizeof(T));
+    const int          c3    = (int)(base / G::NB) * (TmaLayout<k, T>::PERM ? 32 : 1);
+    mbar_expect_tx(mbar, need1 ? 2 * bytes : bytes);
+    tma_load_4d((unsigned)__cvta_generic_to_shared(ops0), map0, 0, 0, 0, c3, mbar);
+    if (need1)
+      tma_load_4d((unsigned)__cvta_generic_to_shared(ops1), map1, 0, 0, 0, c3, mbar);
   }
 
-  template <int k, typename T>
-  __device__ __forceinline__ void
-  tma_mover_loop(T *ops0, T *ops1, const Epilogue<T> &epi, const CUtensorMap *map0, const CUtensorMap *map1, const TmaList &list,
-                 const NextInit<T> &ni, const int m, const unsigned mbar)
-  {
-    using G           = TmaGeom<k, T>;
-    const bool need0  = (epi.kind == EPI_RESIDUAL || epi.kind == EPI_CHEB);
-    const bool need1  = (epi.kind == EPI_CHEB && epi.f1 != T(0) && epi.v1 != nullptr);
-    const int  G1 = (int)gridDim.x;
-    const uint32_t *dw = reinterpret_cast<const uint32_t *>(list.bricks);
-    uint32_t        base = ldg_early(dw + (size_t)blockIdx.x * TMA_DW);
-    bool            first = true;
-    for (int it = blockIdx.x; it < list.n; it += G1)
-      {
-        const uint32_t base_n = (it + G1 < list.n) ? ldg_early(dw + (size_t)(it + G1) * TMA_DW) : 0u;
-        if (!first && need0)
-          bar_sync(FB_OPS_EMPTY, G::NCT + G::NMT); // the compute threads have read the operands of the previous brick
-        if (m == 0 && need0)
-          {
-            constexpr unsigned bytes = (unsigned)(G::NB * sizeof(T));
-            const int          c3    = (int)(base / G::NB) * (TmaLayout<k, T>::PERM ? 32 : 1);
-            mbar_expect_tx(mbar, need1 ? 2 * bytes : bytes);
-            tma_load_4d((unsigned)__cvta_generic_to_shared(ops0), map0, 0, 0, 0, c3, mbar);
-            if (need1)
-              tma_load_4d((unsigned)__cvta_generic_to_shared(ops1), map1, 0, 0, 0, c3, mbar);
-          }
-        tma_next_init<k, T>(ni, base, m);
-        base  = base_n;
-        first = false;
-      }
-  }
-
-  // shared memory of the kernels: header (mbarriers, two brick descriptors) | tile | X slots | operand boxes
+  // shared memory of the kernels: header (mbarriers, two brick descriptors) | tile | X slots | operand boxes | carry plane
   template <int k, typename T>
   struct TmaSmem
   {
@@ -581,12 +597,43 @@ namespace dasm
     static constexpr int TILE  = pad1k(G::TILE);
     static constexpr int XSLOT = pad1k(G::NCELLS * G::CS);
     static constexpr int OPS   = pad1k(G::NB);
+    static constexpr int CARRY = pad1k((G::R + 1) * (G::R + 1));
     static constexpr size_t
     bytes(const int n_x, const int n_ops)
     {
-      return 2048 + (size_t)(TILE + n_x * XSLOT + n_ops * OPS) * sizeof(T);
+      return 2048 + (size_t)(TILE + n_x * XSLOT + n_ops * OPS + 2 * CARRY) * sizeof(T);
     }
   };
+
+  // common pipeline pieces of the two kernels ------------------------------------------------------------------------------
+  // first tile of a block: descriptor -> s_desc[0], tensor copies (and the index-list gather of a mode-1 brick)
+  template <int k, typename T>
+  __device__ __forceinline__ void
+  tma_prologue(uint32_t *s_desc, T *tile, const TmaMaps &tmaps, const TmaList &list, const uint32_t idx, const T *__restrict__ src,
+               const unsigned mb_tile, const int tid)
+  {
+    using G            = TmaGeom<k, T>;
+    const uint32_t *dw = reinterpret_cast<const uint32_t *>(list.bricks);
+    if (tid < TMA_DW)
+      s_desc[tid] = ldg_early(dw + (size_t)idx * TMA_DW + tid);
+    bar_sync(FB_COMPUTE, G::NCT);
+    if (tid == 0)
+      tma_issue_tile<k, T>(tile, tmaps, s_desc, mb_tile);
+    if (list.any_mode1 && (s_desc[1] & TMA_MODE1))
+      tma_foreign_gather<k, T>(tile, list, s_desc[9], src, tid);
+  }
+
+  // after the barrier behind phase A: the tile is dead, fetch the next brick into it
+  template <int k, typename T>
+  __device__ __forceinline__ void
+  tma_fetch_next(const uint32_t *dn, T *tile, const TmaMaps &tmaps, const TmaList &list, const T *__restrict__ src, const unsigned mb_tile,
+                 const int tid)
+  {
+    if (tid == 0)
+      tma_issue_tile<k, T>(tile, tmaps, dn, mb_tile);
+    if (list.any_mode1 && (dn[1] & TMA_MODE1))
+      tma_foreign_gather<k, T>(tile, list, dn[9], src, tid);
+  }
 
   // ---- Laplace, uniform Cartesian geometry --------------------------------------------------------------------------------------
   template <int k, typename T>
@@ -606,7 +653,6 @@ namespace dasm
     using G           = TmaGeom<k, T>;
     using SM          = TmaSmem<k, T>;
     constexpr int n   = k + 1;
-    constexpr int NFT = G::NFT;
     extern __shared__ __align__(16) unsigned char smem_dyn[];
     // the tile and the operand boxes are written by the TMA engine with the 128-byte swizzle pattern: 1024-byte alignment
     unsigned char *smem_raw = smem_dyn + ((1024u - ((unsigned)__cvta_generic_to_shared(smem_dyn) & 1023u)) & 1023u);
@@ -618,7 +664,8 @@ namespace dasm
     T *            Xq      = tile + SM::TILE;
     T *            Xp      = Xq + SM::XSLOT;
     T *            ops0    = Xp + SM::XSLOT;
-    if ((int)blockIdx.x >= list.n)
+    T *            carry   = ops0 + SM::OPS;
+    if ((int)blockIdx.x >= list.n_chunks)
       return;
     if (threadIdx.x == 0)
       {
@@ -627,11 +674,6 @@ namespace dasm
       }
     __syncthreads();
 
-    if (threadIdx.x >= G::NCT)
-      {
-        tma_mover_loop<k, T>(ops0, ops0, epi, &omap0, &omap0, list, ni, threadIdx.x - G::NCT, mb_ops);
-        return;
-      }
     const int       tid = threadIdx.x;
     const int       c = tid % G::NCELLS, t = tid / G::NCELLS;
     const int       cx = c & 3, cy = (c >> 2) & 3, cz = c >> 4;
@@ -639,39 +681,18 @@ namespace dasm
     const PlaneAddr pa = tile_plane_y<k, T>(cx, cy, cz, t);
     T *             xq = Xq + c * G::CS, *xp = Xp + c * G::CS;
     const bool      need0 = (epi.kind == EPI_RESIDUAL || epi.kind == EPI_CHEB);
-    const int       G1 = (int)gridDim.x;
-    int             it = blockIdx.x;
     const uint32_t *dw = reinterpret_cast<const uint32_t *>(list.bricks);
     unsigned        tphase = 0, ophase = 0;
     int             par = 0; // s_desc[par]: this brick, s_desc[par ^ 1]: the next one
-    // first tile
-    uint32_t mode_next = 0, lo_next = 0;
-    {
-      if (tid < TMA_DW)
-        s_desc[tid] = ldg_early(dw + (size_t)it * TMA_DW + tid);
-      bar_sync(FB_COMPUTE, G::NCT);
-      if (tid == 0)
-        tma_issue_tile<k, T>(tile, tmaps, s_desc, mb_tile);
-      if (list.any_mode1)
-        {
-          uint32_t gf[NFT];
-          tma_foreign_idx_load<k, T>(gf, list, s_desc[1], s_desc[9], tid);
-          if (s_desc[1] != 0u)
-            tma_foreign_gather<k, T>(tile, gf, src, tid);
-        }
-      if (it + G1 < list.n)
-        {
-          mode_next = ldg_early(dw + (size_t)(it + G1) * TMA_DW + 1);
-          lo_next   = ldg_early(dw + (size_t)(it + G1) * TMA_DW + 9);
-        }
-    }
-    for (; it < list.n; it += G1, par ^= 1)
+    TmaWalk         w;
+    walk_init(w, list);
+    tma_prologue<k, T>(s_desc, tile, tmaps, list, w.idx, src, mb_tile, tid);
+    for (;; par ^= 1)
       {
-        const bool      has_next = it + G1 < list.n;
         const uint32_t *desc     = s_desc + par * 16;
-        uint32_t gfn[NFT];
-        if (list.any_mode1)
-          tma_foreign_idx_load<k, T>(gfn, list, has_next ? mode_next : 0u, lo_next, tid);
+        const bool      last     = (desc[1] & TMA_LAST) != 0u;
+        const uint32_t  nidx     = walk_peek(w, last);
+        const bool      has_next = nidx != TMA_NONE;
         mbar_wait(mb_tile, tphase); // the tensor copies of this brick's tile have landed
         tphase ^= 1u;
         if (list.any_mode1)
@@ -679,10 +700,13 @@ namespace dasm
         // foreign points gathered by the other threads (mode 1); all phase B reads of the exchange slots of the previous brick are
         // done before phase A overwrites them
         bar_sync(FB_COMPUTE, G::NCT);
+        // all threads have left the epilogue of the previous brick: its operand box may be overwritten
+        if (need0 && tid == 0)
+          tma_issue_ops<k, T>(ops0, ops0, &omap0, &omap0, false, desc[0], mb_ops);
         // descriptor of the next brick -> shared memory (fire and forget, awaited before the barrier after phase A; its buffer held
-        // the descriptor of the previous brick, whose epilogue all threads have left)
+        // the descriptor of the previous brick)
         if (has_next && tid < TMA_DW)
-          cp_async_4(s_desc + (par ^ 1) * 16 + tid, dw + (size_t)(it + G1) * TMA_DW + tid);
+          cp_async_4(s_desc + (par ^ 1) * 16 + tid, dw + (size_t)nidx * TMA_DW + tid);
         // phase A: plane y = t, [z][x]: q = Mx Mz v, p = (g0 Kx Mz + g2 Mx Kz) v
         if (!(dbgmaps.dbg & 1))
           {
@@ -719,19 +743,8 @@ namespace dasm
         if (has_next && tid < TMA_DW)
           cp_async_wait_all();
         bar_sync(FB_COMPUTE, G::NCT);
-        // the tile is dead: fetch the next brick into it
         if (has_next)
-          {
-            if (tid == 0)
-              tma_issue_tile<k, T>(tile, tmaps, s_desc + (par ^ 1) * 16, mb_tile);
-            if (list.any_mode1 && mode_next != 0u)
-              tma_foreign_gather<k, T>(tile, gfn, src, tid);
-          }
-        if (it + 2 * G1 < list.n)
-          {
-            mode_next = ldg_early(dw + (size_t)(it + 2 * G1) * TMA_DW + 1);
-            lo_next   = ldg_early(dw + (size_t)(it + 2 * G1) * TMA_DW + 9);
-          }
+          tma_fetch_next<k, T>(s_desc + (par ^ 1) * 16, tile, tmaps, list, src, mb_tile, tid);
         // phase B: plane z = t, [y][x]: r = My p + g1 Ky q  (+ plane z = k of the cell below for t = 0)
         T r[n][n];
         if (!skip_last)
@@ -769,9 +782,10 @@ namespace dasm
           mbar_wait(mb_ops, ophase); // the operand box has landed
         ophase ^= 1u;
         if (!skip_last && (t < k || cz == 3) && !(dbgmaps.dbg & 2))
-          tma_epilogue_dispatch<k, T>(r, ops0, ops0, dst, acc, epi, shared_mode, desc, list.foreign, cx, cy, cz, t);
-        if (has_next && need0)
-          bar_arrive(FB_OPS_EMPTY, G::NCT + G::NMT);
+          tma_epilogue_dispatch<k, T>(r, ops0, ops0, carry + par * SM::CARRY, carry + (par ^ 1) * SM::CARRY, dst, acc, epi, shared_mode, ni.out, desc, list.foreign, cx, cy, cz, t);
+        if (!has_next)
+          break;
+        walk_advance(w, last, list);
       }
   }
 
@@ -794,7 +808,6 @@ namespace dasm
     using G           = TmaGeom<k, T>;
     using SM          = TmaSmem<k, T>;
     constexpr int n   = k + 1;
-    constexpr int NFT = G::NFT;
     extern __shared__ __align__(16) unsigned char smem_dyn[];
     unsigned char *smem_raw = smem_dyn + ((1024u - ((unsigned)__cvta_generic_to_shared(smem_dyn) & 1023u)) & 1023u);
     const unsigned mb_tile = (unsigned)__cvta_generic_to_shared(smem_raw);
@@ -804,8 +817,9 @@ namespace dasm
     T *            X       = tile + SM::TILE;
     T *            ops0    = X + SM::XSLOT;
     T *            ops1    = ops0 + SM::OPS;
+    T *            carry   = ops1 + SM::OPS;
     __shared__ T   s_inv[n * n * n];
-    if ((int)blockIdx.x >= list.n)
+    if ((int)blockIdx.x >= list.n_chunks)
       return;
     for (int i = threadIdx.x; i < n * n * n; i += G::NT)
       s_inv[i] = mats.inv[i];
@@ -816,11 +830,6 @@ namespace dasm
       }
     __syncthreads();
 
-    if (threadIdx.x >= G::NCT)
-      {
-        tma_mover_loop<k, T>(ops0, ops1, epi, &omap0, &omap1, list, ni, threadIdx.x - G::NCT, mb_ops);
-        return;
-      }
     const int       tid = threadIdx.x;
     const int       c = tid % G::NCELLS, t = tid / G::NCELLS;
     const int       cx = c & 3, cy = (c >> 2) & 3, cz = c >> 4;
@@ -829,38 +838,19 @@ namespace dasm
     T *             xs = X + c * G::CS;
     const T *       inv = s_inv + t * n; // row (z, y = t) of this thread's plane in phase B: broadcast reads
     const bool      need0 = (epi.kind == EPI_RESIDUAL || epi.kind == EPI_CHEB);
-    const int       G1 = (int)gridDim.x;
-    int             it = blockIdx.x;
+    const bool      need1 = (epi.kind == EPI_CHEB && epi.f1 != T(0) && epi.v1 != nullptr);
     const uint32_t *dw = reinterpret_cast<const uint32_t *>(list.bricks);
     unsigned        tphase = 0, ophase = 0;
     int             par = 0;
-    uint32_t        mode_next = 0, lo_next = 0;
-    {
-      if (tid < TMA_DW)
-        s_desc[tid] = ldg_early(dw + (size_t)it * TMA_DW + tid);
-      bar_sync(FB_COMPUTE, G::NCT);
-      if (tid == 0)
-        tma_issue_tile<k, T>(tile, tmaps, s_desc, mb_tile);
-      if (list.any_mode1)
-        {
-          uint32_t gf[NFT];
-          tma_foreign_idx_load<k, T>(gf, list, s_desc[1], s_desc[9], tid);
-          if (s_desc[1] != 0u)
-            tma_foreign_gather<k, T>(tile, gf, src, tid);
-        }
-      if (it + G1 < list.n)
-        {
-          mode_next = ldg_early(dw + (size_t)(it + G1) * TMA_DW + 1);
-          lo_next   = ldg_early(dw + (size_t)(it + G1) * TMA_DW + 9);
-        }
-    }
-    for (; it < list.n; it += G1, par ^= 1)
+    TmaWalk         w;
+    walk_init(w, list);
+    tma_prologue<k, T>(s_desc, tile, tmaps, list, w.idx, src, mb_tile, tid);
+    for (;; par ^= 1)
       {
-        const bool      has_next = it + G1 < list.n;
         const uint32_t *desc     = s_desc + par * 16;
-        uint32_t gfn[NFT];
-        if (list.any_mode1)
-          tma_foreign_idx_load<k, T>(gfn, list, has_next ? mode_next : 0u, lo_next, tid);
+        const bool      last     = (desc[1] & TMA_LAST) != 0u;
+        const uint32_t  nidx     = walk_peek(w, last);
+        const bool      has_next = nidx != TMA_NONE;
         mbar_wait(mb_tile, tphase);
         tphase ^= 1u;
         if (list.any_mode1)
@@ -868,8 +858,10 @@ namespace dasm
         // foreign points gathered by the other threads (mode 1); all phase C reads of the exchange slot of the previous brick are
         // done before phase A overwrites it
         bar_sync(FB_COMPUTE, G::NCT);
+        if (need0 && tid == 0)
+          tma_issue_ops<k, T>(ops0, ops1, &omap0, &omap1, need1, desc[0], mb_ops);
         if (has_next && tid < TMA_DW)
-          cp_async_4(s_desc + (par ^ 1) * 16 + tid, dw + (size_t)(it + G1) * TMA_DW + tid);
+          cp_async_4(s_desc + (par ^ 1) * 16 + tid, dw + (size_t)nidx * TMA_DW + tid);
         // phase A: plane z = t, [y][x]: Ax in x, Ay in y
         if (!(dbgmaps.dbg & 1))
           {
@@ -897,23 +889,12 @@ namespace dasm
         if (has_next && tid < TMA_DW)
           cp_async_wait_all();
         bar_sync(FB_COMPUTE, G::NCT);
-        // the tile is dead: fetch the next brick into it
         if (has_next)
-          {
-            if (tid == 0)
-              tma_issue_tile<k, T>(tile, tmaps, s_desc + (par ^ 1) * 16, mb_tile);
-            if (list.any_mode1 && mode_next != 0u)
-              tma_foreign_gather<k, T>(tile, gfn, src, tid);
-          }
-        if (it + 2 * G1 < list.n)
-          {
-            mode_next = ldg_early(dw + (size_t)(it + 2 * G1) * TMA_DW + 1);
-            lo_next   = ldg_early(dw + (size_t)(it + 2 * G1) * TMA_DW + 9);
-          }
+          tma_fetch_next<k, T>(s_desc + (par ^ 1) * 16, tile, tmaps, list, src, mb_tile, tid);
         // phase B: plane y = t, [z][x]: Az, scale, Bz in z; Bx in x
         if (!(dbgmaps.dbg & 1))
           {
-            T w[n][n];
+            T wv[n][n];
 #pragma unroll
             for (int x = 0; x < n; ++x)
               {
@@ -928,13 +909,13 @@ namespace dasm
                 mat_vec<n, T, false, true, false>(col, mats.Bz, u);
 #pragma unroll
                 for (int z = 0; z < n; ++z)
-                  w[z][x] = col[z];
+                  wv[z][x] = col[z];
               }
 #pragma unroll
             for (int z = 0; z < n; ++z)
               {
                 T u[n];
-                mat_vec<n, T, false, true, false>(u, mats.Bx, w[z]);
+                mat_vec<n, T, false, true, false>(u, mats.Bx, wv[z]);
 #pragma unroll
                 for (int x = 0; x < n; ++x)
                   xs[(z * n + t) * n + x] = u[x];
@@ -970,9 +951,10 @@ namespace dasm
           mbar_wait(mb_ops, ophase);
         ophase ^= 1u;
         if (!skip_last && (t < k || cz == 3) && !(dbgmaps.dbg & 2))
-          tma_epilogue_dispatch<k, T>(r, ops0, ops1, dst, acc, epi, shared_mode, desc, list.foreign, cx, cy, cz, t);
-        if (has_next && need0)
-          bar_arrive(FB_OPS_EMPTY, G::NCT + G::NMT);
+          tma_epilogue_dispatch<k, T>(r, ops0, ops1, carry + par * SM::CARRY, carry + (par ^ 1) * SM::CARRY, dst, acc, epi, shared_mode, ni.out, desc, list.foreign, cx, cy, cz, t);
+        if (!has_next)
+          break;
+        walk_advance(w, last, list);
       }
   }
 } // namespace dasm
