@@ -338,7 +338,11 @@ namespace dasm
         v[1]             = p0.y;
         v[2]             = p1.x;
         v[3]             = p1.y;
-        v[4]             = (cx == 3) ? tile[r < k ? a.x0 + r * a.xs : a.xk] : tile[rowo + (((2 * cx + 2) ^ sw) << 1)];
+        // x = k is x = 0 of the +x neighbour cell (lane + 1), or a point of the +x face of the brick
+        const double nbv = __shfl_down_sync(0xffffffffu, p0.x, 1);
+        v[4]             = nbv;
+        if (cx == 3)
+          v[4] = tile[r < k ? a.x0 + r * a.xs : a.xk];
       }
     else if constexpr (L::PERM)
       {
@@ -347,7 +351,10 @@ namespace dasm
         v[1]            = p0.y;
         v[2]            = p0.z;
         v[3]            = p0.w;
-        v[4]            = (cx == 3) ? tile[r < k ? a.x0 + r * a.xs : a.xk] : tile[rowo + 4 * cx + 4];
+        const float nbv = __shfl_down_sync(0xffffffffu, p0.x, 1);
+        v[4]            = nbv;
+        if (cx == 3)
+          v[4] = tile[r < k ? a.x0 + r * a.xs : a.xk];
       }
     else
       {
@@ -355,7 +362,10 @@ namespace dasm
 #pragma unroll
         for (int x = 0; x < k; ++x)
           v[x] = row[x];
-        v[k] = (cx == 3) ? tile[r < k ? a.x0 + r * a.xs : a.xk] : row[k];
+        const T nbv = __shfl_down_sync(0xffffffffu, v[0], 1);
+        v[k]        = nbv;
+        if (cx == 3)
+          v[k] = tile[r < k ? a.x0 + r * a.xs : a.xk];
       }
   }
 
@@ -366,17 +376,27 @@ namespace dasm
   // faces are private: epilogue with the operands from the (TMA-staged) operand boxes in shared memory and plain global
   // stores straight from the registers.  Points on X = 0, Y = 0 or Z = 0 of the own box, and the points owned by the 7 upper
   // neighbours (X = R, Y = R or Z = R), get red.global.add of alpha y (shared-face protocol of kernels_brick.cuh).
-  template <typename T, int KIND, bool TWO>
-  __device__ __forceinline__ T
-  epi_value(const T y, const T a, const T b, const T f1, const T f2)
+  // All epilogues are one affine form: dst = sa a + cy y + f1 (a - b)
+  //   EPI_STORE (0, 1, 0)   EPI_RESIDUAL (1, -1, 0)   EPI_CHEB (1, f2, f1)   EPI_SCALE (0, f2, 0)
+  // with the operands a (b) read only if need0 (need1).
+  template <typename T>
+  struct EpiCoef
   {
-    if (KIND == EPI_RESIDUAL)
-      return a - y;
-    if (KIND == EPI_CHEB)
-      return a + f2 * y + f1 * (a - (TWO ? b : T(0)));
-    if (KIND == EPI_SCALE)
-      return f2 * y;
-    return y;
+    T    sa, cy, f1;
+    bool need0, need1;
+  };
+
+  template <typename T>
+  __device__ __forceinline__ EpiCoef<T>
+  epi_coef(const Epilogue<T> &epi)
+  {
+    EpiCoef<T> c;
+    c.need0 = (epi.kind == EPI_RESIDUAL || epi.kind == EPI_CHEB);
+    c.need1 = (epi.kind == EPI_CHEB && epi.f1 != T(0) && epi.v1 != nullptr);
+    c.sa    = c.need0 ? T(1) : T(0);
+    c.cy    = (epi.kind == EPI_RESIDUAL) ? T(-1) : ((epi.kind == EPI_CHEB || epi.kind == EPI_SCALE) ? epi.f2 : T(1));
+    c.f1    = (epi.kind == EPI_CHEB) ? epi.f1 : T(0); // (v1 == nullptr: b = 0, the f1 term stays)
+    return c;
   }
 
   // global index of a point owned by upper neighbour q (0 +x, 1 +y, 2 +z, 3 +xy, 4 +xz, 5 +yz, 6 +xyz): box offset `off`
@@ -388,11 +408,12 @@ namespace dasm
   }
 
   // carry: [R + 1][R + 1] values of the plane X = R (Z slow, Y fast) handed from a brick to its +x neighbour
-  template <int k, typename T, int KIND, bool TWO>
+  // NOPS: number of epilogue operands staged in shared memory (0: store / scale, 1: residual or update without x_old, 2: update)
+  template <int k, typename T, int NOPS>
   __device__ __forceinline__ void
-  tma_epilogue(T (&r)[k + 1][k + 1], const T *ops0, const T *ops1, const T *carry_in, T *carry_out, T *__restrict__ dst, T *__restrict__ sh_dst, const T sh_a,
-               const bool direct, T *__restrict__ ni_out, const T f1, const T f2, const uint32_t *desc, const uint32_t *__restrict__ lists, const int cx, const int cy, const int cz,
-               const int t)
+  tma_epilogue(T (&r)[k + 1][k + 1], const T *ops0, const T *ops1, const T *carry_in, T *carry_out, T *__restrict__ dst, T *__restrict__ sh_dst,
+               const bool direct, T *__restrict__ ni_out, const EpiCoef<T> &ec, const uint32_t *desc, const uint32_t *__restrict__ lists,
+               const int cx, const int cy, const int cz, const int t)
   {
     using G         = TmaGeom<k, T>;
     using L         = TmaLayout<k, T>;
@@ -400,6 +421,7 @@ namespace dasm
     const uint32_t  base = desc[0];
     const bool      cin = (desc[1] & TMA_CARRY_IN) != 0u, cout = (desc[1] & TMA_CARRY_OUT) != 0u;
     const int       Z = k * cz + t;
+    const T         sh_a = direct ? ec.cy : T(1); // factor of y in the red.add of a point another brick owns
     // (two carry planes, alternating per brick: no thread writes the plane another one still reads)
     const T *       c_in  = carry_in + Z * (R + 1) + k * cy;
     T *             c_out = carry_out + Z * (R + 1) + k * cy;
@@ -425,23 +447,27 @@ namespace dasm
     const bool x0sh = (cx == 0) && !cin;  // the own face X = 0 is shared with a brick processed elsewhere
     if (Z < R)
       {
-        const bool zsh = (Z == 0);
+        const bool     zsh = (Z == 0);
+        const int      Y0 = k * cy;
+        const uint32_t g0 = base + (uint32_t)((Z * R + Y0) * R + k * cx);
+        // operand rows: row y at rowo0 + y rstep, swizzle sw0 ^ (2 y)
+        const int rho0 = L::row(Y0, Z), rowo0 = rho0 * R, sw0 = L::swz(rho0);
+        constexpr int rstep = (L::PERM ? 2 : 1) * R;
 #pragma unroll
         for (int y = 0; y < k; ++y)
           {
-            const int      Y  = k * cy + y;
-            const uint32_t g  = base + (uint32_t)((Z * R + Y) * R + k * cx);
-            const bool     sh = zsh || (Y == 0);
+            const uint32_t g  = g0 + (uint32_t)(y * R);
+            const bool     sh = zsh || (Y0 + y == 0);
             T              a[k], b[k], res[k];
-            if (KIND == EPI_RESIDUAL || KIND == EPI_CHEB)
+            if constexpr (NOPS >= 1)
               {
-                const int rho = L::row(Y, Z), rowo = rho * R, sw = L::swz(rho);
+                const int rowo = rowo0 + y * rstep, sw = sw0 ^ (L::SWZ ? 2 * y : 0);
                 if constexpr (L::SWZ)
                   {
                     const double2 a0 = *reinterpret_cast<const double2 *>(ops0 + rowo + (((2 * cx) ^ sw) << 1));
                     const double2 a1 = *reinterpret_cast<const double2 *>(ops0 + rowo + (((2 * cx + 1) ^ sw) << 1));
                     a[0] = a0.x, a[1] = a0.y, a[2] = a1.x, a[3] = a1.y;
-                    if (TWO)
+                    if constexpr (NOPS == 2)
                       {
                         const double2 b0 = *reinterpret_cast<const double2 *>(ops1 + rowo + (((2 * cx) ^ sw) << 1));
                         const double2 b1 = *reinterpret_cast<const double2 *>(ops1 + rowo + (((2 * cx + 1) ^ sw) << 1));
@@ -452,7 +478,7 @@ namespace dasm
                   {
                     const float4 a0 = *reinterpret_cast<const float4 *>(ops0 + rowo + 4 * cx);
                     a[0] = a0.x, a[1] = a0.y, a[2] = a0.z, a[3] = a0.w;
-                    if (TWO)
+                    if constexpr (NOPS == 2)
                       {
                         const float4 b0 = *reinterpret_cast<const float4 *>(ops1 + rowo + 4 * cx);
                         b[0] = b0.x, b[1] = b0.y, b[2] = b0.z, b[3] = b0.w;
@@ -464,14 +490,21 @@ namespace dasm
                     for (int x = 0; x < k; ++x)
                       {
                         a[x] = ops0[rowo + k * cx + x];
-                        if (TWO)
+                        if constexpr (NOPS == 2)
                           b[x] = ops1[rowo + k * cx + x];
                       }
                   }
               }
 #pragma unroll
             for (int x = 0; x < k; ++x)
-              res[x] = epi_value<T, KIND, TWO>(r[y][x], a[x], TWO ? b[x] : T(0), f1, f2);
+              {
+                if constexpr (NOPS == 2)
+                  res[x] = a[x] + ec.cy * r[y][x] + ec.f1 * (a[x] - b[x]);
+                else if constexpr (NOPS == 1)
+                  res[x] = a[x] + ec.cy * r[y][x] + ec.f1 * a[x];
+                else
+                  res[x] = ec.cy * r[y][x];
+              }
             if (sh)
               {
                 // own DoFs on the shared faces Y = 0 / Z = 0: this brick adds the full epilogue value; the next kernel's
@@ -512,7 +545,7 @@ namespace dasm
                   }
               }
             if (xred) // X = R: face of the +x neighbour
-              atomic_add(sh_dst + foreign_index(desc, lists, 0, R * (Y + R * Z), Z * R + Y), sh_a * r[y][k]);
+              atomic_add(sh_dst + foreign_index(desc, lists, 0, R * (Y0 + y + R * Z), Z * R + Y0 + y), sh_a * r[y][k]);
           }
         if (cy == 3) // Y = R: face of the +y neighbour, edge of the +xy neighbour
           {
@@ -545,29 +578,6 @@ namespace dasm
               atomic_add(sh_dst + foreign_index(desc, lists, 6, 0, G::J_C), sh_a * r[k][k]);
           }
       }
-  }
-
-  template <int k, typename T>
-  __device__ __forceinline__ void
-  tma_epilogue_dispatch(T (&r)[k + 1][k + 1], const T *ops0, const T *ops1, const T *carry_in, T *carry_out, T *__restrict__ dst, T *__restrict__ acc,
-                        const Epilogue<T> &epi, const int shared_mode, T *__restrict__ ni_out, const uint32_t *desc,
-                        const uint32_t *__restrict__ lists, const int cx, const int cy, const int cz, const int t)
-  {
-    const bool need1  = (epi.kind == EPI_CHEB && epi.f1 != T(0) && epi.v1 != nullptr);
-    const T    alpha  = (epi.kind == EPI_RESIDUAL) ? T(-1) : ((epi.kind == EPI_CHEB || epi.kind == EPI_SCALE) ? epi.f2 : T(1));
-    T *        sh_dst = (shared_mode == SHARED_DIRECT) ? dst : acc;
-    const T    sh_a   = (shared_mode == SHARED_DIRECT) ? alpha : T(1);
-    const bool direct = (shared_mode == SHARED_DIRECT);
-    if (epi.kind == EPI_CHEB && need1)
-      tma_epilogue<k, T, EPI_CHEB, true>(r, ops0, ops1, carry_in, carry_out, dst, sh_dst, sh_a, direct, ni_out, epi.f1, epi.f2, desc, lists, cx, cy, cz, t);
-    else if (epi.kind == EPI_CHEB)
-      tma_epilogue<k, T, EPI_CHEB, false>(r, ops0, ops1, carry_in, carry_out, dst, sh_dst, sh_a, direct, ni_out, epi.f1, epi.f2, desc, lists, cx, cy, cz, t);
-    else if (epi.kind == EPI_RESIDUAL)
-      tma_epilogue<k, T, EPI_RESIDUAL, false>(r, ops0, ops1, carry_in, carry_out, dst, sh_dst, sh_a, direct, ni_out, epi.f1, epi.f2, desc, lists, cx, cy, cz, t);
-    else if (epi.kind == EPI_SCALE)
-      tma_epilogue<k, T, EPI_SCALE, false>(r, ops0, ops1, carry_in, carry_out, dst, sh_dst, sh_a, direct, ni_out, epi.f1, epi.f2, desc, lists, cx, cy, cz, t);
-    else
-      tma_epilogue<k, T, EPI_STORE, false>(r, ops0, ops1, carry_in, carry_out, dst, sh_dst, sh_a, direct, ni_out, epi.f1, epi.f2, desc, lists, cx, cy, cz, t);
   }
 
   // operand boxes of a brick (one elected compute thread, after the barrier that ends the previous epilogue)
@@ -636,7 +646,7 @@ namespace dasm
   }
 
   // ---- Laplace, uniform Cartesian geometry --------------------------------------------------------------------------------------
-  template <int k, typename T>
+  template <int k, typename T, int NOPS>
   __global__ void __launch_bounds__(TmaGeom<k, T>::NT, 1)
   laplace_tma_kernel(const T *__restrict__ src,
                      T *__restrict__ dst,
@@ -680,8 +690,10 @@ namespace dasm
     const bool      skip_last = ((t == k) && (cz < 2)) || (dbgmaps.dbg & 1); // whole warp: its plane z = k belongs to the cell above
     const PlaneAddr pa = tile_plane_y<k, T>(cx, cy, cz, t);
     T *             xq = Xq + c * G::CS, *xp = Xp + c * G::CS;
-    const bool      need0 = (epi.kind == EPI_RESIDUAL || epi.kind == EPI_CHEB);
-    const uint32_t *dw = reinterpret_cast<const uint32_t *>(list.bricks);
+    const EpiCoef<T> ec     = epi_coef(epi);
+    constexpr bool   need0  = NOPS >= 1;
+    const bool       direct = (shared_mode == SHARED_DIRECT);
+    const uint32_t * dw     = reinterpret_cast<const uint32_t *>(list.bricks);
     unsigned        tphase = 0, ophase = 0;
     int             par = 0; // s_desc[par]: this brick, s_desc[par ^ 1]: the next one
     TmaWalk         w;
@@ -782,7 +794,8 @@ namespace dasm
           mbar_wait(mb_ops, ophase); // the operand box has landed
         ophase ^= 1u;
         if (!skip_last && (t < k || cz == 3) && !(dbgmaps.dbg & 2))
-          tma_epilogue_dispatch<k, T>(r, ops0, ops0, carry + par * SM::CARRY, carry + (par ^ 1) * SM::CARRY, dst, acc, epi, shared_mode, ni.out, desc, list.foreign, cx, cy, cz, t);
+          tma_epilogue<k, T, NOPS>(r, ops0, ops0, carry + par * SM::CARRY, carry + (par ^ 1) * SM::CARRY, dst, direct ? dst : acc, direct, ni.out, ec, desc,
+                             list.foreign, cx, cy, cz, t);
         if (!has_next)
           break;
         walk_advance(w, last, list);
@@ -790,7 +803,7 @@ namespace dasm
   }
 
   // ---- FDM, one eigen-decomposition triple, tensor-product weights folded into the matrices ----------------------------------
-  template <int k, typename T>
+  template <int k, typename T, int NOPS>
   __global__ void __launch_bounds__(TmaGeom<k, T>::NT, 1)
   fdm_tma_kernel(const T *__restrict__ src,
                  T *__restrict__ dst,
@@ -837,9 +850,10 @@ namespace dasm
     const PlaneAddr pa = tile_plane_z<k, T>(cx, cy, cz, t);
     T *             xs = X + c * G::CS;
     const T *       inv = s_inv + t * n; // row (z, y = t) of this thread's plane in phase B: broadcast reads
-    const bool      need0 = (epi.kind == EPI_RESIDUAL || epi.kind == EPI_CHEB);
-    const bool      need1 = (epi.kind == EPI_CHEB && epi.f1 != T(0) && epi.v1 != nullptr);
-    const uint32_t *dw = reinterpret_cast<const uint32_t *>(list.bricks);
+    const EpiCoef<T> ec     = epi_coef(epi);
+    constexpr bool   need0 = NOPS >= 1, need1 = NOPS == 2;
+    const bool       direct = (shared_mode == SHARED_DIRECT);
+    const uint32_t * dw     = reinterpret_cast<const uint32_t *>(list.bricks);
     unsigned        tphase = 0, ophase = 0;
     int             par = 0;
     TmaWalk         w;
@@ -951,7 +965,8 @@ namespace dasm
           mbar_wait(mb_ops, ophase);
         ophase ^= 1u;
         if (!skip_last && (t < k || cz == 3) && !(dbgmaps.dbg & 2))
-          tma_epilogue_dispatch<k, T>(r, ops0, ops1, carry + par * SM::CARRY, carry + (par ^ 1) * SM::CARRY, dst, acc, epi, shared_mode, ni.out, desc, list.foreign, cx, cy, cz, t);
+          tma_epilogue<k, T, NOPS>(r, ops0, ops1, carry + par * SM::CARRY, carry + (par ^ 1) * SM::CARRY, dst, direct ? dst : acc, direct, ni.out, ec, desc,
+                             list.foreign, cx, cy, cz, t);
         if (!has_next)
           break;
         walk_advance(w, last, list);

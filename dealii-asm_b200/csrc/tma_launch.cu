@@ -152,8 +152,9 @@ namespace dasm
     eo_fill(mats.K0, P[1], Q[1]);
     eo_fill(mats.K1, P[2], Q[2]);
     eo_fill(mats.K2, P[3], Q[3]);
-    constexpr size_t smem = TmaSmem<K, T>::bytes(2, 1);
-    auto             kern = laplace_tma_kernel<K, T>;
+    constexpr size_t smem  = TmaSmem<K, T>::bytes(2, 1);
+    const bool       need0 = (epi.kind == EPI_RESIDUAL || epi.kind == EPI_CHEB);
+    auto             kern  = need0 ? laplace_tma_kernel<K, T, 1> : laplace_tma_kernel<K, T, 0>;
     check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "laplace_tma_kernel attribute");
     const FastMaps fm = {nullptr, nullptr, nullptr, nullptr, 0, nullptr, dbg};
     kern<<<grid, G::NT, smem, stream>>>(src, dst, acc, epi, mats, maps, omap0, shared_mode, ni, list, fm);
@@ -177,8 +178,10 @@ namespace dasm
     eo_fill(mats.Bz, P[5], Q[5]);
     for (int i = 0; i < n * n * n; ++i)
       mats.inv[i] = (T)inv[i];
-    constexpr size_t smem = TmaSmem<K, T>::bytes(1, 2);
-    auto             kern = fdm_tma_kernel<K, T>;
+    constexpr size_t smem  = TmaSmem<K, T>::bytes(1, 2);
+    const bool       need0 = (epi.kind == EPI_RESIDUAL || epi.kind == EPI_CHEB);
+    const bool       need1 = (epi.kind == EPI_CHEB && epi.f1 != T(0) && epi.v1 != nullptr);
+    auto             kern  = need1 ? fdm_tma_kernel<K, T, 2> : (need0 ? fdm_tma_kernel<K, T, 1> : fdm_tma_kernel<K, T, 0>);
     check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "fdm_tma_kernel attribute");
     const FastMaps fm = {nullptr, nullptr, nullptr, nullptr, 0, nullptr, dbg};
     kern<<<grid, G::NT, smem, stream>>>(src, dst, acc, epi, mats, maps, omap0, omap1, shared_mode, ni, list, fm);
