@@ -58,7 +58,7 @@ def lib():
         _lib.dasm_version.restype = ctypes.c_char_p
         _lib.dasm_ctx_stream.restype = ctypes.c_void_p
         for name in ("dasm_ctx_launch_count", "dasm_mesh_n_cells", "dasm_mesh_n_global_cells", "dasm_op_n_dofs",
-                     "dasm_op_n_ghost", "dasm_op_vec_size", "dasm_op_n_global_dofs", "dasm_op_constrained_dofs",
+                     "dasm_op_n_ghost", "dasm_op_n_import", "dasm_op_vec_size", "dasm_op_n_global_dofs", "dasm_op_constrained_dofs",
                      "dasm_fdm_n_instances", "dasm_fdm_memory_consumption", "dasm_op_n_fast_bricks", "dasm_fdm_n_fast_bricks"):
             getattr(_lib, name).restype = ctypes.c_longlong
     return _lib

@@ -294,8 +294,6 @@ struct dasm_op
   int               max_smem  = 48 * 1024; // opt-in dynamic shared memory per block
   // warp-specialised kernels (kernels_fast.cuh) for the regular bricks; the other bricks go through the brick kernels
   bool              fast_ok     = false;
-  uint16_t *        d_fast_ltab = nullptr;
-  uint16_t *        d_fast_ftab = nullptr;
   uint32_t *        d_fast_ids  = nullptr; // regular bricks
   uint32_t *        d_slow_ids  = nullptr; // all other bricks
   int               n_fast = 0, n_slow = 0;
@@ -367,6 +365,7 @@ struct dasm_cheb
   double    min_ev = 0, max_ev = 0, delta = 0, theta = 0;
   void *    d_inv_diag = nullptr;
   void *    t1 = nullptr, *t1b = nullptr, *t2 = nullptr, *xold = nullptr, *xin = nullptr, *bin = nullptr;
+  void *    d_stage = nullptr; // single precision: double staging buffer of the host entry points
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -491,34 +490,6 @@ eo_fill(EOMat<T, n> &E, const double *P, const double *Q)
     E.P[i] = (T)P[i];
   for (int i = 0; i < h * h; ++i)
     E.Q[i] = (T)Q[i];
-}
-
-// tile layout parameters of kernels_fast.cuh (FastSkew) for the host-side table construction
-static void
-fast_tile_params(const int k, const int esize, int &skew, int &padz)
-{
-  skew = 0;
-  padz = 0;
-  if (esize == 8)
-    {
-      switch (k)
-        {
-          case 3: skew = FastSkew<3, 8>::skew; padz = FastSkew<3, 8>::padz; break;
-          case 4: skew = FastSkew<4, 8>::skew; padz = FastSkew<4, 8>::padz; break;
-          case 5: skew = FastSkew<5, 8>::skew; padz = FastSkew<5, 8>::padz; break;
-          default: break;
-        }
-    }
-  else
-    {
-      switch (k)
-        {
-          case 3: skew = FastSkew<3, 4>::skew; padz = FastSkew<3, 4>::padz; break;
-          case 4: skew = FastSkew<4, 4>::skew; padz = FastSkew<4, 4>::padz; break;
-          case 5: skew = FastSkew<5, 4>::skew; padz = FastSkew<5, 4>::padz; break;
-          default: break;
-        }
-    }
 }
 
 static inline unsigned
@@ -714,58 +685,12 @@ epilogue_n_operands(const Epilogue<T> &epi)
   return 0;
 }
 
-// optional timing instrumentation of the warp-specialised kernels (DASM_FAST_PROF=1): clock64() stamps of compute thread 0
-// (events 0-7, 13, 14) and mover thread 0 (8-12) for the first 16 bricks of every block; average intervals to stderr
+// timing experiments with the warp-specialised kernels (DASM_FAST_DBG, results invalid; kernels_fast.cuh FastMaps)
 static int
 fast_dbg()
 {
   static const int v = getenv("DASM_FAST_DBG") ? atoi(getenv("DASM_FAST_DBG")) : 0;
   return v;
-}
-
-static long long *
-fast_prof_buffer(const int grid)
-{
-  static const bool on = getenv("DASM_FAST_PROF") && getenv("DASM_FAST_PROF")[0] == '1';
-  if (!on)
-    return nullptr;
-  static long long *d = nullptr;
-  if (!d)
-    cudaMalloc(&d, (size_t)1024 * 256 * sizeof(long long));
-  cudaMemset(d, 0, (size_t)1024 * 256 * sizeof(long long));
-  (void)grid;
-  return d;
-}
-
-static void
-fast_prof_report(const char *name, long long *d, const int grid, cudaStream_t s)
-{
-  if (!d)
-    return;
-  cudaStreamSynchronize(s);
-  std::vector<long long> h((size_t)grid * 256);
-  cudaMemcpy(h.data(), d, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
-  // average over blocks of the intervals of iterations 4..11
-  double sum[16][16] = {{0}};
-  int    cnt         = 0;
-  for (int b = 0; b < grid; ++b)
-    for (int it = 4; it < 12; ++it)
-      {
-        const long long *e = h.data() + ((size_t)b * 16 + it) * 16;
-        const long long *p = h.data() + ((size_t)b * 16 + it - 1) * 16;
-        if (e[0] == 0 || e[14] == 0 || p[0] == 0)
-          continue;
-        ++cnt;
-        for (int i = 0; i < 16; ++i)
-          sum[0][i] += (double)(e[i] - e[0]);
-        sum[1][0] += (double)(e[0] - p[0]);
-      }
-  if (cnt == 0)
-    return;
-  fprintf(stderr, "[fast prof] %s: brick period %.0f cycles; offsets from compute top:", name, sum[1][0] / cnt);
-  for (int i = 0; i < 16; ++i)
-    fprintf(stderr, " e%d=%.0f", i, sum[0][i] / cnt);
-  fprintf(stderr, "\n");
 }
 
 // ---- overlap of the halo exchange with the interior bricks (fused SHARED_DIRECT sequences on several ranks) --------------
@@ -932,41 +857,23 @@ launch_laplace_fast(dasm_op *op, T *dst, const T *src, const Epilogue<T> &epi, c
     count = op->n_fast - first;
   if (count == 0)
     return true;
-  using G             = FastGeom<K, T>;
-  constexpr size_t smem = G::smem_bytes(1, 2, 1);
-  if (smem > (size_t)op->max_smem || epilogue_n_operands(epi) > 1) // one operand buffer (b of the residual epilogue)
+  if (!op->tma_ok || epilogue_n_operands(epi) > 1) // one operand box (b of the residual epilogue)
     return false;
-  if (op->tma_ok)
-    {
-      const TmaMaps *tm = tma_maps_for(op, src);
-      if (tm == nullptr || !tma_aligned(dst, epi.v0, epi.v1) || tma_laplace_smem(K, (int)sizeof(T)) > (size_t)op->max_smem)
-        return false;
-      int c_first = 0, c_count = 0;
-      if (!tma_chunk_range(first, count, op->n_fast, op->n_fast_boundary, op->tma_lap_n_chunks, op->tma_lap_n_chunks_boundary, c_first, c_count))
-        return false;
-      if (c_count == 0)
-        return true;
-      const int     grid = std::min(c_count, std::max(1, op->n_sm - reserve_sms));
-      const TmaList list = {op->d_tma_lap, op->d_tma_foreign, op->d_tma_lap_chunks + c_first, c_count, op->tma_any_mode1};
-      const TmaMaps *o0 = epi.v0 ? tma_maps_for(op, epi.v0) : tm;
-      if (o0 == nullptr)
-        return false;
-      launch_laplace_tma<T>(K, op->ctx->stream, grid, src, dst, (T *)op->d_acc, epi, op->lap_P, op->lap_Q, *tm, o0->main, shared_mode, ni, list,
-                            fast_dbg());
-      op->ctx->launches++;
-      return true;
-    }
-  FastLaplaceMats<T, K + 1> mats;
-  eo_fill(mats.M, op->lap_P[0], op->lap_Q[0]);
-  eo_fill(mats.K0, op->lap_P[1], op->lap_Q[1]);
-  eo_fill(mats.K1, op->lap_P[2], op->lap_Q[2]);
-  eo_fill(mats.K2, op->lap_P[3], op->lap_Q[3]);
-  const int grid = std::min(count, std::max(1, op->n_sm - reserve_sms));
-  FastMaps  fm   = {op->d_fast_ltab, op->d_fast_ftab, op->maps.foreign_gidx, op->d_fast_ids + first, count, fast_prof_buffer(grid), fast_dbg()};
-  auto      kern = laplace_fast_kernel<K, T>;
-  CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<grid, G::NT, smem, op->ctx->stream>>>(src, dst, (T *)op->d_acc, epi, op->d_bricks, mats, shared_mode, ni, fm);
-  fast_prof_report("laplace", fm.prof, grid, op->ctx->stream);
+  const TmaMaps *tm = tma_maps_for(op, src);
+  if (tm == nullptr || !tma_aligned(dst, epi.v0, epi.v1) || tma_laplace_smem(K, (int)sizeof(T)) > (size_t)op->max_smem)
+    return false;
+  int c_first = 0, c_count = 0;
+  if (!tma_chunk_range(first, count, op->n_fast, op->n_fast_boundary, op->tma_lap_n_chunks, op->tma_lap_n_chunks_boundary, c_first, c_count))
+    return false;
+  if (c_count == 0)
+    return true;
+  const int      grid = std::min(c_count, std::max(1, op->n_sm - reserve_sms));
+  const TmaList  list = {op->d_tma_lap, op->d_tma_foreign, op->d_tma_lap_chunks + c_first, c_count, op->tma_any_mode1};
+  const TmaMaps *o0   = epi.v0 ? tma_maps_for(op, epi.v0) : tm;
+  if (o0 == nullptr)
+    return false;
+  launch_laplace_tma<T>(K, op->ctx->stream, grid, src, dst, (T *)op->d_acc, epi, op->lap_P, op->lap_Q, *tm, o0->main, shared_mode, ni, list,
+                        fast_dbg());
   op->ctx->launches++;
   return true;
 }
@@ -981,7 +888,7 @@ launch_laplace_brick(dasm_op *op, T *dst, const T *src, const Epilogue<T> &epi, 
   const size_t smem  = BrickGeom<K, BZ>::template smem_bytes<T>(n_ops, BZ == 4);
   if constexpr (BZ == 4 && K >= 2 && K <= 4)
     {
-      if (op->geom_mode == 0 && op->fast_ok && n_ops <= 1 && FastGeom<K, T>::smem_bytes(1, 2, 1) <= (size_t)op->max_smem &&
+      if (op->geom_mode == 0 && op->fast_ok && n_ops <= 1 && tma_laplace_smem(K, (int)sizeof(T)) <= (size_t)op->max_smem &&
           overlap_enabled(op, shared_mode, op->n_fast_boundary, op->n_fast))
         {
           // halo exchange overlapped with the interior bricks (see overlap_pre)
@@ -1173,57 +1080,43 @@ launch_fdm(dasm_fdm *f, T *dst, const T *src)
   DISPATCH_PATCH(f->m, launch_fdm_m<M, T>(f, dst, src));
 }
 
+// The reference skips compress(add) for RAS only after it has verified that the patch that keeps a DoF (weight 1) is a locally
+// owned cell for EVERY owned DoF, and throws otherwise (matrix_free.h:654-668).  Here the winner of an entity is the touching
+// cell with the smallest global id, i.e. on a partition interface a cell of the LOWER rank, while the DoF is owned by the upper
+// one: the result sits in a ghost slot and must be sent.  Several ranks therefore keep the compression.
+static bool
+fdm_needs_compression(const dasm_fdm *f)
+{
+  return f->weight_type != DASM_WEIGHT_RAS || f->op->mesh->mesh->n_ranks() > 1;
+}
+
 template <int K, typename T>
 static bool
 launch_fdm_fast(dasm_fdm *f, T *dst, const T *src, const Epilogue<T> &epi, const int shared_mode, const NextInit<T> &ni, const int first = 0,
                 int count = -1, const int reserve_sms = 0)
 {
+  dasm_op *op = f->op;
   if (count < 0)
     count = f->n_fast - first;
   if (count == 0)
     return true;
-  using G               = FastGeom<K, T>;
-  dasm_op *        op   = f->op;
-  constexpr size_t smem = G::smem_bytes(2, 1, 2);
-  if (smem > (size_t)op->max_smem)
+  if (!op->tma_ok || f->d_tma_list == nullptr)
     return false;
-  if (op->tma_ok)
-    {
-      const TmaMaps *tm = tma_maps_for(op, src);
-      if (tm == nullptr || f->d_tma_list == nullptr || !tma_aligned(dst, epi.v0, epi.v1) ||
-          tma_fdm_smem(K, (int)sizeof(T)) > (size_t)op->max_smem)
-        return false;
-      int c_first = 0, c_count = 0;
-      if (!tma_chunk_range(first, count, f->n_fast, f->n_fast_boundary, f->tma_n_chunks, f->tma_n_chunks_boundary, c_first, c_count))
-        return false;
-      if (c_count == 0)
-        return true;
-      const int     grid = std::min(c_count, std::max(1, op->n_sm - reserve_sms));
-      const TmaList list = {f->d_tma_list, op->d_tma_foreign, f->d_tma_chunks + c_first, c_count, f->tma_any_mode1};
-      const TmaMaps *o0 = epi.v0 ? tma_maps_for(op, epi.v0) : tm, *o1 = epi.v1 ? tma_maps_for(op, epi.v1) : tm;
-      if (o0 == nullptr || o1 == nullptr)
-        return false;
-      launch_fdm_tma<T>(K, op->ctx->stream, grid, src, dst, (T *)op->d_acc, epi, f->fast_P, f->fast_Q, f->fast_inv, *tm, o0->main, o1->main,
-                        shared_mode, ni, list, fast_dbg());
-      op->ctx->launches++;
-      return true;
-    }
-  constexpr int         n = K + 1;
-  FastFdmMats<T, K + 1> mats;
-  eo_fill(mats.Ax, f->fast_P[0], f->fast_Q[0]);
-  eo_fill(mats.Ay, f->fast_P[1], f->fast_Q[1]);
-  eo_fill(mats.Az, f->fast_P[2], f->fast_Q[2]);
-  eo_fill(mats.Bx, f->fast_P[3], f->fast_Q[3]);
-  eo_fill(mats.By, f->fast_P[4], f->fast_Q[4]);
-  eo_fill(mats.Bz, f->fast_P[5], f->fast_Q[5]);
-  for (int i = 0; i < n * n * n; ++i)
-    mats.inv[i] = (T)f->fast_inv[i];
-  const int grid = std::min(count, std::max(1, op->n_sm - reserve_sms));
-  FastMaps  fm   = {op->d_fast_ltab, op->d_fast_ftab, op->maps.foreign_gidx, f->d_fast_ids + first, count, fast_prof_buffer(grid), fast_dbg()};
-  auto      kern = fdm_fast_kernel<K, T>;
-  CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<grid, G::NT, smem, op->ctx->stream>>>(src, dst, (T *)op->d_acc, epi, op->d_bricks, mats, shared_mode, ni, fm);
-  fast_prof_report("fdm", fm.prof, grid, op->ctx->stream);
+  const TmaMaps *tm = tma_maps_for(op, src);
+  if (tm == nullptr || !tma_aligned(dst, epi.v0, epi.v1) || tma_fdm_smem(K, (int)sizeof(T)) > (size_t)op->max_smem)
+    return false;
+  int c_first = 0, c_count = 0;
+  if (!tma_chunk_range(first, count, f->n_fast, f->n_fast_boundary, f->tma_n_chunks, f->tma_n_chunks_boundary, c_first, c_count))
+    return false;
+  if (c_count == 0)
+    return true;
+  const int      grid = std::min(c_count, std::max(1, op->n_sm - reserve_sms));
+  const TmaList  list = {f->d_tma_list, op->d_tma_foreign, f->d_tma_chunks + c_first, c_count, f->tma_any_mode1};
+  const TmaMaps *o0 = epi.v0 ? tma_maps_for(op, epi.v0) : tm, *o1 = epi.v1 ? tma_maps_for(op, epi.v1) : tm;
+  if (o0 == nullptr || o1 == nullptr)
+    return false;
+  launch_fdm_tma<T>(K, op->ctx->stream, grid, src, dst, (T *)op->d_acc, epi, f->fast_P, f->fast_Q, f->fast_inv, *tm, o0->main, o1->main,
+                    shared_mode, ni, list, fast_dbg());
   op->ctx->launches++;
   return true;
 }
@@ -1242,7 +1135,7 @@ launch_fdm_brick(dasm_fdm *f, T *dst, const T *src, const Epilogue<T> &epi, cons
     wt.v[i] = (T)f->wtab[i];
   if constexpr (BZ == 4 && K >= 2 && K <= 4)
     {
-      if (f->fast_ok && FastGeom<K, T>::smem_bytes(2, 1, 2) <= (size_t)op->max_smem &&
+      if (f->fast_ok && tma_fdm_smem(K, (int)sizeof(T)) <= (size_t)op->max_smem &&
           overlap_enabled(op, shared_mode, f->n_fast_boundary, f->n_fast))
         {
           // halo exchange overlapped with the interior bricks (see overlap_pre)
@@ -1259,7 +1152,7 @@ launch_fdm_brick(dasm_fdm *f, T *dst, const T *src, const Epilogue<T> &epi, cons
                                                                          (int)f->w_pre, (int)f->w_post, n_ops, shared_mode, ni, op->maps, dbg, f->d_slow_ids);
                 ctx->launches++;
               }
-            overlap_mid<T>(op, dst, f->weight_type != DASM_WEIGHT_RAS);
+            overlap_mid<T>(op, dst, fdm_needs_compression(f));
             launch_fdm_fast<K, T>(f, dst, src, epi, shared_mode, ni, f->n_fast_boundary, f->n_fast - f->n_fast_boundary, overlap_reserved_sms());
           }
           overlap_post(op);
@@ -1293,7 +1186,7 @@ launch_fdm_brick(dasm_fdm *f, T *dst, const T *src, const Epilogue<T> &epi, cons
       }
   }
   CUDA_CHECK(cudaGetLastError());
-  brick_post_exchange<T>(op, dst, shared_mode, f->weight_type != DASM_WEIGHT_RAS);
+  brick_post_exchange<T>(op, dst, shared_mode, fdm_needs_compression(f));
   brick_finish<K, BZ, T>(op, dst, (const T *)nullptr, epi, shared_mode);
   CUDA_CHECK(cudaGetLastError());
 }
@@ -1344,7 +1237,7 @@ fdm_vmult(dasm_fdm *f, T *dst, const T *src, const dasm_hook *pre, const dasm_ho
   CUDA_CHECK(cudaMemsetAsync(dst, 0, (size_t)op->n_vec * sizeof(T), ctx->stream));
   op->exchange.run<T>(const_cast<T *>(src), false);
   launch_fdm<T>(f, dst, src);
-  if (f->weight_type != DASM_WEIGHT_RAS) // RAS needs no compression (matrix_free.h:654-668)
+  if (fdm_needs_compression(f))
     op->exchange.run<T>(dst, true);
   // post hook without the constrained-DoF copy: the preconditioner leaves constrained DoFs at zero
   if (post != nullptr && post->kind != DASM_HOOK_NONE)
@@ -2155,59 +2048,6 @@ dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping
                 const char *nofast = getenv("DASM_NO_FAST");
                 if (degree >= 2 && degree <= 4 && !(nofast && nofast[0] == '1'))
                   {
-                    const uint32_t reg_sig = 4u | (4u << 4) | (4u << 8) | (0x3Fu << 12);
-                    const auto     itv     = variant_of.find(reg_sig);
-                    int            skew = 0, padz = 0;
-                    fast_tile_params(k, (int)op->esize(), skew, padz);
-                    const int  SZ    = TX * TX + 4 * skew + padz;
-                    const int  NOWN  = 64 * k * k * k, NPRIV = (4 * k - 1) * (4 * k - 1) * (4 * k - 1);
-                    auto       faddr = [&](uint32_t plin) {
-                      const int px = plin % TX, py = (plin / TX) % TY, pz = plin / (TX * TY);
-                      return (uint16_t)(pz * SZ + py * TX + skew * (py / k) + px);
-                    };
-                    bool regular = itv != variant_of.end() && variants[itv->second].flags == 0 &&
-                                   (int)variants[itv->second].store.size() == NOWN && (int)variants[itv->second].ftab.size() == NPTS - NOWN;
-                    if (regular)
-                      {
-                        const Variant &       var = variants[itv->second];
-                        std::vector<uint16_t> lt((NOWN + 7) / 8 * 8, 0), ft(NFP, 0);
-                        for (int i = 0; i < NOWN && regular; ++i)
-                          {
-                            if (var.load[i] == 0xFFFFu)
-                              regular = false;
-                            else
-                              lt[i] = faddr(var.load[i]);
-                          }
-                        for (size_t j = 0; j < var.ftab.size(); ++j)
-                          ft[j] = faddr(var.ftab[j] & 0x1FFFu);
-                        std::vector<uint32_t> fast_ids, slow_ids;
-                        for (size_t b = 0; b < bricks.size(); ++b)
-                          {
-                            const BrickDesc &bd = bricks[b];
-                            // (the operands on the private range are fetched by 16-byte aligned bulk copies)
-                            bool             r  = regular && bd.variant == itv->second && bd.npriv == NPRIV && bd.sh_count == (uint32_t)(NOWN - NPRIV) &&
-                                     bd.sh_base == bd.base + NPRIV && ((size_t)bd.base * op->esize()) % 16 == 0;
-                            for (int j = 0; r && j < NPTS - NOWN; ++j)
-                              if (foreign_gidx[b * NFP + j] == INVALID_INDEX)
-                                r = false;
-                            (r ? fast_ids : slow_ids).push_back((uint32_t)b);
-                          }
-                        if (regular && !fast_ids.empty())
-                          {
-                            std::stable_partition(fast_ids.begin(), fast_ids.end(), [&](uint32_t b) { return op->h_brick_boundary[b] != 0; });
-                            op->n_fast_boundary = 0;
-                            for (const uint32_t b : fast_ids)
-                              op->n_fast_boundary += op->h_brick_boundary[b] ? 1 : 0;
-                            op->fast_ok     = true;
-                            op->d_fast_ltab = dev_upload(lt, ctx->stream);
-                            op->d_fast_ftab = dev_upload(ft, ctx->stream);
-                            op->d_fast_ids  = dev_upload(fast_ids, ctx->stream);
-                            op->d_slow_ids  = dev_upload(slow_ids, ctx->stream);
-                            op->n_fast      = (int)fast_ids.size();
-                            op->n_slow      = (int)slow_ids.size();
-                            op->h_fast_ids  = fast_ids;
-                          }
-                      }
                     // ---- TMA-fed kernels (kernels_tma.cuh): every lex brick with its 7 upper neighbours
                     if (op->nb.n_lex > 0)
                       {
@@ -2351,8 +2191,6 @@ dasm_op_destroy(dasm_op *op)
   cudaFree(op->d_bricks);
   cudaFree(op->d_acc);
   cudaFree(op->d_shared_list);
-  cudaFree(op->d_fast_ltab);
-  cudaFree(op->d_fast_ftab);
   cudaFree(op->d_fast_ids);
   cudaFree(op->d_slow_ids);
   cudaFree(op->d_tma_lap);
@@ -2370,6 +2208,7 @@ dasm_op_destroy(dasm_op *op)
 extern "C" long long dasm_op_n_dofs(const dasm_op *op) { return op->n_owned; }
 extern "C" long long dasm_op_n_fast_bricks(const dasm_op *op) { return (op->fast_ok && op->geom_mode == 0) ? op->n_fast : 0; }
 extern "C" long long dasm_op_n_ghost(const dasm_op *op) { return op->n_ghost; }
+extern "C" long long dasm_op_n_import(const dasm_op *op) { return (long long)op->exchange.n_send; }
 extern "C" long long dasm_op_vec_size(const dasm_op *op) { return op->n_vec; }
 extern "C" long long dasm_op_n_global_dofs(const dasm_op *op) { return op->n_global_dofs; }
 extern "C" int dasm_op_degree(const dasm_op *op) { return op->k; }
@@ -3584,7 +3423,7 @@ dasm_cheb_destroy(dasm_cheb *c)
   if (!c)
     return 0;
   cudaStreamSynchronize(c->op->ctx->stream);
-  for (void *p : {c->t1, c->t1b, c->t2, c->xold, c->xin, c->bin, c->d_inv_diag})
+  for (void *p : {c->t1, c->t1b, c->t2, c->xold, c->xin, c->bin, c->d_inv_diag, c->d_stage})
     cudaFree(p);
   delete c;
   DASM_API_END
@@ -3748,30 +3587,36 @@ cheb_host(dasm_cheb *c, double *dst, const double *src, bool step)
   dasm_op *       op = c->op;
   cudaStream_t    s  = op->ctx->stream;
   const long long n  = op->n_owned;
-  // host vectors are double (the reference's outer vectors); converted on the device
-  static thread_local double *d_stage = nullptr;
-  static thread_local size_t  stage_n = 0;
-  if (stage_n < (size_t)n)
-    {
-      if (d_stage)
-        cudaFree(d_stage);
-      CUDA_CHECK(cudaMalloc(&d_stage, (size_t)n * sizeof(double)));
-      stage_n = n;
-    }
+  // host vectors are double (the reference's outer vectors): copied straight into the device vectors in double precision,
+  // through a staging buffer owned by the smoother (allocated on its device) and a conversion kernel in single precision
   T *x = (T *)c->xin, *b = (T *)c->bin;
-  CUDA_CHECK(cudaMemcpyAsync(d_stage, src, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s));
-  vec_convert_kernel<T, double><<<nblocks(n), 256, 0, s>>>(b, d_stage, n);
-  op->ctx->launches++;
-  if (step)
+  if (sizeof(T) == sizeof(double))
     {
-      CUDA_CHECK(cudaMemcpyAsync(d_stage, dst, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s));
-      vec_convert_kernel<T, double><<<nblocks(n), 256, 0, s>>>(x, d_stage, n);
-      op->ctx->launches++;
+      CUDA_CHECK(cudaMemcpyAsync(b, src, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s));
+      if (step)
+        CUDA_CHECK(cudaMemcpyAsync(x, dst, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s));
+      cheb_run<T>(c, x, b, step);
+      CUDA_CHECK(cudaMemcpyAsync(dst, x, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
     }
-  cheb_run<T>(c, x, b, step);
-  vec_convert_kernel<double, T><<<nblocks(n), 256, 0, s>>>(d_stage, x, n);
-  op->ctx->launches++;
-  CUDA_CHECK(cudaMemcpyAsync(dst, d_stage, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  else
+    {
+      if (c->d_stage == nullptr)
+        CUDA_CHECK(cudaMalloc(&c->d_stage, (size_t)n * sizeof(double)));
+      double *d_stage = (double *)c->d_stage;
+      CUDA_CHECK(cudaMemcpyAsync(d_stage, src, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s));
+      vec_convert_kernel<T, double><<<nblocks(n), 256, 0, s>>>(b, d_stage, n);
+      op->ctx->launches++;
+      if (step)
+        {
+          CUDA_CHECK(cudaMemcpyAsync(d_stage, dst, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s));
+          vec_convert_kernel<T, double><<<nblocks(n), 256, 0, s>>>(x, d_stage, n);
+          op->ctx->launches++;
+        }
+      cheb_run<T>(c, x, b, step);
+      vec_convert_kernel<double, T><<<nblocks(n), 256, 0, s>>>(d_stage, x, n);
+      op->ctx->launches++;
+      CUDA_CHECK(cudaMemcpyAsync(dst, d_stage, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
   CUDA_CHECK(cudaStreamSynchronize(s));
 }
 

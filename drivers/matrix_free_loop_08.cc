@@ -43,6 +43,10 @@ struct Parameters
     mapping_type         = prm.get<std::string>("mapping type", mapping_type);
     if (number_type != "double" && number_type != "float")
       throw std::runtime_error("number type must be double|float");
+    if (!dof_renumbering)
+      std::cerr << "note: \"dof renumbering\": false has no effect - libdasm always uses its brick-grouped data-locality numbering "
+                   "(the counterpart of DoFRenumbering::matrix_free_data_locality, matrix_free_loop_08.likwid.cc:216-222)"
+                << std::endl;
   }
 };
 
@@ -171,7 +175,7 @@ test(const Parameters &params_in, Context &ctx)
       ctx.sync();
       const double time = std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::system_clock::now() - timer).count() / 1e9;
       std::cout << ">> " << label << " " << op.m() << " " << params_in.n_repetitions * factor << " " << time << " " << sizeof(Number) << " "
-                << params_in.fe_degree << " " << dasm_op_n_ghost(op.handle()) << " " << dasm_op_n_ghost(op.handle()) << std::endl;
+                << params_in.fe_degree << " " << dasm_op_n_ghost(op.handle()) << " " << dasm_op_n_import(op.handle()) << std::endl;
     }
 }
 

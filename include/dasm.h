@@ -143,15 +143,15 @@ extern "C"
   int dasm_test_eo_pack(int n, int kind, const double *A, double *P, double *Q);
 
   /* ---- LaplaceOperatorMatrixFree (include/operator.h:266-1628) ------------------------------- */
-  /* ctor operator.h:466-482 + setup_mapping_and_indices 490-753.  mapping_type in {"", "merged"}
-   * ("linear geometry", "quadratic geometry", "construct q" are not built yet and return an error,
-   * like operator.h:747-752 does for unknown names). */
+  /* ctor operator.h:466-482 + setup_mapping_and_indices 490-753.  mapping_type in {"", "merged", "linear geometry",
+   * "quadratic geometry"}; "construct q" is not built yet and, like unknown names (operator.h:747-752), returns an error. */
   int dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping_type, int compress_indices,
                      dasm_op **out);
   int       dasm_op_destroy(dasm_op *op);
   long long dasm_op_n_fast_bricks(const dasm_op *op); /* diagnostics: bricks processed by the warp-specialised kernel */
   long long dasm_op_n_dofs(const dasm_op *op);        /* locally owned (vector_partitioner->locally_owned_size) */
   long long dasm_op_n_ghost(const dasm_op *op);
+  long long dasm_op_n_import(const dasm_op *op);      /* owned DoFs other ranks ghost (partitioner->n_import_indices()) */
   long long dasm_op_vec_size(const dasm_op *op);      /* owned + ghost */
   long long dasm_op_n_global_dofs(const dasm_op *op); /* m(), operator.h:1451 */
   int       dasm_op_degree(const dasm_op *op);
