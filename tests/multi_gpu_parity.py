@@ -57,8 +57,11 @@ def main():
     part = PART[world]
     ok = True
     # the (24, 8, 8) mesh has interior bricks on every rank of a 2 x 1 x 1 partition: the halo exchange overlaps with them
+    # (16, 16, 16) / (24, 8, 8): lex bricks on every rank, also next to the partition boundary (index-list mode of the TMA-fed
+    # kernels); "ras": the patch that keeps an interface DoF lives on the neighbouring rank (compress must run)
     for k, number, nc, wt in ((4, "double", (8, 8, 8), "symm"), (3, "double", (8, 6, 4), "post"), (2, "double", (8, 8, 8), "none"),
-                              (4, "double", (24, 8, 8), "symm"), (3, "float", (24, 8, 8), "post")):
+                              (4, "double", (24, 8, 8), "symm"), (3, "float", (24, 8, 8), "post"), (4, "double", (16, 16, 16), "symm"),
+                              (3, "double", (16, 16, 16), "ras"), (2, "double", (8, 8, 8), "ras")):
         L = tuple(float(c) / 4 for c in nc)
         vsize = None
         results = {}
