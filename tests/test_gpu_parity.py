@@ -144,7 +144,7 @@ def test_inverse_diagonal(pkg, ctx, name, k):
 
 
 @pytest.mark.parametrize("wt", ["none", "pre", "post", "symm", "ras"])
-@pytest.mark.parametrize("seq", ["compressed", "global", "dg"])
+@pytest.mark.parametrize("seq", ["compressed", "global", "local", "dg"])
 def test_fdm_weightings(pkg, ctx, wt, seq):
     mesh = pkg.Mesh(ctx, **MESHES["mixed_aniso"])
     op = pkg.LaplaceOperatorMatrixFree(mesh, 3, "double")

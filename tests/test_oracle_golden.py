@@ -164,3 +164,40 @@ def test_vertex_patch_fdm_equals_restricted_matrix_inverse():
         assert np.allclose(B, Ainv, rtol=1e-10, atol=1e-12)
     # cells without a complete 2x2x2 neighbourhood have an empty patch
     assert not (P.mask[mesh.C - 1] > 0).any()
+
+
+# ---- Krylov iteration counts of the reference's small/ fixtures (element_centered_preconditioners_01.cc:108-203) -----------------
+def _constant_rhs(mesh, cd, nd, bnd, k):
+    """VectorTools::create_right_hand_side with f = 1 (element_centered_preconditioners_01.cc:65-81, operator.h:298-330):
+    b_i = int phi_i, constrained entries 0."""
+    b1 = o.Basis1D(k)
+    M, _ = b1.reference_mass_stiffness()
+    m = np.asarray(M).sum(axis=1)  # int phi_i on the reference interval
+    h = [mesh.lengths[d] / mesh.n_cells[d] for d in range(2)]
+    loc = np.outer(m * h[1], m * h[0]).reshape(-1)
+    rhs = np.zeros(nd)
+    for c in range(mesh.C):
+        np.add.at(rhs, cd[c].astype(np.int64), loc)
+    rhs[np.asarray(bnd, dtype=bool)] = 0.0
+    return rhs
+
+
+@pytest.mark.parametrize("name,gold_its", [("dummy_identity", 24), ("dummy_diagonal", 23), ("dummy_chebyshev_diagonal", 9)])
+def test_gmres_iteration_counts(name, gold_its):
+    """dummy_identity.output (24), dummy_diagonal.output (23), dummy_chebyshev_diagonal.output (9): 2-D Q3, 64 cells, 625 DoFs,
+    f = 1, GMRES with right preconditioning, ReductionControl(1000, 1e-10, 1e-2)."""
+    mesh, cd, nd, bnd, op = level_problem(3)
+    b = _constant_rhs(mesh, cd, nd, bnd, 3)
+    A = lambda v: op.vmult(v, copy_constrained=True)
+    if name == "dummy_identity":
+        P = lambda v: v.copy()
+    elif name == "dummy_diagonal":
+        jac = o.JacobiPreconditioner(op)
+        P = jac.vmult
+    else:
+        ch = o.Chebyshev(op, o.JacobiPreconditioner(op), degree=3, ev_algorithm="power iteration", eig_cg_n_iterations=20)
+        ch.estimate_eigenvalues()
+        P = ch.vmult
+    x, its = o.solve_gmres(A, P, b)
+    assert its == gold_its
+    assert np.linalg.norm(b - A(x)) <= 1e-2 * np.linalg.norm(b) * (1 + 1e-8)
