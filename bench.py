@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--cheb-degree", type=int, default=3)
     ap.add_argument("--weighting", default="symm")
     ap.add_argument("--cells", default="192,128,64", help="cells per GPU (x,y,z)")
-    ap.add_argument("--cpu-cells", default="32,32,32", help="bounded CPU-baseline sample mesh")
+    ap.add_argument("--cpu-cells", default="", help="mesh of the cpu_baseline leg (default: --cells, the GPU workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--extra", action="store_true", help="also time vmult / FDM alone (printed to stderr)")
@@ -132,62 +132,64 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------------
-# CPU arm: the C restatement of the reference algorithm (oracle/), all host threads, bounded sample
+# CPU arm: the optimised C restatement of the reference algorithm (oracle/cpu_baseline.c: compile-time degree, SIMD across
+# 8 cells, Cartesian Kronecker form, fused pre / post operations, one cell range per thread), all host cores
 # ---------------------------------------------------------------------------------------------------------------
-def cpu_smoother(args):
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_smoother(args, cells):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import dasm_oracle as o
     import oracle_c
-    nc = tuple(int(c) for c in args.cpu_cells.split(","))
-    k = args.degree
-    mesh = o.StructuredMesh(3, nc, (True, True, True), lengths=tuple(c / 64.0 for c in nc))
-    mesh.cell_order = o.brick_major_order(nc)
-    cd, nd, con, comp = o.number_dofs_owner_cell(mesh, k)
-    b = o.Basis1D(k)
-    # Cartesian: identical Jacobian in every cell
-    h = [mesh.lengths[d] / nc[d] for d in range(3)]
-    J = np.broadcast_to(np.diag(h), (mesh.C, (k + 1) ** 3, 3, 3)).copy()
-    G = o.merged_coefficients(J, b, 3)
-    oop = o.LaplaceOperator(3, k, cd, nd, con, G)
-    oP = o.FDMPreconditioner(mesh, k, cd, nd, con, 1, args.weighting)
-    sm = oracle_c.CSmoother(mesh, oop, oP, args.cheb_degree, max_ev=2.4, min_ev=1.0)
-    return sm, nd, oracle_c.max_threads(), nc
+    oracle_c.baseline_set_threads(host_cores())  # (torch.distributed.run exports OMP_NUM_THREADS=1)
+    nc = tuple(int(c) for c in cells.split(","))
+    sm = oracle_c.CartesianBaseline(nc, tuple(c / 64.0 for c in nc), args.degree, args.cheb_degree, args.weighting, max_ev=2.4, min_ev=1.0)
+    return sm, sm.n_dofs, oracle_c.baseline_max_threads(), nc
 
 
-def time_cpu(args, steps, warmup, target_s=None):
-    sm, nd, threads, nc = cpu_smoother(args)
+def time_cpu(args, steps, warmup, cells, target_s=None):
+    sm, nd, threads, nc = cpu_smoother(args, cells)
     rng = np.random.default_rng(0)
     x = rng.uniform(-1, 1, nd)
     b = rng.uniform(-1, 1, nd)
-    for _ in range(warmup):
+    t_one = 1.0
+    for _ in range(max(warmup, 1)):
         t0 = time.perf_counter()
-        x = sm.step(x, b)
+        sm.step(x, b)
         t_one = time.perf_counter() - t0
-    if target_s is not None and warmup > 0:
+    if target_s is not None:
         # bounded sample of about target_s seconds of CPU work
-        steps = int(max(steps, min(400, target_s / max(t_one, 1e-6))))
+        steps = int(max(1, min(400, target_s / max(t_one, 1e-6))))
     t0 = time.perf_counter()
     for _ in range(steps):
-        x = sm.step(x, b)
+        sm.step(x, b)
     dt = time.perf_counter() - t0
     value = nd * args.cheb_degree * steps / dt
-    sample = "Chebyshev(%d)+FDM(symm,n=1) step, degree %d, %dx%dx%d periodic Cartesian cells (%d DoFs), %d steps, %.2f s" % (
-        args.cheb_degree, args.degree, nc[0], nc[1], nc[2], nd, steps, dt)
-    return value, threads, sample, dt / steps * 1e3
+    sample = "Chebyshev(%d)+FDM(%s,n=1) step, degree %d, double, %dx%dx%d periodic Cartesian cells (%d DoFs), %d steps, %.2f s" % (
+        args.cheb_degree, args.weighting, args.degree, nc[0], nc[1], nc[2], nd, steps, dt)
+    return value, threads, sample, dt / steps * 1e3, steps
 
 
 def run_reference(args):
+    """the reference's CPU path (restated) on the host cores, on the GPU arm's workload: the same mesh as
+    one GPU of the GPU arm processes (--cells), every step a full smoother step; rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     steps = max(1, args.steps)
-    value, threads, sample, ms = time_cpu(args, steps, max(1, min(args.warmup, 2)))
+    value, threads, sample, ms, steps = time_cpu(args, steps, max(1, min(args.warmup, 2)), args.cells)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "DoFs/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "cheby-3-2-symm-1-c, FE_Q(%d), periodic Cartesian; CPU restatement of the reference algorithm "
-                               "(oracle/dasm_oracle_c.c; deal.II itself cannot be built here), bounded sample" % args.degree,
+        "config": {"workload": "matrix_free_loop_08 label cheby-%d-2-%s-1-c: FE_Q(%d), periodic Cartesian hyper-rectangle, %s cells "
+                               "(the mesh of ONE GPU of the GPU arm); CPU restatement of the reference algorithm "
+                               "(oracle/cpu_baseline.c; deal.II itself cannot be built here)" % (
+                                   args.cheb_degree, args.weighting, args.degree, args.cells.replace(",", "x")),
                    "sample": sample},
         "cpu_baseline": {"value": value, "unit": "DoFs/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "DoFs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -355,6 +357,8 @@ def run_ours(args):
     else:
         # unfused cell kernels: read src, write dst (2 S) + per-cell metadata (SURVEY.md 8(d) `vmult` / `FDM-ASM vmult` rows)
         per_dof = [2 * S + idx_bytes / d_c, 2 * S + (idx_bytes + 27 * S + 12) / d_c][dom]
+    cd = args.cheb_degree
+    step_bytes_per_term = ((6 + 7 * (cd - 1)) * S + cd * (2 * idx_bytes + 27 * S + 12) / d_c) / cd
     bytes_per_launch = per_dof * n_own
     achieved = bytes_per_launch / (dom_ms / max(dom_n, 1) * 1e-3) / 1e9 if dom_n else None
     traffic = None
@@ -369,14 +373,15 @@ def run_ours(args):
                 "algorithmic_bytes_per_dof": per_dof, "avg_launch_ms": dom_ms / max(dom_n, 1), "launches_timed": dom_n,
                 "share_of_step": dom_ms / ms,
                 "kernel_time_ms": {names[i]: ktimes[i][0] for i in range(4)},
-                # whole Chebyshev term against the 7 S + metadata model of SURVEY.md 8(d)
-                "step_algorithmic_bytes_per_dof_per_term": 7 * S + (2 * idx_bytes + 27 * S + 12) / d_c,
-                "step_frac_of_hbm_roofline": value * (7 * S + (2 * idx_bytes + 27 * S + 12) / d_c) / world / (peak * 1e9)}
+                # whole step against the model of SURVEY.md 8(d): the first term of `step` has no x_old: (6 + 7 (d - 1)) S per DoF,
+                # plus the per-cell metadata of every term
+                "step_algorithmic_bytes_per_dof_per_term": step_bytes_per_term,
+                "step_frac_of_hbm_roofline": value * step_bytes_per_term / world / (peak * 1e9)}
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         try:
-            v, threads, sample, _ = time_cpu(args, 3, 2, target_s=10.0)
+            v, threads, sample, _, _ = time_cpu(args, 3, 1, args.cpu_cells or args.cells, target_s=12.0)
             cpu = {"value": v, "unit": "DoFs/s", "cores": threads, "kind": "port", "sample": sample}
         except Exception as e:  # the baseline must never take the GPU number down
             cpu = {"value": None, "unit": "DoFs/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}

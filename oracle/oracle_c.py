@@ -93,3 +93,89 @@ class CSmoother:
                                    _p(z), _p(new))
             old, cur = cur, new
         return cur
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# optimised CPU baseline (oracle/cpu_baseline.c): periodic Cartesian mesh, lexicographic DoF numbering
+# ---------------------------------------------------------------------------------------------------------------
+_blib = None
+
+
+def baseline_lib():
+    global _blib
+    if _blib is None:
+        _blib = ctypes.CDLL(os.path.join(_HERE, "libcpu_baseline.so"))
+    return _blib
+
+
+def baseline_max_threads():
+    return baseline_lib().cpu_baseline_max_threads()
+
+
+def baseline_set_threads(n):
+    """torch.distributed.run exports OMP_NUM_THREADS=1; the CPU baseline is given all host cores explicitly"""
+    baseline_lib().cpu_baseline_set_threads(int(n))
+
+
+def lexicographic_cell_dofs(nc, k):
+    """[C, n^3] DoF indices of the periodic (k nx) x (k ny) x (k nz) lattice, x fastest; cells lexicographic."""
+    n = k + 1
+    nd = [k * c for c in nc]
+    cz, cy, cx = np.meshgrid(np.arange(nc[2]), np.arange(nc[1]), np.arange(nc[0]), indexing="ij")
+    l, j, i = np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij")
+    X = (k * cx.reshape(-1, 1) + i.reshape(1, -1)) % nd[0]
+    Y = (k * cy.reshape(-1, 1) + j.reshape(1, -1)) % nd[1]
+    Z = (k * cz.reshape(-1, 1) + l.reshape(1, -1)) % nd[2]
+    return ((Z * nd[1] + Y) * nd[0] + X).astype(np.uint32), int(np.prod(nd))
+
+
+class CartesianBaseline:
+    """Chebyshev(degree) + FDM-ASM (n_overlap = 1) smoother step of oracle/cpu_baseline.c on a periodic Cartesian mesh."""
+
+    def __init__(self, nc, lengths, k, degree, weight_type="symm", max_ev=2.4, min_ev=1.0, polynomial_type="1st kind"):
+        self.nc = tuple(int(c) for c in nc)
+        self.k = k
+        n = k + 1
+        self.h = np.array([lengths[d] / nc[d] for d in range(3)], dtype=np.float64)
+        b = o.Basis1D(k)
+        M, K = b.reference_mass_stiffness()
+        self.M = np.ascontiguousarray(M, dtype=np.float64)
+        self.K = np.ascontiguousarray(K, dtype=np.float64)
+        S, lam = [], []
+        for d in range(3):
+            ext = (self.h[d], self.h[d], self.h[d])
+            Md, Kd = o.laplace_tensor_product_matrix_1d(M, K, ext, (o.INTERNAL, o.INTERNAL), 1)
+            s, l = o.generalized_eig(Md, Kd)
+            S.append(s)
+            lam.append(l)
+        self.S = np.ascontiguousarray(np.stack(S), dtype=np.float64)
+        self.lam = np.ascontiguousarray(np.stack(lam), dtype=np.float64)
+        # weights of the gathered cell vector: valence = 2^(number of coordinates on the cell boundary)
+        self.w = None
+        self.w_pre = int(weight_type in ("pre", "symm"))
+        self.w_post = int(weight_type in ("post", "symm"))
+        if weight_type != "none":
+            e = np.array([1 if (i == 0 or i == k) else 0 for i in range(n)])
+            val = 2.0 ** (e[:, None, None] + e[None, :, None] + e[None, None, :])
+            self.w = np.ascontiguousarray((1.0 / (np.sqrt(val) if weight_type == "symm" else val)).reshape(-1), dtype=np.float64)
+
+        # coefficient recurrences of the oracle's Chebyshev (deal.II PreconditionChebyshev)
+        helper = o.Chebyshev.__new__(o.Chebyshev)
+        helper.degree, helper.poly, helper.smoothing_range = degree, polynomial_type, 20.0
+        helper.set_eigenvalues(max_ev, min_ev)
+        co = helper.coefficients()
+        self.f1 = np.ascontiguousarray([c[0] for c in co], dtype=np.float64)
+        self.f2 = np.ascontiguousarray([c[1] for c in co], dtype=np.float64)
+        self.degree = degree
+        self.n_dofs = int(np.prod([k * c for c in self.nc]))
+        self.work = np.empty(4 * self.n_dofs)
+
+    def step(self, x, b):
+        """in place on x (float64, lexicographic numbering)"""
+        nc = (ctypes.c_int * 3)(*self.nc)
+        rc = baseline_lib().cpu_baseline_cheb_step(self.k, nc, _p(self.h), _p(self.M), _p(self.K), _p(self.S), _p(self.lam), _p(self.w),
+                                                   self.w_pre, self.w_post, len(self.f1), _p(self.f1), _p(self.f2), _p(x), _p(b),
+                                                   _p(self.work))
+        if rc != 0:
+            raise RuntimeError("cpu_baseline_cheb_step: unsupported size")
+        return x
