@@ -161,6 +161,9 @@ dev_upload(const std::vector<T> &v, cudaStream_t)
 }
 
 // ghost exchange (replaces VectorDataExchange, matrix_free_internal.h:3-109)
+//   default: device-initiated transfers over NVLink: the receive buffers are mapped into the peers with CUDA IPC, the pack kernel
+//            writes into the peer's buffer and publishes a sequence number, the unpack kernel waits for it (kernels.cuh p2p_*);
+//   DASM_P2P=0 or when the mapping fails: pack kernel -> grouped ncclSend / ncclRecv -> unpack kernel.
 struct Exchange
 {
   dasm_ctx *            ctx = nullptr;
@@ -170,6 +173,23 @@ struct Exchange
   void *                d_send_buf = nullptr, *d_recv_buf = nullptr;
   size_t                n_send = 0, n_recv = 0;
   size_t                elem_size = 8;
+  // peer-to-peer state
+  int                   p2p_state = 0; // 0 not tried, 1 ready, -1 unavailable (NCCL path)
+  char *                d_ipc     = nullptr; // [2 halves of cap elements | flags[n_ranks] | acks[n_ranks]]
+  size_t                cap       = 0;
+  unsigned long long    seq       = 0;
+  unsigned int *        d_counters = nullptr;
+  std::vector<char *>   peer_base;               // per peer: mapped IPC block
+  std::vector<size_t>   peer_cap;                // per peer: elements per half
+  std::vector<long long> peer_off_update, peer_off_compress; // per peer: offset of this rank's segment in the peer's buffer
+
+  struct Info
+  {
+    cudaIpcMemHandle_t handle;
+    long long          cap;
+    long long          off_update[64];   // by world rank: offset of the segment received from that rank in a ghost update (-1: none)
+    long long          off_compress[64]; // ... in a compress
+  };
 
   void
   init(dasm_ctx *c, const std::vector<ExchangeList> &lists, size_t esize)
@@ -205,6 +225,116 @@ struct Exchange
     return !peers.empty();
   }
 
+  // collective over all ranks of the communicator: map the receive buffers of the peers
+  void
+  p2p_setup(cudaStream_t s)
+  {
+    p2p_state = -1;
+    if (const char *e = getenv("DASM_P2P"))
+      if (e[0] == '0')
+        return;
+    const int R = ctx->n_ranks;
+    if (R > 64 || (int)peers.size() > P2P_MAX_PEERS)
+      return;
+    cap                    = std::max<size_t>(std::max(n_send, n_recv), 1);
+    const size_t data_bytes = (2 * cap * elem_size + 255) / 256 * 256;
+    if (cudaMalloc(&d_ipc, data_bytes + 2 * 64 * sizeof(unsigned long long)) != cudaSuccess)
+      {
+        cudaGetLastError();
+        return;
+      }
+    CUDA_CHECK(cudaMemsetAsync(d_ipc, 0, data_bytes + 2 * 64 * sizeof(unsigned long long), s));
+    CUDA_CHECK(cudaMalloc(&d_counters, 2 * sizeof(unsigned int)));
+    CUDA_CHECK(cudaMemsetAsync(d_counters, 0, 2 * sizeof(unsigned int), s));
+    Info mine;
+    memset(&mine, 0, sizeof(mine));
+    bool ok  = cudaIpcGetMemHandle(&mine.handle, d_ipc) == cudaSuccess;
+    mine.cap = ok ? (long long)cap : -1;
+    for (int r = 0; r < 64; ++r)
+      mine.off_update[r] = mine.off_compress[r] = -1;
+    for (size_t q = 0; q < peers.size(); ++q)
+      {
+        mine.off_update[peers[q]]   = (long long)recv_off[q];
+        mine.off_compress[peers[q]] = (long long)send_off[q];
+      }
+    // all-gather of the descriptors through NCCL (device staging)
+    Info *d_all = nullptr;
+    CUDA_CHECK(cudaMalloc(&d_all, sizeof(Info) * (size_t)R));
+    CUDA_CHECK(cudaMemcpyAsync(d_all + ctx->rank, &mine, sizeof(Info), cudaMemcpyHostToDevice, s));
+    NCCL_CHECK(ncclAllGather(d_all + ctx->rank, d_all, sizeof(Info), ncclChar, ctx->comm, s));
+    std::vector<Info> all(R);
+    CUDA_CHECK(cudaMemcpyAsync(all.data(), d_all, sizeof(Info) * (size_t)R, cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    cudaFree(d_all);
+    for (int r = 0; r < R; ++r)
+      if (all[r].cap < 0)
+        ok = false; // some rank could not export its buffer: everybody uses NCCL
+    if (ok)
+      for (size_t q = 0; q < peers.size() && ok; ++q)
+        {
+          void *ptr = nullptr;
+          if (cudaIpcOpenMemHandle(&ptr, all[peers[q]].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess)
+            {
+              cudaGetLastError();
+              ok = false;
+              break;
+            }
+          peer_base.push_back((char *)ptr);
+          peer_cap.push_back((size_t)all[peers[q]].cap);
+          peer_off_update.push_back(all[peers[q]].off_update[ctx->rank]);
+          peer_off_compress.push_back(all[peers[q]].off_compress[ctx->rank]);
+        }
+    // agree on the outcome (a rank that failed to map a peer makes everybody fall back)
+    int *d_ok = nullptr, h_ok = ok ? 1 : 0;
+    CUDA_CHECK(cudaMalloc(&d_ok, sizeof(int)));
+    CUDA_CHECK(cudaMemcpyAsync(d_ok, &h_ok, sizeof(int), cudaMemcpyHostToDevice, s));
+    NCCL_CHECK(ncclAllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, ctx->comm, s));
+    CUDA_CHECK(cudaMemcpyAsync(&h_ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    cudaFree(d_ok);
+    if (h_ok)
+      p2p_state = 1;
+    else if (getenv("DASM_VERBOSE"))
+      fprintf(stderr, "[dasm] rank %d: peer-to-peer halo exchange unavailable, using NCCL send/recv\n", ctx->rank);
+  }
+
+  template <typename T>
+  void
+  run_p2p(T *vec, bool compress, cudaStream_t s)
+  {
+    ++seq;
+    const size_t    par   = (size_t)(seq & 1ull);
+    const size_t    n_out = compress ? n_recv : n_send;
+    const size_t    n_in  = compress ? n_send : n_recv;
+    const uint32_t *omap  = compress ? d_recv_map : d_send_map;
+    const uint32_t *imap  = compress ? d_send_map : d_recv_map;
+    const auto &    ooff  = compress ? recv_off : send_off;
+    const size_t    data_bytes = (2 * cap * elem_size + 255) / 256 * 256;
+    P2PPeers        P;
+    P.n = (int)peers.size();
+    for (int q = 0; q < P.n; ++q)
+      {
+        const size_t pdata = (2 * peer_cap[q] * elem_size + 255) / 256 * 256;
+        P.buf[q]           = peer_base[q] + par * peer_cap[q] * elem_size;
+        P.flag[q]          = reinterpret_cast<unsigned long long *>(peer_base[q] + pdata) + ctx->rank;
+        P.ack[q]           = reinterpret_cast<unsigned long long *>(peer_base[q] + pdata) + 64 + ctx->rank;
+        P.dst_off[q]       = compress ? peer_off_compress[q] : peer_off_update[q];
+        P.seg_begin[q]     = (long long)ooff[q];
+        P.my_flag[q]       = reinterpret_cast<unsigned long long *>(d_ipc + data_bytes) + peers[q];
+        P.my_ack[q]        = reinterpret_cast<unsigned long long *>(d_ipc + data_bytes) + 64 + peers[q];
+      }
+    P.seg_begin[P.n] = (long long)ooff[P.n];
+    const unsigned g_out = (unsigned)std::min<size_t>(1184, std::max<size_t>(1, (n_out + 255) / 256));
+    p2p_push_kernel<T><<<g_out, 256, 0, s>>>(vec, omap, P, seq, d_counters);
+    const unsigned g_in = (unsigned)std::min<size_t>(1184, std::max<size_t>(1, (n_in + 255) / 256));
+    const T *      buf  = reinterpret_cast<const T *>(d_ipc + par * cap * elem_size);
+    if (compress)
+      p2p_pull_kernel<T, true><<<g_in, 256, 0, s>>>(vec, buf, imap, (long long)n_in, P, seq, d_counters + 1);
+    else
+      p2p_pull_kernel<T, false><<<g_in, 256, 0, s>>>(vec, buf, imap, (long long)n_in, P, seq, d_counters + 1);
+    ctx->launches += 2;
+  }
+
   // owner -> ghost (update_ghost_values) or ghost -> owner with add (compress)
   template <typename T>
   void
@@ -214,6 +344,13 @@ struct Exchange
       return;
     DASM_REQUIRE(ctx->comm != nullptr, "multi-rank mesh needs dasm_ctx_comm_init before any operator application");
     cudaStream_t    s     = on_stream ? on_stream : ctx->stream;
+    if (p2p_state == 0)
+      p2p_setup(s);
+    if (p2p_state == 1)
+      {
+        run_p2p<T>(vec, compress, s);
+        return;
+      }
     const size_t    n_out = compress ? n_recv : n_send;
     const size_t    n_in  = compress ? n_send : n_recv;
     const uint32_t *omap  = compress ? d_recv_map : d_send_map;
@@ -253,6 +390,10 @@ struct Exchange
     cudaFree(d_recv_map);
     cudaFree(d_send_buf);
     cudaFree(d_recv_buf);
+    for (char *pb : peer_base)
+      cudaIpcCloseMemHandle(pb);
+    cudaFree(d_ipc);
+    cudaFree(d_counters);
   }
 };
 

@@ -645,4 +645,101 @@ namespace dasm
           vec[map[i]] = buf[i];
       }
   }
+
+  // ---- device-initiated halo exchange over NVLink (peer memory mapped with CUDA IPC) -----------------------------------------
+  // push:  every rank writes the values of its send list straight into the receive buffer of the peer (remote stores) and,
+  //        when all blocks are done, publishes the sequence number of the message in the peer's flag word;
+  // pull:  the receiver waits for the flag words of its peers and unpacks its own receive buffer (copy for a ghost update,
+  //        red.add for a compress), then acknowledges.  Receive buffers are double buffered by the parity of the sequence number.
+  constexpr int P2P_MAX_PEERS = 32;
+  struct P2PPeers
+  {
+    int                 n;
+    void *              buf[P2P_MAX_PEERS];      // peer's receive buffer of the current parity (mapped)
+    unsigned long long *flag[P2P_MAX_PEERS];     // peer's flag word for messages from this rank (mapped)
+    unsigned long long *ack[P2P_MAX_PEERS];      // peer's acknowledge word for this rank's reads of ITS messages (mapped)
+    long long           dst_off[P2P_MAX_PEERS];  // element offset of this rank's segment in the peer's receive buffer
+    long long           seg_begin[P2P_MAX_PEERS + 1]; // segments of the local send list per peer
+    unsigned long long *my_flag[P2P_MAX_PEERS];  // local flag words written by the peers
+    unsigned long long *my_ack[P2P_MAX_PEERS];   // local acknowledge words written by the peers
+  };
+
+  __device__ __forceinline__ unsigned long long
+  ld_sys(const unsigned long long *p)
+  {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+  }
+  __device__ __forceinline__ void
+  st_sys(unsigned long long *p, const unsigned long long v)
+  {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+  }
+
+  template <typename T>
+  __global__ void
+  p2p_push_kernel(const T *__restrict__ vec, const uint32_t *__restrict__ map, const P2PPeers peers, const unsigned long long seq,
+                  unsigned int *done_counter)
+  {
+    // the peers must have consumed the message that used this half of their receive buffer (sequence number seq - 2)
+    if (threadIdx.x == 0 && seq > 2)
+      for (int q = 0; q < peers.n; ++q)
+        while (ld_sys(peers.my_ack[q]) + 2 < seq)
+          ;
+    __syncthreads();
+    const long long n = peers.seg_begin[peers.n];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+      {
+        int q = 0;
+        while (i >= peers.seg_begin[q + 1])
+          ++q;
+        reinterpret_cast<T *>(peers.buf[q])[peers.dst_off[q] + (i - peers.seg_begin[q])] = vec[map[i]];
+      }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0)
+      {
+        const unsigned int prev = atomicAdd(done_counter, 1u);
+        if (prev == gridDim.x - 1)
+          {
+            *done_counter = 0;
+            __threadfence_system();
+            for (int q = 0; q < peers.n; ++q)
+              st_sys(peers.flag[q], seq);
+          }
+      }
+  }
+
+  template <typename T, bool ADD>
+  __global__ void
+  p2p_pull_kernel(T *__restrict__ vec, const T *__restrict__ buf, const uint32_t *__restrict__ map, const long long n, const P2PPeers peers,
+                  const unsigned long long seq, unsigned int *done_counter)
+  {
+    if (threadIdx.x == 0)
+      for (int q = 0; q < peers.n; ++q)
+        while (ld_sys(peers.my_flag[q]) < seq)
+          ;
+    __syncthreads();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+      {
+        const T v = __ldcv(buf + i);
+        if (ADD)
+          atomic_add(vec + map[i], v);
+        else
+          vec[map[i]] = v;
+      }
+    __syncthreads();
+    if (threadIdx.x == 0)
+      {
+        const unsigned int prev = atomicAdd(done_counter, 1u);
+        if (prev == gridDim.x - 1)
+          {
+            *done_counter = 0;
+            __threadfence_system();
+            for (int q = 0; q < peers.n; ++q)
+              st_sys(peers.ack[q], seq);
+          }
+      }
+  }
 } // namespace dasm
