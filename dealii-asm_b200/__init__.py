@@ -381,6 +381,33 @@ class PreconditionChebyshev:
             pass
 
 
+def solve(op, x, b, preconditioner=None, params=None):
+    """solve() of element_centered_preconditioners_01.cc:108-203 on the device: `params` is the reference's "solver" JSON block
+    (type CG | GMRES, max iterations 1000, abs tolerance 1e-10, rel tolerance 1e-2, max n tmp vectors 30);
+    preconditioner: None (Identity), "Diagonal", an ASPoissonPreconditioner or a PreconditionChebyshev.  x is overwritten
+    (the reference starts from x = 0).  Returns (n_iterations, last residual norm)."""
+    params = params or {}
+    types = {"CG": 0, "GMRES": 1}
+    t = params.get("type", "")
+    if t not in types:
+        raise DasmError("Solver <" + t + "> is not known!")
+    if preconditioner is None:
+        kind, h = 0, None
+    elif isinstance(preconditioner, str) and preconditioner == "Diagonal":
+        kind, h = 1, None
+    elif isinstance(preconditioner, ASPoissonPreconditioner):
+        kind, h = 2, preconditioner.h
+    elif isinstance(preconditioner, PreconditionChebyshev):
+        kind, h = 3, preconditioner.h
+    else:
+        raise DasmError("Preconditioner <%r> is not known!" % (preconditioner,))
+    n_it, res = ctypes.c_int(), ctypes.c_double()
+    _check(lib().dasm_solve(op.h, types[t], kind, h, _ptr(x), _ptr(b), int(params.get("max iterations", 1000)),
+                            ctypes.c_double(float(params.get("abs tolerance", 1e-10))), ctypes.c_double(float(params.get("rel tolerance", 1e-2))),
+                            int(params.get("max n tmp vectors", 30)), ctypes.byref(n_it), ctypes.byref(res)))
+    return n_it.value, res.value
+
+
 # ---- factories (JSON vocabulary of the reference) -----------------------------------------------
 def get_weighting_type(params):
     """include/precondition.templates.h:10-29."""

@@ -966,6 +966,14 @@ tma_chunk_range(const int first, const int count, const int n_fast, const int n_
   return true;
 }
 
+// thread blocks per SM of the TMA-fed kernels (experiments: DASM_TMA_CTAS)
+static int
+tma_ctas_per_sm()
+{
+  static const int v = getenv("DASM_TMA_CTAS") ? std::max(1, atoi(getenv("DASM_TMA_CTAS"))) : 1;
+  return v;
+}
+
 // tensor maps of a vector for the TMA-fed kernels (cached per pointer); nullptr: not usable (alignment)
 static const TmaMaps *
 tma_maps_for(dasm_op *op, const void *vec)
@@ -1008,7 +1016,7 @@ launch_laplace_fast(dasm_op *op, T *dst, const T *src, const Epilogue<T> &epi, c
     return false;
   if (c_count == 0)
     return true;
-  const int      grid = std::min(c_count, std::max(1, op->n_sm - reserve_sms));
+  const int      grid = std::min(c_count, std::max(1, op->n_sm * tma_ctas_per_sm() - reserve_sms));
   const TmaList  list = {op->d_tma_lap, op->d_tma_foreign, op->d_tma_lap_chunks + c_first, c_count, op->tma_any_mode1};
   const TmaMaps *o0   = epi.v0 ? tma_maps_for(op, epi.v0) : tm;
   if (o0 == nullptr)
@@ -1251,7 +1259,7 @@ launch_fdm_fast(dasm_fdm *f, T *dst, const T *src, const Epilogue<T> &epi, const
     return false;
   if (c_count == 0)
     return true;
-  const int      grid = std::min(c_count, std::max(1, op->n_sm - reserve_sms));
+  const int      grid = std::min(c_count, std::max(1, op->n_sm * tma_ctas_per_sm() - reserve_sms));
   const TmaList  list = {f->d_tma_list, op->d_tma_foreign, f->d_tma_chunks + c_first, c_count, f->tma_any_mode1};
   const TmaMaps *o0 = epi.v0 ? tma_maps_for(op, epi.v0) : tm, *o1 = epi.v1 ? tma_maps_for(op, epi.v1) : tm;
   if (o0 == nullptr || o1 == nullptr)
@@ -3776,5 +3784,194 @@ dasm_cheb_vmult_host(dasm_cheb *c, double *dst_owned, const double *src_owned)
   DASM_API_BEGIN
   CUDA_CHECK(cudaSetDevice(c->op->ctx->device));
   DISPATCH_TYPE(c->op->ntype, cheb_host<T>(c, dst_owned, src_owned, false));
+  DASM_API_END
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI: Krylov solvers (SolverCG / SolverGMRES of the reference's solve(), element_centered_preconditioners_01.cc:108-203)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+static void
+krylov_precon(dasm_op *op, const int kind, void *handle, const T *inv_diag, T *z, const T *r)
+{
+  dasm_ctx *      ctx = op->ctx;
+  const long long n   = op->n_owned;
+  switch (kind)
+    {
+      case DASM_PRECON_IDENTITY:
+        CUDA_CHECK(cudaMemcpyAsync(z, r, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, ctx->stream));
+        break;
+      case DASM_PRECON_DIAGONAL:
+        vec_mul_kernel<T><<<nblocks(n), 256, 0, ctx->stream>>>(z, inv_diag, r, n);
+        ctx->launches++;
+        break;
+      case DASM_PRECON_FDM:
+        fdm_vmult<T>((dasm_fdm *)handle, z, r, nullptr, nullptr);
+        break;
+      case DASM_PRECON_CHEBYSHEV:
+        cheb_run<T>((dasm_cheb *)handle, z, r, false);
+        break;
+      default:
+        throw std::runtime_error("Preconditioner kind is not known!");
+    }
+}
+
+template <typename T>
+static void
+krylov_solve(dasm_op *op, const int solver, const int pkind, void *ph, T *x, const T *b, const int max_it, const double abs_tol,
+             const double rel_tol, int restart, int *n_it, double *residual)
+{
+  dasm_ctx *      ctx = op->ctx;
+  cudaStream_t    s   = ctx->stream;
+  const long long n   = op->n_owned;
+  const size_t    nv  = (size_t)op->n_vec;
+  std::vector<T *> owned;
+  auto             alloc = [&]() {
+    T *p = dev_alloc<T>(nv);
+    CUDA_CHECK(cudaMemsetAsync(p, 0, nv * sizeof(T), s));
+    owned.push_back(p);
+    return p;
+  };
+  T *inv_diag = nullptr;
+  if (pkind == DASM_PRECON_DIAGONAL)
+    {
+      inv_diag = alloc();
+      op_inverse_diagonal<T>(op, inv_diag);
+    }
+  CUDA_CHECK(cudaMemsetAsync(x, 0, nv * sizeof(T), s));
+  const double r0     = std::sqrt(device_dot<T>(ctx, b, b, n));
+  const double target = std::max(abs_tol, rel_tol * r0);
+  int          its    = 0;
+  double       res    = r0;
+  bool         done   = r0 <= target;
+  if (solver == DASM_SOLVER_CG && !done)
+    {
+      T *r = alloc(), *z = alloc(), *p = alloc(), *Ap = alloc();
+      CUDA_CHECK(cudaMemcpyAsync(r, b, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, s));
+      krylov_precon<T>(op, pkind, ph, inv_diag, z, r);
+      CUDA_CHECK(cudaMemcpyAsync(p, z, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, s));
+      double rz = device_dot<T>(ctx, r, z, n);
+      while (its < max_it)
+        {
+          op_vmult<T>(op, Ap, p, nullptr, nullptr);
+          const double alpha = rz / device_dot<T>(ctx, p, Ap, n);
+          vec_axpy_kernel<T><<<nblocks(n), 256, 0, s>>>(x, (T)alpha, p, n);
+          vec_axpy_kernel<T><<<nblocks(n), 256, 0, s>>>(r, (T)(-alpha), Ap, n);
+          ctx->launches += 2;
+          ++its;
+          res = std::sqrt(device_dot<T>(ctx, r, r, n));
+          if (res <= target)
+            {
+              done = true;
+              break;
+            }
+          krylov_precon<T>(op, pkind, ph, inv_diag, z, r);
+          const double rz_new = device_dot<T>(ctx, r, z, n);
+          vec_xpay_kernel<T><<<nblocks(n), 256, 0, s>>>(p, (T)(rz_new / rz), z, n);
+          ctx->launches++;
+          rz = rz_new;
+        }
+    }
+  else if (!done)
+    {
+      // GMRES(restart) with right preconditioning; Z_j = M^-1 v_j kept, so that x += Z y needs no further preconditioner call
+      restart = std::max(1, restart);
+      std::vector<T *> V(restart + 1), Z(restart);
+      for (auto &p : V)
+        p = alloc();
+      for (auto &p : Z)
+        p = alloc();
+      T *                 w = alloc();
+      std::vector<double> H((size_t)(restart + 1) * restart), g(restart + 1), cs(restart), sn(restart);
+      while (its < max_it && !done)
+        {
+          // r = b - A x
+          op_vmult<T>(op, w, x, nullptr, nullptr);
+          vec_residual_kernel<T><<<nblocks(n), 256, 0, s>>>(w, b, n); // w = b - w
+          ctx->launches++;
+          const double beta = std::sqrt(device_dot<T>(ctx, w, w, n));
+          vec_scale_kernel<T><<<nblocks(n), 256, 0, s>>>(V[0], w, (T)(1. / beta), n);
+          ctx->launches++;
+          std::fill(H.begin(), H.end(), 0.);
+          std::fill(g.begin(), g.end(), 0.);
+          g[0]   = beta;
+          int kk = 0;
+          for (int j = 0; j < restart; ++j)
+            {
+              krylov_precon<T>(op, pkind, ph, inv_diag, Z[j], V[j]);
+              op_vmult<T>(op, w, Z[j], nullptr, nullptr);
+              for (int i = 0; i <= j; ++i)
+                {
+                  const double h         = device_dot<T>(ctx, w, V[i], n);
+                  H[(size_t)i * restart + j] = h;
+                  vec_axpy_kernel<T><<<nblocks(n), 256, 0, s>>>(w, (T)(-h), V[i], n);
+                  ctx->launches++;
+                }
+              const double hn                  = std::sqrt(device_dot<T>(ctx, w, w, n));
+              H[(size_t)(j + 1) * restart + j] = hn;
+              vec_scale_kernel<T><<<nblocks(n), 256, 0, s>>>(V[j + 1], w, (T)(hn > 0 ? 1. / hn : 0.), n);
+              ctx->launches++;
+              for (int i = 0; i < j; ++i)
+                {
+                  const double t                   = cs[i] * H[(size_t)i * restart + j] + sn[i] * H[(size_t)(i + 1) * restart + j];
+                  H[(size_t)(i + 1) * restart + j] = -sn[i] * H[(size_t)i * restart + j] + cs[i] * H[(size_t)(i + 1) * restart + j];
+                  H[(size_t)i * restart + j]       = t;
+                }
+              const double d = std::hypot(H[(size_t)j * restart + j], H[(size_t)(j + 1) * restart + j]);
+              cs[j]          = H[(size_t)j * restart + j] / d;
+              sn[j]          = H[(size_t)(j + 1) * restart + j] / d;
+              H[(size_t)j * restart + j]       = d;
+              H[(size_t)(j + 1) * restart + j] = 0;
+              g[j + 1]       = -sn[j] * g[j];
+              g[j]           = cs[j] * g[j];
+              ++its;
+              kk  = j + 1;
+              res = std::fabs(g[j + 1]);
+              if (res <= target || its >= max_it)
+                {
+                  done = res <= target;
+                  break;
+                }
+            }
+          // back substitution and update
+          std::vector<double> y(kk);
+          for (int i = kk - 1; i >= 0; --i)
+            {
+              double v = g[i];
+              for (int l = i + 1; l < kk; ++l)
+                v -= H[(size_t)i * restart + l] * y[l];
+              y[i] = v / H[(size_t)i * restart + i];
+            }
+          for (int i = 0; i < kk; ++i)
+            {
+              vec_axpy_kernel<T><<<nblocks(n), 256, 0, s>>>(x, (T)y[i], Z[i], n);
+              ctx->launches++;
+            }
+          if (its >= max_it)
+            break;
+        }
+    }
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  for (T *p : owned)
+    cudaFree(p);
+  if (n_it)
+    *n_it = its;
+  if (residual)
+    *residual = res;
+  if (!done)
+    throw std::runtime_error("SolverControl::NoConvergence: the solver did not converge in " + std::to_string(max_it) + " iterations");
+}
+
+extern "C" int
+dasm_solve(dasm_op *op, int solver, int precon_kind, void *precon, void *x, const void *b, int max_it, double abs_tol, double rel_tol,
+           int restart, int *n_it, double *residual)
+{
+  DASM_API_BEGIN
+  DASM_REQUIRE(solver == DASM_SOLVER_CG || solver == DASM_SOLVER_GMRES, "Solver is not known!");
+  DASM_REQUIRE((precon_kind == DASM_PRECON_FDM || precon_kind == DASM_PRECON_CHEBYSHEV) == (precon != nullptr),
+               "preconditioner handle does not match its kind");
+  CUDA_CHECK(cudaSetDevice(op->ctx->device));
+  DISPATCH_TYPE(op->ntype, krylov_solve<T>(op, solver, precon_kind, precon, (T *)x, (const T *)b, max_it, abs_tol, rel_tol, restart, n_it,
+                                           residual));
   DASM_API_END
 }

@@ -645,9 +645,12 @@ namespace dasm
       tma_foreign_gather<k, T>(tile, list, dn[9], src, tid);
   }
 
+#ifndef TMA_MINB
+#define TMA_MINB(k) 1
+#endif
   // ---- Laplace, uniform Cartesian geometry --------------------------------------------------------------------------------------
   template <int k, typename T, int NOPS>
-  __global__ void __launch_bounds__(TmaGeom<k, T>::NT, 1)
+  __global__ void __launch_bounds__(TmaGeom<k, T>::NT, TMA_MINB(k))
   laplace_tma_kernel(const T *__restrict__ src,
                      T *__restrict__ dst,
                      T *__restrict__ acc,
@@ -804,7 +807,7 @@ namespace dasm
 
   // ---- FDM, one eigen-decomposition triple, tensor-product weights folded into the matrices ----------------------------------
   template <int k, typename T, int NOPS>
-  __global__ void __launch_bounds__(TmaGeom<k, T>::NT, 1)
+  __global__ void __launch_bounds__(TmaGeom<k, T>::NT, TMA_MINB(k))
   fdm_tma_kernel(const T *__restrict__ src,
                  T *__restrict__ dst,
                  T *__restrict__ acc,

@@ -210,6 +210,28 @@ extern "C"
   int dasm_cheb_step_host(dasm_cheb *cheb, double *dst_owned, const double *src_owned);
   int dasm_cheb_vmult_host(dasm_cheb *cheb, double *dst_owned, const double *src_owned);
 
+  /* ---- Krylov solvers on the device: solve() of element_centered_preconditioners_01.cc:108-203 --------------------
+   * solver: DASM_SOLVER_CG (SolverCG) or DASM_SOLVER_GMRES (SolverGMRES, right preconditioning, restart after `restart` vectors;
+   * the reference's default max_n_tmp_vectors = 30); stopping rule of ReductionControl(max_it, abs_tol, rel_tol): the residual
+   * norm drops below max(abs_tol, rel_tol * ||r0||).  x starts from 0 (`x = 0` in dispatch()).
+   * preconditioner: DASM_PRECON_IDENTITY (handle NULL), DASM_PRECON_DIAGONAL (NULL; DiagonalMatrix of the inverse diagonal),
+   * DASM_PRECON_FDM (dasm_fdm*), DASM_PRECON_CHEBYSHEV (dasm_cheb*).  n_it = solver_control.last_step(), residual = last
+   * residual norm (estimate for GMRES).  Returns an error when max_it is reached (SolverControl::NoConvergence). */
+  enum
+  {
+    DASM_SOLVER_CG    = 0,
+    DASM_SOLVER_GMRES = 1
+  };
+  enum
+  {
+    DASM_PRECON_IDENTITY  = 0,
+    DASM_PRECON_DIAGONAL  = 1,
+    DASM_PRECON_FDM       = 2,
+    DASM_PRECON_CHEBYSHEV = 3
+  };
+  int dasm_solve(dasm_op *op, int solver, int precon_kind, void *precon, void *x, const void *b, int max_it, double abs_tol,
+                 double rel_tol, int restart, int *n_it, double *residual);
+
 #ifdef __cplusplus
 }
 #endif

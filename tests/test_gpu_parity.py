@@ -342,3 +342,51 @@ def test_smoother_reduces_residual_large(pkg, ctx):
         cheb.step(xd, bd)
     e1 = np.linalg.norm(op.to_host(xd) - xt)
     assert e1 < 0.5 * e0
+
+
+# ---- Krylov solvers on the device (dasm_solve) against the oracle's restatement of the reference's solve() ---------------------
+@pytest.mark.parametrize("solver,precon", [("CG", None), ("CG", "Diagonal"), ("CG", "fdm-symm"), ("GMRES", "Diagonal"),
+                                           ("GMRES", "fdm-post"), ("GMRES", "cheb-fdm-post"), ("CG", "cheb-diag")])
+def test_krylov_iteration_counts(pkg, ctx, solver, precon):
+    """element_centered_preconditioners_01.cc:108-203: CG / GMRES (right preconditioning) with ReductionControl(1000, 1e-10, 1e-2);
+    same iteration count as the oracle and the same solution to 1e-10 (the oracle's solvers are pinned to the reference's
+    iteration counts 24 / 23 / 9 in tests/test_oracle_golden.py)."""
+    mesh = pkg.Mesh(ctx, (6, 5, 4), periodic=(0, 0, 0), dirichlet=True)
+    k = 3
+    op = pkg.LaplaceOperatorMatrixFree(mesh, k, "double")
+    wt = "symm" if precon in (None, "Diagonal", "fdm-symm", "cheb-diag") else "post"
+    oop, oP = oracle_problem(pkg, mesh, op, 1, wt)
+    n = op.n_dofs()
+    rng = np.random.default_rng(11)
+    b = rng.uniform(-1, 1, n)
+    b[op.constrained_dofs()] = 0.0
+    A = lambda v: oop.vmult(v, copy_constrained=True)
+    if precon is None:
+        P, dev_P = (lambda v: v.copy()), None
+    elif precon == "Diagonal":
+        P, dev_P = o.JacobiPreconditioner(oop).vmult, "Diagonal"
+    elif precon.startswith("fdm"):
+        dev_P = pkg.create_fdm_preconditioner(op, {"weighting type": wt})
+        P = oP.vmult
+    elif precon == "cheb-diag":
+        dev_P = pkg.PreconditionChebyshev(op, None, degree=3)
+        dev_P.set_eigenvalues(0.5, 2.0)
+        och = o.Chebyshev(oop, o.JacobiPreconditioner(oop), degree=3)
+        och.set_eigenvalues(2.0, 0.5)
+        P = och.vmult
+    else:
+        fdm = pkg.create_fdm_preconditioner(op, {"weighting type": wt})
+        dev_P = pkg.PreconditionChebyshev(op, fdm, degree=2)
+        dev_P.set_eigenvalues(1.0, 2.2)
+        och = o.Chebyshev(oop, oP, degree=2)
+        och.set_eigenvalues(2.2, 1.0)
+        P = och.vmult
+    if solver == "CG":
+        x_ref, its_ref = o.solve_cg(A, P, b)
+    else:
+        x_ref, its_ref = o.solve_gmres(A, P, b)
+    xd = op.initialize_dof_vector()
+    its, res = pkg.solve(op, xd, op.to_device(b), dev_P, {"type": solver})
+    assert its == its_ref
+    assert relerr(op.to_host(xd), x_ref) < 1e-10
+    assert res <= 1e-2 * np.linalg.norm(b) * (1 + 1e-8)
