@@ -966,12 +966,12 @@ tma_chunk_range(const int first, const int count, const int n_fast, const int n_
   return true;
 }
 
-// thread blocks per SM of the TMA-fed kernels (experiments: DASM_TMA_CTAS)
+// thread blocks per SM of the TMA-fed kernels (kernels_tma.cuh TMA_MINB; DASM_TMA_CTAS overrides for experiments)
 static int
-tma_ctas_per_sm()
+tma_ctas_per_sm(const int k)
 {
-  static const int v = getenv("DASM_TMA_CTAS") ? std::max(1, atoi(getenv("DASM_TMA_CTAS"))) : 1;
-  return v;
+  static const int v = getenv("DASM_TMA_CTAS") ? std::max(1, atoi(getenv("DASM_TMA_CTAS"))) : 0;
+  return v > 0 ? v : TMA_MINB(k);
 }
 
 // tensor maps of a vector for the TMA-fed kernels (cached per pointer); nullptr: not usable (alignment)
@@ -1016,7 +1016,7 @@ launch_laplace_fast(dasm_op *op, T *dst, const T *src, const Epilogue<T> &epi, c
     return false;
   if (c_count == 0)
     return true;
-  const int      grid = std::min(c_count, std::max(1, op->n_sm * tma_ctas_per_sm() - reserve_sms));
+  const int      grid = std::min(c_count, std::max(1, op->n_sm * tma_ctas_per_sm(K) - reserve_sms));
   const TmaList  list = {op->d_tma_lap, op->d_tma_foreign, op->d_tma_lap_chunks + c_first, c_count, op->tma_any_mode1};
   const TmaMaps *o0   = epi.v0 ? tma_maps_for(op, epi.v0) : tm;
   if (o0 == nullptr)
@@ -1259,7 +1259,7 @@ launch_fdm_fast(dasm_fdm *f, T *dst, const T *src, const Epilogue<T> &epi, const
     return false;
   if (c_count == 0)
     return true;
-  const int      grid = std::min(c_count, std::max(1, op->n_sm * tma_ctas_per_sm() - reserve_sms));
+  const int      grid = std::min(c_count, std::max(1, op->n_sm * tma_ctas_per_sm(K) - reserve_sms));
   const TmaList  list = {f->d_tma_list, op->d_tma_foreign, f->d_tma_chunks + c_first, c_count, f->tma_any_mode1};
   const TmaMaps *o0 = epi.v0 ? tma_maps_for(op, epi.v0) : tm, *o1 = epi.v1 ? tma_maps_for(op, epi.v1) : tm;
   if (o0 == nullptr || o1 == nullptr)

@@ -645,8 +645,10 @@ namespace dasm
       tma_foreign_gather<k, T>(tile, list, dn[9], src, tid);
   }
 
+// resident thread blocks per SM: two for k <= 3 (shared memory and registers allow it; two independent blocks overlap the barrier /
+// latency stalls of one with the work of the other: +34 % (double), +49 % (float) at k = 3, profiles/r02l_k3_two_blocks.txt)
 #ifndef TMA_MINB
-#define TMA_MINB(k) 1
+#define TMA_MINB(k) ((k) <= 3 ? 2 : 1)
 #endif
   // ---- Laplace, uniform Cartesian geometry --------------------------------------------------------------------------------------
   template <int k, typename T, int NOPS>
