@@ -507,6 +507,7 @@ struct dasm_cheb
   void *    d_inv_diag = nullptr;
   void *    t1 = nullptr, *t1b = nullptr, *t2 = nullptr, *xold = nullptr, *xin = nullptr, *bin = nullptr;
   void *    d_stage = nullptr; // single precision: double staging buffer of the host entry points
+  int       t1_zero_idx = -1; // residual buffer (0 / 1) whose shared DoFs the last kernel of the previous fused call left zero
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -907,14 +908,11 @@ struct TmaChunked
 };
 
 static TmaChunked
-tma_build_list(const dasm_op *op, const std::vector<uint32_t> &ids, const int n_boundary)
+tma_build_list_L(const dasm_op *op, const std::vector<uint32_t> &ids, const int n_boundary, const int L)
 {
   TmaChunked out;
-  const int  n = (int)ids.size();
-  int        L = std::max(1, std::min(8, n / std::max(1, 4 * op->n_sm)));
-  if (const char *e = getenv("DASM_TMA_CHUNK"))
-    L = std::max(1, atoi(e));
-  int len = 0;
+  const int  n   = (int)ids.size();
+  int        len = 0;
   for (int i = 0; i < n; ++i)
     {
       TmaBrick t = op->h_tma[ids[i]];
@@ -948,6 +946,48 @@ tma_build_list(const dasm_op *op, const std::vector<uint32_t> &ids, const int n_
     out.n_chunks_boundary = (int)out.chunk_start.size();
   out.chunk_start.push_back((uint32_t)n);
   return out;
+}
+
+// Chunk length: long chunks save the red.add / zeroing of the faces between their bricks (measured: time ~ 1 + 0.235 / L), but the
+// chunks are dealt out statically to the resident blocks, so their number should fill the last round: the length 1..16 with the
+// best product of both effects (DASM_TMA_CHUNK overrides).
+static TmaChunked
+tma_build_list(const dasm_op *op, const std::vector<uint32_t> &ids, const int n_boundary)
+{
+  if (const char *e = getenv("DASM_TMA_CHUNK"))
+    return tma_build_list_L(op, ids, n_boundary, std::max(1, atoi(e)));
+  const int  blocks = std::max(1, op->n_sm * TMA_MINB(op->k));
+  if (getenv("DASM_VERBOSE"))
+    fprintf(stderr, "[dasm] chunking %zu lex bricks over %d resident blocks\n", ids.size(), blocks);
+  TmaChunked best;
+  double     best_score = -1;
+  for (int L = 16; L >= 1; --L)
+    {
+      TmaChunked   c  = tma_build_list_L(op, ids, n_boundary, L);
+      const int    nc = (int)c.chunk_start.size() - 1;
+      // static deal: block b processes the chunks b, b + blocks, ...; efficiency = mean load / maximum load (in bricks)
+      double eff = 1.;
+      if (nc > 0)
+        {
+          const int             nb_used = std::min(nc, blocks);
+          std::vector<uint32_t> load(nb_used, 0);
+          for (int q = 0; q < nc; ++q)
+            load[q % nb_used] += c.chunk_start[q + 1] - c.chunk_start[q];
+          const uint32_t mx = *std::max_element(load.begin(), load.end());
+          eff               = (double)ids.size() / ((double)blocks * mx);
+        }
+      // average number of bricks per chunk (chunks are cut at the ends of the brick rows and at non-lex neighbours)
+      const double len = nc == 0 ? 1. : (double)ids.size() / nc;
+      const double score = eff / (1. + 0.235 / len);
+      if (getenv("DASM_VERBOSE"))
+        fprintf(stderr, "[dasm]   L = %d: %d chunks, efficiency %.3f, score %.3f\n", L, nc, eff, score);
+      if (score > best_score)
+        {
+          best_score = score;
+          best       = std::move(c);
+        }
+    }
+  return best;
 }
 
 // chunk range of a launch over the bricks [first, first + count) of a fast list (whole list, boundary part or interior part)
@@ -3633,6 +3673,10 @@ cheb_run(dasm_cheb *c, T *x_user, const T *b, bool first_is_step)
   const bool direct = op->use_brick && op->shared_ranges_ok && c->fdm != nullptr && fdm_uses_brick(c->fdm) && c->optimize >= 2 &&
                       !(getenv("DASM_NO_DIRECT") && getenv("DASM_NO_DIRECT")[0] == '1');
   T *t1buf[2] = {t1, (T *)c->t1b};
+  // the residual buffers alternate; the sequence starts with the one the previous fused call left zeroed on the shared DoFs
+  const int t1_off = (direct && c->t1_zero_idx >= 0) ? c->t1_zero_idx : 0;
+  const bool t1_ready = direct && c->t1_zero_idx >= 0;
+  c->t1_zero_idx = -1;
   for (int term = 0; term < n_terms; ++term)
     {
       double f1 = 0, f2 = f2_0;
@@ -3654,7 +3698,7 @@ cheb_run(dasm_cheb *c, T *x_user, const T *b, bool first_is_step)
         }
       const bool  need_A   = !(term == 0 && !first_is_step);
       const bool  last     = (term == n_terms - 1);
-      T *         t1cur    = t1buf[term & 1];
+      T *         t1cur    = t1buf[(term + t1_off) & 1];
       const T *   old_used = (have_old && f1 != 0.) ? old : nullptr;
       dasm_hook   upd;
       if (!need_A)
@@ -3668,11 +3712,11 @@ cheb_run(dasm_cheb *c, T *x_user, const T *b, bool first_is_step)
           NextInit<T> ni_upd = no_next_init<T>();
           ni_upd.out         = nxt;
           NextInit<T> ni_res = no_next_init<T>();
-          ni_res.out         = t1buf[(term + 1) & 1];
+          ni_res.out         = t1buf[(term + 1 + t1_off) & 1]; // (also after the last term: ready for the next call)
           const T *rhs_for_P = b;
           if (need_A)
             {
-              if (term == 0)
+              if (term == 0 && !t1_ready)
                 {
                   NextInit<T> first = ni_res;
                   first.out         = t1cur;
@@ -3683,7 +3727,9 @@ cheb_run(dasm_cheb *c, T *x_user, const T *b, bool first_is_step)
             }
           else
             init_shared<T>(op, ni_upd);
-          fdm_vmult_brick<T>(c->fdm, nxt, rhs_for_P, &upd, SHARED_DIRECT, last ? no_next_init<T>() : ni_res);
+          fdm_vmult_brick<T>(c->fdm, nxt, rhs_for_P, &upd, SHARED_DIRECT, ni_res);
+          if (last)
+            c->t1_zero_idx = (term + 1 + t1_off) & 1;
         }
       else
         {

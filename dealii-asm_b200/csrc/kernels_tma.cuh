@@ -1,19 +1,24 @@
 // Warp-specialised, TMA-fed brick kernels (sm_100a) for the "lex" bricks of a mesh (mesh.h): full 4 x 4 x 4 bricks whose
 // own DoFs are the lexicographic box [0, 4k)^3 = block i of 64 k^3 entries of every vector, i.e. a 4-D tensor
-// (x, y, z, brick) that the TMA engine moves with box copies (cp.async.bulk.tensor, SASS UTMALDG):
+// (x, y, z, brick) that the TMA engine moves with box copies (cp.async.bulk.tensor, SASS UTMALDG).
 //
-//   tile of a brick = own box {R, R, R} (R = 4k)                                  one tensor copy
-//                   + the faces / edges / corner owned by the 7 upper neighbours   7 tensor copies: {XW,R,R} (x = 0 plane of the
-//                     +x brick, XW = 16 bytes wide), {R,1,R}, {R,R,1}, {XW,1,R}, {XW,R,1}, {R,1,1}, {XW,1,1}
+// Work item of a thread block = a z-slab of BZ cell layers of a brick (BZ = 4: the whole brick, k <= 3; BZ = 2: half a brick,
+// k = 4, so that TWO blocks are resident per SM and the barrier / latency stalls of one overlap with the work of the other):
+//
+//   tile of an item = own box {R, R, RZ} (R = 4k, RZ = BZ k)                         one tensor copy
+//                   + the faces / edges / corner towards +x, +y, +z                   7 tensor copies: {XW,R,RZ} (x = 0 plane of
+//                     the +x brick, XW = 16 bytes wide), {R,1,RZ}, {R,R,1}, {XW,1,RZ}, {XW,R,1}, {R,1,1}, {XW,1,1}
 //   all issued by ONE thread on one mbarrier (complete_tx); no index tables, no LSU work, no per-brick index traffic.
 //   Bricks with an upper neighbour that is not a local lex brick (partition boundary: ghost entries; irregular bricks)
-//   fetch the foreign points through an index list with cp.async instead (mode 1).
-//   epilogue operands (b; x and x_old) of the own box: 1-D bulk copies (the box is contiguous in global memory).
+//   fetch those points through an index list with cp.async instead (mode 1).
+//   The epilogue operands (b; x and x_old) of the own box are staged by tensor copies as well.
 //
-// Compute phases, even-odd contractions, the merge by shuffles and the named-barrier hand-over to the mover warps are
-// those of kernels_fast.cuh (which remains the path for the old numbering, DASM_NO_LEX=1).  The mover warps run the
-// fused vector epilogue in the order of the box: 16-byte shared-memory loads and global stores, red.global.add for the
-// box points on the shared lower faces (X = 0, Y = 0 or Z = 0) and for the points owned by the upper neighbours.
+// Compute: thread (cell, plane t), lanes = cells; phases, even-odd contractions and the merge by shuffles are described in
+// kernels_fast.cuh.  After the merge every point of the item's closure is final in exactly one thread, which runs the fused
+// vector epilogue straight from its registers: plain 16-byte global stores for the private points, red.global.add for the own
+// points on the faces shared with bricks processed elsewhere and for the points owned by the upper neighbours.
+// Items are walked in chunks of +x neighbours (and the slabs of a brick bottom-up): the contributions to the face between
+// two consecutive items are handed over through shared memory, so these faces need neither red.add nor zeroing.
 #pragma once
 #include <cuda.h>
 
@@ -34,21 +39,20 @@ namespace dasm
   {
     TMA_MODE1     = 1u, // an upper neighbour is not a local lex brick: foreign points through the index list
     TMA_CARRY_IN  = 2u, // the previous brick of the chunk is the -x neighbour: its X = R contributions arrive through shared memory,
-                        // the own face X = 0 is complete after this brick (plain stores, no red.add / pre-initialisation)
+                        // the own face X = 0 is complete after this brick (plain stores, no red.add / zeroing)
     TMA_CARRY_OUT = 4u, // the next brick of the chunk is the +x neighbour: X = R contributions are handed over, not red.add-ed
     TMA_LAST      = 8u, // last brick of its chunk
     TMA_NONE      = 0xFFFFFFFFu
   };
 
-  // tensor maps of one vector (kernel parameters)
+  // tensor maps of one vector (kernel parameters): own box, +x face, +y face, +z face, edges, corner
   struct TmaMaps
   {
     CUtensorMap main, fx, fy, fz, exy, exz, eyz, cxyz;
   };
 
   // Bricks are processed in chunks of consecutive +x neighbours: thread block b walks the chunks b, b + grid, ... and the
-  // bricks [chunk_start[c], chunk_start[c + 1]) of a chunk in order, so that the contributions to the face between two bricks
-  // of a chunk never leave the SM.
+  // bricks [chunk_start[c], chunk_start[c + 1]) of a chunk in order.
   struct TmaList
   {
     const TmaBrick *bricks;      // whole list
@@ -65,86 +69,68 @@ namespace dasm
     int      chunk;
   };
 
-  template <int k, typename T>
+  // geometry of the foreign index list of a brick (whole brick, face order):
+  //   fx[Z][Y] | fy[Z][X] | fz[Y][X] | exy[Z] | exz[Y] | eyz[X] | c
+  template <int k>
+  struct TmaListGeom
+  {
+    static constexpr int R     = 4 * k;
+    static constexpr int J_FX  = 0;
+    static constexpr int J_FY  = R * R;
+    static constexpr int J_FZ  = 2 * R * R;
+    static constexpr int J_EXY = 3 * R * R;
+    static constexpr int J_EXZ = J_EXY + R;
+    static constexpr int J_EYZ = J_EXZ + R;
+    static constexpr int J_C   = J_EYZ + R;
+    static constexpr int NFOR  = J_C + 1;
+    static constexpr int NFP   = (NFOR + 3) / 4 * 4;
+  };
+
+  template <int k, typename T, int BZ>
   struct TmaGeom
   {
     static constexpr int n      = k + 1;
-    static constexpr int R      = 4 * k;
+    static constexpr int R      = 4 * k;  // box edge in x and y
+    static constexpr int RZ     = BZ * k; // box edge in z of one item
+    static constexpr int NH     = 4 / BZ; // items per brick
     static constexpr int XW     = 16 / (int)sizeof(T);
-    static constexpr int NB     = R * R * R;
-    static constexpr int NCELLS = 64;
+    static constexpr int NB     = R * R * R;  // DoFs of a brick
+    static constexpr int NBI    = R * R * RZ; // DoFs of an item
+    static constexpr int NCELLS = 16 * BZ;
     static constexpr int NCT    = NCELLS * n;
     static constexpr int NT     = NCT;
     static constexpr int CS     = (n * n * n) | 1;
-    static constexpr int V      = 16 / (int)sizeof(T); // elements per 16-byte vector
     __host__ __device__ static constexpr int
     pad(const int e)
     {
       return (e * (int)sizeof(T) + 127) / 128 * 128 / (int)sizeof(T);
     }
-    // tile regions (element offsets, 128-byte aligned: TMA destinations)
-    static constexpr int O_MAIN = 0;
-    static constexpr int O_FX   = O_MAIN + pad(NB);
-    static constexpr int O_FY   = O_FX + pad(R * R * XW);
-    static constexpr int O_FZ   = O_FY + pad(R * R);
-    static constexpr int O_EXY  = O_FZ + pad(R * R);
-    static constexpr int O_EXZ  = O_EXY + pad(R * XW);
-    static constexpr int O_EYZ  = O_EXZ + pad(R * XW);
-    static constexpr int O_C    = O_EYZ + pad(R);
+    // tile regions (element offsets, 128-byte aligned: TMA destinations); Z is local to the item (0 .. RZ)
+    static constexpr int O_MAIN = 0;                       // [Z][Y][X] (layout TmaLayout)
+    static constexpr int O_FX   = O_MAIN + pad(NBI);       // X = R:          [Z][Y][XW]
+    static constexpr int O_FY   = O_FX + pad(RZ * R * XW); // Y = R:          [Z][X]
+    static constexpr int O_FZ   = O_FY + pad(RZ * R);      // Z = RZ:         [Y][X]
+    static constexpr int O_EXY  = O_FZ + pad(R * R);       // X = R, Y = R:   [Z][XW]
+    static constexpr int O_EXZ  = O_EXY + pad(RZ * XW);    // X = R, Z = RZ:  [Y][XW]
+    static constexpr int O_EYZ  = O_EXZ + pad(R * XW);     // Y = R, Z = RZ:  [X]
+    static constexpr int O_C    = O_EYZ + pad(R);          // corner
     static constexpr int TILE   = O_C + pad(XW);
-    static constexpr unsigned BYTES_MAIN = (unsigned)(NB * sizeof(T));
-    static constexpr unsigned BYTES_FOR  = (unsigned)((R * R * XW + 2 * R * R + 2 * R * XW + R + XW) * sizeof(T));
-    // points owned by the upper neighbours in face order: fx[Z][Y] | fy[Z][X] | fz[Y][X] | exy[Z] | exz[Y] | eyz[X] | c
-    static constexpr int J_FY   = R * R;
-    static constexpr int J_FZ   = 2 * R * R;
-    static constexpr int J_EXY  = 3 * R * R;
-    static constexpr int J_EXZ  = J_EXY + R;
-    static constexpr int J_EYZ  = J_EXZ + R;
-    static constexpr int J_C    = J_EYZ + R;
-    static constexpr int NFOR   = J_C + 1;
-    static constexpr int NFP    = (NFOR + 3) / 4 * 4;
-    static constexpr int NFORP  = pad(NFOR);
-    static constexpr int NSH    = NB - (R - 1) * (R - 1) * (R - 1); // own DoFs on the shared lower faces
-    static constexpr int NFT    = (NFOR + NCT - 1) / NCT;
-    static constexpr int XSLOT  = pad(NCELLS * CS);
-    // tile offset of the j-th foreign point
-    __host__ __device__ static constexpr int
-    foreign_tile_offset(const int j)
-    {
-      return j < J_FY ? O_FX + j * XW :
-                        (j < J_FZ ? O_FY + (j - J_FY) :
-                                    (j < J_EXY ? O_FZ + (j - J_FZ) :
-                                                 (j < J_EXZ ? O_EXY + (j - J_EXY) * XW :
-                                                              (j < J_EYZ ? O_EXZ + (j - J_EXZ) * XW : (j < J_C ? O_EYZ + (j - J_EYZ) : O_C)))));
-    }
-    // offset of the j-th foreign point relative to the base of the neighbour brick that owns it, and which neighbour
-    __host__ __device__ static constexpr int
-    foreign_owner(const int j)
-    {
-      return j < J_FY ? 0 : (j < J_FZ ? 1 : (j < J_EXY ? 2 : (j < J_EXZ ? 3 : (j < J_EYZ ? 4 : (j < J_C ? 5 : 6)))));
-    }
-    __host__ __device__ static constexpr int
-    foreign_box_offset(const int j)
-    {
-      // fx (Z, Y): R Y + R^2 Z = R j;  fy (Z, X): X + R^2 Z;  fz (Y, X): X + R Y;  exy (Z): R^2 Z;  exz (Y): R Y;  eyz (X): X
-      return j < J_FY ? R * j :
-                        (j < J_FZ ? ((j - J_FY) % R) + R * R * ((j - J_FY) / R) :
-                                    (j < J_EXY ? (j - J_FZ) : (j < J_EXZ ? R * R * (j - J_EXY) : (j < J_EYZ ? R * (j - J_EXZ) : (j < J_C ? (j - J_EYZ) : 0)))));
-    }
-    // box index of the s-th own DoF on the shared lower faces: plane Z = 0, then per Z >= 1 the row Y = 0 and the column X = 0
-    __host__ __device__ static constexpr int
-    shared_box_index(const int s)
-    {
-      if (s < R * R)
-        return s;
-      const int q = s - R * R, Z = 1 + q / (2 * R - 1), w = q % (2 * R - 1);
-      return Z * R * R + (w < R ? w : (w - R + 1) * R);
-    }
+    static constexpr unsigned BYTES_MAIN = (unsigned)(NBI * sizeof(T));
+    static constexpr unsigned BYTES_FOR  = (unsigned)((RZ * R * XW + RZ * R + R * R + RZ * XW + R * XW + R + XW) * sizeof(T));
+    // foreign points of an item in its own face order: fx[Z][Y] | fy[Z][X] | fz[Y][X] | exy[Z] | exz[Y] | eyz[X] | c
+    static constexpr int I_FY  = RZ * R;
+    static constexpr int I_FZ  = 2 * RZ * R;
+    static constexpr int I_EXY = I_FZ + R * R;
+    static constexpr int I_EXZ = I_EXY + RZ;
+    static constexpr int I_EYZ = I_EXZ + R;
+    static constexpr int I_C   = I_EYZ + R;
+    static constexpr int NFOR  = I_C + 1;
+    static constexpr int NFT   = (NFOR + NCT - 1) / NCT;
   };
 
-  // Layout of a box [0, R)^3 in shared memory (tile main region, output box).  Natural: row (Y, Z) of R elements at
-  // (Y + R Z) R.  k = 4: a cell row is 4 elements and the rows of the four cells (cx, cy = 0..3) a quarter-warp reads with
-  // one 16-byte load per lane must cover all 32 banks:
+  // Layout of a box [0, R) x [0, R) x [0, RZ) in shared memory (tile main region, operand boxes).  Natural: row (Y, Z) of R
+  // elements at (Y + R Z) R.  k = 4: a cell row is 4 elements and the rows of the four cells (cx, cy = 0..3) a quarter-warp
+  // reads with one 16-byte load per lane must cover all 32 banks:
   //   PERM  the rows are stored in the order rho = ((Y >> 2) & 1) + 2 (Y & 3) + 8 (Y >> 3) + 16 Z, i.e. the rows Y and Y + 4
   //         (cells cy and cy + 1) are adjacent; the tensor map enumerates the box as (x, (Y>>2)&1, Y&3, (Y>>3) + 2 Z) to make
   //         the TMA engine write it that way.  float: the two adjacent 64-byte rows are one 128-byte line: conflict-free.
@@ -162,25 +148,9 @@ namespace dasm
       return PERM ? ((Y >> 2) & 1) + 2 * (Y & 3) + 8 * (Y >> 3) + 16 * Z : Y + R * Z;
     }
     __host__ __device__ static constexpr int
-    row_y(const int rho) // inverse: Y of a row
-    {
-      return PERM ? (((rho & 1) << 2) | ((rho >> 1) & 3) | (rho & 8)) : rho % R;
-    }
-    __host__ __device__ static constexpr int
-    row_z(const int rho)
-    {
-      return PERM ? (rho >> 4) : rho / R;
-    }
-    __host__ __device__ static constexpr int
     swz(const int rho)
     {
       return SWZ ? (rho & 7) : 0;
-    }
-    // element offset of column X in a row with swizzle s
-    __host__ __device__ static constexpr int
-    col(const int X, const int s)
-    {
-      return SWZ ? ((((X >> 1) ^ s) << 1) | (X & 1)) : X;
     }
   };
 
@@ -218,55 +188,113 @@ namespace dasm
                  : "memory");
   }
 
-  // all tensor copies of one tile (one elected thread)
-  template <int k, typename T>
+  // own box of item (brick at `base`, slab hz) through the `main` map of a vector
+  template <int k, typename T, int BZ>
   __device__ __forceinline__ void
-  tma_issue_tile(T *tile, const TmaMaps &maps, const uint32_t *desc, const unsigned mbar)
+  tma_load_box(const unsigned dst, const CUtensorMap *map, const uint32_t base, const int hz, const unsigned mbar)
   {
-    using G                = TmaGeom<k, T>;
+    using G       = TmaGeom<k, T, BZ>;
+    const int brk = (int)(base / G::NB), z0 = hz * G::RZ;
+    if (TmaLayout<k, T>::PERM)
+      tma_load_4d(dst, map, 0, 0, 0, 32 * brk + 2 * z0, mbar);
+    else
+      tma_load_4d(dst, map, 0, 0, z0, brk, mbar);
+  }
+
+  // all tensor copies of the tile of one item (one elected thread)
+  template <int k, typename T, int BZ>
+  __device__ __forceinline__ void
+  tma_issue_tile(T *tile, const TmaMaps &maps, const uint32_t *desc, const int hz, const unsigned mbar)
+  {
+    using G                = TmaGeom<k, T, BZ>;
     const unsigned t0      = (unsigned)__cvta_generic_to_shared(tile);
     const uint32_t base    = desc[0];
     const bool     mode0   = (desc[1] & TMA_MODE1) == 0u;
     constexpr unsigned ES  = (unsigned)sizeof(T);
     mbar_expect_tx(mbar, mode0 ? G::BYTES_MAIN + G::BYTES_FOR : G::BYTES_MAIN);
-    tma_load_4d(t0 + G::O_MAIN * ES, &maps.main, 0, 0, 0, (int)(base / G::NB) * (TmaLayout<k, T>::PERM ? 32 : 1), mbar);
+    tma_load_box<k, T, BZ>(t0 + G::O_MAIN * ES, &maps.main, base, hz, mbar);
     if (mode0)
       {
-        tma_load_4d(t0 + G::O_FX * ES, &maps.fx, 0, 0, 0, (int)(desc[2] / G::NB), mbar);
-        tma_load_4d(t0 + G::O_FY * ES, &maps.fy, 0, 0, 0, (int)(desc[3] / G::NB), mbar);
-        tma_load_4d(t0 + G::O_FZ * ES, &maps.fz, 0, 0, 0, (int)(desc[4] / G::NB), mbar);
-        tma_load_4d(t0 + G::O_EXY * ES, &maps.exy, 0, 0, 0, (int)(desc[5] / G::NB), mbar);
-        tma_load_4d(t0 + G::O_EXZ * ES, &maps.exz, 0, 0, 0, (int)(desc[6] / G::NB), mbar);
-        tma_load_4d(t0 + G::O_EYZ * ES, &maps.eyz, 0, 0, 0, (int)(desc[7] / G::NB), mbar);
-        tma_load_4d(t0 + G::O_C * ES, &maps.cxyz, 0, 0, 0, (int)(desc[8] / G::NB), mbar);
+        // the +z plane of the item lies in the bricks themselves (next slab) or in their +z neighbours (top slab)
+        const bool top = (hz == G::NH - 1);
+        const int  z0 = hz * G::RZ, zc = top ? 0 : z0 + G::RZ;
+        const int  b_x = (int)(desc[2] / G::NB), b_y = (int)(desc[3] / G::NB), b_xy = (int)(desc[5] / G::NB);
+        const int  b_z = (int)((top ? desc[4] : base) / G::NB), b_xz = top ? (int)(desc[6] / G::NB) : b_x;
+        const int  b_yz = top ? (int)(desc[7] / G::NB) : b_y, b_xyz = top ? (int)(desc[8] / G::NB) : b_xy;
+        tma_load_4d(t0 + G::O_FX * ES, &maps.fx, 0, 0, z0, b_x, mbar);
+        tma_load_4d(t0 + G::O_FY * ES, &maps.fy, 0, 0, z0, b_y, mbar);
+        tma_load_4d(t0 + G::O_FZ * ES, &maps.fz, 0, 0, zc, b_z, mbar);
+        tma_load_4d(t0 + G::O_EXY * ES, &maps.exy, 0, 0, z0, b_xy, mbar);
+        tma_load_4d(t0 + G::O_EXZ * ES, &maps.exz, 0, 0, zc, b_xz, mbar);
+        tma_load_4d(t0 + G::O_EYZ * ES, &maps.eyz, 0, 0, zc, b_yz, mbar);
+        tma_load_4d(t0 + G::O_C * ES, &maps.cxyz, 0, 0, zc, b_xyz, mbar);
       }
   }
 
-  // mode 1: foreign points of the tile through the index list (cp.async by the compute threads)
-  template <int k, typename T>
-  __device__ __forceinline__ void
-  tma_foreign_gather(T *tile, const TmaList &list, const uint32_t list_off, const T *__restrict__ src, const int tid)
+  // global index of the tile point (X, Y, Zl) of item (desc, hz) with X = R, Y = R or Zl = RZ (a point the item does not own)
+  template <int k, typename T, int BZ>
+  __device__ __forceinline__ uint32_t
+  tma_foreign_index(const uint32_t *desc, const uint32_t *__restrict__ lists, const int hz, const int X, const int Y, const int Zl)
   {
-    using G = TmaGeom<k, T>;
-    uint32_t gf[G::NFT];
-#pragma unroll
-    for (int jj = 0; jj < G::NFT; ++jj)
+    using G            = TmaGeom<k, T, BZ>;
+    using LG           = TmaListGeom<k>;
+    constexpr int R    = G::R;
+    const bool    top  = (hz == G::NH - 1);
+    const bool    xR = (X == R), yR = (Y == R), zR = (Zl == G::RZ);
+    const int     Z    = hz * G::RZ + Zl; // within the brick (R for the plane above the top slab)
+    const bool    zf   = zR && top;       // the point lies in a +z neighbour
+    if ((desc[1] & TMA_MODE1) == 0u)
       {
-        const int j = tid + jj * G::NCT;
-        gf[jj]      = (j < G::NFOR) ? ldg_early(list.foreign + list_off + j) : 0u;
+        // owner among self / the 7 upper neighbours and the offset in its box
+        const int      q   = (xR ? 1 : 0) | (yR ? 2 : 0) | (zf ? 4 : 0); // bits: x, y, z
+        const uint32_t own = q == 0 ? desc[0] :
+                                      (q == 1 ? desc[2] :
+                                                (q == 2 ? desc[3] : (q == 3 ? desc[5] : (q == 4 ? desc[4] : (q == 5 ? desc[6] : (q == 6 ? desc[7] : desc[8]))))));
+        return own + (uint32_t)((xR ? 0 : X) + R * ((yR ? 0 : Y) + R * (zf ? 0 : Z)));
       }
+    if (!xR && !yR && !zf)
+      return desc[0] + (uint32_t)(X + R * (Y + R * Z)); // own brick (the plane between two slabs)
+    const int j = zf ? (xR ? (yR ? LG::J_C : LG::J_EXZ + Y) : (yR ? LG::J_EYZ + X : LG::J_FZ + Y * R + X)) :
+                       (xR ? (yR ? LG::J_EXY + Z : LG::J_FX + Z * R + Y) : LG::J_FY + Z * R + X);
+    return __ldg(lists + desc[9] + j);
+  }
+
+  // mode 1: foreign points of the tile through the index list (cp.async by the compute threads)
+  template <int k, typename T, int BZ>
+  __device__ __forceinline__ void
+  tma_foreign_gather(T *tile, const uint32_t *desc, const uint32_t *__restrict__ lists, const int hz, const T *__restrict__ src, const int tid)
+  {
+    using G         = TmaGeom<k, T, BZ>;
+    constexpr int R = G::R, RZ = G::RZ, XW = G::XW;
 #pragma unroll
     for (int jj = 0; jj < G::NFT; ++jj)
       {
         const int j = tid + jj * G::NCT;
         if (j < G::NFOR)
-          cp_async_value(tile + G::foreign_tile_offset(j), src + gf[jj]);
+          {
+            int X, Y, Zl, o;
+            if (j < G::I_FY)
+              X = R, Y = j % R, Zl = j / R, o = G::O_FX + j * XW;
+            else if (j < G::I_FZ)
+              X = (j - G::I_FY) % R, Y = R, Zl = (j - G::I_FY) / R, o = G::O_FY + (j - G::I_FY);
+            else if (j < G::I_EXY)
+              X = (j - G::I_FZ) % R, Y = (j - G::I_FZ) / R, Zl = RZ, o = G::O_FZ + (j - G::I_FZ);
+            else if (j < G::I_EXZ)
+              X = R, Y = R, Zl = j - G::I_EXY, o = G::O_EXY + (j - G::I_EXY) * XW;
+            else if (j < G::I_EYZ)
+              X = R, Y = j - G::I_EXZ, Zl = RZ, o = G::O_EXZ + (j - G::I_EXZ) * XW;
+            else if (j < G::I_C)
+              X = j - G::I_EYZ, Y = R, Zl = RZ, o = G::O_EYZ + (j - G::I_EYZ);
+            else
+              X = R, Y = R, Zl = RZ, o = G::O_C;
+            cp_async_value(tile + o, src + tma_foreign_index<k, T, BZ>(desc, lists, hz, X, Y, Zl));
+          }
       }
   }
 
-  // per-thread addressing of a cell plane in the tile / output box: rows r = 0..k (row r < k starts at r0 + r rs, row k at rk;
-  // the x position inside a row depends on the layout and the row's swizzle (s0 ^ (r SX)) & sm, sk), and the point x = k of
-  // the cells cx = 3 (owned by the +x neighbours) through a second set of offsets
+  // per-thread addressing of a cell plane in the tile: rows r = 0..k (row r < k starts at r0 + r rs, row k at rk; the x
+  // position inside a row depends on the layout and the row's swizzle (s0 ^ (r SX)) & sm, sk), and the point x = k of the
+  // cells cx = 3 (owned by the +x neighbours) through a second set of offsets
   struct PlaneAddr
   {
     int r0, rs, rk;
@@ -274,16 +302,16 @@ namespace dasm
     int s0, sm, sk;
   };
 
-  // Laplace phase A: plane y = t of cell (cx, cy, cz), rows z
-  template <int k, typename T>
+  // Laplace phase A: plane y = t of cell (cx, cy, cz), rows z   (cz: cell layer inside the item)
+  template <int k, typename T, int BZ>
   __device__ __forceinline__ PlaneAddr
-  tile_plane_y(const int cx, const int cy, const int cz, const int t)
+  tile_plane_y(const int cy, const int cz, const int t)
   {
-    using G       = TmaGeom<k, T>;
-    using L       = TmaLayout<k, T>;
+    using G         = TmaGeom<k, T, BZ>;
+    using L         = TmaLayout<k, T>;
     constexpr int R = G::R, XW = G::XW;
     const int     Y = k * cy + t, Z0 = k * cz;
-    const bool    yR = (Y == R), zR = (cz == 3);
+    const bool    yR = (Y == R), zR = (cz == BZ - 1);
     PlaneAddr     a;
     a.r0 = yR ? G::O_FY + Z0 * R : G::O_MAIN + L::row(Y, Z0) * R;
     a.rs = yR ? R : R * R;
@@ -294,20 +322,19 @@ namespace dasm
     a.x0 = yR ? G::O_EXY + Z0 * XW : G::O_FX + (Z0 * R + Y) * XW;
     a.xs = yR ? XW : R * XW;
     a.xk = zR ? (yR ? G::O_C : G::O_EXZ + Y * XW) : a.x0 + k * a.xs;
-    (void)cx;
     return a;
   }
 
   // FDM phase A: plane z = t of cell (cx, cy, cz), rows y
-  template <int k, typename T>
+  template <int k, typename T, int BZ>
   __device__ __forceinline__ PlaneAddr
-  tile_plane_z(const int cx, const int cy, const int cz, const int t)
+  tile_plane_z(const int cy, const int cz, const int t)
   {
-    using G       = TmaGeom<k, T>;
-    using L       = TmaLayout<k, T>;
+    using G         = TmaGeom<k, T, BZ>;
+    using L         = TmaLayout<k, T>;
     constexpr int R = G::R, XW = G::XW;
     const int     Z = k * cz + t, Y0 = k * cy;
-    const bool    zR = (Z == R), yR = (cy == 3);
+    const bool    zR = (Z == G::RZ), yR = (cy == 3);
     PlaneAddr     a;
     a.r0 = zR ? G::O_FZ + Y0 * R : G::O_MAIN + L::row(Y0, Z) * R;
     a.rs = zR ? R : (L::PERM ? 2 * R : R);
@@ -318,7 +345,6 @@ namespace dasm
     a.x0 = zR ? G::O_EXZ + Y0 * XW : G::O_FX + (Z * R + Y0) * XW;
     a.xs = XW;
     a.xk = yR ? (zR ? G::O_C : G::O_EXY + Z * XW) : a.x0 + k * XW;
-    (void)cx;
     return a;
   }
 
@@ -369,21 +395,14 @@ namespace dasm
       }
   }
 
-
   // ---- fused vector epilogue from the registers of the compute threads ------------------------------------------------------
-  // After the merge every thread (cell, plane z = t) holds the FINAL values of its exclusive points x < k (or x <= k for
-  // cx = 3), y < k (or y <= k for cy = 3) of the plane Z = k cz + t.  Points inside the own box and off the shared lower
-  // faces are private: epilogue with the operands from the (TMA-staged) operand boxes in shared memory and plain global
-  // stores straight from the registers.  Points on X = 0, Y = 0 or Z = 0 of the own box, and the points owned by the 7 upper
-  // neighbours (X = R, Y = R or Z = R), get red.global.add of alpha y (shared-face protocol of kernels_brick.cuh).
   // All epilogues are one affine form: dst = sa a + cy y + f1 (a - b)
   //   EPI_STORE (0, 1, 0)   EPI_RESIDUAL (1, -1, 0)   EPI_CHEB (1, f2, f1)   EPI_SCALE (0, f2, 0)
-  // with the operands a (b) read only if need0 (need1).
+  // with the operands a (b) read only if NOPS >= 1 (NOPS == 2).
   template <typename T>
   struct EpiCoef
   {
-    T    sa, cy, f1;
-    bool need0, need1;
+    T cy, f1;
   };
 
   template <typename T>
@@ -391,67 +410,95 @@ namespace dasm
   epi_coef(const Epilogue<T> &epi)
   {
     EpiCoef<T> c;
-    c.need0 = (epi.kind == EPI_RESIDUAL || epi.kind == EPI_CHEB);
-    c.need1 = (epi.kind == EPI_CHEB && epi.f1 != T(0) && epi.v1 != nullptr);
-    c.sa    = c.need0 ? T(1) : T(0);
-    c.cy    = (epi.kind == EPI_RESIDUAL) ? T(-1) : ((epi.kind == EPI_CHEB || epi.kind == EPI_SCALE) ? epi.f2 : T(1));
-    c.f1    = (epi.kind == EPI_CHEB) ? epi.f1 : T(0); // (v1 == nullptr: b = 0, the f1 term stays)
+    c.cy = (epi.kind == EPI_RESIDUAL) ? T(-1) : ((epi.kind == EPI_CHEB || epi.kind == EPI_SCALE) ? epi.f2 : T(1));
+    c.f1 = (epi.kind == EPI_CHEB) ? epi.f1 : T(0); // (v1 == nullptr: b = 0, the f1 term stays)
     return c;
   }
 
-  // global index of a point owned by upper neighbour q (0 +x, 1 +y, 2 +z, 3 +xy, 4 +xz, 5 +yz, 6 +xyz): box offset `off`
-  // in the neighbour's box (mode 0) or entry j of the brick's index list (mode 1)
-  __device__ __forceinline__ uint32_t
-  foreign_index(const uint32_t *desc, const uint32_t *__restrict__ lists, const int q, const int off, const int j)
+  // carries of an item (shared memory):
+  //   cx_in / cx_out  [RZ + 1][R + 1] values of the plane X = R (Z slow, Y fast) handed to the same slab of the +x brick
+  //   cz              [R + 1][R + 1]  values of the plane Zl = RZ (Y slow, X fast) handed to the next slab of the same brick
+  template <typename T>
+  struct TmaCarry
   {
-    return (desc[1] & TMA_MODE1) == 0u ? desc[2 + q] + (uint32_t)off : __ldg(lists + desc[9] + j);
-  }
+    const T *cx_in;
+    T *      cx_out;
+    T *      cz;
+  };
 
-  // carry: [R + 1][R + 1] values of the plane X = R (Z slow, Y fast) handed from a brick to its +x neighbour
+  // After the merge every thread (cell, plane z = t) holds the FINAL values of its exclusive points x < k (or x <= k for
+  // cx = 3), y < k (or y <= k for cy = 3) of the plane Zl = k cz + t of the item.
   // NOPS: number of epilogue operands staged in shared memory (0: store / scale, 1: residual or update without x_old, 2: update)
-  template <int k, typename T, int NOPS>
+  template <int k, typename T, int BZ, int NOPS>
   __device__ __forceinline__ void
-  tma_epilogue(T (&r)[k + 1][k + 1], const T *ops0, const T *ops1, const T *carry_in, T *carry_out, T *__restrict__ dst, T *__restrict__ sh_dst,
+  tma_epilogue(T (&r)[k + 1][k + 1], const T *ops0, const T *ops1, const TmaCarry<T> &cr, T *__restrict__ dst, T *__restrict__ sh_dst,
                const bool direct, T *__restrict__ ni_out, const EpiCoef<T> &ec, const uint32_t *desc, const uint32_t *__restrict__ lists,
-               const int cx, const int cy, const int cz, const int t)
+               const int hz, const int cx, const int cy, const int cz, const int t)
   {
-    using G         = TmaGeom<k, T>;
+    using G         = TmaGeom<k, T, BZ>;
     using L         = TmaLayout<k, T>;
-    constexpr int R = G::R;
+    constexpr int R = G::R, RZ = G::RZ;
     const uint32_t  base = desc[0];
-    const bool      cin = (desc[1] & TMA_CARRY_IN) != 0u, cout = (desc[1] & TMA_CARRY_OUT) != 0u;
-    const int       Z = k * cz + t;
-    const T         sh_a = direct ? ec.cy : T(1); // factor of y in the red.add of a point another brick owns
-    // (two carry planes, alternating per brick: no thread writes the plane another one still reads)
-    const T *       c_in  = carry_in + Z * (R + 1) + k * cy;
-    T *             c_out = carry_out + Z * (R + 1) + k * cy;
-    // contributions of the -x neighbour (the previous brick of this block) to the plane X = 0
-    if (cin && cx == 0)
+    // (only in the fused sequences: with the accumulator protocol finish_shared_kernel owns every DoF of the shared-DoF list)
+    const bool      cin = direct && (desc[1] & TMA_CARRY_IN) != 0u, cout = direct && (desc[1] & TMA_CARRY_OUT) != 0u;
+    const int       Zl = k * cz + t;   // plane inside the item (RZ: the plane above it)
+    const int       Z  = hz * RZ + Zl; // plane inside the brick
+    const bool      zcarry_in  = (hz > 0) && (Zl == 0);          // the slab below (processed just before) contributed to this plane
+    const bool      zcarry_out = (hz < G::NH - 1) && (Zl == RZ); // this plane belongs to the next slab of the brick
+    const T         sh_a = direct ? ec.cy : T(1);                // factor of y in the red.add of a point another brick owns
+    const int       Y0 = k * cy, X0 = k * cx;
+    // contributions of the slab below to the plane Zl = 0 (all points of the plane, X = R / Y = R included)
+    if (zcarry_in)
       {
+        const T *c = cr.cz + Y0 * (R + 1) + X0;
+#pragma unroll
+        for (int y = 0; y <= k; ++y)
+#pragma unroll
+          for (int x = 0; x <= k; ++x)
+            if ((x < k || cx == 3) && (y < k || cy == 3))
+              r[y][x] += c[y * (R + 1) + x];
+      }
+    // contributions of the -x neighbour (the same slab of the previous brick of this block) to the plane X = 0
+    // (not for a plane that is handed to the next slab: its x-neighbour contributions are merged there)
+    if (cin && cx == 0 && !zcarry_out)
+      {
+        const T *c = cr.cx_in + Zl * (R + 1) + Y0;
 #pragma unroll
         for (int y = 0; y < k; ++y)
-          r[y][0] += c_in[y];
+          r[y][0] += c[y];
         if (cy == 3)
-          r[k][0] += c_in[k];
+          r[k][0] += c[k];
       }
-    // contributions to the plane X = R: handed to the next brick of this block
+    // the plane above the item goes to the next slab as a whole
+    if (zcarry_out)
+      {
+        T *c = cr.cz + Y0 * (R + 1) + X0;
+#pragma unroll
+        for (int y = 0; y <= k; ++y)
+#pragma unroll
+          for (int x = 0; x <= k; ++x)
+            if ((x < k || cx == 3) && (y < k || cy == 3))
+              c[y * (R + 1) + x] = r[y][x];
+        return;
+      }
+    // contributions to the plane X = R: handed to the same slab of the next brick of this block
     if (cout && cx == 3)
       {
+        T *c = cr.cx_out + Zl * (R + 1) + Y0;
 #pragma unroll
         for (int y = 0; y < k; ++y)
-          c_out[y] = r[y][k];
+          c[y] = r[y][k];
         if (cy == 3)
-          c_out[k] = r[k][k];
+          c[k] = r[k][k];
       }
     const bool xred = (cx == 3) && !cout; // X = R points go to the neighbours with red.add
     const bool x0sh = (cx == 0) && !cin;  // the own face X = 0 is shared with a brick processed elsewhere
-    if (Z < R)
+    if (Zl < RZ)
       {
         const bool     zsh = (Z == 0);
-        const int      Y0 = k * cy;
-        const uint32_t g0 = base + (uint32_t)((Z * R + Y0) * R + k * cx);
+        const uint32_t g0  = base + (uint32_t)((Z * R + Y0) * R + X0);
         // operand rows: row y at rowo0 + y rstep, swizzle sw0 ^ (2 y)
-        const int rho0 = L::row(Y0, Z), rowo0 = rho0 * R, sw0 = L::swz(rho0);
+        const int     rho0 = L::row(Y0, Zl), rowo0 = rho0 * R, sw0 = L::swz(rho0);
         constexpr int rstep = (L::PERM ? 2 : 1) * R;
 #pragma unroll
         for (int y = 0; y < k; ++y)
@@ -489,9 +536,9 @@ namespace dasm
 #pragma unroll
                     for (int x = 0; x < k; ++x)
                       {
-                        a[x] = ops0[rowo + k * cx + x];
+                        a[x] = ops0[rowo + X0 + x];
                         if constexpr (NOPS == 2)
-                          b[x] = ops1[rowo + k * cx + x];
+                          b[x] = ops1[rowo + X0 + x];
                       }
                   }
               }
@@ -545,114 +592,130 @@ namespace dasm
                   }
               }
             if (xred) // X = R: face of the +x neighbour
-              atomic_add(sh_dst + foreign_index(desc, lists, 0, R * (Y0 + y + R * Z), Z * R + Y0 + y), sh_a * r[y][k]);
+              atomic_add(sh_dst + tma_foreign_index<k, T, BZ>(desc, lists, hz, R, Y0 + y, Zl), sh_a * r[y][k]);
           }
         if (cy == 3) // Y = R: face of the +y neighbour, edge of the +xy neighbour
           {
 #pragma unroll
             for (int x = 0; x < k; ++x)
-              atomic_add(sh_dst + foreign_index(desc, lists, 1, k * cx + x + R * R * Z, G::J_FY + Z * R + k * cx + x), sh_a * r[k][x]);
+              atomic_add(sh_dst + tma_foreign_index<k, T, BZ>(desc, lists, hz, X0 + x, R, Zl), sh_a * r[k][x]);
             if (xred)
-              atomic_add(sh_dst + foreign_index(desc, lists, 3, R * R * Z, G::J_EXY + Z), sh_a * r[k][k]);
+              atomic_add(sh_dst + tma_foreign_index<k, T, BZ>(desc, lists, hz, R, R, Zl), sh_a * r[k][k]);
           }
       }
     else
       {
-        // Z = R (cz = 3, t = k): face of the +z neighbour, edges of +xz, +yz, corner of +xyz
+        // Zl = RZ of the top slab: face of the +z neighbour, edges of +xz, +yz, corner of +xyz
 #pragma unroll
         for (int y = 0; y < k; ++y)
           {
-            const int Y = k * cy + y;
 #pragma unroll
             for (int x = 0; x < k; ++x)
-              atomic_add(sh_dst + foreign_index(desc, lists, 2, k * cx + x + R * Y, G::J_FZ + Y * R + k * cx + x), sh_a * r[y][x]);
+              atomic_add(sh_dst + tma_foreign_index<k, T, BZ>(desc, lists, hz, X0 + x, Y0 + y, RZ), sh_a * r[y][x]);
             if (xred)
-              atomic_add(sh_dst + foreign_index(desc, lists, 4, R * Y, G::J_EXZ + Y), sh_a * r[y][k]);
+              atomic_add(sh_dst + tma_foreign_index<k, T, BZ>(desc, lists, hz, R, Y0 + y, RZ), sh_a * r[y][k]);
           }
         if (cy == 3)
           {
 #pragma unroll
             for (int x = 0; x < k; ++x)
-              atomic_add(sh_dst + foreign_index(desc, lists, 5, k * cx + x, G::J_EYZ + k * cx + x), sh_a * r[k][x]);
+              atomic_add(sh_dst + tma_foreign_index<k, T, BZ>(desc, lists, hz, X0 + x, R, RZ), sh_a * r[k][x]);
             if (xred)
-              atomic_add(sh_dst + foreign_index(desc, lists, 6, 0, G::J_C), sh_a * r[k][k]);
+              atomic_add(sh_dst + tma_foreign_index<k, T, BZ>(desc, lists, hz, R, R, RZ), sh_a * r[k][k]);
           }
       }
   }
 
-  // operand boxes of a brick (one elected compute thread, after the barrier that ends the previous epilogue)
-  template <int k, typename T>
+  // operand boxes of an item (one elected compute thread, after the barrier that ends the previous epilogue)
+  template <int k, typename T, int BZ>
   __device__ __forceinline__ void
-  tma_issue_ops(T *ops0, T *ops1, const CUtensorMap *map0, const CUtensorMap *map1, const bool need1, const uint32_t base, const unsigned mbar)
+  tma_issue_ops(T *ops0, T *ops1, const CUtensorMap *map0, const CUtensorMap *map1, const bool need1, const uint32_t base, const int hz,
+                const unsigned mbar)
   {
-    using G                  = TmaGeom<k, T>;
-    constexpr unsigned bytes = (unsigned)(G::NB * sizeof(T));
-    const int          c3    = (int)(base / G::NB) * (TmaLayout<k, T>::PERM ? 32 : 1);
+    using G                  = TmaGeom<k, T, BZ>;
+    constexpr unsigned bytes = (unsigned)(G::NBI * sizeof(T));
     mbar_expect_tx(mbar, need1 ? 2 * bytes : bytes);
-    tma_load_4d((unsigned)__cvta_generic_to_shared(ops0), map0, 0, 0, 0, c3, mbar);
+    tma_load_box<k, T, BZ>((unsigned)__cvta_generic_to_shared(ops0), map0, base, hz, mbar);
     if (need1)
-      tma_load_4d((unsigned)__cvta_generic_to_shared(ops1), map1, 0, 0, 0, c3, mbar);
+      tma_load_box<k, T, BZ>((unsigned)__cvta_generic_to_shared(ops1), map1, base, hz, mbar);
   }
 
-  // shared memory of the kernels: header (mbarriers, two brick descriptors) | tile | X slots | operand boxes | carry plane
-  template <int k, typename T>
+  // shared memory of the kernels: header (mbarriers, two brick descriptors) | tile | X slots | operand boxes | carry planes
+  template <int k, typename T, int BZ>
   struct TmaSmem
   {
-    using G = TmaGeom<k, T>;
+    using G = TmaGeom<k, T, BZ>;
     static constexpr int
     pad1k(const int e)
     {
       return (e * (int)sizeof(T) + 1023) / 1024 * 1024 / (int)sizeof(T);
     }
-    static constexpr int TILE  = pad1k(G::TILE);
-    static constexpr int XSLOT = pad1k(G::NCELLS * G::CS);
-    static constexpr int OPS   = pad1k(G::NB);
-    static constexpr int CARRY = pad1k((G::R + 1) * (G::R + 1));
+    static constexpr int TILE   = pad1k(G::TILE);
+    static constexpr int XSLOT  = pad1k(G::NCELLS * G::CS);
+    static constexpr int OPS    = pad1k(G::NBI);
+    static constexpr int CARRYX = G::pad((G::RZ + 1) * (G::R + 1)); // per slab and brick parity
+    static constexpr int CARRYZ = G::pad((G::R + 1) * (G::R + 1));
+    static constexpr int CARRY  = pad1k(2 * G::NH * CARRYX + CARRYZ);
     static constexpr size_t
     bytes(const int n_x, const int n_ops)
     {
-      return 2048 + (size_t)(TILE + n_x * XSLOT + n_ops * OPS + 2 * CARRY) * sizeof(T);
+      return 2048 + (size_t)(TILE + n_x * XSLOT + n_ops * OPS + CARRY) * sizeof(T);
     }
   };
 
-  // common pipeline pieces of the two kernels ------------------------------------------------------------------------------
+  // resident thread blocks per SM: two (two independent blocks overlap the barrier / latency stalls of one with the work of the
+  // other: +34 % (double), +49 % (float) at k = 3, profiles/r02l_k3_two_blocks.txt): k <= 3 with whole bricks, k = 4 with
+  // half bricks (shared memory)
+#ifndef TMA_MINB
+#define TMA_MINB(k) 2
+#endif
+  // cell layers per work item
+  template <int k>
+  struct TmaItem
+  {
+    static constexpr int BZ = (k <= 3) ? 4 : 2;
+  };
+
+  // state of the walk over the items of a block
+  struct TmaCursor
+  {
+    TmaWalk w;
+    int     hz;  // slab of the current brick
+    int     par; // parity of the current brick (descriptor / x-carry ping-pong)
+  };
+
   // first tile of a block: descriptor -> s_desc[0], tensor copies (and the index-list gather of a mode-1 brick)
-  template <int k, typename T>
+  template <int k, typename T, int BZ>
   __device__ __forceinline__ void
   tma_prologue(uint32_t *s_desc, T *tile, const TmaMaps &tmaps, const TmaList &list, const uint32_t idx, const T *__restrict__ src,
                const unsigned mb_tile, const int tid)
   {
-    using G            = TmaGeom<k, T>;
+    using G            = TmaGeom<k, T, BZ>;
     const uint32_t *dw = reinterpret_cast<const uint32_t *>(list.bricks);
     if (tid < TMA_DW)
       s_desc[tid] = ldg_early(dw + (size_t)idx * TMA_DW + tid);
     bar_sync(FB_COMPUTE, G::NCT);
     if (tid == 0)
-      tma_issue_tile<k, T>(tile, tmaps, s_desc, mb_tile);
+      tma_issue_tile<k, T, BZ>(tile, tmaps, s_desc, 0, mb_tile);
     if (list.any_mode1 && (s_desc[1] & TMA_MODE1))
-      tma_foreign_gather<k, T>(tile, list, s_desc[9], src, tid);
+      tma_foreign_gather<k, T, BZ>(tile, s_desc, list.foreign, 0, src, tid);
   }
 
-  // after the barrier behind phase A: the tile is dead, fetch the next brick into it
-  template <int k, typename T>
+  // after the barrier behind phase A: the tile is dead, fetch the next item into it
+  template <int k, typename T, int BZ>
   __device__ __forceinline__ void
-  tma_fetch_next(const uint32_t *dn, T *tile, const TmaMaps &tmaps, const TmaList &list, const T *__restrict__ src, const unsigned mb_tile,
-                 const int tid)
+  tma_fetch_next(const uint32_t *dn, const int hz_next, T *tile, const TmaMaps &tmaps, const TmaList &list, const T *__restrict__ src,
+                 const unsigned mb_tile, const int tid)
   {
     if (tid == 0)
-      tma_issue_tile<k, T>(tile, tmaps, dn, mb_tile);
+      tma_issue_tile<k, T, BZ>(tile, tmaps, dn, hz_next, mb_tile);
     if (list.any_mode1 && (dn[1] & TMA_MODE1))
-      tma_foreign_gather<k, T>(tile, list, dn[9], src, tid);
+      tma_foreign_gather<k, T, BZ>(tile, dn, list.foreign, hz_next, src, tid);
   }
 
-// resident thread blocks per SM: two for k <= 3 (shared memory and registers allow it; two independent blocks overlap the barrier /
-// latency stalls of one with the work of the other: +34 % (double), +49 % (float) at k = 3, profiles/r02l_k3_two_blocks.txt)
-#ifndef TMA_MINB
-#define TMA_MINB(k) ((k) <= 3 ? 2 : 1)
-#endif
   // ---- Laplace, uniform Cartesian geometry --------------------------------------------------------------------------------------
   template <int k, typename T, int NOPS>
-  __global__ void __launch_bounds__(TmaGeom<k, T>::NT, TMA_MINB(k))
+  __global__ void __launch_bounds__((TmaGeom<k, T, TmaItem<k>::BZ>::NT), TMA_MINB(k))
   laplace_tma_kernel(const T *__restrict__ src,
                      T *__restrict__ dst,
                      T *__restrict__ acc,
@@ -665,9 +728,10 @@ namespace dasm
                      const TmaList     list,
                      const FastMaps    dbgmaps)
   {
-    using G           = TmaGeom<k, T>;
-    using SM          = TmaSmem<k, T>;
-    constexpr int n   = k + 1;
+    constexpr int BZ = TmaItem<k>::BZ;
+    using G          = TmaGeom<k, T, BZ>;
+    using SM         = TmaSmem<k, T, BZ>;
+    constexpr int n  = k + 1;
     extern __shared__ __align__(16) unsigned char smem_dyn[];
     // the tile and the operand boxes are written by the TMA engine with the 128-byte swizzle pattern: 1024-byte alignment
     unsigned char *smem_raw = smem_dyn + ((1024u - ((unsigned)__cvta_generic_to_shared(smem_dyn) & 1023u)) & 1023u);
@@ -689,41 +753,43 @@ namespace dasm
       }
     __syncthreads();
 
-    const int       tid = threadIdx.x;
-    const int       c = tid % G::NCELLS, t = tid / G::NCELLS;
-    const int       cx = c & 3, cy = (c >> 2) & 3, cz = c >> 4;
-    const bool      skip_last = ((t == k) && (cz < 2)) || (dbgmaps.dbg & 1); // whole warp: its plane z = k belongs to the cell above
-    const PlaneAddr pa = tile_plane_y<k, T>(cx, cy, cz, t);
-    T *             xq = Xq + c * G::CS, *xp = Xp + c * G::CS;
+    const int        tid = threadIdx.x;
+    const int        c = tid % G::NCELLS, t = tid / G::NCELLS;
+    const int        cx = c & 3, cy = (c >> 2) & 3, cz = c >> 4;
+    // BZ = 4: the warp (t = k, layers 0 / 1) has nothing to do in the last phase (its planes belong to the cells above)
+    const bool       skip_last = (BZ == 4 && (t == k) && (cz < 2)) || (dbgmaps.dbg & 1);
+    const PlaneAddr  pa = tile_plane_y<k, T, BZ>(cy, cz, t);
+    T *              xq = Xq + c * G::CS, *xp = Xp + c * G::CS;
     const EpiCoef<T> ec     = epi_coef(epi);
     constexpr bool   need0  = NOPS >= 1;
     const bool       direct = (shared_mode == SHARED_DIRECT);
     const uint32_t * dw     = reinterpret_cast<const uint32_t *>(list.bricks);
-    unsigned        tphase = 0, ophase = 0;
-    int             par = 0; // s_desc[par]: this brick, s_desc[par ^ 1]: the next one
-    TmaWalk         w;
-    walk_init(w, list);
-    tma_prologue<k, T>(s_desc, tile, tmaps, list, w.idx, src, mb_tile, tid);
-    for (;; par ^= 1)
+    unsigned         tphase = 0, ophase = 0;
+    TmaCursor        cur;
+    cur.hz  = 0;
+    cur.par = 0; // s_desc[par]: this brick, s_desc[par ^ 1]: the next one
+    walk_init(cur.w, list);
+    tma_prologue<k, T, BZ>(s_desc, tile, tmaps, list, cur.w.idx, src, mb_tile, tid);
+    for (;;)
       {
-        const uint32_t *desc     = s_desc + par * 16;
-        const bool      last     = (desc[1] & TMA_LAST) != 0u;
-        const uint32_t  nidx     = walk_peek(w, last);
-        const bool      has_next = nidx != TMA_NONE;
-        mbar_wait(mb_tile, tphase); // the tensor copies of this brick's tile have landed
+        const uint32_t *desc      = s_desc + cur.par * 16;
+        const bool      last      = (desc[1] & TMA_LAST) != 0u;
+        const bool      last_slab = (cur.hz == G::NH - 1);
+        const uint32_t  nidx      = walk_peek(cur.w, last);
+        const bool      has_next  = !last_slab || nidx != TMA_NONE;
+        mbar_wait(mb_tile, tphase); // the tensor copies of this item's tile have landed
         tphase ^= 1u;
         if (list.any_mode1)
           cp_async_wait_all();
-        // foreign points gathered by the other threads (mode 1); all phase B reads of the exchange slots of the previous brick are
-        // done before phase A overwrites them
+        // foreign points gathered by the other threads (mode 1); all phase B reads of the exchange slots of the previous item are
+        // done before phase A overwrites them; all threads have left the epilogue of the previous item
         bar_sync(FB_COMPUTE, G::NCT);
-        // all threads have left the epilogue of the previous brick: its operand box may be overwritten
         if (need0 && tid == 0)
-          tma_issue_ops<k, T>(ops0, ops0, &omap0, &omap0, false, desc[0], mb_ops);
+          tma_issue_ops<k, T, BZ>(ops0, ops0, &omap0, &omap0, false, desc[0], cur.hz, mb_ops);
         // descriptor of the next brick -> shared memory (fire and forget, awaited before the barrier after phase A; its buffer held
         // the descriptor of the previous brick)
-        if (has_next && tid < TMA_DW)
-          cp_async_4(s_desc + (par ^ 1) * 16 + tid, dw + (size_t)nidx * TMA_DW + tid);
+        if (cur.hz == 0 && nidx != TMA_NONE && tid < TMA_DW)
+          cp_async_4(s_desc + (cur.par ^ 1) * 16 + tid, dw + (size_t)nidx * TMA_DW + tid);
         // phase A: plane y = t, [z][x]: q = Mx Mz v, p = (g0 Kx Mz + g2 Mx Kz) v
         if (!(dbgmaps.dbg & 1))
           {
@@ -757,11 +823,16 @@ namespace dasm
                   }
               }
           }
-        if (has_next && tid < TMA_DW)
+        if (cur.hz == 0 && nidx != TMA_NONE && tid < TMA_DW)
           cp_async_wait_all();
         bar_sync(FB_COMPUTE, G::NCT);
         if (has_next)
-          tma_fetch_next<k, T>(s_desc + (par ^ 1) * 16, tile, tmaps, list, src, mb_tile, tid);
+          {
+            if (last_slab)
+              tma_fetch_next<k, T, BZ>(s_desc + (cur.par ^ 1) * 16, 0, tile, tmaps, list, src, mb_tile, tid);
+            else
+              tma_fetch_next<k, T, BZ>(desc, cur.hz + 1, tile, tmaps, list, src, mb_tile, tid);
+          }
         // phase B: plane z = t, [y][x]: r = My p + g1 Ky q  (+ plane z = k of the cell below for t = 0)
         T r[n][n];
         if (!skip_last)
@@ -798,18 +869,29 @@ namespace dasm
         if (need0)
           mbar_wait(mb_ops, ophase); // the operand box has landed
         ophase ^= 1u;
-        if (!skip_last && (t < k || cz == 3) && !(dbgmaps.dbg & 2))
-          tma_epilogue<k, T, NOPS>(r, ops0, ops0, carry + par * SM::CARRY, carry + (par ^ 1) * SM::CARRY, dst, direct ? dst : acc, direct, ni.out, ec, desc,
-                             list.foreign, cx, cy, cz, t);
+        if (!skip_last && (t < k || cz == BZ - 1) && !(dbgmaps.dbg & 2))
+          {
+            const TmaCarry<T> cr = {carry + (cur.hz * 2 + cur.par) * SM::CARRYX, carry + (cur.hz * 2 + (cur.par ^ 1)) * SM::CARRYX,
+                                    carry + 2 * G::NH * SM::CARRYX};
+            tma_epilogue<k, T, BZ, NOPS>(r, ops0, ops0, cr, dst, direct ? dst : acc, direct, ni.out, ec, desc, list.foreign, cur.hz, cx, cy, cz,
+                                         t);
+          }
         if (!has_next)
           break;
-        walk_advance(w, last, list);
+        if (last_slab)
+          {
+            walk_advance(cur.w, last, list);
+            cur.hz = 0;
+            cur.par ^= 1;
+          }
+        else
+          ++cur.hz;
       }
   }
 
   // ---- FDM, one eigen-decomposition triple, tensor-product weights folded into the matrices ----------------------------------
   template <int k, typename T, int NOPS>
-  __global__ void __launch_bounds__(TmaGeom<k, T>::NT, TMA_MINB(k))
+  __global__ void __launch_bounds__((TmaGeom<k, T, TmaItem<k>::BZ>::NT), TMA_MINB(k))
   fdm_tma_kernel(const T *__restrict__ src,
                  T *__restrict__ dst,
                  T *__restrict__ acc,
@@ -823,9 +905,10 @@ namespace dasm
                  const TmaList     list,
                  const FastMaps    dbgmaps)
   {
-    using G           = TmaGeom<k, T>;
-    using SM          = TmaSmem<k, T>;
-    constexpr int n   = k + 1;
+    constexpr int BZ = TmaItem<k>::BZ;
+    using G          = TmaGeom<k, T, BZ>;
+    using SM         = TmaSmem<k, T, BZ>;
+    constexpr int n  = k + 1;
     extern __shared__ __align__(16) unsigned char smem_dyn[];
     unsigned char *smem_raw = smem_dyn + ((1024u - ((unsigned)__cvta_generic_to_shared(smem_dyn) & 1023u)) & 1023u);
     const unsigned mb_tile = (unsigned)__cvta_generic_to_shared(smem_raw);
@@ -848,39 +931,41 @@ namespace dasm
       }
     __syncthreads();
 
-    const int       tid = threadIdx.x;
-    const int       c = tid % G::NCELLS, t = tid / G::NCELLS;
-    const int       cx = c & 3, cy = (c >> 2) & 3, cz = c >> 4;
-    const bool      skip_last = ((t == k) && (cz < 2)) || (dbgmaps.dbg & 1);
-    const PlaneAddr pa = tile_plane_z<k, T>(cx, cy, cz, t);
-    T *             xs = X + c * G::CS;
-    const T *       inv = s_inv + t * n; // row (z, y = t) of this thread's plane in phase B: broadcast reads
+    const int        tid = threadIdx.x;
+    const int        c = tid % G::NCELLS, t = tid / G::NCELLS;
+    const int        cx = c & 3, cy = (c >> 2) & 3, cz = c >> 4;
+    const bool       skip_last = (BZ == 4 && (t == k) && (cz < 2)) || (dbgmaps.dbg & 1);
+    const PlaneAddr  pa = tile_plane_z<k, T, BZ>(cy, cz, t);
+    T *              xs = X + c * G::CS;
+    const T *        inv = s_inv + t * n; // row (z, y = t) of this thread's plane in phase B: broadcast reads
     const EpiCoef<T> ec     = epi_coef(epi);
     constexpr bool   need0 = NOPS >= 1, need1 = NOPS == 2;
     const bool       direct = (shared_mode == SHARED_DIRECT);
     const uint32_t * dw     = reinterpret_cast<const uint32_t *>(list.bricks);
-    unsigned        tphase = 0, ophase = 0;
-    int             par = 0;
-    TmaWalk         w;
-    walk_init(w, list);
-    tma_prologue<k, T>(s_desc, tile, tmaps, list, w.idx, src, mb_tile, tid);
-    for (;; par ^= 1)
+    unsigned         tphase = 0, ophase = 0;
+    TmaCursor        cur;
+    cur.hz  = 0;
+    cur.par = 0;
+    walk_init(cur.w, list);
+    tma_prologue<k, T, BZ>(s_desc, tile, tmaps, list, cur.w.idx, src, mb_tile, tid);
+    for (;;)
       {
-        const uint32_t *desc     = s_desc + par * 16;
-        const bool      last     = (desc[1] & TMA_LAST) != 0u;
-        const uint32_t  nidx     = walk_peek(w, last);
-        const bool      has_next = nidx != TMA_NONE;
+        const uint32_t *desc      = s_desc + cur.par * 16;
+        const bool      last      = (desc[1] & TMA_LAST) != 0u;
+        const bool      last_slab = (cur.hz == G::NH - 1);
+        const uint32_t  nidx      = walk_peek(cur.w, last);
+        const bool      has_next  = !last_slab || nidx != TMA_NONE;
         mbar_wait(mb_tile, tphase);
         tphase ^= 1u;
         if (list.any_mode1)
           cp_async_wait_all();
-        // foreign points gathered by the other threads (mode 1); all phase C reads of the exchange slot of the previous brick are
-        // done before phase A overwrites it
+        // foreign points gathered by the other threads (mode 1); all phase C reads of the exchange slot of the previous item are
+        // done before phase A overwrites it; all threads have left the epilogue of the previous item
         bar_sync(FB_COMPUTE, G::NCT);
         if (need0 && tid == 0)
-          tma_issue_ops<k, T>(ops0, ops1, &omap0, &omap1, need1, desc[0], mb_ops);
-        if (has_next && tid < TMA_DW)
-          cp_async_4(s_desc + (par ^ 1) * 16 + tid, dw + (size_t)nidx * TMA_DW + tid);
+          tma_issue_ops<k, T, BZ>(ops0, ops1, &omap0, &omap1, need1, desc[0], cur.hz, mb_ops);
+        if (cur.hz == 0 && nidx != TMA_NONE && tid < TMA_DW)
+          cp_async_4(s_desc + (cur.par ^ 1) * 16 + tid, dw + (size_t)nidx * TMA_DW + tid);
         // phase A: plane z = t, [y][x]: Ax in x, Ay in y
         if (!(dbgmaps.dbg & 1))
           {
@@ -905,11 +990,16 @@ namespace dasm
                   xs[(t * n + y) * n + x] = q[y];
               }
           }
-        if (has_next && tid < TMA_DW)
+        if (cur.hz == 0 && nidx != TMA_NONE && tid < TMA_DW)
           cp_async_wait_all();
         bar_sync(FB_COMPUTE, G::NCT);
         if (has_next)
-          tma_fetch_next<k, T>(s_desc + (par ^ 1) * 16, tile, tmaps, list, src, mb_tile, tid);
+          {
+            if (last_slab)
+              tma_fetch_next<k, T, BZ>(s_desc + (cur.par ^ 1) * 16, 0, tile, tmaps, list, src, mb_tile, tid);
+            else
+              tma_fetch_next<k, T, BZ>(desc, cur.hz + 1, tile, tmaps, list, src, mb_tile, tid);
+          }
         // phase B: plane y = t, [z][x]: Az, scale, Bz in z; Bx in x
         if (!(dbgmaps.dbg & 1))
           {
@@ -969,12 +1059,23 @@ namespace dasm
         if (need0)
           mbar_wait(mb_ops, ophase);
         ophase ^= 1u;
-        if (!skip_last && (t < k || cz == 3) && !(dbgmaps.dbg & 2))
-          tma_epilogue<k, T, NOPS>(r, ops0, ops1, carry + par * SM::CARRY, carry + (par ^ 1) * SM::CARRY, dst, direct ? dst : acc, direct, ni.out, ec, desc,
-                             list.foreign, cx, cy, cz, t);
+        if (!skip_last && (t < k || cz == BZ - 1) && !(dbgmaps.dbg & 2))
+          {
+            const TmaCarry<T> cr = {carry + (cur.hz * 2 + cur.par) * SM::CARRYX, carry + (cur.hz * 2 + (cur.par ^ 1)) * SM::CARRYX,
+                                    carry + 2 * G::NH * SM::CARRYX};
+            tma_epilogue<k, T, BZ, NOPS>(r, ops0, ops1, cr, dst, direct ? dst : acc, direct, ni.out, ec, desc, list.foreign, cur.hz, cx, cy, cz,
+                                         t);
+          }
         if (!has_next)
           break;
-        walk_advance(w, last, list);
+        if (last_slab)
+          {
+            walk_advance(cur.w, last, list);
+            cur.hz = 0;
+            cur.par ^= 1;
+          }
+        else
+          ++cur.hz;
       }
   }
 } // namespace dasm

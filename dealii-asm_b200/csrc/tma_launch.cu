@@ -1,5 +1,7 @@
 // Launchers and tensor-map encoding of the TMA-fed kernels (kernels_tma.cuh); separate translation unit of libdasm.so.
 #include <cstdio>
+#include <cstdlib>
+#include <map>
 #include <stdexcept>
 #include <string>
 
@@ -37,6 +39,22 @@ namespace dasm
         E.Q[i] = (T)Q[i];
     }
 
+    // DASM_VERBOSE: resident blocks per SM of a kernel (once per kernel)
+    void
+    report_occupancy(const char *name, const void *kern, const int threads, const size_t smem)
+    {
+      static const bool verbose = getenv("DASM_VERBOSE") != nullptr;
+      if (!verbose)
+        return;
+      static std::map<const void *, int> seen;
+      if (seen.count(kern))
+        return;
+      int occ = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem);
+      seen[kern] = occ;
+      fprintf(stderr, "[dasm] %s: %d threads, %zu bytes of shared memory, %d resident blocks per SM\n", name, threads, smem, occ);
+    }
+
     void
     check(cudaError_t e, const char *what)
     {
@@ -60,6 +78,7 @@ namespace dasm
         return false;
       }
     const cuuint64_t R = 4 * k, XW = 16 / esize;
+    const cuuint32_t RZ = (cuuint32_t)((k <= 3 ? 4 : 2) * k); // z extent of a work item (kernels_tma.cuh TmaItem)
     const cuuint64_t dims[4]    = {R, R, R, (cuuint64_t)n_lex};
     const cuuint64_t strides[3] = {R * esize, R * R * esize, R * R * R * esize};
     const cuuint32_t estr[4]    = {1, 1, 1, 1};
@@ -68,11 +87,11 @@ namespace dasm
     {
       CUtensorMap *m;
       cuuint32_t   box[4];
-    } specs[8] = {{&out.main, {(cuuint32_t)R, (cuuint32_t)R, (cuuint32_t)R, 1}},
-                  {&out.fx, {(cuuint32_t)XW, (cuuint32_t)R, (cuuint32_t)R, 1}},
-                  {&out.fy, {(cuuint32_t)R, 1, (cuuint32_t)R, 1}},
+    } specs[8] = {{&out.main, {(cuuint32_t)R, (cuuint32_t)R, RZ, 1}},
+                  {&out.fx, {(cuuint32_t)XW, (cuuint32_t)R, RZ, 1}},
+                  {&out.fy, {(cuuint32_t)R, 1, RZ, 1}},
                   {&out.fz, {(cuuint32_t)R, (cuuint32_t)R, 1, 1}},
-                  {&out.exy, {(cuuint32_t)XW, 1, (cuuint32_t)R, 1}},
+                  {&out.exy, {(cuuint32_t)XW, 1, RZ, 1}},
                   {&out.exz, {(cuuint32_t)XW, (cuuint32_t)R, 1, 1}},
                   {&out.eyz, {(cuuint32_t)R, 1, 1, 1}},
                   {&out.cxyz, {(cuuint32_t)XW, 1, 1, 1}}};
@@ -82,7 +101,7 @@ namespace dasm
         const cuuint64_t row        = R * esize;
         const cuuint64_t pdims[4]   = {R, 2, 4, (cuuint64_t)(32 * n_lex)};
         const cuuint64_t pstr[3]    = {4 * row, row, 8 * row};
-        const cuuint32_t pbox[4]    = {(cuuint32_t)R, 2, 4, 32};
+        const cuuint32_t pbox[4]    = {(cuuint32_t)R, 2, 4, 2 * RZ};
         const CUresult   r = fn(&out.main, dt, 4, const_cast<void *>(vec), pdims, pstr, pbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                               esize == 8 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -110,7 +129,7 @@ namespace dasm
   size_t
   tma_laplace_smem(int k, int esize)
   {
-#define DASM_TMA_SMEM(K) (esize == 8 ? TmaSmem<K, double>::bytes(2, 1) : TmaSmem<K, float>::bytes(2, 1))
+#define DASM_TMA_SMEM(K) (esize == 8 ? TmaSmem<K, double, TmaItem<K>::BZ>::bytes(2, 1) : TmaSmem<K, float, TmaItem<K>::BZ>::bytes(2, 1))
     switch (k)
       {
         case 2:
@@ -127,7 +146,7 @@ namespace dasm
   size_t
   tma_fdm_smem(int k, int esize)
   {
-#define DASM_TMA_SMEM(K) (esize == 8 ? TmaSmem<K, double>::bytes(1, 2) + 8 * 125 : TmaSmem<K, float>::bytes(1, 2) + 8 * 125)
+#define DASM_TMA_SMEM(K) (esize == 8 ? TmaSmem<K, double, TmaItem<K>::BZ>::bytes(1, 2) + 8 * 125 : TmaSmem<K, float, TmaItem<K>::BZ>::bytes(1, 2) + 8 * 125)
     switch (k)
       {
         case 2:
@@ -146,16 +165,18 @@ namespace dasm
   launch_laplace_tma_k(cudaStream_t stream, int grid, const T *src, T *dst, T *acc, const Epilogue<T> &epi, const double (*P)[25],
                        const double (*Q)[25], const TmaMaps &maps, const CUtensorMap &omap0, int shared_mode, const NextInit<T> &ni, const TmaList &list, int dbg)
   {
-    using G = TmaGeom<K, T>;
+    using G = TmaGeom<K, T, TmaItem<K>::BZ>;
     FastLaplaceMats<T, K + 1> mats;
     eo_fill(mats.M, P[0], Q[0]);
     eo_fill(mats.K0, P[1], Q[1]);
     eo_fill(mats.K1, P[2], Q[2]);
     eo_fill(mats.K2, P[3], Q[3]);
-    constexpr size_t smem  = TmaSmem<K, T>::bytes(2, 1);
+    constexpr size_t smem  = TmaSmem<K, T, TmaItem<K>::BZ>::bytes(2, 1);
     const bool       need0 = (epi.kind == EPI_RESIDUAL || epi.kind == EPI_CHEB);
     auto             kern  = need0 ? laplace_tma_kernel<K, T, 1> : laplace_tma_kernel<K, T, 0>;
     check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "laplace_tma_kernel attribute");
+    check(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), "carveout");
+    report_occupancy("laplace_tma_kernel", (const void *)kern, G::NT, smem);
     const FastMaps fm = {nullptr, nullptr, nullptr, nullptr, 0, nullptr, dbg};
     kern<<<grid, G::NT, smem, stream>>>(src, dst, acc, epi, mats, maps, omap0, shared_mode, ni, list, fm);
     check(cudaGetLastError(), "laplace_tma_kernel launch");
@@ -167,7 +188,7 @@ namespace dasm
                    const double (*Q)[25], const double *inv, const TmaMaps &maps, const CUtensorMap &omap0, const CUtensorMap &omap1, int shared_mode, const NextInit<T> &ni,
                    const TmaList &list, int dbg)
   {
-    using G         = TmaGeom<K, T>;
+    using G         = TmaGeom<K, T, TmaItem<K>::BZ>;
     constexpr int n = K + 1;
     FastFdmMats<T, n> mats;
     eo_fill(mats.Ax, P[0], Q[0]);
@@ -178,11 +199,13 @@ namespace dasm
     eo_fill(mats.Bz, P[5], Q[5]);
     for (int i = 0; i < n * n * n; ++i)
       mats.inv[i] = (T)inv[i];
-    constexpr size_t smem  = TmaSmem<K, T>::bytes(1, 2);
+    constexpr size_t smem  = TmaSmem<K, T, TmaItem<K>::BZ>::bytes(1, 2);
     const bool       need0 = (epi.kind == EPI_RESIDUAL || epi.kind == EPI_CHEB);
     const bool       need1 = (epi.kind == EPI_CHEB && epi.f1 != T(0) && epi.v1 != nullptr);
     auto             kern  = need1 ? fdm_tma_kernel<K, T, 2> : (need0 ? fdm_tma_kernel<K, T, 1> : fdm_tma_kernel<K, T, 0>);
     check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "fdm_tma_kernel attribute");
+    check(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), "carveout");
+    report_occupancy("fdm_tma_kernel", (const void *)kern, G::NT, smem);
     const FastMaps fm = {nullptr, nullptr, nullptr, nullptr, 0, nullptr, dbg};
     kern<<<grid, G::NT, smem, stream>>>(src, dst, acc, epi, mats, maps, omap0, omap1, shared_mode, ni, list, fm);
     check(cudaGetLastError(), "fdm_tma_kernel launch");
