@@ -1264,3 +1264,110 @@ def thomas_solve(a, b, c, d):
     for i in range(n - 2, -1, -1):
         x[i] = dp[i] - cp[i] * x[i + 1]
     return x
+
+
+# --------------------------------------------------------------------------------------
+# Multigrid: two-level transfer and V-cycle
+#   [deal.II MGTwoLevelTransfer / MGTransferGlobalCoarsening, Multigrid, PreconditionMG as set up by the reference in
+#    include/multigrid.h:260-465 and element_centered_preconditioners_01.cc:540-740]
+# --------------------------------------------------------------------------------------
+def transfer_matrix_1d(k_fine, k_coarse, child=None):
+    """Values of the coarse 1-D Lagrange basis (Gauss-Lobatto nodes, degree k_coarse) at the fine nodes:
+    child = None: same cell, fine degree k_fine (polynomial transfer); child = 0 / 1: the fine cell is the lower / upper half
+    of the coarse cell (geometric 2:1 transfer).  [n_fine, n_coarse]"""
+    xc = gauss_lobatto_points(k_coarse + 1)
+    xf = gauss_lobatto_points(k_fine + 1)
+    if child is not None:
+        xf = 0.5 * (xf + child)
+    P = lagrange(xc, xf)[0]
+    P[np.abs(P) < 1e-15] = 0.0
+    return P
+
+
+class TwoLevelTransfer:
+    """Prolongation = embedding of the coarse finite element space into the fine one, cell by cell, weighted with the
+    inverse valence of the fine DoFs (so that the contributions of all cells sharing a DoF sum to its interpolated value);
+    restriction = its transpose.  Constrained (homogeneous Dirichlet) DoFs are read as zero and not written
+    (MGTwoLevelTransfer::prolongate_and_add / restrict_and_add).
+    Geometric transfer: mesh_f has twice the cells of mesh_c per direction, same degree; polynomial transfer: same mesh."""
+
+    def __init__(self, mesh_f, op_f, mesh_c, op_c):
+        dim = op_f.dim
+        self.dim, self.op_f, self.op_c = dim, op_f, op_c
+        self.geometric = tuple(mesh_f.n_cells) != tuple(mesh_c.n_cells)
+        if self.geometric:
+            assert all(f == 2 * c for f, c in zip(mesh_f.n_cells, mesh_c.n_cells)) and op_f.k == op_c.k
+            self.P1 = [transfer_matrix_1d(op_f.k, op_c.k, a) for a in (0, 1)]
+        else:
+            self.P1 = [transfer_matrix_1d(op_f.k, op_c.k)] * 2
+        # parent cell of every fine cell and the child position per direction
+        self.parent = np.zeros(mesh_f.C, dtype=np.int64)
+        self.child = np.zeros((mesh_f.C, dim), dtype=np.int64)
+        for c in range(mesh_f.C):
+            ijk = mesh_f.cell_ijk(c)
+            if self.geometric:
+                self.parent[c] = mesh_c.cell_lex(tuple(i // 2 for i in ijk))
+                self.child[c] = [i % 2 for i in ijk]
+            else:
+                self.parent[c] = c
+        val = np.zeros(op_f.n_dofs)
+        np.add.at(val, op_f.idx.reshape(-1), (op_f.cell_dofs != int(INVALID)).astype(np.float64).reshape(-1))
+        self.w = 1.0 / np.maximum(val, 1.0)
+
+    def _local(self, c, transpose, u):
+        n_f, n_c = self.op_f.n, self.op_c.n
+        u = u.reshape((n_c if not transpose else n_f,) * self.dim)
+        for d in range(self.dim):
+            P = self.P1[self.child[c, d]]
+            u = _apply_1d(P.T if transpose else P, u[None], u.ndim - d)[0]
+        return u.reshape(-1)
+
+    def prolongate_and_add(self, dst, src):
+        of, oc = self.op_f, self.op_c
+        src = np.asarray(src, dtype=np.float64)
+        add = np.zeros(of.n_dofs)
+        for c in range(of.idx.shape[0]):
+            p = self.parent[c]
+            loc = self._local(c, False, src[oc.idx[p]] * oc.mask[p])
+            np.add.at(add, of.idx[c], loc * self.w[of.idx[c]] * of.mask[c])
+        return (np.asarray(dst, dtype=np.float64) + add).astype(of.dtype)
+
+    def restrict_and_add(self, dst, src):
+        of, oc = self.op_f, self.op_c
+        src = np.asarray(src, dtype=np.float64)
+        add = np.zeros(oc.n_dofs)
+        for c in range(of.idx.shape[0]):
+            p = self.parent[c]
+            loc = self._local(c, True, src[of.idx[c]] * self.w[of.idx[c]] * of.mask[c])
+            np.add.at(add, oc.idx[p], loc * oc.mask[p])
+        return (np.asarray(dst, dtype=np.float64) + add).astype(oc.dtype)
+
+
+class Multigrid:
+    """V-cycle preconditioner (deal.II Multigrid::level_v_step through PreconditionMG::vmult):
+         level 0:  x_0 = coarse.vmult(d_0)
+         level l:  x_l = S_l.vmult(d_l);  t = d_l - A_l x_l;  d_{l-1} = R t;  recurse;  x_l += P x_{l-1};  x_l = S_l.step(x_l, d_l)
+    ops[l], smoothers[l] (smoothers[0] = coarse-grid solver), transfers[l] between levels l and l - 1 (l >= 1).  The level
+    number type is that of the level operators (float in the reference's matrix-free set-up,
+    element_centered_preconditioners_01.cc:787-792); the outer vectors are double."""
+
+    def __init__(self, ops, smoothers, transfers):
+        self.ops, self.smoothers, self.transfers = ops, smoothers, transfers
+        self.L = len(ops) - 1
+
+    def _level(self, l, d):
+        if l == 0:
+            return self.smoothers[0].vmult(d)
+        op = self.ops[l]
+        x = self.smoothers[l].vmult(d)
+        t = (d - op.vmult(x)).astype(op.dtype)
+        t[op.constrained] = 0
+        dc = self.transfers[l].restrict_and_add(np.zeros(self.ops[l - 1].n_dofs, dtype=self.ops[l - 1].dtype), t)
+        xc = self._level(l - 1, dc)
+        x = self.transfers[l].prolongate_and_add(x, xc)
+        return self.smoothers[l].step(x, d)
+
+    def vmult(self, src):
+        op = self.ops[self.L]
+        d = np.asarray(src).astype(op.dtype)
+        return self._level(self.L, d).astype(np.float64)

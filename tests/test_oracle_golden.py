@@ -201,3 +201,60 @@ def test_gmres_iteration_counts(name, gold_its):
     x, its = o.solve_gmres(A, P, b)
     assert its == gold_its
     assert np.linalg.norm(b - A(x)) <= 1e-2 * np.linalg.norm(b) * (1 + 1e-8)
+
+
+# ---- multigrid V-cycle (include/multigrid.h:260-465, element_centered_preconditioners_01.cc:540-740) -----------------------------
+def build_multigrid_2d(n_overlap, wt, dtype, n_levels=4, k=3):
+    levels = [level_problem(r, k, dtype=dtype) for r in range(n_levels)]
+    ops = [l[4] for l in levels]
+    smoothers = []
+    for (mesh, cd, nd, bnd, op) in levels:
+        P = o.FDMPreconditioner(mesh, k, cd, nd, bnd, n_overlap, wt)
+        ch = o.Chebyshev(op, P, degree=1, ev_algorithm="power iteration", eig_cg_n_iterations=20)
+        ch.estimate_eigenvalues()
+        smoothers.append(ch)
+    transfers = [None] + [o.TwoLevelTransfer(levels[l][0], ops[l], levels[l - 1][0], ops[l - 1]) for l in range(1, n_levels)]
+    return levels, o.Multigrid(ops, smoothers, transfers)
+
+
+@pytest.mark.parametrize("name,n_overlap,wt,gold_its", [
+    ("dummy_mg_chebyshev_fdm_1_post", 1, "post", 3),
+    ("dummy_mg_chebyshev_fdm_1_pre", 1, "pre", 2),
+    ("dummy_mg_chebyshev_fdm_1_symm", 1, "symm", 3),
+    ("dummy_mg_chebyshev_fdm_1_none", 1, "none", 3),
+    ("dummy_mg_chebyshev_fdm_3", 3, "post", 4),
+])
+def test_multigrid_gmres_iteration_counts(name, n_overlap, wt, gold_its):
+    """small/dummy_mg_chebyshev_fdm_*.output: 2-D Q3, h-multigrid over 1 / 4 / 16 / 64 cells, Chebyshev(1) + FDM smoother on every
+    level (coarse grid too), float level operators, double outer GMRES: `n iterations` of the fixtures."""
+    levels, mg = build_multigrid_2d(n_overlap, wt, np.float32)
+    mesh, cd, nd, bnd, _ = levels[-1]
+    op = level_problem(3)[4]
+    b = _constant_rhs(mesh, cd, nd, bnd, 3)
+    A = lambda v: op.vmult(v, copy_constrained=True)
+    x, its = o.solve_gmres(A, mg.vmult, b)
+    assert its == gold_its, name
+    assert np.linalg.norm(b - A(x)) <= 1e-2 * np.linalg.norm(b) * (1 + 1e-6)
+
+
+def test_transfer_is_embedding_and_transpose():
+    """prolongation reproduces a coarse finite element function exactly; restriction is its transpose."""
+    (mc, cdc, ndc, bc, opc), (mf, cdf, ndf, bf, opf) = level_problem(1), level_problem(2)
+    tr = o.TwoLevelTransfer(mf, opf, mc, opc)
+    rng = np.random.default_rng(0)
+    u, v = rng.standard_normal(ndc), rng.standard_normal(ndf)
+    u[bc] = 0
+    v[bf] = 0
+    Pu = tr.prolongate_and_add(np.zeros(ndf), u)
+    Rv = tr.restrict_and_add(np.zeros(ndc), v)
+    assert abs(Pu @ v - u @ Rv) < 1e-12 * np.linalg.norm(Pu) * np.linalg.norm(v)
+    # u as a function: evaluate the coarse interpolant at the fine support points of one fine cell
+    nodes = o.gauss_lobatto_points(4)
+    c_f = mf.cell_lex((1, 2))
+    ref = (np.array([1, 2]) % 2 + np.stack(np.meshgrid(nodes, nodes, indexing="ij")[::-1], axis=-1)) / 2.0  # [y, x, (x, y)]
+    Vx, Vy = o.lagrange(nodes, ref[..., 0].reshape(-1))[0], o.lagrange(nodes, ref[..., 1].reshape(-1))[0]
+    uc = (u[opc.idx[mc.cell_lex((0, 1))]] * opc.mask[mc.cell_lex((0, 1))]).reshape(4, 4)
+    expect = np.einsum("pj,pi,ji->p", Vy, Vx, uc)
+    got = Pu[opf.idx[c_f]]
+    keep = opf.mask[c_f] > 0
+    assert np.allclose(got[keep], expect[keep], atol=1e-12)
