@@ -381,6 +381,84 @@ class PreconditionChebyshev:
             pass
 
 
+class MGTwoLevelTransfer:
+    """Two-level transfer of MGTransferGlobalCoarsening between two operators (geometric 2:1 or polynomial), the transfer
+    operators PreconditionerGMG sets up in include/multigrid.h:338-349."""
+
+    def __init__(self, fine, coarse):
+        self.fine, self.coarse = fine, coarse
+        self.h = ctypes.c_void_p()
+        _check(lib().dasm_transfer_create(fine.h, coarse.h, ctypes.byref(self.h)))
+
+    def prolongate_and_add(self, dst_fine, src_coarse):
+        _check(lib().dasm_transfer_prolongate_and_add(self.h, _ptr(dst_fine), _ptr(src_coarse)))
+
+    def restrict_and_add(self, dst_coarse, src_fine):
+        _check(lib().dasm_transfer_restrict_and_add(self.h, _ptr(dst_coarse), _ptr(src_fine)))
+
+    def __del__(self):
+        try:
+            lib().dasm_transfer_destroy(self.h)
+        except Exception:
+            pass
+
+
+class PreconditionerGMG:
+    """include/multigrid.h:109-537: V-cycle over level operators (coarsest first) with one smoother per level
+    (smoothers[0] = coarse-grid solver).  vmult takes vectors of the OUTER number type (that of `outer_op`, double in the
+    reference) and converts to the level number type and back."""
+
+    def __init__(self, level_ops, smoothers, outer_op=None, use_one_sided_v_cycle=False):
+        assert len(level_ops) == len(smoothers) and len(level_ops) >= 1
+        self.level_ops, self.smoothers = list(level_ops), list(smoothers)
+        self.outer_ntype = (outer_op or level_ops[-1]).ntype
+        n = len(level_ops)
+        ops = (ctypes.c_void_p * n)(*[o.h for o in level_ops])
+        sms = (ctypes.c_void_p * n)(*[s.h for s in smoothers])
+        self.h = ctypes.c_void_p()
+        _check(lib().dasm_mg_create(n, ops, sms, 1 if use_one_sided_v_cycle else 0, ctypes.byref(self.h)))
+
+    def vmult(self, dst, src):
+        _check(lib().dasm_mg_vmult_outer(self.h, _ptr(dst), _ptr(src), int(self.outer_ntype)))
+
+    def __del__(self):
+        try:
+            lib().dasm_mg_destroy(self.h)
+        except Exception:
+            pass
+
+
+class RestrictedPreconditioner:
+    """Exact-block additive Schwarz (include/preconditioners.h:744-813 over Restrictors::ElementCenteredRestrictor,
+    include/restrictors.h:17-378): the patches and weights of `layout` (an ASPoissonPreconditioner) with the exact inverse of the
+    restricted operator matrix per patch."""
+
+    def __init__(self, layout):
+        self.layout = layout
+        self.op = layout.op
+        self.h = ctypes.c_void_p()
+        _check(lib().dasm_asm_create(layout.h, ctypes.byref(self.h)))
+
+    def vmult(self, dst, src):
+        _check(lib().dasm_asm_vmult(self.h, _ptr(dst), _ptr(src)))
+
+    def memory_consumption(self):
+        lib().dasm_asm_memory_consumption.restype = ctypes.c_longlong
+        return lib().dasm_asm_memory_consumption(self.h)
+
+    def block_inverse(self, cell):
+        m3 = self.layout.patch_size_1d() ** 3
+        out = np.zeros((m3, m3))
+        _check(lib().dasm_asm_block(self.h, ctypes.c_longlong(cell), out.ctypes.data_as(ctypes.c_void_p)))
+        return out
+
+    def __del__(self):
+        try:
+            lib().dasm_asm_destroy(self.h)
+        except Exception:
+            pass
+
+
 def solve(op, x, b, preconditioner=None, params=None):
     """solve() of element_centered_preconditioners_01.cc:108-203 on the device: `params` is the reference's "solver" JSON block
     (type CG | GMRES, max iterations 1000, abs tolerance 1e-10, rel tolerance 1e-2, max n tmp vectors 30);
@@ -399,6 +477,10 @@ def solve(op, x, b, preconditioner=None, params=None):
         kind, h = 2, preconditioner.h
     elif isinstance(preconditioner, PreconditionChebyshev):
         kind, h = 3, preconditioner.h
+    elif isinstance(preconditioner, PreconditionerGMG):
+        kind, h = 4, preconditioner.h
+    elif isinstance(preconditioner, RestrictedPreconditioner):
+        kind, h = 5, preconditioner.h
     else:
         raise DasmError("Preconditioner <%r> is not known!" % (preconditioner,))
     n_it, res = ctypes.c_int(), ctypes.c_double()

@@ -2403,6 +2403,42 @@ extern "C" long long dasm_op_n_global_dofs(const dasm_op *op) { return op->n_glo
 extern "C" int dasm_op_degree(const dasm_op *op) { return op->k; }
 extern "C" int dasm_op_number_type(const dasm_op *op) { return op->ntype; }
 extern "C" int dasm_op_uses_compressed_indices(const dasm_op *op) { return op->compress_indices ? 1 : 0; }
+extern "C" const uint32_t *dasm_op_device_indices(const dasm_op *op) { return op->d_cidx; }
+extern "C" dasm_ctx *dasm_op_ctx(const dasm_op *op) { return op->ctx; }
+extern "C" dasm_mesh *dasm_op_mesh(const dasm_op *op) { return op->mesh; }
+
+extern "C" int
+dasm_mesh_global_size(const dasm_mesh *mesh, int n_cells[3], int periodic[3])
+{
+  DASM_API_BEGIN
+  for (int d = 0; d < 3; ++d)
+    {
+      n_cells[d]  = mesh->mesh->p.nc[d];
+      periodic[d] = mesh->mesh->p.periodic[d];
+    }
+  DASM_API_END
+}
+
+// update_ghost_values / compress(VectorOperation::add) of a vector in the operator's layout (matrix_free_internal.h:321-352)
+extern "C" int
+dasm_op_update_ghost_values(dasm_op *op, void *vec)
+{
+  DASM_API_BEGIN
+  CUDA_CHECK(cudaSetDevice(op->ctx->device));
+  DISPATCH_TYPE(op->ntype, op->exchange.run<T>((T *)vec, false));
+  DASM_API_END
+}
+
+extern "C" int
+dasm_op_compress_add(dasm_op *op, void *vec)
+{
+  DASM_API_BEGIN
+  CUDA_CHECK(cudaSetDevice(op->ctx->device));
+  DISPATCH_TYPE(op->ntype, op->exchange.run<T>((T *)vec, true));
+  if (op->exchange.active() && op->n_ghost > 0)
+    CUDA_CHECK(cudaMemsetAsync((char *)vec + (size_t)op->n_owned * op->esize(), 0, (size_t)op->n_ghost * op->esize(), op->ctx->stream));
+  DASM_API_END
+}
 
 extern "C" int
 dasm_op_vmult(dasm_op *op, void *dst, const void *src)
@@ -3290,6 +3326,73 @@ dasm_fdm_is_symmetric(const dasm_fdm *f)
 }
 extern "C" int dasm_fdm_patch_size_1d(const dasm_fdm *f) { return f->m; }
 
+// entity weights [cell][27] -> per-entry weights [cell][n^3]
+template <int k, typename T>
+__global__ void
+expand_entity_weights_kernel(T *out, const T *cw, const long long n_cells)
+{
+  constexpr int   n = k + 1, n3 = n * n * n;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_cells * n3)
+    return;
+  const long long c = i / n3;
+  const int       l = i % n3;
+  int             ex, ey, ez, o;
+  split_1d<k>(l % n, ex, o);
+  split_1d<k>((l / n) % n, ey, o);
+  split_1d<k>(l / (n * n), ez, o);
+  out[i] = cw[c * 27 + ex + 3 * ey + 9 * ez];
+}
+
+template <typename T>
+__global__ void
+fill_kernel(T *out, const T v, const long long n)
+{
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    out[i] = v;
+}
+
+// Patch layout of the preconditioner for callers that replace the FDM block inverse (block_asm.cu): explicit DoF indices
+// d_idx[cell][m^3] (0xFFFFFFFF: outside the domain / constrained) and the weight d_w[cell][m^3] every entry is multiplied with
+// (before and / or after the block solve: *w_pre, *w_post) - the data of Restrictors::ElementCenteredRestrictor
+// (include/restrictors.h:48-338).  Both arrays are device buffers of the caller.
+extern "C" int
+dasm_fdm_export_patches(dasm_fdm *f, uint32_t *d_idx, void *d_w, int *w_pre, int *w_post)
+{
+  DASM_API_BEGIN
+  dasm_op * op  = f->op;
+  dasm_ctx *ctx = op->ctx;
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  const int       m3 = f->m * f->m * f->m;
+  const long long ne = op->n_cells * m3;
+  if (f->d_pidx == nullptr)
+    {
+      DISPATCH_DEGREE(op->k, expand_compressed_kernel<K><<<nblocks(ne), 256, 0, ctx->stream>>>(d_idx, op->d_cidx, op->n_cells));
+    }
+  else
+    CUDA_CHECK(cudaMemcpyAsync(d_idx, f->d_pidx, (size_t)ne * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+  ctx->launches++;
+  *w_pre  = f->w_pre ? 1 : 0;
+  *w_post = f->w_post ? 1 : 0;
+  DISPATCH_TYPE(op->ntype, {
+    T *w = (T *)d_w;
+    if (f->wmode == 0)
+      fill_kernel<T><<<nblocks(ne), 256, 0, ctx->stream>>>(w, T(1), ne);
+    else if (f->wmode == 1)
+      {
+        DISPATCH_DEGREE(op->k, (expand_entity_weights_kernel<K, T><<<nblocks(ne), 256, 0, ctx->stream>>>(w, (const T *)f->d_cw, op->n_cells)));
+      }
+    else if (f->wmode == 2)
+      CUDA_CHECK(cudaMemcpyAsync(w, f->d_cw, (size_t)ne * sizeof(T), cudaMemcpyDeviceToDevice, ctx->stream));
+    else
+      gather_entity_weights_kernel<T><<<nblocks(ne), 256, 0, ctx->stream>>>(w, (const T *)f->d_wvec, d_idx, ne);
+    ctx->launches++;
+  });
+  DASM_API_END
+}
+extern "C" dasm_op *dasm_fdm_op(const dasm_fdm *f) { return f->op; }
+
 extern "C" int
 dasm_fdm_weights(const dasm_fdm *f, double *out)
 {
@@ -3605,6 +3708,9 @@ dasm_cheb_create(dasm_op *op, dasm_fdm *fdm, int degree, double smoothing_range,
   DASM_API_END
 }
 
+extern "C" dasm_op *dasm_cheb_op(const dasm_cheb *c) { return c->op; }
+extern "C" void dasm_set_last_error(const char *msg) { g_last_error = msg; }
+
 extern "C" int
 dasm_cheb_destroy(dasm_cheb *c)
 {
@@ -3857,6 +3963,14 @@ krylov_precon(dasm_op *op, const int kind, void *handle, const T *inv_diag, T *z
       case DASM_PRECON_CHEBYSHEV:
         cheb_run<T>((dasm_cheb *)handle, z, r, false);
         break;
+      case DASM_PRECON_MULTIGRID:
+        if (dasm_mg_vmult_outer((dasm_mg *)handle, z, r, op->ntype) != 0)
+          throw std::runtime_error(dasm_last_error());
+        break;
+      case DASM_PRECON_BLOCK_ASM:
+        if (dasm_asm_vmult((dasm_asm *)handle, z, r) != 0)
+          throw std::runtime_error(dasm_last_error());
+        break;
       default:
         throw std::runtime_error("Preconditioner kind is not known!");
     }
@@ -4014,7 +4128,8 @@ dasm_solve(dasm_op *op, int solver, int precon_kind, void *precon, void *x, cons
 {
   DASM_API_BEGIN
   DASM_REQUIRE(solver == DASM_SOLVER_CG || solver == DASM_SOLVER_GMRES, "Solver is not known!");
-  DASM_REQUIRE((precon_kind == DASM_PRECON_FDM || precon_kind == DASM_PRECON_CHEBYSHEV) == (precon != nullptr),
+  DASM_REQUIRE((precon_kind == DASM_PRECON_FDM || precon_kind == DASM_PRECON_CHEBYSHEV || precon_kind == DASM_PRECON_MULTIGRID ||
+                precon_kind == DASM_PRECON_BLOCK_ASM) == (precon != nullptr),
                "preconditioner handle does not match its kind");
   CUDA_CHECK(cudaSetDevice(op->ctx->device));
   DISPATCH_TYPE(op->ntype, krylov_solve<T>(op, solver, precon_kind, precon, (T *)x, (const T *)b, max_it, abs_tol, rel_tol, restart, n_it,

@@ -227,10 +227,69 @@ extern "C"
     DASM_PRECON_IDENTITY  = 0,
     DASM_PRECON_DIAGONAL  = 1,
     DASM_PRECON_FDM       = 2,
-    DASM_PRECON_CHEBYSHEV = 3
+    DASM_PRECON_CHEBYSHEV = 3,
+    DASM_PRECON_MULTIGRID = 4, /* dasm_mg*  */
+    DASM_PRECON_BLOCK_ASM = 5  /* dasm_asm* */
   };
   int dasm_solve(dasm_op *op, int solver, int precon_kind, void *precon, void *x, const void *b, int max_it, double abs_tol,
                  double rel_tol, int restart, int *n_it, double *residual);
+
+
+  /* ---- layout accessors used by the components built on top of the operator (mg.cu, block_asm.cu) -------------------------- */
+  dasm_ctx * dasm_op_ctx(const dasm_op *op);
+  dasm_mesh *dasm_op_mesh(const dasm_op *op);
+  dasm_op *  dasm_fdm_op(const dasm_fdm *fdm);
+  dasm_op *  dasm_cheb_op(const dasm_cheb *cheb);
+  /* DEVICE pointer to the 27 compressed start indices per local cell (constrained entities 0xFFFFFFFF; bit 31 = the entity lies in a
+   * lexicographic brick box and expands with the strides 1, 4k, 16k^2) */
+  const uint32_t *dasm_op_device_indices(const dasm_op *op);
+  /* cells per direction of the whole mesh and the periodicity flags */
+  int dasm_mesh_global_size(const dasm_mesh *mesh, int n_cells[3], int periodic[3]);
+  /* update_ghost_values() / compress(VectorOperation::add) of a device vector in the operator's layout
+   * (VectorDataExchange, include/matrix_free_internal.h:3-109, 321-352); compress zeroes the ghost part afterwards */
+  int dasm_op_update_ghost_values(dasm_op *op, void *vec);
+  int dasm_op_compress_add(dasm_op *op, void *vec);
+  /* patch layout of a preconditioner: DoF indices d_idx[n_cells * m^3] (0xFFFFFFFF = not part of the patch) and per-entry weights
+   * d_w[n_cells * m^3] (number type of the operator), both DEVICE buffers of the caller; *w_pre / *w_post: the weights are applied
+   * before / after the block solve.  This is the data of Restrictors::ElementCenteredRestrictor (include/restrictors.h:48-338). */
+  int  dasm_fdm_export_patches(dasm_fdm *fdm, uint32_t *d_idx, void *d_w, int *w_pre, int *w_post);
+  void dasm_set_last_error(const char *msg);
+
+  /* ---- Geometric / polynomial multigrid V-cycle (include/multigrid.h:109-537: PreconditionerGMG; deal.II Multigrid +
+   *      MGTransferGlobalCoarsening + PreconditionMG as set up in element_centered_preconditioners_01.cc:540-740) ------------------
+   * Two-level transfer between two operators on the same context: geometric (the fine mesh has twice the cells of the coarse mesh in
+   * every direction, same degree: "mg type" h) or polynomial (same mesh, lower degree: "mg type" p).  Prolongation = embedding,
+   * restriction = its transpose; constrained DoFs are read as zero and not written (MGTwoLevelTransfer). */
+  typedef struct dasm_transfer dasm_transfer;
+  int dasm_transfer_create(dasm_op *fine, dasm_op *coarse, dasm_transfer **out);
+  int dasm_transfer_destroy(dasm_transfer *t);
+  int dasm_transfer_prolongate_and_add(dasm_transfer *t, void *dst_fine, const void *src_coarse);
+  int dasm_transfer_restrict_and_add(dasm_transfer *t, void *dst_coarse, const void *src_fine);
+  /* levels[0] = coarsest.  smoothers[l] (l >= 1): pre- and post-smoother of level l (MGSmootherRelaxation with one step: vmult
+   * before and step after the coarse-grid correction); smoothers[0]: coarse-grid solver (MGCoarseGridApplyPreconditioner,
+   * include/multigrid.h:96-108).  All level operators share one number type (float in the reference's matrix-free set-up,
+   * element_centered_preconditioners_01.cc:787-792).  one_sided_v_cycle: no post-smoothing (include/multigrid.h:303-312). */
+  typedef struct dasm_mg dasm_mg;
+  int dasm_mg_create(int n_levels, dasm_op **level_ops, dasm_cheb **smoothers, int one_sided_v_cycle, dasm_mg **out);
+  int dasm_mg_destroy(dasm_mg *mg);
+  /* PreconditionerGMG::vmult (include/multigrid.h:463-469): dst = V-cycle(src); dst / src are device vectors of the finest level's
+   * layout in the number type `outer_number_type` (converted to the level number type and back, PreconditionMG copy_to_mg /
+   * copy_from_mg) */
+  int dasm_mg_vmult_outer(dasm_mg *mg, void *dst, const void *src, int outer_number_type);
+  int dasm_mg_vmult(dasm_mg *mg, void *dst, const void *src); /* vectors of the level number type */
+
+  /* ---- Exact-block additive Schwarz (RestrictedPreconditioner over ElementCenteredRestrictor with RestrictedMatrixView blocks
+   *      inverted by gauss_jordan: include/preconditioners.h:528-605, 744-813; include/restrictors.h:17-378) ---------------------
+   * The patches (indices, weights, weighting type) are those of `layout`; the block of a patch is the restriction of the operator's
+   * matrix to the patch DoFs, obtained by applying the operator to coloured unit vectors, and inverted on the device. */
+  typedef struct dasm_asm dasm_asm;
+  int       dasm_asm_create(dasm_fdm *layout, dasm_asm **out);
+  int       dasm_asm_destroy(dasm_asm *a);
+  int       dasm_asm_vmult(dasm_asm *a, void *dst, const void *src);
+  long long dasm_asm_memory_consumption(const dasm_asm *a);
+  /* inverse block of one local cell, out[m^3 * m^3] host doubles, row-major (rows / columns of entries outside the patch are those
+   * of the identity) */
+  int dasm_asm_block(const dasm_asm *a, long long cell, double *out);
 
 #ifdef __cplusplus
 }

@@ -1371,3 +1371,27 @@ class Multigrid:
         op = self.ops[self.L]
         d = np.asarray(src).astype(op.dtype)
         return self._level(self.L, d).astype(np.float64)
+
+
+# --------------------------------------------------------------------------------------
+# Exact-block additive Schwarz  (include/preconditioners.h:528-605 RestrictedMatrixView, 744-813 RestrictedPreconditioner;
+# include/restrictors.h:48-338 ElementCenteredRestrictor)
+# --------------------------------------------------------------------------------------
+class ExactBlockASM(FDMPreconditioner):
+    """Same patches and weights as the FDM preconditioner, but the block of a patch is the inverse of the restriction
+    R_c A R_c^T of the assembled operator matrix (gauss_jordan in the reference) instead of the fast-diagonalisation
+    approximation.  `A` : dense matrix of the operator (LaplaceOperator.dense())."""
+
+    def __init__(self, A, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.block_inv = []
+        for c in range(self.idx.shape[0]):
+            sel = self.mask[c] > 0
+            ii = self.idx[c][sel]
+            B = np.eye(self.idx.shape[1])
+            if ii.size:
+                B[np.ix_(sel, sel)] = np.linalg.inv(A[np.ix_(ii, ii)])
+            self.block_inv.append(B.astype(self.dtype))
+
+    def apply_inverse(self, rl):
+        return np.stack([self.block_inv[c] @ rl[c] for c in range(rl.shape[0])])
