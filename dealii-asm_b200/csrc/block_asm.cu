@@ -347,3 +347,34 @@ dasm_asm_block(const dasm_asm *a, long long cell, double *out)
     }
   BA_API_END
 }
+
+// host copy of the patch layout (Restrictors::ElementCenteredRestrictor: indices and weights, include/restrictors.h:48-338)
+extern "C" int
+dasm_fdm_patches_host(dasm_fdm *fdm, uint32_t *idx, double *w, int *w_pre, int *w_post)
+{
+  BA_API_BEGIN
+  dasm_op *       op = dasm_fdm_op(fdm);
+  const int       m  = dasm_fdm_patch_size_1d(fdm);
+  const size_t    n  = (size_t)dasm_mesh_n_cells(dasm_op_mesh(op)) * m * m * m;
+  const bool      f64 = dasm_op_number_type(op) == DASM_F64;
+  cudaStream_t    s   = (cudaStream_t)dasm_ctx_stream(dasm_op_ctx(op));
+  uint32_t *      d_idx = nullptr;
+  void *          d_w   = nullptr;
+  BA_CUDA_CHECK(cudaMalloc(&d_idx, std::max<size_t>(1, n) * sizeof(uint32_t)));
+  BA_CUDA_CHECK(cudaMalloc(&d_w, std::max<size_t>(1, n) * 8));
+  BA_CALL(dasm_fdm_export_patches(fdm, d_idx, d_w, w_pre, w_post));
+  BA_CUDA_CHECK(cudaStreamSynchronize(s));
+  BA_CUDA_CHECK(cudaMemcpy(idx, d_idx, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  if (f64)
+    BA_CUDA_CHECK(cudaMemcpy(w, d_w, n * sizeof(double), cudaMemcpyDeviceToHost));
+  else
+    {
+      std::vector<float> h(n);
+      BA_CUDA_CHECK(cudaMemcpy(h.data(), d_w, n * sizeof(float), cudaMemcpyDeviceToHost));
+      for (size_t i = 0; i < n; ++i)
+        w[i] = h[i];
+    }
+  cudaFree(d_idx);
+  cudaFree(d_w);
+  BA_API_END
+}

@@ -410,11 +410,13 @@ dasm_mg_destroy(dasm_mg *mg)
 {
   if (mg)
     {
+      cudaDeviceSynchronize();
       for (size_t l = 0; l < mg->ops.size(); ++l)
         {
-          dasm_op_vec_free(mg->ops[l], mg->defect[l]);
-          dasm_op_vec_free(mg->ops[l], mg->solution[l]);
-          dasm_op_vec_free(mg->ops[l], mg->t[l]);
+          // (plain frees: the level operators may already have been destroyed by the caller)
+          cudaFree(mg->defect[l]);
+          cudaFree(mg->solution[l]);
+          cudaFree(mg->t[l]);
           dasm_transfer_destroy(mg->transfers[l]);
         }
       delete mg;

@@ -253,6 +253,8 @@ extern "C"
    * d_w[n_cells * m^3] (number type of the operator), both DEVICE buffers of the caller; *w_pre / *w_post: the weights are applied
    * before / after the block solve.  This is the data of Restrictors::ElementCenteredRestrictor (include/restrictors.h:48-338). */
   int  dasm_fdm_export_patches(dasm_fdm *fdm, uint32_t *d_idx, void *d_w, int *w_pre, int *w_post);
+  /* the same on the host: idx[n_cells * m^3], w[n_cells * m^3] (doubles) */
+  int  dasm_fdm_patches_host(dasm_fdm *fdm, uint32_t *idx, double *w, int *w_pre, int *w_post);
   void dasm_set_last_error(const char *msg);
 
   /* ---- Geometric / polynomial multigrid V-cycle (include/multigrid.h:109-537: PreconditionerGMG; deal.II Multigrid +

@@ -115,6 +115,7 @@ namespace dasm
     }
     void vmult(VectorType &dst, const VectorType &src) const override { check(dasm_cheb_vmult(h, dst.data(), src.data())); }
     void step(VectorType &dst, const VectorType &src) const override { check(dasm_cheb_step(h, dst.data(), src.data())); }
+    dasm_cheb *handle() const { return h; }
 
   private:
     dasm_cheb *h = nullptr;
