@@ -57,7 +57,12 @@ def main():
         ctx.sync()
         t_setup = time.perf_counter() - t0
         params = {"type": solver, "rel tolerance": 1e-8, "abs tolerance": 1e-20, "max iterations": 300}  # experiments: reduction 1e-8
-        its, res = pkg.solve(op, x, b, mg, params)  # warm-up (the reference also solves twice, :221-236)
+        try:
+            its, res = pkg.solve(op, x, b, mg, params)  # warm-up (the reference also solves twice, :221-236)
+        except pkg.DasmError as e:
+            results.append(dict(solver=solver, weighting=wt, smoother="Chebyshev(%d) + FDM n=1" % cheb_degree, failed=str(e)))
+            json.dump(results, open(out, "w"), indent=1)
+            continue
         ctx.sync()
         t1 = time.perf_counter()
         its, res = pkg.solve(op, x, b, mg, params)
@@ -75,6 +80,7 @@ def main():
                    dofs_per_s_per_iteration=n * its / dt)
         print(row, flush=True)
         results.append(row)
+        json.dump(results, open(out, "w"), indent=1)
         del mg, smoothers, levels, op
         torch.cuda.empty_cache()
     json.dump(results, open(out, "w"), indent=1)
