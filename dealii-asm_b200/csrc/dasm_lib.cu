@@ -422,6 +422,7 @@ struct dasm_op
   std::vector<void *> scratch; // owned by op, freed at destroy
   // tuned brick path
   bool              use_brick = false;
+  bool              tma_only  = false; // degrees 5 and 6: every brick is a lex brick and runs the TMA-fed kernels (no brick kernels)
   int               brick_bz  = 4;
   BrickDesc *       d_bricks  = nullptr;
   int               n_bricks  = 0;
@@ -956,7 +957,7 @@ tma_build_list(const dasm_op *op, const std::vector<uint32_t> &ids, const int n_
 {
   if (const char *e = getenv("DASM_TMA_CHUNK"))
     return tma_build_list_L(op, ids, n_boundary, std::max(1, atoi(e)));
-  const int  blocks = std::max(1, op->n_sm * TMA_MINB(op->k));
+  const int  blocks = std::max(1, op->n_sm * tma_min_blocks(op->k, (int)op->esize()));
   if (getenv("DASM_VERBOSE"))
     fprintf(stderr, "[dasm] chunking %zu lex bricks over %d resident blocks\n", ids.size(), blocks);
   TmaChunked best;
@@ -1008,10 +1009,10 @@ tma_chunk_range(const int first, const int count, const int n_fast, const int n_
 
 // thread blocks per SM of the TMA-fed kernels (kernels_tma.cuh TMA_MINB; DASM_TMA_CTAS overrides for experiments)
 static int
-tma_ctas_per_sm(const int k)
+tma_ctas_per_sm(const int k, const int esize)
 {
   static const int v = getenv("DASM_TMA_CTAS") ? std::max(1, atoi(getenv("DASM_TMA_CTAS"))) : 0;
-  return v > 0 ? v : TMA_MINB(k);
+  return v > 0 ? v : tma_min_blocks(k, esize);
 }
 
 // tensor maps of a vector for the TMA-fed kernels (cached per pointer); nullptr: not usable (alignment)
@@ -1056,7 +1057,7 @@ launch_laplace_fast(dasm_op *op, T *dst, const T *src, const Epilogue<T> &epi, c
     return false;
   if (c_count == 0)
     return true;
-  const int      grid = std::min(c_count, std::max(1, op->n_sm * tma_ctas_per_sm(K) - reserve_sms));
+  const int      grid = std::min(c_count, std::max(1, op->n_sm * tma_ctas_per_sm(K, (int)sizeof(T)) - reserve_sms));
   const TmaList  list = {op->d_tma_lap, op->d_tma_foreign, op->d_tma_lap_chunks + c_first, c_count, op->tma_any_mode1};
   const TmaMaps *o0   = epi.v0 ? tma_maps_for(op, epi.v0) : tm;
   if (o0 == nullptr)
@@ -1151,6 +1152,22 @@ launch_laplace_brick(dasm_op *op, T *dst, const T *src, const Epilogue<T> &epi, 
   CUDA_CHECK(cudaGetLastError());
 }
 
+// degrees 5 and 6 on meshes whose bricks are all lex bricks (one rank, periodic or interior only): the TMA-fed kernel is the only
+// cell kernel; there are no constrained DoFs and no ghost entries
+template <int K, typename T>
+static void
+launch_laplace_tma_only(dasm_op *op, T *dst, const T *src, const Epilogue<T> &epi, const int shared_mode, const NextInit<T> &ni)
+{
+  {
+    KernelTimer timer(op->ctx, KC_LAPLACE);
+    if (!launch_laplace_fast<K, T>(op, dst, src, epi, shared_mode, ni))
+      throw std::runtime_error("laplace_tma_kernel: vectors must be 16-byte aligned device vectors of the operator's layout");
+  }
+  CUDA_CHECK(cudaGetLastError());
+  brick_finish<K, 4, T>(op, dst, (const T *)nullptr, epi, shared_mode);
+  CUDA_CHECK(cudaGetLastError());
+}
+
 template <typename T>
 static NextInit<T>
 no_next_init()
@@ -1181,7 +1198,19 @@ op_vmult_brick(dasm_op *op, T *dst, const T *src, const dasm_hook *post, const i
         else
           launch_laplace_brick<4, 4, T>(op, dst, src, epi, copy, shared_mode, ni);
         break;
-      case 5: launch_laplace_brick<5, 2, T>(op, dst, src, epi, copy, shared_mode, ni); break;
+      case 5:
+        if (op->tma_only)
+          launch_laplace_tma_only<5, T>(op, dst, src, epi, shared_mode, ni);
+        else
+          launch_laplace_brick<5, 2, T>(op, dst, src, epi, copy, shared_mode, ni);
+        break;
+      case 6:
+        if (op->tma_only)
+          {
+            launch_laplace_tma_only<6, T>(op, dst, src, epi, shared_mode, ni);
+            break;
+          }
+        // fall through
       default: throw std::runtime_error("internal: brick path for unsupported degree");
     }
 }
@@ -1206,7 +1235,15 @@ op_vmult(dasm_op *op, T *dst, const T *src, const dasm_hook *pre, const dasm_hoo
   if (pre != nullptr && pre->kind != DASM_HOOK_NONE && pre->kind != DASM_HOOK_ZERO_DST)
     throw std::runtime_error("LaplaceOperatorMatrixFree::vmult: only the zeroing pre-operation is supported");
   DASM_REQUIRE((const void *)dst != (const void *)src, "vmult: dst and src must not alias");
-  if (op->use_brick)
+  bool brick_path = op->use_brick;
+  if (op->tma_only)
+    {
+      // the TMA-fed kernel is the only brick kernel of these degrees: two-operand epilogues and unaligned user vectors go
+      // through the generic kernels
+      const Epilogue<T> epi = epilogue_from_hook<T>(post);
+      brick_path            = epilogue_n_operands(epi) <= 1 && tma_aligned(dst, epi.v0, epi.v1) && tma_aligned(src, nullptr, nullptr);
+    }
+  if (brick_path)
     {
       op_vmult_brick<T>(op, dst, src, post);
       return;
@@ -1299,7 +1336,7 @@ launch_fdm_fast(dasm_fdm *f, T *dst, const T *src, const Epilogue<T> &epi, const
     return false;
   if (c_count == 0)
     return true;
-  const int      grid = std::min(c_count, std::max(1, op->n_sm * tma_ctas_per_sm(K) - reserve_sms));
+  const int      grid = std::min(c_count, std::max(1, op->n_sm * tma_ctas_per_sm(K, (int)sizeof(T)) - reserve_sms));
   const TmaList  list = {f->d_tma_list, op->d_tma_foreign, f->d_tma_chunks + c_first, c_count, f->tma_any_mode1};
   const TmaMaps *o0 = epi.v0 ? tma_maps_for(op, epi.v0) : tm, *o1 = epi.v1 ? tma_maps_for(op, epi.v1) : tm;
   if (o0 == nullptr || o1 == nullptr)
@@ -1383,7 +1420,24 @@ launch_fdm_brick(dasm_fdm *f, T *dst, const T *src, const Epilogue<T> &epi, cons
 static bool
 fdm_uses_brick(const dasm_fdm *f)
 {
+  if (f->op->tma_only) // no brick kernels behind the TMA-fed kernel: every brick must qualify for it
+    return f->d_pidx == nullptr && f->fast_ok && f->n_slow == 0 && f->d_tma_list != nullptr;
   return f->op->use_brick && f->d_pidx == nullptr && (f->wmode == 0 || f->wmode == 1);
+}
+
+template <int K, typename T>
+static void
+launch_fdm_tma_only(dasm_fdm *f, T *dst, const T *src, const Epilogue<T> &epi, const int shared_mode, const NextInit<T> &ni)
+{
+  dasm_op *op = f->op;
+  {
+    KernelTimer timer(op->ctx, KC_FDM);
+    if (!launch_fdm_fast<K, T>(f, dst, src, epi, shared_mode, ni))
+      throw std::runtime_error("fdm_tma_kernel: vectors must be 16-byte aligned device vectors of the operator's layout");
+  }
+  CUDA_CHECK(cudaGetLastError());
+  brick_finish<K, 4, T>(op, dst, (const T *)nullptr, epi, shared_mode);
+  CUDA_CHECK(cudaGetLastError());
 }
 
 template <typename T>
@@ -1404,7 +1458,19 @@ fdm_vmult_brick(dasm_fdm *f, T *dst, const T *src, const dasm_hook *post, const 
         else
           launch_fdm_brick<4, 4, T>(f, dst, src, epi, shared_mode, ni);
         break;
-      case 5: launch_fdm_brick<5, 2, T>(f, dst, src, epi, shared_mode, ni); break;
+      case 5:
+        if (op->tma_only)
+          launch_fdm_tma_only<5, T>(f, dst, src, epi, shared_mode, ni);
+        else
+          launch_fdm_brick<5, 2, T>(f, dst, src, epi, shared_mode, ni);
+        break;
+      case 6:
+        if (op->tma_only)
+          {
+            launch_fdm_tma_only<6, T>(f, dst, src, epi, shared_mode, ni);
+            break;
+          }
+        // fall through
       default: throw std::runtime_error("internal: brick path for unsupported degree");
     }
 }
@@ -1418,7 +1484,13 @@ fdm_vmult(dasm_fdm *f, T *dst, const T *src, const dasm_hook *pre, const dasm_ho
   if (pre != nullptr && pre->kind != DASM_HOOK_NONE && pre->kind != DASM_HOOK_ZERO_DST)
     throw std::runtime_error("ASPoissonPreconditioner::vmult: only the zeroing pre-operation is supported");
   DASM_REQUIRE((const void *)dst != (const void *)src, "vmult: dst and src must not alias");
-  if (fdm_uses_brick(f))
+  bool brick_path = fdm_uses_brick(f);
+  if (brick_path && op->tma_only)
+    {
+      const Epilogue<T> epi = epilogue_from_hook<T>(post);
+      brick_path            = tma_aligned(dst, epi.v0, epi.v1) && tma_aligned(src, nullptr, nullptr);
+    }
+  if (brick_path)
     {
       fdm_vmult_brick<T>(f, dst, src, post);
       return;
@@ -1448,6 +1520,124 @@ fdm_vmult(dasm_fdm *f, T *dst, const T *src, const dasm_hook *pre, const dasm_ho
         }
       ctx->launches++;
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Degrees 5 and 6: TMA-fed kernels only.  Applies when every mesh brick is a lex brick (full 4 x 4 x 4 bricks with neighbour cells
+// across all faces: the periodic meshes of matrix_free_loop_08) on one rank: then there are no constrained DoFs, no ghost entries and
+// no irregular bricks, so the brick kernels (instantiated up to degree 4 / 5) are not needed behind the TMA-fed kernels.
+// ------------------------------------------------------------------------------------------------
+static bool
+setup_tma_only(dasm_op *op)
+{
+  const Mesh &M   = *op->mesh->mesh;
+  dasm_ctx *  ctx = op->ctx;
+  const int   k = op->k, n = k + 1;
+  const size_t n_mesh_bricks = M.brick_ptr.size() - 1;
+  if (M.n_ranks() != 1 || op->geom_mode != 0 || op->n_constrained != 0 || op->n_ghost != 0 || op->nb.n_lex == 0 ||
+      (size_t)op->nb.n_lex != n_mesh_bricks || (size_t)op->n_cells != 64 * n_mesh_bricks)
+    return false;
+  cudaDeviceProp prop;
+  CUDA_CHECK(cudaGetDeviceProperties(&prop, ctx->device));
+  op->n_sm     = prop.multiProcessorCount;
+  op->max_smem = (int)prop.sharedMemPerBlockOptin;
+  if (tma_laplace_smem(k, (int)op->esize()) > (size_t)op->max_smem)
+    return false;
+  // 1-D matrices of the Kronecker form in even-odd form
+  {
+    std::vector<double> A(n * n);
+    bool                eo = eo_pack_centrosymmetric(n, op->basis.M_ref.data(), op->lap_P[0], op->lap_Q[0]);
+    for (int d = 0; d < 3; ++d)
+      {
+        for (int i = 0; i < n * n; ++i)
+          A[i] = op->cart.g[d] * op->basis.K_ref[i];
+        eo = eo_pack_centrosymmetric(n, A.data(), op->lap_P[1 + d], op->lap_Q[1 + d]) && eo;
+      }
+    if (!eo)
+      return false;
+  }
+  const int                 R = 4 * k;
+  std::vector<BrickDesc>    bricks(n_mesh_bricks);
+  std::vector<uint32_t>     shared_list, fast_ids(n_mesh_bricks);
+  std::map<long long, uint32_t> brick_at; // global coordinates of the first cell / 4 -> brick
+  auto key = [&](const int c0, const int c1, const int c2) { return ((long long)(c2 / 4) * (M.p.nc[1] / 4 + 1) + c1 / 4) * (M.p.nc[0] / 4 + 1) + c0 / 4; };
+  for (size_t b = 0; b < n_mesh_bricks; ++b)
+    {
+      const auto &c0 = M.cell_ijk[M.brick_ptr[b]];
+      if (c0[0] % 4 != 0 || c0[1] % 4 != 0 || c0[2] % 4 != 0 || !op->nb.brick_lex[b])
+        return false;
+      brick_at[key(c0[0], c0[1], c0[2])] = (uint32_t)b;
+    }
+  op->h_tma.assign(n_mesh_bricks, TmaBrick());
+  static const int off7[7][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {1, 1, 0}, {1, 0, 1}, {0, 1, 1}, {1, 1, 1}};
+  for (size_t b = 0; b < n_mesh_bricks; ++b)
+    {
+      BrickDesc &bd = bricks[b];
+      bd.first_cell = M.brick_ptr[b];
+      bd.b[0] = bd.b[1] = bd.b[2] = 4;
+      bd.shared   = 0x3F | BRICK_LEX;
+      bd.base     = op->nb.brick_base[b];
+      bd.sh_base  = bd.base;
+      bd.sh_count = 0;
+      bd.npriv    = 0;
+      bd.variant  = 0xFFFFu;
+      if (bd.base % (uint32_t)(64 * k * k * k) != 0)
+        return false;
+      fast_ids[b] = (uint32_t)b;
+      // own DoFs on the lower faces of the box (shared with the lower neighbour bricks)
+      for (int Z = 0; Z < R; ++Z)
+        for (int Y = 0; Y < R; ++Y)
+          for (int X = 0; X < R; ++X)
+            if (X == 0 || Y == 0 || Z == 0)
+              shared_list.push_back(bd.base + (uint32_t)(X + R * (Y + R * Z)));
+      TmaBrick &t  = op->h_tma[b];
+      t.base       = bd.base;
+      t.flags      = 0;
+      t.list_off   = 0;
+      const auto &o = M.cell_ijk[bd.first_cell];
+      for (int q = 0; q < 7; ++q)
+        {
+          int c2[3];
+          for (int d = 0; d < 3; ++d)
+            {
+              c2[d] = o[d] + 4 * off7[q][d];
+              if (c2[d] >= M.p.nc[d])
+                c2[d] -= M.p.nc[d];
+            }
+          const auto it = brick_at.find(key(c2[0], c2[1], c2[2]));
+          if (it == brick_at.end())
+            return false;
+          t.nb[q] = op->nb.brick_base[it->second];
+        }
+    }
+  op->tma_only         = true;
+  op->use_brick        = true;
+  op->brick_bz         = 4;
+  op->n_bricks         = (int)n_mesh_bricks;
+  op->d_bricks         = dev_upload(bricks, ctx->stream);
+  op->h_brick_boundary.assign(n_mesh_bricks, 0);
+  op->n_shared         = (long long)shared_list.size();
+  op->d_shared_list    = dev_upload(shared_list, ctx->stream);
+  op->shared_ranges_ok = true;
+  op->n_fast_boundary  = 0;
+  op->tma_ok           = true; // (tma_build_list reads the block count of the kernels)
+  const TmaChunked ch  = tma_build_list(op, fast_ids, 0);
+  op->fast_ok          = true;
+  op->tma_any_mode1    = ch.any_mode1;
+  op->d_tma_lap        = dev_upload(ch.descs, ctx->stream);
+  op->d_tma_lap_chunks = dev_upload(ch.chunk_start, ctx->stream);
+  op->tma_lap_n_chunks = (int)ch.chunk_start.size() - 1;
+  op->tma_lap_n_chunks_boundary = ch.n_chunks_boundary;
+  std::vector<uint32_t> none(4, 0);
+  op->d_tma_foreign    = dev_upload(none, ctx->stream);
+  op->d_fast_ids       = dev_upload(fast_ids, ctx->stream);
+  op->d_slow_ids       = dev_upload(none, ctx->stream);
+  op->n_fast           = (int)fast_ids.size();
+  op->n_slow           = 0;
+  op->h_fast_ids       = fast_ids;
+  CUDA_CHECK(cudaMalloc(&op->d_acc, std::max<size_t>(1, (size_t)op->n_vec) * op->esize()));
+  CUDA_CHECK(cudaMemset(op->d_acc, 0, std::max<size_t>(1, (size_t)op->n_vec) * op->esize()));
+  return true;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1871,7 +2061,10 @@ dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping
     // DASM_BRICK_K5=1 selects the 4x4x2 brick kernels)
     const char *k5    = getenv("DASM_BRICK_K5");
     op->use_brick     = (degree <= 4 || (degree == 5 && k5 && k5[0] == '1')) && !(force && force[0] == '1');
-    if (op->use_brick)
+    const char *nofast_hi = getenv("DASM_NO_FAST");
+    if (!op->use_brick && (degree == 5 || degree == 6) && !(force && force[0] == '1') && !(nofast_hi && nofast_hi[0] == '1'))
+      setup_tma_only(op);
+    if (op->use_brick && !op->tma_only)
       {
         op->brick_bz = (degree <= 4) ? 4 : 2;
         if (const char *bz = getenv("DASM_BRICK_BZ"))
@@ -3255,6 +3448,8 @@ dasm_fdm_create(dasm_op *op, int n_overlap, int sub_mesh_approximation, int weig
               f->n_slow     = (int)slow_ids.size();
               f->d_fast_ids = dev_upload(fast_ids, op->ctx->stream);
               f->d_slow_ids = dev_upload(slow_ids, op->ctx->stream);
+              if (op->tma_only && f->n_slow > 0)
+                f->fast_ok = false; // (no brick kernel for the remaining bricks: the generic kernel runs all cells)
               if (op->tma_ok)
                 {
                   const TmaChunked ch = tma_build_list(op, fast_ids, f->n_fast_boundary);

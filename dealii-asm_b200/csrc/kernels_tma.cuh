@@ -417,13 +417,14 @@ namespace dasm
 
   // carries of an item (shared memory):
   //   cx_in / cx_out  [RZ + 1][R + 1] values of the plane X = R (Z slow, Y fast) handed to the same slab of the +x brick
-  //   cz              [R + 1][R + 1]  values of the plane Zl = RZ (Y slow, X fast) handed to the next slab of the same brick
+  //   cz_in / cz_out  [R + 1][R + 1]  values of the plane Zl = RZ (Y slow, X fast) handed to the next slab of the same brick
   template <typename T>
   struct TmaCarry
   {
     const T *cx_in;
     T *      cx_out;
-    T *      cz;
+    const T *cz_in;  // written by the slab below (double buffer by slab parity: a middle slab reads one and writes the other)
+    T *      cz_out;
   };
 
   // After the merge every thread (cell, plane z = t) holds the FINAL values of its exclusive points x < k (or x <= k for
@@ -450,7 +451,7 @@ namespace dasm
     // contributions of the slab below to the plane Zl = 0 (all points of the plane, X = R / Y = R included)
     if (zcarry_in)
       {
-        const T *c = cr.cz + Y0 * (R + 1) + X0;
+        const T *c = cr.cz_in + Y0 * (R + 1) + X0;
 #pragma unroll
         for (int y = 0; y <= k; ++y)
 #pragma unroll
@@ -472,7 +473,7 @@ namespace dasm
     // the plane above the item goes to the next slab as a whole
     if (zcarry_out)
       {
-        T *c = cr.cz + Y0 * (R + 1) + X0;
+        T *c = cr.cz_out + Y0 * (R + 1) + X0;
 #pragma unroll
         for (int y = 0; y <= k; ++y)
 #pragma unroll
@@ -655,7 +656,7 @@ namespace dasm
     static constexpr int OPS    = pad1k(G::NBI);
     static constexpr int CARRYX = G::pad((G::RZ + 1) * (G::R + 1)); // per slab and brick parity
     static constexpr int CARRYZ = G::pad((G::R + 1) * (G::R + 1));
-    static constexpr int CARRY  = pad1k(2 * G::NH * CARRYX + CARRYZ);
+    static constexpr int CARRY  = pad1k(2 * G::NH * CARRYX + 2 * CARRYZ);
     static constexpr size_t
     bytes(const int n_x, const int n_ops)
     {
@@ -663,18 +664,41 @@ namespace dasm
     }
   };
 
-  // resident thread blocks per SM: two (two independent blocks overlap the barrier / latency stalls of one with the work of the
-  // other: +34 % (double), +49 % (float) at k = 3, profiles/r02l_k3_two_blocks.txt): k <= 3 with whole bricks, k = 4 with
-  // half bricks (shared memory)
-#ifndef TMA_MINB
-#define TMA_MINB(k) 2
-#endif
-  // cell layers per work item
-  template <int k>
+  // Work item and residency per degree and number type:
+  //   k <= 3   whole bricks (BZ = 4), two resident blocks per SM (two independent blocks overlap the barrier / latency stalls of one
+  //            with the work of the other: +34 % (double), +49 % (float) at k = 3, profiles/r02l_k3_two_blocks.txt)
+  //   k  = 4   half bricks (BZ = 2), two blocks per SM
+  //   k  = 5   double: single cell layers (BZ = 1, 110 KB), float: half bricks; two blocks per SM
+  //   k  = 6   single cell layers; double: one block per SM (170 KB), float: two
+  // (shared memory: tile + 2 exchange slots of NCELLS n^3 + operand box + carries, TmaSmem)
+  template <int k, typename T>
   struct TmaItem
   {
-    static constexpr int BZ = (k <= 3) ? 4 : 2;
+    static constexpr int BZ   = (k <= 3) ? 4 : (k == 4 ? 2 : ((k == 5 && sizeof(T) == 4) ? 2 : 1));
+    static constexpr int MINB = (k == 6 && sizeof(T) == 8) ? 1 : 2;
   };
+  // host-side view (chunking and grid size): resident blocks per SM
+  inline int
+  tma_min_blocks(const int k, const int esize)
+  {
+    return (k == 6 && esize == 8) ? 1 : 2;
+  }
+  inline int
+  tma_item_layers(const int k, const int esize)
+  {
+    return (k <= 3) ? 4 : (k == 4 ? 2 : ((k == 5 && esize == 4) ? 2 : 1));
+  }
+
+  // barrier over all threads of the block (all threads are compute threads; bar.sync with a thread count needs a multiple of 32)
+  template <int NCT>
+  __device__ __forceinline__ void
+  block_sync()
+  {
+    if constexpr (NCT % 32 == 0)
+      bar_sync(FB_COMPUTE, NCT);
+    else
+      __syncthreads();
+  }
 
   // state of the walk over the items of a block
   struct TmaCursor
@@ -694,7 +718,7 @@ namespace dasm
     const uint32_t *dw = reinterpret_cast<const uint32_t *>(list.bricks);
     if (tid < TMA_DW)
       s_desc[tid] = ldg_early(dw + (size_t)idx * TMA_DW + tid);
-    bar_sync(FB_COMPUTE, G::NCT);
+    block_sync<G::NCT>();
     if (tid == 0)
       tma_issue_tile<k, T, BZ>(tile, tmaps, s_desc, 0, mb_tile);
     if (list.any_mode1 && (s_desc[1] & TMA_MODE1))
@@ -715,7 +739,7 @@ namespace dasm
 
   // ---- Laplace, uniform Cartesian geometry --------------------------------------------------------------------------------------
   template <int k, typename T, int NOPS>
-  __global__ void __launch_bounds__((TmaGeom<k, T, TmaItem<k>::BZ>::NT), TMA_MINB(k))
+  __global__ void __launch_bounds__((TmaGeom<k, T, TmaItem<k, T>::BZ>::NT), (TmaItem<k, T>::MINB))
   laplace_tma_kernel(const T *__restrict__ src,
                      T *__restrict__ dst,
                      T *__restrict__ acc,
@@ -728,7 +752,7 @@ namespace dasm
                      const TmaList     list,
                      const FastMaps    dbgmaps)
   {
-    constexpr int BZ = TmaItem<k>::BZ;
+    constexpr int BZ = TmaItem<k, T>::BZ;
     using G          = TmaGeom<k, T, BZ>;
     using SM         = TmaSmem<k, T, BZ>;
     constexpr int n  = k + 1;
@@ -783,7 +807,7 @@ namespace dasm
           cp_async_wait_all();
         // foreign points gathered by the other threads (mode 1); all phase B reads of the exchange slots of the previous item are
         // done before phase A overwrites them; all threads have left the epilogue of the previous item
-        bar_sync(FB_COMPUTE, G::NCT);
+        block_sync<G::NCT>();
         if (need0 && tid == 0)
           tma_issue_ops<k, T, BZ>(ops0, ops0, &omap0, &omap0, false, desc[0], cur.hz, mb_ops);
         // descriptor of the next brick -> shared memory (fire and forget, awaited before the barrier after phase A; its buffer held
@@ -791,7 +815,58 @@ namespace dasm
         if (cur.hz == 0 && nidx != TMA_NONE && tid < TMA_DW)
           cp_async_4(s_desc + (cur.par ^ 1) * 16 + tid, dw + (size_t)nidx * TMA_DW + tid);
         // phase A: plane y = t, [z][x]: q = Mx Mz v, p = (g0 Kx Mz + g2 Mx Kz) v
-        if (!(dbgmaps.dbg & 1))
+        if constexpr (n >= 7)
+          {
+            // two passes over the plane (one n x n array in registers instead of two): first q = Mx Mz v and p = g2 Mx Kz v,
+            // then p += g0 Kx Mz v
+            if (!(dbgmaps.dbg & 1))
+              {
+                T a[n][n];
+#pragma unroll
+                for (int z = 0; z < n; ++z)
+                  {
+                    T v[n];
+                    plane_load_row<k, T, 0>(v, tile, pa, z, cx);
+                    mat_vec<n, T, true, true, false>(a[z], mats.M, v);
+                  }
+#pragma unroll
+                for (int x = 0; x < n; ++x)
+                  {
+                    T ca[n], q[n], p[n];
+#pragma unroll
+                    for (int z = 0; z < n; ++z)
+                      ca[z] = a[z][x];
+                    mat_vec<n, T, true, true, false>(q, mats.M, ca);
+                    mat_vec<n, T, true, true, false>(p, mats.K2, ca);
+#pragma unroll
+                    for (int z = 0; z < n; ++z)
+                      {
+                        xq[(z * n + t) * n + x] = q[z];
+                        xp[(z * n + t) * n + x] = p[z];
+                      }
+                  }
+#pragma unroll
+                for (int z = 0; z < n; ++z)
+                  {
+                    T v[n];
+                    plane_load_row<k, T, 0>(v, tile, pa, z, cx);
+                    mat_vec<n, T, true, true, false>(a[z], mats.K0, v);
+                  }
+#pragma unroll
+                for (int x = 0; x < n; ++x)
+                  {
+                    T cb[n], p[n];
+#pragma unroll
+                    for (int z = 0; z < n; ++z)
+                      cb[z] = a[z][x];
+                    mat_vec<n, T, true, true, false>(p, mats.M, cb);
+#pragma unroll
+                    for (int z = 0; z < n; ++z)
+                      xp[(z * n + t) * n + x] += p[z];
+                  }
+              }
+          }
+        else if (!(dbgmaps.dbg & 1))
           {
             T a[n][n], b[n][n];
 #pragma unroll
@@ -825,7 +900,7 @@ namespace dasm
           }
         if (cur.hz == 0 && nidx != TMA_NONE && tid < TMA_DW)
           cp_async_wait_all();
-        bar_sync(FB_COMPUTE, G::NCT);
+        block_sync<G::NCT>();
         if (has_next)
           {
             if (last_slab)
@@ -872,7 +947,8 @@ namespace dasm
         if (!skip_last && (t < k || cz == BZ - 1) && !(dbgmaps.dbg & 2))
           {
             const TmaCarry<T> cr = {carry + (cur.hz * 2 + cur.par) * SM::CARRYX, carry + (cur.hz * 2 + (cur.par ^ 1)) * SM::CARRYX,
-                                    carry + 2 * G::NH * SM::CARRYX};
+                                    carry + 2 * G::NH * SM::CARRYX + ((cur.hz + 1) & 1) * SM::CARRYZ,
+                                    carry + 2 * G::NH * SM::CARRYX + (cur.hz & 1) * SM::CARRYZ};
             tma_epilogue<k, T, BZ, NOPS>(r, ops0, ops0, cr, dst, direct ? dst : acc, direct, ni.out, ec, desc, list.foreign, cur.hz, cx, cy, cz,
                                          t);
           }
@@ -891,7 +967,7 @@ namespace dasm
 
   // ---- FDM, one eigen-decomposition triple, tensor-product weights folded into the matrices ----------------------------------
   template <int k, typename T, int NOPS>
-  __global__ void __launch_bounds__((TmaGeom<k, T, TmaItem<k>::BZ>::NT), TMA_MINB(k))
+  __global__ void __launch_bounds__((TmaGeom<k, T, TmaItem<k, T>::BZ>::NT), (TmaItem<k, T>::MINB))
   fdm_tma_kernel(const T *__restrict__ src,
                  T *__restrict__ dst,
                  T *__restrict__ acc,
@@ -905,7 +981,7 @@ namespace dasm
                  const TmaList     list,
                  const FastMaps    dbgmaps)
   {
-    constexpr int BZ = TmaItem<k>::BZ;
+    constexpr int BZ = TmaItem<k, T>::BZ;
     using G          = TmaGeom<k, T, BZ>;
     using SM         = TmaSmem<k, T, BZ>;
     constexpr int n  = k + 1;
@@ -961,7 +1037,7 @@ namespace dasm
           cp_async_wait_all();
         // foreign points gathered by the other threads (mode 1); all phase C reads of the exchange slot of the previous item are
         // done before phase A overwrites it; all threads have left the epilogue of the previous item
-        bar_sync(FB_COMPUTE, G::NCT);
+        block_sync<G::NCT>();
         if (need0 && tid == 0)
           tma_issue_ops<k, T, BZ>(ops0, ops1, &omap0, &omap1, need1, desc[0], cur.hz, mb_ops);
         if (cur.hz == 0 && nidx != TMA_NONE && tid < TMA_DW)
@@ -992,7 +1068,7 @@ namespace dasm
           }
         if (cur.hz == 0 && nidx != TMA_NONE && tid < TMA_DW)
           cp_async_wait_all();
-        bar_sync(FB_COMPUTE, G::NCT);
+        block_sync<G::NCT>();
         if (has_next)
           {
             if (last_slab)
@@ -1030,7 +1106,7 @@ namespace dasm
                   xs[(z * n + t) * n + x] = u[x];
               }
           }
-        bar_sync(FB_COMPUTE, G::NCT);
+        block_sync<G::NCT>();
         // phase C: plane z = t, [y][x]: By in y (+ plane z = k of the cell below for t = 0)
         T r[n][n];
         if (!skip_last)
@@ -1062,7 +1138,8 @@ namespace dasm
         if (!skip_last && (t < k || cz == BZ - 1) && !(dbgmaps.dbg & 2))
           {
             const TmaCarry<T> cr = {carry + (cur.hz * 2 + cur.par) * SM::CARRYX, carry + (cur.hz * 2 + (cur.par ^ 1)) * SM::CARRYX,
-                                    carry + 2 * G::NH * SM::CARRYX};
+                                    carry + 2 * G::NH * SM::CARRYX + ((cur.hz + 1) & 1) * SM::CARRYZ,
+                                    carry + 2 * G::NH * SM::CARRYX + (cur.hz & 1) * SM::CARRYZ};
             tma_epilogue<k, T, BZ, NOPS>(r, ops0, ops1, cr, dst, direct ? dst : acc, direct, ni.out, ec, desc, list.foreign, cur.hz, cx, cy, cz,
                                          t);
           }

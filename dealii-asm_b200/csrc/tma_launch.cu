@@ -78,7 +78,7 @@ namespace dasm
         return false;
       }
     const cuuint64_t R = 4 * k, XW = 16 / esize;
-    const cuuint32_t RZ = (cuuint32_t)((k <= 3 ? 4 : 2) * k); // z extent of a work item (kernels_tma.cuh TmaItem)
+    const cuuint32_t RZ = (cuuint32_t)(tma_item_layers(k, esize) * k); // z extent of a work item (kernels_tma.cuh TmaItem)
     const cuuint64_t dims[4]    = {R, R, R, (cuuint64_t)n_lex};
     const cuuint64_t strides[3] = {R * esize, R * R * esize, R * R * R * esize};
     const cuuint32_t estr[4]    = {1, 1, 1, 1};
@@ -129,7 +129,7 @@ namespace dasm
   size_t
   tma_laplace_smem(int k, int esize)
   {
-#define DASM_TMA_SMEM(K) (esize == 8 ? TmaSmem<K, double, TmaItem<K>::BZ>::bytes(2, 1) : TmaSmem<K, float, TmaItem<K>::BZ>::bytes(2, 1))
+#define DASM_TMA_SMEM(K) (esize == 8 ? TmaSmem<K, double, TmaItem<K, double>::BZ>::bytes(2, 1) : TmaSmem<K, float, TmaItem<K, float>::BZ>::bytes(2, 1))
     switch (k)
       {
         case 2:
@@ -138,6 +138,10 @@ namespace dasm
           return DASM_TMA_SMEM(3);
         case 4:
           return DASM_TMA_SMEM(4);
+        case 5:
+          return DASM_TMA_SMEM(5);
+        case 6:
+          return DASM_TMA_SMEM(6);
       }
 #undef DASM_TMA_SMEM
     return (size_t)-1;
@@ -146,7 +150,7 @@ namespace dasm
   size_t
   tma_fdm_smem(int k, int esize)
   {
-#define DASM_TMA_SMEM(K) (esize == 8 ? TmaSmem<K, double, TmaItem<K>::BZ>::bytes(1, 2) + 8 * 125 : TmaSmem<K, float, TmaItem<K>::BZ>::bytes(1, 2) + 8 * 125)
+#define DASM_TMA_SMEM(K) (esize == 8 ? TmaSmem<K, double, TmaItem<K, double>::BZ>::bytes(1, 2) + 8 * (K + 1) * (K + 1) * (K + 1) : TmaSmem<K, float, TmaItem<K, float>::BZ>::bytes(1, 2) + 4 * (K + 1) * (K + 1) * (K + 1))
     switch (k)
       {
         case 2:
@@ -155,6 +159,10 @@ namespace dasm
           return DASM_TMA_SMEM(3);
         case 4:
           return DASM_TMA_SMEM(4);
+        case 5:
+          return DASM_TMA_SMEM(5);
+        case 6:
+          return DASM_TMA_SMEM(6);
       }
 #undef DASM_TMA_SMEM
     return (size_t)-1;
@@ -165,13 +173,13 @@ namespace dasm
   launch_laplace_tma_k(cudaStream_t stream, int grid, const T *src, T *dst, T *acc, const Epilogue<T> &epi, const double (*P)[25],
                        const double (*Q)[25], const TmaMaps &maps, const CUtensorMap &omap0, int shared_mode, const NextInit<T> &ni, const TmaList &list, int dbg)
   {
-    using G = TmaGeom<K, T, TmaItem<K>::BZ>;
+    using G = TmaGeom<K, T, TmaItem<K, T>::BZ>;
     FastLaplaceMats<T, K + 1> mats;
     eo_fill(mats.M, P[0], Q[0]);
     eo_fill(mats.K0, P[1], Q[1]);
     eo_fill(mats.K1, P[2], Q[2]);
     eo_fill(mats.K2, P[3], Q[3]);
-    constexpr size_t smem  = TmaSmem<K, T, TmaItem<K>::BZ>::bytes(2, 1);
+    constexpr size_t smem  = TmaSmem<K, T, TmaItem<K, T>::BZ>::bytes(2, 1);
     const bool       need0 = (epi.kind == EPI_RESIDUAL || epi.kind == EPI_CHEB);
     auto             kern  = need0 ? laplace_tma_kernel<K, T, 1> : laplace_tma_kernel<K, T, 0>;
     check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "laplace_tma_kernel attribute");
@@ -188,7 +196,7 @@ namespace dasm
                    const double (*Q)[25], const double *inv, const TmaMaps &maps, const CUtensorMap &omap0, const CUtensorMap &omap1, int shared_mode, const NextInit<T> &ni,
                    const TmaList &list, int dbg)
   {
-    using G         = TmaGeom<K, T, TmaItem<K>::BZ>;
+    using G         = TmaGeom<K, T, TmaItem<K, T>::BZ>;
     constexpr int n = K + 1;
     FastFdmMats<T, n> mats;
     eo_fill(mats.Ax, P[0], Q[0]);
@@ -199,7 +207,7 @@ namespace dasm
     eo_fill(mats.Bz, P[5], Q[5]);
     for (int i = 0; i < n * n * n; ++i)
       mats.inv[i] = (T)inv[i];
-    constexpr size_t smem  = TmaSmem<K, T, TmaItem<K>::BZ>::bytes(1, 2);
+    constexpr size_t smem  = TmaSmem<K, T, TmaItem<K, T>::BZ>::bytes(1, 2);
     const bool       need0 = (epi.kind == EPI_RESIDUAL || epi.kind == EPI_CHEB);
     const bool       need1 = (epi.kind == EPI_CHEB && epi.f1 != T(0) && epi.v1 != nullptr);
     auto             kern  = need1 ? fdm_tma_kernel<K, T, 2> : (need0 ? fdm_tma_kernel<K, T, 1> : fdm_tma_kernel<K, T, 0>);
@@ -224,6 +232,10 @@ namespace dasm
           return launch_laplace_tma_k<3, T>(stream, grid, src, dst, acc, epi, P, Q, maps, omap0, shared_mode, ni, list, dbg);
         case 4:
           return launch_laplace_tma_k<4, T>(stream, grid, src, dst, acc, epi, P, Q, maps, omap0, shared_mode, ni, list, dbg);
+        case 5:
+          return launch_laplace_tma_k<5, T>(stream, grid, src, dst, acc, epi, P, Q, maps, omap0, shared_mode, ni, list, dbg);
+        case 6:
+          return launch_laplace_tma_k<6, T>(stream, grid, src, dst, acc, epi, P, Q, maps, omap0, shared_mode, ni, list, dbg);
       }
     throw std::runtime_error("laplace_tma_kernel: degree not instantiated");
   }
@@ -242,6 +254,10 @@ namespace dasm
           return launch_fdm_tma_k<3, T>(stream, grid, src, dst, acc, epi, P, Q, inv, maps, omap0, omap1, shared_mode, ni, list, dbg);
         case 4:
           return launch_fdm_tma_k<4, T>(stream, grid, src, dst, acc, epi, P, Q, inv, maps, omap0, omap1, shared_mode, ni, list, dbg);
+        case 5:
+          return launch_fdm_tma_k<5, T>(stream, grid, src, dst, acc, epi, P, Q, inv, maps, omap0, omap1, shared_mode, ni, list, dbg);
+        case 6:
+          return launch_fdm_tma_k<6, T>(stream, grid, src, dst, acc, epi, P, Q, inv, maps, omap0, omap1, shared_mode, ni, list, dbg);
       }
     throw std::runtime_error("fdm_tma_kernel: degree not instantiated");
   }

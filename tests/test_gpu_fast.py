@@ -50,7 +50,7 @@ class no_fast:
         os.environ.pop("DASM_NO_FAST", None)
 
 
-@pytest.mark.parametrize("k", [2, 3, 4])
+@pytest.mark.parametrize("k", [2, 3, 4, 5, 6])
 @pytest.mark.parametrize("number", ["double", "float"])
 @pytest.mark.parametrize("name", ["periodic_2bricks", "periodic_aniso"])
 def test_fast_vmult_vs_oracle(pkg, ctx, name, k, number):
@@ -64,7 +64,7 @@ def test_fast_vmult_vs_oracle(pkg, ctx, name, k, number):
     assert relerr(op.to_host(yd), oop.vmult(x)) < TOL[number]
 
 
-@pytest.mark.parametrize("k", [2, 3, 4])
+@pytest.mark.parametrize("k", [2, 3, 4, 5, 6])
 @pytest.mark.parametrize("wt", ["none", "pre", "post", "symm", "ras"])
 def test_fast_fdm_vs_oracle(pkg, ctx, k, wt):
     mesh = pkg.Mesh(ctx, **FAST_MESHES["periodic_aniso"])
@@ -79,7 +79,9 @@ def test_fast_fdm_vs_oracle(pkg, ctx, k, wt):
 
 
 @pytest.mark.parametrize("k,number,wt,degree,poly,is_step", [(4, "double", "symm", 3, "1st kind", True), (3, "float", "post", 2, "4th kind", True),
-                                                             (2, "double", "pre", 4, "1st kind", False), (4, "float", "symm", 3, "1st kind", False)])
+                                                             (2, "double", "pre", 4, "1st kind", False), (4, "float", "symm", 3, "1st kind", False),
+                                                             (5, "double", "symm", 3, "1st kind", True), (5, "float", "post", 3, "1st kind", False),
+                                                             (6, "double", "post", 2, "4th kind", True), (6, "float", "symm", 3, "1st kind", True)])
 def test_fast_chebyshev_vs_oracle(pkg, ctx, k, number, wt, degree, poly, is_step):
     mesh = pkg.Mesh(ctx, **FAST_MESHES["periodic_2bricks"])
     op = pkg.LaplaceOperatorMatrixFree(mesh, k, number)
