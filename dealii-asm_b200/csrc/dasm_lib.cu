@@ -844,9 +844,10 @@ fast_dbg()
 static bool
 overlap_enabled(const dasm_op *op, const int shared_mode, const int n_fast_boundary, const int n_fast)
 {
-  // opt-in (DASM_OVERLAP=1): measured gain 1 % at 2 and 8 GPUs only - the NCCL send / receive kernels do not run next to the
-  // persistent cell kernels (also not with 8 SMs left free) - and verified by the parity script at 2 ranks only
-  static const bool on = getenv("DASM_OVERLAP") && getenv("DASM_OVERLAP")[0] == '1';
+  // default on (DASM_OVERLAP=0 switches it off): with the device-initiated exchange (pack kernel writes into the peer, no NCCL
+  // kernels) the exchange runs next to the interior bricks: 5.96 instead of 6.20 ms per step at 2 GPUs (profiles/r02k); with the
+  // NCCL send / receive fallback the gain was 1 % (r01f).  Parity: tests/multi_gpu_parity.py at 2, 4 and 8 ranks.
+  static const bool on = !(getenv("DASM_OVERLAP") && getenv("DASM_OVERLAP")[0] == '0');
   return on && op->exchange.active() && shared_mode == SHARED_DIRECT && n_fast > n_fast_boundary;
 }
 

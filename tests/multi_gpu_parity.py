@@ -61,7 +61,8 @@ def main():
     # kernels); "ras": the patch that keeps an interface DoF lives on the neighbouring rank (compress must run)
     for k, number, nc, wt in ((4, "double", (8, 8, 8), "symm"), (3, "double", (8, 6, 4), "post"), (2, "double", (8, 8, 8), "none"),
                               (4, "double", (24, 8, 8), "symm"), (3, "float", (24, 8, 8), "post"), (4, "double", (16, 16, 16), "symm"),
-                              (3, "double", (16, 16, 16), "ras"), (2, "double", (8, 8, 8), "ras")):
+                              (3, "double", (16, 16, 16), "ras"), (2, "double", (8, 8, 8), "ras")) + \
+            (((4, "double", (32, 32, 32), "symm"), (3, "float", (32, 32, 16), "post")) if world >= 4 else ()):  # interior bricks on every rank of 2 x 2 x 2
         L = tuple(float(c) / 4 for c in nc)
         vsize = None
         results = {}
