@@ -452,7 +452,7 @@ struct dasm_op
   uint32_t *            d_tma_lap_chunks = nullptr; // chunk_start of the chunks of +x neighbours (kernels_tma.cuh)
   int                   tma_lap_n_chunks = 0, tma_lap_n_chunks_boundary = 0;
   uint32_t *            d_tma_foreign = nullptr; // foreign index lists of the mode-1 bricks
-  int                   tma_any_mode1 = 0;
+  int                   tma_any_mode1 = 0, tma_any_mode1_interior = 0;
   std::unordered_map<const void *, TmaMaps> tma_cache; // tensor maps per vector
 
   dasm_op(int degree)
@@ -489,7 +489,7 @@ struct dasm_fdm
   TmaBrick *d_tma_list = nullptr; // TMA-fed kernel: descriptors in the order of d_fast_ids
   uint32_t *d_tma_chunks = nullptr;
   int       tma_n_chunks = 0, tma_n_chunks_boundary = 0;
-  int       tma_any_mode1 = 0;
+  int       tma_any_mode1 = 0, tma_any_mode1_interior = 0;
   double    fast_P[6][25], fast_Q[6][25]; // even-odd blocks of Ax Ay Az Bx By Bz
   double    fast_inv[729];
   std::vector<double>   h_S, h_lam; // double copies for inspection
@@ -907,6 +907,7 @@ struct TmaChunked
   std::vector<uint32_t> chunk_start;
   int                   n_chunks_boundary = 0;
   int                   any_mode1         = 0;
+  int                   any_mode1_interior = 0; // ... among the chunks behind the boundary chunks
 };
 
 static TmaChunked
@@ -919,6 +920,8 @@ tma_build_list_L(const dasm_op *op, const std::vector<uint32_t> &ids, const int 
     {
       TmaBrick t = op->h_tma[ids[i]];
       out.any_mode1 |= (int)(t.flags & TMA_MODE1);
+      if (i >= n_boundary)
+        out.any_mode1_interior |= (int)(t.flags & TMA_MODE1);
       bool cont = false; // continues the chunk of the previous brick
       if (i > 0 && i != n_boundary && len < L)
         {
@@ -1059,7 +1062,10 @@ launch_laplace_fast(dasm_op *op, T *dst, const T *src, const Epilogue<T> &epi, c
   if (c_count == 0)
     return true;
   const int      grid = std::min(c_count, std::max(1, op->n_sm * tma_ctas_per_sm(K, (int)sizeof(T)) - reserve_sms));
-  const TmaList  list = {op->d_tma_lap, op->d_tma_foreign, op->d_tma_lap_chunks + c_first, c_count, op->tma_any_mode1};
+  // (a launch over the interior bricks only - the overlapped schedule - usually contains no brick with an index list)
+  const bool     interior_only = first > 0 && first == op->n_fast_boundary;
+  const TmaList  list = {op->d_tma_lap, op->d_tma_foreign, op->d_tma_lap_chunks + c_first, c_count,
+                         interior_only ? op->tma_any_mode1_interior : op->tma_any_mode1};
   const TmaMaps *o0   = epi.v0 ? tma_maps_for(op, epi.v0) : tm;
   if (o0 == nullptr)
     return false;
@@ -1338,7 +1344,9 @@ launch_fdm_fast(dasm_fdm *f, T *dst, const T *src, const Epilogue<T> &epi, const
   if (c_count == 0)
     return true;
   const int      grid = std::min(c_count, std::max(1, op->n_sm * tma_ctas_per_sm(K, (int)sizeof(T)) - reserve_sms));
-  const TmaList  list = {f->d_tma_list, op->d_tma_foreign, f->d_tma_chunks + c_first, c_count, f->tma_any_mode1};
+  const bool     interior_only = first > 0 && first == f->n_fast_boundary;
+  const TmaList  list = {f->d_tma_list, op->d_tma_foreign, f->d_tma_chunks + c_first, c_count,
+                         interior_only ? f->tma_any_mode1_interior : f->tma_any_mode1};
   const TmaMaps *o0 = epi.v0 ? tma_maps_for(op, epi.v0) : tm, *o1 = epi.v1 ? tma_maps_for(op, epi.v1) : tm;
   if (o0 == nullptr || o1 == nullptr)
     return false;
@@ -1625,6 +1633,7 @@ setup_tma_only(dasm_op *op)
   const TmaChunked ch  = tma_build_list(op, fast_ids, 0);
   op->fast_ok          = true;
   op->tma_any_mode1    = ch.any_mode1;
+  op->tma_any_mode1_interior = ch.any_mode1_interior;
   op->d_tma_lap        = dev_upload(ch.descs, ctx->stream);
   op->d_tma_lap_chunks = dev_upload(ch.chunk_start, ctx->stream);
   op->tma_lap_n_chunks = (int)ch.chunk_start.size() - 1;
@@ -2519,6 +2528,7 @@ dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping
                         op->tma_ok        = true;
                         op->fast_ok       = true;
                         op->tma_any_mode1 = ch.any_mode1;
+                        op->tma_any_mode1_interior = ch.any_mode1_interior;
                         op->d_tma_lap     = dev_upload(ch.descs, ctx->stream);
                         op->d_tma_lap_chunks = dev_upload(ch.chunk_start, ctx->stream);
                         op->tma_lap_n_chunks = (int)ch.chunk_start.size() - 1;
@@ -3455,6 +3465,7 @@ dasm_fdm_create(dasm_op *op, int n_overlap, int sub_mesh_approximation, int weig
                 {
                   const TmaChunked ch = tma_build_list(op, fast_ids, f->n_fast_boundary);
                   f->tma_any_mode1    = ch.any_mode1;
+                  f->tma_any_mode1_interior = ch.any_mode1_interior;
                   f->d_tma_list       = dev_upload(ch.descs, op->ctx->stream);
                   f->d_tma_chunks     = dev_upload(ch.chunk_start, op->ctx->stream);
                   f->tma_n_chunks     = (int)ch.chunk_start.size() - 1;

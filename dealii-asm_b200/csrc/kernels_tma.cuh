@@ -266,10 +266,15 @@ namespace dasm
   {
     using G         = TmaGeom<k, T, BZ>;
     constexpr int R = G::R, RZ = G::RZ, XW = G::XW;
+    // all index loads first (independent, one round of latency), then the copies
+    uint32_t gi[G::NFT];
+    int      oo[G::NFT];
 #pragma unroll
     for (int jj = 0; jj < G::NFT; ++jj)
       {
         const int j = tid + jj * G::NCT;
+        oo[jj]      = -1;
+        gi[jj]      = 0;
         if (j < G::NFOR)
           {
             int X, Y, Zl, o;
@@ -287,9 +292,14 @@ namespace dasm
               X = j - G::I_EYZ, Y = R, Zl = RZ, o = G::O_EYZ + (j - G::I_EYZ);
             else
               X = R, Y = R, Zl = RZ, o = G::O_C;
-            cp_async_value(tile + o, src + tma_foreign_index<k, T, BZ>(desc, lists, hz, X, Y, Zl));
+            oo[jj] = o;
+            gi[jj] = tma_foreign_index<k, T, BZ>(desc, lists, hz, X, Y, Zl);
           }
       }
+#pragma unroll
+    for (int jj = 0; jj < G::NFT; ++jj)
+      if (oo[jj] >= 0)
+        cp_async_value(tile + oo[jj], src + gi[jj]);
   }
 
   // per-thread addressing of a cell plane in the tile: rows r = 0..k (row r < k starts at r0 + r rs, row k at rk; the x
@@ -430,7 +440,9 @@ namespace dasm
   // After the merge every thread (cell, plane z = t) holds the FINAL values of its exclusive points x < k (or x <= k for
   // cx = 3), y < k (or y <= k for cy = 3) of the plane Zl = k cz + t of the item.
   // NOPS: number of epilogue operands staged in shared memory (0: store / scale, 1: residual or update without x_old, 2: update)
-  template <int k, typename T, int BZ, int NOPS>
+  // HOIST (items with an index list, mode 1): the global indices of the points other bricks own are loaded up front, so that the
+  // loads of a thread are in flight together instead of one round trip in front of every red.add
+  template <int k, typename T, int BZ, int NOPS, bool HOIST>
   __device__ __forceinline__ void
   tma_epilogue(T (&r)[k + 1][k + 1], const T *ops0, const T *ops1, const TmaCarry<T> &cr, T *__restrict__ dst, T *__restrict__ sh_dst,
                const bool direct, T *__restrict__ ni_out, const EpiCoef<T> &ec, const uint32_t *desc, const uint32_t *__restrict__ lists,
@@ -494,6 +506,47 @@ namespace dasm
       }
     const bool xred = (cx == 3) && !cout; // X = R points go to the neighbours with red.add
     const bool x0sh = (cx == 0) && !cin;  // the own face X = 0 is shared with a brick processed elsewhere
+    uint32_t gf[HOIST ? k + 1 : 1][HOIST ? k + 1 : 1];
+    if (!HOIST)
+      {
+      }
+    else if (Zl < RZ)
+      {
+        if (xred)
+          {
+#pragma unroll
+            for (int y = 0; y < k; ++y)
+              gf[y][k] = tma_foreign_index<k, T, BZ>(desc, lists, hz, R, Y0 + y, Zl);
+          }
+        if (cy == 3)
+          {
+#pragma unroll
+            for (int x = 0; x < k; ++x)
+              gf[k][x] = tma_foreign_index<k, T, BZ>(desc, lists, hz, X0 + x, R, Zl);
+            if (xred)
+              gf[k][k] = tma_foreign_index<k, T, BZ>(desc, lists, hz, R, R, Zl);
+          }
+      }
+    else
+      {
+#pragma unroll
+        for (int y = 0; y < k; ++y)
+          {
+#pragma unroll
+            for (int x = 0; x < k; ++x)
+              gf[y][x] = tma_foreign_index<k, T, BZ>(desc, lists, hz, X0 + x, Y0 + y, RZ);
+            if (xred)
+              gf[y][k] = tma_foreign_index<k, T, BZ>(desc, lists, hz, R, Y0 + y, RZ);
+          }
+        if (cy == 3)
+          {
+#pragma unroll
+            for (int x = 0; x < k; ++x)
+              gf[k][x] = tma_foreign_index<k, T, BZ>(desc, lists, hz, X0 + x, R, RZ);
+            if (xred)
+              gf[k][k] = tma_foreign_index<k, T, BZ>(desc, lists, hz, R, R, RZ);
+          }
+      }
     if (Zl < RZ)
       {
         const bool     zsh = (Z == 0);
@@ -593,15 +646,15 @@ namespace dasm
                   }
               }
             if (xred) // X = R: face of the +x neighbour
-              atomic_add(sh_dst + tma_foreign_index<k, T, BZ>(desc, lists, hz, R, Y0 + y, Zl), sh_a * r[y][k]);
+              atomic_add(sh_dst + (HOIST ? gf[HOIST ? y : 0][HOIST ? k : 0] : tma_foreign_index<k, T, BZ>(desc, lists, hz, R, Y0 + y, Zl)), sh_a * r[y][k]);
           }
         if (cy == 3) // Y = R: face of the +y neighbour, edge of the +xy neighbour
           {
 #pragma unroll
             for (int x = 0; x < k; ++x)
-              atomic_add(sh_dst + tma_foreign_index<k, T, BZ>(desc, lists, hz, X0 + x, R, Zl), sh_a * r[k][x]);
+              atomic_add(sh_dst + (HOIST ? gf[HOIST ? k : 0][HOIST ? x : 0] : tma_foreign_index<k, T, BZ>(desc, lists, hz, X0 + x, R, Zl)), sh_a * r[k][x]);
             if (xred)
-              atomic_add(sh_dst + tma_foreign_index<k, T, BZ>(desc, lists, hz, R, R, Zl), sh_a * r[k][k]);
+              atomic_add(sh_dst + (HOIST ? gf[HOIST ? k : 0][HOIST ? k : 0] : tma_foreign_index<k, T, BZ>(desc, lists, hz, R, R, Zl)), sh_a * r[k][k]);
           }
       }
     else
@@ -612,17 +665,17 @@ namespace dasm
           {
 #pragma unroll
             for (int x = 0; x < k; ++x)
-              atomic_add(sh_dst + tma_foreign_index<k, T, BZ>(desc, lists, hz, X0 + x, Y0 + y, RZ), sh_a * r[y][x]);
+              atomic_add(sh_dst + (HOIST ? gf[HOIST ? y : 0][HOIST ? x : 0] : tma_foreign_index<k, T, BZ>(desc, lists, hz, X0 + x, Y0 + y, Zl)), sh_a * r[y][x]);
             if (xred)
-              atomic_add(sh_dst + tma_foreign_index<k, T, BZ>(desc, lists, hz, R, Y0 + y, RZ), sh_a * r[y][k]);
+              atomic_add(sh_dst + (HOIST ? gf[HOIST ? y : 0][HOIST ? k : 0] : tma_foreign_index<k, T, BZ>(desc, lists, hz, R, Y0 + y, Zl)), sh_a * r[y][k]);
           }
         if (cy == 3)
           {
 #pragma unroll
             for (int x = 0; x < k; ++x)
-              atomic_add(sh_dst + tma_foreign_index<k, T, BZ>(desc, lists, hz, X0 + x, R, RZ), sh_a * r[k][x]);
+              atomic_add(sh_dst + (HOIST ? gf[HOIST ? k : 0][HOIST ? x : 0] : tma_foreign_index<k, T, BZ>(desc, lists, hz, X0 + x, R, Zl)), sh_a * r[k][x]);
             if (xred)
-              atomic_add(sh_dst + tma_foreign_index<k, T, BZ>(desc, lists, hz, R, R, RZ), sh_a * r[k][k]);
+              atomic_add(sh_dst + (HOIST ? gf[HOIST ? k : 0][HOIST ? k : 0] : tma_foreign_index<k, T, BZ>(desc, lists, hz, R, R, Zl)), sh_a * r[k][k]);
           }
       }
   }
@@ -656,7 +709,8 @@ namespace dasm
     static constexpr int OPS    = pad1k(G::NBI);
     static constexpr int CARRYX = G::pad((G::RZ + 1) * (G::R + 1)); // per slab and brick parity
     static constexpr int CARRYZ = G::pad((G::R + 1) * (G::R + 1));
-    static constexpr int CARRY  = pad1k(2 * G::NH * CARRYX + 2 * CARRYZ);
+    static constexpr int NCZ    = (G::NH > 2) ? 2 : 1; // z-carry buffers: a middle slab reads one and writes the other
+    static constexpr int CARRY  = pad1k(2 * G::NH * CARRYX + NCZ * CARRYZ);
     static constexpr size_t
     bytes(const int n_x, const int n_ops)
     {
@@ -709,7 +763,7 @@ namespace dasm
   };
 
   // first tile of a block: descriptor -> s_desc[0], tensor copies (and the index-list gather of a mode-1 brick)
-  template <int k, typename T, int BZ>
+  template <int k, typename T, int BZ, bool M1>
   __device__ __forceinline__ void
   tma_prologue(uint32_t *s_desc, T *tile, const TmaMaps &tmaps, const TmaList &list, const uint32_t idx, const T *__restrict__ src,
                const unsigned mb_tile, const int tid)
@@ -721,24 +775,26 @@ namespace dasm
     block_sync<G::NCT>();
     if (tid == 0)
       tma_issue_tile<k, T, BZ>(tile, tmaps, s_desc, 0, mb_tile);
-    if (list.any_mode1 && (s_desc[1] & TMA_MODE1))
+    if (M1 && (s_desc[1] & TMA_MODE1))
       tma_foreign_gather<k, T, BZ>(tile, s_desc, list.foreign, 0, src, tid);
   }
 
   // after the barrier behind phase A: the tile is dead, fetch the next item into it
-  template <int k, typename T, int BZ>
+  template <int k, typename T, int BZ, bool M1>
   __device__ __forceinline__ void
   tma_fetch_next(const uint32_t *dn, const int hz_next, T *tile, const TmaMaps &tmaps, const TmaList &list, const T *__restrict__ src,
                  const unsigned mb_tile, const int tid)
   {
     if (tid == 0)
       tma_issue_tile<k, T, BZ>(tile, tmaps, dn, hz_next, mb_tile);
-    if (list.any_mode1 && (dn[1] & TMA_MODE1))
+    if (M1 && (dn[1] & TMA_MODE1))
       tma_foreign_gather<k, T, BZ>(tile, dn, list.foreign, hz_next, src, tid);
   }
 
   // ---- Laplace, uniform Cartesian geometry --------------------------------------------------------------------------------------
-  template <int k, typename T, int NOPS>
+  // M1: the launch contains mode-1 bricks (index lists): gather of the foreign points with cp.async and an epilogue that loads
+  // the indices up front; launches without such bricks run the leaner instantiation
+  template <int k, typename T, int NOPS, bool M1>
   __global__ void __launch_bounds__((TmaGeom<k, T, TmaItem<k, T>::BZ>::NT), (TmaItem<k, T>::MINB))
   laplace_tma_kernel(const T *__restrict__ src,
                      T *__restrict__ dst,
@@ -793,7 +849,7 @@ namespace dasm
     cur.hz  = 0;
     cur.par = 0; // s_desc[par]: this brick, s_desc[par ^ 1]: the next one
     walk_init(cur.w, list);
-    tma_prologue<k, T, BZ>(s_desc, tile, tmaps, list, cur.w.idx, src, mb_tile, tid);
+    tma_prologue<k, T, BZ, M1>(s_desc, tile, tmaps, list, cur.w.idx, src, mb_tile, tid);
     for (;;)
       {
         const uint32_t *desc      = s_desc + cur.par * 16;
@@ -803,7 +859,7 @@ namespace dasm
         const bool      has_next  = !last_slab || nidx != TMA_NONE;
         mbar_wait(mb_tile, tphase); // the tensor copies of this item's tile have landed
         tphase ^= 1u;
-        if (list.any_mode1)
+        if (M1)
           cp_async_wait_all();
         // foreign points gathered by the other threads (mode 1); all phase B reads of the exchange slots of the previous item are
         // done before phase A overwrites them; all threads have left the epilogue of the previous item
@@ -904,9 +960,9 @@ namespace dasm
         if (has_next)
           {
             if (last_slab)
-              tma_fetch_next<k, T, BZ>(s_desc + (cur.par ^ 1) * 16, 0, tile, tmaps, list, src, mb_tile, tid);
+              tma_fetch_next<k, T, BZ, M1>(s_desc + (cur.par ^ 1) * 16, 0, tile, tmaps, list, src, mb_tile, tid);
             else
-              tma_fetch_next<k, T, BZ>(desc, cur.hz + 1, tile, tmaps, list, src, mb_tile, tid);
+              tma_fetch_next<k, T, BZ, M1>(desc, cur.hz + 1, tile, tmaps, list, src, mb_tile, tid);
           }
         // phase B: plane z = t, [y][x]: r = My p + g1 Ky q  (+ plane z = k of the cell below for t = 0)
         T r[n][n];
@@ -947,10 +1003,10 @@ namespace dasm
         if (!skip_last && (t < k || cz == BZ - 1) && !(dbgmaps.dbg & 2))
           {
             const TmaCarry<T> cr = {carry + (cur.hz * 2 + cur.par) * SM::CARRYX, carry + (cur.hz * 2 + (cur.par ^ 1)) * SM::CARRYX,
-                                    carry + 2 * G::NH * SM::CARRYX + ((cur.hz + 1) & 1) * SM::CARRYZ,
-                                    carry + 2 * G::NH * SM::CARRYX + (cur.hz & 1) * SM::CARRYZ};
-            tma_epilogue<k, T, BZ, NOPS>(r, ops0, ops0, cr, dst, direct ? dst : acc, direct, ni.out, ec, desc, list.foreign, cur.hz, cx, cy, cz,
-                                         t);
+                                    carry + 2 * G::NH * SM::CARRYX + (SM::NCZ == 2 ? ((cur.hz + 1) & 1) : 0) * SM::CARRYZ,
+                                    carry + 2 * G::NH * SM::CARRYX + (SM::NCZ == 2 ? (cur.hz & 1) : 0) * SM::CARRYZ};
+            tma_epilogue<k, T, BZ, NOPS, M1>(r, ops0, ops0, cr, dst, direct ? dst : acc, direct, ni.out, ec, desc, list.foreign, cur.hz, cx, cy,
+                                                 cz, t);
           }
         if (!has_next)
           break;
@@ -966,7 +1022,7 @@ namespace dasm
   }
 
   // ---- FDM, one eigen-decomposition triple, tensor-product weights folded into the matrices ----------------------------------
-  template <int k, typename T, int NOPS>
+  template <int k, typename T, int NOPS, bool M1>
   __global__ void __launch_bounds__((TmaGeom<k, T, TmaItem<k, T>::BZ>::NT), (TmaItem<k, T>::MINB))
   fdm_tma_kernel(const T *__restrict__ src,
                  T *__restrict__ dst,
@@ -1023,7 +1079,7 @@ namespace dasm
     cur.hz  = 0;
     cur.par = 0;
     walk_init(cur.w, list);
-    tma_prologue<k, T, BZ>(s_desc, tile, tmaps, list, cur.w.idx, src, mb_tile, tid);
+    tma_prologue<k, T, BZ, M1>(s_desc, tile, tmaps, list, cur.w.idx, src, mb_tile, tid);
     for (;;)
       {
         const uint32_t *desc      = s_desc + cur.par * 16;
@@ -1033,7 +1089,7 @@ namespace dasm
         const bool      has_next  = !last_slab || nidx != TMA_NONE;
         mbar_wait(mb_tile, tphase);
         tphase ^= 1u;
-        if (list.any_mode1)
+        if (M1)
           cp_async_wait_all();
         // foreign points gathered by the other threads (mode 1); all phase C reads of the exchange slot of the previous item are
         // done before phase A overwrites it; all threads have left the epilogue of the previous item
@@ -1072,9 +1128,9 @@ namespace dasm
         if (has_next)
           {
             if (last_slab)
-              tma_fetch_next<k, T, BZ>(s_desc + (cur.par ^ 1) * 16, 0, tile, tmaps, list, src, mb_tile, tid);
+              tma_fetch_next<k, T, BZ, M1>(s_desc + (cur.par ^ 1) * 16, 0, tile, tmaps, list, src, mb_tile, tid);
             else
-              tma_fetch_next<k, T, BZ>(desc, cur.hz + 1, tile, tmaps, list, src, mb_tile, tid);
+              tma_fetch_next<k, T, BZ, M1>(desc, cur.hz + 1, tile, tmaps, list, src, mb_tile, tid);
           }
         // phase B: plane y = t, [z][x]: Az, scale, Bz in z; Bx in x
         if (!(dbgmaps.dbg & 1))
@@ -1138,10 +1194,10 @@ namespace dasm
         if (!skip_last && (t < k || cz == BZ - 1) && !(dbgmaps.dbg & 2))
           {
             const TmaCarry<T> cr = {carry + (cur.hz * 2 + cur.par) * SM::CARRYX, carry + (cur.hz * 2 + (cur.par ^ 1)) * SM::CARRYX,
-                                    carry + 2 * G::NH * SM::CARRYX + ((cur.hz + 1) & 1) * SM::CARRYZ,
-                                    carry + 2 * G::NH * SM::CARRYX + (cur.hz & 1) * SM::CARRYZ};
-            tma_epilogue<k, T, BZ, NOPS>(r, ops0, ops1, cr, dst, direct ? dst : acc, direct, ni.out, ec, desc, list.foreign, cur.hz, cx, cy, cz,
-                                         t);
+                                    carry + 2 * G::NH * SM::CARRYX + (SM::NCZ == 2 ? ((cur.hz + 1) & 1) : 0) * SM::CARRYZ,
+                                    carry + 2 * G::NH * SM::CARRYX + (SM::NCZ == 2 ? (cur.hz & 1) : 0) * SM::CARRYZ};
+            tma_epilogue<k, T, BZ, NOPS, M1>(r, ops0, ops1, cr, dst, direct ? dst : acc, direct, ni.out, ec, desc, list.foreign, cur.hz, cx, cy,
+                                                 cz, t);
           }
         if (!has_next)
           break;

@@ -181,7 +181,8 @@ namespace dasm
     eo_fill(mats.K2, P[3], Q[3]);
     constexpr size_t smem  = TmaSmem<K, T, TmaItem<K, T>::BZ>::bytes(2, 1);
     const bool       need0 = (epi.kind == EPI_RESIDUAL || epi.kind == EPI_CHEB);
-    auto             kern  = need0 ? laplace_tma_kernel<K, T, 1> : laplace_tma_kernel<K, T, 0>;
+    auto             kern  = list.any_mode1 ? (need0 ? laplace_tma_kernel<K, T, 1, true> : laplace_tma_kernel<K, T, 0, true>) :
+                                              (need0 ? laplace_tma_kernel<K, T, 1, false> : laplace_tma_kernel<K, T, 0, false>);
     check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "laplace_tma_kernel attribute");
     check(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), "carveout");
     report_occupancy("laplace_tma_kernel", (const void *)kern, G::NT, smem);
@@ -210,7 +211,8 @@ namespace dasm
     constexpr size_t smem  = TmaSmem<K, T, TmaItem<K, T>::BZ>::bytes(1, 2);
     const bool       need0 = (epi.kind == EPI_RESIDUAL || epi.kind == EPI_CHEB);
     const bool       need1 = (epi.kind == EPI_CHEB && epi.f1 != T(0) && epi.v1 != nullptr);
-    auto             kern  = need1 ? fdm_tma_kernel<K, T, 2> : (need0 ? fdm_tma_kernel<K, T, 1> : fdm_tma_kernel<K, T, 0>);
+    auto             kern  = list.any_mode1 ? (need1 ? fdm_tma_kernel<K, T, 2, true> : (need0 ? fdm_tma_kernel<K, T, 1, true> : fdm_tma_kernel<K, T, 0, true>)) :
+                                              (need1 ? fdm_tma_kernel<K, T, 2, false> : (need0 ? fdm_tma_kernel<K, T, 1, false> : fdm_tma_kernel<K, T, 0, false>));
     check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "fdm_tma_kernel attribute");
     check(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), "carveout");
     report_occupancy("fdm_tma_kernel", (const void *)kern, G::NT, smem);
