@@ -164,6 +164,23 @@ class Mesh:
         return dict(n_owned=n_owned, n_ghost=n_ghost, n_cells=n_cells, cidx_plain=cidx, peers=peers[:n_peers], send_count=sc[:n_peers],
                     recv_count=rc[:n_peers], send_idx=si[:ns], recv_idx=ri[:nr])
 
+    def host_halo_numbering(self, degree):
+        """host-only: the enlarged ghost layout (halo cells around the rank's box); cidx_plain / coords cover local + halo cells"""
+        sizes = (ctypes.c_longlong * 7)()
+        none = ctypes.c_void_p()
+        _check(lib().dasm_mesh_host_halo_numbering(self.h, int(degree), sizes, none, none, none, none, none, none, none))
+        n_owned, n_ghost, n_cells, n_halo, n_peers, ns, nr = [int(v) for v in sizes]
+        halo = np.zeros((max(n_halo, 1), 3), dtype=np.int32)
+        cidx = np.zeros((n_cells + n_halo, 27), dtype=np.uint32)
+        peers = np.zeros(max(n_peers, 1), dtype=np.int32)
+        sc, rc = np.zeros(max(n_peers, 1), dtype=np.int64), np.zeros(max(n_peers, 1), dtype=np.int64)
+        si, ri = np.zeros(max(ns, 1), dtype=np.uint32), np.zeros(max(nr, 1), dtype=np.uint32)
+        p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        _check(lib().dasm_mesh_host_halo_numbering(self.h, int(degree), sizes, p(halo), p(cidx), p(peers), p(sc), p(rc), p(si), p(ri)))
+        coords = np.concatenate([self.cell_coordinates(), halo[:n_halo]], axis=0)
+        return dict(n_owned=n_owned, n_ghost=n_ghost, n_cells=n_cells, n_halo=n_halo, coords=coords, cidx_plain=cidx, peers=peers[:n_peers],
+                    send_count=sc[:n_peers], recv_count=rc[:n_peers], send_idx=si[:ns], recv_idx=ri[:nr])
+
     def cell_coordinates(self):
         out = np.zeros((self.n_cells, 3), dtype=np.int32)
         lib().dasm_mesh_cell_coordinates(self.h, out.ctypes.data_as(ctypes.c_void_p))

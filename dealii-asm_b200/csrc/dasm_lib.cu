@@ -419,6 +419,11 @@ struct dasm_op
   bool              linear_geometry = false;
   CartesianCoef     cart;
   Exchange          exchange;
+  // enlarged ghost layout for preconditioners with overlapping patches on several ranks (matrix_free.h:154-213; the operator and
+  // the preconditioner share ONE vector layout, which is what set_partitioner, operator.h:780-849, establishes in the reference)
+  Mesh::HaloNumbering halo;
+  Exchange          exchange_ext; // all ghosts (those of `exchange` + the DoFs of the halo cells)
+  long long         n_ghost_ext = 0;
   std::vector<void *> scratch; // owned by op, freed at destroy
   // tuned brick path
   bool              use_brick = false;
@@ -469,6 +474,7 @@ struct dasm_fdm
 {
   dasm_op * op;
   int       n_overlap, weight_type, weight_sequence, element_centric;
+  bool      use_ext = false; // several ranks + overlapping patches: the enlarged ghost layout and its exchange
   int       m;          // 1-D patch size
   long long n_instances; // unique 1-D (S, lambda) instances
   uint32_t *d_inst   = nullptr;
@@ -1505,10 +1511,11 @@ fdm_vmult(dasm_fdm *f, T *dst, const T *src, const dasm_hook *pre, const dasm_ho
       return;
     }
   CUDA_CHECK(cudaMemsetAsync(dst, 0, (size_t)op->n_vec * sizeof(T), ctx->stream));
-  op->exchange.run<T>(const_cast<T *>(src), false);
+  Exchange &ex = f->use_ext ? op->exchange_ext : op->exchange; // overlapping patches reach into the cells of the neighbour ranks
+  ex.run<T>(const_cast<T *>(src), false);
   launch_fdm<T>(f, dst, src);
   if (fdm_needs_compression(f))
-    op->exchange.run<T>(dst, true);
+    ex.run<T>(dst, true);
   // post hook without the constrained-DoF copy: the preconditioner leaves constrained DoFs at zero
   if (post != nullptr && post->kind != DASM_HOOK_NONE)
     {
@@ -1930,6 +1937,64 @@ dasm_mesh_host_numbering(const dasm_mesh *mesh, int degree, long long sizes[6], 
   DASM_API_END
 }
 
+// Host-only view of the enlarged ghost layout (Mesh::halo_numbering): halo cells, their index rows and the exchange lists of ALL
+// ghosts.  sizes = {n_owned, n_ghost (old + new), n_local_cells, n_halo_cells, n_peers, n_send_total, n_recv_total}; cidx_plain has
+// (n_local_cells + n_halo_cells) * 27 entries (local cells first).
+extern "C" int
+dasm_mesh_host_halo_numbering(const dasm_mesh *mesh, int degree, long long sizes[7], int *halo_cells, unsigned int *cidx_plain, int *peers,
+                              long long *send_count, long long *recv_count, unsigned int *send_idx, unsigned int *recv_idx)
+{
+  DASM_API_BEGIN
+  DASM_REQUIRE(mesh != nullptr && degree >= 1 && degree <= MAX_DEGREE, "invalid arguments");
+  const Mesh::Numbering     nb = mesh->mesh->number_dofs(degree);
+  const Mesh::HaloNumbering h  = mesh->mesh->halo_numbering(nb);
+  long long                 ns = 0, nr = 0;
+  for (const ExchangeList &l : h.exchange)
+    {
+      ns += (long long)l.n_send;
+      nr += (long long)l.n_recv;
+    }
+  if (sizes)
+    {
+      sizes[0] = nb.n_owned;
+      sizes[1] = (long long)nb.n_ghost + h.n_ghost_ext;
+      sizes[2] = (long long)mesh->mesh->n_cells;
+      sizes[3] = (long long)h.cells.size();
+      sizes[4] = (long long)h.exchange.size();
+      sizes[5] = ns;
+      sizes[6] = nr;
+    }
+  if (halo_cells)
+    for (size_t i = 0; i < h.cells.size(); ++i)
+      for (int d = 0; d < 3; ++d)
+        halo_cells[3 * i + d] = h.cells[i][d];
+  if (cidx_plain)
+    {
+      std::copy(nb.cidx_plain.begin(), nb.cidx_plain.end(), cidx_plain);
+      std::copy(h.cidx_plain.begin(), h.cidx_plain.end(), cidx_plain + nb.cidx_plain.size());
+    }
+  size_t so = 0, ro = 0;
+  for (size_t p = 0; p < h.exchange.size(); ++p)
+    {
+      const ExchangeList &l = h.exchange[p];
+      if (peers)
+        peers[p] = l.peer;
+      if (send_count)
+        send_count[p] = (long long)l.n_send;
+      if (recv_count)
+        recv_count[p] = (long long)l.n_recv;
+      if (send_idx)
+        for (size_t r = 0; r < l.send_start.size(); ++r)
+          for (uint32_t i = 0; i < l.send_len[r]; ++i)
+            send_idx[so++] = l.send_start[r] + i;
+      if (recv_idx)
+        for (size_t r = 0; r < l.recv_start.size(); ++r)
+          for (uint32_t i = 0; i < l.recv_len[r]; ++i)
+            recv_idx[ro++] = l.recv_start[r] + i;
+    }
+  DASM_API_END
+}
+
 extern "C" int
 dasm_test_eo_pack(int n, int kind, const double *A, double *P, double *Q)
 {
@@ -1997,7 +2062,12 @@ dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping
   op->n_cells          = (long long)M.n_cells;
   op->n_owned          = op->nb.n_owned;
   op->n_ghost          = op->nb.n_ghost;
-  op->n_vec            = op->n_owned + op->n_ghost;
+  if (M.n_ranks() > 1 && !(getenv("DASM_NO_HALO") && getenv("DASM_NO_HALO")[0] == '1'))
+    {
+      op->halo        = M.halo_numbering(op->nb);
+      op->n_ghost_ext = op->halo.n_ghost_ext;
+    }
+  op->n_vec            = op->n_owned + op->n_ghost + op->n_ghost_ext;
   {
     long long g = 1;
     for (int d = 0; d < 3; ++d)
@@ -2008,6 +2078,8 @@ dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping
   op->d_constrained = dev_upload(op->nb.constrained, ctx->stream);
   op->n_constrained = (long long)op->nb.constrained.size();
   op->exchange.init(ctx, op->nb.exchange, op->esize());
+  if (!op->halo.exchange.empty())
+    op->exchange_ext.init(ctx, op->halo.exchange, op->esize());
   // geometry
   const int n3 = (degree + 1) * (degree + 1) * (degree + 1);
   if (M.is_cartesian() && mt == "")
@@ -2592,6 +2664,7 @@ dasm_op_destroy(dasm_op *op)
   for (void *p : op->d_map_bufs)
     cudaFree(p);
   op->exchange.destroy();
+  op->exchange_ext.destroy();
   for (void *p : op->scratch)
     cudaFree(p);
   delete op;
@@ -2911,10 +2984,11 @@ fdm_setup_device(dasm_fdm *f, const std::vector<double> &S, const std::vector<do
     }
   valence_kernel<T><<<nblocks(n_entries), 256, 0, ctx->stream>>>(w, compressed_idx ? d_full : f->d_pidx, n_entries);
   ctx->launches += 2;
-  op->exchange.run<T>(w, true);
+  Exchange &ex = f->use_ext ? op->exchange_ext : op->exchange;
+  ex.run<T>(w, true);
   weights_from_valence_kernel<T><<<nblocks(op->n_owned), 256, 0, ctx->stream>>>(w, f->weight_type == DASM_WEIGHT_SYMM ? 1 : 0, op->n_owned);
   ctx->launches++;
-  op->exchange.run<T>(w, false);
+  ex.run<T>(w, false);
   f->d_wvec = w;
   {
     std::vector<T> hw(op->n_owned);
@@ -2959,8 +3033,9 @@ dasm_fdm_create(dasm_op *op, int n_overlap, int sub_mesh_approximation, int weig
   const int k = op->k;
   n_overlap   = std::min(std::max(n_overlap, 1), k); // precondition.templates.h:195-196
   const Mesh &M = *op->mesh->mesh;
-  if (n_overlap > 1 || !element_centric)
-    DASM_REQUIRE(M.n_ranks() == 1, "n overlap > 1 / vertex patches on several ranks are not implemented in libdasm yet");
+  if ((n_overlap > 1 || !element_centric) && M.n_ranks() > 1)
+    DASM_REQUIRE(!op->halo.exchange.empty() || op->halo.cells.empty(),
+                 "n overlap > 1 / vertex patches on several ranks need the enlarged ghost layout (DASM_NO_HALO is set)");
   if (!element_centric)
     {
       DASM_REQUIRE(weight_type != DASM_WEIGHT_RAS, "RAS weighting with vertex patches is not implemented in libdasm yet");
@@ -2968,6 +3043,7 @@ dasm_fdm_create(dasm_op *op, int n_overlap, int sub_mesh_approximation, int weig
     }
   auto f             = new dasm_fdm;
   f->op              = op;
+  f->use_ext         = (n_overlap > 1 || !element_centric) && M.n_ranks() > 1;
   f->n_overlap       = n_overlap;
   f->weight_type     = weight_type;
   f->weight_sequence = weight_sequence;
@@ -3054,12 +3130,16 @@ dasm_fdm_create(dasm_op *op, int n_overlap, int sub_mesh_approximation, int weig
     {
       const int n = k + 1, n3 = n * n * n, m3 = m * m * m;
       // expand the plain compressed indices of every cell on the host
-      std::vector<uint32_t> full((size_t)op->n_cells * n3);
+      // (several ranks: the cells around the rank's box - halo cells - follow the local cells)
+      const long long n_halo = f->use_ext ? (long long)op->halo.cells.size() : 0;
+      std::vector<uint32_t> full((size_t)(op->n_cells + n_halo) * n3);
       std::map<std::array<int, 3>, long long> cell_of;
-      for (long long c = 0; c < op->n_cells; ++c)
+      for (long long c = 0; c < op->n_cells + n_halo; ++c)
         {
-          cell_of[{M.cell_ijk[c][0], M.cell_ijk[c][1], M.cell_ijk[c][2]}] = c;
-          const uint32_t *ci = op->nb.cidx.data() + c * 27;
+          const bool      loc = c < op->n_cells;
+          const auto &    cc  = loc ? M.cell_ijk[c] : op->halo.cells[c - op->n_cells];
+          cell_of[{cc[0], cc[1], cc[2]}] = c;
+          const uint32_t *ci = loc ? op->nb.cidx.data() + c * 27 : op->halo.cidx.data() + (c - op->n_cells) * 27;
           for (int z = 0; z < n; ++z)
             for (int y = 0; y < n; ++y)
               for (int x = 0; x < n; ++x)

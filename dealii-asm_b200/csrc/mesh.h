@@ -32,6 +32,7 @@
 #include <cstring>
 #include <functional>
 #include <map>
+#include <set>
 #include <stdexcept>
 #include <vector>
 
@@ -750,6 +751,249 @@ namespace dasm
             }
         }
       return nb;
+    }
+
+    // ---- enlarged ghost layout (include/matrix_free.h:154-213 of the reference: the partitioner of a preconditioner with
+    // overlapping patches holds, besides the ghost DoFs of the operator, all DoFs of the cells around the rank's cells) ------------
+    // Halo cells = cells of other ranks adjacent (face, edge, corner) to a local cell.  Their 27 start indices point to owned DoFs,
+    // to the ghost DoFs of `nb` or to NEW ghost DoFs appended behind them (grouped by owner rank, ordered by owner cell and entity
+    // like the ghosts of number_dofs).  `exchange` lists ALL ghosts (old and new) per peer, both sides ordered by the same key.
+    struct HaloNumbering
+    {
+      std::vector<std::array<int, 3>> cells;      // global coordinates of the halo cells
+      std::vector<uint32_t>           cidx;       // [halo cell * 27 + e], INVALID if constrained
+      std::vector<uint32_t>           cidx_plain;
+      uint32_t                        n_ghost_ext = 0; // new ghost DoFs (behind n_owned + n_ghost)
+      std::vector<ExchangeList>       exchange;
+    };
+
+    HaloNumbering
+    halo_numbering(const Numbering &nb) const
+    {
+      HaloNumbering h;
+      if (n_ranks() == 1)
+        return h;
+      const int k       = nb.k;
+      const int my_rank = p.rank;
+      std::vector<uint32_t> proc_of_local(n_cells);
+      for (size_t i = 0; i < n_cells; ++i)
+        {
+          const auto &c = cell_ijk[i];
+          proc_of_local[((size_t)(c[2] - lo[2]) * nl[1] + (c[1] - lo[1])) * nl[0] + (c[0] - lo[0])] = i;
+        }
+      auto is_local = [&](const int c[3]) {
+        return c[0] >= lo[0] && c[0] < hi[0] && c[1] >= lo[1] && c[1] < hi[1] && c[2] >= lo[2] && c[2] < hi[2];
+      };
+      auto local_index = [&](const int c[3]) {
+        return (size_t)proc_of_local[((size_t)(c[2] - lo[2]) * nl[1] + (c[1] - lo[1])) * nl[0] + (c[0] - lo[0])];
+      };
+      // owner cell, entity code relative to it and owner rank of entity e of cell c
+      auto owner_of = [&](const int c[3], const int e, int s[3], int oc[3], int &eo) {
+        cell_slot(c, e, s);
+        owner_cell(s, oc);
+        eo = 0;
+        for (int d = 2; d >= 0; --d)
+          eo = eo * 3 + (s[d] - 2 * oc[d]);
+        return rank_of_cell(oc);
+      };
+      auto gid_of = [&](const int c[3]) { return ((long)c[2] * p.nc[1] + c[1]) * p.nc[0] + c[0]; };
+      // ghosts of nb by key
+      std::map<std::array<long, 3>, uint32_t> ghosts;
+      for (size_t i = 0; i < n_cells; ++i)
+        {
+          const int c[3] = {cell_ijk[i][0], cell_ijk[i][1], cell_ijk[i][2]};
+          for (int e = 0; e < 27; ++e)
+            {
+              int       s[3], oc[3], eo;
+              const int orank = owner_of(c, e, s, oc, eo);
+              if (orank != my_rank)
+                ghosts[{(long)orank, gid_of(oc), (long)eo}] = nb.cidx_plain[i * 27 + e];
+            }
+        }
+      // halo cells
+      std::set<std::array<int, 3>> halo;
+      for (int z = lo[2] - 1; z <= hi[2]; ++z)
+        for (int y = lo[1] - 1; y <= hi[1]; ++y)
+          for (int x = lo[0] - 1; x <= hi[0]; ++x)
+            {
+              int  c[3] = {x, y, z};
+              bool ok   = true;
+              for (int d = 0; d < 3 && ok; ++d)
+                if (c[d] < 0 || c[d] >= p.nc[d])
+                  {
+                    if (!p.periodic[d])
+                      ok = false;
+                    else
+                      c[d] = (c[d] + p.nc[d]) % p.nc[d];
+                  }
+              if (ok && !is_local(c))
+                halo.insert({c[0], c[1], c[2]});
+            }
+      h.cells.assign(halo.begin(), halo.end());
+      // new ghosts
+      std::map<std::array<long, 3>, uint32_t> fresh;
+      for (const auto &hc : h.cells)
+        {
+          const int c[3] = {hc[0], hc[1], hc[2]};
+          for (int e = 0; e < 27; ++e)
+            {
+              int       s[3], oc[3], eo;
+              const int orank = owner_of(c, e, s, oc, eo);
+              if (orank == my_rank)
+                continue;
+              const std::array<long, 3> key = {(long)orank, gid_of(oc), (long)eo};
+              if (!ghosts.count(key))
+                fresh[key] = 0;
+            }
+        }
+      uint32_t next = nb.n_owned + nb.n_ghost;
+      for (auto &kv : fresh)
+        {
+          kv.second = next;
+          next += entity_size((int)kv.first[2], k);
+        }
+      h.n_ghost_ext = next - (nb.n_owned + nb.n_ghost);
+      if (next >= LEX_FLAG)
+        throw std::runtime_error("too many DoFs per rank for 31-bit start indices");
+      // index rows of the halo cells
+      h.cidx.assign(h.cells.size() * 27, INVALID_INDEX);
+      h.cidx_plain.assign(h.cells.size() * 27, INVALID_INDEX);
+      for (size_t i = 0; i < h.cells.size(); ++i)
+        {
+          const int c[3] = {h.cells[i][0], h.cells[i][1], h.cells[i][2]};
+          for (int e = 0; e < 27; ++e)
+            {
+              int       s[3], oc[3], eo;
+              const int orank = owner_of(c, e, s, oc, eo);
+              uint32_t  idx;
+              if (orank == my_rank)
+                idx = nb.cidx_plain[local_index(oc) * 27 + eo];
+              else
+                {
+                  const std::array<long, 3> key = {(long)orank, gid_of(oc), (long)eo};
+                  const auto                it  = ghosts.find(key);
+                  idx                           = it != ghosts.end() ? it->second : fresh[key];
+                }
+              h.cidx_plain[i * 27 + e] = idx;
+              if (!slot_on_dirichlet_boundary(s))
+                h.cidx[i * 27 + e] = idx;
+            }
+        }
+      // receive lists: all ghosts per owner rank in key order
+      std::map<std::array<long, 3>, uint32_t> all(ghosts);
+      all.insert(fresh.begin(), fresh.end());
+      {
+        int           cur_rank = -1;
+        ExchangeList *cur      = nullptr;
+        for (const auto &kv : all)
+          {
+            const int sz = entity_size((int)kv.first[2], k);
+            if ((int)kv.first[0] != cur_rank)
+              {
+                cur_rank = (int)kv.first[0];
+                h.exchange.emplace_back();
+                cur       = &h.exchange.back();
+                cur->peer = cur_rank;
+              }
+            if (sz > 0)
+              {
+                cur->recv_start.push_back(kv.second);
+                cur->recv_len.push_back(sz);
+                cur->n_recv += sz;
+              }
+          }
+      }
+      // send lists: owned entities touched by a cell inside the grown box of another rank
+      std::map<int, std::map<std::array<long, 3>, uint32_t>> send;
+      for (size_t i = 0; i < n_cells; ++i)
+        {
+          const int c[3] = {cell_ijk[i][0], cell_ijk[i][1], cell_ijk[i][2]};
+          bool      near_boundary = false;
+          for (int d = 0; d < 3; ++d)
+            if (c[d] - lo[d] < 2 || hi[d] - c[d] <= 2)
+              near_boundary = true;
+          if (!near_boundary)
+            continue;
+          for (int e = 0; e < 27; ++e)
+            {
+              bool owned = true;
+              for (int d = 0, ee = e; d < 3; ++d, ee /= 3)
+                if (ee % 3 == 2 && !(!p.periodic[d] && c[d] == p.nc[d] - 1))
+                  owned = false;
+              if (!owned || entity_size(e, k) == 0)
+                continue;
+              int s[3];
+              cell_slot(c, e, s);
+              // cells within one cell of a cell touching the slot: per direction the range [first touching - 1, last touching + 1]
+              int cand[3][4], ncand[3];
+              for (int d = 0; d < 3; ++d)
+                {
+                  ncand[d]     = 0;
+                  const int t0 = (s[d] % 2 == 1) ? s[d] / 2 : s[d] / 2 - 1, t1 = s[d] / 2;
+                  for (int v = t0 - 1; v <= t1 + 1; ++v)
+                    {
+                      int w = v;
+                      if (p.periodic[d])
+                        w = ((w % p.nc[d]) + p.nc[d]) % p.nc[d];
+                      else if ((s[d] % 2 == 0) && (v == t1) && t1 >= p.nc[d])
+                        continue; // (upper boundary slot: the cell above does not exist)
+                      if (w < 0 || w >= p.nc[d])
+                        continue;
+                      bool dup = false;
+                      for (int q = 0; q < ncand[d]; ++q)
+                        if (cand[d][q] == w)
+                          dup = true;
+                      if (!dup)
+                        cand[d][ncand[d]++] = w;
+                    }
+                }
+              const long gid = gid_of(c);
+              for (int a = 0; a < ncand[0]; ++a)
+                for (int b2 = 0; b2 < ncand[1]; ++b2)
+                  for (int g = 0; g < ncand[2]; ++g)
+                    {
+                      const int tc[3] = {cand[0][a], cand[1][b2], cand[2][g]};
+                      const int q     = rank_of_cell(tc);
+                      if (q != my_rank)
+                        send[q][{(long)my_rank, gid, (long)e}] = nb.cidx_plain[i * 27 + e];
+                    }
+            }
+        }
+      for (auto &pr : send)
+        {
+          ExchangeList *ex = nullptr;
+          for (auto &x : h.exchange)
+            if (x.peer == pr.first)
+              ex = &x;
+          if (!ex)
+            {
+              h.exchange.emplace_back();
+              ex       = &h.exchange.back();
+              ex->peer = pr.first;
+            }
+          for (auto &kv : pr.second)
+            {
+              const int      e   = (int)kv.first[2];
+              const uint32_t st  = kv.second;
+              const int      ex1 = (e % 3 == 1) ? k - 1 : 1, ey1 = ((e / 3) % 3 == 1) ? k - 1 : 1, ez1 = (e / 9 == 1) ? k - 1 : 1;
+              if (st & LEX_FLAG)
+                {
+                  for (int l = 0; l < ez1; ++l)
+                    for (int j = 0; j < ey1; ++j)
+                      {
+                        ex->send_start.push_back((st & ~LEX_FLAG) + 4 * k * (j + 4 * k * l));
+                        ex->send_len.push_back((uint32_t)ex1);
+                      }
+                }
+              else
+                {
+                  ex->send_start.push_back(st);
+                  ex->send_len.push_back((uint32_t)(ex1 * ey1 * ez1));
+                }
+              ex->n_send += (size_t)ex1 * ey1 * ez1;
+            }
+        }
+      return h;
     }
   };
 } // namespace dasm

@@ -136,6 +136,13 @@ extern "C"
   int dasm_mesh_host_numbering(const dasm_mesh *mesh, int degree, long long sizes[6], unsigned int *cidx_plain, int *peers,
                                long long *send_count, long long *recv_count, unsigned int *send_idx, unsigned int *recv_idx);
 
+  /* The same for the enlarged ghost layout a preconditioner with overlapping patches needs on several ranks (include/matrix_free.h:154-213:
+   * all DoFs of the cells around the rank's cells are ghosts): sizes = {n_owned, n_ghost (old + new), n_local_cells, n_halo_cells,
+   * n_peers, n_send_total, n_recv_total}; halo_cells[n_halo_cells*3] global coordinates; cidx_plain[(n_local_cells + n_halo_cells)*27]. */
+  int dasm_mesh_host_halo_numbering(const dasm_mesh *mesh, int degree, long long sizes[7], int *halo_cells, unsigned int *cidx_plain,
+                                    int *peers, long long *send_count, long long *recv_count, unsigned int *send_idx,
+                                    unsigned int *recv_idx);
+
   /* Host-only test hook: even-odd blocks (m x m block P on the even parts, h x h block Q on the odd parts, m = ceil(n/2),
    * h = floor(n/2)) of an n x n 1-D matrix as the warp-specialised kernels use them.  kind 0: centrosymmetric matrix
    * (mass / stiffness), 1: forward eigenvector matrix (rows = eigen index, even eigenvectors first), 2: backward.
@@ -178,7 +185,9 @@ extern "C"
   int dasm_op_vec_download(dasm_op *op, double *host_owned, const void *dev);
 
   /* ---- ASPoissonPreconditioner (include/matrix_free.h:63-1568) ------------------------------- */
-  /* create_fdm_preconditioner, precondition.templates.h:162-247, + ctor matrix_free.h:73-894 */
+  /* create_fdm_preconditioner, precondition.templates.h:162-247, + ctor matrix_free.h:73-894.  On several ranks n_overlap > 1 and
+   * vertex patches use the enlarged ghost layout of the operator (every vector of dasm_op_vec_size() entries already holds it; this
+   * replaces set_partitioner, operator.h:780-849) */
   int dasm_fdm_create(dasm_op *op, int n_overlap, int sub_mesh_approximation, int weight_type, int weight_sequence,
                       int overlap_pre_post, int element_centric, dasm_fdm **out);
   int dasm_fdm_destroy(dasm_fdm *fdm);

@@ -62,15 +62,24 @@ def main():
     for k, number, nc, wt in ((4, "double", (8, 8, 8), "symm"), (3, "double", (8, 6, 4), "post"), (2, "double", (8, 8, 8), "none"),
                               (4, "double", (24, 8, 8), "symm"), (3, "float", (24, 8, 8), "post"), (4, "double", (16, 16, 16), "symm"),
                               (3, "double", (16, 16, 16), "ras"), (2, "double", (8, 8, 8), "ras")) + \
-            (((4, "double", (32, 32, 32), "symm"), (3, "float", (32, 32, 16), "post")) if world >= 4 else ()):  # interior bricks on every rank of 2 x 2 x 2
+            (((4, "double", (32, 32, 32), "symm"), (3, "float", (32, 32, 16), "post")) if world >= 4 else ()) + \
+            ((3, "double", (8, 8, 8), "symm-2"), (2, "double", (8, 4, 6), "post-2"), (3, "double", (8, 4, 4), "post-3"),
+             (2, "double", (8, 8, 4), "post-v"), (3, "float", (8, 6, 4), "symm-v")):
+        # "<weighting>-<n overlap>" / "<weighting>-v" (vertex patches): overlapping patches reach into the cells of the neighbour
+        # ranks (enlarged ghost layout, include/matrix_free.h:154-213; labels *-2-g-p-n / *-v-c of matrix_free_loop_08)
+        fdm_params = {"weighting type": wt.split("-")[0]}
+        if wt.endswith("-v"):
+            fdm_params["element centric"] = False
+        elif "-" in wt:
+            fdm_params["n overlap"] = int(wt.split("-")[1])
         L = tuple(float(c) / 4 for c in nc)
         vsize = None
         results = {}
         for tag, prt, rk, c in (("multi", part, rank, ctx), ("single", (1, 1, 1), 0, pkg.Context(local_rank))):
             mesh = pkg.Mesh(c, nc, periodic=(1, 1, 1), length=L, partition=prt, rank=rk)
             op = pkg.LaplaceOperatorMatrixFree(mesh, k, number)
-            fdm = pkg.create_fdm_preconditioner(op, {"weighting type": wt})
-            cheb = pkg.PreconditionChebyshev(op, fdm, degree=3)
+            fdm = pkg.create_fdm_preconditioner(op, fdm_params)
+            cheb = pkg.PreconditionChebyshev(op, fdm, degree=3, optimize=2 if len(fdm_params) == 1 else 1)
             cheb.set_eigenvalues(1.0, 2.4)
             coords, idx, vals = cell_local_values(pkg, mesh, op, k, L, nc)
             nvec = op.vec_size()

@@ -24,7 +24,7 @@ def _field(pos, L):
     return np.sin(2 * np.pi * pos[..., 0] / L[0]) + 0.5 * np.cos(2 * np.pi * pos[..., 1] / L[1]) * (1 + pos[..., 2] / L[2])
 
 
-def _worker(rank, world, port, nc, periodic, k, result, part=(2, 1, 1)):
+def _worker(rank, world, port, nc, periodic, k, result, part=(2, 1, 1), halo=False):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import dasm_oracle as o  # only index expansion and Gauss-Lobatto points
@@ -36,11 +36,11 @@ def _worker(rank, world, port, nc, periodic, k, result, part=(2, 1, 1)):
     try:
         L = tuple(float(c) for c in nc)
         mesh = pkg.Mesh(None, nc, periodic=periodic, dirichlet=False, length=L, partition=part, rank=rank)
-        nb = mesh.host_numbering(k)
+        nb = mesh.host_halo_numbering(k) if halo else mesh.host_numbering(k)
         n_owned, n_ghost = nb["n_owned"], nb["n_ghost"]
         n = k + 1
         idx = o.expand_compressed(nb["cidx_plain"], k, 3).astype(np.int64)  # [cells, n^3]
-        coords = mesh.cell_coordinates()
+        coords = nb["coords"] if halo else mesh.cell_coordinates()
         gll = o.gauss_lobatto_points(n)
         zz, yy, xx = np.meshgrid(gll, gll, gll, indexing="ij")
         ref = np.stack([xx.reshape(-1), yy.reshape(-1), zz.reshape(-1)], axis=-1)
@@ -54,6 +54,7 @@ def _worker(rank, world, port, nc, periodic, k, result, part=(2, 1, 1)):
         own = idx < n_owned
         x[idx[own]] = vals[own]
         assert not np.isnan(x[:n_owned]).any()  # every owned DoF is touched by a local cell
+        assert idx.max() == n_owned + n_ghost - 1 or n_ghost == 0  # (the cells reach the last ghost)
         so = ro = 0
         for p, ns, nr in zip(nb["peers"], nb["send_count"], nb["recv_count"]):
             send = torch.from_numpy(np.ascontiguousarray(x[nb["send_idx"][so:so + ns]]))
@@ -105,3 +106,25 @@ def test_ghost_exchange_lists(nc, periodic, k, part):
         assert added == n_ghost_total            # every ghost copy arrives exactly once at an owner
         assert n_owned_total == n_dofs_expected  # the owned ranges partition the global DoFs
         assert mx <= world - 1                   # at most one ghost copy per other rank
+
+
+@pytest.mark.parametrize("nc,periodic,k,part", [((8, 4, 4), (1, 1, 1), 3, (2, 1, 1)), ((6, 3, 2), (0, 0, 0), 2, (2, 1, 1)),
+                                                ((8, 8, 4), (1, 0, 1), 2, (2, 2, 1)), ((4, 6, 4), (0, 1, 0), 3, (1, 2, 2))])
+def test_enlarged_ghost_layout(nc, periodic, k, part):
+    """the partitioner of a preconditioner with overlapping patches (include/matrix_free.h:154-213): all DoFs of the cells around a
+    rank's cells are ghosts; values seen through local AND halo cells are the owner's after the exchange, compress conserves."""
+    world = part[0] * part[1] * part[2]
+    port = 29300 + (os.getpid() + 11 * k) % 250
+    mgr = mp.get_context("spawn").Manager()
+    result = mgr.dict()
+    mp.spawn(_worker, args=(world, port, nc, periodic, k, result, part, True), nprocs=world, join=True)
+    assert len(result) == world
+    n_dofs_expected = 1
+    for d in range(3):
+        n_dofs_expected *= nc[d] * k + (0 if periodic[d] else 1)
+    for rank in range(world):
+        err, added, n_ghost_total, n_owned_total, mx = result[rank]
+        assert err < 1e-14
+        assert added == n_ghost_total
+        assert n_owned_total == n_dofs_expected
+        assert mx <= world - 1
