@@ -715,6 +715,12 @@ launch_laplace(dasm_op *op, T *dst, const T *src)
         CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, CPB * n * n, smem, ctx->stream>>>(src, dst, op->d_cidx, (const T *)nullptr, op->cart, op->n_cells);
       }
+    else if (op->geom_mode == 3)
+      {
+        auto kern = laplace_generic_kernel<K, T, 2>;
+        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, CPB * n * n, smem, ctx->stream>>>(src, dst, op->d_cidx, (const T *)op->d_geom, op->cart, op->n_cells);
+      }
     else
       {
         auto kern = laplace_generic_kernel<K, T, 1>;
@@ -2044,9 +2050,7 @@ dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping
   DASM_REQUIRE(degree >= 1 && degree <= MAX_DEGREE, "degree must be in 1..8");
   DASM_REQUIRE(number_type == DASM_F64 || number_type == DASM_F32, "unknown number type");
   const std::string mt = mapping_type ? mapping_type : "";
-  if (mt == "construct q")
-    throw std::runtime_error("Mapping type <" + mt + "> is not implemented in libdasm yet");
-  if (mt != "" && mt != "merged" && mt != "quadratic geometry" && mt != "linear geometry")
+  if (mt != "" && mt != "merged" && mt != "quadratic geometry" && mt != "linear geometry" && mt != "construct q")
     throw std::runtime_error("Mapping type <" + mt + "> is not known!"); // operator.h:747-752
   dasm_ctx *ctx = mesh->ctx;
   CUDA_CHECK(cudaSetDevice(ctx->device));
@@ -2092,9 +2096,30 @@ dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping
     }
   else
     {
-      op->geom_mode       = (mt == "quadratic geometry" || mt == "linear geometry") ? 2 : 1;
+      op->geom_mode       = (mt == "quadratic geometry" || mt == "linear geometry") ? 2 : (mt == "construct q" ? 3 : 1);
       op->linear_geometry = (mt == "linear geometry");
       const bool lingeo   = op->linear_geometry;
+      if (op->geom_mode == 3)
+        {
+          // "construct q" (operator.h:712-746): 3 n^3 coordinates of the quadrature points per cell; the Jacobians are rebuilt in
+          // the kernels by collocation differentiation (generic kernels; the brick kernels have no such geometry mode)
+          std::vector<double> xq((size_t)op->n_cells * 3 * n3);
+          for (long long c = 0; c < op->n_cells; ++c)
+            {
+              const int cc[3] = {M.cell_ijk[c][0], M.cell_ijk[c][1], M.cell_ijk[c][2]};
+              M.quadrature_points(cc, op->basis, xq.data() + (size_t)c * 3 * n3);
+            }
+          if (number_type == DASM_F64)
+            op->d_geom = dev_upload(xq, ctx->stream);
+          else
+            {
+              std::vector<float> xf(xq.begin(), xq.end());
+              op->d_geom = dev_upload(xf, ctx->stream);
+            }
+          op->cart.g[0] = op->cart.g[1] = op->cart.g[2] = 0;
+        }
+      else
+        {
       if (op->geom_mode == 2)
         {
           std::vector<double> qc((size_t)op->n_cells * 81);
@@ -2135,6 +2160,7 @@ dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping
           op->d_geom = dev_upload(g, ctx->stream);
         }
       op->cart.g[0] = op->cart.g[1] = op->cart.g[2] = 0;
+        }
     }
   // tuned brick path: degrees 1..5, one rank (the multi-rank path uses the generic kernels for now)
   {
@@ -2142,7 +2168,7 @@ dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping
     // (degree 5 runs faster through the generic kernels: 1.70e10 vs 1.24e10 DoFs/s per Chebyshev term, profiles/r01c_secondary.log;
     // DASM_BRICK_K5=1 selects the 4x4x2 brick kernels)
     const char *k5    = getenv("DASM_BRICK_K5");
-    op->use_brick     = (degree <= 4 || (degree == 5 && k5 && k5[0] == '1')) && !(force && force[0] == '1');
+    op->use_brick     = (degree <= 4 || (degree == 5 && k5 && k5[0] == '1')) && !(force && force[0] == '1') && op->geom_mode != 3;
     const char *nofast_hi = getenv("DASM_NO_FAST");
     if (!op->use_brick && (degree == 5 || degree == 6) && !(force && force[0] == '1') && !(nofast_hi && nofast_hi[0] == '1'))
       setup_tma_only(op);
@@ -2746,6 +2772,8 @@ op_inverse_diagonal(dasm_op *op, T *diag)
     const long long total = op->n_cells * n3;
     if (op->geom_mode == 0)
       laplace_diagonal_kernel<K, T, 0><<<nblocks(total, 128), 128, 0, ctx->stream>>>(diag, op->d_cidx, (const T *)nullptr, op->cart, op->n_cells);
+    else if (op->geom_mode == 3)
+      laplace_diagonal_kernel<K, T, 2><<<nblocks(total, 128), 128, 0, ctx->stream>>>(diag, op->d_cidx, (const T *)op->d_geom, op->cart, op->n_cells);
     else
       laplace_diagonal_kernel<K, T, 1><<<nblocks(total, 128), 128, 0, ctx->stream>>>(diag, op->d_cidx, (const T *)op->d_geom, op->cart, op->n_cells);
   });

@@ -171,8 +171,54 @@ namespace dasm
     double g[3]; // diag of  det * J^-1 J^-T  (without quadrature weight)
   };
 
+  // "construct q" (operator.h:712-746, 1221-1333): the cell stores the coordinates of its quadrature points, X[e][q]; the Jacobian
+  // at a point is the collocation derivative of the coordinate field, G = JxW J^-1 J^-T is rebuilt per point (order xx xy xz yy yz zz)
+  template <int k, typename T, typename Basis>
+  __device__ __forceinline__ void
+  construct_q_coefficients(const T *__restrict__ X, const int qx, const int qy, const int qz, const Basis &B, T (&G)[6])
+  {
+    constexpr int n = k + 1, n3 = n * n * n;
+    T             J[3][3]; // J[e][d] = d x_e / d xi_d
+#pragma unroll
+    for (int e = 0; e < 3; ++e)
+      {
+        const T *Xe = X + e * n3;
+        T        s0 = 0, s1 = 0, s2 = 0;
+#pragma unroll
+        for (int i = 0; i < n; ++i)
+          {
+            s0 += B.Dq[qx * n + i] * Xe[(qz * n + qy) * n + i];
+            s1 += B.Dq[qy * n + i] * Xe[(qz * n + i) * n + qx];
+            s2 += B.Dq[qz * n + i] * Xe[(i * n + qy) * n + qx];
+          }
+        J[e][0] = s0;
+        J[e][1] = s1;
+        J[e][2] = s2;
+      }
+    const T det = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) - J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0]) +
+                  J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+    const T id = T(1) / det;
+    T       I[3][3]; // inverse: I[d][e] = d xi_d / d x_e
+    I[0][0] = (J[1][1] * J[2][2] - J[1][2] * J[2][1]) * id;
+    I[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * id;
+    I[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * id;
+    I[1][0] = (J[1][2] * J[2][0] - J[1][0] * J[2][2]) * id;
+    I[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * id;
+    I[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * id;
+    I[2][0] = (J[1][0] * J[2][1] - J[1][1] * J[2][0]) * id;
+    I[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * id;
+    I[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * id;
+    const T jxw = det * B.qw[qx] * B.qw[qy] * B.qw[qz];
+    int     cc  = 0;
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+#pragma unroll
+      for (int e = d; e < 3; ++e, ++cc)
+        G[cc] = jxw * (I[d][0] * I[e][0] + I[d][1] * I[e][1] + I[d][2] * I[e][2]);
+  }
+
   // ---- K1: Laplace cell kernel (generic) ---------------------------------------------------------
-  // GEOM 0: uniform Cartesian (3 constants), 1: merged coefficients geom[cell][6][n^3]
+  // GEOM 0: uniform Cartesian (3 constants), 1: merged coefficients geom[cell][6][n^3], 2: construct q, geom[cell][3][n^3]
   template <int k, typename T, int GEOM>
   __global__ void __launch_bounds__(cells_per_block<k>() * (k + 1) * (k + 1))
   laplace_generic_kernel(const T *__restrict__ src,
@@ -249,13 +295,21 @@ namespace dasm
                 GY[q]     = T(cart.g[1]) * w * gy;
                 GZ[q]     = T(cart.g[2]) * w * gz;
               }
-            else
+            else if (GEOM == 1)
               {
                 const T *G   = geom + (size_t)cell * 6 * n3 + q;
                 const T  gxx = G[0], gxy = G[n3], gxz = G[2 * n3], gyy = G[3 * n3], gyz = G[4 * n3], gzz = G[5 * n3];
                 GX[q]        = gxx * gx + gxy * gy + gxz * gz;
                 GY[q]        = gxy * gx + gyy * gy + gyz * gz;
                 GZ[q]        = gxz * gx + gyz * gy + gzz * gz;
+              }
+            else
+              {
+                T G[6];
+                construct_q_coefficients<k, T>(geom + (size_t)cell * 3 * n3, x, a, b, B, G);
+                GX[q] = G[0] * gx + G[1] * gy + G[2] * gz;
+                GY[q] = G[1] * gx + G[3] * gy + G[4] * gz;
+                GZ[q] = G[2] * gx + G[4] * gy + G[5] * gz;
               }
           }
       }
@@ -322,12 +376,19 @@ namespace dasm
                 const double w = (double)B.qw[qx] * (double)B.qw[qy] * (double)B.qw[qz];
                 s += w * (cart.g[0] * gx * gx + cart.g[1] * gy * gy + cart.g[2] * gz * gz);
               }
-            else
+            else if (GEOM == 1)
               {
                 const int q = (qz * n + qy) * n + qx;
                 const T * G = geom + (size_t)cell * 6 * n3 + q;
                 s += (double)G[0] * gx * gx + (double)G[3 * n3] * gy * gy + (double)G[5 * n3] * gz * gz +
                      2 * ((double)G[n3] * gx * gy + (double)G[2 * n3] * gx * gz + (double)G[4 * n3] * gy * gz);
+              }
+            else
+              {
+                T G[6];
+                construct_q_coefficients<k, T>(geom + (size_t)cell * 3 * n3, qx, qy, qz, B, G);
+                s += (double)G[0] * gx * gx + (double)G[3] * gy * gy + (double)G[5] * gz * gz +
+                     2 * ((double)G[1] * gx * gy + (double)G[2] * gx * gz + (double)G[4] * gy * gz);
               }
           }
     const uint32_t gi = compressed_index<k>(cidx + cell * 27, ix, iy, iz);

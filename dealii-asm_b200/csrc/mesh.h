@@ -366,6 +366,34 @@ namespace dasm
       return ext;
     }
 
+    // coordinates of the n^3 Gauss points of a cell in the Q2 geometry: out[e*n3 + q] ("construct q", operator.h:712-746)
+    void
+    quadrature_points(const int c[3], const Basis1D &b, double *out) const
+    {
+      const int n = b.n, n3 = n * n * n;
+      double    X[27][3];
+      cell_support_points(c, X, false);
+      const std::vector<double> q2nodes = {0., 0.5, 1.};
+      std::vector<double>       V, D;
+      lagrange(q2nodes, b.qp, V, D);
+      for (int qz = 0; qz < n; ++qz)
+        for (int qy = 0; qy < n; ++qy)
+          for (int qx = 0; qx < n; ++qx)
+            {
+              double x[3] = {0, 0, 0};
+              for (int k = 0; k < 3; ++k)
+                for (int j = 0; j < 3; ++j)
+                  for (int i = 0; i < 3; ++i)
+                    {
+                      const double w = V[qx * 3 + i] * V[qy * 3 + j] * V[qz * 3 + k];
+                      for (int e = 0; e < 3; ++e)
+                        x[e] += w * X[9 * k + 3 * j + i][e];
+                    }
+              for (int e = 0; e < 3; ++e)
+                out[e * n3 + (qz * n + qy) * n + qx] = x[e];
+            }
+    }
+
     // merged coefficients JxW * J^-1 J^-T at the n^3 Gauss points: out[comp*n3 + q], comp order
     // xx,xy,xz,yy,yz,zz (operator.h:696-704)
     void

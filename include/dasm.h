@@ -151,7 +151,7 @@ extern "C"
 
   /* ---- LaplaceOperatorMatrixFree (include/operator.h:266-1628) ------------------------------- */
   /* ctor operator.h:466-482 + setup_mapping_and_indices 490-753.  mapping_type in {"", "merged", "linear geometry",
-   * "quadratic geometry"}; "construct q" is not built yet and, like unknown names (operator.h:747-752), returns an error. */
+   * "quadratic geometry", "construct q"}; unknown names return the reference's error (operator.h:747-752). */
   int dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping_type, int compress_indices,
                      dasm_op **out);
   int       dasm_op_destroy(dasm_op *op);

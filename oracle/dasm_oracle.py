@@ -587,6 +587,23 @@ def merged_coefficients(J, basis, dim):
     return G
 
 
+def construct_q_coefficients(mesh, basis):
+    """mapping type "construct q" (include/operator.h:712-746, 1221-1333): the cell stores the coordinates of its quadrature
+    points; the Jacobian at a point is the collocation derivative (Lagrange basis through the Gauss points) of that coordinate
+    field, then G = JxW J^-1 J^-T as in merged_coefficients.  Returns G[c, q, d, e]."""
+    dim, n = mesh.dim, basis.n
+    qp = basis.qp
+    grids = np.meshgrid(*[qp] * dim, indexing="ij")               # [(z,) y, x]
+    ref = np.stack([g for g in reversed(grids)], axis=-1)         # [..., (x, y(, z))]
+    J = np.zeros((mesh.C, n ** dim, dim, dim))
+    for c in range(mesh.C):
+        X = mesh.cell_points(mesh.cell_ijk(c), ref)               # [(z,) y, x, dim]
+        for e in range(dim):                                       # derivative along direction e = contraction of axis dim-1-e
+            dX = np.moveaxis(np.tensordot(X, basis.Dq, axes=([dim - 1 - e], [1])), -1, dim - 1 - e)
+            J[c, :, :, e] = dX.reshape(n ** dim, dim)
+    return merged_coefficients(J, basis, dim)
+
+
 class LaplaceOperator:
     """Matrix-free weak Laplacian, the restatement of LaplaceOperatorMatrixFree::vmult
     (include/operator.h:1353-1430).  Constrained (homogeneous Dirichlet) DoFs are read as zero and

@@ -96,6 +96,30 @@ def test_vmult_linear_geometry(pkg, ctx, name, k):
     assert relerr(op.to_host(d), oop.inverse_diagonal()) < 1e-12
 
 
+@pytest.mark.parametrize("name", ["sine", "kershaw", "mixed_aniso"])
+@pytest.mark.parametrize("k,number", [(1, "double"), (2, "double"), (4, "double"), (3, "float"), (6, "double")])
+def test_vmult_construct_q(pkg, ctx, name, k, number):
+    """mapping type "construct q" (operator.h:712-746, 1221-1333): quadrature-point coordinates per cell, Jacobians by collocation
+    differentiation in the kernel; vmult and the inverse diagonal against the oracle's restatement (for k = 1 the two Gauss points
+    cannot represent the Q2 geometry, so this differs from "merged" - in the reference too)."""
+    from parity_util import oracle_mesh
+    mesh = pkg.Mesh(ctx, **MESHES[name])
+    op = pkg.LaplaceOperatorMatrixFree(mesh, k, number, mapping_type="construct q")
+    oop, _ = oracle_problem(pkg, mesh, op, with_fdm=False)
+    G = o.construct_q_coefficients(oracle_mesh(mesh), o.Basis1D(k))
+    if k >= 2:
+        assert np.allclose(G, oop.G, rtol=1e-9, atol=1e-12 * np.abs(oop.G).max())
+    oop.G = G.astype(oop.dtype)
+    x = np.random.default_rng(k).uniform(-1, 1, op.n_dofs())
+    yd = op.initialize_dof_vector()
+    op.vmult(yd, op.to_device(x))
+    assert relerr(op.to_host(yd), oop.vmult(x)) < (1e-12 if number == "double" else 5e-5)
+    if number == "double":
+        d = op.initialize_dof_vector()
+        op.compute_inverse_diagonal(d)
+        assert relerr(op.to_host(d), oop.inverse_diagonal()) < 1e-12
+
+
 def test_vmult_merged_on_cartesian_equals_default(pkg, ctx):
     mesh = pkg.Mesh(ctx, (3, 3, 3), periodic=(1, 1, 1))
     a = pkg.LaplaceOperatorMatrixFree(mesh, 3, "double", mapping_type="")
