@@ -261,6 +261,14 @@ class LaplaceOperatorMatrixFree:
             _check(lib().dasm_op_vmult_hooks(self.h, _ptr(dst), _ptr(src), ctypes.byref(pre) if pre else None,
                                              ctypes.byref(post) if post else None))
 
+    def rhs(self, vec, value=1.0):
+        """LaplaceOperatorBase::rhs for a constant right-hand-side function (include/operator.h:53-56, 298-330)."""
+        _check(lib().dasm_op_rhs_constant(self.h, _ptr(vec), ctypes.c_double(value)))
+
+    def get_constraints(self):
+        """the constrained (homogeneous Dirichlet) DoFs, include/operator.h:46-51"""
+        return self.constrained_dofs()
+
     def compute_inverse_diagonal(self, diag):
         _check(lib().dasm_op_inverse_diagonal(self.h, _ptr(diag)))
 

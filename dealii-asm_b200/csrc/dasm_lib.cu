@@ -411,6 +411,7 @@ struct dasm_op
   long long         n_owned, n_ghost, n_vec;
   long long         n_global_dofs;
   uint32_t *        d_cidx        = nullptr;
+  uint32_t *        d_plain       = nullptr; // compress_indices = false: (k+1)^3 indices per cell (operator.h:1343-1350, plain branch)
   uint32_t *        d_constrained = nullptr;
   long long         n_constrained = 0;
   int               geom_mode     = 0; // 0 cartesian, 1 merged, 2 quadratic / linear coefficients (brick kernel)
@@ -561,6 +562,9 @@ struct dasm_cheb
       using T = float;                            \
       __VA_ARGS__;                                \
     }
+
+template <int k>
+__global__ void expand_compressed_kernel(uint32_t *out, const uint32_t *cidx, const long long n_cells);
 
 // ---- even-odd blocks of the 1-D matrices of the warp-specialised kernels (EOMat in kernels_fast.cuh) -------------------
 // centrosymmetric matrix A[o][i] = A[n-1-o][n-1-i] (mass / stiffness on symmetric nodes), nodal -> nodal
@@ -713,19 +717,19 @@ launch_laplace(dasm_op *op, T *dst, const T *src)
       {
         auto kern = laplace_generic_kernel<K, T, 0>;
         CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, CPB * n * n, smem, ctx->stream>>>(src, dst, op->d_cidx, (const T *)nullptr, op->cart, op->n_cells);
+        kern<<<grid, CPB * n * n, smem, ctx->stream>>>(src, dst, op->d_cidx, (const T *)nullptr, op->cart, op->n_cells, op->d_plain);
       }
     else if (op->geom_mode == 3)
       {
         auto kern = laplace_generic_kernel<K, T, 2>;
         CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, CPB * n * n, smem, ctx->stream>>>(src, dst, op->d_cidx, (const T *)op->d_geom, op->cart, op->n_cells);
+        kern<<<grid, CPB * n * n, smem, ctx->stream>>>(src, dst, op->d_cidx, (const T *)op->d_geom, op->cart, op->n_cells, op->d_plain);
       }
     else
       {
         auto kern = laplace_generic_kernel<K, T, 1>;
         CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, CPB * n * n, smem, ctx->stream>>>(src, dst, op->d_cidx, (const T *)op->d_geom, op->cart, op->n_cells);
+        kern<<<grid, CPB * n * n, smem, ctx->stream>>>(src, dst, op->d_cidx, (const T *)op->d_geom, op->cart, op->n_cells, op->d_plain);
       }
   });
   ctx->launches++;
@@ -2168,9 +2172,19 @@ dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping
     // (degree 5 runs faster through the generic kernels: 1.70e10 vs 1.24e10 DoFs/s per Chebyshev term, profiles/r01c_secondary.log;
     // DASM_BRICK_K5=1 selects the 4x4x2 brick kernels)
     const char *k5    = getenv("DASM_BRICK_K5");
-    op->use_brick     = (degree <= 4 || (degree == 5 && k5 && k5[0] == '1')) && !(force && force[0] == '1') && op->geom_mode != 3;
+    op->use_brick     = (degree <= 4 || (degree == 5 && k5 && k5[0] == '1')) && !(force && force[0] == '1') && op->geom_mode != 3 &&
+                    op->compress_indices;
+    if (!op->compress_indices)
+      {
+        // plain index storage: (k+1)^3 indices per cell read by the generic kernels (the compressed / tile formats of the tuned kernels
+        // are what compress_indices = true stands for)
+        const long long ne = op->n_cells * n3;
+        op->d_plain        = dev_alloc<uint32_t>(std::max<long long>(ne, 1));
+        DISPATCH_DEGREE(degree, expand_compressed_kernel<K><<<nblocks(ne), 256, 0, ctx->stream>>>(op->d_plain, op->d_cidx, op->n_cells));
+        ctx->launches++;
+      }
     const char *nofast_hi = getenv("DASM_NO_FAST");
-    if (!op->use_brick && (degree == 5 || degree == 6) && !(force && force[0] == '1') && !(nofast_hi && nofast_hi[0] == '1'))
+    if (!op->use_brick && op->compress_indices && (degree == 5 || degree == 6) && !(force && force[0] == '1') && !(nofast_hi && nofast_hi[0] == '1'))
       setup_tma_only(op);
     if (op->use_brick && !op->tma_only)
       {
@@ -2682,6 +2696,7 @@ dasm_op_destroy(dasm_op *op)
   cudaFree(op->d_bricks);
   cudaFree(op->d_acc);
   cudaFree(op->d_shared_list);
+  cudaFree(op->d_plain);
   cudaFree(op->d_fast_ids);
   cudaFree(op->d_slow_ids);
   cudaFree(op->d_tma_lap);
@@ -2822,6 +2837,72 @@ dasm_op_merged_coefficients(const dasm_op *op, long long cell, double *out)
   const Mesh &M    = *op->mesh->mesh;
   const int   c[3] = {M.cell_ijk[cell][0], M.cell_ijk[cell][1], M.cell_ijk[cell][2]};
   M.merged_coefficients(c, op->basis, out, op->linear_geometry);
+  DASM_API_END
+}
+
+// LaplaceOperatorBase::rhs(vec, func) for a constant function (include/operator.h:298-330 with VectorTools::create_right_hand_side:
+// b_i = int f phi_i, constrained entries zero): assembled on the host (set-up operation) with the operator's geometry, added up
+// over the ranks by the ghost exchange
+extern "C" int
+dasm_op_rhs_constant(dasm_op *op, void *vec, double value)
+{
+  DASM_API_BEGIN
+  CUDA_CHECK(cudaSetDevice(op->ctx->device));
+  const Mesh &        M = *op->mesh->mesh;
+  const int           k = op->k, n = k + 1, n3 = n * n * n;
+  const Basis1D &     b = op->basis;
+  std::vector<double> host((size_t)op->n_vec, 0.), jxw(n3), t0(n3), t1(n3);
+  for (long long c = 0; c < op->n_cells; ++c)
+    {
+      const int cc[3] = {M.cell_ijk[c][0], M.cell_ijk[c][1], M.cell_ijk[c][2]};
+      M.jxw(cc, b, jxw.data(), op->linear_geometry);
+      // local vector = (N^T x N^T x N^T) (f JxW), N[q*n+i]
+      for (int qz = 0; qz < n; ++qz)
+        for (int qy = 0; qy < n; ++qy)
+          for (int i = 0; i < n; ++i)
+            {
+              double s = 0;
+              for (int qx = 0; qx < n; ++qx)
+                s += b.N[qx * n + i] * jxw[(qz * n + qy) * n + qx];
+              t0[(qz * n + qy) * n + i] = s * value;
+            }
+      for (int qz = 0; qz < n; ++qz)
+        for (int j = 0; j < n; ++j)
+          for (int i = 0; i < n; ++i)
+            {
+              double s = 0;
+              for (int qy = 0; qy < n; ++qy)
+                s += b.N[qy * n + j] * t0[(qz * n + qy) * n + i];
+              t1[(qz * n + j) * n + i] = s;
+            }
+      const uint32_t *ci = op->nb.cidx.data() + c * 27;
+      for (int l = 0; l < n; ++l)
+        for (int j = 0; j < n; ++j)
+          for (int i = 0; i < n; ++i)
+            {
+              double s = 0;
+              for (int qz = 0; qz < n; ++qz)
+                s += b.N[qz * n + l] * t1[(qz * n + j) * n + i];
+              const uint32_t g = expand_start_index(ci, k, i, j, l);
+              if (g != INVALID_INDEX)
+                host[g] += s;
+            }
+    }
+  if (op->ntype == DASM_F64)
+    {
+      CUDA_CHECK(cudaMemcpyAsync(vec, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice, op->ctx->stream));
+      CUDA_CHECK(cudaStreamSynchronize(op->ctx->stream));
+      op->exchange.run<double>((double *)vec, true);
+    }
+  else
+    {
+      std::vector<float> hf(host.begin(), host.end());
+      CUDA_CHECK(cudaMemcpyAsync(vec, hf.data(), hf.size() * sizeof(float), cudaMemcpyHostToDevice, op->ctx->stream));
+      CUDA_CHECK(cudaStreamSynchronize(op->ctx->stream));
+      op->exchange.run<float>((float *)vec, true);
+    }
+  if (op->n_vec > op->n_owned)
+    CUDA_CHECK(cudaMemsetAsync((char *)vec + (size_t)op->n_owned * op->esize(), 0, (size_t)(op->n_vec - op->n_owned) * op->esize(), op->ctx->stream));
   DASM_API_END
 }
 
@@ -3266,6 +3347,14 @@ dasm_fdm_create(dasm_op *op, int n_overlap, int sub_mesh_approximation, int weig
                 }
         }
       f->d_pidx = dev_upload(pidx, op->ctx->stream);
+    }
+
+  if (f->d_pidx == nullptr && op->d_plain != nullptr)
+    {
+      // the operator stores plain indices (compress_indices = false): the patch lists are those n^3 indices per cell
+      const size_t ne = (size_t)op->n_cells * (k + 1) * (k + 1) * (k + 1);
+      f->d_pidx       = dev_alloc<uint32_t>(std::max<size_t>(ne, 1));
+      CUDA_CHECK(cudaMemcpyAsync(f->d_pidx, op->d_plain, ne * sizeof(uint32_t), cudaMemcpyDeviceToDevice, op->ctx->stream));
     }
 
   // RAS ownership: the patch of the touching cell with the smallest global lexicographic id owns

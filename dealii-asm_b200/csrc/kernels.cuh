@@ -226,7 +226,8 @@ namespace dasm
                          const uint32_t *__restrict__ cidx,
                          const T *__restrict__ geom,
                          const CartesianCoef cart,
-                         const long long     n_cells)
+                         const long long     n_cells,
+                         const uint32_t *__restrict__ plain = nullptr) // compress_indices = false: n^3 indices per cell
   {
     constexpr int n = k + 1, n2 = n * n, n3 = n2 * n, CPB = cells_per_block<k>();
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -257,7 +258,7 @@ namespace dasm
 #pragma unroll
         for (int x = 0; x < n; ++x)
           {
-            const uint32_t gi = compressed_index<k>(s_ci[cl], x, a, b);
+            const uint32_t gi = plain ? plain[cell * n3 + (b * n + a) * n + x] : compressed_index<k>(s_ci[cl], x, a, b);
             U[(b * n + a) * n + x] = (gi == DEV_INVALID) ? T(0) : src[gi];
           }
       }
@@ -339,7 +340,7 @@ namespace dasm
 #pragma unroll
         for (int x = 0; x < n; ++x)
           {
-            const uint32_t gi = compressed_index<k>(s_ci[cl], x, a, b);
+            const uint32_t gi = plain ? plain[cell * n3 + (b * n + a) * n + x] : compressed_index<k>(s_ci[cl], x, a, b);
             if (gi != DEV_INVALID)
               atomic_add(dst + gi, U[(b * n + a) * n + x]);
           }

@@ -366,6 +366,42 @@ namespace dasm
       return ext;
     }
 
+    // JxW at the n^3 Gauss points of a cell: out[q]
+    void
+    jxw(const int c[3], const Basis1D &b, double *out, const bool linear = false) const
+    {
+      const int n = b.n;
+      double    X[27][3];
+      cell_support_points(c, X, linear);
+      const std::vector<double> q2nodes = {0., 0.5, 1.};
+      std::vector<double>       V, D;
+      lagrange(q2nodes, b.qp, V, D);
+      for (int qz = 0; qz < n; ++qz)
+        for (int qy = 0; qy < n; ++qy)
+          for (int qx = 0; qx < n; ++qx)
+            {
+              double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+              for (int k = 0; k < 3; ++k)
+                for (int j = 0; j < 3; ++j)
+                  for (int i = 0; i < 3; ++i)
+                    {
+                      const double *P  = X[9 * k + 3 * j + i];
+                      const double  gx = D[qx * 3 + i] * V[qy * 3 + j] * V[qz * 3 + k];
+                      const double  gy = V[qx * 3 + i] * D[qy * 3 + j] * V[qz * 3 + k];
+                      const double  gz = V[qx * 3 + i] * V[qy * 3 + j] * D[qz * 3 + k];
+                      for (int dd = 0; dd < 3; ++dd)
+                        {
+                          J[dd][0] += P[dd] * gx;
+                          J[dd][1] += P[dd] * gy;
+                          J[dd][2] += P[dd] * gz;
+                        }
+                    }
+              const double det = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) - J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0]) +
+                                 J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+              out[(qz * n + qy) * n + qx] = det * b.qw[qx] * b.qw[qy] * b.qw[qz];
+            }
+    }
+
     // coordinates of the n^3 Gauss points of a cell in the Q2 geometry: out[e*n3 + q] ("construct q", operator.h:712-746)
     void
     quadrature_points(const int c[3], const Basis1D &b, double *out) const

@@ -168,6 +168,9 @@ extern "C"
   int dasm_op_vmult(dasm_op *op, void *dst, const void *src);
   /* vmult(dst, src, pre, post), operator.h:1367-1430 (constrained DoFs: dst = src when post given) */
   int dasm_op_vmult_hooks(dasm_op *op, void *dst, const void *src, const dasm_hook *pre, const dasm_hook *post);
+  /* LaplaceOperatorBase::rhs(vec, func), operator.h:53-56 / 298-330, for a constant function f = value: vec_i = int f phi_i
+   * (VectorTools::create_right_hand_side; constrained entries zero).  get_constraints(): dasm_op_constrained_dofs. */
+  int dasm_op_rhs_constant(dasm_op *op, void *vec, double value);
   /* compute_inverse_diagonal, operator.h:1512-1524 */
   int dasm_op_inverse_diagonal(dasm_op *op, void *diag);
   /* 27 compressed start indices per local cell (ConstraintInfoReduced::compressed_dof_indices,

@@ -7,6 +7,7 @@
 // The reference's operators are templated on deal.II's MatrixFree; here the mesh/DoF infrastructure is the
 // library's structured-mesh object (dasm::Mesh) and vectors are device vectors (dasm::Vector<Number>).
 #pragma once
+#include <cstdint>
 #include <functional>
 #include <memory>
 #include <stdexcept>
@@ -194,6 +195,24 @@ namespace dasm
                                  "use the dasm_hook overload (DASM_HOOK_RESIDUAL / DASM_HOOK_CHEB_UPDATE / DASM_HOOK_SCALE)");
       (void)pre; // the zeroing pre-operation is implied
       vmult(dst, src);
+    }
+
+    // rhs(vec, func), operator.h:53-56: constant functions only (the reference's drivers use f = 1)
+    void
+    rhs(VectorType &vec, const double value = 1.0) const
+    {
+      if (vec.data() == nullptr)
+        vec.reinit(h);
+      check(dasm_op_rhs_constant(h, vec.data(), value));
+    }
+    // get_constraints(), operator.h:46-51: the list of constrained (homogeneous Dirichlet) DoFs
+    std::vector<std::uint32_t>
+    get_constraints() const
+    {
+      std::vector<std::uint32_t> out((std::size_t)dasm_op_constrained_dofs(h, nullptr));
+      if (!out.empty())
+        dasm_op_constrained_dofs(h, out.data());
+      return out;
     }
 
     void Tvmult(VectorType &, const VectorType &) const { throw std::runtime_error("ExcNotImplemented"); }

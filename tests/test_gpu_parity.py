@@ -120,6 +120,64 @@ def test_vmult_construct_q(pkg, ctx, name, k, number):
         assert relerr(op.to_host(d), oop.inverse_diagonal()) < 1e-12
 
 
+@pytest.mark.parametrize("name", ["periodic", "dirichlet", "kershaw"])
+@pytest.mark.parametrize("k,number", [(2, "double"), (4, "double"), (3, "float")])
+def test_plain_indices(pkg, ctx, name, k, number):
+    """AdditionalData::compress_indices = false (operator.h:285-295, plain branch of do_cell_integral_global 1343-1350): (k+1)^3
+    indices per cell instead of the 27 compressed start indices; vmult, FDM and a Chebyshev step equal the oracle."""
+    mesh = pkg.Mesh(ctx, **MESHES[name])
+    mt = "quadratic geometry" if name == "kershaw" else ""
+    op = pkg.LaplaceOperatorMatrixFree(mesh, k, number, mapping_type="merged" if name == "kershaw" else mt, compress_indices=False)
+    assert not op.uses_compressed_indices()
+    dt = NPDT[number]
+    oop, oP = oracle_problem(pkg, mesh, op, 1, "symm", dtype=dt)
+    rng = np.random.default_rng(k)
+    x, b = rng.uniform(-1, 1, op.n_dofs()), rng.uniform(-1, 1, op.n_dofs())
+    con = op.constrained_dofs()
+    x[con] = 0
+    b[con] = 0
+    yd = op.initialize_dof_vector()
+    op.vmult(yd, op.to_device(x))
+    assert relerr(op.to_host(yd), oop.vmult(x)) < TOL[number]
+    fdm = pkg.create_fdm_preconditioner(op, {"weighting type": "symm"})
+    fdm.vmult(yd, op.to_device(b))
+    assert relerr(op.to_host(yd), oP.vmult(b)) < TOL[number]
+    cheb = pkg.PreconditionChebyshev(op, fdm, degree=3)
+    cheb.set_eigenvalues(0.9, 2.3)
+    och = o.Chebyshev(oop, oP, degree=3)
+    och.set_eigenvalues(2.3, 0.9)
+    xd = op.to_device(x)
+    cheb.step(xd, op.to_device(b))
+    assert relerr(op.to_host(xd), och.step(x.astype(dt), b.astype(dt)).astype(np.float64)) < TOL[number]
+
+
+@pytest.mark.parametrize("name", ["dirichlet", "mixed_aniso", "kershaw", "periodic"])
+def test_rhs_and_constraints(pkg, ctx, name):
+    """LaplaceOperatorBase::rhs (f = 1: b_i = int phi_i, constrained entries zero, operator.h:298-330) and get_constraints:
+    against the oracle's assembly; the entries sum to the volume of the domain when nothing is constrained."""
+    from parity_util import oracle_mesh
+    k = 3
+    mesh = pkg.Mesh(ctx, **MESHES[name])
+    op = pkg.LaplaceOperatorMatrixFree(mesh, k, "double", mapping_type="" if name in ("periodic", "dirichlet", "mixed_aniso") else "merged")
+    oop, _ = oracle_problem(pkg, mesh, op, with_fdm=False)
+    om = oracle_mesh(mesh)
+    bas = o.Basis1D(k)
+    J = om.jacobians(bas)
+    w = np.einsum("c,b,a->cba", bas.qw, bas.qw, bas.qw).reshape(-1)
+    jxw = np.linalg.det(J) * w[None, :]
+    N = bas.N
+    loc = np.einsum("qk,rj,si,cqrs->ckji", N, N, N, jxw.reshape(-1, k + 1, k + 1, k + 1)).reshape(om.C, -1)
+    ref = np.zeros(oop.n_dofs)
+    np.add.at(ref, oop.idx.reshape(-1), (loc * oop.mask).reshape(-1))
+    bd = op.initialize_dof_vector()
+    op.rhs(bd, 1.0)
+    got = op.to_host(bd)
+    assert relerr(got, ref) < 1e-12
+    assert np.array_equal(np.sort(op.get_constraints()), np.nonzero(oop.constrained)[0].astype(np.uint32))
+    if name == "periodic":
+        assert abs(got.sum() - np.prod(mesh.length)) < 1e-12 * np.prod(mesh.length)
+
+
 def test_vmult_merged_on_cartesian_equals_default(pkg, ctx):
     mesh = pkg.Mesh(ctx, (3, 3, 3), periodic=(1, 1, 1))
     a = pkg.LaplaceOperatorMatrixFree(mesh, 3, "double", mapping_type="")
