@@ -3349,7 +3349,7 @@ dasm_fdm_create(dasm_op *op, int n_overlap, int sub_mesh_approximation, int weig
       f->d_pidx = dev_upload(pidx, op->ctx->stream);
     }
 
-  if (f->d_pidx == nullptr && op->d_plain != nullptr)
+  if (f->d_pidx == nullptr && op->d_plain != nullptr && f->m >= 3) // (the kernels with explicit lists start at patch size 3)
     {
       // the operator stores plain indices (compress_indices = false): the patch lists are those n^3 indices per cell
       const size_t ne = (size_t)op->n_cells * (k + 1) * (k + 1) * (k + 1);

@@ -43,3 +43,49 @@ def test_matrix_free_loop_08_output(tmp_path):
     p.write_text(json.dumps(cfg))
     out = subprocess.run([DRIVER, str(p)], capture_output=True, text=True, timeout=300)
     assert out.returncode != 0 and "is not known" in out.stderr
+
+
+SOLVER_DRIVER = os.path.join(ROOT, "drivers", "element_centered_preconditioners_01")
+
+
+@pytest.mark.gpu
+def test_element_centered_preconditioners_01_driver(tmp_path):
+    """the reference's solver driver (element_centered_preconditioners_01.cc) on libdasm: the small/dummy_*.json configurations of the
+    reference's tests in 3-D (dim 2 does not exist here): Identity / Diagonal / Chebyshev(Diagonal) / multigrid with Chebyshev + FDM
+    smoothers; output format of the reference, iteration counts ordered as in the reference's 2-D goldens (24 / 23 / 9 / 3)."""
+    if not os.path.exists(SOLVER_DRIVER):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "drivers")])
+    base = {"type": "matrixfree", "dim": 3, "degree": 3, "n refinements": 2, "solver": {"type": "GMRES"}}
+    mg = {"type": "Multigrid",
+          "mg smoother": {"type": "Chebyshev", "degree": 1, "preconditioner": {"type": "FDM", "n overlap": 1, "weighting type": "post"}},
+          "mg coarse grid solver": {"type": "Chebyshev", "degree": 1, "preconditioner": {"type": "FDM", "n overlap": 1, "weighting type": "post"}}}
+    configs = {"identity": {"type": "Identity"}, "diagonal": {"type": "Diagonal"},
+               "chebyshev_diagonal": {"type": "Chebyshev", "degree": 3, "preconditioner": {"type": "Diagonal"}},
+               "mg_h": mg, "mg_p": dict(mg, **{"mg type": "p"}),
+               "asm": {"type": "AdditiveSchwarzPreconditioner", "n overlap": 2, "weighting type": "symm"}}
+    its = {}
+    for name, pre in configs.items():
+        cfg = dict(base, preconditioner=pre)
+        if name == "asm":
+            cfg["degree"] = 2
+        p = tmp_path / (name + ".json")
+        p.write_text(json.dumps(cfg))
+        out = subprocess.run([SOLVER_DRIVER, str(p)], capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr + out.stdout[-2000:]
+        assert "- Create operator:" in out.stdout and " - Solving with GMRES" in out.stdout
+        line = [l for l in out.stdout.splitlines() if "n iterations:" in l]
+        assert len(line) == 1
+        its[name] = int(line[0].split()[-1])
+        row = out.stdout.strip().splitlines()[-1].split("|")
+        assert int(row[1]) == 64 and int(row[3]) == (13 ** 3 if name != "asm" else 9 ** 3) and int(row[4]) == its[name]
+        if name.startswith("mg"):
+            n_smoothers = 2 if name == "mg_h" else 1  # h: 1 / 8 / 64 cells; p (bisect): degrees 1, 3
+            assert out.stdout.count("- Setting up smoother on level") == n_smoothers and "- Setting up coarse-grid solver on level 0" in out.stdout
+    assert its["mg_h"] <= 6 and its["mg_p"] <= 8
+    assert its["mg_h"] < its["chebyshev_diagonal"] < its["diagonal"] <= its["identity"]
+    # unknown solver -> the reference's error text
+    cfg = dict(base, preconditioner={"type": "Identity"}, solver={"type": "BiCG"})
+    p = tmp_path / "bad.json"
+    p.write_text(json.dumps(cfg))
+    out = subprocess.run([SOLVER_DRIVER, str(p)], capture_output=True, text=True, timeout=300)
+    assert out.returncode != 0 and "Solver <BiCG> is not known!" in out.stderr
