@@ -484,6 +484,27 @@ class RestrictedPreconditioner:
             pass
 
 
+def reduced_access_read(degree, cidx, orientation, src):
+    """ConstraintInfoReduced::read_dof_values with the packed orientation word per cell (include/vector_access_reduced.h:267-405,
+    include/reduced_access.h:528-702): cidx [cells, 27] uint32 and orientation [cells] uint32 torch CUDA tensors (orientation may be
+    None), src a CUDA vector; returns local values [cells, (degree+1)^3]."""
+    import torch
+    n_cells = cidx.shape[0]
+    local = torch.zeros((n_cells, (degree + 1) ** 3), dtype=src.dtype, device=src.device)
+    nt = F64 if src.dtype == torch.float64 else F32
+    _check(lib().dasm_reduced_access_read(int(degree), nt, _ptr(cidx), _ptr(orientation), ctypes.c_longlong(n_cells), _ptr(src), _ptr(local),
+                                          ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    return local
+
+
+def reduced_access_distribute(degree, cidx, orientation, dst, local):
+    """ConstraintInfoReduced::distribute_local_to_global (include/vector_access_reduced.h:407-548): the transpose of reduced_access_read."""
+    import torch
+    nt = F64 if dst.dtype == torch.float64 else F32
+    _check(lib().dasm_reduced_access_distribute(int(degree), nt, _ptr(cidx), _ptr(orientation), ctypes.c_longlong(cidx.shape[0]), _ptr(dst),
+                                                _ptr(local), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+
 def solve(op, x, b, preconditioner=None, params=None):
     """solve() of element_centered_preconditioners_01.cc:108-203 on the device: `params` is the reference's "solver" JSON block
     (type CG | GMRES, max iterations 1000, abs tolerance 1e-10, rel tolerance 1e-2, max n tmp vectors 30);

@@ -269,6 +269,17 @@ extern "C"
   int  dasm_fdm_patches_host(dasm_fdm *fdm, uint32_t *idx, double *w, int *w_pre, int *w_post);
   void dasm_set_last_error(const char *msg);
 
+  /* ---- Orientation-aware compressed vector access (ConstraintInfoReduced::read_dof_values / distribute_local_to_global,
+   *      include/vector_access_reduced.h:267-548, with adjust_for_orientation, include/reduced_access.h:528-702) ------------------
+   * d_cidx: 27 start indices per cell (0xFFFFFFFF = constrained), d_orientation: one packed word per cell (12 line bits + 6 x 3 quad
+   * bits, the "post" word of compress_orientation; NULL = all standard), local: [n_cells][(degree+1)^3] values in lexicographic
+   * order.  All pointers are DEVICE pointers; `stream` is a cudaStream_t.  The structured meshes of this library only produce the
+   * standard orientation; these entry points are the general form for unstructured meshes. */
+  int dasm_reduced_access_read(int degree, int number_type, const uint32_t *d_cidx, const uint32_t *d_orientation, long long n_cells,
+                               const void *src, void *local, void *stream);
+  int dasm_reduced_access_distribute(int degree, int number_type, const uint32_t *d_cidx, const uint32_t *d_orientation,
+                                     long long n_cells, void *dst, const void *local, void *stream);
+
   /* ---- Geometric / polynomial multigrid V-cycle (include/multigrid.h:109-537: PreconditionerGMG; deal.II Multigrid +
    *      MGTransferGlobalCoarsening + PreconditionMG as set up in element_centered_preconditioners_01.cc:540-740) ------------------
    * Two-level transfer between two operators on the same context: geometric (the fine mesh has twice the cells of the coarse mesh in

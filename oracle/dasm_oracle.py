@@ -1412,3 +1412,202 @@ class ExactBlockASM(FDMPreconditioner):
 
     def apply_inverse(self, rl):
         return np.stack([self.block_inv[c] @ rl[c] for c in range(rl.shape[0])])
+
+
+# --------------------------------------------------------------------------------------
+# Orientation-aware compressed access (include/reduced_access.h:66-152, 286-770): the 3^dim start indices of a cell plus one
+# orientation word (dim = 2: 4 line bits; dim = 3: 12 line bits + 6 x 3 quad bits).  Pinned by reduced_access_01.result (2-D) and
+# reduced_access_02.result (3-D) - line flips and quad flag 1 (transposed quad); the other quad flags follow deal.II's
+# ShapeInfo::compute_orientation_table as recollected and are NOT pinned by a golden.
+# --------------------------------------------------------------------------------------
+def orientation_table(n):
+    """[8, n*n]: position inside a quad of n x n interior DoFs for the 8 (orientation, flip, rotation) combinations; row 0 is the
+    standard orientation, row 1 the transposed quad (pinned), rows 2..7 unpinned."""
+    t = np.zeros((8, n * n), dtype=np.int64)
+    for j in range(n):
+        for i in range(n):
+            q = i + j * n
+            t[0, q] = i + j * n
+            t[1, q] = j + i * n
+            t[2, q] = j + (n - 1 - i) * n
+            t[3, q] = i + (n - 1 - j) * n
+            t[4, q] = (n - 1 - i) + (n - 1 - j) * n
+            t[5, q] = (n - 1 - j) + (n - 1 - i) * n
+            t[6, q] = (n - 1 - j) + i * n
+            t[7, q] = (n - 1 - i) + j * n
+    return t
+
+
+def compress_orientation(orientations, do_post=False):
+    """include/reduced_access.h:66-152 (orientations: 4 line flags in 2-D; 12 line flags + 6 quad flags in 3-D, deal.II order)."""
+    o = list(orientations)
+    word = 0
+    if len(o) == 4:
+        order = [2, 3, 0, 1] if do_post else [2, 0, 1, 3]
+        for s, i in enumerate(order):
+            word += o[i] << s
+    elif len(o) == 18:
+        if do_post:
+            shift = 0
+            for i in (2, 3, 6, 7, 0, 1, 4, 5, 8, 9, 10, 11):
+                word |= o[i] << shift
+                shift += 1
+            for i in range(6):
+                word |= o[12 + i] << shift
+                shift += 3
+        else:
+            tab = [(1, o[2]), (1, o[0]), (3, o[16]), (1, o[1]), (1, o[3]),
+                   (1, o[8]), (3, o[14]), (1, o[9]), (3, o[12]), (3, o[13]), (1, o[10]), (3, o[15]), (1, o[11]),
+                   (1, o[6]), (1, o[4]), (3, o[17]), (1, o[5]), (1, o[7])]
+            s = 0
+            for width, val in tab:
+                word += val << s
+                s += width
+    else:
+        raise NotImplementedError
+    return word
+
+
+def adjust_for_orientation(dim, degree, local, orientation, table, integrate=False):
+    """include/reduced_access.h:528-702: in-place reorientation of the (degree+1)^dim local values that were gathered in the
+    standard layout (`orientation` = post word of compress_orientation)."""
+    if dim == 1 or orientation == 0:
+        return local
+    np_, np2 = degree + 1, (degree + 1) ** 2
+    n_lines = 4 if dim == 2 else 12
+    v = local
+    if dim == 2 or (orientation & 0b111111111111):
+        for l in range(n_lines):
+            if orientation & 1:
+                stride = np_ ** (l // (2 if dim == 2 else 4))
+                if dim == 2:
+                    begin = [1, degree * degree + degree + 1, degree + 1, 2 * degree + 1][l]
+                else:
+                    begin = [1, np_ * degree + 1, np2 * degree + 1, np2 * degree + np_ * degree + 1, np_, np_ + degree,
+                             np2 * degree + np_, np2 * degree + np_ + degree, np2, np2 + degree, np2 + np_ * degree,
+                             np2 + np_ * degree + degree][l]
+                for i0 in range((degree - 1) // 2):
+                    a, b = begin + i0 * stride, begin + (degree - 2 - i0) * stride
+                    v[a], v[b] = v[b], v[a]
+            orientation >>= 1
+    elif dim == 3:
+        orientation >>= 12
+    if dim == 3 and orientation != 0:
+        for q in range(6):
+            flag = orientation & 0b111
+            if flag != 0:
+                d = q // 2
+                stride0 = np_ if d == 0 else 1
+                stride1 = np_ if d == 2 else np2
+                begin = 0 if q % 2 == 0 else (np_ ** (q // 2)) * degree
+                temp = [None] * ((degree - 1) ** 2)
+                i = 0
+                for i1 in range(1, degree):
+                    for i0 in range(1, degree):
+                        if integrate:
+                            j = table[flag][(i0 - 1) + (i1 - 1) * (degree - 1)]
+                            i0_, i1_ = (j % (degree - 1)) + 1, (j // (degree - 1)) + 1
+                            temp[i] = v[begin + i0_ * stride0 + i1_ * stride1]
+                        else:
+                            temp[table[flag][i]] = v[begin + i0 * stride0 + i1 * stride1]
+                        i += 1
+                i = 0
+                for i1 in range(1, degree):
+                    for i0 in range(1, degree):
+                        v[begin + i0 * stride0 + i1 * stride1] = temp[i]
+                        i += 1
+            orientation >>= 3
+    return v
+
+
+def gather_post(global_vector, dim, degree, dofs_of_cell, orientation, table):
+    """include/reduced_access.h:704-770: standard expansion of the 3^dim start indices, then adjust_for_orientation."""
+    comp = np.asarray(dofs_of_cell, dtype=np.uint32).reshape(1, -1)
+    idx = expand_compressed(comp, degree, dim)[0].astype(np.int64)
+    local = [global_vector[i] for i in idx]
+    return adjust_for_orientation(dim, degree, local, orientation, table, False)
+
+
+def _rotr32(x, r):
+    r %= 32
+    return ((x >> r) | (x << (32 - r))) & 0xFFFFFFFF
+
+
+def gather_oriented(global_vector, dim, degree, dofs_of_cell, orientation_in, table):
+    """include/reduced_access.h:286-526: gather with the orientation applied on the fly (`orientation_in` = pre word)."""
+    g, d = global_vector, list(dofs_of_cell)
+    out = []
+    if dim == 2:
+        orientation, offset, compressed = orientation_in, 0, 0
+        for j in range(degree + 1):
+            ind = d[compressed * 3: compressed * 3 + 3]
+            if orientation and (orientation & 1) and (j == 0 or j == degree):
+                out.append(g[ind[0]])
+                out += [g[ind[1] + (degree - 2 - i)] for i in range(degree - 1)]
+                out.append(g[ind[2]])
+            elif orientation and (orientation & 0b11) and 0 < j < degree:
+                out.append(g[ind[0] + (degree - 2 - offset)] if orientation & 0b01 else g[ind[0] + offset])
+                out += [g[ind[1] + offset * (degree - 1) + i] for i in range(degree - 1)]
+                out.append(g[ind[2] + (degree - 2 - offset)] if orientation & 0b10 else g[ind[2] + offset])
+            else:
+                out.append(g[ind[0] + offset])
+                out += [g[ind[1] + offset * (degree - 1) + i] for i in range(degree - 1)]
+                out.append(g[ind[2] + offset])
+            if j == 0 or j == degree - 1:
+                compressed += 1
+                offset = 0
+                orientation = orientation >> 1 if j == 0 else orientation >> 2
+            else:
+                offset += 1
+        return out
+    orientation = orientation_in
+    o_ptr, compressed_k, offset_k = orientation, 0, 0
+    for k in range(degree + 1):
+        compressed_j = offset_j = 0
+        for j in range(degree + 1):
+            offset = ((degree - 1) if compressed_j == 1 else 1) * offset_k + offset_j
+            ind = d[3 * (compressed_k * 3 + compressed_j): 3 * (compressed_k * 3 + compressed_j) + 3]
+            k_end, j_end = (k == 0 or k == degree), (j == 0 or j == degree)
+            if orientation != 0 and (o_ptr & 1) and k_end and j_end:
+                out.append(g[ind[0]])
+                out += [g[ind[1] + (degree - 2 - i)] for i in range(degree - 1)]
+                out.append(g[ind[2]])
+            elif orientation != 0 and (o_ptr & 0b11111) and ((k_end and 0 < j < degree) or (0 < k < degree and j_end)):
+                jk = j if k_end else k
+                out.append(g[ind[0] + (degree - 1 - jk)] if o_ptr & 0b00001 else g[ind[0] + (jk - 1)])
+                qf = (o_ptr >> 1) & 0b111
+                for i in range(degree - 1):
+                    out.append(g[ind[1] + (table[qf][(degree - 1) * (jk - 1) + i] if qf != 0 else (degree - 1) * (jk - 1) + i)])
+                out.append(g[ind[2] + (degree - 1 - jk)] if o_ptr & 0b10000 else g[ind[2] + (jk - 1)])
+            elif orientation != 0 and (o_ptr & 0b111111) and 0 < k < degree and 0 < j < degree:
+                q0, q1 = o_ptr & 0b111, (o_ptr >> 3) & 0b111
+                out.append(g[ind[0] + (table[q0][offset] if q0 != 0 else offset)])
+                out += [g[ind[1] + offset * (degree - 1) + i] for i in range(degree - 1)]
+                out.append(g[ind[2] + (table[q1][offset] if q1 != 0 else offset)])
+            else:
+                out.append(g[ind[0] + offset])
+                out += [g[ind[1] + offset * (degree - 1) + i] for i in range(degree - 1)]
+                out.append(g[ind[2] + offset])
+            if j == 0 or j == degree - 1:
+                compressed_j += 1
+                offset_j = 0
+            else:
+                offset_j += 1
+            if k_end:
+                if j_end:
+                    o_ptr = _rotr32(o_ptr, 1)
+                elif j == degree - 1:
+                    o_ptr = _rotr32(o_ptr, 5)
+            else:
+                if j_end:
+                    o_ptr = _rotr32(o_ptr, 5)
+                elif j == degree - 1:
+                    o_ptr = _rotr32(o_ptr, 6)
+            if 0 < k < degree - 1 and j == degree:
+                o_ptr = _rotr32(o_ptr, 32 - 16)
+        if k == 0 or k == degree - 1:
+            compressed_k += 1
+            offset_k = 0
+        else:
+            offset_k += 1
+    return out

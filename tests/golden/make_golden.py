@@ -33,6 +33,13 @@ def main():
         if len(p) == 6:
             rows.append([int(p[0]), int(p[1]), int(p[2]), int(p[3]), int(p[4]), float(p[5])])
     json.dump(rows, open(os.path.join(HERE, "subdivided_hyper_cube_balanced_01.json"), "w"))
+    # reduced_access_01.result / reduced_access_02.result: command lines and the printed local vectors as integer lists
+    for name in ("reduced_access_01", "reduced_access_02"):
+        cases = []
+        for block in open(os.path.join(REF, name + ".result")).read().split("./" + name)[1:]:
+            lines = block.strip().splitlines()
+            cases.append({"args": [int(a) for a in lines[0].split()], "local": [int(x) for l in lines[1:] for x in l.split()]})
+        json.dump(cases, open(os.path.join(HERE, name + ".json"), "w"))
 
 
 if __name__ == "__main__":

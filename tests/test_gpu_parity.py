@@ -472,3 +472,53 @@ def test_krylov_iteration_counts(pkg, ctx, solver, precon):
     assert its == its_ref
     assert relerr(op.to_host(xd), x_ref) < 1e-10
     assert res <= 1e-2 * np.linalg.norm(b) * (1 + 1e-8)
+
+
+# ---- orientation-aware compressed access on the device against the reference's golden and the oracle -------------------------------
+def test_reduced_access_orientation(pkg, ctx):
+    """ConstraintInfoReduced::read_dof_values / distribute_local_to_global with the packed orientation word
+    (include/vector_access_reduced.h:267-548, include/reduced_access.h:528-702): all 19 post-variant cases of the reference's
+    reduced_access_02.result bit-exactly, random orientation words against the oracle's adjust_for_orientation, and
+    distribute = read^T."""
+    import json
+    import os
+    import torch
+    from test_oracle_golden import _reduced_access_setup
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reduced_access_02.json")))
+    dev = torch.device("cuda", 0)
+    n_checked = 0
+    for case in gold:
+        degree, do_post, orientations = case["args"][0], case["args"][1], case["args"][2:]
+        dofs, g = _reduced_access_setup(3, degree)
+        word = o.compress_orientation(orientations, True)
+        cidx = torch.tensor(np.array(dofs, dtype=np.int64).reshape(1, 27), dtype=torch.int64, device=dev).to(torch.int32)
+        ori = torch.tensor([word], dtype=torch.int64, device=dev).to(torch.int32)
+        src = torch.tensor(g, dtype=torch.float64, device=dev)
+        loc = pkg.reduced_access_read(degree, cidx, ori, src)
+        assert [int(v) for v in loc[0].cpu().numpy()] == case["local"]  # (the pre and the post variant print the same vector)
+        n_checked += 1
+    assert n_checked == 38
+    # random words (line bits and quad flags 0 / 1, the pinned rows of the orientation table), several cells, degrees 2..5
+    rng = np.random.default_rng(3)
+    for degree in (2, 3, 5):
+        dofs, g = _reduced_access_setup(3, degree)
+        n_cells = 7
+        words, ref = [], []
+        table = o.orientation_table(degree - 1)
+        for c in range(n_cells):
+            orientations = list(rng.integers(0, 2, 18))
+            w = o.compress_orientation([int(v) for v in orientations], True)
+            words.append(w)
+            ref.append(o.gather_post([float(v) for v in g], 3, degree, dofs, w, table))
+        cidx = torch.tensor(np.tile(np.array(dofs, dtype=np.int64), (n_cells, 1)), device=dev).to(torch.int32)
+        ori = torch.tensor(np.array(words, dtype=np.int64), device=dev).to(torch.int32)
+        src = torch.tensor(g, dtype=torch.float64, device=dev)
+        loc = pkg.reduced_access_read(degree, cidx, ori, src)
+        assert np.array_equal(loc.cpu().numpy(), np.array(ref))
+        # transpose: <read(x), y> = <x, distribute(y)>
+        x = torch.rand(len(g), dtype=torch.float64, device=dev)
+        y = torch.rand((n_cells, (degree + 1) ** 3), dtype=torch.float64, device=dev)
+        rx = pkg.reduced_access_read(degree, cidx, ori, x)
+        dy = torch.zeros(len(g), dtype=torch.float64, device=dev)
+        pkg.reduced_access_distribute(degree, cidx, ori, dy, y)
+        assert abs(float((rx * y).sum()) - float((x * dy).sum())) < 1e-10

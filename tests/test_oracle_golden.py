@@ -258,3 +258,50 @@ def test_transfer_is_embedding_and_transpose():
     got = Pu[opf.idx[c_f]]
     keep = opf.mask[c_f] > 0
     assert np.allclose(got[keep], expect[keep], atol=1e-12)
+
+
+# ---- orientation-aware compressed access (include/reduced_access.h) against reduced_access_01.result / reduced_access_02.result ------
+def _reduced_access_setup(dim, degree):
+    """the dpo / entity tables of reduced_access_01.cc:33-58 and reduced_access_02.cc:36-66"""
+    if dim == 2:
+        dpo = [(4, 1), (4, degree - 1), (1, (degree - 1) ** 2)]
+        entities = [0, 6, 1, 4, 8, 5, 2, 7, 3]
+    else:
+        dpo = [(8, 1), (12, degree - 1), (6, (degree - 1) ** 2), (1, (degree - 1) ** 3)]
+        entities = [0, 10, 1, 8, 24, 9, 2, 11, 3, 16, 22, 17, 20, 26, 21, 18, 23, 19, 4, 14, 5, 12, 25, 13, 6, 15, 7]
+    dofs, counter = [], 0
+    for n_ent, size in dpo:
+        for _ in range(n_ent):
+            dofs.append(counter)
+            counter += size
+    return [dofs[e] for e in entities], list(range(counter))
+
+
+@pytest.mark.parametrize("name,dim", [("reduced_access_01", 2), ("reduced_access_02", 3)])
+def test_reduced_access_goldens(name, dim):
+    """every case of the reference's reduced_access_01.sh (10 cases, 2-D: line flips) and reduced_access_02.sh (38 cases, 3-D: 12 line
+    flips, 6 quad flags) reproduced bit-exactly, with the orientation applied during the gather (`gather`) and after it
+    (`gather_post` + `adjust_for_orientation`)."""
+    cases = json.load(open(os.path.join(GOLD, name + ".json")))
+    assert len(cases) == (10 if dim == 2 else 38)
+    for case in cases:
+        args = case["args"]
+        degree, do_post, orientations = args[0], bool(args[1]), args[2:]
+        if dim == 2:
+            orientations = args[1:5]  # reduced_access_01.cc:29-30 reads the four line flags from argv[2 + i] (argv[2] is also do_post)
+        assert len(orientations) == (4 if dim == 2 else 18)
+        dofs_of_cell, global_vector = _reduced_access_setup(dim, degree)
+        table = o.orientation_table(degree - 1)
+        if do_post:
+            got = o.gather_post(global_vector, dim, degree, dofs_of_cell, o.compress_orientation(orientations, True), table)
+        else:
+            got = o.gather_oriented(global_vector, dim, degree, dofs_of_cell, o.compress_orientation(orientations, False), table)
+        assert [int(v) for v in got] == case["local"], (name, args)
+    # both variants agree with each other on every case, and the standard orientation is the plain expansion
+    for case in cases:
+        degree, orientations = case["args"][0], (case["args"][1:5] if dim == 2 else case["args"][2:])
+        dofs_of_cell, g = _reduced_access_setup(dim, degree)
+        table = o.orientation_table(degree - 1)
+        a = o.gather_post(g, dim, degree, dofs_of_cell, o.compress_orientation(orientations, True), table)
+        b = o.gather_oriented(g, dim, degree, dofs_of_cell, o.compress_orientation(orientations, False), table)
+        assert list(a) == list(b)
