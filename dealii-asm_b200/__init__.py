@@ -59,7 +59,7 @@ def lib():
         _lib.dasm_ctx_stream.restype = ctypes.c_void_p
         for name in ("dasm_ctx_launch_count", "dasm_mesh_n_cells", "dasm_mesh_n_global_cells", "dasm_op_n_dofs",
                      "dasm_op_n_ghost", "dasm_op_n_import", "dasm_op_vec_size", "dasm_op_n_global_dofs", "dasm_op_constrained_dofs",
-                     "dasm_fdm_n_instances", "dasm_fdm_memory_consumption", "dasm_op_n_fast_bricks", "dasm_fdm_n_fast_bricks"):
+                     "dasm_fdm_n_instances", "dasm_fdm_memory_consumption", "dasm_op_n_fast_bricks", "dasm_fdm_n_fast_bricks", "dasm_op_n_cells"):
             getattr(_lib, name).restype = ctypes.c_longlong
     return _lib
 
@@ -208,9 +208,51 @@ class LaplaceOperatorMatrixFree:
         _check(lib().dasm_op_create(mesh.h, int(degree), self.ntype, mapping_type.encode(), int(compress_indices),
                                     ctypes.byref(self.h)))
 
+    @classmethod
+    def from_arrays(cls, ctx, vertices, cells, degree, support=None, dirichlet=True, number="double", mapping_type=""):
+        """operator on an unstructured all-hex mesh (the ball of element_centered_preconditioners_01.cc:398-402): vertices [V, 3],
+        cells [C, 8] (lexicographic vertex order), support [C, 27, 3] support points of the triquadratic cell map or None
+        (dealii-asm_b200/grid.py builds such arrays)."""
+        import torch
+        self = cls.__new__(cls)
+        self.mesh = None
+        self.ctx = ctx
+        self.degree = degree
+        self.number = number
+        self.ntype = F64 if number == "double" else F32
+        self.torch_dtype = torch.float64 if number == "double" else torch.float32
+        self.h = ctypes.c_void_p()
+        v = np.ascontiguousarray(vertices, dtype=np.float64)
+        c = np.ascontiguousarray(cells, dtype=np.uint32)
+        sp = np.ascontiguousarray(support, dtype=np.float64) if support is not None else None
+        _check(lib().dasm_op_create_unstructured(ctx.h, int(degree), self.ntype, mapping_type.encode(), ctypes.c_longlong(v.shape[0]),
+                                                 v.ctypes.data_as(ctypes.c_void_p), ctypes.c_longlong(c.shape[0]), c.ctypes.data_as(ctypes.c_void_p),
+                                                 sp.ctypes.data_as(ctypes.c_void_p) if sp is not None else None, int(bool(dirichlet)),
+                                                 ctypes.byref(self.h)))
+        return self
+
     # -- sizes
     def n_dofs(self):
         return lib().dasm_op_n_dofs(self.h)
+
+    def n_cells(self):
+        return lib().dasm_op_n_cells(self.h)
+
+    def orientations(self):
+        """packed orientation word per cell (unstructured meshes), include/reduced_access.h:66-152"""
+        out = np.zeros(self.n_cells(), dtype=np.uint32)
+        _check(lib().dasm_op_orientations(self.h, out.ctypes.data_as(ctypes.c_void_p)))
+        return out
+
+    def plain_indices(self):
+        out = np.zeros((self.n_cells(), (self.degree + 1) ** 3), dtype=np.uint32)
+        _check(lib().dasm_op_plain_indices(self.h, out.ctypes.data_as(ctypes.c_void_p)))
+        return out
+
+    def patch_extents(self):
+        out = np.zeros((self.n_cells(), 3, 3))
+        _check(lib().dasm_op_patch_extents(self.h, out.ctypes.data_as(ctypes.c_void_p)))
+        return out
 
     def n_fast_bricks(self):
         return lib().dasm_op_n_fast_bricks(self.h)
@@ -273,7 +315,7 @@ class LaplaceOperatorMatrixFree:
         _check(lib().dasm_op_inverse_diagonal(self.h, _ptr(diag)))
 
     def compressed_indices(self, plain=False):
-        out = np.zeros((self.mesh.n_cells, 27), dtype=np.uint32)
+        out = np.zeros((self.n_cells(), 27), dtype=np.uint32)
         lib().dasm_op_compressed_indices(self.h, int(plain), out.ctypes.data_as(ctypes.c_void_p))
         return out
 
@@ -482,6 +524,27 @@ class RestrictedPreconditioner:
             lib().dasm_asm_destroy(self.h)
         except Exception:
             pass
+
+
+def umesh_host_numbering(degree, vertices, cells, support=None, dirichlet=True):
+    """host-only (no device): numbering of an unstructured mesh as the library builds it: dict(n_dofs, n_lines, n_quads, cidx [C, 27],
+    orientation [C], plain [C, (k+1)^3], constrained, extents [C, 3, 3])"""
+    v = np.ascontiguousarray(vertices, dtype=np.float64)
+    c = np.ascontiguousarray(cells, dtype=np.uint32)
+    sp = np.ascontiguousarray(support, dtype=np.float64) if support is not None else None
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+    sizes = (ctypes.c_longlong * 4)()
+    args = (int(degree), ctypes.c_longlong(v.shape[0]), p(v), ctypes.c_longlong(c.shape[0]), p(c), p(sp), int(bool(dirichlet)), sizes)
+    _check(lib().dasm_umesh_host_numbering(*args, None, None, None, None, None))
+    n_dofs, n_lines, n_quads, n_con = [int(x) for x in sizes]
+    C = c.shape[0]
+    cidx = np.zeros((C, 27), dtype=np.uint32)
+    ori = np.zeros(C, dtype=np.uint32)
+    plain = np.zeros((C, (degree + 1) ** 3), dtype=np.uint32)
+    con = np.zeros(max(n_con, 1), dtype=np.uint32)
+    ext = np.zeros((C, 3, 3))
+    _check(lib().dasm_umesh_host_numbering(*args, p(cidx), p(ori), p(plain), p(con), p(ext)))
+    return dict(n_dofs=n_dofs, n_lines=n_lines, n_quads=n_quads, cidx=cidx, orientation=ori, plain=plain, constrained=con[:n_con], extents=ext)
 
 
 def reduced_access_read(degree, cidx, orientation, src):

@@ -263,7 +263,7 @@ dasm_asm_create(dasm_fdm *layout, dasm_asm **out)
   a->ntype   = dasm_op_number_type(a->op);
   const int m = dasm_fdm_patch_size_1d(layout);
   a->m3      = m * m * m;
-  a->n_cells = dasm_mesh_n_cells(dasm_op_mesh(a->op));
+  a->n_cells = dasm_op_n_cells(a->op);
   if (dasm_op_n_ghost(a->op) > 0)
     throw std::runtime_error("exact-block ASM is built for one rank (the coloured probing writes owned DoFs only)");
   const size_t es = a->ntype == DASM_F64 ? 8 : 4;
@@ -355,7 +355,7 @@ dasm_fdm_patches_host(dasm_fdm *fdm, uint32_t *idx, double *w, int *w_pre, int *
   BA_API_BEGIN
   dasm_op *       op = dasm_fdm_op(fdm);
   const int       m  = dasm_fdm_patch_size_1d(fdm);
-  const size_t    n  = (size_t)dasm_mesh_n_cells(dasm_op_mesh(op)) * m * m * m;
+  const size_t    n  = (size_t)dasm_op_n_cells(op) * m * m * m;
   const bool      f64 = dasm_op_number_type(op) == DASM_F64;
   cudaStream_t    s   = (cudaStream_t)dasm_ctx_stream(dasm_op_ctx(op));
   uint32_t *      d_idx = nullptr;

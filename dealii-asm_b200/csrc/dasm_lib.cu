@@ -21,6 +21,7 @@
 #include "kernels_brick.cuh"
 #include "kernels_fast.cuh"
 #include "mesh.h"
+#include "unstructured.h"
 #include "tma_launch.h"
 
 using namespace dasm;
@@ -412,6 +413,9 @@ struct dasm_op
   long long         n_global_dofs;
   uint32_t *        d_cidx        = nullptr;
   uint32_t *        d_plain       = nullptr; // compress_indices = false: (k+1)^3 indices per cell (operator.h:1343-1350, plain branch)
+  // unstructured hex mesh (csrc/unstructured.h; mesh == nullptr): 27 start indices + orientation word per cell, expanded to d_plain
+  std::unique_ptr<UMesh> umesh;
+  std::vector<uint32_t>  h_plain;
   uint32_t *        d_constrained = nullptr;
   long long         n_constrained = 0;
   int               geom_mode     = 0; // 0 cartesian, 1 merged, 2 quadratic / linear coefficients (brick kernel)
@@ -1336,7 +1340,7 @@ launch_fdm(dasm_fdm *f, T *dst, const T *src)
 static bool
 fdm_needs_compression(const dasm_fdm *f)
 {
-  return f->weight_type != DASM_WEIGHT_RAS || f->op->mesh->mesh->n_ranks() > 1;
+  return f->weight_type != DASM_WEIGHT_RAS || (f->op->mesh != nullptr && f->op->mesh->mesh->n_ranks() > 1);
 }
 
 template <int K, typename T>
@@ -2682,6 +2686,158 @@ dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping
   DASM_API_END
 }
 
+// LaplaceOperatorMatrixFree on an unstructured all-hex mesh given by arrays (SURVEY 8(b) dasm_mesh_create_from_arrays; the ball of
+// element_centered_preconditioners_01.cc:398-402).  Connectivity, orientation words, compressed indices and geometry: csrc/unstructured.h.
+// The generic kernels run it: (k+1)^3 oriented addresses per cell (= read_dof_values of ConstraintInfoReduced with the orientation
+// word, vector_access_reduced.h:267-405, expanded once at set-up) and merged coefficients or quadrature points per cell.
+extern "C" int
+dasm_op_create_unstructured(dasm_ctx *ctx, int degree, int number_type, const char *mapping_type, long long n_vertices, const double *coords,
+                            long long n_cells, const uint32_t *cell_vertices, const double *support_points, int dirichlet, dasm_op **out)
+{
+  DASM_API_BEGIN
+  DASM_REQUIRE(degree >= 1 && degree <= MAX_DEGREE, "degree must be in 1..8");
+  DASM_REQUIRE(number_type == DASM_F64 || number_type == DASM_F32, "unknown number type");
+  DASM_REQUIRE(ctx != nullptr, "unstructured operator: context required");
+  DASM_REQUIRE(n_vertices > 0 && n_cells > 0 && coords != nullptr && cell_vertices != nullptr, "unstructured mesh: empty mesh");
+  const std::string mt = mapping_type ? mapping_type : "";
+  if (mt != "" && mt != "merged" && mt != "construct q")
+    {
+      if (mt == "quadratic geometry" || mt == "linear geometry")
+        throw std::runtime_error("Mapping type <" + mt + "> is built for structured meshes only (brick kernels); use \"merged\" or \"construct q\"");
+      throw std::runtime_error("Mapping type <" + mt + "> is not known!"); // operator.h:747-752
+    }
+  std::unique_ptr<UMesh> U(new UMesh);
+  U->n_vertices = n_vertices;
+  U->n_cells    = n_cells;
+  U->dirichlet  = dirichlet != 0;
+  U->coords.assign(coords, coords + 3 * n_vertices);
+  U->cells.assign(cell_vertices, cell_vertices + 8 * n_cells);
+  if (support_points)
+    U->support.assign(support_points, support_points + 81 * n_cells);
+  U->build();
+  UMesh::Numbering un = U->number_dofs(degree);
+  auto             op = new dasm_op(degree);
+  op->ctx              = ctx;
+  op->mesh             = nullptr;
+  op->k                = degree;
+  op->ntype            = number_type;
+  op->compress_indices = true; // 27 start indices + orientation word per cell are the stored format; the kernels read their expansion
+  op->mapping_type     = mt;
+  op->n_cells          = n_cells;
+  op->n_owned          = un.n_dofs;
+  op->n_ghost          = 0;
+  op->n_vec            = un.n_dofs;
+  op->n_global_dofs    = un.n_dofs;
+  op->nb.k             = degree;
+  op->nb.n_owned       = (uint32_t)un.n_dofs;
+  op->nb.cidx          = un.cidx;
+  op->nb.cidx_plain    = un.cidx_plain;
+  op->nb.constrained   = un.constrained;
+  op->h_plain          = std::move(un.plain);
+    {
+      CUDA_CHECK(cudaSetDevice(ctx->device));
+      op->d_cidx        = dev_upload(op->nb.cidx, ctx->stream);
+      op->d_plain       = dev_upload(op->h_plain, ctx->stream);
+      op->d_constrained = dev_upload(op->nb.constrained, ctx->stream);
+      op->n_constrained = (long long)op->nb.constrained.size();
+      op->exchange.init(ctx, op->nb.exchange, op->esize());
+      const int n3      = (degree + 1) * (degree + 1) * (degree + 1);
+      const int per     = (mt == "construct q") ? 3 * n3 : 6 * n3;
+      op->geom_mode     = (mt == "construct q") ? 3 : 1;
+      std::vector<double> g((size_t)n_cells * per);
+      for (long long c = 0; c < n_cells; ++c)
+        if (op->geom_mode == 3)
+          U->cell_geometry(c, op->basis, g.data() + (size_t)c * per, nullptr, nullptr);
+        else
+          U->cell_geometry(c, op->basis, nullptr, nullptr, g.data() + (size_t)c * per);
+      if (number_type == DASM_F64)
+        op->d_geom = dev_upload(g, ctx->stream);
+      else
+        {
+          std::vector<float> gf(g.begin(), g.end());
+          op->d_geom = dev_upload(gf, ctx->stream);
+        }
+      op->cart.g[0] = op->cart.g[1] = op->cart.g[2] = 0;
+    }
+  op->use_brick = false;
+  op->umesh     = std::move(U);
+  *out          = op;
+  DASM_API_END
+}
+
+// host-only (no device): connectivity, numbering and patch extents of an unstructured mesh.  sizes = {n_dofs, n_lines, n_quads,
+// n_constrained}; every output array may be NULL (first call: sizes only).  cidx [cell][27] (constrained entities invalid),
+// orientation [cell], plain [cell][(k+1)^3], constrained [n_constrained], extents [cell][3][3]
+extern "C" int
+dasm_umesh_host_numbering(int degree, long long n_vertices, const double *coords, long long n_cells, const uint32_t *cell_vertices,
+                          const double *support_points, int dirichlet, long long sizes[4], uint32_t *cidx, uint32_t *orientation, uint32_t *plain,
+                          uint32_t *constrained, double *extents)
+{
+  DASM_API_BEGIN
+  DASM_REQUIRE(degree >= 1 && degree <= MAX_DEGREE, "degree must be in 1..8");
+  UMesh U;
+  U.n_vertices = n_vertices;
+  U.n_cells    = n_cells;
+  U.dirichlet  = dirichlet != 0;
+  U.coords.assign(coords, coords + 3 * n_vertices);
+  U.cells.assign(cell_vertices, cell_vertices + 8 * n_cells);
+  if (support_points)
+    U.support.assign(support_points, support_points + 81 * n_cells);
+  U.build();
+  const UMesh::Numbering un = U.number_dofs(degree);
+  sizes[0] = un.n_dofs;
+  sizes[1] = U.n_lines;
+  sizes[2] = U.n_quads;
+  sizes[3] = (long long)un.constrained.size();
+  if (cidx)
+    memcpy(cidx, un.cidx.data(), un.cidx.size() * sizeof(uint32_t));
+  if (orientation)
+    memcpy(orientation, U.orientation.data(), U.orientation.size() * sizeof(uint32_t));
+  if (plain)
+    memcpy(plain, un.plain.data(), un.plain.size() * sizeof(uint32_t));
+  if (constrained && !un.constrained.empty())
+    memcpy(constrained, un.constrained.data(), un.constrained.size() * sizeof(uint32_t));
+  if (extents)
+    {
+      const Basis1D             b(degree);
+      const std::vector<double> e = U.patch_extents(b);
+      memcpy(extents, e.data(), e.size() * sizeof(double));
+    }
+  DASM_API_END
+}
+
+// the packed orientation word per cell (12 line bits + 6 x 3 quad bits) and the (k+1)^3 oriented addresses per cell (host copies)
+extern "C" int
+dasm_op_orientations(const dasm_op *op, uint32_t *out)
+{
+  DASM_API_BEGIN
+  DASM_REQUIRE(op->umesh != nullptr, "orientation words exist for operators on unstructured meshes (structured meshes: all standard)");
+  memcpy(out, op->umesh->orientation.data(), op->umesh->orientation.size() * sizeof(uint32_t));
+  DASM_API_END
+}
+
+extern "C" int
+dasm_op_plain_indices(const dasm_op *op, uint32_t *out)
+{
+  DASM_API_BEGIN
+  DASM_REQUIRE(op->umesh != nullptr, "plain index export is provided for operators on unstructured meshes");
+  memcpy(out, op->h_plain.data(), op->h_plain.size() * sizeof(uint32_t));
+  DASM_API_END
+}
+
+extern "C" long long dasm_op_n_cells(const dasm_op *op) { return op->n_cells; }
+
+// harmonic patch extents [cell][3][3] of an unstructured operator (grid_tools.h:54-138), for inspection
+extern "C" int
+dasm_op_patch_extents(const dasm_op *op, double *out)
+{
+  DASM_API_BEGIN
+  DASM_REQUIRE(op->umesh != nullptr, "patch extent export is provided for operators on unstructured meshes");
+  const std::vector<double> e = op->umesh->patch_extents(op->basis);
+  memcpy(out, e.data(), e.size() * sizeof(double));
+  DASM_API_END
+}
+
 extern "C" int
 dasm_op_destroy(dasm_op *op)
 {
@@ -2729,6 +2885,7 @@ extern "C" int
 dasm_mesh_global_size(const dasm_mesh *mesh, int n_cells[3], int periodic[3])
 {
   DASM_API_BEGIN
+  DASM_REQUIRE(mesh != nullptr, "this operation needs an operator on a structured mesh (the operator was built on an unstructured one)");
   for (int d = 0; d < 3; ++d)
     {
       n_cells[d]  = mesh->mesh->p.nc[d];
@@ -2786,11 +2943,11 @@ op_inverse_diagonal(dasm_op *op, T *diag)
     constexpr int   n3    = (K + 1) * (K + 1) * (K + 1);
     const long long total = op->n_cells * n3;
     if (op->geom_mode == 0)
-      laplace_diagonal_kernel<K, T, 0><<<nblocks(total, 128), 128, 0, ctx->stream>>>(diag, op->d_cidx, (const T *)nullptr, op->cart, op->n_cells);
+      laplace_diagonal_kernel<K, T, 0><<<nblocks(total, 128), 128, 0, ctx->stream>>>(diag, op->d_cidx, (const T *)nullptr, op->cart, op->n_cells, op->d_plain);
     else if (op->geom_mode == 3)
-      laplace_diagonal_kernel<K, T, 2><<<nblocks(total, 128), 128, 0, ctx->stream>>>(diag, op->d_cidx, (const T *)op->d_geom, op->cart, op->n_cells);
+      laplace_diagonal_kernel<K, T, 2><<<nblocks(total, 128), 128, 0, ctx->stream>>>(diag, op->d_cidx, (const T *)op->d_geom, op->cart, op->n_cells, op->d_plain);
     else
-      laplace_diagonal_kernel<K, T, 1><<<nblocks(total, 128), 128, 0, ctx->stream>>>(diag, op->d_cidx, (const T *)op->d_geom, op->cart, op->n_cells);
+      laplace_diagonal_kernel<K, T, 1><<<nblocks(total, 128), 128, 0, ctx->stream>>>(diag, op->d_cidx, (const T *)op->d_geom, op->cart, op->n_cells, op->d_plain);
   });
   ctx->launches++;
   op->exchange.run<T>(diag, true);
@@ -2834,6 +2991,11 @@ dasm_op_merged_coefficients(const dasm_op *op, long long cell, double *out)
 {
   DASM_API_BEGIN
   DASM_REQUIRE(cell >= 0 && cell < op->n_cells, "cell out of range");
+  if (op->umesh)
+    {
+      op->umesh->cell_geometry(cell, op->basis, nullptr, nullptr, out);
+      return 0;
+    }
   const Mesh &M    = *op->mesh->mesh;
   const int   c[3] = {M.cell_ijk[cell][0], M.cell_ijk[cell][1], M.cell_ijk[cell][2]};
   M.merged_coefficients(c, op->basis, out, op->linear_geometry);
@@ -2848,14 +3010,19 @@ dasm_op_rhs_constant(dasm_op *op, void *vec, double value)
 {
   DASM_API_BEGIN
   CUDA_CHECK(cudaSetDevice(op->ctx->device));
-  const Mesh &        M = *op->mesh->mesh;
   const int           k = op->k, n = k + 1, n3 = n * n * n;
   const Basis1D &     b = op->basis;
   std::vector<double> host((size_t)op->n_vec, 0.), jxw(n3), t0(n3), t1(n3);
   for (long long c = 0; c < op->n_cells; ++c)
     {
-      const int cc[3] = {M.cell_ijk[c][0], M.cell_ijk[c][1], M.cell_ijk[c][2]};
-      M.jxw(cc, b, jxw.data(), op->linear_geometry);
+      if (op->umesh)
+        op->umesh->cell_geometry(c, b, nullptr, jxw.data(), nullptr);
+      else
+        {
+          const Mesh &M     = *op->mesh->mesh;
+          const int   cc[3] = {M.cell_ijk[c][0], M.cell_ijk[c][1], M.cell_ijk[c][2]};
+          M.jxw(cc, b, jxw.data(), op->linear_geometry);
+        }
       // local vector = (N^T x N^T x N^T) (f JxW), N[q*n+i]
       for (int qz = 0; qz < n; ++qz)
         for (int qy = 0; qy < n; ++qy)
@@ -2883,7 +3050,7 @@ dasm_op_rhs_constant(dasm_op *op, void *vec, double value)
               double s = 0;
               for (int qz = 0; qz < n; ++qz)
                 s += b.N[qz * n + l] * t1[(qz * n + j) * n + i];
-              const uint32_t g = expand_start_index(ci, k, i, j, l);
+              const uint32_t g = op->umesh ? op->h_plain[(size_t)c * n3 + (l * n + j) * n + i] : expand_start_index(ci, k, i, j, l);
               if (g != INVALID_INDEX)
                 host[g] += s;
             }
@@ -3129,6 +3296,82 @@ fdm_setup_device(dasm_fdm *f, const std::vector<double> &S, const std::vector<do
     cudaFree(d_full);
 }
 
+// ASPoissonPreconditioner on an unstructured mesh (include/matrix_free.h:73-894 with the unstructured pieces: grid_tools.h:54-138 for
+// the patch extents; experiments/ball.py generates n overlap = 1 only): one patch per cell in the cell's own frame, the patch indices
+// are the cell's (k+1)^3 oriented addresses, 1-D matrices from the cell's extent and those of the face neighbours, Dirichlet rows on
+// boundary faces; weights through the explicit-list path (valence per DoF; RAS: the cell with the smallest index keeps a DoF)
+static dasm_fdm *
+fdm_create_unstructured(dasm_op *op, int n_overlap, int weight_type, int weight_sequence, int element_centric)
+{
+  const int    k = op->k, n = k + 1, n3 = n * n * n;
+  const UMesh &U = *op->umesh;
+  if (n_overlap != 1 || !element_centric)
+    throw std::runtime_error("unstructured meshes: element-centred patches with n overlap = 1 only (as generated for the ball, experiments/ball.py:71-73)");
+  if (k < 2)
+    throw std::runtime_error("unstructured meshes: the explicit-list FDM kernel is instantiated for degrees >= 2");
+  auto f             = new dasm_fdm;
+  f->op              = op;
+  f->use_ext         = false;
+  f->n_overlap       = 1;
+  f->weight_type     = weight_type;
+  f->weight_sequence = (weight_sequence == DASM_WSEQ_COMPRESSED) ? DASM_WSEQ_DG : weight_sequence; // (27 weights per cell need the standard orientation)
+  f->element_centric = 1;
+  f->m               = n;
+  const std::vector<double> ext = U.patch_extents(op->basis);
+  std::map<std::array<uint64_t, 4>, uint32_t> cache;
+  std::vector<double>                         S_all, lam_all;
+  f->h_inst.resize((size_t)op->n_cells * 3);
+  for (long long c = 0; c < op->n_cells; ++c)
+    for (int d = 0; d < 3; ++d)
+      {
+        const double *e3   = ext.data() + (c * 3 + d) * 3;
+        const int     bt[2] = {U.face_at_boundary(c, 2 * d) ? (U.dirichlet ? 1 : 2) : 0, U.face_at_boundary(c, 2 * d + 1) ? (U.dirichlet ? 1 : 2) : 0};
+        std::array<uint64_t, 4> key;
+        memcpy(&key[0], &e3[0], 8);
+        memcpy(&key[1], &e3[1], 8);
+        memcpy(&key[2], &e3[2], 8);
+        key[3]  = (uint64_t)(bt[0] * 3 + bt[1]);
+        auto it = cache.find(key);
+        if (it == cache.end())
+          {
+            std::vector<double> Mm, Km, S, lam;
+            laplace_tp_matrix_1d(op->basis, e3, bt, 1, Mm, Km);
+            generalized_eig(n, Mm, Km, S, lam);
+            it = cache.emplace(key, (uint32_t)cache.size()).first;
+            S_all.insert(S_all.end(), S.begin(), S.end());
+            lam_all.insert(lam_all.end(), lam.begin(), lam.end());
+          }
+        f->h_inst[c * 3 + d] = it->second;
+      }
+  f->n_instances = (long long)cache.size();
+  f->h_S         = S_all;
+  f->h_lam       = lam_all;
+  f->d_inst      = dev_upload(f->h_inst, op->ctx->stream);
+  f->d_pidx      = dev_upload(op->h_plain, op->ctx->stream);
+  std::vector<float> ras_cw;
+  if (weight_type == DASM_WEIGHT_RAS)
+    {
+      std::vector<uint32_t> winner((size_t)op->n_owned, INVALID_INDEX);
+      for (long long c = op->n_cells - 1; c >= 0; --c)
+        for (int i = 0; i < n3; ++i)
+          {
+            const uint32_t g = op->h_plain[(size_t)c * n3 + i];
+            if (g != INVALID_INDEX)
+              winner[g] = (uint32_t)c;
+          }
+      ras_cw.assign((size_t)op->n_cells * n3, 0.f);
+      for (long long c = 0; c < op->n_cells; ++c)
+        for (int i = 0; i < n3; ++i)
+          {
+            const uint32_t g = op->h_plain[(size_t)c * n3 + i];
+            if (g != INVALID_INDEX && winner[g] == (uint32_t)c)
+              ras_cw[(size_t)c * n3 + i] = 1.f;
+          }
+    }
+  DISPATCH_TYPE(op->ntype, fdm_setup_device<T>(f, S_all, lam_all, ras_cw));
+  return f;
+}
+
 extern "C" int
 dasm_fdm_create(dasm_op *op, int n_overlap, int sub_mesh_approximation, int weight_type, int weight_sequence, int overlap_pre_post,
                 int element_centric, dasm_fdm **out)
@@ -3141,6 +3384,11 @@ dasm_fdm_create(dasm_op *op, int n_overlap, int sub_mesh_approximation, int weig
   DASM_REQUIRE(weight_sequence >= 0 && weight_sequence <= 3, "weight sequence is not known!");
   const int k = op->k;
   n_overlap   = std::min(std::max(n_overlap, 1), k); // precondition.templates.h:195-196
+  if (op->umesh)
+    {
+      *out = fdm_create_unstructured(op, n_overlap, weight_type, weight_sequence, element_centric);
+      return 0;
+    }
   const Mesh &M = *op->mesh->mesh;
   if ((n_overlap > 1 || !element_centric) && M.n_ranks() > 1)
     DASM_REQUIRE(!op->halo.exchange.empty() || op->halo.cells.empty(),

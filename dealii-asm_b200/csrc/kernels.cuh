@@ -354,7 +354,8 @@ namespace dasm
                           const uint32_t *__restrict__ cidx,
                           const T *__restrict__ geom,
                           const CartesianCoef cart,
-                          const long long     n_cells)
+                          const long long     n_cells,
+                          const uint32_t *__restrict__ plain = nullptr) // n^3 indices per cell (plain storage / unstructured meshes)
   {
     constexpr int   n = k + 1, n3 = n * n * n;
     const long long gid  = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -392,7 +393,7 @@ namespace dasm
                      2 * ((double)G[1] * gx * gy + (double)G[2] * gx * gz + (double)G[4] * gy * gz);
               }
           }
-    const uint32_t gi = compressed_index<k>(cidx + cell * 27, ix, iy, iz);
+    const uint32_t gi = plain ? plain[gid] : compressed_index<k>(cidx + cell * 27, ix, iy, iz);
     if (gi != DEV_INVALID)
       atomic_add(diag + gi, (T)s);
   }

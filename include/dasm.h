@@ -269,6 +269,28 @@ extern "C"
   int  dasm_fdm_patches_host(dasm_fdm *fdm, uint32_t *idx, double *w, int *w_pre, int *w_post);
   void dasm_set_last_error(const char *msg);
 
+  /* ---- Unstructured all-hex meshes (BASELINE configs[3]: the ball, element_centered_preconditioners_01.cc:398-402; SURVEY 8(b)
+   *      dasm_mesh_create_from_arrays) ------------------------------------------------------------------------------------------
+   * The mesh comes as arrays: 3 coordinates per vertex, 8 vertices per cell in lexicographic order (x fastest, deal.II's vertex order)
+   * and, optionally, the 27 support points per cell of a triquadratic cell map (MappingQCache(2), lexicographic; NULL: trilinear
+   * cells from the vertices).  The library derives lines / quads, the packed orientation word per cell and the 3^3 compressed start
+   * indices (ConstraintInfoReduced, include/vector_access_reduced.h:30-164, include/reduced_access.h:154-285); DoFs of boundary
+   * entities are constrained when `dirichlet` is set.  mapping_type: "" or "merged" (6 coefficients per quadrature point), "construct
+   * q".  The operator works with dasm_op_vmult*, dasm_op_inverse_diagonal, dasm_op_rhs_constant, dasm_fdm_create (n overlap = 1,
+   * all weighting types incl. ras; weight sequences global / local / dg), dasm_cheb_* and dasm_solve; multigrid transfers and the
+   * exact-block ASM need a structured mesh.  One rank. */
+  int dasm_op_create_unstructured(dasm_ctx *ctx, int degree, int number_type, const char *mapping_type, long long n_vertices,
+                                  const double *coords, long long n_cells, const uint32_t *cell_vertices, const double *support_points,
+                                  int dirichlet, dasm_op **out);
+  int dasm_op_orientations(const dasm_op *op, uint32_t *out);          /* [n_cells] */
+  int dasm_op_plain_indices(const dasm_op *op, uint32_t *out);         /* [n_cells][(k+1)^3] oriented addresses, host copy */
+  int dasm_op_patch_extents(const dasm_op *op, double *out);           /* [n_cells][3][3], include/grid_tools.h:54-138 */
+  long long dasm_op_n_cells(const dasm_op *op);
+  /* host-only (no device needed): sizes = {n_dofs, n_lines, n_quads, n_constrained}; output arrays may be NULL */
+  int dasm_umesh_host_numbering(int degree, long long n_vertices, const double *coords, long long n_cells, const uint32_t *cell_vertices,
+                                const double *support_points, int dirichlet, long long sizes[4], uint32_t *cidx, uint32_t *orientation,
+                                uint32_t *plain, uint32_t *constrained, double *extents);
+
   /* ---- Orientation-aware compressed vector access (ConstraintInfoReduced::read_dof_values / distribute_local_to_global,
    *      include/vector_access_reduced.h:267-548, with adjust_for_orientation, include/reduced_access.h:528-702) ------------------
    * d_cidx: 27 start indices per cell (0xFFFFFFFF = constrained), d_orientation: one packed word per cell (12 line bits + 6 x 3 quad

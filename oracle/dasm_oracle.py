@@ -716,6 +716,8 @@ def harmonic_cell_extents(mesh, basis):
 
 def harmonic_patch_extents(mesh, basis):
     """result[c,d,:] = (left neighbour extent or 0, own, right neighbour extent or 0)."""
+    if hasattr(mesh, "harmonic_patch_extents"):
+        return mesh.harmonic_patch_extents(basis)   # unstructured meshes: through the faces (UnstructuredMesh below)
     ext = harmonic_cell_extents(mesh, basis)
     out = np.zeros((mesh.C, mesh.dim, 3))
     for c in range(mesh.C):
@@ -1611,3 +1613,198 @@ def gather_oriented(global_vector, dim, degree, dofs_of_cell, orientation_in, ta
         else:
             offset_k += 1
     return out
+
+
+# --------------------------------------------------------------------------------------
+# Unstructured all-hex meshes (the ball of element_centered_preconditioners_01.cc:398-402): entity connectivity, the packed
+# orientation word of a cell and the 3^3 compressed indices that deal.II's DoFHandler / ConstraintInfoReduced::initialize
+# (include/vector_access_reduced.h:30-164, include/reduced_access.h:154-285) provide in the reference, restated for a mesh given by
+# arrays.  parity unpinned against deal.II's own numbering (a permutation of it); the expansion is the pinned
+# adjust_for_orientation above.
+# --------------------------------------------------------------------------------------
+class UnstructuredMesh:
+    """vertices [V, 3]; cells [C, 8] vertex numbers in lexicographic order; support [C, 27, 3] support points of the triquadratic
+    cell map (lexicographic; None: trilinear from the vertices).  An entity (line, quad) takes its frame from the first cell that
+    contains it: a line is flipped in a cell that runs it the other way, the code f of a quad is the row of orientation_table
+    under which the entity's DoFs appear in the cell's face layout."""
+    dim = 3
+
+    def __init__(self, vertices, cells, support=None, dirichlet=True):
+        self.vertices = np.asarray(vertices, dtype=np.float64)
+        self.cells = np.asarray(cells, dtype=np.int64)
+        self.C = self.cells.shape[0]
+        self.dirichlet = bool(dirichlet)
+        self.cell_order = np.arange(self.C)
+        if support is None:
+            r = np.array([0.0, 0.5, 1.0])
+            w = np.stack([1 - r, r], axis=-1)                                       # [3, 2]
+            Xv = self.vertices[self.cells].reshape(self.C, 2, 2, 2, 3)              # [c, z, y, x, :]
+            support = np.einsum("kz,jy,ix,nzyxd->nkjid", w, w, w, Xv).reshape(self.C, 27, 3)
+        self.support = np.asarray(support, dtype=np.float64).reshape(self.C, 27, 3)
+        self._connect()
+
+    # local description of the 27 entities: e = ex + 3 ey + 9 ez, component 1 = "runs along this direction"
+    @staticmethod
+    def _corners(e):
+        c = (e % 3, (e // 3) % 3, e // 9)
+        free = [d for d in range(3) if c[d] == 1]
+        out = []
+        for p in range(2 ** len(free)):
+            bits = [cc // 2 for cc in c]
+            for t, d in enumerate(free):
+                bits[d] = (p >> t) & 1
+            out.append(bits[0] + 2 * bits[1] + 4 * bits[2])
+        return out
+
+    @staticmethod
+    def _line_number(e):
+        ex, ey, ez = e % 3, (e // 3) % 3, e // 9
+        if ex == 1:
+            return (ey == 2) + 2 * (ez == 2)
+        if ey == 1:
+            return 4 + (ex == 2) + 2 * (ez == 2)
+        return 8 + (ex == 2) + 2 * (ey == 2)
+
+    @staticmethod
+    def _quad_number(e):
+        c = (e % 3, (e // 3) % 3, e // 9)
+        d = [i for i in range(3) if c[i] != 1][0]
+        return 2 * d + (c[d] == 2)
+
+    def _connect(self):
+        t2 = orientation_table(2)                       # corner version of the 8 codes: entity corner q sits at local corner t2[f][q]
+        lines, quads = {}, {}
+        self.entity = np.zeros((self.C, 27), dtype=np.int64)
+        self.orientation = np.zeros(self.C, dtype=np.int64)
+        self.quad_cells = []
+        for c in range(self.C):
+            cv = self.cells[c]
+            word = 0
+            for e in range(27):
+                loc = [int(cv[v]) for v in self._corners(e)]
+                if len(loc) == 1:
+                    self.entity[c, e] = loc[0]
+                elif len(loc) == 2:
+                    key = (min(loc), max(loc))
+                    if key not in lines:
+                        lines[key] = (len(lines), loc[0])
+                    self.entity[c, e] = lines[key][0]
+                    if lines[key][1] != loc[0]:
+                        word |= 1 << self._line_number(e)
+                elif len(loc) == 4:
+                    key = tuple(sorted(loc))
+                    if key not in quads:
+                        quads[key] = (len(quads), loc)
+                        self.quad_cells.append([c])
+                    else:
+                        self.quad_cells[quads[key][0]].append(c)
+                    qid, frame = quads[key]
+                    self.entity[c, e] = qid
+                    code = [f for f in range(8) if all(loc[t2[f][q]] == frame[q] for q in range(4))]
+                    word |= code[0] << (12 + 3 * self._quad_number(e))
+                else:
+                    self.entity[c, e] = c
+            self.orientation[c] = word
+        self.n_lines, self.n_quads = len(lines), len(quads)
+        V = self.vertices.shape[0]
+        self.quad_bnd = np.array([len(q) == 1 for q in self.quad_cells])
+        self.vertex_bnd = np.zeros(V, dtype=bool)
+        self.line_bnd = np.zeros(self.n_lines, dtype=bool)
+        for c in range(self.C):
+            for fe in (12, 14, 10, 16, 4, 22):
+                if self.quad_bnd[self.entity[c, fe]]:
+                    fc = (fe % 3, (fe // 3) % 3, fe // 9)
+                    d = [i for i in range(3) if fc[i] != 1][0]
+                    for e in range(27):
+                        ec = (e % 3, (e // 3) % 3, e // 9)
+                        if ec[d] != fc[d]:
+                            continue
+                        nd = sum(1 for x in ec if x == 1)
+                        if nd == 0:
+                            self.vertex_bnd[self.entity[c, e]] = True
+                        elif nd == 1:
+                            self.line_bnd[self.entity[c, e]] = True
+
+    def number_dofs(self, k):
+        """returns (cell_dofs [C, n^3] oriented addresses with INVALID on constrained entities, n_dofs, constrained mask,
+        compressed [C, 27] with constrained entities INVALID, compressed_plain)."""
+        V = self.vertices.shape[0]
+        pl, pq, ph = k - 1, (k - 1) ** 2, (k - 1) ** 3
+        line0 = V
+        quad0 = line0 + self.n_lines * pl
+        hex0 = quad0 + self.n_quads * pq
+        n_dofs = hex0 + self.C * ph
+        comp_plain = np.zeros((self.C, 27), dtype=np.int64)
+        bnd = np.zeros((self.C, 27), dtype=bool)
+        for e in range(27):
+            nd = (e % 3 == 1) + ((e // 3) % 3 == 1) + (e // 9 == 1)
+            ids = self.entity[:, e]
+            if nd == 0:
+                comp_plain[:, e], bnd[:, e] = ids, self.vertex_bnd[ids]
+            elif nd == 1:
+                comp_plain[:, e], bnd[:, e] = line0 + ids * pl, self.line_bnd[ids]
+            elif nd == 2:
+                comp_plain[:, e], bnd[:, e] = quad0 + ids * pq, self.quad_bnd[ids]
+            else:
+                comp_plain[:, e] = hex0 + ids * ph
+        comp = np.where(bnd & self.dirichlet, int(INVALID), comp_plain)
+        constrained = np.zeros(n_dofs, dtype=bool)
+        if self.dirichlet:
+            constrained[np.nonzero(self.vertex_bnd)[0]] = True
+            for l in np.nonzero(self.line_bnd)[0]:
+                constrained[line0 + l * pl: line0 + (l + 1) * pl] = True
+            for q in np.nonzero(self.quad_bnd)[0]:
+                constrained[quad0 + q * pq: quad0 + (q + 1) * pq] = True
+        std = expand_compressed(comp.astype(np.uint32), k, 3).astype(np.int64)
+        table = orientation_table(k - 1)
+        cell_dofs = np.zeros_like(std)
+        for c in range(self.C):
+            cell_dofs[c] = adjust_for_orientation(3, k, list(std[c]), int(self.orientation[c]), table, False)
+        return cell_dofs, n_dofs, constrained, comp.astype(np.uint32), comp_plain.astype(np.uint32)
+
+    # ---- geometry (MappingQCache(2) data = the support points) ------------------------------------------------------------------
+    def cell_ijk(self, c):
+        return c
+
+    def neighbor(self, c, d, side):
+        """anything but None when the face 2 d + side is interior (FDMPreconditioner only asks whether there is a neighbour)."""
+        fe = (12, 14, 10, 16, 4, 22)[2 * d + side]
+        return None if self.quad_bnd[self.entity[c, fe]] else True
+
+    def cell_points(self, c, ref):
+        nodes = np.array([0.0, 0.5, 1.0])
+        ref = np.asarray(ref)
+        Vs = [lagrange(nodes, ref[..., d].reshape(-1))[0] for d in range(3)]
+        X = self.support[c].reshape(3, 3, 3, 3)
+        return np.einsum("pk,pj,pi,kjid->pd", Vs[2], Vs[1], Vs[0], X).reshape(ref.shape[:-1] + (3,))
+
+    def jacobians(self, basis):
+        nodes = np.array([0.0, 0.5, 1.0])
+        V, D = lagrange(nodes, basis.qp)
+        nq = basis.n
+        J = np.zeros((self.C, nq ** 3, 3, 3))
+        X = self.support.reshape(self.C, 3, 3, 3, 3)
+        for e in range(3):
+            mats = [D if d == e else V for d in range(3)]
+            g = np.einsum("ck,bj,ai,nkjid->ncbad", mats[2], mats[1], mats[0], X)
+            J[:, :, :, e] = g.reshape(self.C, nq ** 3, 3)
+        return J
+
+    def harmonic_patch_extents(self, basis):
+        """include/grid_tools.h:54-138: every cell adds its extent normal to a face to that face; a neighbour's extent is the
+        face total minus the own one (0 on the boundary)."""
+        ext = harmonic_cell_extents(self, basis)
+        face = np.zeros(self.n_quads)
+        fes = (12, 14, 10, 16, 4, 22)
+        for c in range(self.C):
+            for d in range(3):
+                face[self.entity[c, fes[2 * d]]] += ext[c, d]
+                face[self.entity[c, fes[2 * d + 1]]] += ext[c, d]
+        out = np.zeros((self.C, 3, 3))
+        for c in range(self.C):
+            for d in range(3):
+                out[c, d, 1] = ext[c, d]
+                for side in (0, 1):
+                    q = self.entity[c, fes[2 * d + side]]
+                    out[c, d, 2 * side] = 0.0 if self.quad_bnd[q] else face[q] - ext[c, d]
+        return out

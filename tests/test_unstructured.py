@@ -1,0 +1,249 @@
+"""Unstructured all-hex meshes (BASELINE configs[3], the ball): the library's connectivity / orientation words / compressed indices
+against the oracle's restatement (bit-exact, host only) and the device path (vmult, inverse diagonal, FDM additive Schwarz with
+every weighting, Chebyshev step, CG) against the oracle on the same arrays (1e-12 double, 1e-5 float)."""
+import importlib
+
+import numpy as np
+import pytest
+
+import dasm_oracle as o
+from __graft_entry__ import load_package
+
+grid = importlib.import_module("dealii-asm_b200.grid")
+
+NPDT = {"double": np.float64, "float": np.float32}
+
+
+def relerr(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def wavy(X):
+    """smooth deformation of the unit cube (keeps cells valid)"""
+    X = np.asarray(X)
+    Y = X.copy()
+    Y[..., 0] += 0.04 * np.sin(np.pi * X[..., 1]) * np.sin(2 * np.pi * X[..., 2])
+    Y[..., 1] += 0.05 * np.sin(2 * np.pi * X[..., 0]) * X[..., 2]
+    Y[..., 2] += 0.03 * np.sin(np.pi * X[..., 0] * X[..., 1])
+    return Y
+
+
+def make_mesh(name):
+    if name == "cube2":
+        return grid.rotated_cube(2, seed=1)
+    if name == "cube3_wavy":
+        return grid.rotated_cube(3, seed=5, mapfun=wavy)
+    if name == "ball0":
+        return grid.hyper_ball(0)
+    if name == "ball1":
+        return grid.hyper_ball(1)
+    raise KeyError(name)
+
+
+@pytest.mark.parametrize("name", ["cube2", "cube3_wavy", "ball0", "ball1"])
+@pytest.mark.parametrize("k", [2, 3, 5])
+def test_host_numbering_against_oracle(name, k):
+    """connectivity, orientation words, 27 start indices, oriented (k+1)^3 addresses, constrained DoFs and harmonic patch extents:
+    C++ (dasm_umesh_host_numbering) == oracle (UnstructuredMesh); every DoF has ONE support point whichever cell evaluates it."""
+    if name == "ball1" and k == 5:
+        pytest.skip("covered by k = 2, 3 (keeps the CPU suite short)")
+    pkg = load_package()
+    g = make_mesh(name)
+    h = pkg.umesh_host_numbering(k, g["vertices"], g["cells"], g["support"])
+    m = o.UnstructuredMesh(g["vertices"], g["cells"], g["support"])
+    cd, nd, con, comp, comp_plain = m.number_dofs(k)
+    assert nd == h["n_dofs"]
+    assert np.array_equal(comp, h["cidx"])
+    assert np.array_equal(m.orientation.astype(np.uint32), h["orientation"])
+    assert np.array_equal(cd.astype(np.uint32), h["plain"])
+    assert np.array_equal(np.nonzero(con)[0].astype(np.uint32), np.sort(h["constrained"]))
+    assert np.allclose(m.harmonic_patch_extents(o.Basis1D(k)), h["extents"], rtol=1e-13, atol=1e-14)
+    nodes = o.gauss_lobatto_points(k + 1)
+    ref = np.array([(x, y, z) for z in nodes for y in nodes for x in nodes])
+    pos = np.full((nd, 3), np.nan)
+    for c in range(m.C):
+        X = m.cell_points(c, ref)
+        idx = h["plain"][c].astype(np.int64)
+        ok = idx != 0xFFFFFFFF
+        new = ok & np.isnan(pos[np.where(ok, idx, 0), 0])
+        pos[idx[new]] = X[new]
+        assert np.abs(pos[idx[ok]] - X[ok]).max() < 1e-12
+    if name.startswith("cube3"):
+        codes = {(int(w) >> (12 + 3 * q)) & 7 for w in h["orientation"] for q in range(6)}
+        assert codes == set(range(8))  # all 8 quad orientations occur (and line flips)
+        assert any(int(w) & 0xFFF for w in h["orientation"])
+
+
+def test_trilinear_default_support_points():
+    pkg = load_package()
+    g = grid.rotated_cube(2, seed=3)
+    h0 = pkg.umesh_host_numbering(3, g["vertices"], g["cells"], None)
+    h1 = pkg.umesh_host_numbering(3, g["vertices"], g["cells"], g["support"])
+    assert np.allclose(h0["extents"], h1["extents"], rtol=1e-14)
+    m = o.UnstructuredMesh(g["vertices"], g["cells"], None)
+    assert np.allclose(m.support, g["support"], atol=1e-15)
+
+
+def test_bad_meshes_are_rejected():
+    pkg = load_package()
+    g = grid.rotated_cube(2, seed=0, rotate=False)
+    cells = g["cells"].copy()
+    cells[0, 0] = 10 ** 6
+    with pytest.raises(pkg.DasmError):
+        pkg.umesh_host_numbering(2, g["vertices"], cells, None)
+    # a third cell glued onto an interior face
+    cells = np.concatenate([g["cells"], g["cells"][:1]], axis=0)
+    with pytest.raises(pkg.DasmError):
+        pkg.umesh_host_numbering(2, g["vertices"], cells, None)
+
+
+# ---- device ------------------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def pkg():
+    return load_package()
+
+
+@pytest.fixture(scope="module")
+def ctx(pkg):
+    return pkg.Context(0)
+
+
+def oracle_problem(g, op, k, dtype, weight_type=None, dirichlet=True):
+    m = o.UnstructuredMesh(g["vertices"], g["cells"], g["support"], dirichlet=dirichlet)
+    cd, nd, con, comp, _ = m.number_dofs(k)
+    assert nd == op.n_dofs()
+    assert np.array_equal(comp, op.compressed_indices())
+    assert np.array_equal(m.orientation.astype(np.uint32), op.orientations())
+    assert np.array_equal(cd.astype(np.uint32), op.plain_indices())
+    b = o.Basis1D(k)
+    G = o.merged_coefficients(m.jacobians(b), b, 3)
+    oop = o.LaplaceOperator(3, k, cd, nd, con, G, dtype=dtype)
+    oP = None
+    if weight_type is not None:
+        oP = o.FDMPreconditioner(m, k, cd, nd, con, 1, weight_type, dtype=dtype, cell_rank=np.arange(m.C))
+    return m, oop, oP
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,k", [("cube2", 2), ("cube3_wavy", 3), ("cube3_wavy", 4), ("ball0", 5), ("ball1", 2), ("ball1", 3), ("ball0", 7)])
+@pytest.mark.parametrize("number", ["double", "float"])
+@pytest.mark.parametrize("mapping_type", ["", "construct q"])
+def test_vmult_and_diagonal(pkg, ctx, name, k, number, mapping_type):
+    import torch
+    g = make_mesh(name)
+    op = pkg.LaplaceOperatorMatrixFree.from_arrays(ctx, g["vertices"], g["cells"], k, g["support"], number=number, mapping_type=mapping_type)
+    m, oop, _ = oracle_problem(g, op, k, NPDT[number])
+    tol = 1e-12 if number == "double" else 1e-5
+    rng = np.random.default_rng(k)
+    x = rng.uniform(-1, 1, op.n_dofs())
+    xd, yd = op.to_device(x), op.initialize_dof_vector()
+    op.vmult(yd, xd)
+    # ("construct q" differentiates the degree-k interpolant of the quadrature points: exact for the triquadratic map when k >= 2)
+    assert relerr(op.to_host(yd), oop.vmult(x).astype(np.float64)) < tol
+    dd = op.initialize_dof_vector()
+    op.compute_inverse_diagonal(dd)
+    assert relerr(op.to_host(dd), oop.inverse_diagonal().astype(np.float64)) < tol
+    if mapping_type == "" and number == "double":
+        # the a5 device kernel (orientation-aware read of the 27 start indices) reproduces the addresses the operator stores
+        dev = torch.device("cuda", 0)
+        cidx = torch.tensor(op.compressed_indices().astype(np.int64), device=dev).to(torch.int32)
+        ori = torch.tensor(op.orientations().astype(np.int64), device=dev).to(torch.int32)
+        iota = torch.arange(1, op.n_dofs() + 1, dtype=torch.float64, device=dev)
+        loc = pkg.reduced_access_read(k, cidx, ori, iota).cpu().numpy().astype(np.int64) - 1
+        plain = op.plain_indices().astype(np.int64)
+        assert np.array_equal(loc, np.where(plain == 0xFFFFFFFF, -1, plain))
+        # rhs for f = 1: sum of the entries = volume when nothing is constrained
+        op2 = pkg.LaplaceOperatorMatrixFree.from_arrays(ctx, g["vertices"], g["cells"], k, g["support"], dirichlet=False)
+        r = op2.initialize_dof_vector()
+        op2.rhs(r, 1.0)
+        vol = 4.0 / 3.0 * np.pi if name.startswith("ball") else None
+        if vol is None:
+            b = o.Basis1D(k)
+            J = o.UnstructuredMesh(g["vertices"], g["cells"], g["support"]).jacobians(b)
+            w = np.einsum("c,b,a->cba", b.qw, b.qw, b.qw).reshape(-1)
+            assert abs(op2.to_host(r).sum() - (np.linalg.det(J) * w).sum()) < 1e-12
+        else:
+            assert abs(op2.to_host(r).sum() - vol) < 2e-2 * vol  # (triquadratic approximation of the sphere)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,k", [("cube3_wavy", 3), ("ball0", 5), ("ball1", 2)])
+@pytest.mark.parametrize("wt", ["none", "pre", "post", "symm", "ras"])
+@pytest.mark.parametrize("seq", ["global", "dg"])
+def test_fdm_weightings(pkg, ctx, name, k, wt, seq):
+    g = make_mesh(name)
+    op = pkg.LaplaceOperatorMatrixFree.from_arrays(ctx, g["vertices"], g["cells"], k, g["support"])
+    m, oop, oP = oracle_problem(g, op, k, np.float64, wt)
+    fdm = pkg.create_fdm_preconditioner(op, {"weighting type": wt, "weight sequence": seq})
+    assert np.allclose(op.patch_extents(), oP.extents, rtol=1e-13)
+    rng = np.random.default_rng(7)
+    r = rng.uniform(-1, 1, op.n_dofs())
+    rd, zd = op.to_device(r), op.initialize_dof_vector()
+    fdm.vmult(zd, rd)
+    assert relerr(op.to_host(zd), oP.vmult(r)) < 1e-12
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,k,number,wt", [("ball1", 3, "double", "symm"), ("ball0", 5, "double", "post"), ("ball0", 5, "float", "symm"),
+                                              ("cube3_wavy", 4, "double", "ras"), ("ball1", 2, "double", "diag")])
+def test_chebyshev_step(pkg, ctx, name, k, number, wt):
+    g = make_mesh(name)
+    dt = NPDT[number]
+    op = pkg.LaplaceOperatorMatrixFree.from_arrays(ctx, g["vertices"], g["cells"], k, g["support"], number=number)
+    if wt == "diag":
+        m, oop, _ = oracle_problem(g, op, k, dt)
+        fdm, oP = None, o.JacobiPreconditioner(oop)
+    else:
+        m, oop, oP = oracle_problem(g, op, k, dt, wt)
+        fdm = pkg.create_fdm_preconditioner(op, {"weighting type": wt})
+    cheb = pkg.PreconditionChebyshev(op, fdm, degree=3)
+    cheb.set_eigenvalues(0.9, 2.2)
+    och = o.Chebyshev(oop, oP, degree=3)
+    och.set_eigenvalues(2.2, 0.9)
+    rng = np.random.default_rng(13)
+    b, x0 = rng.uniform(-1, 1, op.n_dofs()), rng.uniform(-1, 1, op.n_dofs())
+    con = op.constrained_dofs()
+    b[con] = 0
+    x0[con] = 0
+    xd, bd = op.to_device(x0), op.to_device(b)
+    cheb.step(xd, bd)
+    ref = och.step(x0.astype(dt), b.astype(dt))
+    assert relerr(op.to_host(xd), ref.astype(np.float64)) < (1e-12 if number == "double" else 1e-5)
+    yd = op.initialize_dof_vector()
+    cheb.vmult(yd, bd)
+    assert relerr(op.to_host(yd), och.vmult(b.astype(dt)).astype(np.float64)) < (1e-12 if number == "double" else 1e-5)
+
+
+@pytest.mark.gpu
+def test_ball_cg_with_chebyshev_fdm(pkg, ctx):
+    """-Laplace u = 1 on the ball, CG preconditioned by Chebyshev(3) + FDM (symm): same iteration count and solution as the oracle,
+    and the solution is the paraboloid (1 - r^2) / 6 up to the discretisation error."""
+    k = 3
+    g = grid.hyper_ball(1)
+    op = pkg.LaplaceOperatorMatrixFree.from_arrays(ctx, g["vertices"], g["cells"], k, g["support"])
+    m, oop, oP = oracle_problem(g, op, k, np.float64, "symm")
+    fdm = pkg.create_fdm_preconditioner(op, {"weighting type": "symm"})
+    cheb = pkg.PreconditionChebyshev(op, fdm, degree=3)
+    mn, mx = cheb.estimate_eigenvalues()
+    och = o.Chebyshev(oop, oP, degree=3)
+    omn, omx = och.estimate_eigenvalues()
+    assert abs(mx - omx) < 1e-8 * omx
+    bd = op.initialize_dof_vector()
+    op.rhs(bd, 1.0)
+    b = op.to_host(bd)
+    xd = op.initialize_dof_vector()
+    its, res = pkg.solve(op, xd, bd, cheb, {"type": "CG", "rel tolerance": 1e-8})
+    x_ref, its_ref = o.solve_cg(lambda v: oop.vmult(v, copy_constrained=True), och.vmult, b, rel_tol=1e-8)
+    assert its == its_ref
+    x = op.to_host(xd)
+    assert relerr(x, x_ref) < 1e-9
+    # analytic solution at the DoF support points
+    nodes = o.gauss_lobatto_points(k + 1)
+    ref = np.array([(a, bb, c) for c in nodes for bb in nodes for a in nodes])
+    plain = op.plain_indices().astype(np.int64)
+    err = 0.0
+    for c in range(m.C):
+        X = m.cell_points(c, ref)
+        ok = plain[c] != 0xFFFFFFFF
+        err = max(err, np.abs(x[plain[c][ok]] - (1 - (X[ok] ** 2).sum(-1)) / 6).max())
+    assert err < 2e-3
