@@ -59,7 +59,7 @@ def lib():
         _lib.dasm_ctx_stream.restype = ctypes.c_void_p
         for name in ("dasm_ctx_launch_count", "dasm_mesh_n_cells", "dasm_mesh_n_global_cells", "dasm_op_n_dofs",
                      "dasm_op_n_ghost", "dasm_op_n_import", "dasm_op_vec_size", "dasm_op_n_global_dofs", "dasm_op_constrained_dofs",
-                     "dasm_fdm_n_instances", "dasm_fdm_memory_consumption", "dasm_op_n_fast_bricks", "dasm_fdm_n_fast_bricks", "dasm_op_n_cells"):
+                     "dasm_fdm_n_instances", "dasm_fdm_memory_consumption", "dasm_op_n_fast_bricks", "dasm_fdm_n_fast_bricks", "dasm_op_n_cells", "dasm_power_n_waves", "dasm_power_post_count"):
             getattr(_lib, name).restype = ctypes.c_longlong
     return _lib
 
@@ -522,6 +522,31 @@ class RestrictedPreconditioner:
     def __del__(self):
         try:
             lib().dasm_asm_destroy(self.h)
+        except Exception:
+            pass
+
+
+class PowerKernel:
+    """power_kernel_01.likwid.cc:479-599: dst_0 += A src, dst_1 += M dst_0 (mass operator); fused (power kernel: the second operator
+    runs on a cell once its dst_0 entries are complete, wave by wave) or sequential (two sweeps)."""
+
+    def __init__(self, op, cell_granularity=0, batch_size=1):
+        self.op = op
+        self.h = ctypes.c_void_p()
+        _check(lib().dasm_power_create(op.h, ctypes.c_longlong(cell_granularity), int(batch_size), ctypes.byref(self.h)))
+
+    def run(self, dst_0, dst_1, src, fused=True, do_computation=True):
+        _check(lib().dasm_power_run(self.h, _ptr(dst_0), _ptr(dst_1), _ptr(src), int(fused), int(do_computation)))
+
+    def n_waves(self):
+        return lib().dasm_power_n_waves(self.h)
+
+    def post_counts(self):
+        return [lib().dasm_power_post_count(self.h, ctypes.c_longlong(w)) for w in range(self.n_waves())]
+
+    def __del__(self):
+        try:
+            lib().dasm_power_destroy(self.h)
         except Exception:
             pass
 

@@ -721,19 +721,19 @@ launch_laplace(dasm_op *op, T *dst, const T *src)
       {
         auto kern = laplace_generic_kernel<K, T, 0>;
         CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, CPB * n * n, smem, ctx->stream>>>(src, dst, op->d_cidx, (const T *)nullptr, op->cart, op->n_cells, op->d_plain);
+        kern<<<grid, CPB * n * n, smem, ctx->stream>>>(src, dst, op->d_cidx, (const T *)nullptr, op->cart, op->n_cells, op->d_plain, nullptr);
       }
     else if (op->geom_mode == 3)
       {
         auto kern = laplace_generic_kernel<K, T, 2>;
         CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, CPB * n * n, smem, ctx->stream>>>(src, dst, op->d_cidx, (const T *)op->d_geom, op->cart, op->n_cells, op->d_plain);
+        kern<<<grid, CPB * n * n, smem, ctx->stream>>>(src, dst, op->d_cidx, (const T *)op->d_geom, op->cart, op->n_cells, op->d_plain, nullptr);
       }
     else
       {
         auto kern = laplace_generic_kernel<K, T, 1>;
         CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, CPB * n * n, smem, ctx->stream>>>(src, dst, op->d_cidx, (const T *)op->d_geom, op->cart, op->n_cells, op->d_plain);
+        kern<<<grid, CPB * n * n, smem, ctx->stream>>>(src, dst, op->d_cidx, (const T *)op->d_geom, op->cart, op->n_cells, op->d_plain, nullptr);
       }
   });
   ctx->launches++;
@@ -4786,5 +4786,176 @@ dasm_solve(dasm_op *op, int solver, int precon_kind, void *precon, void *x, cons
   CUDA_CHECK(cudaSetDevice(op->ctx->device));
   DISPATCH_TYPE(op->ntype, krylov_solve<T>(op, solver, precon_kind, precon, (T *)x, (const T *)b, max_it, abs_tol, rel_tol, restart, n_it,
                                            residual));
+  DASM_API_END
+}
+
+// ------------------------------------------------------------------------------------------------
+// Power kernel (power_kernel_01.likwid.cc:122-308, 479-599): dst_0 = A src (Laplace), dst_1 = M dst_0 (mass operator on the same
+// cells), "sequential" = two sweeps over all cells, "power" = the second operator runs on a cell as soon as every cell that
+// contributes to its dst_0 entries has been processed (determine_pre_post), so that dst_0 is still on chip.  On the device a wave of
+// `cell_granularity` cells is one launch of the generic cell kernel on a cell range, followed by one launch of the second operator on
+// the list of cells that became complete (dst_0 of the last waves then sits in the 126 MB L2).  `batch_size` > 1 releases cells in
+// batches (the "use matrix-free batches" variant), 1 tracks every cell (the "own batches" variant).
+// ------------------------------------------------------------------------------------------------
+struct dasm_power
+{
+  dasm_op *              op;
+  long long              granularity;
+  std::vector<long long> wave_first;      // cells [wave_first[w], wave_first[w+1])
+  std::vector<long long> post_ptr;        // post cells of wave w: post_ids[post_ptr[w] .. post_ptr[w+1])
+  uint32_t *             d_post_ids = nullptr;
+  double                 cell_volume = 1;
+};
+
+extern "C" int
+dasm_power_create(dasm_op *op, long long cell_granularity, int batch_size, dasm_power **out)
+{
+  DASM_API_BEGIN
+  DASM_REQUIRE(op->geom_mode == 0 && op->mesh != nullptr, "power kernel: Cartesian structured mesh expected (MappingQ1 on a hyper-cube in the reference)");
+  DASM_REQUIRE(op->mesh->mesh->n_ranks() == 1, "power kernel: one rank");
+  CUDA_CHECK(cudaSetDevice(op->ctx->device));
+  auto p         = new dasm_power;
+  p->op          = op;
+  const long long nc = op->n_cells;
+  p->granularity = (cell_granularity <= 0 || cell_granularity > nc) ? nc : cell_granularity;
+  batch_size     = std::max(batch_size, 1);
+  const Mesh &M  = *op->mesh->mesh;
+  p->cell_volume = M.h(0) * M.h(1) * M.h(2);
+  const long long n_waves = (nc + p->granularity - 1) / p->granularity;
+  for (long long w = 0; w <= n_waves; ++w)
+    p->wave_first.push_back(std::min(w * p->granularity, nc));
+  // last wave that touches an entity with DoFs (the 27 start indices identify the entities; constrained ones are not accessed)
+  const int                               k = op->k;
+  std::unordered_map<uint32_t, long long> last;
+  auto has_dofs = [&](const int e) { return k > 1 || ((e % 3 != 1) && ((e / 3) % 3 != 1) && (e / 9 != 1)); };
+  for (long long c = 0; c < nc; ++c)
+    for (int e = 0; e < 27; ++e)
+      {
+        const uint32_t s = op->nb.cidx[c * 27 + e];
+        if (s != INVALID_INDEX && has_dofs(e))
+          last[s] = c / p->granularity; // (cells are visited in increasing wave order)
+      }
+  std::vector<long long> ready(nc, 0);
+  for (long long c = 0; c < nc; ++c)
+    {
+      long long r = c / p->granularity;
+      for (int e = 0; e < 27; ++e)
+        {
+          const uint32_t s = op->nb.cidx[c * 27 + e];
+          if (s != INVALID_INDEX && has_dofs(e))
+            r = std::max(r, last[s]);
+        }
+      ready[c] = r;
+    }
+  if (batch_size > 1)
+    for (long long c0 = 0; c0 < nc; c0 += batch_size)
+      {
+        long long r = 0;
+        for (long long c = c0; c < std::min(nc, c0 + batch_size); ++c)
+          r = std::max(r, ready[c]);
+        for (long long c = c0; c < std::min(nc, c0 + batch_size); ++c)
+          ready[c] = r;
+      }
+  std::vector<uint32_t> ids(nc);
+  p->post_ptr.assign(n_waves + 1, 0);
+  for (long long c = 0; c < nc; ++c)
+    p->post_ptr[ready[c] + 1]++;
+  for (long long w = 0; w < n_waves; ++w)
+    p->post_ptr[w + 1] += p->post_ptr[w];
+  std::vector<long long> fill(p->post_ptr.begin(), p->post_ptr.end() - 1);
+  for (long long c = 0; c < nc; ++c)
+    ids[fill[ready[c]]++] = (uint32_t)c;
+  p->d_post_ids = dev_upload(ids, op->ctx->stream);
+  *out          = p;
+  DASM_API_END
+}
+
+template <typename T>
+static void
+power_launch(dasm_op *op, const int geom, const double cell_volume, T *dst, const T *src, const long long first, const long long count,
+             const uint32_t *cell_ids)
+{
+  if (count <= 0)
+    return;
+  dasm_ctx *ctx = op->ctx;
+  DISPATCH_DEGREE(op->k, {
+    constexpr int  n = K + 1, CPB = cells_per_block<K>();
+    const size_t   smem = (size_t)CPB * 4 * n * n * n * sizeof(T);
+    const unsigned grid = (unsigned)((count + CPB - 1) / CPB);
+    const uint32_t *ci  = cell_ids ? op->d_cidx : op->d_cidx + first * 27;
+    CartesianCoef   cc  = op->cart;
+    if (geom == 0)
+      {
+        auto kern = laplace_generic_kernel<K, T, 0>;
+        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, CPB * n * n, smem, ctx->stream>>>(src, dst, ci, (const T *)nullptr, cc, count, nullptr, cell_ids);
+      }
+    else if (geom == 4)
+      {
+        cc.g[0]   = cell_volume;
+        auto kern = laplace_generic_kernel<K, T, 4>;
+        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, CPB * n * n, smem, ctx->stream>>>(src, dst, ci, (const T *)nullptr, cc, count, nullptr, cell_ids);
+      }
+    else
+      {
+        auto kern = laplace_generic_kernel<K, T, 5>;
+        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, CPB * n * n, smem, ctx->stream>>>(src, dst, ci, (const T *)nullptr, cc, count, nullptr, cell_ids);
+      }
+  });
+  ctx->launches++;
+}
+
+// fused != 0: power kernel; 0: sequential.  The results are ADDED to dst_0 / dst_1 (distribute_local_to_global, as in the reference,
+// which zeroes the two vectors once before the repetitions, power_kernel_01.likwid.cc:443-445)
+extern "C" int
+dasm_power_run(dasm_power *p, void *dst_0, void *dst_1, const void *src, int fused, int do_computation)
+{
+  DASM_API_BEGIN
+  dasm_op *op = p->op;
+  CUDA_CHECK(cudaSetDevice(op->ctx->device));
+  const int g0 = do_computation ? 0 : 5, g1 = do_computation ? 4 : 5;
+  DISPATCH_TYPE(op->ntype, {
+    if (!fused)
+      {
+        for (size_t w = 0; w + 1 < p->wave_first.size(); ++w)
+          power_launch<T>(op, g0, p->cell_volume, (T *)dst_0, (const T *)src, p->wave_first[w], p->wave_first[w + 1] - p->wave_first[w], nullptr);
+        for (size_t w = 0; w + 1 < p->wave_first.size(); ++w)
+          power_launch<T>(op, g1, p->cell_volume, (T *)dst_1, (const T *)dst_0, p->wave_first[w], p->wave_first[w + 1] - p->wave_first[w], nullptr);
+      }
+    else
+      for (size_t w = 0; w + 1 < p->wave_first.size(); ++w)
+        {
+          power_launch<T>(op, g0, p->cell_volume, (T *)dst_0, (const T *)src, p->wave_first[w], p->wave_first[w + 1] - p->wave_first[w], nullptr);
+          power_launch<T>(op, g1, p->cell_volume, (T *)dst_1, (const T *)dst_0, 0, p->post_ptr[w + 1] - p->post_ptr[w], p->d_post_ids + p->post_ptr[w]);
+        }
+  });
+  CUDA_CHECK(cudaGetLastError());
+  DASM_API_END
+}
+
+// number of cells the second operator processes after wave w (the post_indices_ptr of determine_pre_post), for inspection
+extern "C" long long
+dasm_power_n_waves(const dasm_power *p)
+{
+  return (long long)p->wave_first.size() - 1;
+}
+
+extern "C" long long
+dasm_power_post_count(const dasm_power *p, long long wave)
+{
+  return (wave >= 0 && wave + 1 < (long long)p->post_ptr.size()) ? p->post_ptr[wave + 1] - p->post_ptr[wave] : -1;
+}
+
+extern "C" int
+dasm_power_destroy(dasm_power *p)
+{
+  DASM_API_BEGIN
+  if (p)
+    {
+      cudaFree(p->d_post_ids);
+      delete p;
+    }
   DASM_API_END
 }

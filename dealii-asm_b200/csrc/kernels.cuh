@@ -227,8 +227,11 @@ namespace dasm
                          const T *__restrict__ geom,
                          const CartesianCoef cart,
                          const long long     n_cells,
-                         const uint32_t *__restrict__ plain = nullptr) // compress_indices = false: n^3 indices per cell
+                         const uint32_t *__restrict__ plain = nullptr, // compress_indices = false: n^3 indices per cell
+                         const uint32_t *__restrict__ cell_ids = nullptr) // work on the cells cell_ids[0 .. n_cells) (power kernel)
   {
+    // GEOM 0 Cartesian, 1 merged coefficients, 2 construct q; 4 mass operator on a Cartesian mesh (cart.g[0] = cell volume),
+    // 5 no computation (gather + scatter only): the second operator / the do_computation = false mode of power_kernel_01
     constexpr int n = k + 1, n2 = n * n, n3 = n2 * n, CPB = cells_per_block<k>();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *smem = reinterpret_cast<T *>(smem_raw);
@@ -237,8 +240,9 @@ namespace dasm
     const int       t    = threadIdx.x % n2;
     const int       a    = t % n;
     const int       b    = t / n;
-    const long long cell = (long long)blockIdx.x * CPB + cl;
-    const bool      act  = cell < n_cells;
+    const long long slot = (long long)blockIdx.x * CPB + cl;
+    const bool      act  = slot < n_cells;
+    const long long cell = (act && cell_ids != nullptr) ? (long long)cell_ids[slot] : slot;
 
     T *U  = smem + (size_t)cl * 4 * n3;
     T *GX = U + n3;
@@ -263,6 +267,8 @@ namespace dasm
           }
       }
     __syncthreads();
+    if (GEOM != 5)
+      {
     // interpolate to Gauss points (in place)
     if (act)
       sweep_const<n, T, 0, false, false>(B.N, U, U, a, b);
@@ -273,6 +279,18 @@ namespace dasm
     if (act)
       sweep_const<n, T, 2, false, false>(B.N, U, U, a, b);
     __syncthreads();
+    if (GEOM == 4)
+      {
+        // mass operator: values times JxW (evaluate(values) / submit_value / integrate(values), power_kernel_01.likwid.cc:423-440)
+        if (act)
+          {
+#pragma unroll
+            for (int x = 0; x < n; ++x)
+              U[(b * n + a) * n + x] *= T(cart.g[0]) * B.qw[x] * B.qw[a] * B.qw[b];
+          }
+      }
+    else
+      {
     // collocation gradients
     if (act)
       {
@@ -324,6 +342,7 @@ namespace dasm
     __syncthreads();
     if (act)
       sweep_const<n, T, 2, true, true>(B.Dq, GZ, U, a, b);
+      } // GEOM != 4
     __syncthreads();
     if (act)
       sweep_const<n, T, 2, true, false>(B.N, U, U, a, b);
@@ -334,6 +353,7 @@ namespace dasm
     if (act)
       sweep_const<n, T, 0, true, false>(B.N, U, U, a, b);
     __syncthreads();
+      } // GEOM != 5
     // scatter-add
     if (act)
       {

@@ -291,6 +291,18 @@ extern "C"
                                 const double *support_points, int dirichlet, long long sizes[4], uint32_t *cidx, uint32_t *orientation,
                                 uint32_t *plain, uint32_t *constrained, double *extents);
 
+  /* ---- Power kernel (power_kernel_01.likwid.cc:122-308, 479-599): dst_0 += A src (Laplace), dst_1 += M dst_0 (mass operator), with the
+   *      second operator applied to a cell as soon as its dst_0 entries are complete (fused != 0) or in a second sweep (fused == 0).
+   * cell_granularity: cells per wave (0: all cells = one wave); batch_size 1: every cell is released on its own ("own batches"),
+   * > 1: cells are released in batches of that size ("matrix-free batches").  do_computation == 0: gather / scatter only.
+   * Cartesian structured meshes, one rank.  Vectors: device pointers in the operator's layout. */
+  typedef struct dasm_power dasm_power;
+  int       dasm_power_create(dasm_op *op, long long cell_granularity, int batch_size, dasm_power **out);
+  int       dasm_power_run(dasm_power *p, void *dst_0, void *dst_1, const void *src, int fused, int do_computation);
+  long long dasm_power_n_waves(const dasm_power *p);
+  long long dasm_power_post_count(const dasm_power *p, long long wave);
+  int       dasm_power_destroy(dasm_power *p);
+
   /* ---- Orientation-aware compressed vector access (ConstraintInfoReduced::read_dof_values / distribute_local_to_global,
    *      include/vector_access_reduced.h:267-548, with adjust_for_orientation, include/reduced_access.h:528-702) ------------------
    * d_cidx: 27 start indices per cell (0xFFFFFFFF = constrained), d_orientation: one packed word per cell (12 line bits + 6 x 3 quad

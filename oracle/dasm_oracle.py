@@ -1808,3 +1808,54 @@ class UnstructuredMesh:
                     q = self.entity[c, fes[2 * d + side]]
                     out[c, d, 2 * side] = 0.0 if self.quad_bnd[q] else face[q] - ext[c, d]
         return out
+
+
+# --------------------------------------------------------------------------------------
+# Power kernel (power_kernel_01.likwid.cc): dst_0 = A src, dst_1 = M dst_0 with the second operator applied per wave of cells
+# --------------------------------------------------------------------------------------
+def mass_vmult(op, x, JxW):
+    """process_batch_post of power_kernel_01.likwid.cc:423-440 summed over the cells: evaluate(values), submit_value(get_value),
+    integrate(values), distribute_local_to_global; `op` supplies the index lists and the basis, JxW [C, n^dim] the weights."""
+    x = np.asarray(x, dtype=op.dtype)
+    C = op.idx.shape[0]
+    u = (x[op.idx] * op.mask).reshape((C,) + (op.n,) * op.dim)
+    for d in range(op.dim):
+        u = _apply_1d(op.N, u, u.ndim - 1 - d)
+    u = u * np.asarray(JxW, dtype=op.dtype).reshape(u.shape)
+    for d in range(op.dim):
+        u = _apply_1d(op.N.T, u, u.ndim - 1 - d)
+    y = np.zeros(op.n_dofs, dtype=op.dtype)
+    np.add.at(y, op.idx.reshape(-1), (u.reshape(C, -1) * op.mask).reshape(-1))
+    return y
+
+
+def determine_pre_post(cell_vertices, cell_granularity, batch_size=1, track_individual_cell=True):
+    """power_kernel_01.likwid.cc:122-260: cells are processed in waves of `cell_granularity`; a vertex remembers the first / last wave
+    that touches it; an entity (a cell, or a batch of `batch_size` consecutive cells) may be pre-processed in the first wave and
+    post-processed in the last wave over its vertices.  Returns (pre_indices, pre_ptr, post_indices, post_ptr)."""
+    cv = np.asarray(cell_vertices)
+    C = cv.shape[0]
+    g = C if cell_granularity <= 0 else cell_granularity
+    wave = np.arange(C) // g
+    n_waves = int(wave[-1]) + 1
+    first = np.full(int(cv.max()) + 1, np.iinfo(np.int64).max, dtype=np.int64)
+    last = np.zeros(int(cv.max()) + 1, dtype=np.int64)
+    for c in range(C):
+        first[cv[c]] = np.minimum(first[cv[c]], wave[c])
+        last[cv[c]] = np.maximum(last[cv[c]], wave[c])
+    ent = np.arange(C) if track_individual_cell else np.arange(C) // batch_size
+    n_ent = int(ent[-1]) + 1
+    mn = np.full(n_ent, np.iinfo(np.int64).max, dtype=np.int64)
+    mx = np.zeros(n_ent, dtype=np.int64)
+    for c in range(C):
+        mn[ent[c]] = min(mn[ent[c]], first[cv[c]].min())
+        mx[ent[c]] = max(mx[ent[c]], last[cv[c]].max())
+
+    def process(ids):
+        temp = [[] for _ in range(n_waves)]
+        for i, w in enumerate(ids):
+            temp[w].append(i)
+        ptr = np.cumsum([0] + [len(t) for t in temp])
+        return np.array([i for t in temp for i in t], dtype=np.int64), ptr
+
+    return process(mn) + process(mx)
