@@ -452,10 +452,16 @@ class MGTwoLevelTransfer:
     """Two-level transfer of MGTransferGlobalCoarsening between two operators (geometric 2:1 or polynomial), the transfer
     operators PreconditionerGMG sets up in include/multigrid.h:338-349."""
 
-    def __init__(self, fine, coarse):
+    def __init__(self, fine, coarse, parent=None):
+        """parent (unstructured meshes, geometric transfer): parent[fine cell] = coarse cell | child position << 28
+        (dealii-asm_b200/grid.py ball_parents)"""
         self.fine, self.coarse = fine, coarse
         self.h = ctypes.c_void_p()
-        _check(lib().dasm_transfer_create(fine.h, coarse.h, ctypes.byref(self.h)))
+        if parent is None:
+            _check(lib().dasm_transfer_create(fine.h, coarse.h, ctypes.byref(self.h)))
+        else:
+            par = np.ascontiguousarray(parent, dtype=np.uint32)
+            _check(lib().dasm_transfer_create_unstructured(fine.h, coarse.h, par.ctypes.data_as(ctypes.c_void_p), ctypes.byref(self.h)))
 
     def prolongate_and_add(self, dst_fine, src_coarse):
         _check(lib().dasm_transfer_prolongate_and_add(self.h, _ptr(dst_fine), _ptr(src_coarse)))
@@ -475,15 +481,22 @@ class PreconditionerGMG:
     (smoothers[0] = coarse-grid solver).  vmult takes vectors of the OUTER number type (that of `outer_op`, double in the
     reference) and converts to the level number type and back."""
 
-    def __init__(self, level_ops, smoothers, outer_op=None, use_one_sided_v_cycle=False):
+    def __init__(self, level_ops, smoothers, outer_op=None, use_one_sided_v_cycle=False, transfers=None):
+        """transfers: optional list (one entry per level, entry l between the levels l and l - 1, None = built by the library)"""
         assert len(level_ops) == len(smoothers) and len(level_ops) >= 1
         self.level_ops, self.smoothers = list(level_ops), list(smoothers)
+        self.transfers = list(transfers) if transfers is not None else None
         self.outer_ntype = (outer_op or level_ops[-1]).ntype
         n = len(level_ops)
         ops = (ctypes.c_void_p * n)(*[o.h for o in level_ops])
         sms = (ctypes.c_void_p * n)(*[s.h for s in smoothers])
         self.h = ctypes.c_void_p()
-        _check(lib().dasm_mg_create(n, ops, sms, 1 if use_one_sided_v_cycle else 0, ctypes.byref(self.h)))
+        if transfers is None:
+            _check(lib().dasm_mg_create(n, ops, sms, 1 if use_one_sided_v_cycle else 0, ctypes.byref(self.h)))
+        else:
+            assert len(transfers) == n
+            trs = (ctypes.c_void_p * n)(*[(t.h if t is not None else None) for t in transfers])
+            _check(lib().dasm_mg_create_with_transfers(n, ops, sms, trs, 1 if use_one_sided_v_cycle else 0, ctypes.byref(self.h)))
 
     def vmult(self, dst, src):
         _check(lib().dasm_mg_vmult_outer(self.h, _ptr(dst), _ptr(src), int(self.outer_ntype)))

@@ -2826,6 +2826,38 @@ dasm_op_plain_indices(const dasm_op *op, uint32_t *out)
 }
 
 extern "C" long long dasm_op_n_cells(const dasm_op *op) { return op->n_cells; }
+extern "C" int dasm_op_is_unstructured(const dasm_op *op) { return op->umesh ? 1 : 0; }
+extern "C" const uint32_t *dasm_op_device_plain_indices(const dasm_op *op) { return op->d_plain; }
+
+// number of cells that share the entity e of a cell (out[cell*27+e]; entities without DoFs: 1): the weights of the two-level
+// transfers on unstructured meshes
+extern "C" int
+dasm_op_entity_valence(const dasm_op *op, uint8_t *out)
+{
+  DASM_API_BEGIN
+  DASM_REQUIRE(op->umesh != nullptr, "entity valences are exported for operators on unstructured meshes");
+  const UMesh &         U = *op->umesh;
+  std::vector<uint32_t> nv((size_t)U.n_vertices, 0), nl((size_t)U.n_lines, 0), nq((size_t)U.n_quads, 0);
+  for (long long c = 0; c < U.n_cells; ++c)
+    for (int e = 0; e < 27; ++e)
+      {
+        const int dim = UMesh::entity_dim(e);
+        auto &    cnt = dim == 0 ? nv : (dim == 1 ? nl : nq);
+        if (dim < 3)
+          cnt[U.entity[c * 27 + e]]++;
+      }
+  for (long long c = 0; c < U.n_cells; ++c)
+    for (int e = 0; e < 27; ++e)
+      {
+        const int dim = UMesh::entity_dim(e);
+        uint32_t  v   = 1;
+        if (dim < 3)
+          v = (dim == 0 ? nv : (dim == 1 ? nl : nq))[U.entity[c * 27 + e]];
+        DASM_REQUIRE(v <= 255, "entity valence above 255");
+        out[c * 27 + e] = (uint8_t)v;
+      }
+  DASM_API_END
+}
 
 // harmonic patch extents [cell][3][3] of an unstructured operator (grid_tools.h:54-138), for inspection
 extern "C" int

@@ -72,6 +72,7 @@ namespace
     const uint32_t *cidx_f, *cidx_c; // 27 start indices per cell
     const uint32_t *parent;          // per fine cell: parent coarse cell (local index) | child code << 28 (bits x, y, z)
     const uint8_t * valence;         // per fine cell: 27 entity valences
+    const uint32_t *plain_f = nullptr, *plain_c = nullptr; // unstructured meshes: (k+1)^3 oriented addresses per cell
     int             kf, kc;
     long long       n_cells_f;
   };
@@ -127,7 +128,7 @@ namespace
       {
         for (int i = threadIdx.x; i < nc * nc * nc; i += blockDim.x)
           {
-            const uint32_t g = decode(ci_c, a.kc, i % nc, (i / nc) % nc, i / (nc * nc));
+            const uint32_t g = a.plain_c ? a.plain_c[(long long)par * nc * nc * nc + i] : decode(ci_c, a.kc, i % nc, (i / nc) % nc, i / (nc * nc));
             buf0[i]          = (g == INVALID) ? T(0) : src[g];
           }
         __syncthreads();
@@ -140,7 +141,7 @@ namespace
         for (int i = threadIdx.x; i < nf * nf * nf; i += blockDim.x)
           {
             const int      x = i % nf, y = (i / nf) % nf, z = i / (nf * nf);
-            const uint32_t g = decode(ci_f, a.kf, x, y, z);
+            const uint32_t g = a.plain_f ? a.plain_f[cell * nf * nf * nf + i] : decode(ci_f, a.kf, x, y, z);
             const int      e = ((x == 0) ? 0 : ((x == a.kf) ? 2 : 1)) + 3 * ((y == 0) ? 0 : ((y == a.kf) ? 2 : 1)) +
                           9 * ((z == 0) ? 0 : ((z == a.kf) ? 2 : 1));
             if (g != INVALID)
@@ -152,7 +153,7 @@ namespace
         for (int i = threadIdx.x; i < nf * nf * nf; i += blockDim.x)
           {
             const int      x = i % nf, y = (i / nf) % nf, z = i / (nf * nf);
-            const uint32_t g = decode(ci_f, a.kf, x, y, z);
+            const uint32_t g = a.plain_f ? a.plain_f[cell * nf * nf * nf + i] : decode(ci_f, a.kf, x, y, z);
             const int      e = ((x == 0) ? 0 : ((x == a.kf) ? 2 : 1)) + 3 * ((y == 0) ? 0 : ((y == a.kf) ? 2 : 1)) +
                           9 * ((z == 0) ? 0 : ((z == a.kf) ? 2 : 1));
             buf0[i] = (g == INVALID) ? T(0) : wv[e] * src[g];
@@ -166,7 +167,7 @@ namespace
         __syncthreads();
         for (int i = threadIdx.x; i < nc * nc * nc; i += blockDim.x)
           {
-            const uint32_t g = decode(ci_c, a.kc, i % nc, (i / nc) % nc, i / (nc * nc));
+            const uint32_t g = a.plain_c ? a.plain_c[(long long)par * nc * nc * nc + i] : decode(ci_c, a.kc, i % nc, (i / nc) % nc, i / (nc * nc));
             if (g != INVALID)
               atomicAdd(dst + g, buf1[i]);
           }
@@ -195,9 +196,76 @@ struct dasm_transfer
   TransferArgs args;
 };
 
+// two-level transfer between operators on unstructured meshes (the ball): the same cell-wise embedding through the oriented
+// addresses of both levels; weights = 1 / number of cells sharing the fine entity
+extern "C" int
+dasm_transfer_create_unstructured(dasm_op *fine, dasm_op *coarse, const uint32_t *parent_in, dasm_transfer **out)
+{
+  MG_API_BEGIN
+  if (!dasm_op_is_unstructured(fine) || !dasm_op_is_unstructured(coarse))
+    throw std::runtime_error("transfer: both operators must live on unstructured meshes");
+  if (dasm_op_ctx(fine) != dasm_op_ctx(coarse))
+    throw std::runtime_error("transfer: both operators must live on one context");
+  if (dasm_op_number_type(fine) != dasm_op_number_type(coarse))
+    throw std::runtime_error("transfer: both operators must have one number type");
+  const long long nf = dasm_op_n_cells(fine), nc = dasm_op_n_cells(coarse);
+  const int       kf = dasm_op_degree(fine), kc = dasm_op_degree(coarse);
+  auto            t  = new dasm_transfer;
+  t->fine      = fine;
+  t->coarse    = coarse;
+  t->stream    = (cudaStream_t)dasm_ctx_stream(dasm_op_ctx(fine));
+  t->ntype     = dasm_op_number_type(fine);
+  t->geometric = parent_in != nullptr;
+  if (t->geometric ? (nf != 8 * nc || kf != kc) : (nf != nc || kc > kf))
+    {
+      delete t;
+      throw std::runtime_error("transfer: the levels must be related by global 2:1 coarsening (same degree) or share the mesh (lower degree)");
+    }
+  const std::vector<double> xc = dasm::gauss_lobatto_points(kc + 1), xf0 = dasm::gauss_lobatto_points(kf + 1);
+  for (int ch = 0; ch < 2; ++ch)
+    {
+      std::vector<double> xf(xf0), V, D;
+      if (t->geometric)
+        for (auto &x : xf)
+          x = 0.5 * (x + ch);
+      dasm::lagrange(xc, xf, V, D);
+      for (int i = 0; i < (kf + 1) * (kc + 1); ++i)
+        t->P[ch][i] = std::fabs(V[i]) < 1e-15 ? 0. : V[i];
+    }
+  std::vector<uint32_t> parent(nf);
+  for (long long c = 0; c < nf; ++c)
+    {
+      parent[c] = t->geometric ? parent_in[c] : (uint32_t)c;
+      if ((long long)(parent[c] & 0x0FFFFFFFu) >= nc)
+        {
+          delete t;
+          throw std::runtime_error("transfer: parent cell out of range");
+        }
+    }
+  std::vector<uint8_t> valence((size_t)nf * 27);
+  MG_CALL(dasm_op_entity_valence(fine, valence.data()));
+  MG_CUDA_CHECK(cudaMalloc(&t->d_parent, std::max<size_t>(1, parent.size()) * sizeof(uint32_t)));
+  MG_CUDA_CHECK(cudaMalloc(&t->d_valence, std::max<size_t>(1, valence.size())));
+  MG_CUDA_CHECK(cudaMemcpy(t->d_parent, parent.data(), parent.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  MG_CUDA_CHECK(cudaMemcpy(t->d_valence, valence.data(), valence.size(), cudaMemcpyHostToDevice));
+  t->args.cidx_f    = dasm_op_device_indices(fine);
+  t->args.cidx_c    = dasm_op_device_indices(coarse);
+  t->args.plain_f   = dasm_op_device_plain_indices(fine);
+  t->args.plain_c   = dasm_op_device_plain_indices(coarse);
+  t->args.parent    = t->d_parent;
+  t->args.valence   = t->d_valence;
+  t->args.kf        = kf;
+  t->args.kc        = kc;
+  t->args.n_cells_f = nf;
+  *out              = t;
+  MG_API_END
+}
+
 extern "C" int
 dasm_transfer_create(dasm_op *fine, dasm_op *coarse, dasm_transfer **out)
 {
+  if (dasm_op_is_unstructured(fine) || dasm_op_is_unstructured(coarse))
+    return dasm_transfer_create_unstructured(fine, coarse, nullptr, out); // same mesh, polynomial transfer
   MG_API_BEGIN
   if (dasm_op_ctx(fine) != dasm_op_ctx(coarse))
     throw std::runtime_error("transfer: both operators must live on one context");
@@ -361,6 +429,7 @@ struct dasm_mg
   std::vector<dasm_op *>       ops;
   std::vector<dasm_cheb *>     smoothers;
   std::vector<dasm_transfer *> transfers; // [l]: between l and l - 1
+  std::vector<bool>            borrowed;  // transfer owned by the caller
   std::vector<void *>          defect, solution, t;
   std::vector<long long>       vec_size, n_owned;
   size_t                       esize = 8;
@@ -368,6 +437,15 @@ struct dasm_mg
 
 extern "C" int
 dasm_mg_create(int n_levels, dasm_op **level_ops, dasm_cheb **smoothers, int one_sided_v_cycle, dasm_mg **out)
+{
+  return dasm_mg_create_with_transfers(n_levels, level_ops, smoothers, nullptr, one_sided_v_cycle, out);
+}
+
+// same with caller-built transfers (transfers[l] between the levels l and l - 1; NULL entries are created here): the geometric levels
+// of an unstructured mesh need the parent map of dasm_transfer_create_unstructured.  The caller keeps the ownership of its transfers.
+extern "C" int
+dasm_mg_create_with_transfers(int n_levels, dasm_op **level_ops, dasm_cheb **smoothers, dasm_transfer **transfers, int one_sided_v_cycle,
+                              dasm_mg **out)
 {
   MG_API_BEGIN
   if (n_levels < 1)
@@ -379,6 +457,7 @@ dasm_mg_create(int n_levels, dasm_op **level_ops, dasm_cheb **smoothers, int one
   mg->one_sided = one_sided_v_cycle != 0;
   mg->stream    = (cudaStream_t)dasm_ctx_stream(dasm_op_ctx(level_ops[0]));
   mg->transfers.assign(n_levels, nullptr);
+  mg->borrowed.assign(n_levels, false);
   for (int l = 0; l < n_levels; ++l)
     {
       if (dasm_op_number_type(level_ops[l]) != mg->ntype)
@@ -398,7 +477,14 @@ dasm_mg_create(int n_levels, dasm_op **level_ops, dasm_cheb **smoothers, int one
       mg->defect.push_back(v[0]);
       mg->solution.push_back(v[1]);
       mg->t.push_back(v[2]);
-      if (l > 0)
+      if (l > 0 && transfers != nullptr && transfers[l] != nullptr)
+        {
+          if (transfers[l]->fine != level_ops[l] || transfers[l]->coarse != level_ops[l - 1])
+            throw std::runtime_error("multigrid: transfer of level " + std::to_string(l) + " does not connect the level operators");
+          mg->transfers[l] = transfers[l];
+          mg->borrowed[l]  = true;
+        }
+      else if (l > 0)
         MG_CALL(dasm_transfer_create(level_ops[l], level_ops[l - 1], &mg->transfers[l]));
     }
   *out = mg;
@@ -417,7 +503,8 @@ dasm_mg_destroy(dasm_mg *mg)
           cudaFree(mg->defect[l]);
           cudaFree(mg->solution[l]);
           cudaFree(mg->t[l]);
-          dasm_transfer_destroy(mg->transfers[l]);
+          if (!mg->borrowed[l])
+            dasm_transfer_destroy(mg->transfers[l]);
         }
       delete mg;
     }

@@ -125,3 +125,16 @@ def rotated_cube(n=2, seed=0, mapfun=None, rotate=True):
         support = mapfun(support)
         vertices = mapfun(vertices)
     return dict(vertices=np.ascontiguousarray(vertices), cells=inv.reshape(-1, 8).astype(np.uint32), support=np.ascontiguousarray(support))
+
+
+def ball_parents(n_refinements):
+    """parent[fine cell] = coarse cell | child position << 28 between hyper_ball(n_refinements) and hyper_ball(n_refinements - 1)
+    (dasm_transfer_create_unstructured): the children of a cell keep its frame"""
+    mf = 2 ** n_refinements
+    mc = mf // 2
+    f = np.arange(32 * mf ** 3, dtype=np.int64)
+    q, r = f // mf ** 3, f % mf ** 3
+    i, j, l = r % mf, (r // mf) % mf, r // (mf * mf)
+    parent = q * mc ** 3 + ((l // 2) * mc + j // 2) * mc + i // 2
+    code = (i & 1) | ((j & 1) << 1) | ((l & 1) << 2)
+    return (parent | (code << 28)).astype(np.uint32)

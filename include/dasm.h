@@ -286,6 +286,9 @@ extern "C"
   int dasm_op_plain_indices(const dasm_op *op, uint32_t *out);         /* [n_cells][(k+1)^3] oriented addresses, host copy */
   int dasm_op_patch_extents(const dasm_op *op, double *out);           /* [n_cells][3][3], include/grid_tools.h:54-138 */
   long long dasm_op_n_cells(const dasm_op *op);
+  int dasm_op_is_unstructured(const dasm_op *op);
+  const uint32_t *dasm_op_device_plain_indices(const dasm_op *op);     /* device copy of the oriented addresses (NULL: compressed storage) */
+  int dasm_op_entity_valence(const dasm_op *op, uint8_t *out);         /* [n_cells][27] cells per entity (unstructured meshes) */
   /* host-only (no device needed): sizes = {n_dofs, n_lines, n_quads, n_constrained}; output arrays may be NULL */
   int dasm_umesh_host_numbering(int degree, long long n_vertices, const double *coords, long long n_cells, const uint32_t *cell_vertices,
                                 const double *support_points, int dirichlet, long long sizes[4], uint32_t *cidx, uint32_t *orientation,
@@ -321,6 +324,10 @@ extern "C"
    * restriction = its transpose; constrained DoFs are read as zero and not written (MGTwoLevelTransfer). */
   typedef struct dasm_transfer dasm_transfer;
   int dasm_transfer_create(dasm_op *fine, dasm_op *coarse, dasm_transfer **out);
+  /* two operators on unstructured meshes: parent == NULL: both on the same mesh (polynomial transfer, coarse degree <= fine degree);
+   * otherwise parent[fine cell] = coarse cell | child position << 28 (bit 28 / 29 / 30: upper half in x / y / z of the parent's frame):
+   * geometric 2:1 transfer between a mesh and its global refinement whose children keep the parent's frame */
+  int dasm_transfer_create_unstructured(dasm_op *fine, dasm_op *coarse, const uint32_t *parent, dasm_transfer **out);
   int dasm_transfer_destroy(dasm_transfer *t);
   int dasm_transfer_prolongate_and_add(dasm_transfer *t, void *dst_fine, const void *src_coarse);
   int dasm_transfer_restrict_and_add(dasm_transfer *t, void *dst_coarse, const void *src_fine);
@@ -330,6 +337,10 @@ extern "C"
    * element_centered_preconditioners_01.cc:787-792).  one_sided_v_cycle: no post-smoothing (include/multigrid.h:303-312). */
   typedef struct dasm_mg dasm_mg;
   int dasm_mg_create(int n_levels, dasm_op **level_ops, dasm_cheb **smoothers, int one_sided_v_cycle, dasm_mg **out);
+  /* same with caller-built transfers (transfers[l] between the levels l and l - 1, NULL entries are created by the library; the caller
+   * keeps their ownership): the geometric levels of an unstructured mesh need dasm_transfer_create_unstructured's parent map */
+  int dasm_mg_create_with_transfers(int n_levels, dasm_op **level_ops, dasm_cheb **smoothers, dasm_transfer **transfers, int one_sided_v_cycle,
+                                    dasm_mg **out);
   int dasm_mg_destroy(dasm_mg *mg);
   /* PreconditionerGMG::vmult (include/multigrid.h:463-469): dst = V-cycle(src); dst / src are device vectors of the finest level's
    * layout in the number type `outer_number_type` (converted to the level number type and back, PreconditionMG copy_to_mg /

@@ -1310,12 +1310,14 @@ class TwoLevelTransfer:
     (MGTwoLevelTransfer::prolongate_and_add / restrict_and_add).
     Geometric transfer: mesh_f has twice the cells of mesh_c per direction, same degree; polynomial transfer: same mesh."""
 
-    def __init__(self, mesh_f, op_f, mesh_c, op_c):
+    def __init__(self, mesh_f, op_f, mesh_c, op_c, parent=None):
+        """parent (unstructured meshes): parent[fine cell] = coarse cell | child position << 28, None on the same mesh"""
         dim = op_f.dim
         self.dim, self.op_f, self.op_c = dim, op_f, op_c
-        self.geometric = tuple(mesh_f.n_cells) != tuple(mesh_c.n_cells)
+        unstructured = not hasattr(mesh_f, "n_cells")
+        self.geometric = (parent is not None) if unstructured else tuple(mesh_f.n_cells) != tuple(mesh_c.n_cells)
         if self.geometric:
-            assert all(f == 2 * c for f, c in zip(mesh_f.n_cells, mesh_c.n_cells)) and op_f.k == op_c.k
+            assert op_f.k == op_c.k and (unstructured or all(f == 2 * c for f, c in zip(mesh_f.n_cells, mesh_c.n_cells)))
             self.P1 = [transfer_matrix_1d(op_f.k, op_c.k, a) for a in (0, 1)]
         else:
             self.P1 = [transfer_matrix_1d(op_f.k, op_c.k)] * 2
@@ -1324,7 +1326,11 @@ class TwoLevelTransfer:
         self.child = np.zeros((mesh_f.C, dim), dtype=np.int64)
         for c in range(mesh_f.C):
             ijk = mesh_f.cell_ijk(c)
-            if self.geometric:
+            if unstructured:
+                self.parent[c] = (int(parent[c]) & 0x0FFFFFFF) if self.geometric else c
+                if self.geometric:
+                    self.child[c] = [(int(parent[c]) >> (28 + d)) & 1 for d in range(dim)]
+            elif self.geometric:
                 self.parent[c] = mesh_c.cell_lex(tuple(i // 2 for i in ijk))
                 self.child[c] = [i % 2 for i in ijk]
             else:

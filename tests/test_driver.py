@@ -89,3 +89,36 @@ def test_element_centered_preconditioners_01_driver(tmp_path):
     p.write_text(json.dumps(cfg))
     out = subprocess.run([SOLVER_DRIVER, str(p)], capture_output=True, text=True, timeout=300)
     assert out.returncode != 0 and "Solver <BiCG> is not known!" in out.stderr
+
+
+POWER_DRIVER = os.path.join(ROOT, "drivers", "power_kernel_01")
+
+
+@pytest.mark.gpu
+def test_power_kernel_01_driver(tmp_path):
+    """the reference's power-kernel driver (power_kernel_01.likwid.cc): its JSON keys, the three norm lines (the fused and the
+    sequential versions produce the same vectors) and the result table with the reference's columns."""
+    if not os.path.exists(POWER_DRIVER):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "drivers")])
+    cfg = {"dim": 3, "fe degree": 3, "n components": 1, "n subdivisions": 14, "n lanes": 4, "cell granularity": 32, "n repetitions": 2,
+           "dof renumbering": False, "use dg": False, "do computation": True, "number type": "double"}
+    p = tmp_path / "in.json"
+    p.write_text(json.dumps(cfg))
+    out = subprocess.run([POWER_DRIVER, str(p)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.splitlines()
+    norms = [[float(v) for v in l.split()] for l in lines if len(l.split()) == 3 and "|" not in l and "{" not in l]
+    assert len(norms) == 3
+    for a, b in zip(norms[0], norms[1]):
+        assert abs(a - b) <= 1e-10 * abs(a)
+    for a, b in zip(norms[0], norms[2]):
+        assert abs(a - b) <= 1e-10 * abs(a)
+    header = [c.strip() for c in [l for l in lines if l.startswith("| degree")][0].strip("|").split("|")]
+    assert header == ["degree", "n_lanes", "granularity", "n_repetitions", "n_procs", "n_cells", "n_dofs", "s_own", "s_batch", "t_own", "t_batch",
+                      "t_sequential", "tp_own", "tp_batch", "tp_sequential"]
+    row = [c.strip() for c in lines[-1 if lines[-1].startswith("|") else -2].strip("|").split("|")]
+    assert int(row[0]) == 3 and int(row[1]) == 4 and int(row[2]) == 32 and int(row[5]) == 8 * 4 * 4 and int(row[6]) == 25 * 13 * 13
+    cfg["use dg"] = True
+    p.write_text(json.dumps(cfg))
+    out = subprocess.run([POWER_DRIVER, str(p)], capture_output=True, text=True, timeout=300)
+    assert out.returncode != 0 and "ExcNotImplemented" in out.stderr

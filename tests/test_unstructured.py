@@ -247,3 +247,111 @@ def test_ball_cg_with_chebyshev_fdm(pkg, ctx):
         ok = plain[c] != 0xFFFFFFFF
         err = max(err, np.abs(x[plain[c][ok]] - (1 - (X[ok] ** 2).sum(-1)) / 6).max())
     assert err < 2e-3
+
+
+# ---- multigrid on the ball: polynomial and geometric two-level transfers, V-cycle, CG + hp-multigrid ------------------------------
+def ball_level(pkg, ctx, L, k, number, wt=None):
+    g = grid.hyper_ball(L)
+    op = pkg.LaplaceOperatorMatrixFree.from_arrays(ctx, g["vertices"], g["cells"], k, g["support"], number=number)
+    m, oop, oP = oracle_problem(g, op, k, NPDT[number], wt)
+    return dict(g=g, op=op, omesh=m, oop=oop, oP=oP)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", [dict(Lf=1, Lc=1, kf=3, kc=1), dict(Lf=0, Lc=0, kf=5, kc=2), dict(Lf=1, Lc=0, kf=2, kc=2), dict(Lf=1, Lc=0, kf=3, kc=3)])
+@pytest.mark.parametrize("number", ["double", "float"])
+def test_two_level_transfer_ball(pkg, ctx, case, number):
+    lf = ball_level(pkg, ctx, case["Lf"], case["kf"], number)
+    lc = ball_level(pkg, ctx, case["Lc"], case["kc"], number)
+    parent = grid.ball_parents(case["Lf"]) if case["Lf"] != case["Lc"] else None
+    tr = pkg.MGTwoLevelTransfer(lf["op"], lc["op"], parent)
+    otr = o.TwoLevelTransfer(lf["omesh"], lf["oop"], lc["omesh"], lc["oop"], parent)
+    dt = NPDT[number]
+    rng = np.random.default_rng(3)
+    uc, uf = rng.uniform(-1, 1, lc["op"].n_dofs()), rng.uniform(-1, 1, lf["op"].n_dofs())
+    base_f, base_c = rng.uniform(-1, 1, lf["op"].n_dofs()), rng.uniform(-1, 1, lc["op"].n_dofs())
+    base_f[lf["oop"].constrained] = 0
+    base_c[lc["oop"].constrained] = 0
+    tol = 1e-12 if number == "double" else 2e-6
+    d = lf["op"].to_device(base_f)
+    tr.prolongate_and_add(d, lc["op"].to_device(uc))
+    assert relerr(lf["op"].to_host(d), otr.prolongate_and_add(base_f.astype(dt), uc.astype(dt)).astype(np.float64)) < tol
+    d = lc["op"].to_device(base_c)
+    tr.restrict_and_add(d, lf["op"].to_device(uf))
+    assert relerr(lc["op"].to_host(d), otr.restrict_and_add(base_c.astype(dt), uf.astype(dt)).astype(np.float64)) < tol
+    if case["Lf"] != case["Lc"] and number == "double":
+        # the prolongation reproduces a coarse finite element function: a linear field given at the coarse nodes arrives at the
+        # fine nodes up to the difference of the two triquadratic geometries (zero for the trilinear inner cells)
+        k = case["kf"]
+        nodes = o.gauss_lobatto_points(k + 1)
+        ref = np.array([(a, b, c) for c in nodes for b in nodes for a in nodes])
+
+        def field(lv):
+            v = np.zeros(lv["op"].n_dofs())
+            plain = lv["op"].plain_indices().astype(np.int64)
+            for c in range(lv["omesh"].C):
+                X = lv["omesh"].cell_points(c, ref)
+                ok = plain[c] != 0xFFFFFFFF
+                v[plain[c][ok]] = 1 + X[ok, 0] - 2 * X[ok, 1] + 0.5 * X[ok, 2]
+            return v
+        d = lf["op"].initialize_dof_vector()
+        tr.prolongate_and_add(d, lc["op"].to_device(field(lc)))
+        got, want = lf["op"].to_host(d), field(lf)
+        inner = np.zeros(lf["op"].n_dofs(), dtype=bool)
+        inner[np.unique(lf["op"].plain_indices()[: 8 * 8 ** case["Lf"]].reshape(-1))[:-1]] = True   # DoFs of the 8 inner coarse cells
+        near_bnd = np.zeros(lf["op"].n_dofs(), dtype=bool)
+        plain_f = lf["op"].plain_indices().astype(np.int64)
+        for c in range(lf["omesh"].C):
+            if np.any(plain_f[c] == 0xFFFFFFFF):
+                near_bnd[plain_f[c][plain_f[c] != 0xFFFFFFFF]] = True
+        sel = inner & ~near_bnd
+        assert np.abs(got - want)[sel].max() < 1e-12
+        assert np.abs(got - want)[~near_bnd].max() < 0.5   # curved shell cells: the level-0 geometry is coarse
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("solver,wt", [("CG", "symm"), ("GMRES", "post")])
+def test_ball_hp_multigrid(pkg, ctx, solver, wt):
+    """the reference's ball experiment in small (experiments/ball.py: CG / GMRES, multigrid with Chebyshev + FDM smoothers): levels
+    (ball 0, k = 1) -> (ball 0, k = 3) -> (ball 1, k = 3), float levels under a double outer solver; iteration count identical to the
+    oracle's and small."""
+    spec = [(0, 1), (0, 3), (1, 3)]
+    levels = [ball_level(pkg, ctx, L, k, "float", wt if k > 1 else None) for L, k in spec]
+    sm, osm = [], []
+    for lv, (L, k) in zip(levels, spec):
+        if k > 1:
+            lv["fdm"] = pkg.create_fdm_preconditioner(lv["op"], {"weighting type": wt})
+            oP = lv["oP"]
+        else:
+            lv["fdm"] = None                      # coarse level: Chebyshev around the point Jacobi preconditioner
+            oP = o.JacobiPreconditioner(lv["oop"])
+        deg = 2 if k > 1 else 8
+        ch = pkg.PreconditionChebyshev(lv["op"], lv["fdm"], degree=deg)
+        och = o.Chebyshev(lv["oop"], oP, degree=deg)
+        mn, mx = ch.estimate_eigenvalues()
+        omn, omx = och.estimate_eigenvalues()
+        assert abs(mx - omx) < 1e-3 * omx
+        och.set_eigenvalues(mx, mn)               # identical smoother parameters on both sides
+        sm.append(ch)
+        osm.append(och)
+    parents = [None, None, grid.ball_parents(1)]
+    trs = [None] + [pkg.MGTwoLevelTransfer(levels[l]["op"], levels[l - 1]["op"], parents[l]) for l in (1, 2)]
+    otr = [None] + [o.TwoLevelTransfer(levels[l]["omesh"], levels[l]["oop"], levels[l - 1]["omesh"], levels[l - 1]["oop"], parents[l]) for l in (1, 2)]
+    omg = o.Multigrid([lv["oop"] for lv in levels], osm, otr)
+    g = levels[-1]["g"]
+    op = pkg.LaplaceOperatorMatrixFree.from_arrays(ctx, g["vertices"], g["cells"], 3, g["support"], number="double")
+    _, oop, _ = oracle_problem(g, op, 3, np.float64)
+    mg = pkg.PreconditionerGMG([lv["op"] for lv in levels], sm, outer_op=op, transfers=trs)
+    bd = op.initialize_dof_vector()
+    op.rhs(bd, 1.0)
+    b = op.to_host(bd)
+    A = lambda v: oop.vmult(v, copy_constrained=True)
+    if solver == "CG":
+        x_ref, its_ref = o.solve_cg(A, omg.vmult, b, rel_tol=1e-6)
+    else:
+        x_ref, its_ref = o.solve_gmres(A, omg.vmult, b, rel_tol=1e-6)
+    xd = op.initialize_dof_vector()
+    its, res = pkg.solve(op, xd, bd, mg, {"type": solver, "rel tolerance": 1e-6})
+    assert its == its_ref
+    assert 2 <= its <= 15
+    assert relerr(op.to_host(xd), x_ref) < 1e-4
