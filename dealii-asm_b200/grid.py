@@ -15,10 +15,17 @@ import itertools
 import numpy as np
 
 
-def _dedup(points, decimals=9):
-    """unique rows of points [N, 3] (rounded) -> (unique [V, 3], inverse [N]) with vertices in order of first appearance"""
-    key = np.round(points, decimals) + 0.0
-    _, first, inv = np.unique(key, axis=0, return_index=True, return_inverse=True)
+def _dedup(points, tol=1e-10):
+    """unique rows of points [N, 3] up to `tol` -> (unique [V, 3], inverse [N]) with vertices in order of first appearance.
+    Every coordinate axis is clustered on its own (sorted values, a new cluster where the gap exceeds tol), a vertex is the triple of
+    its cluster numbers: no rounding boundary can split two evaluations of the same point."""
+    keys = np.zeros(points.shape, dtype=np.int64)
+    for d in range(points.shape[1]):
+        order = np.argsort(points[:, d], kind="stable")
+        v = points[order, d]
+        cluster = np.concatenate([[0], np.cumsum(np.diff(v) > tol)])
+        keys[order, d] = cluster
+    _, first, inv = np.unique(keys, axis=0, return_index=True, return_inverse=True)
     order = np.argsort(first)                    # unique ids sorted by first appearance
     rank = np.empty_like(order)
     rank[order] = np.arange(len(order))

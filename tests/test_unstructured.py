@@ -355,3 +355,15 @@ def test_ball_hp_multigrid(pkg, ctx, solver, wt):
     assert its == its_ref
     assert 2 <= its <= 15
     assert relerr(op.to_host(xd), x_ref) < 1e-4
+
+
+@pytest.mark.parametrize("L", [2, 4])
+def test_ball_is_watertight(L):
+    """the generator merges the vertices of neighbouring cells robustly: the only boundary is the sphere (24 * 4^L faces)"""
+    pkg = load_package()
+    g = grid.hyper_ball(L)
+    h = pkg.umesh_host_numbering(1, g["vertices"], g["cells"], g["support"])
+    F = 24 * 4 ** L
+    assert len(h["constrained"]) == F + 2                      # Euler: V = F + 2 on the sphere
+    assert h["n_quads"] == (6 * len(g["cells"]) + F) // 2
+    assert np.allclose(np.linalg.norm(g["vertices"][h["constrained"]], axis=1), 1.0, atol=1e-12)

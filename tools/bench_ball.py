@@ -79,20 +79,67 @@ def main():
                 xs = x.clone()
                 dc = timed(lambda: cheb.step(xs, b), stream, 5)
                 row.update(cheby_step_value=n * 3 / dc, cheby_step_unit="DoFs/s per Chebyshev term", cheby_step_ms=dc * 1e3)
-                rhs = op.initialize_dof_vector()
-                op.rhs(rhs, 1.0)
-                sol = op.initialize_dof_vector()
-                solver = "CG" if wt == "symm" else "GMRES"
-                ctx.sync()
-                t0 = time.perf_counter()
-                its, res = pkg.solve(op, sol, rhs, cheb, {"type": solver, "rel tolerance": 1e-8})
-                ctx.sync()
-                row.update(solver=solver, iterations=its, solve_s=time.perf_counter() - t0, residual=res)
+                if number == "double":  # (a relative residual of 1e-8 is below single precision)
+                    rhs = op.initialize_dof_vector()
+                    op.rhs(rhs, 1.0)
+                    sol = op.initialize_dof_vector()
+                    solver = "CG" if wt == "symm" else "GMRES"
+                    ctx.sync()
+                    t0 = time.perf_counter()
+                    its, res = pkg.solve(op, sol, rhs, cheb, {"type": solver, "rel tolerance": 1e-8})
+                    ctx.sync()
+                    row.update(solver=solver, iterations=its, solve_s=time.perf_counter() - t0, residual=res, max_u=float(op.to_host(sol).max()),
+                               max_u_exact=1.0 / 6.0)
                 del cheb
             out.write(json.dumps(row) + "\n")
             out.flush()
             del fdm
         del op, x, b, y
+        torch.cuda.empty_cache()
+    # the reference's ball experiment (experiments/ball.py): CG (symm) / GMRES (post) with hp-multigrid, Chebyshev(3) + FDM smoothers,
+    # float levels under a double outer solver; p sequence "bisect" (k -> k/2 -> ... -> 1), then global coarsening to the 32-cell ball
+    for solver, wt in (("CG", "symm"), ("GMRES", "post")):
+        t0 = time.perf_counter()
+        spec = [(l, 1) for l in range(L + 1)]
+        kk, ps = k, []
+        while kk > 1:
+            ps.append(kk)
+            kk = max(1, kk // 2)
+        spec += [(L, q) for q in reversed(ps)]
+        grids = {l: (g if l == L else grid.hyper_ball(l)) for l in range(L + 1)}
+        ops, sms, keep = [], [], []
+        for (l, q) in spec:
+            gl = grids[l]
+            lop = pkg.LaplaceOperatorMatrixFree.from_arrays(ctx, gl["vertices"], gl["cells"], q, gl["support"], number="float")
+            fdm = pkg.create_fdm_preconditioner(lop, {"weighting type": wt, "weight sequence": "dg"}) if q > 1 else None
+            ch = pkg.PreconditionChebyshev(lop, fdm, degree=3 if (l, q) != spec[0] else 8)
+            ch.estimate_eigenvalues()
+            ops.append(lop)
+            sms.append(ch)
+            keep.append(fdm)
+        trs = [None]
+        for i in range(1, len(spec)):
+            par = grid.ball_parents(spec[i][0]) if spec[i][0] != spec[i - 1][0] else None
+            trs.append(pkg.MGTwoLevelTransfer(ops[i], ops[i - 1], par))
+        op = pkg.LaplaceOperatorMatrixFree.from_arrays(ctx, g["vertices"], g["cells"], k, g["support"], number="double")
+        mg = pkg.PreconditionerGMG(ops, sms, outer_op=op, transfers=trs)
+        rhs, sol = op.initialize_dof_vector(), op.initialize_dof_vector()
+        op.rhs(rhs, 1.0)
+        ctx.sync()
+        t_setup = time.perf_counter() - t0
+        pkg.solve(op, sol, rhs, mg, {"type": solver, "rel tolerance": 1e-8})   # warm-up
+        ctx.sync()
+        t0 = time.perf_counter()
+        its, res = pkg.solve(op, sol, rhs, mg, {"type": solver, "rel tolerance": 1e-8})
+        ctx.sync()
+        t_solve = time.perf_counter() - t0
+        x = op.to_host(sol)
+        out.write(json.dumps({"mesh": "hyper_ball", "n_refinements": L, "degree": k, "n_cells": int(op.n_cells()), "n_dofs": int(op.n_dofs()),
+                              "variant": "%s + hp-multigrid, Chebyshev(3) + FDM %s smoothers" % (solver, wt), "levels": spec, "iterations": its,
+                              "time_to_solution_s": t_solve, "setup_s": t_setup, "residual": res, "rel_tolerance": 1e-8,
+                              "max_u": float(x.max()), "max_u_exact": 1.0 / 6.0}) + "\n")
+        out.flush()
+        del mg, trs, sms, keep, ops, op
         torch.cuda.empty_cache()
 
 
