@@ -729,6 +729,12 @@ launch_laplace(dasm_op *op, T *dst, const T *src)
         CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, CPB * n * n, smem, ctx->stream>>>(src, dst, op->d_cidx, (const T *)op->d_geom, op->cart, op->n_cells, op->d_plain, nullptr);
       }
+    else if (op->geom_mode == 5)
+      {
+        auto kern = laplace_generic_kernel<K, T, 3>;
+        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, CPB * n * n, smem, ctx->stream>>>(src, dst, op->d_cidx, (const T *)op->d_geom, op->cart, op->n_cells, op->d_plain, nullptr);
+      }
     else
       {
         auto kern = laplace_generic_kernel<K, T, 1>;
@@ -2700,10 +2706,10 @@ dasm_op_create_unstructured(dasm_ctx *ctx, int degree, int number_type, const ch
   DASM_REQUIRE(ctx != nullptr, "unstructured operator: context required");
   DASM_REQUIRE(n_vertices > 0 && n_cells > 0 && coords != nullptr && cell_vertices != nullptr, "unstructured mesh: empty mesh");
   const std::string mt = mapping_type ? mapping_type : "";
-  if (mt != "" && mt != "merged" && mt != "construct q")
+  if (mt != "" && mt != "merged" && mt != "construct q" && mt != "quadratic geometry")
     {
-      if (mt == "quadratic geometry" || mt == "linear geometry")
-        throw std::runtime_error("Mapping type <" + mt + "> is built for structured meshes only (brick kernels); use \"merged\" or \"construct q\"");
+      if (mt == "linear geometry")
+        throw std::runtime_error("Mapping type <" + mt + "> is built for structured meshes only (brick kernels)");
       throw std::runtime_error("Mapping type <" + mt + "> is not known!"); // operator.h:747-752
     }
   std::unique_ptr<UMesh> U(new UMesh);
@@ -2742,11 +2748,19 @@ dasm_op_create_unstructured(dasm_ctx *ctx, int degree, int number_type, const ch
       op->n_constrained = (long long)op->nb.constrained.size();
       op->exchange.init(ctx, op->nb.exchange, op->esize());
       const int n3      = (degree + 1) * (degree + 1) * (degree + 1);
-      const int per     = (mt == "construct q") ? 3 * n3 : 6 * n3;
-      op->geom_mode     = (mt == "construct q") ? 3 : 1;
+      const int per     = (mt == "construct q") ? 3 * n3 : (mt == "quadratic geometry" ? 81 : 6 * n3);
+      op->geom_mode     = (mt == "construct q") ? 3 : (mt == "quadratic geometry" ? 5 : 1);
       std::vector<double> g((size_t)n_cells * per);
       for (long long c = 0; c < n_cells; ++c)
-        if (op->geom_mode == 3)
+        if (op->geom_mode == 5)
+          {
+            // "quadratic geometry" (operator.h:1035-1159): 81 numbers per cell, the Jacobian is rebuilt per quadrature point in the
+            // kernel; only differences of the support points enter it, so they are stored relative to the first one (single precision)
+            const double *X = U->support.data() + (size_t)c * 81;
+            for (int i = 0; i < 81; ++i)
+              g[(size_t)c * 81 + i] = X[i] - X[i % 3];
+          }
+        else if (op->geom_mode == 3)
           U->cell_geometry(c, op->basis, g.data() + (size_t)c * per, nullptr, nullptr);
         else
           U->cell_geometry(c, op->basis, nullptr, nullptr, g.data() + (size_t)c * per);
@@ -2978,6 +2992,8 @@ op_inverse_diagonal(dasm_op *op, T *diag)
       laplace_diagonal_kernel<K, T, 0><<<nblocks(total, 128), 128, 0, ctx->stream>>>(diag, op->d_cidx, (const T *)nullptr, op->cart, op->n_cells, op->d_plain);
     else if (op->geom_mode == 3)
       laplace_diagonal_kernel<K, T, 2><<<nblocks(total, 128), 128, 0, ctx->stream>>>(diag, op->d_cidx, (const T *)op->d_geom, op->cart, op->n_cells, op->d_plain);
+    else if (op->geom_mode == 5)
+      laplace_diagonal_kernel<K, T, 3><<<nblocks(total, 128), 128, 0, ctx->stream>>>(diag, op->d_cidx, (const T *)op->d_geom, op->cart, op->n_cells, op->d_plain);
     else
       laplace_diagonal_kernel<K, T, 1><<<nblocks(total, 128), 128, 0, ctx->stream>>>(diag, op->d_cidx, (const T *)op->d_geom, op->cart, op->n_cells, op->d_plain);
   });

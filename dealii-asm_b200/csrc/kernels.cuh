@@ -217,8 +217,98 @@ namespace dasm
         G[cc] = jxw * (I[d][0] * I[e][0] + I[d][1] * I[e][1] + I[d][2] * I[e][2]);
   }
 
+  // "quadratic geometry" on unstructured meshes (operator.h:1035-1159: the Jacobian rebuilt per quadrature point from the 27 x 3
+  // coefficients of the triquadratic cell map; here the coefficients are the support points themselves, shifted by the first one).
+  // A thread works along an x-line of quadrature points at fixed (ty, tz): the sums over the y and z basis functions are formed once
+  // per line (P0: d/dxi, P1: d/deta, P2: d/dzeta still open in x), a point then costs 27 FMAs for its Jacobian.
+  template <typename T>
+  __device__ __forceinline__ void
+  q2_basis(const T t, T (&V)[3], T (&D)[3])
+  {
+    V[0] = (T(1) - T(2) * t) * (T(1) - t);
+    V[1] = T(4) * t * (T(1) - t);
+    V[2] = t * (T(2) * t - T(1));
+    D[0] = T(4) * t - T(3);
+    D[1] = T(4) - T(8) * t;
+    D[2] = T(4) * t - T(1);
+  }
+
+  template <typename T>
+  struct SupportLine
+  {
+    T P0[3][3], P1[3][3], P2[3][3]; // [i][e]
+  };
+
+  template <typename T>
+  __device__ __forceinline__ void
+  support_line(const T *__restrict__ X, const T ty, const T tz, SupportLine<T> &L)
+  {
+    T Vy[3], Dy[3], Vz[3], Dz[3];
+    q2_basis(ty, Vy, Dy);
+    q2_basis(tz, Vz, Dz);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int e = 0; e < 3; ++e)
+        L.P0[i][e] = L.P1[i][e] = L.P2[i][e] = T(0);
+#pragma unroll
+    for (int l = 0; l < 3; ++l)
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        {
+          const T w0 = Vy[j] * Vz[l], w1 = Dy[j] * Vz[l], w2 = Vy[j] * Dz[l];
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int e = 0; e < 3; ++e)
+              {
+                const T x = X[(9 * l + 3 * j + i) * 3 + e];
+                L.P0[i][e] += w0 * x;
+                L.P1[i][e] += w1 * x;
+                L.P2[i][e] += w2 * x;
+              }
+        }
+  }
+
+  // G = JxW J^-1 J^-T at the point tx of the line (w = product of the three quadrature weights), order xx xy xz yy yz zz
+  template <typename T>
+  __device__ __forceinline__ void
+  support_point_coefficients(const SupportLine<T> &L, const T tx, const T w, T (&G)[6])
+  {
+    T Vx[3], Dx[3], J[3][3];
+    q2_basis(tx, Vx, Dx);
+#pragma unroll
+    for (int e = 0; e < 3; ++e)
+      {
+        J[e][0] = Dx[0] * L.P0[0][e] + Dx[1] * L.P0[1][e] + Dx[2] * L.P0[2][e];
+        J[e][1] = Vx[0] * L.P1[0][e] + Vx[1] * L.P1[1][e] + Vx[2] * L.P1[2][e];
+        J[e][2] = Vx[0] * L.P2[0][e] + Vx[1] * L.P2[1][e] + Vx[2] * L.P2[2][e];
+      }
+    const T det = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) - J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0]) +
+                  J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+    const T id = T(1) / det;
+    T       I[3][3];
+    I[0][0] = (J[1][1] * J[2][2] - J[1][2] * J[2][1]) * id;
+    I[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * id;
+    I[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * id;
+    I[1][0] = (J[1][2] * J[2][0] - J[1][0] * J[2][2]) * id;
+    I[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * id;
+    I[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * id;
+    I[2][0] = (J[1][0] * J[2][1] - J[1][1] * J[2][0]) * id;
+    I[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * id;
+    I[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * id;
+    const T jxw = det * w;
+    int     cc  = 0;
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+#pragma unroll
+      for (int e = d; e < 3; ++e, ++cc)
+        G[cc] = jxw * (I[d][0] * I[e][0] + I[d][1] * I[e][1] + I[d][2] * I[e][2]);
+  }
+
   // ---- K1: Laplace cell kernel (generic) ---------------------------------------------------------
-  // GEOM 0: uniform Cartesian (3 constants), 1: merged coefficients geom[cell][6][n^3], 2: construct q, geom[cell][3][n^3]
+  // GEOM 0: uniform Cartesian (3 constants), 1: merged coefficients geom[cell][6][n^3], 2: construct q, geom[cell][3][n^3],
+  // 3: support points of the triquadratic cell map geom[cell][27][3] (Jacobian rebuilt per point)
   template <int k, typename T, int GEOM>
   __global__ void __launch_bounds__(cells_per_block<k>() * (k + 1) * (k + 1))
   laplace_generic_kernel(const T *__restrict__ src,
@@ -249,9 +339,13 @@ namespace dasm
     T *GY = GX + n3;
     T *GZ = GY + n3;
     __shared__ uint32_t s_ci[CPB][27];
+    __shared__ T        s_X[GEOM == 3 ? CPB : 1][81];
     if (act)
       for (int e = t; e < 27; e += n2)
         s_ci[cl][e] = cidx[cell * 27 + e];
+    if (GEOM == 3 && act)
+      for (int e = t; e < 81; e += n2)
+        s_X[cl][e] = geom[(size_t)cell * 81 + e];
     __syncthreads();
 
     const auto &B = BasisOf<T>::template get<k>();
@@ -302,6 +396,9 @@ namespace dasm
     // quadrature-point operation on the x-line (y=a, z=b)
     if (act)
       {
+        SupportLine<T> SL;
+        if (GEOM == 3)
+          support_line<T>(s_X[cl], B.qp[a], B.qp[b], SL);
 #pragma unroll
         for (int x = 0; x < n; ++x)
           {
@@ -321,6 +418,14 @@ namespace dasm
                 GX[q]        = gxx * gx + gxy * gy + gxz * gz;
                 GY[q]        = gxy * gx + gyy * gy + gyz * gz;
                 GZ[q]        = gxz * gx + gyz * gy + gzz * gz;
+              }
+            else if (GEOM == 3)
+              {
+                T G[6];
+                support_point_coefficients<T>(SL, B.qp[x], B.qw[x] * B.qw[a] * B.qw[b], G);
+                GX[q] = G[0] * gx + G[1] * gy + G[2] * gz;
+                GY[q] = G[1] * gx + G[3] * gy + G[4] * gz;
+                GZ[q] = G[2] * gx + G[4] * gy + G[5] * gz;
               }
             else
               {
@@ -388,6 +493,10 @@ namespace dasm
     double      s  = 0;
     for (int qz = 0; qz < n; ++qz)
       for (int qy = 0; qy < n; ++qy)
+        {
+          SupportLine<T> SL;
+          if (GEOM == 3)
+            support_line<T>(geom + (size_t)cell * 81, B.qp[qy], B.qp[qz], SL);
         for (int qx = 0; qx < n; ++qx)
           {
             const double gx = (double)B.Dn[qx * n + ix] * (double)B.N[qy * n + iy] * (double)B.N[qz * n + iz];
@@ -405,6 +514,13 @@ namespace dasm
                 s += (double)G[0] * gx * gx + (double)G[3 * n3] * gy * gy + (double)G[5 * n3] * gz * gz +
                      2 * ((double)G[n3] * gx * gy + (double)G[2 * n3] * gx * gz + (double)G[4 * n3] * gy * gz);
               }
+            else if (GEOM == 3)
+              {
+                T G[6];
+                support_point_coefficients<T>(SL, B.qp[qx], B.qw[qx] * B.qw[qy] * B.qw[qz], G);
+                s += (double)G[0] * gx * gx + (double)G[3] * gy * gy + (double)G[5] * gz * gz +
+                     2 * ((double)G[1] * gx * gy + (double)G[2] * gx * gz + (double)G[4] * gy * gz);
+              }
             else
               {
                 T G[6];
@@ -413,6 +529,7 @@ namespace dasm
                      2 * ((double)G[1] * gx * gy + (double)G[2] * gx * gz + (double)G[4] * gy * gz);
               }
           }
+        }
     const uint32_t gi = plain ? plain[gid] : compressed_index<k>(cidx + cell * 27, ix, iy, iz);
     if (gi != DEV_INVALID)
       atomic_add(diag + gi, (T)s);

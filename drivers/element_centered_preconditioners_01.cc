@@ -3,7 +3,7 @@
 // (element_centered_preconditioners_01.cc of the reference: solve() 108-263, test() 266-778, MyMultigrid include/precondition.h:82-186).
 //
 //   keys: "type" ("matrixfree"), "dim" (3), "degree", "n refinements", "operator mapping type", "operator compress indices",
-//         "mesh": {"name": "hypercube" | "kershaw", "n subdivisions", "n initial refinements", "eps" | "epsy" / "epsz"},
+//         "mesh": {"name": "hypercube" | "kershaw" | "hyperball", "n subdivisions", "n initial refinements", "eps" | "epsy" / "epsz"},
 //         "solver": {"type": "CG" | "GMRES", "max iterations", "abs tolerance", "rel tolerance", "max n tmp vectors"},
 //         "preconditioner": {"type": "Identity" | "Diagonal" | "FDM" | "Chebyshev" | "AdditiveSchwarzPreconditioner" | "Multigrid",
 //                            "mg type": "h" | "p", "mg p sequence": "bisect" | "decrease by one" | "go to one",
@@ -12,7 +12,9 @@
 //           and its result table.
 // The mesh is libdasm's structured hexahedral mesh (the reference's hyper_cube / subdivided_hyper_cube + global refinement; Kershaw map
 // include/kershaw.h); matrix-free level operators are float, the outer operator and the Krylov vectors double
-// (LaplaceOperatorMatrixFreeTrait, :787-792).  Not available here: dim = 2, "type": "matrixbased", AMG, hyperball.
+// (LaplaceOperatorMatrixFreeTrait, :787-792); "hyperball" is the unstructured ball of include/dasm/grid_generator.h (FDM with n overlap = 1 on
+// degrees >= 2, multigrid h / p / hp / ph through transfers with the parent map of the refinement).  Not available here: dim = 2,
+// "type": "matrixbased", AMG.
 //
 //   ./element_centered_preconditioners_01 input_0.json [input_1.json ...]
 #include <chrono>
@@ -121,6 +123,7 @@ test(const ptree &params, Context &ctx)
   int    coarse_cells = 1, map_kind = DASM_MAP_CARTESIAN;
   double map_params[4] = {0, 0, 0, 0};
   unsigned int n_levels_h = n_refine + 1;
+  bool         is_ball    = false;
   if (geometry == "hypercube")
     {
       coarse_cells = mesh_prm.get<int>("n subdivisions", 1);
@@ -142,6 +145,12 @@ test(const ptree &params, Context &ctx)
       map_params[1] = epsz;
       n_levels_h += n_initial; // subdivided_hyper_cube(n) + n_initial + n_refine global refinements
     }
+  else if (geometry == "hyperball")
+    {
+      // GridGenerator::hyper_ball_balanced + MappingQCache(2) in the reference (:398-402); here include/dasm/grid_generator.h
+      is_ball = true;
+      std::cout << "- Create mesh: hyperball" << std::endl << std::endl;
+    }
   else
     throw std::runtime_error("Geometry with the name <" + geometry + "> is not known!");
 
@@ -153,14 +162,28 @@ test(const ptree &params, Context &ctx)
     return std::make_shared<Mesh>(ctx, nc, periodic, /*dirichlet*/ true, length, map_kind, map_params);
   };
   const unsigned int finest = n_levels_h - 1;
-  auto               mesh   = make_mesh(finest);
   using OperatorType        = LaplaceOperatorMatrixFree<3, double>;
   using LevelOperatorType   = LaplaceOperatorMatrixFree<3, float>;
-  OperatorType op(*mesh, fe_degree, OperatorType::AdditionalData(op_compress, op_mapping));
-  print_operator(op, mesh->n_cells(), op_compress, op_mapping);
+  std::shared_ptr<Mesh>                          mesh;
+  std::vector<std::shared_ptr<UnstructuredMesh>> umeshes(n_levels_h);
+  auto make_umesh = [&](const unsigned int level) {
+    if (!umeshes[level])
+      umeshes[level] = std::make_shared<UnstructuredMesh>(GridGenerator::hyper_ball(level));
+    return umeshes[level];
+  };
+  std::unique_ptr<OperatorType> op_ptr;
+  if (is_ball)
+    op_ptr.reset(new OperatorType(ctx, *make_umesh(finest), fe_degree, OperatorType::AdditionalData(op_compress, op_mapping)));
+  else
+    {
+      mesh = make_mesh(finest);
+      op_ptr.reset(new OperatorType(*mesh, fe_degree, OperatorType::AdditionalData(op_compress, op_mapping)));
+    }
+  OperatorType &op = *op_ptr;
+  print_operator(op, op.n_cells(), op_compress, op_mapping);
 
   Result result;
-  result.n_cells = mesh->n_cells();
+  result.n_cells = op.n_cells();
   result.L       = (int)n_levels_h;
   result.n_dofs  = (long long)op.m();
 
@@ -216,10 +239,15 @@ test(const ptree &params, Context &ctx)
       std::vector<std::shared_ptr<PreconditionChebyshev<3, float>>>         mg_smoothers;
       for (const auto &lv : levels)
         {
-          if (!meshes[lv.first])
-            meshes[lv.first] = lv.first == finest ? mesh : make_mesh(lv.first);
-          mg_operators.push_back(std::make_shared<LevelOperatorType>(*meshes[lv.first], lv.second, LevelOperatorType::AdditionalData(op_compress, op_mapping)));
-          print_operator(*mg_operators.back(), meshes[lv.first]->n_cells(), op_compress, op_mapping);
+          if (is_ball)
+            mg_operators.push_back(std::make_shared<LevelOperatorType>(ctx, *make_umesh(lv.first), lv.second, LevelOperatorType::AdditionalData(op_compress, op_mapping)));
+          else
+            {
+              if (!meshes[lv.first])
+                meshes[lv.first] = lv.first == finest ? mesh : make_mesh(lv.first);
+              mg_operators.push_back(std::make_shared<LevelOperatorType>(*meshes[lv.first], lv.second, LevelOperatorType::AdditionalData(op_compress, op_mapping)));
+            }
+          print_operator(*mg_operators.back(), mg_operators.back()->n_cells(), op_compress, op_mapping);
         }
       for (unsigned int l = 0; l < levels.size(); ++l)
         {
@@ -234,8 +262,20 @@ test(const ptree &params, Context &ctx)
           keep.push_back(p);
           mg_smoothers.push_back(s->chebyshev);
         }
-      PreconditionerGMG<3, float, double> mg(mg_operators, mg_smoothers, precon_prm.get<bool>("one-sided v-cycle", false));
-      result.it = solve(op, solution, rhs, DASM_PRECON_MULTIGRID, mg.handle(), solver_prm, ctx);
+      std::unique_ptr<PreconditionerGMG<3, float, double>> mg;
+      if (is_ball)
+        {
+          // unstructured levels: the geometric transfers need the parent map of the refinement
+          std::vector<std::shared_ptr<MGTwoLevelTransfer<3, float>>> transfers(levels.size());
+          for (unsigned int l = 1; l < levels.size(); ++l)
+            transfers[l] = std::make_shared<MGTwoLevelTransfer<3, float>>(*mg_operators[l], *mg_operators[l - 1],
+                                                                          levels[l].first != levels[l - 1].first ? GridGenerator::ball_parents(levels[l].first) :
+                                                                                                                    std::vector<std::uint32_t>());
+          mg.reset(new PreconditionerGMG<3, float, double>(mg_operators, mg_smoothers, transfers, precon_prm.get<bool>("one-sided v-cycle", false)));
+        }
+      else
+        mg.reset(new PreconditionerGMG<3, float, double>(mg_operators, mg_smoothers, precon_prm.get<bool>("one-sided v-cycle", false)));
+      result.it = solve(op, solution, rhs, DASM_PRECON_MULTIGRID, mg->handle(), solver_prm, ctx);
     }
   else if (precon_type == "AdditiveSchwarzPreconditioner")
     {

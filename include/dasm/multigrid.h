@@ -22,7 +22,15 @@ namespace dasm
     {
       check(dasm_transfer_create(fine.handle(), coarse.handle(), &h));
     }
+    // operators on unstructured meshes, geometric transfer: parent[fine cell] = coarse cell | child position << 28
+    // (GridGenerator::ball_parents)
+    MGTwoLevelTransfer(const LaplaceOperatorMatrixFree<dim, Number> &fine, const LaplaceOperatorMatrixFree<dim, Number> &coarse,
+                       const std::vector<std::uint32_t> &parent)
+    {
+      check(dasm_transfer_create_unstructured(fine.handle(), coarse.handle(), parent.empty() ? nullptr : parent.data(), &h));
+    }
     ~MGTwoLevelTransfer() { dasm_transfer_destroy(h); }
+    dasm_transfer *handle() const { return h; }
     MGTwoLevelTransfer(const MGTwoLevelTransfer &) = delete;
     void prolongate_and_add(VectorType &dst, const VectorType &src) const { check(dasm_transfer_prolongate_and_add(h, dst.data(), src.data())); }
     void restrict_and_add(VectorType &dst, const VectorType &src) const { check(dasm_transfer_restrict_and_add(h, dst.data(), src.data())); }
@@ -59,6 +67,28 @@ namespace dasm
         sms.push_back(s->handle());
       check(dasm_mg_create((int)ops.size(), ops.data(), sms.data(), use_one_sided_v_cycle ? 1 : 0, &h));
     }
+    // same with caller-built transfers (entry l between the levels l and l - 1, empty pointers are built by the library): the geometric
+    // levels of an unstructured mesh
+    PreconditionerGMG(const std::vector<std::shared_ptr<LevelMatrixType>> &mg_operators,
+                      const std::vector<std::shared_ptr<SmootherType>> &   mg_smoothers,
+                      const std::vector<std::shared_ptr<MGTwoLevelTransfer<dim, LevelNumber>>> &transfers, const bool use_one_sided_v_cycle = false)
+      : mg_operators(mg_operators)
+      , mg_smoothers(mg_smoothers)
+      , mg_transfers(transfers)
+    {
+      if (mg_operators.size() != mg_smoothers.size() || mg_operators.size() != transfers.size() || mg_operators.empty())
+        throw std::runtime_error("ExcDimensionMismatch: one smoother and one transfer entry per multigrid level are needed");
+      std::vector<dasm_op *>       ops;
+      std::vector<dasm_cheb *>     sms;
+      std::vector<dasm_transfer *> trs;
+      for (const auto &o : mg_operators)
+        ops.push_back(o->handle());
+      for (const auto &s : mg_smoothers)
+        sms.push_back(s->handle());
+      for (const auto &t : transfers)
+        trs.push_back(t ? t->handle() : nullptr);
+      check(dasm_mg_create_with_transfers((int)ops.size(), ops.data(), sms.data(), trs.data(), use_one_sided_v_cycle ? 1 : 0, &h));
+    }
     ~PreconditionerGMG() override { dasm_mg_destroy(h); }
 
     void
@@ -74,6 +104,7 @@ namespace dasm
   private:
     std::vector<std::shared_ptr<LevelMatrixType>> mg_operators;
     std::vector<std::shared_ptr<SmootherType>>    mg_smoothers;
+    std::vector<std::shared_ptr<MGTwoLevelTransfer<dim, LevelNumber>>> mg_transfers;
     dasm_mg *                                     h = nullptr;
     mutable unsigned int                          all_mg_counter = 0;
   };

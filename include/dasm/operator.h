@@ -16,6 +16,8 @@
 
 #include "../dasm.h"
 
+#include "grid_generator.h"
+
 namespace dasm
 {
   inline void
@@ -163,12 +165,23 @@ namespace dasm
     };
 
     LaplaceOperatorMatrixFree(Mesh &mesh, const unsigned int fe_degree, const AdditionalData &ad = AdditionalData())
-      : mesh(mesh)
+      : mesh(&mesh)
       , fe_degree(fe_degree)
     {
       check(dasm_op_create(mesh.h, (int)fe_degree, NumberType<Number>::value, ad.mapping_type.c_str(), ad.compress_indices ? 1 : 0, &h));
     }
+    // operator on an unstructured all-hex mesh given by arrays (grid_generator.h; dasm_op_create_unstructured): the ball of
+    // element_centered_preconditioners_01.cc:398-402.  Homogeneous Dirichlet conditions on the whole boundary (:404-413).
+    LaplaceOperatorMatrixFree(Context &ctx, const UnstructuredMesh &umesh, const unsigned int fe_degree, const AdditionalData &ad = AdditionalData())
+      : mesh(nullptr)
+      , fe_degree(fe_degree)
+    {
+      check(dasm_op_create_unstructured(ctx.h, (int)fe_degree, NumberType<Number>::value, ad.mapping_type.c_str(), umesh.n_vertices(),
+                                        umesh.vertices.data(), umesh.n_cells(), umesh.cells.data(),
+                                        umesh.support.empty() ? nullptr : umesh.support.data(), 1, &h));
+    }
     ~LaplaceOperatorMatrixFree() override { dasm_op_destroy(h); }
+    long long n_cells() const { return dasm_op_n_cells(h); }
 
     virtual bool uses_compressed_indices() const { return dasm_op_uses_compressed_indices(h) != 0; }
     static constexpr bool is_matrix_free() { return true; }
@@ -225,11 +238,17 @@ namespace dasm
       check(dasm_op_inverse_diagonal(h, diagonal.data()));
     }
     unsigned int get_fe_degree() const { return fe_degree; }
-    Mesh &       get_mesh() const { return mesh; }
+    Mesh &
+    get_mesh() const
+    {
+      if (mesh == nullptr)
+        throw std::runtime_error("the operator lives on an unstructured mesh");
+      return *mesh;
+    }
     dasm_op *    handle() const { return h; }
 
   private:
-    Mesh &       mesh;
+    Mesh *       mesh;
     unsigned int fe_degree;
     dasm_op *    h = nullptr;
   };

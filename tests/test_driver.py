@@ -122,3 +122,49 @@ def test_power_kernel_01_driver(tmp_path):
     p.write_text(json.dumps(cfg))
     out = subprocess.run([POWER_DRIVER, str(p)], capture_output=True, text=True, timeout=300)
     assert out.returncode != 0 and "ExcNotImplemented" in out.stderr
+
+
+@pytest.mark.gpu
+def test_element_centered_preconditioners_01_hyperball(tmp_path):
+    """BASELINE configs[3] through the reference's solver driver: "mesh": {"name": "hyperball"} (element_centered_preconditioners_01.cc:398-402),
+    CG + hp-multigrid with Chebyshev + FDM smoothers.  The C++ ball generator (include/dasm/grid_generator.h) and the Python one
+    (dealii-asm_b200/grid.py) feed the same library: same number of cells / DoFs and the same iteration count."""
+    import importlib
+    import numpy as np
+    from __graft_entry__ import load_package
+    if not os.path.exists(SOLVER_DRIVER):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "drivers")])
+    smoother = {"type": "Chebyshev", "degree": 2, "preconditioner": {"type": "FDM", "n overlap": 1, "weighting type": "symm"}}
+    coarse = {"type": "Chebyshev", "degree": 8, "preconditioner": {"type": "Diagonal"}}
+    cfg = {"type": "matrixfree", "dim": 3, "degree": 3, "n refinements": 1, "mesh": {"name": "hyperball"},
+           "solver": {"type": "CG", "rel tolerance": 1e-6},
+           "preconditioner": {"type": "Multigrid", "mg type": "hp", "mg p sequence": "bisect", "mg smoother": smoother, "mg coarse grid solver": coarse}}
+    p = tmp_path / "ball.json"
+    p.write_text(json.dumps(cfg))
+    out = subprocess.run([SOLVER_DRIVER, str(p)], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr + out.stdout[-2000:]
+    assert "- Create mesh: hyperball" in out.stdout
+    its = int([l for l in out.stdout.splitlines() if "n iterations:" in l][0].split()[-1])
+    row = out.stdout.strip().splitlines()[-1].split("|")
+    # the same configuration through the Python mirror
+    pkg = load_package()
+    grid = importlib.import_module("dealii-asm_b200.grid")
+    ctx = pkg.Context(0)
+    spec = [(0, 1), (0, 3), (1, 3)]
+    gs = {0: grid.hyper_ball(0), 1: grid.hyper_ball(1)}
+    ops = [pkg.LaplaceOperatorMatrixFree.from_arrays(ctx, gs[L]["vertices"], gs[L]["cells"], k, gs[L]["support"], number="float") for L, k in spec]
+    sms = [pkg.create_system_preconditioner(o_, coarse if i == 0 else smoother) for i, o_ in enumerate(ops)]
+    trs = [None, pkg.MGTwoLevelTransfer(ops[1], ops[0]), pkg.MGTwoLevelTransfer(ops[2], ops[1], grid.ball_parents(1))]
+    A = pkg.LaplaceOperatorMatrixFree.from_arrays(ctx, gs[1]["vertices"], gs[1]["cells"], 3, gs[1]["support"])
+    assert int(row[1]) == A.n_cells() == 256 and int(row[3]) == A.n_dofs()
+    mg = pkg.PreconditionerGMG(ops, sms, outer_op=A, transfers=trs)
+    b, x = A.initialize_dof_vector(), A.initialize_dof_vector()
+    A.rhs(b, 1.0)
+    its_py, _ = pkg.solve(A, x, b, mg, {"type": "CG", "rel tolerance": 1e-6})
+    assert its == its_py and 2 <= its <= 15
+    assert abs(float(A.to_host(x).max()) - 1.0 / 6.0) < 2e-3
+    # FDM on a degree-1 level of the ball is rejected with the library's message
+    cfg["preconditioner"]["mg coarse grid solver"] = smoother
+    p.write_text(json.dumps(cfg))
+    out = subprocess.run([SOLVER_DRIVER, str(p)], capture_output=True, text=True, timeout=600)
+    assert out.returncode != 0 and "degrees >= 2" in (out.stderr + out.stdout)

@@ -127,7 +127,7 @@ def oracle_problem(g, op, k, dtype, weight_type=None, dirichlet=True):
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,k", [("cube2", 2), ("cube3_wavy", 3), ("cube3_wavy", 4), ("ball0", 5), ("ball1", 2), ("ball1", 3), ("ball0", 7)])
 @pytest.mark.parametrize("number", ["double", "float"])
-@pytest.mark.parametrize("mapping_type", ["", "construct q"])
+@pytest.mark.parametrize("mapping_type", ["", "construct q", "quadratic geometry"])
 def test_vmult_and_diagonal(pkg, ctx, name, k, number, mapping_type):
     import torch
     g = make_mesh(name)

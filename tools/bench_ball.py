@@ -110,7 +110,7 @@ def main():
         ops, sms, keep = [], [], []
         for (l, q) in spec:
             gl = grids[l]
-            lop = pkg.LaplaceOperatorMatrixFree.from_arrays(ctx, gl["vertices"], gl["cells"], q, gl["support"], number="float")
+            lop = pkg.LaplaceOperatorMatrixFree.from_arrays(ctx, gl["vertices"], gl["cells"], q, gl["support"], number="float", mapping_type=mapping_type)
             fdm = pkg.create_fdm_preconditioner(lop, {"weighting type": wt, "weight sequence": "dg"}) if q > 1 else None
             ch = pkg.PreconditionChebyshev(lop, fdm, degree=3 if (l, q) != spec[0] else 8)
             ch.estimate_eigenvalues()
@@ -121,7 +121,7 @@ def main():
         for i in range(1, len(spec)):
             par = grid.ball_parents(spec[i][0]) if spec[i][0] != spec[i - 1][0] else None
             trs.append(pkg.MGTwoLevelTransfer(ops[i], ops[i - 1], par))
-        op = pkg.LaplaceOperatorMatrixFree.from_arrays(ctx, g["vertices"], g["cells"], k, g["support"], number="double")
+        op = pkg.LaplaceOperatorMatrixFree.from_arrays(ctx, g["vertices"], g["cells"], k, g["support"], number="double", mapping_type=mapping_type)
         mg = pkg.PreconditionerGMG(ops, sms, outer_op=op, transfers=trs)
         rhs, sol = op.initialize_dof_vector(), op.initialize_dof_vector()
         op.rhs(rhs, 1.0)
@@ -135,7 +135,7 @@ def main():
         t_solve = time.perf_counter() - t0
         x = op.to_host(sol)
         out.write(json.dumps({"mesh": "hyper_ball", "n_refinements": L, "degree": k, "n_cells": int(op.n_cells()), "n_dofs": int(op.n_dofs()),
-                              "variant": "%s + hp-multigrid, Chebyshev(3) + FDM %s smoothers" % (solver, wt), "levels": spec, "iterations": its,
+                              "variant": "%s + hp-multigrid, Chebyshev(3) + FDM %s smoothers" % (solver, wt), "mapping_type": mapping_type or "merged", "levels": spec, "iterations": its,
                               "time_to_solution_s": t_solve, "setup_s": t_setup, "residual": res, "rel_tolerance": 1e-8,
                               "max_u": float(x.max()), "max_u_exact": 1.0 / 6.0}) + "\n")
         out.flush()
