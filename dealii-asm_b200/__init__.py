@@ -438,6 +438,21 @@ class PreconditionChebyshev:
         """host-buffer call (float64 numpy arrays of the owned size; dst is updated in place)."""
         _check(lib().dasm_cheb_step_host(self.h, dst_np.ctypes.data_as(ctypes.c_void_p), src_np.ctypes.data_as(ctypes.c_void_p)))
 
+    def step_host_batch(self, dst_list, src_list):
+        """pipelined host-buffer call for independent problems: dst_list[i] (x_i, updated in place) and src_list[i] (b_i) are float64
+        numpy arrays of the owned size, ideally views of pinned memory; copies of neighbouring problems overlap the kernels."""
+        n = len(dst_list)
+        assert n == len(src_list)
+        d = (ctypes.c_void_p * n)(*[a.ctypes.data for a in dst_list])
+        s_ = (ctypes.c_void_p * n)(*[a.ctypes.data for a in src_list])
+        _check(lib().dasm_cheb_step_host_batch(self.h, n, d, s_))
+
+    def vmult_host_batch(self, dst_list, src_list):
+        n = len(dst_list)
+        d = (ctypes.c_void_p * n)(*[a.ctypes.data for a in dst_list])
+        s_ = (ctypes.c_void_p * n)(*[a.ctypes.data for a in src_list])
+        _check(lib().dasm_cheb_vmult_host_batch(self.h, n, d, s_))
+
     def vmult_host(self, dst_np, src_np):
         _check(lib().dasm_cheb_vmult_host(self.h, dst_np.ctypes.data_as(ctypes.c_void_p), src_np.ctypes.data_as(ctypes.c_void_p)))
 

@@ -519,6 +519,15 @@ struct dasm_cheb
   void *    d_inv_diag = nullptr;
   void *    t1 = nullptr, *t1b = nullptr, *t2 = nullptr, *xold = nullptr, *xin = nullptr, *bin = nullptr;
   void *    d_stage = nullptr; // single precision: double staging buffer of the host entry points
+  // pipelined host entry point (dasm_cheb_step_host_batch): two sets of device vectors, one copy stream per direction
+  struct Pipe
+  {
+    bool         ready = false;
+    cudaStream_t h2d = nullptr, d2h = nullptr;
+    cudaEvent_t  ev_h2d[2], ev_run[2], ev_d2h[2];
+    void *       x[2] = {nullptr, nullptr}, *b[2] = {nullptr, nullptr};
+    double *     sx[2] = {nullptr, nullptr}, *sb[2] = {nullptr, nullptr};
+  } pipe;
   int       t1_zero_idx = -1; // residual buffer (0 / 1) whose shared DoFs the last kernel of the previous fused call left zero
 };
 
@@ -4420,6 +4429,23 @@ dasm_cheb_destroy(dasm_cheb *c)
   cudaStreamSynchronize(c->op->ctx->stream);
   for (void *p : {c->t1, c->t1b, c->t2, c->xold, c->xin, c->bin, c->d_inv_diag, c->d_stage})
     cudaFree(p);
+  if (c->pipe.ready)
+    {
+      cudaStreamSynchronize(c->pipe.h2d);
+      cudaStreamSynchronize(c->pipe.d2h);
+      for (int i = 0; i < 2; ++i)
+        {
+          cudaFree(c->pipe.x[i]);
+          cudaFree(c->pipe.b[i]);
+          cudaFree(c->pipe.sx[i]);
+          cudaFree(c->pipe.sb[i]);
+          cudaEventDestroy(c->pipe.ev_h2d[i]);
+          cudaEventDestroy(c->pipe.ev_run[i]);
+          cudaEventDestroy(c->pipe.ev_d2h[i]);
+        }
+      cudaStreamDestroy(c->pipe.h2d);
+      cudaStreamDestroy(c->pipe.d2h);
+    }
   delete c;
   DASM_API_END
 }
@@ -4619,6 +4645,95 @@ cheb_host(dasm_cheb *c, double *dst, const double *src, bool step)
       CUDA_CHECK(cudaMemcpyAsync(dst, d_stage, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
     }
   CUDA_CHECK(cudaStreamSynchronize(s));
+}
+
+// n independent problems (x_i, b_i) on one smoother: x_i <- step(x_i, b_i) (or x_i = vmult(b_i)).  The host -> device copies of problem
+// i + 1 and the device -> host copy of problem i - 1 run on their own streams next to the kernels of problem i (PCIe is full duplex),
+// so that a step costs max(copy in, copy out, kernels) instead of their sum.  Pinned host buffers are needed for the overlap.
+template <typename T>
+static void
+cheb_host_batch(dasm_cheb *c, const int n_steps, double *const *dst, const double *const *src, const bool step)
+{
+  dasm_op *       op = c->op;
+  cudaStream_t    s  = op->ctx->stream;
+  const long long n  = op->n_owned;
+  const bool      f64 = sizeof(T) == sizeof(double);
+  auto &          P   = c->pipe;
+  if (!P.ready)
+    {
+      CUDA_CHECK(cudaStreamCreateWithFlags(&P.h2d, cudaStreamNonBlocking));
+      CUDA_CHECK(cudaStreamCreateWithFlags(&P.d2h, cudaStreamNonBlocking));
+      for (int i = 0; i < 2; ++i)
+        {
+          CUDA_CHECK(cudaEventCreateWithFlags(&P.ev_h2d[i], cudaEventDisableTiming));
+          CUDA_CHECK(cudaEventCreateWithFlags(&P.ev_run[i], cudaEventDisableTiming));
+          CUDA_CHECK(cudaEventCreateWithFlags(&P.ev_d2h[i], cudaEventDisableTiming));
+          CUDA_CHECK(cudaMalloc(&P.x[i], std::max<size_t>(1, (size_t)op->n_vec) * sizeof(T)));
+          CUDA_CHECK(cudaMalloc(&P.b[i], std::max<size_t>(1, (size_t)op->n_vec) * sizeof(T)));
+          CUDA_CHECK(cudaMemset(P.x[i], 0, std::max<size_t>(1, (size_t)op->n_vec) * sizeof(T)));
+          CUDA_CHECK(cudaMemset(P.b[i], 0, std::max<size_t>(1, (size_t)op->n_vec) * sizeof(T)));
+          if (!f64)
+            {
+              CUDA_CHECK(cudaMalloc(&P.sx[i], std::max<size_t>(1, (size_t)n) * sizeof(double)));
+              CUDA_CHECK(cudaMalloc(&P.sb[i], std::max<size_t>(1, (size_t)n) * sizeof(double)));
+            }
+        }
+      P.ready = true;
+    }
+  CUDA_CHECK(cudaStreamSynchronize(s)); // (earlier work on the smoother's stream is finished before the copy streams start)
+  for (int i = 0; i < n_steps; ++i)
+    {
+      const int slot = i & 1;
+      T *       x = (T *)P.x[slot], *b = (T *)P.b[slot];
+      double *  hx = f64 ? (double *)x : P.sx[slot], *hb = f64 ? (double *)b : P.sb[slot];
+      if (i >= 2)
+        CUDA_CHECK(cudaStreamWaitEvent(P.h2d, P.ev_d2h[slot], 0)); // the slot's previous result has left the device
+      CUDA_CHECK(cudaMemcpyAsync(hb, src[i], (size_t)n * sizeof(double), cudaMemcpyHostToDevice, P.h2d));
+      if (step)
+        CUDA_CHECK(cudaMemcpyAsync(hx, dst[i], (size_t)n * sizeof(double), cudaMemcpyHostToDevice, P.h2d));
+      CUDA_CHECK(cudaEventRecord(P.ev_h2d[slot], P.h2d));
+      CUDA_CHECK(cudaStreamWaitEvent(s, P.ev_h2d[slot], 0));
+      if (!f64)
+        {
+          vec_convert_kernel<T, double><<<nblocks(n), 256, 0, s>>>(b, hb, n);
+          if (step)
+            vec_convert_kernel<T, double><<<nblocks(n), 256, 0, s>>>(x, hx, n);
+          op->ctx->launches += step ? 2 : 1;
+        }
+      cheb_run<T>(c, x, b, step);
+      if (!f64)
+        {
+          vec_convert_kernel<double, T><<<nblocks(n), 256, 0, s>>>(hx, x, n);
+          op->ctx->launches++;
+        }
+      CUDA_CHECK(cudaEventRecord(P.ev_run[slot], s));
+      CUDA_CHECK(cudaStreamWaitEvent(P.d2h, P.ev_run[slot], 0));
+      CUDA_CHECK(cudaMemcpyAsync(dst[i], hx, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, P.d2h));
+      CUDA_CHECK(cudaEventRecord(P.ev_d2h[slot], P.d2h));
+    }
+  CUDA_CHECK(cudaStreamSynchronize(P.d2h));
+  CUDA_CHECK(cudaStreamSynchronize(P.h2d));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+}
+
+extern "C" int
+dasm_cheb_step_host_batch(dasm_cheb *c, int n_steps, double *const *dst_owned, const double *const *src_owned)
+{
+  DASM_API_BEGIN
+  DASM_REQUIRE(n_steps >= 0 && (n_steps == 0 || (dst_owned != nullptr && src_owned != nullptr)), "step_host_batch: invalid arguments");
+  CUDA_CHECK(cudaSetDevice(c->op->ctx->device));
+  DISPATCH_TYPE(c->op->ntype, cheb_host_batch<T>(c, n_steps, dst_owned, src_owned, true));
+  DASM_API_END
+}
+
+extern "C" int
+dasm_cheb_vmult_host_batch(dasm_cheb *c, int n_steps, double *const *dst_owned, const double *const *src_owned)
+{
+  DASM_API_BEGIN
+  DASM_REQUIRE(n_steps >= 0 && (n_steps == 0 || (dst_owned != nullptr && src_owned != nullptr)), "vmult_host_batch: invalid arguments");
+  CUDA_CHECK(cudaSetDevice(c->op->ctx->device));
+  DISPATCH_TYPE(c->op->ntype, cheb_host_batch<T>(c, n_steps, dst_owned, src_owned, false));
+  DASM_API_END
 }
 
 extern "C" int

@@ -221,6 +221,12 @@ extern "C"
   /* the call the reference's user makes with host vectors: copies src (and dst for step) in, result out */
   int dasm_cheb_step_host(dasm_cheb *cheb, double *dst_owned, const double *src_owned);
   int dasm_cheb_vmult_host(dasm_cheb *cheb, double *dst_owned, const double *src_owned);
+  /* n independent problems on one smoother, pipelined: x_i <- step(x_i, b_i) with dst_owned[i] = x_i (in / out) and src_owned[i] = b_i.
+   * The host -> device copies of problem i + 1 and the device -> host copy of problem i - 1 overlap the kernels of problem i (two sets
+   * of device vectors, one copy stream per direction): a step costs max(copy in, copy out, kernels) instead of their sum.  The host
+   * buffers should be pinned (cudaHostAlloc / cudaHostRegister); distinct problems must not share buffers. */
+  int dasm_cheb_step_host_batch(dasm_cheb *cheb, int n, double *const *dst_owned, const double *const *src_owned);
+  int dasm_cheb_vmult_host_batch(dasm_cheb *cheb, int n, double *const *dst_owned, const double *const *src_owned);
 
   /* ---- Krylov solvers on the device: solve() of element_centered_preconditioners_01.cc:108-203 --------------------
    * solver: DASM_SOLVER_CG (SolverCG) or DASM_SOLVER_GMRES (SolverGMRES, right preconditioning, restart after `restart` vectors;

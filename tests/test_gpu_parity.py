@@ -522,3 +522,39 @@ def test_reduced_access_orientation(pkg, ctx):
         dy = torch.zeros(len(g), dtype=torch.float64, device=dev)
         pkg.reduced_access_distribute(degree, cidx, ori, dy, y)
         assert abs(float((rx * y).sum()) - float((x * dy).sum())) < 1e-10
+
+
+@pytest.mark.parametrize("k,number,n_cells", [(4, "double", (8, 8, 8)), (3, "float", (4, 4, 8)), (2, "double", (3, 4, 2))])
+def test_step_host_batch(pkg, ctx, k, number, n_cells):
+    """the pipelined host entry point (dasm_cheb_step_host_batch): five chained problems on two host buffer pairs give the
+    results of five blocking dasm_cheb_step_host calls on the same data"""
+    import torch
+    periodic = (1, 1, 1) if n_cells[0] % 4 == 0 else (0, 0, 0)
+    mesh = pkg.Mesh(ctx, n_cells, periodic=periodic, dirichlet=True)
+    op = pkg.LaplaceOperatorMatrixFree(mesh, k, number)
+    fdm = pkg.create_fdm_preconditioner(op, {"weighting type": "symm"})
+    cheb = pkg.PreconditionChebyshev(op, fdm, degree=3)
+    cheb.set_eigenvalues(0.9, 2.2)
+    rng = np.random.default_rng(1)
+    n = op.n_dofs()
+    x0 = [rng.uniform(-1, 1, n) for _ in range(2)]
+    b0 = [rng.uniform(-1, 1, n) for _ in range(2)]
+    for v in x0 + b0:
+        v[op.constrained_dofs()] = 0
+    # sequential: problem i uses pair i % 2, x updated in place
+    xs = [v.copy() for v in x0]
+    for i in range(5):
+        cheb.step_host(xs[i % 2], b0[i % 2])
+    hx = [torch.tensor(v).pin_memory() for v in x0]
+    hb = [torch.tensor(v).pin_memory() for v in b0]
+    cheb.step_host_batch([hx[i % 2].numpy() for i in range(5)], [hb[i % 2].numpy() for i in range(5)])
+    for i in range(2):
+        assert relerr(hx[i].numpy(), xs[i]) < (1e-13 if number == "double" else 1e-6)
+    # vmult variant
+    ys = [np.zeros(n), np.zeros(n)]
+    for i in range(2):
+        cheb.vmult_host(ys[i], b0[i])
+    hy = [torch.zeros(n, dtype=torch.float64).pin_memory() for _ in range(2)]
+    cheb.vmult_host_batch([hy[0].numpy(), hy[1].numpy()], [hb[0].numpy(), hb[1].numpy()])
+    for i in range(2):
+        assert relerr(hy[i].numpy(), ys[i]) < (1e-13 if number == "double" else 1e-6)
