@@ -132,6 +132,18 @@ namespace dasm
     };
   }
 
+  // Utilities::MPI::Partitioner as far as the hot path uses it (include/matrix_free.h:154-213, include/operator.h:780-849): the layout of
+  // a distributed vector.  libdasm gives the operator and every preconditioner built on it ONE layout that already contains the
+  // enlarged ghost set of overlapping patches, so the partitioner of a preconditioner is always the one of its operator.
+  struct Partitioner
+  {
+    const void *owner = nullptr; // the operator that defines the layout
+    long long   n_locally_owned = 0, n_ghost = 0, n_import = 0, vec_size = 0;
+    long long   locally_owned_size() const { return n_locally_owned; }
+    long long   n_ghost_indices() const { return n_ghost; }
+    long long   n_import_indices() const { return n_import; }
+  };
+
   // operator.h:32-60
   template <int dim, typename VectorType>
   class LaplaceOperatorBase
@@ -236,6 +248,25 @@ namespace dasm
       if (diagonal.data() == nullptr)
         diagonal.reinit(h);
       check(dasm_op_inverse_diagonal(h, diagonal.data()));
+    }
+    // get_partitioner / set_partitioner (operator.h:780-849): the reference re-targets the operator's vector access to the
+    // preconditioner's larger ghost layout; here both already share it, so set_partitioner only checks that the layout is this one
+    std::shared_ptr<const Partitioner>
+    get_partitioner() const
+    {
+      auto p             = std::make_shared<Partitioner>();
+      p->owner           = h;
+      p->n_locally_owned = dasm_op_n_dofs(h);
+      p->vec_size        = dasm_op_vec_size(h);
+      p->n_ghost         = p->vec_size - p->n_locally_owned;
+      p->n_import        = dasm_op_n_import(h);
+      return p;
+    }
+    void
+    set_partitioner(const std::shared_ptr<const Partitioner> &vector_partitioner) const
+    {
+      if (!vector_partitioner || vector_partitioner->owner != h)
+        throw std::runtime_error("ExcNotImplemented: the partitioner must be the one of a preconditioner built on this operator");
     }
     unsigned int get_fe_degree() const { return fe_degree; }
     Mesh &

@@ -55,7 +55,10 @@ namespace dasm
         throw std::runtime_error("weight sequence <" + weight_local_global + "> is not known!");
       check(dasm_fdm_create(op.handle(), (int)n_overlap, (int)sub_mesh_approximation, (int)weight_type, seq, overlap_pre_post ? 1 : 0,
                             element_centric ? 1 : 0, &h));
+      partitioner = op.get_partitioner();
     }
+    // matrix_free.h:994-999: the (enlarged) vector layout of the preconditioner = the operator's layout in libdasm
+    const std::shared_ptr<const Partitioner> &get_partitioner() const { return partitioner; }
     ~ASPoissonPreconditioner() override { dasm_fdm_destroy(h); }
 
     SymmetryType::SymmetryType
@@ -76,7 +79,8 @@ namespace dasm
     dasm_fdm *   handle() const { return h; }
 
   private:
-    dasm_fdm *h = nullptr;
+    dasm_fdm *                         h = nullptr;
+    std::shared_ptr<const Partitioner> partitioner;
   };
 
   template <int dim, typename Number>
