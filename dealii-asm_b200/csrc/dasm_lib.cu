@@ -416,6 +416,11 @@ struct dasm_op
   // unstructured hex mesh (csrc/unstructured.h; mesh == nullptr): 27 start indices + orientation word per cell, expanded to d_plain
   std::unique_ptr<UMesh> umesh;
   std::vector<uint32_t>  h_plain;
+  // DASM_DETERMINISTIC=1: bitwise reproducible results.  The cells are coloured so that no two cells of a colour share a DoF; the
+  // generic kernels run colour by colour, so every vector entry receives its contributions in a fixed order
+  bool                   deterministic = false;
+  std::vector<long long> color_ptr;               // cells of colour c: d_color_cells[color_ptr[c] .. color_ptr[c + 1])
+  uint32_t *             d_color_cells = nullptr;
   uint32_t *        d_constrained = nullptr;
   long long         n_constrained = 0;
   int               geom_mode     = 0; // 0 cartesian, 1 merged, 2 quadratic / linear coefficients (brick kernel)
@@ -491,6 +496,8 @@ struct dasm_fdm
   double    wtab[16] = {0};     // weight value per code
   uint4 *   d_brick_tri = nullptr; // per kernel brick: instance triple of the first cell + uniform flag
   uint32_t *d_pidx   = nullptr; // explicit patch index list for n_overlap > 1
+  std::vector<long long> color_ptr; // deterministic mode with explicit patch lists: colouring of the patches
+  uint32_t *d_color_cells = nullptr;
   int       wmode    = 0;       // kernel weight mode
   bool      w_pre = false, w_post = false;
   // warp-specialised kernel: bricks with the most frequent instance triple and weight pattern
@@ -716,42 +723,109 @@ apply_hook_post(dasm_op *op, T *dst, const T *src, const dasm_hook *post)
 // ------------------------------------------------------------------------------------------------
 // operator application
 // ------------------------------------------------------------------------------------------------
+static bool
+deterministic_env()
+{
+  const char *e = getenv("DASM_DETERMINISTIC");
+  return e != nullptr && e[0] == '1';
+}
+
+// greedy colouring of the cells by shared vector entries: idx[cell][per_cell] (invalid entries skipped); cells of one colour touch
+// disjoint entries.  ptr / cells: the cells grouped by colour.
+static void
+greedy_coloring(const uint32_t *idx, const long long n_cells, const int per_cell, const long long n_vec, std::vector<long long> &ptr,
+                std::vector<uint32_t> &cells)
+{
+  std::vector<uint64_t> used((size_t)std::max<long long>(n_vec, 1), 0);
+  std::vector<uint8_t>  color((size_t)n_cells);
+  int                   n_colors = 0;
+  for (long long c = 0; c < n_cells; ++c)
+    {
+      uint64_t m = 0;
+      for (int i = 0; i < per_cell; ++i)
+        {
+          const uint32_t g = idx[c * per_cell + i];
+          if (g != INVALID_INDEX)
+            m |= used[g & ~LEX_FLAG];
+        }
+      int col = 0;
+      while (col < 64 && ((m >> col) & 1))
+        ++col;
+      if (col >= 64)
+        throw std::runtime_error("deterministic mode: more than 64 colours needed");
+      color[c] = (uint8_t)col;
+      n_colors = std::max(n_colors, col + 1);
+      for (int i = 0; i < per_cell; ++i)
+        {
+          const uint32_t g = idx[c * per_cell + i];
+          if (g != INVALID_INDEX)
+            used[g & ~LEX_FLAG] |= (uint64_t)1 << col;
+        }
+    }
+  ptr.assign(n_colors + 1, 0);
+  for (long long c = 0; c < n_cells; ++c)
+    ptr[color[c] + 1]++;
+  for (int i = 0; i < n_colors; ++i)
+    ptr[i + 1] += ptr[i];
+  cells.resize((size_t)n_cells);
+  std::vector<long long> fill(ptr.begin(), ptr.end() - 1);
+  for (long long c = 0; c < n_cells; ++c)
+    cells[fill[color[c]]++] = (uint32_t)c;
+}
+
+static void
+setup_deterministic(dasm_op *op)
+{
+  op->deterministic = true;
+  std::vector<uint32_t> cells;
+  greedy_coloring(op->nb.cidx.data(), op->n_cells, 27, op->n_vec, op->color_ptr, cells);
+  op->d_color_cells = dev_upload(cells, op->ctx->stream);
+}
+
 template <typename T>
 static void
 launch_laplace(dasm_op *op, T *dst, const T *src)
 {
   dasm_ctx *ctx = op->ctx;
   KernelTimer timer(ctx, KC_LAPLACE);
-  DISPATCH_DEGREE(op->k, {
-    constexpr int n = K + 1, CPB = cells_per_block<K>();
-    const size_t  smem = (size_t)CPB * 4 * n * n * n * sizeof(T);
-    const unsigned grid = (unsigned)((op->n_cells + CPB - 1) / CPB);
-    if (op->geom_mode == 0)
-      {
-        auto kern = laplace_generic_kernel<K, T, 0>;
-        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, CPB * n * n, smem, ctx->stream>>>(src, dst, op->d_cidx, (const T *)nullptr, op->cart, op->n_cells, op->d_plain, nullptr);
-      }
-    else if (op->geom_mode == 3)
-      {
-        auto kern = laplace_generic_kernel<K, T, 2>;
-        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, CPB * n * n, smem, ctx->stream>>>(src, dst, op->d_cidx, (const T *)op->d_geom, op->cart, op->n_cells, op->d_plain, nullptr);
-      }
-    else if (op->geom_mode == 5)
-      {
-        auto kern = laplace_generic_kernel<K, T, 3>;
-        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, CPB * n * n, smem, ctx->stream>>>(src, dst, op->d_cidx, (const T *)op->d_geom, op->cart, op->n_cells, op->d_plain, nullptr);
-      }
-    else
-      {
-        auto kern = laplace_generic_kernel<K, T, 1>;
-        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, CPB * n * n, smem, ctx->stream>>>(src, dst, op->d_cidx, (const T *)op->d_geom, op->cart, op->n_cells, op->d_plain, nullptr);
-      }
-  });
-  ctx->launches++;
+  const int n_pass = op->deterministic ? (int)op->color_ptr.size() - 1 : 1;
+  for (int pass = 0; pass < n_pass; ++pass)
+    {
+      const long long count = op->deterministic ? op->color_ptr[pass + 1] - op->color_ptr[pass] : op->n_cells;
+      const uint32_t *ids   = op->deterministic ? op->d_color_cells + op->color_ptr[pass] : nullptr;
+      if (count == 0)
+        continue;
+      DISPATCH_DEGREE(op->k, {
+        constexpr int n = K + 1, CPB = cells_per_block<K>();
+        const size_t  smem = (size_t)CPB * 4 * n * n * n * sizeof(T);
+        const unsigned grid = (unsigned)((count + CPB - 1) / CPB);
+        if (op->geom_mode == 0)
+          {
+            auto kern = laplace_generic_kernel<K, T, 0>;
+            CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<grid, CPB * n * n, smem, ctx->stream>>>(src, dst, op->d_cidx, (const T *)nullptr, op->cart, count, op->d_plain, ids);
+          }
+        else if (op->geom_mode == 3)
+          {
+            auto kern = laplace_generic_kernel<K, T, 2>;
+            CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<grid, CPB * n * n, smem, ctx->stream>>>(src, dst, op->d_cidx, (const T *)op->d_geom, op->cart, count, op->d_plain, ids);
+          }
+        else if (op->geom_mode == 5)
+          {
+            auto kern = laplace_generic_kernel<K, T, 3>;
+            CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<grid, CPB * n * n, smem, ctx->stream>>>(src, dst, op->d_cidx, (const T *)op->d_geom, op->cart, count, op->d_plain, ids);
+          }
+        else
+          {
+            auto kern = laplace_generic_kernel<K, T, 1>;
+            CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<grid, CPB * n * n, smem, ctx->stream>>>(src, dst, op->d_cidx, (const T *)op->d_geom, op->cart, count, op->d_plain, ids);
+          }
+      });
+      ctx->launches++;
+    }
   CUDA_CHECK(cudaGetLastError());
 }
 
@@ -1311,33 +1385,44 @@ launch_fdm_m(dasm_fdm *f, T *dst, const T *src)
   KernelTimer    timer(ctx, KC_FDM);
   constexpr int  CPB  = fdm_cells_per_block<M>();
   const size_t   smem = (size_t)CPB * (M * M * M + 3 * M * M + 3 * M) * sizeof(T);
-  const unsigned grid = (unsigned)((op->n_cells + CPB - 1) / CPB);
   const void *   w    = (f->wmode == 3) ? f->d_wvec : f->d_cw;
-  if (f->d_pidx == nullptr)
+  // deterministic mode: colour by colour (patches with explicit lists have their own colouring)
+  const std::vector<long long> &cptr = f->d_color_cells ? f->color_ptr : op->color_ptr;
+  const uint32_t *              call = f->d_color_cells ? f->d_color_cells : op->d_color_cells;
+  const int                     n_pass = op->deterministic ? (int)cptr.size() - 1 : 1;
+  for (int pass = 0; pass < n_pass; ++pass)
     {
-      if (M - 1 != op->k)
-        throw std::runtime_error("internal: compressed FDM patch needs m == k+1");
-      if constexpr (M <= 9)
+      const long long count = op->deterministic ? cptr[pass + 1] - cptr[pass] : op->n_cells;
+      const uint32_t *ids   = op->deterministic ? call + cptr[pass] : nullptr;
+      if (count == 0)
+        continue;
+      const unsigned grid = (unsigned)((count + CPB - 1) / CPB);
+      if (f->d_pidx == nullptr)
         {
-          auto kern = fdm_generic_kernel<M, T, 0>;
-          CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          kern<<<grid, CPB * M * M, smem, ctx->stream>>>(src, dst, op->d_cidx, f->d_inst, (const T *)f->d_S, (const T *)f->d_lam,
-                                                         (const T *)w, f->wmode, (int)f->w_pre, (int)f->w_post, op->n_cells);
-        }
-    }
-  else
-    {
-      if constexpr (M >= 3)
-        {
-          auto kern = fdm_generic_kernel<M, T, 1>;
-          CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          kern<<<grid, CPB * M * M, smem, ctx->stream>>>(src, dst, f->d_pidx, f->d_inst, (const T *)f->d_S, (const T *)f->d_lam,
-                                                         (const T *)w, f->wmode, (int)f->w_pre, (int)f->w_post, op->n_cells);
+          if (M - 1 != op->k)
+            throw std::runtime_error("internal: compressed FDM patch needs m == k+1");
+          if constexpr (M <= 9)
+            {
+              auto kern = fdm_generic_kernel<M, T, 0>;
+              CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+              kern<<<grid, CPB * M * M, smem, ctx->stream>>>(src, dst, op->d_cidx, f->d_inst, (const T *)f->d_S, (const T *)f->d_lam,
+                                                             (const T *)w, f->wmode, (int)f->w_pre, (int)f->w_post, count, ids);
+            }
         }
       else
-        throw std::runtime_error("explicit patch lists are instantiated for patch sizes >= 3");
+        {
+          if constexpr (M >= 3)
+            {
+              auto kern = fdm_generic_kernel<M, T, 1>;
+              CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+              kern<<<grid, CPB * M * M, smem, ctx->stream>>>(src, dst, f->d_pidx, f->d_inst, (const T *)f->d_S, (const T *)f->d_lam,
+                                                             (const T *)w, f->wmode, (int)f->w_pre, (int)f->w_post, count, ids);
+            }
+          else
+            throw std::runtime_error("explicit patch lists are instantiated for patch sizes >= 3");
+        }
+      ctx->launches++;
     }
-  ctx->launches++;
   CUDA_CHECK(cudaGetLastError());
 }
 
@@ -2191,7 +2276,7 @@ dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping
     // (degree 5 runs faster through the generic kernels: 1.70e10 vs 1.24e10 DoFs/s per Chebyshev term, profiles/r01c_secondary.log;
     // DASM_BRICK_K5=1 selects the 4x4x2 brick kernels)
     const char *k5    = getenv("DASM_BRICK_K5");
-    op->use_brick     = (degree <= 4 || (degree == 5 && k5 && k5[0] == '1')) && !(force && force[0] == '1') && op->geom_mode != 3 &&
+    op->use_brick     = (degree <= 4 || (degree == 5 && k5 && k5[0] == '1')) && !((force && force[0] == '1') || deterministic_env()) && op->geom_mode != 3 &&
                     op->compress_indices;
     if (!op->compress_indices)
       {
@@ -2203,7 +2288,7 @@ dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping
         ctx->launches++;
       }
     const char *nofast_hi = getenv("DASM_NO_FAST");
-    if (!op->use_brick && op->compress_indices && (degree == 5 || degree == 6) && !(force && force[0] == '1') && !(nofast_hi && nofast_hi[0] == '1'))
+    if (!op->use_brick && op->compress_indices && (degree == 5 || degree == 6) && !((force && force[0] == '1') || deterministic_env()) && !(nofast_hi && nofast_hi[0] == '1'))
       setup_tma_only(op);
     if (op->use_brick && !op->tma_only)
       {
@@ -2697,6 +2782,8 @@ dasm_op_create(dasm_mesh *mesh, int degree, int number_type, const char *mapping
         op->max_smem = (int)prop.sharedMemPerBlockOptin;
       }
   }
+  if (deterministic_env())
+    setup_deterministic(op);
   *out = op;
   DASM_API_END
 }
@@ -2784,6 +2871,8 @@ dasm_op_create_unstructured(dasm_ctx *ctx, int degree, int number_type, const ch
     }
   op->use_brick = false;
   op->umesh     = std::move(U);
+  if (deterministic_env())
+    setup_deterministic(op);
   *out          = op;
   DASM_API_END
 }
@@ -2908,6 +2997,7 @@ dasm_op_destroy(dasm_op *op)
   cudaFree(op->d_acc);
   cudaFree(op->d_shared_list);
   cudaFree(op->d_plain);
+  cudaFree(op->d_color_cells);
   cudaFree(op->d_fast_ids);
   cudaFree(op->d_slow_ids);
   cudaFree(op->d_tma_lap);
@@ -3652,6 +3742,13 @@ dasm_fdm_create(dasm_op *op, int n_overlap, int sub_mesh_approximation, int weig
                 }
         }
       f->d_pidx = dev_upload(pidx, op->ctx->stream);
+      if (op->deterministic)
+        {
+          // overlapping patches reach beyond the cell: they get their own colouring
+          std::vector<uint32_t> cells;
+          greedy_coloring(pidx.data(), op->n_cells, m * m * m, op->n_vec, f->color_ptr, cells);
+          f->d_color_cells = dev_upload(cells, op->ctx->stream);
+        }
     }
 
   if (f->d_pidx == nullptr && op->d_plain != nullptr && f->m >= 3) // (the kernels with explicit lists start at patch size 3)
@@ -3999,6 +4096,7 @@ dasm_fdm_destroy(dasm_fdm *f)
   cudaFree(f->d_tma_list);
   cudaFree(f->d_tma_chunks);
   cudaFree(f->d_pidx);
+  cudaFree(f->d_color_cells);
   delete f;
   DASM_API_END
 }

@@ -558,7 +558,8 @@ namespace dasm
                      const int       WMODE,
                      const int       w_pre,
                      const int       w_post,
-                     const long long n_cells)
+                     const long long n_cells,
+                     const uint32_t *__restrict__ cell_ids = nullptr) // work on the cells cell_ids[0 .. n_cells) (coloured launches)
   {
     constexpr int m2 = m * m, m3 = m2 * m, CPB = fdm_cells_per_block<m>(), k = m - 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -568,8 +569,9 @@ namespace dasm
     const int       t    = threadIdx.x % m2;
     const int       a    = t % m;
     const int       b    = t / m;
-    const long long cell = (long long)blockIdx.x * CPB + cl;
-    const bool      act  = cell < n_cells;
+    const long long slot = (long long)blockIdx.x * CPB + cl;
+    const bool      act  = slot < n_cells;
+    const long long cell = (act && cell_ids != nullptr) ? (long long)cell_ids[slot] : slot;
 
     T *U  = smem + (size_t)cl * (m3 + 3 * m2 + 3 * m);
     T *S0 = U + m3;

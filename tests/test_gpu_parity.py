@@ -558,3 +558,69 @@ def test_step_host_batch(pkg, ctx, k, number, n_cells):
     cheb.vmult_host_batch([hy[0].numpy(), hy[1].numpy()], [hb[0].numpy(), hb[1].numpy()])
     for i in range(2):
         assert relerr(hy[i].numpy(), ys[i]) < (1e-13 if number == "double" else 1e-6)
+
+
+def test_deterministic_mode(pkg, ctx, monkeypatch):
+    """DASM_DETERMINISTIC=1: the cells are coloured so that no two cells of a colour share a vector entry and the generic kernels run
+    colour by colour: repeated applications are bitwise identical (the default kernels add shared-face contributions with red.add in
+    varying order, reproducible to 1e-15 only) and agree with the oracle and with the default path."""
+    import importlib
+    k = 4
+    rng = np.random.default_rng(5)
+
+    def run(op, fdm, cheb, x, b):
+        xd, bd, yd = op.to_device(x), op.to_device(b), op.initialize_dof_vector()
+        op.vmult(yd, xd)
+        y = op.to_host(yd).copy()
+        fdm.vmult(yd, bd)
+        z = op.to_host(yd).copy()
+        cheb.step(xd, bd)
+        return y, z, op.to_host(xd).copy()
+
+    def build(number="double", n_overlap=1):
+        mesh = pkg.Mesh(ctx, (8, 8, 8), periodic=(1, 1, 1))
+        op = pkg.LaplaceOperatorMatrixFree(mesh, k, number)
+        fdm = pkg.create_fdm_preconditioner(op, {"weighting type": "symm", "n overlap": n_overlap})
+        cheb = pkg.PreconditionChebyshev(op, fdm, degree=3)
+        cheb.set_eigenvalues(0.9, 2.2)
+        return mesh, op, fdm, cheb
+
+    mesh0, op0, fdm0, cheb0 = build()                       # default path (TMA-fed kernels)
+    assert op0.n_fast_bricks() > 0
+    x, b = rng.uniform(-1, 1, op0.n_dofs()), rng.uniform(-1, 1, op0.n_dofs())
+    ref = run(op0, fdm0, cheb0, x, b)
+    monkeypatch.setenv("DASM_DETERMINISTIC", "1")
+    mesh1, op1, fdm1, cheb1 = build()
+    assert op1.n_fast_bricks() == 0
+    first = run(op1, fdm1, cheb1, x, b)
+    for _ in range(3):
+        again = run(op1, fdm1, cheb1, x, b)
+        for u, v in zip(first, again):
+            assert np.array_equal(u, v)                      # bitwise
+    for u, v in zip(first, ref):
+        assert relerr(u, v) < 1e-13
+    oop, oP = oracle_problem(pkg, mesh1, op1, 1, "symm")
+    assert relerr(first[0], oop.vmult(x)) < 1e-12 and relerr(first[1], oP.vmult(b)) < 1e-12
+    # overlapping patches (own colouring of the patches) and an unstructured mesh
+    mesh2, op2, fdm2, cheb2 = build(n_overlap=2)
+    a1, a2 = run(op2, fdm2, cheb2, x, b), run(op2, fdm2, cheb2, x, b)
+    assert all(np.array_equal(u, v) for u, v in zip(a1, a2))
+    _, oP2 = oracle_problem(pkg, mesh2, op2, 2, "symm")
+    assert relerr(a1[1], oP2.vmult(b)) < 1e-12
+    grid = importlib.import_module("dealii-asm_b200.grid")
+    g = grid.hyper_ball(1)
+    opb = pkg.LaplaceOperatorMatrixFree.from_arrays(ctx, g["vertices"], g["cells"], 3, g["support"])
+    fdmb = pkg.create_fdm_preconditioner(opb, {"weighting type": "symm"})
+    chebb = pkg.PreconditionChebyshev(opb, fdmb, degree=3)
+    chebb.set_eigenvalues(0.9, 2.2)
+    xb, bb = rng.uniform(-1, 1, opb.n_dofs()), rng.uniform(-1, 1, opb.n_dofs())
+    b1, b2 = run(opb, fdmb, chebb, xb, bb), run(opb, fdmb, chebb, xb, bb)
+    assert all(np.array_equal(u, v) for u, v in zip(b1, b2))
+    # Krylov solve: identical iteration count and bitwise identical solution in repeated runs
+    rhs = op1.to_device(b - b.mean())                        # (periodic mesh: the right-hand side must be orthogonal to the constants)
+    sols = []
+    for _ in range(2):
+        sol = op1.initialize_dof_vector()
+        its, res = pkg.solve(op1, sol, rhs, cheb1, {"type": "GMRES", "rel tolerance": 1e-6})
+        sols.append((its, res, op1.to_host(sol).copy()))
+    assert sols[0][0] == sols[1][0] and sols[0][1] == sols[1][1] and np.array_equal(sols[0][2], sols[1][2])
