@@ -135,23 +135,85 @@ namespace dasm
       }
   }
 
-  // same with a runtime matrix in shared memory (row-major M[o*m+i])
-  template <int n, typename T, int DIR, bool TRANS>
+  // row of a runtime matrix in shared memory into registers; rows of a multiple of 16 bytes (the matrices of the FDM kernel then
+  // start on 16-byte boundaries, see fdm_rows_aligned) are read with 128-bit loads: the matrix reads are what occupies the LSU pipe
+  template <int m, typename T, bool VEC>
+  __device__ __forceinline__ void
+  load_row(const T *__restrict__ row, T (&out)[m])
+  {
+    if constexpr (VEC && sizeof(T) == 8)
+      {
+#pragma unroll
+        for (int j = 0; j < m / 2; ++j)
+          {
+            const double2 q = reinterpret_cast<const double2 *>(row)[j];
+            out[2 * j]      = q.x;
+            out[2 * j + 1]  = q.y;
+          }
+      }
+    else if constexpr (VEC && sizeof(T) == 4)
+      {
+#pragma unroll
+        for (int j = 0; j < m / 4; ++j)
+          {
+            const float4 q = reinterpret_cast<const float4 *>(row)[j];
+            out[4 * j]     = q.x;
+            out[4 * j + 1] = q.y;
+            out[4 * j + 2] = q.z;
+            out[4 * j + 3] = q.w;
+          }
+      }
+    else
+      {
+#pragma unroll
+        for (int i = 0; i < m; ++i)
+          out[i] = row[i];
+      }
+  }
+
+  // per-cell shared-memory block of the FDM kernel: U[m^3] S0 S1 S2 [m^2 each] L0 L1 L2 [m each]; rows and blocks 16-byte aligned?
+  template <int m, typename T>
+  __host__ __device__ constexpr bool
+  fdm_rows_aligned()
+  {
+    return (m * sizeof(T)) % 16 == 0 && ((m * m * m + 3 * m * m + 3 * m) * sizeof(T)) % 16 == 0;
+  }
+
+  // same with a runtime matrix in shared memory (row-major M[o*m+i]); the sums run over i in ascending order in both variants
+  template <int n, typename T, int DIR, bool TRANS, bool VEC = false>
   __device__ __forceinline__ void
   sweep_smem(const T *__restrict__ M, T *buf, int a, int b)
   {
-    T v[n], r[n];
+    T v[n], r[n], row[n];
 #pragma unroll
     for (int i = 0; i < n; ++i)
       v[i] = buf[line_idx<n, DIR>(a, b, i)];
-#pragma unroll
-    for (int o = 0; o < n; ++o)
+    if (TRANS)
       {
-        T s = 0;
+#pragma unroll
+        for (int o = 0; o < n; ++o)
+          r[o] = 0;
 #pragma unroll
         for (int i = 0; i < n; ++i)
-          s += (TRANS ? M[i * n + o] : M[o * n + i]) * v[i];
-        r[o] = s;
+          {
+            load_row<n, T, VEC>(M + i * n, row);
+#pragma unroll
+            for (int o = 0; o < n; ++o)
+              r[o] += row[o] * v[i];
+          }
+      }
+    else
+      {
+#pragma unroll
+        for (int o = 0; o < n; ++o)
+          {
+            load_row<n, T, VEC>(M + o * n, row);
+            T s = 0;
+#pragma unroll
+            for (int i = 0; i < n; ++i)
+              s += row[i] * v[i];
+            r[o] = s;
+          }
       }
 #pragma unroll
     for (int o = 0; o < n; ++o)
@@ -561,7 +623,8 @@ namespace dasm
                      const long long n_cells,
                      const uint32_t *__restrict__ cell_ids = nullptr) // work on the cells cell_ids[0 .. n_cells) (coloured launches)
   {
-    constexpr int m2 = m * m, m3 = m2 * m, CPB = fdm_cells_per_block<m>(), k = m - 1;
+    constexpr int  m2 = m * m, m3 = m2 * m, CPB = fdm_cells_per_block<m>(), k = m - 1;
+    constexpr bool VEC = fdm_rows_aligned<m, T>();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *smem = reinterpret_cast<T *>(smem_raw);
 
@@ -636,43 +699,49 @@ namespace dasm
       }
     __syncthreads();
     if (act)
-      sweep_smem<m, T, 0, true>(S0, U, a, b);
+      sweep_smem<m, T, 0, true, VEC>(S0, U, a, b);
     __syncthreads();
     if (act)
-      sweep_smem<m, T, 1, true>(S1, U, a, b);
+      sweep_smem<m, T, 1, true, VEC>(S1, U, a, b);
     __syncthreads();
     if (act)
       {
         // z sweep (transposed), scaling and forward z sweep on the same line (x=a, y=b)
-        T v[m], r[m];
+        T v[m], r[m], row[m];
 #pragma unroll
         for (int i = 0; i < m; ++i)
           v[i] = U[(i * m + b) * m + a];
 #pragma unroll
         for (int o = 0; o < m; ++o)
-          {
-            T s = 0;
+          r[o] = 0;
 #pragma unroll
-            for (int i = 0; i < m; ++i)
-              s += S2[i * m + o] * v[i];
-            r[o] = s / (L0[a] + L1[b] + L2[o]);
+        for (int i = 0; i < m; ++i)
+          {
+            load_row<m, T, VEC>(S2 + i * m, row);
+#pragma unroll
+            for (int o = 0; o < m; ++o)
+              r[o] += row[o] * v[i];
           }
 #pragma unroll
         for (int o = 0; o < m; ++o)
+          r[o] = r[o] / (L0[a] + L1[b] + L2[o]);
+#pragma unroll
+        for (int o = 0; o < m; ++o)
           {
+            load_row<m, T, VEC>(S2 + o * m, row);
             T s = 0;
 #pragma unroll
             for (int i = 0; i < m; ++i)
-              s += S2[o * m + i] * r[i];
+              s += row[i] * r[i];
             U[(o * m + b) * m + a] = s;
           }
       }
     __syncthreads();
     if (act)
-      sweep_smem<m, T, 1, false>(S1, U, a, b);
+      sweep_smem<m, T, 1, false, VEC>(S1, U, a, b);
     __syncthreads();
     if (act)
-      sweep_smem<m, T, 0, false>(S0, U, a, b);
+      sweep_smem<m, T, 0, false, VEC>(S0, U, a, b);
     // the x sweep wrote the line (y=a,z=b) that the same thread scatters: no sync needed
     if (act)
       {

@@ -85,10 +85,13 @@ def main():
                     sol = op.initialize_dof_vector()
                     solver = "CG" if wt == "symm" else "GMRES"
                     ctx.sync()
-                    t0 = time.perf_counter()
-                    its, res = pkg.solve(op, sol, rhs, cheb, {"type": solver, "rel tolerance": 1e-8})
-                    ctx.sync()
-                    row.update(solver=solver, iterations=its, solve_s=time.perf_counter() - t0, residual=res, max_u=float(op.to_host(sol).max()),
+                    times = []
+                    for _ in range(2):
+                        t0 = time.perf_counter()
+                        its, res = pkg.solve(op, sol, rhs, cheb, {"type": solver, "rel tolerance": 1e-8})
+                        ctx.sync()
+                        times.append(time.perf_counter() - t0)
+                    row.update(solver=solver, iterations=its, solve_s=min(times), residual=res, max_u=float(op.to_host(sol).max()),
                                max_u_exact=1.0 / 6.0)
                 del cheb
             out.write(json.dumps(row) + "\n")
@@ -129,14 +132,17 @@ def main():
         t_setup = time.perf_counter() - t0
         pkg.solve(op, sol, rhs, mg, {"type": solver, "rel tolerance": 1e-8})   # warm-up
         ctx.sync()
-        t0 = time.perf_counter()
-        its, res = pkg.solve(op, sol, rhs, mg, {"type": solver, "rel tolerance": 1e-8})
-        ctx.sync()
-        t_solve = time.perf_counter() - t0
+        times = []
+        for _ in range(3):   # (the solver allocates its Krylov vectors per call: the wall time varies, the minimum is reported)
+            t0 = time.perf_counter()
+            its, res = pkg.solve(op, sol, rhs, mg, {"type": solver, "rel tolerance": 1e-8})
+            ctx.sync()
+            times.append(time.perf_counter() - t0)
+        t_solve = min(times)
         x = op.to_host(sol)
         out.write(json.dumps({"mesh": "hyper_ball", "n_refinements": L, "degree": k, "n_cells": int(op.n_cells()), "n_dofs": int(op.n_dofs()),
                               "variant": "%s + hp-multigrid, Chebyshev(3) + FDM %s smoothers" % (solver, wt), "mapping_type": mapping_type or "merged", "levels": spec, "iterations": its,
-                              "time_to_solution_s": t_solve, "setup_s": t_setup, "residual": res, "rel_tolerance": 1e-8,
+                              "time_to_solution_s": t_solve, "time_to_solution_all_s": times, "setup_s": t_setup, "residual": res, "rel_tolerance": 1e-8,
                               "max_u": float(x.max()), "max_u_exact": 1.0 / 6.0}) + "\n")
         out.flush()
         del mg, trs, sms, keep, ops, op
