@@ -435,6 +435,7 @@ struct dasm_op
   Exchange          exchange_ext; // all ghosts (those of `exchange` + the DoFs of the halo cells)
   long long         n_ghost_ext = 0;
   std::vector<void *> scratch; // owned by op, freed at destroy
+  std::vector<void *> krylov_pool; // work vectors of dasm_solve, kept between solves (entries are also listed in scratch)
   // tuned brick path
   bool              use_brick = false;
   bool              tma_only  = false; // degrees 5 and 6: every brick is a lex brick and runs the TMA-fed kernels (no brick kernels)
@@ -4898,11 +4899,18 @@ krylov_solve(dasm_op *op, const int solver, const int pkind, void *ph, T *x, con
   cudaStream_t    s   = ctx->stream;
   const long long n   = op->n_owned;
   const size_t    nv  = (size_t)op->n_vec;
-  std::vector<T *> owned;
-  auto             alloc = [&]() {
-    T *p = dev_alloc<T>(nv);
+  // work vectors come from a pool kept by the operator: a solve after the first one allocates nothing (cudaMalloc / cudaFree of
+  // up to 35 vectors per call cost more than the iterations of a multigrid-preconditioned solve)
+  size_t pool_used = 0;
+  auto   alloc     = [&]() {
+    if (pool_used == op->krylov_pool.size())
+      {
+        T *q = dev_alloc<T>(nv);
+        op->krylov_pool.push_back(q);
+        op->scratch.push_back(q);
+      }
+    T *p = (T *)op->krylov_pool[pool_used++];
     CUDA_CHECK(cudaMemsetAsync(p, 0, nv * sizeof(T), s));
-    owned.push_back(p);
     return p;
   };
   T *inv_diag = nullptr;
@@ -5025,8 +5033,6 @@ krylov_solve(dasm_op *op, const int solver, const int pkind, void *ph, T *x, con
         }
     }
   CUDA_CHECK(cudaStreamSynchronize(s));
-  for (T *p : owned)
-    cudaFree(p);
   if (n_it)
     *n_it = its;
   if (residual)

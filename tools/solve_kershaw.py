@@ -29,7 +29,7 @@ def main():
     results = []
     for solver, wt, cheb_degree in (("CG", "symm", 3), ("GMRES", "post", 3), ("CG", "symm", 2), ("CG", "symm", 5)):
         t0 = time.perf_counter()
-        levels, smoothers, ev = [], [], []
+        levels, smoothers, ev, keepalive = [], [], [], []
         for r in range(n_ref + 1):
             c = 6 * 2 ** r
             mesh = pkg.Mesh(ctx, (c, c, c), periodic=(0, 0, 0), dirichlet=True, map_kind="kershaw", map_params=(0.3, 0.3, 0, 0))
@@ -39,8 +39,8 @@ def main():
             ev.append(ch.estimate_eigenvalues())
             levels.append(op)
             smoothers.append(ch)
-            keep = (mesh, fdm)
-            levels[-1]._keep = keep
+            keepalive.append((mesh, fdm))  # (not stored on the operator: operator -> fdm -> operator would be a reference cycle, whose
+            # members the garbage collector finalises in arbitrary order - the FDM object must be destroyed before its operator)
         mesh = levels[-1].mesh
         op = pkg.LaplaceOperatorMatrixFree(mesh, k, "double", mapping_type="quadratic geometry")
         mg = pkg.PreconditionerGMG(levels, smoothers, outer_op=op)
