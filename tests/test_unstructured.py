@@ -367,3 +367,18 @@ def test_ball_is_watertight(L):
     assert len(h["constrained"]) == F + 2                      # Euler: V = F + 2 on the sphere
     assert h["n_quads"] == (6 * len(g["cells"]) + F) // 2
     assert np.allclose(np.linalg.norm(g["vertices"][h["constrained"]], axis=1), 1.0, atol=1e-12)
+
+
+def test_natural_boundary_numbering():
+    """dirichlet = False: no constrained entries, every start index valid; the oracle agrees"""
+    pkg = load_package()
+    g = grid.hyper_ball(0)
+    h = pkg.umesh_host_numbering(2, g["vertices"], g["cells"], g["support"], dirichlet=False)
+    assert len(h["constrained"]) == 0 and not np.any(h["cidx"] == 0xFFFFFFFF) and not np.any(h["plain"] == 0xFFFFFFFF)
+    m = o.UnstructuredMesh(g["vertices"], g["cells"], g["support"], dirichlet=False)
+    cd, nd, con, comp, _ = m.number_dofs(2)
+    assert nd == h["n_dofs"] and not con.any() and np.array_equal(comp, h["cidx"]) and np.array_equal(cd.astype(np.uint32), h["plain"])
+    # every DoF is addressed by at least one cell, vertex DoFs by as many cells as the vertex has
+    counts = np.bincount(h["plain"].reshape(-1).astype(np.int64), minlength=nd)
+    assert counts.min() >= 1
+    assert np.array_equal(counts[: len(g["vertices"])], np.bincount(g["cells"].reshape(-1).astype(np.int64), minlength=len(g["vertices"])))
